@@ -1,0 +1,123 @@
+"""Deterministic synthetic satellite-ray batches (SURVEY.md §8d "Synthetic inputs").
+
+The ray record is the reference's `(N, 11)` fp32 row `[o(3), d(3), near, far, sun_d(3)]`
+(reference `datasets/satellite_rgb_dep.py:311-322,390,550-559`), normalised scene in [-1, 1]^3.
+Everything is generated on the CPU with an explicit `torch.Generator` so that the GPU run, the
+CPU oracle and the golden fixtures all see identical bits.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+RAY_SEED = 20240912
+
+_OFF_NADIR_DEG = (5.0, 15.0, 25.0)
+_VIEW_AZ_DEG = (30.0, 150.0, 270.0)
+_SUN_EL_DEG = (60.0, 50.0, 40.0)
+_SUN_AZ_DEG = (140.0, 150.0, 160.0)
+_SLAB_TOP = 0.3
+_SLAB_THICKNESS = 0.6
+
+
+@dataclass
+class RayBatch:
+    rays: torch.Tensor                 # (N, 11) fp32
+    rgbs: torch.Tensor                 # (N, 3)  fp32 targets
+    valid_depth: Optional[torch.Tensor] = None     # (N,) int64
+    target_depths: Optional[torch.Tensor] = None   # (N, 2) [depth, correlation weight]
+    target_std: Optional[torch.Tensor] = None      # (N,)
+
+    def to(self, device, non_blocking=False):
+        mv = lambda t: None if t is None else t.to(device, non_blocking=non_blocking)
+        return RayBatch(mv(self.rays), mv(self.rgbs), mv(self.valid_depth),
+                        mv(self.target_depths), mv(self.target_std))
+
+    def pin(self):
+        pn = lambda t: None if t is None else t.pin_memory()
+        return RayBatch(pn(self.rays), pn(self.rgbs), pn(self.valid_depth),
+                        pn(self.target_depths), pn(self.target_std))
+
+    def nbytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in
+                   (self.rays, self.rgbs, self.valid_depth, self.target_depths, self.target_std)
+                   if t is not None)
+
+    def shard(self, rank: int, world: int) -> "RayBatch":
+        """Contiguous ray shard of rank `rank`."""
+        n = self.rays.shape[0]
+        per = n // world
+        sl = slice(rank * per, (rank + 1) * per)
+        cut = lambda t: None if t is None else t[sl].contiguous()
+        return RayBatch(cut(self.rays), cut(self.rgbs), cut(self.valid_depth),
+                        cut(self.target_depths), cut(self.target_std))
+
+
+def _view_and_sun(v: int):
+    th, az = math.radians(_OFF_NADIR_DEG[v]), math.radians(_VIEW_AZ_DEG[v])
+    d = torch.tensor([math.sin(th) * math.sin(az), math.sin(th) * math.cos(az), -math.cos(th)],
+                     dtype=torch.float64)
+    el, saz = math.radians(_SUN_EL_DEG[v]), math.radians(_SUN_AZ_DEG[v])
+    # sun direction formula: reference satellite_rgb_dep.py:571-573
+    s = torch.tensor([math.sin(saz) * math.cos(el), math.cos(saz) * math.cos(el), math.sin(el)],
+                     dtype=torch.float64)
+    return d, s
+
+
+def _surface_depth(o: torch.Tensor, d: torch.Tensor) -> torch.Tensor:
+    """Ray / height-field z = -0.1 + 0.1 sin(3x) cos(2y) intersection distance (fp64 bisection)."""
+    lo = torch.zeros(o.shape[0], dtype=torch.float64)
+    hi = (_SLAB_THICKNESS / d[:, 2].abs())
+    f = lambda t: (o[:, 2] + d[:, 2] * t) - (-0.1 + 0.1 * torch.sin(3 * (o[:, 0] + d[:, 0] * t))
+                                             * torch.cos(2 * (o[:, 1] + d[:, 1] * t)))
+    for _ in range(60):
+        mid = 0.5 * (lo + hi)
+        above = f(mid) > 0
+        lo = torch.where(above, mid, lo)
+        hi = torch.where(above, hi, mid)
+    return 0.5 * (lo + hi)
+
+
+def make_rays(n: int, seed: int = RAY_SEED, depth_supervision: bool = False,
+              zero_std: bool = False, stdscale: float = 1.0, margin: float = 1e-4,
+              single_view: Optional[int] = None) -> RayBatch:
+    """`n` synthetic pushbroom rays over three views (or one, for tile inference)."""
+    g = torch.Generator().manual_seed(seed)
+    xy = torch.rand(n, 2, generator=g, dtype=torch.float64) * 2 - 1
+    jitter = torch.randn(n, 3, generator=g, dtype=torch.float64) * 1e-3
+    rgbs = torch.rand(n, 3, generator=g, dtype=torch.float32)
+    view = torch.arange(n) % 3 if single_view is None else torch.full((n,), single_view)
+    dv = torch.stack([_view_and_sun(v)[0] for v in range(3)])[view]
+    sv = torch.stack([_view_and_sun(v)[1] for v in range(3)])[view]
+    d = dv + jitter
+    d = d / d.norm(dim=-1, keepdim=True)
+    o = torch.cat([xy, torch.full((n, 1), _SLAB_TOP, dtype=torch.float64)], -1)
+    near = torch.zeros(n, 1, dtype=torch.float64)        # satellite_rgb_dep.py:73
+    far = _SLAB_THICKNESS / d[:, 2:3].abs()
+    rays = torch.cat([o, d, near, far, sv], -1).to(torch.float32).contiguous()
+    batch = RayBatch(rays=rays, rgbs=rgbs)
+    if depth_supervision:
+        valid = (torch.rand(n, generator=g) < 0.7).to(torch.int64)
+        corr = torch.rand(n, generator=g, dtype=torch.float64) * 0.5 + 0.5
+        depth = _surface_depth(o, d)
+        batch.valid_depth = valid
+        batch.target_depths = torch.stack([depth, corr], -1).to(torch.float32).contiguous()
+        std = torch.zeros(n, dtype=torch.float64) if zero_std else stdscale * (1 - corr) + margin
+        batch.target_std = std.to(torch.float32).contiguous()
+    return batch
+
+
+def make_tile_rays(h: int, w: int, view: int = 0) -> torch.Tensor:
+    """Row-major pixel grid of one view for full-tile inference (cfg 5); returns (h*w, 11)."""
+    ys, xs = torch.meshgrid(torch.linspace(-1, 1, h, dtype=torch.float64),
+                            torch.linspace(-1, 1, w, dtype=torch.float64), indexing="ij")
+    d0, s0 = _view_and_sun(view)
+    n = h * w
+    o = torch.stack([xs.reshape(-1), ys.reshape(-1), torch.full((n,), _SLAB_TOP, dtype=torch.float64)], -1)
+    d = d0.expand(n, 3)
+    far = torch.full((n, 1), _SLAB_THICKNESS / abs(float(d0[2])), dtype=torch.float64)
+    rays = torch.cat([o, d, torch.zeros(n, 1, dtype=torch.float64), far, s0.expand(n, 3)], -1)
+    return rays.to(torch.float32).contiguous()

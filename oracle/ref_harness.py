@@ -1,0 +1,112 @@
+"""ORACLE (test infrastructure only — never imported by the product path).
+
+Runs the UNMODIFIED reference (read-only tree at $BRDFNERF_REF or /root/reference) in this process
+so the restatement in oracle/ can be pinned against it and golden vectors can be generated.
+The reference tree does not exist on the GPU box; everything here must therefore only be reached
+from tests that skip when the tree is absent, and from oracle/make_golden.py.
+
+Import recipe: the path imports `rasterio` (train_utils.py:9) and, for the losses,
+`kornia.losses.ssim` (metrics.py:7); neither is installed nor used on the path, so empty stub
+modules are registered before importing.
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+import os
+import sys
+import types
+from typing import List
+
+import torch
+
+REF_ROOT = os.environ.get("BRDFNERF_REF", "/root/reference")
+
+
+def available() -> bool:
+    return os.path.isfile(os.path.join(REF_ROOT, "rendering.py"))
+
+
+_mods = None
+
+
+def load():
+    """Import (once) and return (rendering, load_model, metrics) of the live reference."""
+    global _mods
+    if _mods is not None:
+        return _mods
+    if not available():
+        raise RuntimeError(f"reference tree not found at {REF_ROOT}")
+    for name in ("rasterio", "kornia", "kornia.losses"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["kornia.losses"].ssim = lambda *a, **k: None
+    sys.modules["kornia"].losses = sys.modules["kornia.losses"]
+    if REF_ROOT not in sys.path:
+        sys.path.insert(0, REF_ROOT)
+    with contextlib.redirect_stdout(io.StringIO()):
+        import rendering as ref_rendering          # noqa
+        from models import load_model as ref_load  # noqa
+        import metrics as ref_metrics              # noqa
+    _mods = (ref_rendering, ref_load, ref_metrics)
+    return _mods
+
+
+def build_model(args, seed=0):
+    """Random-init reference model exactly as the reference does (spsbrdfnerf.py:537-539)."""
+    _, ref_load, _ = load()
+    torch.manual_seed(seed)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = ref_load(args)
+    return model
+
+
+@contextlib.contextmanager
+def inject_draws(queue: List[torch.Tensor]):
+    """Replace torch.rand / rand_like / randn by a FIFO of pre-drawn tensors (shape-checked)."""
+    q = list(queue)
+    orig = (torch.rand, torch.rand_like, torch.randn)
+
+    def pop(shape, what):
+        if not q:
+            raise RuntimeError(f"draw queue exhausted at {what}{tuple(shape)}")
+        t = q.pop(0)
+        if tuple(t.shape) != tuple(shape):
+            raise RuntimeError(f"draw shape mismatch at {what}: want {tuple(shape)}, queued {tuple(t.shape)}")
+        return t.clone()
+
+    def _shape(a):
+        return tuple(a[0]) if len(a) == 1 and isinstance(a[0], (tuple, list, torch.Size)) else tuple(a)
+
+    torch.rand = lambda *a, **k: pop(_shape(a), "rand")
+    torch.rand_like = lambda t, **k: pop(t.shape, "rand_like").to(t.dtype)
+    torch.randn = lambda *a, **k: pop(_shape(a), "randn")
+    try:
+        yield q
+    finally:
+        torch.rand, torch.rand_like, torch.randn = orig
+
+
+def draw_queue(draws, valid_depth=None, mode="test", dtype=torch.float32):
+    """Order of draws inside one reference render_rays call."""
+    q = [draws.u_strat, draws.noise1]
+    if draws.u_sun is not None:
+        q += [draws.u_sun, draws.noise_sun]
+    q += [draws.u_pred]
+    if mode == "train" and valid_depth is not None:
+        q += [draws.u_gt[valid_depth > 0]]
+    q += [draws.noise2]
+    return [t.to(dtype) for t in q]
+
+
+def render(model, args, rays, draws, dtype=torch.float32, **kw):
+    """Call the live reference render_rays with injected draws; stdout is swallowed."""
+    ref_rendering, _, _ = load()
+    mode = kw.get("mode", "test")
+    q = draw_queue(draws, kw.get("valid_depth"), mode, dtype)
+    buf = io.StringIO()
+    with inject_draws(q) as rest, contextlib.redirect_stdout(buf):
+        res, btype = ref_rendering.render_rays({"coarse": model}, args, rays.to(dtype), None, **kw)
+    if rest:
+        raise RuntimeError(f"{len(rest)} queued draws were not consumed")
+    return res, btype
