@@ -1,0 +1,66 @@
+"""Builds brdf_nerf_b200/libbrdfnerf_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+    python -m brdf_nerf_b200.build [--force]
+"""
+from __future__ import annotations
+
+import concurrent.futures as cf
+import hashlib
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "libbrdfnerf_b200.so")
+OBJ_DIR = os.path.join(HERE, "build")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
+          "-diag-suppress", "177"]
+# per-file extra flags: the sample generator must round after every operation (bit-exact contract)
+EXTRA = {"sampler.cu": ["-fmad=false"]}
+SOURCES = ["api.cu", "sampler.cu", "composite.cu", "shade.cu", "mlp.cu", "normals.cu", "tc_host.cu"]
+
+
+def _digest() -> str:
+    h = hashlib.sha256()
+    for root in (CSRC, os.path.join(HERE, "..", "include")):
+        for name in sorted(os.listdir(root)):
+            if name.endswith((".cu", ".cuh", ".h")):
+                with open(os.path.join(root, name), "rb") as f:
+                    h.update(name.encode()); h.update(f.read())
+    return h.hexdigest()
+
+
+def _compile(src: str) -> str:
+    obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
+    cmd = [NVCC, *ARCH, *COMMON, *EXTRA.get(src, []), "-c", os.path.join(CSRC, src), "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+    return obj
+
+
+def build(force: bool = False, verbose: bool = True) -> str:
+    stamp = os.path.join(OBJ_DIR, "digest.txt")
+    digest = _digest()
+    if not force and os.path.exists(OUT) and os.path.exists(stamp) and open(stamp).read() == digest:
+        return OUT
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    if verbose:
+        print(f"[brdf_nerf_b200.build] nvcc sm_100a: {', '.join(srcs)}", file=sys.stderr)
+    with cf.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+        objs = list(ex.map(_compile, srcs))
+    cmd = [NVCC, *ARCH, "-shared", "-Xcompiler", "-fPIC", "-o", OUT, *objs, "-lcudart"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    with open(stamp, "w") as f:
+        f.write(digest)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv))

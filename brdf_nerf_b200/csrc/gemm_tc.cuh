@@ -1,0 +1,297 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a: bf16 operands, fp32 accumulation in tensor memory,
+// fused epilogue functors (epilogues.cuh).  Persistent, warp-specialised:
+//   warp 0   TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
+//   warp 1   MMA issuer     (one elected lane issues tcgen05.mma, tcgen05.commit frees ring slots)
+//   warp 2   TMEM allocator (2 accumulator stages x BN columns)
+//   warp 4-7 epilogue       (tcgen05.ld 32x32b -> registers -> fused math -> global), overlapped
+//                            with the next tile's mainloop through the second TMEM stage
+//
+//   kNT == false : C[m][n] = sum_k A[m][k] B[n][k]   A:[M,K] B:[N,K], both K-major   (fwd, dgrad)
+//   kNT == true  : C[m][n] = sum_p A[p][m] B[p][n]   A:[P,M] B:[P,N], both MN-major  (wgrad,
+//                  reduction over points split across CTAs, fp32 atomics in the epilogue)
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+
+namespace bn {
+namespace tc {
+
+constexpr int kBM = 128;          // rows of the output tile (UMMA M, cta_group::1)
+constexpr int kBK = 64;           // bf16 elements per smem row = 128 bytes = one swizzle atom row
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded wait: a pipeline bug must end in a trapped launch, never in a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) { printf("bn::tc mbarrier timeout block %d thread %d\n", blockIdx.x, threadIdx.x); __trap(); }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// UMMA shared-memory descriptors (SWIZZLE_128B, version 1 = Blackwell).  Units of 16 bytes.
+//   K-major  : 8-row groups 1024 B apart (SBO); LBO unused (=1)
+//   MN-major : 64-element (128 B) column chunks `lbo_bytes` apart, 8-row K groups 1024 B apart
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;     // descriptor version
+  d |= (uint64_t)2 << 61;     // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: D=f32, A=B=bf16, M=128, N=BN, majorness per operand
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((mn_major ? 1u : 0u) << 15) | ((mn_major ? 1u : 0u) << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+}
+
+struct Work {
+  int m_tiles, n_tiles, splits;   // splits only for kNT
+  int kb_total, kb_per_split;     // k-blocks (of kBK) in the reduction dimension
+};
+
+template <int BN, int STAGES, bool kNT, class Epi>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Work wk, Epi epi) {
+  constexpr uint32_t A_BYTES = kBM * kBK * 2;
+  constexpr uint32_t B_BYTES = BN * kBK * 2;
+  constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int n_items = wk.m_tiles * wk.n_tiles * wk.splits;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const int split = it / (wk.m_tiles * wk.n_tiles);
+        const int t = it % (wk.m_tiles * wk.n_tiles);
+        const int m_blk = t / wk.n_tiles, n_blk = t % wk.n_tiles;
+        const int kb0 = split * wk.kb_per_split;
+        const int kb1 = min(wk.kb_total, kb0 + wk.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], A_BYTES + B_BYTES);
+          uint8_t* a = sA + stage * A_BYTES;
+          uint8_t* b = sB + stage * B_BYTES;
+          if (!kNT) {
+            tma_load_2d(a, &tmA, &full[stage], kb * kBK, m_blk * kBM);
+            tma_load_2d(b, &tmB, &full[stage], kb * kBK, n_blk * BN);
+          } else {
+            // boxes of 64 (contiguous MN) x 64 (reduction rows); one box per 64 output rows/cols
+#pragma unroll
+            for (int c = 0; c < kBM / 64; ++c) tma_load_2d(a + c * 8192, &tmA, &full[stage], m_blk * kBM + c * 64, kb * kBK);
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c) tma_load_2d(b + c * 8192, &tmB, &full[stage], n_blk * BN + c * 64, kb * kBK);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN, kNT);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const int split = it / (wk.m_tiles * wk.n_tiles);
+        const int kb0 = split * wk.kb_per_split;
+        const int kb1 = min(wk.kb_total, kb0 + wk.kb_per_split);
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full[stage], phase);
+          fence_after_sync();
+          const uint32_t a_addr = smem_u32(sA + stage * A_BYTES);
+          const uint32_t b_addr = smem_u32(sB + stage * B_BYTES);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            uint64_t da, db;
+            if (!kNT) {
+              da = make_desc(a_addr + k * 32, 16, 1024);
+              db = make_desc(b_addr + k * 32, 16, 1024);
+            } else {
+              da = make_desc(a_addr + k * 2048, 8192, 1024);
+              db = make_desc(b_addr + k * 2048, 8192, 1024);
+            }
+            umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp - 4;                       // TMEM lane quadrant == warp % 4
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      const int t = it % (wk.m_tiles * wk.n_tiles);
+      const int m_blk = t / wk.n_tiles, n_blk = t % wk.n_tiles;
+      mbar_wait(&tfull[acc], acc_phase);
+      fence_after_sync();
+      const int row = m_blk * kBM + q * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        float v[32];
+        tmem_ld32(taddr + c * 32, v);
+        epi.template apply<32>(row, n_blk * BN + c * 32, v);
+      }
+      fence_before_sync();
+      mbar_arrive(&tempty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 2) { fence_after_sync(); tmem_dealloc(tmem_base, TMEM_COLS); }
+}
+
+// ---- host side: tensor maps ------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn();
+
+// 2-D bf16 tensor [rows, cols] with row pitch `ld` elements; box = box_cols x box_rows, 128B swizzle
+int make_map_bf16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld,
+                  int box_cols, int box_rows);
+
+template <int BN, bool kNT> constexpr int smem_bytes(int stages) {
+  return stages * (kBM * kBK * 2 + BN * kBK * 2) + (2 * stages + 4) * 8 + 16 + 1024;
+}
+
+// A:[M,K] (ld lda), B:[N,K]: C = A B^T through `epi`
+template <int BN, class Epi>
+int launch_tn(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* B, long long ldb,
+              long long M, int N, int K, const Epi& epi, int num_sms, cudaStream_t s) {
+  constexpr int STAGES = (BN == 256) ? 4 : 6;
+  if (K % kBK) { set_error("tc::launch_tn: K=%d not a multiple of 64", K); return BN_ERR_ARG; }
+  CUtensorMap ma, mb;
+  if (int rc = make_map_bf16(&ma, A, M, K, lda, kBK, kBM)) return rc;
+  if (int rc = make_map_bf16(&mb, B, N, K, ldb, kBK, BN)) return rc;
+  Work wk{(int)ceil_div_ll(M, kBM), ceil_div(N, BN), 1, K / kBK, K / kBK};
+  auto kern = gemm_tc_kernel<BN, STAGES, false, Epi>;
+  constexpr int smem = smem_bytes<BN, false>(STAGES);
+  BN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int items = wk.m_tiles * wk.n_tiles;
+  kern<<<min(items, num_sms), kThreads, smem, s>>>(ma, mb, wk, epi);
+  return check_cuda(cudaGetLastError(), "gemm_tc_kernel<tn>");
+}
+
+// A:[P,Mo] (ld lda), B:[P,No]: C[Mo,No] = A^T B through `epi` (atomic accumulate), split over P
+template <int BN, class Epi>
+int launch_nt(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* B, long long ldb,
+              int Mo, int No, long long P, const Epi& epi, int num_sms, cudaStream_t s) {
+  constexpr int STAGES = (BN == 256) ? 4 : 6;
+  if (Mo % 64) { set_error("tc::launch_nt: Mo=%d not a multiple of 64", Mo); return BN_ERR_ARG; }
+  CUtensorMap ma, mb;
+  if (int rc = make_map_bf16(&ma, A, P, Mo, lda, 64, kBK)) return rc;
+  if (int rc = make_map_bf16(&mb, B, P, No, ldb, 64, kBK)) return rc;
+  Work wk;
+  wk.m_tiles = ceil_div(Mo, kBM); wk.n_tiles = ceil_div(No, BN);
+  wk.kb_total = (int)ceil_div_ll(P, kBK);
+  const int tiles = wk.m_tiles * wk.n_tiles;
+  int splits = max(1, min(ceil_div(num_sms, tiles), ceil_div(wk.kb_total, 8)));
+  wk.kb_per_split = ceil_div(wk.kb_total, splits);
+  wk.splits = ceil_div(wk.kb_total, wk.kb_per_split);
+  auto kern = gemm_tc_kernel<BN, STAGES, true, Epi>;
+  constexpr int smem = smem_bytes<BN, true>(STAGES);
+  BN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int items = tiles * wk.splits;
+  kern<<<min(items, num_sms), kThreads, smem, s>>>(ma, mb, wk, epi);
+  return check_cuda(cudaGetLastError(), "gemm_tc_kernel<nt>");
+}
+
+}  // namespace tc
+}  // namespace bn

@@ -1,0 +1,777 @@
+// K-B: positional encoding + SIREN MLP (trunk, sigma / feature / colour / BRDF heads), forward and
+// backward, as a chain of fused GEMMs.
+//
+// Replaces (reference, paths relative to /root/reference):
+//   xyz = o + d z                        rendering.py:184,216,254,273
+//   Mapping.forward                      models/nerf.py:53-70
+//   SpSBRDFNeRF.calc_features            models/spsbrdfnerf.py:636-646 (layers :513-524)
+//   sigma / feats / rgb / BRDF heads     models/spsbrdfnerf.py:527-535,582-613,682-755
+//   autograd backward of all of it       implicit (dgrad + wgrad)
+//
+// Two precision modes share this orchestration and the epilogue functors:
+//   BN_PREC_BF16 : tcgen05.mma (gemm_tc.cuh) — bf16 activations/weights in HBM, fp32 accumulation in
+//                  TMEM, sin / cos / bias / Hadamard fused in the epilogue warps;
+//   BN_PREC_FP32 : CUDA-core fp32 (gemm_simt.cuh) — parity mode and on-device checker.
+// Activation layout in the caller's workspace (row = point, row-major, element type T):
+//   X3 [P, 64+F]  : cols 0..63 = encoding (60 real + 4 zero pad), cols 64.. = h_{skip-1}; the skip
+//                   layer reads the whole row as its K = 64+F operand (no concat copy)
+//   H_l, C_l [P,F]: h_l = sin(w0 z_l) and c_l = w0 cos(w0 z_l) (kept only when training)
+//   FE [P,F], HD / CD [P, 256*blocks]: features and the heads' hidden layer (+ cosine)
+#include <vector>
+#include <type_traits>
+#include <string.h>
+#include <math.h>
+#include "epilogues.cuh"
+#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
+
+namespace bn {
+
+constexpr int kEncPad = 64;
+constexpr int kMaxBlocks = 8;     // rgb + up to 7 BRDF heads
+constexpr int kMaxOut = 16;       // scalar outputs of the heads' second layers
+constexpr float kPiF = 3.14159265358979323846f;
+
+enum { XF_SIGMOID = 0, XF_K = 1, XF_THETA_RPV = 2, XF_THETA_H = 3 };
+
+struct OutDesc { int block; long long w_off; long long b_off; int ch; int rep; int xform; };
+struct HeadPlan {
+  int n_out; OutDesc o[kMaxOut];
+  int n_blocks;                 // blocks of the hidden layer that are evaluated
+  int HH;                       // hidden width of one block (feat / 2)
+  int ch_sigma, ch_nlr;         // packed channel of sigma / learned normal (-1 = off)
+  long long wsig, bsig, wg, bg; // offsets of sigma_from_xyz.0 / grad_from_xyz
+};
+
+}  // namespace bn
+
+struct bn_mlp {
+  bn_mlp_cfg cfg;
+  int F, L, E, HH, skip;
+  int num_sms;
+  bool bf16;
+  size_t es;
+  void* Wp[16]; void* WTp[16]; int Kpad[16]; int Kreal[16];
+  void* Wf; void* WfT;
+  void* W1; void* W1T; float* b1cat;
+  int n_blocks;
+  int blk_lin0[bn::kMaxBlocks], blk_lin2[bn::kMaxBlocks], blk_head[bn::kMaxBlocks];
+  bool synced;
+};
+
+namespace bn {
+
+// ------------------------------------------------------------------------------------------------
+// weight packing: flat fp32 [N, Kreal] -> Wp [N, Kpad] and WTp [Kpad, N] (element type T), with the
+// encoding columns padded from E to 64.
+template <typename T>
+__global__ void pack_weight_kernel(const float* __restrict__ W, int N, int Kreal, int E, int Kpad,
+                                   T* __restrict__ Wp, long long ldp, T* __restrict__ WTp, long long ldt, int row0) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)N * Kpad) return;
+  const int n = (int)(idx / Kpad), kp = (int)(idx % Kpad);
+  int k = -1;                                   // source column, -1 = padding
+  if (E >= 0) { if (kp < E) k = kp; else if (kp >= kEncPad) k = kp - (kEncPad - E); }
+  else k = kp;
+  const float v = (k >= 0 && k < Kreal) ? W[(long long)n * Kreal + k] : 0.f;
+  if (Wp) Wp[(long long)(row0 + n) * ldp + kp] = from_f<T>(v);
+  if (WTp) WTp[(long long)kp * ldt + row0 + n] = from_f<T>(v);
+}
+
+// ------------------------------------------------------------------------------------------------
+// x = o + d z (separately rounded mul and add, as the reference) and the positional encoding
+// [sin(2^k x), cos(2^k x)]_k written into cols 0..63 of X3 (zero padded).  One thread per point.
+template <typename T>
+__global__ void encode_kernel(const float* __restrict__ origins, int o_stride, const float* __restrict__ dirs,
+                              int d_stride, const float* __restrict__ z, int S, long long P, int n_freq,
+                              T* __restrict__ X3, long long ld) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const long long r = p / S;
+  const float zz = z[p];
+  float x[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) x[a] = __fadd_rn(origins[r * o_stride + a], __fmul_rn(dirs[r * d_stride + a], zz));
+  float e[kEncPad];
+#pragma unroll
+  for (int i = 0; i < kEncPad; ++i) e[i] = 0.f;
+  if (n_freq == 0) { e[0] = x[0]; e[1] = x[1]; e[2] = x[2]; }
+  else {
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+      if (k < n_freq) {
+        const float f = (float)(1 << k);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { float s, c; sincosf(f * x[a], &s, &c); e[k * 6 + a] = s; e[k * 6 + 3 + a] = c; }
+      }
+    }
+  }
+  T* dst = X3 + p * ld;
+#pragma unroll
+  for (int i = 0; i < kEncPad; i += 8) {
+    float t[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t[j] = e[i + j];
+    Pack<T, 8>::store(dst + i, t);
+  }
+}
+
+template <typename T> __device__ __forceinline__ void load8g(const T* p, float (&v)[8]) { load8<T>(p, v); }
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float softplusf_(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+
+// ------------------------------------------------------------------------------------------------
+// second layers of all heads + sigma + learned normal: one warp per point, lanes split K.
+template <typename T>
+__global__ void __launch_bounds__(128) heads_fwd_kernel(HeadPlan hp, const float* __restrict__ params,
+                                                        const T* __restrict__ Hlast, long long ldh, int F,
+                                                        const T* __restrict__ HD, long long ldd,
+                                                        float* __restrict__ out, int pitch, long long P, bool sigma_only) {
+  const int lane = threadIdx.x % 32;
+  const long long p = (long long)blockIdx.x * 4 + threadIdx.x / 32;
+  if (p >= P) return;
+  // sigma (+ learned normal) from the trunk's last activation
+  float s_acc = 0.f, g_acc[3] = {0.f, 0.f, 0.f};
+  for (int i = lane * 8; i < F; i += 256) {
+    float h[8]; load8g<T>(Hlast + p * ldh + i, h);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s_acc = fmaf(h[j], __ldg(params + hp.wsig + i + j), s_acc);
+      if (hp.ch_nlr >= 0) {
+#pragma unroll
+        for (int o = 0; o < 3; ++o) g_acc[o] = fmaf(h[j], __ldg(params + hp.wg + (long long)o * F + i + j), g_acc[o]);
+      }
+    }
+  }
+  s_acc = warp_sum(s_acc);
+  const float sigma = softplusf_(s_acc + __ldg(params + hp.bsig));
+  if (sigma_only) { if (lane == 0) out[p] = sigma; return; }
+  float* row = out + p * pitch;
+  if (lane == 0) row[hp.ch_sigma] = sigma;
+  if (hp.ch_nlr >= 0) {
+    float g[3];
+#pragma unroll
+    for (int o = 0; o < 3; ++o) g[o] = warp_sum(g_acc[o]) + __ldg(params + hp.bg + o);
+    const float inv = 1.0f / sqrtf(fmaxf(g[0] * g[0] + g[1] * g[1] + g[2] * g[2], 1.1920929e-07f));
+    if (lane < 3) row[hp.ch_nlr + lane] = -g[lane] * inv;
+  }
+  for (int b = 0; b < hp.n_blocks; ++b) {
+    float acc[kMaxOut];
+#pragma unroll
+    for (int o = 0; o < kMaxOut; ++o) acc[o] = 0.f;
+    for (int i = lane * 8; i < hp.HH; i += 256) {
+      float h[8]; load8g<T>(HD + p * ldd + (long long)b * hp.HH + i, h);
+#pragma unroll
+      for (int o = 0; o < kMaxOut; ++o) {
+        if (o < hp.n_out && hp.o[o].block == b) {
+          const float* w = params + hp.o[o].w_off + i;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[o] = fmaf(h[j], __ldg(w + j), acc[o]);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < kMaxOut; ++o) {
+      if (o < hp.n_out && hp.o[o].block == b) {
+        const float pre = warp_sum(acc[o]) + __ldg(params + hp.o[o].b_off);
+        const float s = sigmoidf_(pre);
+        float v = s;
+        if (hp.o[o].xform == XF_K) v = (s - 0.5f) * 2.0f + 1.0f;
+        else if (hp.o[o].xform == XF_THETA_RPV) v = (s - 0.5f) * 2.0f;
+        else if (hp.o[o].xform == XF_THETA_H) v = s * (float)(M_PI * 30.0 / 180.0);
+        if (lane < hp.o[o].rep) row[hp.o[o].ch + lane] = v;
+      }
+    }
+  }
+}
+
+// backward of heads_fwd_kernel.  Writes, per point:
+//   GHD [P, n_blocks*HH] = (sum_o dpre_o W2_o) ⊙ CD      (dgrad operand of the heads' first layer)
+//   G7D [P, F]           = dpre_sigma w_sigma + sum_o dpre_nlr,o Wg_o   (direct grads into h_{L-1})
+//   DPRE [P, 16], DPRE2 [P, 8]  pre-activation grads (operands of the skinny weight gradients)
+template <typename T>
+__global__ void __launch_bounds__(128) heads_bwd_kernel(HeadPlan hp, const float* __restrict__ params,
+                                                        const float* __restrict__ out, const float* __restrict__ g_out, int pitch,
+                                                        const T* __restrict__ Hlast, long long ldh, int F,
+                                                        const T* __restrict__ CD, long long ldd,
+                                                        T* __restrict__ GHD, T* __restrict__ G7D,
+                                                        T* __restrict__ DPRE, T* __restrict__ DPRE2, long long P) {
+  const int lane = threadIdx.x % 32;
+  const long long p = (long long)blockIdx.x * 4 + threadIdx.x / 32;
+  if (p >= P) return;
+  const float* row = out + p * pitch;
+  const float* grow = g_out + p * pitch;
+  float dpre[kMaxOut];
+#pragma unroll
+  for (int o = 0; o < kMaxOut; ++o) {
+    dpre[o] = 0.f;
+    if (o < hp.n_out) {
+      const OutDesc& d = hp.o[o];
+      float g = 0.f;
+      for (int c = 0; c < d.rep; ++c) g += grow[d.ch + c];
+      float s, scale;
+      const float v = row[d.ch];
+      if (d.xform == XF_K) { s = (v - 1.0f) * 0.5f + 0.5f; scale = 2.0f; }
+      else if (d.xform == XF_THETA_RPV) { s = v * 0.5f + 0.5f; scale = 2.0f; }
+      else if (d.xform == XF_THETA_H) { const float k = (float)(M_PI * 30.0 / 180.0); s = v / k; scale = k; }
+      else { s = v; scale = 1.0f; }
+      dpre[o] = g * scale * s * (1.0f - s);
+    }
+  }
+  const float sigma = row[hp.ch_sigma];
+  const float dsig = grow[hp.ch_sigma] * (1.0f - expf(-sigma));      // softplus'(x) = 1 - exp(-softplus(x))
+  float dv[3] = {0.f, 0.f, 0.f};
+  if (hp.ch_nlr >= 0) {
+    // n = -v/|v| ; recompute v = Wg h + bg
+    float g_acc[3] = {0.f, 0.f, 0.f};
+    for (int i = lane * 8; i < F; i += 256) {
+      float h[8]; load8g<T>(Hlast + p * ldh + i, h);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int o = 0; o < 3; ++o) g_acc[o] = fmaf(h[j], __ldg(params + hp.wg + (long long)o * F + i + j), g_acc[o]);
+    }
+    float v[3];
+#pragma unroll
+    for (int o = 0; o < 3; ++o) v[o] = warp_sum(g_acc[o]) + __ldg(params + hp.bg + o);
+    const float sq = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+    const float gn[3] = {grow[hp.ch_nlr], grow[hp.ch_nlr + 1], grow[hp.ch_nlr + 2]};
+    if (sq > 1.1920929e-07f) {
+      const float inv = 1.0f / sqrtf(sq);
+      const float u[3] = {v[0] * inv, v[1] * inv, v[2] * inv};
+      const float gu = gn[0] * u[0] + gn[1] * u[1] + gn[2] * u[2];
+#pragma unroll
+      for (int o = 0; o < 3; ++o) dv[o] = -(gn[o] - gu * u[o]) * inv;
+    } else {
+      const float inv = 1.0f / sqrtf(1.1920929e-07f);
+#pragma unroll
+      for (int o = 0; o < 3; ++o) dv[o] = -gn[o] * inv;
+    }
+  }
+  if (lane == 0) {
+    float t[16];
+#pragma unroll
+    for (int o = 0; o < 16; ++o) t[o] = dpre[o];
+    Pack<T, 16>::store(DPRE + p * 16, t);
+    float u8[8] = {dsig, dv[0], dv[1], dv[2], 0.f, 0.f, 0.f, 0.f};
+    Pack<T, 8>::store(DPRE2 + p * 8, u8);
+  }
+  for (int i = lane * 8; i < F; i += 256) {
+    float g[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float a = dsig * __ldg(params + hp.wsig + i + j);
+      if (hp.ch_nlr >= 0) {
+#pragma unroll
+        for (int o = 0; o < 3; ++o) a = fmaf(dv[o], __ldg(params + hp.wg + (long long)o * F + i + j), a);
+      }
+      g[j] = a;
+    }
+    Pack<T, 8>::store(G7D + p * F + i, g);
+  }
+  for (int b = 0; b < hp.n_blocks; ++b) {
+    for (int i = lane * 8; i < hp.HH; i += 256) {
+      float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int o = 0; o < kMaxOut; ++o) {
+        if (o < hp.n_out && hp.o[o].block == b) {
+          const float* w = params + hp.o[o].w_off + i;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a[j] = fmaf(dpre[o], __ldg(w + j), a[j]);
+        }
+      }
+      float c[8]; load8g<T>(CD + p * ldd + (long long)b * hp.HH + i, c);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] *= c[j];
+      Pack<T, 8>::store(GHD + p * ldd + (long long)b * hp.HH + i, a);
+    }
+  }
+}
+
+// out_o[i - c0_o] += sum_p D[p][o] X[p][i]   for i in [c0_o, c1_o), plus bias_o += sum_p D[p][o].
+struct SkinnyRow { float* dst; float* bias; int col; int c0, c1; };
+struct SkinnyPlan { int n; SkinnyRow r[kMaxOut]; };
+
+template <typename T>
+__global__ void __launch_bounds__(256) skinny_wgrad_kernel(SkinnyPlan sp, const T* __restrict__ D, int ldd,
+                                                           const T* __restrict__ X, long long ldx, int ncols,
+                                                           long long P, long long rows_per_block) {
+  __shared__ float sD[32][kMaxOut];
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  const long long p0 = (long long)blockIdx.y * rows_per_block;
+  const long long p1 = min(P, p0 + rows_per_block);
+  float acc[kMaxOut], bacc[kMaxOut];
+#pragma unroll
+  for (int o = 0; o < kMaxOut; ++o) { acc[o] = 0.f; bacc[o] = 0.f; }
+  for (long long pb = p0; pb < p1; pb += 32) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < 32 * kMaxOut; t += 256) {
+      const int pp = t / kMaxOut, o = t % kMaxOut;
+      sD[pp][o] = (pb + pp < p1 && o < sp.n) ? to_f<T>(D[(pb + pp) * ldd + sp.r[o].col]) : 0.f;
+    }
+    __syncthreads();
+    const int cnt = (int)min(32LL, p1 - pb);
+    for (int pp = 0; pp < cnt; ++pp) {
+      const float x = i < ncols ? to_f<T>(X[(pb + pp) * ldx + i]) : 0.f;
+#pragma unroll
+      for (int o = 0; o < kMaxOut; ++o) { acc[o] = fmaf(sD[pp][o], x, acc[o]); bacc[o] += sD[pp][o]; }
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < kMaxOut; ++o) {
+    if (o < sp.n) {
+      if (i >= sp.r[o].c0 && i < sp.r[o].c1) atomicAdd(sp.r[o].dst + (i - sp.r[o].c0), acc[o]);
+      if (sp.r[o].bias && i == sp.r[o].c0) atomicAdd(sp.r[o].bias, bacc[o]);
+    }
+  }
+}
+
+// dst[c] += sum_p X[p][c]   (bias gradients), 8 columns per thread
+template <typename T>
+__global__ void __launch_bounds__(128) colsum_kernel(const T* __restrict__ X, long long ldx, int ncols, long long P,
+                                                     long long rows_per_block, float* __restrict__ dst) {
+  const int c = (blockIdx.x * 128 + threadIdx.x) * 8;
+  if (c >= ncols) return;
+  const long long p0 = (long long)blockIdx.y * rows_per_block;
+  const long long p1 = min(P, p0 + rows_per_block);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (long long p = p0; p < p1; ++p) {
+    float v[8]; load8<T>(X + p * ldx + c, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += v[j];
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) atomicAdd(dst + c + j, acc[j]);
+}
+
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
+                            float wd, float bc1, float bc2_sqrt, float gscale) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float gi = g[i] * gscale;
+  float pi = p[i];
+  if (wd != 0.f) gi += wd * pi;
+  const float mi = b1 * m[i] + (1.0f - b1) * gi;
+  const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+  m[i] = mi; v[i] = vi;
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;
+  p[i] = pi - (lr / bc1) * (mi / denom);
+}
+
+// ------------------------------------------------------------------------------------------------
+template <typename T> struct Ws {
+  T* X3; T* H[16]; long long Hld[16]; T* C[16];
+  T* FE; T* HD; T* CD; T* GHD; T* G7D; T* GFE; T* GA; T* GB; T* DPRE; T* DPRE2;
+  long long ldx3, ldhd;
+};
+
+static size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
+
+template <typename T>
+static size_t carve(const bn_mlp* h, long long P, int flags, void* base, Ws<T>* w) {
+  const bool train = flags & BN_MLP_TRAIN, sig_only = flags & BN_MLP_SIGMA_ONLY;
+  const int F = h->F, L = h->L;
+  size_t off = 0;
+  auto take = [&](long long elems) -> T* {
+    T* p = base ? reinterpret_cast<T*>(reinterpret_cast<uint8_t*>(base) + off) : nullptr;
+    off += align_up((size_t)elems * sizeof(T));
+    return p;
+  };
+  Ws<T> t{};
+  t.ldx3 = kEncPad + F;
+  t.ldhd = (long long)h->n_blocks * h->HH;
+  t.X3 = take(P * t.ldx3);
+  if (train) {
+    for (int l = 0; l < L; ++l) {
+      if (l == h->skip - 1) { t.H[l] = t.X3 ? t.X3 + kEncPad : nullptr; t.Hld[l] = t.ldx3; }
+      else { t.H[l] = take(P * F); t.Hld[l] = F; }
+      t.C[l] = take(P * F);
+    }
+  } else {
+    T* ping = take(P * F); T* pong = take(P * F);
+    for (int l = 0; l < L; ++l) {
+      if (l == h->skip - 1) { t.H[l] = t.X3 ? t.X3 + kEncPad : nullptr; t.Hld[l] = t.ldx3; }
+      else { t.H[l] = (l & 1) ? pong : ping; t.Hld[l] = F; }
+      t.C[l] = nullptr;
+    }
+  }
+  if (!sig_only) {
+    t.FE = take(P * F);
+    t.HD = take(P * t.ldhd);
+    if (train) {
+      t.CD = take(P * t.ldhd); t.GHD = take(P * t.ldhd);
+      t.G7D = take(P * F); t.GFE = take(P * F); t.GA = take(P * F); t.GB = take(P * F);
+      t.DPRE = take(P * 16); t.DPRE2 = take(P * 8);
+    }
+  }
+  if (w) *w = t;
+  return off;
+}
+
+static int build_plan(const bn_mlp* h, int flags, HeadPlan* hp, int* n_channels) {
+  HeadPlan p{};
+  const bn_mlp_cfg& c = h->cfg;
+  p.HH = h->HH;
+  p.wsig = c.w_off[BN_LIN_SIGMA]; p.bsig = c.b_off[BN_LIN_SIGMA];
+  p.wg = c.w_off[BN_LIN_GRAD]; p.bg = c.b_off[BN_LIN_GRAD];
+  int ch = 0;
+  // albedo: rgb_from_xyzdir.2 rows 0..2 on block 0
+  for (int o = 0; o < 3; ++o)
+    p.o[p.n_out++] = OutDesc{0, c.w_off[BN_LIN_RGB2] + (long long)o * h->HH, c.b_off[BN_LIN_RGB2] + o, ch++, 1, XF_SIGMOID};
+  p.ch_sigma = ch++;
+  if (flags & BN_MLP_NORMAL_AN) ch += 3;        // written by the analytic-normal sweep
+  p.ch_nlr = -1;
+  if (flags & BN_MLP_NORMAL_LR) {
+    if (!c.normal_lr) { set_error("learned normal requested but the model has no grad_from_xyz head"); return BN_ERR_ARG; }
+    p.ch_nlr = ch; ch += 3;
+  }
+  int last_block = 0;
+  auto add_head = [&](int head, int xform) {
+    int blk = -1;
+    for (int b = 0; b < h->n_blocks; ++b) if (h->blk_head[b] == head) blk = b;
+    if (blk < 0) return;
+    const int dim = c.head_dim[head];
+    const int lin2 = h->blk_lin2[blk];
+    if (head == BN_HEAD_ROUGH || head == BN_HEAD_THETA) {
+      p.o[p.n_out++] = OutDesc{blk, c.w_off[lin2], c.b_off[lin2], ch, 1, xform}; ch += 1;
+    } else if (dim == 1) {
+      p.o[p.n_out++] = OutDesc{blk, c.w_off[lin2], c.b_off[lin2], ch, 3, xform}; ch += 3;
+    } else {
+      for (int o = 0; o < 3; ++o)
+        p.o[p.n_out++] = OutDesc{blk, c.w_off[lin2] + (long long)o * h->HH, c.b_off[lin2] + o, ch + o, 1, xform};
+      ch += 3;
+    }
+    last_block = max(last_block, blk);
+  };
+  if (flags & BN_MLP_ROUGH) add_head(BN_HEAD_ROUGH, XF_SIGMOID);
+  else if (flags & BN_MLP_RPV) { add_head(BN_HEAD_K, XF_K); add_head(BN_HEAD_THETA_RPV, XF_THETA_RPV); add_head(BN_HEAD_RHOC, XF_SIGMOID); }
+  else if (flags & BN_MLP_HAPKE) {
+    add_head(BN_HEAD_B, XF_SIGMOID); add_head(BN_HEAD_C, XF_SIGMOID);
+    if (flags & BN_MLP_HAPKE_THETA) add_head(BN_HEAD_THETA, XF_THETA_H);
+  }
+  p.n_blocks = last_block + 1;
+  if (hp) *hp = p;
+  if (n_channels) *n_channels = ch;
+  return BN_OK;
+}
+
+// GEMM dispatch: tcgen05 for bf16, CUDA cores for fp32
+template <typename T, class Epi>
+static int gemm_tn(const bn_mlp* h, const T* A, long long lda, const T* B, long long ldb, long long M, int N, int K,
+                   const Epi& epi, cudaStream_t s) {
+  if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+    if (N >= 256) return tc::launch_tn<256>(A, lda, B, ldb, M, N, K, epi, h->num_sms, s);
+    if (N >= 128) return tc::launch_tn<128>(A, lda, B, ldb, M, N, K, epi, h->num_sms, s);
+    return tc::launch_tn<64>(A, lda, B, ldb, M, N, K, epi, h->num_sms, s);
+  } else {
+    return launch_tn_simt<T, Epi>(A, lda, B, ldb, (int)M, N, K, epi, s);
+  }
+}
+template <typename T>
+static int gemm_nt(const bn_mlp* h, const T* A, long long lda, const T* B, long long ldb, int Mo, int No, long long P,
+                   const EpiWgrad& epi, cudaStream_t s) {
+  if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+    if (No >= 256) return tc::launch_nt<256>(A, lda, B, ldb, Mo, No, P, epi, h->num_sms, s);
+    if (No >= 128) return tc::launch_nt<128>(A, lda, B, ldb, Mo, No, P, epi, h->num_sms, s);
+    return tc::launch_nt<64>(A, lda, B, ldb, Mo, No, P, epi, h->num_sms, s);
+  } else {
+    return launch_nt_simt<T, EpiWgrad>(A, lda, B, ldb, Mo, No, P, epi, s);
+  }
+}
+
+template <typename T>
+static int colsum(const T* X, long long ldx, int ncols, long long P, float* dst, cudaStream_t s) {
+  const int bx = ceil_div(ncols, 128 * 8);
+  int by = (int)max(1LL, min(ceil_div_ll(P, 64), (long long)(148 * 8 / bx)));
+  const long long rows = ceil_div_ll(P, by);
+  by = (int)ceil_div_ll(P, rows);
+  colsum_kernel<T><<<dim3(bx, by), 128, 0, s>>>(X, ldx, ncols, P, rows, dst);
+  return check_cuda(cudaGetLastError(), "colsum_kernel");
+}
+
+template <typename T>
+static int sync_weights_t(bn_mlp* h, const float* params, cudaStream_t s) {
+  const bn_mlp_cfg& c = h->cfg;
+  auto pack = [&](int lin, int N, int Kreal, int E, int Kpad, void* Wp, long long ldp, void* WTp, long long ldt, int row0) {
+    const long long tot = (long long)N * Kpad;
+    pack_weight_kernel<T><<<(unsigned)ceil_div_ll(tot, 256), 256, 0, s>>>(params + c.w_off[lin], N, Kreal, E, Kpad,
+                                                                         (T*)Wp, ldp, (T*)WTp, ldt, row0);
+    return check_cuda(cudaGetLastError(), "pack_weight_kernel");
+  };
+  for (int l = 0; l < h->L; ++l) {
+    const bool enc_in = (l == 0 || l == h->skip);
+    if (int rc = pack(BN_LIN_TRUNK0 + l, h->F, h->Kreal[l], enc_in ? h->E : -1, h->Kpad[l], h->Wp[l], h->Kpad[l], h->WTp[l], h->F, 0)) return rc;
+  }
+  if (int rc = pack(BN_LIN_FEATS, h->F, h->F, -1, h->F, h->Wf, h->F, h->WfT, h->F, 0)) return rc;
+  const long long HK = (long long)h->n_blocks * h->HH;
+  for (int b = 0; b < h->n_blocks; ++b) {
+    if (int rc = pack(h->blk_lin0[b], h->HH, h->F, -1, h->F, h->W1, h->F, h->W1T, HK, b * h->HH)) return rc;
+    BN_CUDA(cudaMemcpyAsync(h->b1cat + b * h->HH, params + c.b_off[h->blk_lin0[b]], sizeof(float) * h->HH,
+                            cudaMemcpyDeviceToDevice, s));
+  }
+  h->synced = true;
+  return BN_OK;
+}
+
+template <typename T>
+static int forward_t(bn_mlp* h, const float* params, const float* origins, int o_stride, const float* dirs,
+                     int d_stride, const float* z, int N, int S, int flags, float* out, int pitch, void* wsp,
+                     cudaStream_t s) {
+  const long long P = (long long)N * S;
+  const bool train = flags & BN_MLP_TRAIN, sig_only = flags & BN_MLP_SIGMA_ONLY;
+  const bn_mlp_cfg& c = h->cfg;
+  const int F = h->F, L = h->L;
+  Ws<T> w; carve<T>(h, P, flags, wsp, &w);
+  HeadPlan hp; int nch;
+  if (int rc = build_plan(h, flags, &hp, &nch)) return rc;
+  if (!sig_only && pitch < nch) { set_error("bn_mlp_forward: out_pitch %d < %d channels", pitch, nch); return BN_ERR_ARG; }
+  encode_kernel<T><<<(unsigned)ceil_div_ll(P, 128), 128, 0, s>>>(origins, o_stride, dirs, d_stride, z, S, P,
+                                                               c.n_freq_xyz, w.X3, w.ldx3);
+  BN_LAUNCH_CHECK();
+  constexpr bool kFast = std::is_same<T, __nv_bfloat16>::value;
+  for (int l = 0; l < L; ++l) {
+    const T* A; long long lda;
+    if (l == 0 || l == h->skip) { A = w.X3; lda = w.ldx3; } else { A = w.H[l - 1]; lda = w.Hld[l - 1]; }
+    if (l == 0) {
+      // first layer: sin(30 z) — accurate sincos even on the bf16 path (arguments reach |30 z|)
+      EpiSin<T, false> epi{params + c.b_off[l], 30.0f, w.H[l], w.Hld[l], train ? w.C[l] : nullptr, F, (int)P, F};
+      if (int rc = gemm_tn<T>(h, A, lda, (const T*)h->Wp[l], h->Kpad[l], P, F, h->Kpad[l], epi, s)) return rc;
+    } else {
+      EpiSin<T, kFast> epi{params + c.b_off[l], 1.0f, w.H[l], w.Hld[l], train ? w.C[l] : nullptr, F, (int)P, F};
+      if (int rc = gemm_tn<T>(h, A, lda, (const T*)h->Wp[l], h->Kpad[l], P, F, h->Kpad[l], epi, s)) return rc;
+    }
+  }
+  const T* Hl = w.H[L - 1]; const long long ldl = w.Hld[L - 1];
+  if (sig_only) {
+    heads_fwd_kernel<T><<<(unsigned)ceil_div_ll(P, 4), 128, 0, s>>>(hp, params, Hl, ldl, F, nullptr, 0, out, 1, P, true);
+    BN_LAUNCH_CHECK();
+    return BN_OK;
+  }
+  {
+    EpiBias<T> epi{params + c.b_off[BN_LIN_FEATS], w.FE, F, (int)P, F};
+    if (int rc = gemm_tn<T>(h, Hl, ldl, (const T*)h->Wf, F, P, F, F, epi, s)) return rc;
+  }
+  {
+    const int HKa = hp.n_blocks * h->HH;
+    EpiSin<T, kFast> epi{h->b1cat, 1.0f, w.HD, w.ldhd, train ? w.CD : nullptr, w.ldhd, (int)P, HKa};
+    if (int rc = gemm_tn<T>(h, w.FE, F, (const T*)h->W1, F, P, HKa, F, epi, s)) return rc;
+  }
+  heads_fwd_kernel<T><<<(unsigned)ceil_div_ll(P, 4), 128, 0, s>>>(hp, params, Hl, ldl, F, w.HD, w.ldhd, out, pitch, P, false);
+  BN_LAUNCH_CHECK();
+  return BN_OK;
+}
+
+template <typename T>
+static int backward_t(bn_mlp* h, const float* params, const float* out, const float* g_out, int pitch, int N, int S,
+                      int flags, float* g, void* wsp, cudaStream_t s) {
+  const long long P = (long long)N * S;
+  const bn_mlp_cfg& c = h->cfg;
+  const int F = h->F, L = h->L;
+  Ws<T> w; carve<T>(h, P, flags, wsp, &w);
+  HeadPlan hp; int nch;
+  if (int rc = build_plan(h, flags, &hp, &nch)) return rc;
+  const T* Hl = w.H[L - 1]; const long long ldl = w.Hld[L - 1];
+  const int HKa = hp.n_blocks * h->HH;
+  heads_bwd_kernel<T><<<(unsigned)ceil_div_ll(P, 4), 128, 0, s>>>(hp, params, out, g_out, pitch, Hl, ldl, F, w.CD, w.ldhd,
+                                                               w.GHD, w.G7D, w.DPRE, w.DPRE2, P);
+  BN_LAUNCH_CHECK();
+  // second-layer weight/bias gradients of the heads, sigma and learned-normal heads (skinny reductions)
+  {
+    SkinnyPlan sp{};
+    for (int o = 0; o < hp.n_out; ++o)
+      sp.r[sp.n++] = SkinnyRow{g + hp.o[o].w_off, g + hp.o[o].b_off, o, hp.o[o].block * h->HH, (hp.o[o].block + 1) * h->HH};
+    const int bx = ceil_div(HKa, 256);
+    int by = (int)max(1LL, min(ceil_div_ll(P, 128), (long long)(148 * 4 / bx)));
+    const long long rows = ceil_div_ll(ceil_div_ll(P, by), 32) * 32;
+    by = (int)ceil_div_ll(P, rows);
+    skinny_wgrad_kernel<T><<<dim3(bx, by), 256, 0, s>>>(sp, w.DPRE, 16, w.HD, w.ldhd, HKa, P, rows);
+    BN_LAUNCH_CHECK();
+    SkinnyPlan s2{};
+    s2.r[s2.n++] = SkinnyRow{g + hp.wsig, g + hp.bsig, 0, 0, F};
+    if (hp.ch_nlr >= 0)
+      for (int o = 0; o < 3; ++o) s2.r[s2.n++] = SkinnyRow{g + hp.wg + (long long)o * F, g + hp.bg + o, 1 + o, 0, F};
+    const int bx2 = ceil_div(F, 256);
+    int by2 = (int)max(1LL, min(ceil_div_ll(P, 128), (long long)(148 * 4 / bx2)));
+    const long long rows2 = ceil_div_ll(ceil_div_ll(P, by2), 32) * 32;
+    by2 = (int)ceil_div_ll(P, rows2);
+    skinny_wgrad_kernel<T><<<dim3(bx2, by2), 256, 0, s>>>(s2, w.DPRE2, 8, Hl, ldl, F, P, rows2);
+    BN_LAUNCH_CHECK();
+  }
+  // heads' first layer: wgrad per block, bias grads, dgrad into the features
+  for (int b = 0; b < hp.n_blocks; ++b) {
+    const int lin = h->blk_lin0[b];
+    EpiWgrad ew{g + c.w_off[lin], F, h->HH, F, F, F};
+    if (int rc = gemm_nt<T>(h, w.GHD + (long long)b * h->HH, w.ldhd, w.FE, F, h->HH, F, P, ew, s)) return rc;
+    if (int rc = colsum<T>(w.GHD + (long long)b * h->HH, w.ldhd, h->HH, P, g + c.b_off[lin], s)) return rc;
+  }
+  {
+    EpiDgrad<T> ed{nullptr, 0, nullptr, 0, w.GFE, F, (int)P, F};
+    if (int rc = gemm_tn<T>(h, w.GHD, w.ldhd, (const T*)h->W1T, (long long)h->n_blocks * h->HH, P, F, HKa, ed, s)) return rc;
+  }
+  // feature layer
+  {
+    EpiWgrad ew{g + c.w_off[BN_LIN_FEATS], F, F, F, F, F};
+    if (int rc = gemm_nt<T>(h, w.GFE, F, Hl, ldl, F, F, P, ew, s)) return rc;
+    if (int rc = colsum<T>(w.GFE, F, F, P, g + c.b_off[BN_LIN_FEATS], s)) return rc;
+    EpiDgrad<T> ed{w.G7D, F, w.C[L - 1], F, w.GA, F, (int)P, F};
+    if (int rc = gemm_tn<T>(h, w.GFE, F, (const T*)h->WfT, F, P, F, F, ed, s)) return rc;
+  }
+  // trunk, last layer first.  cur = dZ_l
+  T* cur = w.GA; T* nxt = w.GB;
+  for (int l = L - 1; l >= 0; --l) {
+    const bool enc_in = (l == 0 || l == h->skip);
+    const T* In; long long ldin;
+    if (enc_in) { In = w.X3; ldin = w.ldx3; } else { In = w.H[l - 1]; ldin = w.Hld[l - 1]; }
+    EpiWgrad ew{g + c.w_off[l], h->Kreal[l], F, h->Kpad[l], enc_in ? h->E : h->Kpad[l], enc_in ? kEncPad : h->Kpad[l]};
+    if (int rc = gemm_nt<T>(h, cur, F, In, ldin, F, h->Kpad[l], P, ew, s)) return rc;
+    if (int rc = colsum<T>(cur, F, F, P, g + c.b_off[l], s)) return rc;
+    if (l > 0) {
+      const T* BT = (const T*)h->WTp[l] + (l == h->skip ? (long long)kEncPad * F : 0);
+      EpiDgrad<T> ed{nullptr, 0, w.C[l - 1], F, nxt, F, (int)P, F};
+      if (int rc = gemm_tn<T>(h, cur, F, BT, F, P, F, F, ed, s)) return rc;
+      T* t = cur; cur = nxt; nxt = t;
+    }
+  }
+  return BN_OK;
+}
+
+}  // namespace bn
+
+using namespace bn;
+
+extern "C" __attribute__((visibility("default"))) int bn_mlp_create(const bn_mlp_cfg* cfg, bn_mlp** out) {
+  BN_CHECK_ARG(cfg && out, "null pointer");
+  BN_CHECK_ARG(cfg->feat >= 128 && cfg->feat % 128 == 0 && cfg->feat <= 1024, "feat must be a multiple of 128 in [128, 1024]");
+  BN_CHECK_ARG(cfg->layers >= 2 && cfg->layers <= 16, "layers must be in [2, 16]");
+  BN_CHECK_ARG(cfg->skip_layer == -1 || (cfg->skip_layer >= 1 && cfg->skip_layer < cfg->layers), "skip_layer out of range");
+  BN_CHECK_ARG(cfg->n_freq_xyz >= 0 && cfg->n_freq_xyz <= 10, "n_freq_xyz must be in [0, 10]");
+  BN_CHECK_ARG(cfg->precision == BN_PREC_FP32 || cfg->precision == BN_PREC_BF16, "unknown precision");
+  int dev = 0;
+  BN_CUDA(cudaGetDevice(&dev));
+  if (int rc = bn_device_check(dev)) return rc;
+  bn_mlp* h = new bn_mlp();
+  memset(h, 0, sizeof(*h));
+  h->cfg = *cfg;
+  h->F = cfg->feat; h->L = cfg->layers; h->HH = cfg->feat / 2; h->skip = cfg->skip_layer;
+  h->E = cfg->n_freq_xyz == 0 ? 3 : 6 * cfg->n_freq_xyz;
+  h->bf16 = cfg->precision == BN_PREC_BF16;
+  h->es = h->bf16 ? 2 : 4;
+  cudaDeviceProp prop;
+  BN_CUDA(cudaGetDeviceProperties(&prop, dev));
+  h->num_sms = prop.multiProcessorCount;
+  // blocks of the heads' hidden layer: rgb first, then every BRDF head that exists
+  h->n_blocks = 0;
+  h->blk_lin0[0] = BN_LIN_RGB0; h->blk_lin2[0] = BN_LIN_RGB2; h->blk_head[0] = -1; h->n_blocks = 1;
+  for (int hd = 0; hd < BN_NUM_HEADS; ++hd) {
+    if (cfg->head_dim[hd] > 0) {
+      h->blk_lin0[h->n_blocks] = BN_LIN_HEAD0 + 2 * hd;
+      h->blk_lin2[h->n_blocks] = BN_LIN_HEAD0 + 2 * hd + 1;
+      h->blk_head[h->n_blocks] = hd;
+      ++h->n_blocks;
+    }
+  }
+  for (int l = 0; l < h->L; ++l) {
+    const bool enc_in = (l == 0 || l == h->skip);
+    h->Kreal[l] = l == 0 ? h->E : (l == h->skip ? h->E + h->F : h->F);
+    h->Kpad[l] = l == 0 ? kEncPad : (l == h->skip ? kEncPad + h->F : h->F);
+    (void)enc_in;
+    BN_CUDA(cudaMalloc(&h->Wp[l], (size_t)h->F * h->Kpad[l] * h->es));
+    BN_CUDA(cudaMalloc(&h->WTp[l], (size_t)h->F * h->Kpad[l] * h->es));
+  }
+  const size_t HK = (size_t)h->n_blocks * h->HH;
+  BN_CUDA(cudaMalloc(&h->Wf, (size_t)h->F * h->F * h->es));
+  BN_CUDA(cudaMalloc(&h->WfT, (size_t)h->F * h->F * h->es));
+  BN_CUDA(cudaMalloc(&h->W1, HK * h->F * h->es));
+  BN_CUDA(cudaMalloc(&h->W1T, HK * h->F * h->es));
+  BN_CUDA(cudaMalloc(&h->b1cat, HK * sizeof(float)));
+  *out = h;
+  return BN_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) void bn_mlp_destroy(bn_mlp* h) {
+  if (!h) return;
+  for (int l = 0; l < h->L; ++l) { cudaFree(h->Wp[l]); cudaFree(h->WTp[l]); }
+  cudaFree(h->Wf); cudaFree(h->WfT); cudaFree(h->W1); cudaFree(h->W1T); cudaFree(h->b1cat);
+  delete h;
+}
+
+extern "C" __attribute__((visibility("default"))) int bn_mlp_sync_weights(bn_mlp* h, const float* params, cudaStream_t stream) {
+  BN_CHECK_ARG(h && params, "null pointer");
+  return h->bf16 ? sync_weights_t<__nv_bfloat16>(h, params, stream) : sync_weights_t<float>(h, params, stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int bn_mlp_out_channels(const bn_mlp* h, int flags) {
+  if (!h) return BN_ERR_ARG;
+  if (flags & BN_MLP_SIGMA_ONLY) return 1;
+  int n = 0;
+  if (build_plan(h, flags, nullptr, &n)) return BN_ERR_ARG;
+  return n;
+}
+
+extern "C" __attribute__((visibility("default"))) size_t bn_mlp_workspace_bytes(const bn_mlp* h, int64_t n_points, int flags) {
+  if (!h || n_points <= 0) return 0;
+  return h->bf16 ? carve<__nv_bfloat16>(h, n_points, flags, nullptr, nullptr) : carve<float>(h, n_points, flags, nullptr, nullptr);
+}
+
+extern "C" __attribute__((visibility("default"))) int bn_mlp_forward(bn_mlp* h, const float* params, const float* origins, int o_stride,
+                              const float* dirs, int d_stride, const float* z, int n_rays, int n_samples,
+                              int flags, float* out, int out_pitch, void* workspace, size_t workspace_bytes,
+                              cudaStream_t stream) {
+  BN_CHECK_ARG(h && params && origins && dirs && z && out && workspace, "null pointer");
+  BN_CHECK_ARG(n_rays > 0 && n_samples > 0, "empty batch");
+  if (!h->synced) { set_error("bn_mlp_forward: call bn_mlp_sync_weights first"); return BN_ERR_STATE; }
+  if (workspace_bytes < bn_mlp_workspace_bytes(h, (int64_t)n_rays * n_samples, flags)) {
+    set_error("bn_mlp_forward: workspace too small"); return BN_ERR_STATE;
+  }
+  BN_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
+  return h->bf16 ? forward_t<__nv_bfloat16>(h, params, origins, o_stride, dirs, d_stride, z, n_rays, n_samples, flags, out, out_pitch, workspace, stream)
+                 : forward_t<float>(h, params, origins, o_stride, dirs, d_stride, z, n_rays, n_samples, flags, out, out_pitch, workspace, stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int bn_mlp_backward(bn_mlp* h, const float* params, const float* out, const float* g_out, int out_pitch,
+                               int n_rays, int n_samples, int flags, float* g_params,
+                               void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  BN_CHECK_ARG(h && params && out && g_out && g_params && workspace, "null pointer");
+  BN_CHECK_ARG(n_rays > 0 && n_samples > 0, "empty batch");
+  BN_CHECK_ARG((flags & BN_MLP_TRAIN) && !(flags & BN_MLP_SIGMA_ONLY), "backward needs a BN_MLP_TRAIN full forward");
+  if (workspace_bytes < bn_mlp_workspace_bytes(h, (int64_t)n_rays * n_samples, flags)) {
+    set_error("bn_mlp_backward: workspace too small"); return BN_ERR_STATE;
+  }
+  return h->bf16 ? backward_t<__nv_bfloat16>(h, params, out, g_out, out_pitch, n_rays, n_samples, flags, g_params, workspace, stream)
+                 : backward_t<float>(h, params, out, g_out, out_pitch, n_rays, n_samples, flags, g_params, workspace, stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int bn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                            float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                            float grad_scale, cudaStream_t stream) {
+  BN_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && n > 0 && step >= 1, "bad arguments");
+  const float bc1 = 1.0f - powf(beta1, (float)step);
+  const float bc2 = 1.0f - powf(beta2, (float)step);
+  adam_kernel<<<(unsigned)ceil_div_ll(n, 256), 256, 0, stream>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
+                                                                eps, weight_decay, bc1, sqrtf(bc2), grad_scale);
+  BN_LAUNCH_CHECK();
+  return BN_OK;
+}
+
+// Unit-test hook: run one GEMM of the MLP engine in isolation.
+//   kind 0 (TN): out[M,N] = A[M,K] B[N,K]^T            (fp32 store)
+//   kind 1 (NT): out[Mo=M, No=N] += A[P=K, M]^T B[P=K, N]  (fp32 atomics; zero `out` first)
+// precision BN_PREC_BF16 -> tcgen05 path on bf16 operands, BN_PREC_FP32 -> CUDA-core path on fp32.
+extern "C" __attribute__((visibility("default")))
+int bn_debug_gemm(int kind, int precision, const void* A, long long lda, const void* B, long long ldb,
+                  float* out, long long ldo, long long M, int N, long long K, cudaStream_t stream) {
+  BN_CHECK_ARG(A && B && out, "null pointer");
+  int dev = 0; BN_CUDA(cudaGetDevice(&dev));
+  if (int rc = bn_device_check(dev)) return rc;
+  bn_mlp h{}; cudaDeviceProp prop; BN_CUDA(cudaGetDeviceProperties(&prop, dev)); h.num_sms = prop.multiProcessorCount;
+  if (kind == 0) {
+    EpiStoreF32 epi{out, ldo, (int)M, N};
+    if (precision == BN_PREC_BF16) return gemm_tn<__nv_bfloat16>(&h, (const __nv_bfloat16*)A, lda, (const __nv_bfloat16*)B, ldb, M, N, (int)K, epi, stream);
+    return gemm_tn<float>(&h, (const float*)A, lda, (const float*)B, ldb, M, N, (int)K, epi, stream);
+  }
+  EpiWgrad epi{out, ldo, (int)M, N, N, N};
+  if (precision == BN_PREC_BF16) return gemm_nt<__nv_bfloat16>(&h, (const __nv_bfloat16*)A, lda, (const __nv_bfloat16*)B, ldb, (int)M, N, K, epi, stream);
+  return gemm_nt<float>(&h, (const float*)A, lda, (const float*)B, ldb, (int)M, N, K, epi, stream);
+}

@@ -1,0 +1,176 @@
+"""Thin Python wrappers over the C ABI: they allocate outputs with torch and enqueue the kernels on
+torch's current CUDA stream.  No arithmetic happens here."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib as L
+
+_TABLES: Dict[Tuple, Tuple[torch.Tensor, torch.Tensor]] = {}
+
+
+def sampler_tables(n: int, d_range: float, device) -> Tuple[torch.Tensor, torch.Tensor]:
+    """t_vals = linspace(0,1,n) and the (n-1)-bin Gaussian window, built with torch on the CPU exactly
+    as the reference does (rendering.py:63,68-69,151) and cached on the device; the kernels take them
+    as inputs because torch.linspace / torch.exp have their own rounding."""
+    key = (n, float(d_range), str(device))
+    if key not in _TABLES:
+        t = torch.linspace(0.0, 1.0, steps=n)
+        x = torch.linspace(-d_range, d_range, steps=n - 1)
+        g = 1.0 / math.sqrt(2 * math.pi) * torch.exp(-0.5 * x.pow(2))
+        _TABLES[key] = (t.to(device), g.to(device))
+    return _TABLES[key]
+
+
+def sample_stratified(near: torch.Tensor, far: torch.Tensor, stride: int, t_vals, u) -> torch.Tensor:
+    """near/far: 1-element-offset views into a row-major buffer read with `stride` floats per ray."""
+    n, s = u.shape
+    z = torch.empty_like(u)
+    L.check(L.load().bn_sample_stratified(C.c_void_p(near.data_ptr()), C.c_void_p(far.data_ptr()), stride,
+                                          L.ptr(t_vals), L.ptr(u), L.ptr(z), n, s, L.stream_ptr()))
+    return z
+
+
+def sample_guided(z1, depth, weights, t_vals, gauss_w, u_pred, near0, far0, d_range,
+                  valid_depth=None, gt_depth=None, gt_depth_stride=1, gt_std=None, u_gt=None, want_std=False):
+    n, s1 = z1.shape
+    g = u_pred.shape[1]
+    z2 = torch.empty((n, g), dtype=torch.float32, device=z1.device)
+    std = torch.empty(n, dtype=torch.float32, device=z1.device) if want_std else None
+    L.check(L.load().bn_sample_guided(
+        L.ptr(z1), L.ptr(depth), L.ptr(weights), L.ptr(t_vals), L.ptr(gauss_w), L.ptr(u_pred),
+        C.c_void_p(near0.data_ptr()), C.c_void_p(far0.data_ptr()), float(d_range),
+        L.ptr(valid_depth, torch.int64), None if gt_depth is None else C.c_void_p(gt_depth.data_ptr()),
+        gt_depth_stride, L.ptr(gt_std), L.ptr(u_gt), L.ptr(z2), L.ptr(std), n, s1, g, L.stream_ptr()))
+    return (z2, std) if want_std else z2
+
+
+def merge_samples(z1, z2):
+    n, s1 = z1.shape
+    g = z2.shape[1]
+    z = torch.empty((n, s1 + g), dtype=torch.float32, device=z1.device)
+    idx = torch.empty((n, s1 + g), dtype=torch.int64, device=z1.device)
+    unsort = torch.empty_like(z)
+    L.check(L.load().bn_merge_samples(L.ptr(z1), L.ptr(z2), L.ptr(z), L.ptr(idx, torch.int64), L.ptr(unsort),
+                                      n, s1, g, L.stream_ptr()))
+    return z, idx, unsort
+
+
+def sort_rows(x):
+    out = torch.empty_like(x)
+    L.check(L.load().bn_sort_rows(L.ptr(x), L.ptr(out), x.shape[0], x.shape[1], L.stream_ptr()))
+    return out
+
+
+def composite_sigma(z, sigma, noise, noise_std, want_all=False, want_std=False):
+    n, s = z.shape
+    dev = z.device
+    w = torch.empty_like(z)
+    depth = torch.empty(n, dtype=torch.float32, device=dev)
+    alpha = torch.empty_like(z) if want_all else None
+    trans = torch.empty_like(z) if want_all else None
+    std = torch.empty(n, dtype=torch.float32, device=dev) if want_std else None
+    L.check(L.load().bn_composite_sigma(L.ptr(z), L.ptr(sigma), L.ptr(noise), float(noise_std), L.ptr(alpha),
+                                        L.ptr(trans), L.ptr(w), L.ptr(depth), L.ptr(std), n, s, L.stream_ptr()))
+    return alpha, trans, w, depth, std
+
+
+def composite_forward(z, packed, noise, noise_std, irr=None):
+    n, s, c = packed.shape
+    dev = z.device
+    alpha, trans, w = torch.empty_like(z), torch.empty_like(z), torch.empty_like(z)
+    depth = torch.empty(n, dtype=torch.float32, device=dev)
+    wsum = torch.empty(n, dtype=torch.float32, device=dev)
+    acc = torch.empty((n, c), dtype=torch.float32, device=dev)
+    acc_irr = torch.empty((n, 4), dtype=torch.float32, device=dev) if irr is not None else None
+    L.check(L.load().bn_composite_forward(L.ptr(z), L.ptr(packed), c, 3, L.ptr(noise), float(noise_std), L.ptr(irr),
+                                          L.ptr(alpha), L.ptr(trans), L.ptr(w), L.ptr(depth), L.ptr(wsum), L.ptr(acc),
+                                          L.ptr(acc_irr), n, s, L.stream_ptr()))
+    return alpha, trans, w, depth, wsum, acc, acc_irr
+
+
+def composite_backward(z, packed, noise, noise_std, irr, alpha, trans, w, g_acc, g_acc_irr, g_depth, g_wsum,
+                       g_weights, g_packed_direct):
+    n, s, c = packed.shape
+    g_packed = torch.empty_like(packed)
+    L.check(L.load().bn_composite_backward(
+        L.ptr(z), L.ptr(packed), c, 3, L.ptr(noise), float(noise_std), L.ptr(irr), L.ptr(alpha), L.ptr(trans), L.ptr(w),
+        L.ptr(g_acc), L.ptr(g_acc_irr), L.ptr(g_depth), L.ptr(g_wsum), L.ptr(g_weights), L.ptr(g_packed_direct),
+        L.ptr(g_packed), n, s, L.stream_ptr()))
+    return g_packed
+
+
+def shade_rays_forward(cfg: L.ShadeCfg, rays, acc, wsum, acc_irr, irr_last, want_normal, want_brdf):
+    n = rays.shape[0]
+    dev = rays.device
+    f = lambda *sh: torch.empty(sh, dtype=torch.float32, device=dev)
+    rgb, albedo_accu = f(n, 3), f(n, 3)
+    normal_s = f(n, 3) if want_normal else None
+    nr_vw = f(n) if want_normal else None
+    nr_sun = f(n) if want_normal else None
+    hpk = f(n) if want_normal else None
+    brdf = f(n, 3) if want_brdf else None
+    aux = torch.zeros((n, 3, 8), dtype=torch.float32, device=dev) if want_brdf else None
+    L.check(L.load().bn_shade_rays_forward(C.byref(cfg), L.ptr(rays), L.ptr(acc), L.ptr(wsum), L.ptr(acc_irr),
+                                           L.ptr(irr_last), L.ptr(rgb), L.ptr(albedo_accu), L.ptr(normal_s), L.ptr(nr_vw),
+                                           L.ptr(nr_sun), L.ptr(hpk), L.ptr(brdf), L.ptr(aux), n, L.stream_ptr()))
+    return dict(rgb=rgb, albedo_accu=albedo_accu, normal_s=normal_s, nr_vw=nr_vw, nr_sun=nr_sun, hpk_scl=hpk,
+                brdf=brdf, aux=aux)
+
+
+def shade_rays_backward(cfg: L.ShadeCfg, rays, acc, wsum, acc_irr, irr_last, g_rgb):
+    n, c = acc.shape
+    dev = rays.device
+    g_acc = torch.empty((n, c), dtype=torch.float32, device=dev)
+    g_wsum = torch.empty(n, dtype=torch.float32, device=dev)
+    g_acc_irr = torch.zeros((n, 4), dtype=torch.float32, device=dev) if acc_irr is not None else None
+    L.check(L.load().bn_shade_rays_backward(C.byref(cfg), L.ptr(rays), L.ptr(acc), L.ptr(wsum), L.ptr(acc_irr),
+                                            L.ptr(irr_last), L.ptr(g_rgb), L.ptr(g_acc), L.ptr(g_wsum), L.ptr(g_acc_irr),
+                                            n, L.stream_ptr()))
+    return g_acc, g_wsum, g_acc_irr
+
+
+def brdf_points_forward(cfg: L.ShadeCfg, rays, packed, want_aux=False):
+    n, s, _ = packed.shape
+    aux = torch.zeros((n, s, 3, 8), dtype=torch.float32, device=rays.device) if want_aux else None
+    L.check(L.load().bn_brdf_points_forward(C.byref(cfg), L.ptr(rays), L.ptr(packed), L.ptr(aux), n, s, L.stream_ptr()))
+    return aux
+
+
+def brdf_points_backward(cfg: L.ShadeCfg, rays, packed, g_packed):
+    n, s, _ = packed.shape
+    L.check(L.load().bn_brdf_points_backward(C.byref(cfg), L.ptr(rays), L.ptr(packed), L.ptr(g_packed), n, s, L.stream_ptr()))
+
+
+def mlp_forward(model, origins, o_stride, dirs, d_stride, z, flags, out, pitch, ws):
+    """origins / dirs: tensors whose data_ptr is the first coordinate of ray 0."""
+    n, s = z.shape
+    L.check(L.load().bn_mlp_forward(model.handle(), L.ptr(model.flat_params), C.c_void_p(origins.data_ptr()), o_stride,
+                                    C.c_void_p(dirs.data_ptr()), d_stride, L.ptr(z), n, s, flags, L.ptr(out), pitch,
+                                    C.c_void_p(ws.data_ptr()), ws.numel(), L.stream_ptr()))
+
+
+def mlp_backward(model, out, g_out, pitch, n, s, flags, g_params, ws):
+    L.check(L.load().bn_mlp_backward(model.handle(), L.ptr(model.flat_params), L.ptr(out), L.ptr(g_out), pitch, n, s, flags,
+                                     L.ptr(g_params), C.c_void_p(ws.data_ptr()), ws.numel(), L.stream_ptr()))
+
+
+def mlp_normals_forward(model, out, pitch, n, s, flags, ws):
+    L.check(L.load().bn_mlp_normals_forward(model.handle(), L.ptr(model.flat_params), L.ptr(out), pitch, n, s, flags, 4,
+                                            C.c_void_p(ws.data_ptr()), ws.numel(), L.stream_ptr()))
+
+
+def mlp_normals_backward(model, out, g_out, pitch, n, s, flags, g_params, ws):
+    L.check(L.load().bn_mlp_normals_backward(model.handle(), L.ptr(model.flat_params), L.ptr(out), L.ptr(g_out), pitch, n, s,
+                                             flags, 4, L.ptr(g_params), C.c_void_p(ws.data_ptr()), ws.numel(),
+                                             L.stream_ptr()))
+
+
+def adam_step(params, grads, m, v, lr, step, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_scale=1.0):
+    L.check(L.load().bn_adam_step(L.ptr(params), L.ptr(grads), L.ptr(m), L.ptr(v), params.numel(), float(lr),
+                                  float(betas[0]), float(betas[1]), float(eps), float(weight_decay), int(step),
+                                  float(grad_scale), L.stream_ptr()))

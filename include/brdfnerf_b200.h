@@ -1,0 +1,240 @@
+/* brdfnerf_b200 — C ABI of the B200-native (sm_100a) BRDF-NeRF ray-rendering hot path.
+ *
+ * Drop-in boundary for the reference's `rendering.render_rays` (rendering.py:168-334) and the
+ * `models/spsbrdfnerf.py` forward/backward.  The reference is pure Python/PyTorch and has no FFI of
+ * its own; each entry point below names the reference function (file:line under /root/reference)
+ * whose arithmetic it replaces.  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless stated otherwise; the caller owns all memory
+ *     (inputs, outputs, workspaces); the library never allocates or frees caller tensors;
+ *   - all work is enqueued on `stream`; no entry point synchronises or reads device memory on the
+ *     host, so a whole render / training step is CUDA-graph capturable;
+ *   - return value: BN_OK (0) or a negative bn_status; `bn_last_error()` returns a thread-local
+ *     human readable message for the last failure on the calling thread;
+ *   - the library refuses to run on anything but compute capability 10.x (no fallback path).
+ */
+#ifndef BRDFNERF_B200_H_
+#define BRDFNERF_B200_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+#define BN_ABI_VERSION 1
+
+typedef enum bn_status {
+  BN_OK = 0,
+  BN_ERR_ARG = -1,      /* invalid argument (null pointer, size out of range, unsupported config) */
+  BN_ERR_CUDA = -2,     /* a CUDA runtime / driver call failed */
+  BN_ERR_DEVICE = -3,   /* not a compute-capability 10.x device */
+  BN_ERR_STATE = -4     /* handle used before weights were set, workspace too small, ... */
+} bn_status;
+
+int bn_abi_version(void);
+const char* bn_last_error(void);
+/* BN_OK iff device `device` is sm_100-class. Host-only query. */
+int bn_device_check(int device);
+
+/* ------------------------------------------------------------------ K-A  sample generators */
+
+/* get_z_vals (rendering.py:149-166, perturb == 1): z = lower + (upper-lower)*u over the strata of
+ * near*(1-t)+far*t.  near/far are read as near_p[r*stride], far_p[r*stride] (pass &rays[0][6],
+ * &rays[0][7], 11 for a ray record).  t_vals = torch.linspace(0,1,S) (S floats), u (N,S) uniform
+ * draws, z_out (N,S).  Bit-exact against the reference's torch-CPU result. */
+int bn_sample_stratified(const float* near_p, const float* far_p, int stride,
+                         const float* t_vals, const float* u, float* z_out,
+                         int n_rays, int n_samples, cudaStream_t stream);
+
+/* GenerateGuidedSamples (rendering.py:132-147) = calc_depth_std (train_utils.py:35-39) +
+ * compute_samples_around_depth (rendering.py:116-130) + sample_3sigma_asym (:76-91) +
+ * sample_3sigma (:54-74) + sample_pdf (:13-52) + sort, one warp per ray.
+ *   z1, weights (N,S1), depth (N): pass-1 results; t_vals (G) and gauss_w (G-1): host-built tables
+ *   (torch.linspace / Gaussian window of rendering.py:63,68-69); u_pred (N,G) uniform draws;
+ *   near0/far0: device pointers to the chunk clamp scalars (reference uses ray 0's near/far);
+ *   valid_depth (N) int64 or NULL: rows > 0 sample around gt_depth[r*gt_depth_stride] +-
+ *   d_range*gt_std[r] with draws u_gt[r] instead (mask form of the reference's np.where scatter);
+ *   z2_out (N,G) ascending; std_out (N) optional sampling std of pass 1. */
+int bn_sample_guided(const float* z1, const float* depth, const float* weights,
+                     const float* t_vals, const float* gauss_w, const float* u_pred,
+                     const float* near0, const float* far0, float d_range,
+                     const int64_t* valid_depth, const float* gt_depth, int gt_depth_stride,
+                     const float* gt_std, const float* u_gt,
+                     float* z2_out, float* std_out,
+                     int n_rays, int n_samples, int n_guided, cudaStream_t stream);
+
+/* cat + sort with indices (rendering.py:271-272): z_out (N,S1+G) ascending, idx_out int64 source
+ * positions in [z1|z2] (stable on ties), unsort_out = [z1|z2] (both optional). */
+int bn_merge_samples(const float* z1, const float* z2, float* z_out, int64_t* idx_out,
+                     float* unsort_out, int n_rays, int n_samples, int n_guided, cudaStream_t stream);
+
+/* per-row ascending sort (rendering.py:263). */
+int bn_sort_rows(const float* in, float* out, int n_rays, int n, cudaStream_t stream);
+
+/* ------------------------------------------------------------------ K-C  compositing */
+
+/* cal_weight (spsbrdfnerf.py:50-69) for the sigma-only pass: alpha/trans optional outputs,
+ * weights (N,S), depth (N), std_out optional = calc_depth_std. noise may be NULL. */
+int bn_composite_sigma(const float* z, const float* sigma, const float* noise, float noise_std,
+                       float* alpha, float* trans, float* weights, float* depth, float* std_out,
+                       int n_rays, int n_samples, cudaStream_t stream);
+
+/* cal_weight + every weighted accumulation of `inference` (spsbrdfnerf.py:196-199,242,270-275,
+ * 292,314-317,326-338).  packed (N,S,C) is the MLP's packed per-sample output in the reference's
+ * channel order [albedo(3), sigma, normal_an(3)?, normal_lr(3)?, brdf params...]; acc (N,C) receives
+ * sum_s w*packed (channel 3 is meaningless), wsum (N) = sum_s w.  irr (N,S) optional per-sample
+ * irradiance scalar (sun visibility) -> acc_irr (N,3) = sum_s w*irr*albedo. */
+int bn_composite_forward(const float* z, const float* packed, int n_channels, int sigma_channel,
+                         const float* noise, float noise_std, const float* irr,
+                         float* alpha, float* trans, float* weights,
+                         float* depth, float* wsum, float* acc, float* acc_irr,
+                         int n_rays, int n_samples, cudaStream_t stream);
+
+/* backward of bn_composite_forward: given grads w.r.t. acc / acc_irr / depth / wsum (per ray),
+ * weights (per sample, optional) and optionally direct grads w.r.t. packed, writes g_packed
+ * (N,S,C) (channel 3 = d loss / d sigma). */
+int bn_composite_backward(const float* z, const float* packed, int n_channels, int sigma_channel,
+                          const float* noise, float noise_std, const float* irr,
+                          const float* alpha, const float* trans, const float* weights,
+                          const float* g_acc, const float* g_acc_irr, const float* g_depth,
+                          const float* g_wsum, const float* g_weights, const float* g_packed_direct,
+                          float* g_packed, int n_rays, int n_samples, cudaStream_t stream);
+
+/* ------------------------------------------------------------------ K-C  shading / BRDF */
+
+enum { BN_BRDF_NONE = 0, BN_BRDF_MICROFACET = 1, BN_BRDF_RPV = 2, BN_BRDF_HAPKE = 3 };
+enum { BN_IRR_ONES = 0, BN_IRR_COS = 1, BN_IRR_SUNVIS = 2 };
+
+/* Which channels of a packed row mean what, and which BRDF is active for this call
+ * (mirrors the switches `inference` reads: spsbrdfnerf.py:104-116,144-190,286-346). */
+typedef struct bn_shade_cfg {
+  int n_channels;      /* C of packed / acc rows */
+  int normal_ch;       /* first channel of the normal used for shading (learned wins), -1 = none */
+  int param_ch;        /* first BRDF-parameter channel, -1 = none */
+  int brdf_ch;         /* MultiBRDF: first of 3 per-sample brdf channels appended to the row, else -1 */
+  int brdf_type;       /* BN_BRDF_* active for this call (NONE when apply_brdf is off) */
+  int funcM, funcF, funcH;                         /* RPV factors; funcH == 2: rhoc = albedo */
+  int hapke_b, hapke_c, hapke_theta, shell_hapke;  /* Hapke parameters present in the row */
+  int multi_brdf;      /* one BRDF per sample instead of one per ray */
+  int irr_mode;        /* BN_IRR_* */
+  float hpk_scl, fresnel_f0;
+} bn_shade_cfg;
+
+/* Per-ray epilogue of `inference` (spsbrdfnerf.py:198-199,241-275,284-357): from the accumulations
+ * of bn_composite_forward to albedo_accu, rgb, normal_s, nr_vw, nr_sun, hpk_scl and the per-ray BRDF
+ * (calc_angles + RPV.py / Hapke.py / microfacet.py).  Optional outputs may be NULL.
+ * brdf (N,3); aux (N,3,8) per colour channel: RPV [M1,G,H,ci,cv], Hapke [P,Hi,Hv,ci,cv,S],
+ * microfacet [glossy,f,g,d,l.n,v.n,n.h]. irr_last (N): irradiance of the last sample (sun-vis). */
+int bn_shade_rays_forward(const bn_shade_cfg* cfg, const float* rays, const float* acc,
+                          const float* wsum, const float* acc_irr, const float* irr_last,
+                          float* rgb, float* albedo_accu, float* normal_s, float* nr_vw,
+                          float* nr_sun, float* hpk_scl, float* brdf, float* aux,
+                          int n_rays, cudaStream_t stream);
+
+/* d loss / d rgb (N,3)  ->  d loss / d {acc (N,C), wsum (N), acc_irr (N,4)}. */
+int bn_shade_rays_backward(const bn_shade_cfg* cfg, const float* rays, const float* acc,
+                           const float* wsum, const float* acc_irr, const float* irr_last,
+                           const float* g_rgb, float* g_acc, float* g_wsum, float* g_acc_irr,
+                           int n_rays, cudaStream_t stream);
+
+/* MultiBRDF (spsbrdfnerf.py:289-290,297-307,343-344): one BRDF per sample, written into channels
+ * brdf_ch..brdf_ch+2 of the packed rows; backward folds d/d brdf into the other channels' grads. */
+int bn_brdf_points_forward(const bn_shade_cfg* cfg, const float* rays, float* packed, float* aux,
+                           int n_rays, int n_samples, cudaStream_t stream);
+int bn_brdf_points_backward(const bn_shade_cfg* cfg, const float* rays, const float* packed,
+                            float* g_packed, int n_rays, int n_samples, cudaStream_t stream);
+
+/* ------------------------------------------------------------------ K-B  PE + SIREN MLP */
+
+enum { BN_PREC_FP32 = 0,   /* CUDA-core fp32 everywhere: parity mode (<= 1e-3 against the fp32 oracle) */
+       BN_PREC_BF16 = 1 }; /* tcgen05 bf16 operands / fp32 TMEM accumulation: throughput mode */
+
+/* linear-layer ids used to address weights/biases inside the caller's flat fp32 parameter buffer
+ * (state_dict names of the reference: spsbrdfnerf.py:513-613) */
+enum {
+  BN_LIN_TRUNK0 = 0,        /* fc_net.{2l}           l = 0..15 */
+  BN_LIN_SIGMA = 16,        /* sigma_from_xyz.0 */
+  BN_LIN_FEATS = 17,        /* feats_from_xyz */
+  BN_LIN_RGB0 = 18,         /* rgb_from_xyzdir.0 */
+  BN_LIN_RGB2 = 19,         /* rgb_from_xyzdir.2 */
+  BN_LIN_GRAD = 20,         /* grad_from_xyz (learned normal) */
+  BN_LIN_HEAD0 = 21,        /* head h: 21+2h = {name}.0, 22+2h = {name}.2 */
+  BN_NUM_LINEAR = 35
+};
+/* optional BRDF heads, in the reference's output-channel order */
+enum { BN_HEAD_ROUGH = 0, BN_HEAD_K = 1, BN_HEAD_THETA_RPV = 2, BN_HEAD_RHOC = 3,
+       BN_HEAD_B = 4, BN_HEAD_C = 5, BN_HEAD_THETA = 6, BN_NUM_HEADS = 7 };
+
+typedef struct bn_mlp_cfg {
+  int feat;               /* fc_feat (multiple of 64; 512 in the reference recipe) */
+  int layers;             /* fc_layers (<= 16) */
+  int skip_layer;         /* layer whose input is [PE | h], -1 = none (reference: 4) */
+  int n_freq_xyz;         /* positional-encoding frequencies, 0 = raw xyz (no --mapping) */
+  int normal_lr;          /* grad_from_xyz head exists */
+  int head_dim[BN_NUM_HEADS];   /* output width of each BRDF head that exists (0 = absent) */
+  int precision;          /* BN_PREC_* */
+  int64_t w_off[BN_NUM_LINEAR]; /* element offset of each weight / bias in the flat buffer, -1 = absent */
+  int64_t b_off[BN_NUM_LINEAR];
+  int64_t n_params;       /* total elements of the flat buffer */
+} bn_mlp_cfg;
+
+typedef struct bn_mlp bn_mlp;   /* opaque: config + packed (bf16 / transposed) weight copies */
+
+/* flags of one MLP evaluation (what `SpSBRDFNeRF.forward` is asked for, spsbrdfnerf.py:662) */
+enum {
+  BN_MLP_SIGMA_ONLY = 1,   /* sigma_only=True: out is (P) densities */
+  BN_MLP_TRAIN = 2,        /* keep activations for bn_mlp_backward */
+  BN_MLP_NORMAL_AN = 4,    /* nr_an_on: analytic normal -l2n(d sigma / d x) */
+  BN_MLP_NORMAL_LR = 8,    /* nr_lr_on */
+  BN_MLP_ROUGH = 16,       /* evaluate the roughness head (microfacet, apply_brdf) */
+  BN_MLP_RPV = 32,         /* evaluate k / theta_rpv / rhoc heads that exist */
+  BN_MLP_HAPKE = 64,       /* evaluate b / c heads that exist */
+  BN_MLP_HAPKE_THETA = 128 /* ... and the Hapke theta head (apply_theta) */
+};
+
+int bn_mlp_create(const bn_mlp_cfg* cfg, bn_mlp** out);
+void bn_mlp_destroy(bn_mlp* h);
+/* refresh the packed weight copies from the flat fp32 master (after every optimizer step) */
+int bn_mlp_sync_weights(bn_mlp* h, const float* params, cudaStream_t stream);
+/* number of packed output channels for `flags` (4 + normals + BRDF parameters) */
+int bn_mlp_out_channels(const bn_mlp* h, int flags);
+size_t bn_mlp_workspace_bytes(const bn_mlp* h, int64_t n_points, int flags);
+
+/* PE (nerf.py:53-70) + trunk (spsbrdfnerf.py:636-646) + heads (:682-755) for the points
+ * x = origin[r] + dir[r] * z[r][s].  origins/dirs are read as origins[r*o_stride + {0,1,2}].
+ * out: (P) sigma when BN_MLP_SIGMA_ONLY, else packed rows (P, out_pitch >= out_channels) in the
+ * reference's channel order. */
+int bn_mlp_forward(bn_mlp* h, const float* params, const float* origins, int o_stride,
+                   const float* dirs, int d_stride, const float* z, int n_rays, int n_samples,
+                   int flags, float* out, int out_pitch, void* workspace, size_t workspace_bytes,
+                   cudaStream_t stream);
+
+/* backward of the last BN_MLP_TRAIN forward on `workspace`: `out` is that forward's packed output,
+ * g_out (P, out_pitch) its gradient -> g_params (flat fp32, ACCUMULATED: zero it at the start of a
+ * step; it is the allreduce bucket). */
+int bn_mlp_backward(bn_mlp* h, const float* params, const float* out, const float* g_out, int out_pitch,
+                    int n_rays, int n_samples, int flags, float* g_params,
+                    void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+/* fused Adam on the flat buffers (torch.optim.Adam semantics, main.py:150): one launch per step */
+int bn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                 float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                 float grad_scale, cudaStream_t stream);
+
+/* Unit-test hook: one GEMM of the MLP engine in isolation (kind 0: out[M,N] = A[M,K] B[N,K]^T;
+ * kind 1: out[M,N] += A[K,M]^T B[K,N], fp32 atomics). precision selects tcgen05 (bf16 operands)
+ * or CUDA cores (fp32 operands). */
+int bn_debug_gemm(int kind, int precision, const void* A, long long lda, const void* B, long long ldb,
+                  float* out, long long ldo, long long M, int N, long long K, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BRDFNERF_B200_H_ */

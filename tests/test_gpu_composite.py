@@ -1,0 +1,69 @@
+"""K-C parity: compositing forward/backward vs the torch oracle (tolerance 1e-5 abs, fp32)."""
+import pytest
+import torch
+
+from brdf_nerf_b200 import ops
+from oracle import render_torch as RT
+
+pytestmark = pytest.mark.gpu
+
+
+def _inputs(n, s, c, seed):
+    g = torch.Generator().manual_seed(seed)
+    z = torch.sort(torch.rand(n, s, generator=g) * 0.6, -1)[0]
+    packed = torch.rand(n, s, c, generator=g)
+    packed[..., 3] = torch.randn(n, s, generator=g) * 4 + 1      # density (relu'd inside)
+    noise = torch.randn(n, s, generator=g)
+    return z, packed, noise
+
+
+@pytest.mark.parametrize("n,s", [(1, 64), (130, 64), (37, 128), (5, 100), (3, 1)])
+def test_composite_sigma(cuda, n, s):
+    z, packed, noise = _inputs(n, s, 4, 3)
+    sig = packed[..., 3].contiguous()
+    a, T, w, d = RT.volume_weights(z, sig, noise, 0.3)
+    ga, gT, gw, gd, gstd = ops.composite_sigma(z.to(cuda), sig.to(cuda), noise.to(cuda), 0.3, want_all=True, want_std=True)
+    for x, y in ((a, ga), (T, gT), (w, gw), (d, gd)):
+        assert torch.allclose(x, y.cpu(), atol=2e-6, rtol=1e-5)
+    std = torch.sqrt((((z - d[:, None]) ** 2) * w).sum(-1))
+    assert torch.allclose(std, gstd.cpu(), atol=1e-5)
+
+
+@pytest.mark.parametrize("n,s,c,noise_std,with_irr", [(64, 128, 4, 0.0, False), (33, 128, 16, 0.2, False),
+                                                      (17, 64, 7, 0.0, True), (9, 96, 13, 0.0, False), (4, 128, 19, 0.0, False)])
+def test_composite_forward_backward(cuda, n, s, c, noise_std, with_irr):
+    z, packed, noise = _inputs(n, s, c, 11)
+    g = torch.Generator().manual_seed(5)
+    irr = torch.rand(n, s, generator=g) if with_irr else None
+    packed_r = packed.clone().requires_grad_(True)
+    a, T, w, d = RT.volume_weights(z, packed_r[..., 3], noise, noise_std)
+    acc = (w.unsqueeze(-1) * packed_r).sum(1)
+    wsum = w.sum(-1)
+    outs = ops.composite_forward(z.to(cuda), packed.to(cuda), noise.to(cuda) if noise_std else None, noise_std,
+                                 irr.to(cuda) if with_irr else None)
+    ga, gT, gw, gd, gws, gacc, gacc_irr = outs
+    mask = torch.ones(c, dtype=torch.bool); mask[3] = False
+    assert torch.allclose(a, ga.cpu(), atol=2e-6) and torch.allclose(T, gT.cpu(), atol=2e-6)
+    assert torch.allclose(w, gw.cpu(), atol=2e-6) and torch.allclose(d, gd.cpu(), atol=2e-6)
+    assert torch.allclose(wsum, gws.cpu(), atol=2e-6)
+    assert torch.allclose(acc[:, mask], gacc.cpu()[:, mask], atol=5e-6)
+    loss_terms = []
+    G_acc, G_d, G_ws, G_w = torch.randn(n, c, generator=g), torch.randn(n, generator=g), torch.randn(n, generator=g), torch.randn(n, s, generator=g)
+    G_acc[:, 3] = 0
+    G_direct = torch.randn(n, s, c, generator=g)
+    loss = (acc * G_acc).sum() + (d * G_d).sum() + (wsum * G_ws).sum() + (w * G_w).sum() + (packed_r * G_direct).sum()
+    G_irr = None
+    if with_irr:
+        acc_irr = torch.cat([(w.unsqueeze(-1) * irr.unsqueeze(-1) * packed_r[..., :3]).sum(1), (w * irr).sum(-1, keepdim=True)], -1)
+        assert torch.allclose(acc_irr, gacc_irr.cpu(), atol=5e-6)
+        G_irr = torch.randn(n, 4, generator=g)
+        loss = loss + (acc_irr * G_irr).sum()
+    loss.backward()
+    gp = ops.composite_backward(z.to(cuda), packed.to(cuda), noise.to(cuda) if noise_std else None, noise_std,
+                                irr.to(cuda) if with_irr else None, ga, gT, gw, G_acc.to(cuda),
+                                G_irr.to(cuda) if with_irr else None, G_d.to(cuda), G_ws.to(cuda), G_w.to(cuda),
+                                G_direct.to(cuda))
+    ref = packed_r.grad
+    err = (gp.cpu() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= 2e-5 * max(1.0, scale), f"composite backward max err {err} (scale {scale})"

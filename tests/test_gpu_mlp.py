@@ -1,0 +1,111 @@
+"""K-B parity: PE + SIREN MLP forward / backward vs the torch oracle.
+fp32 mode: <= 1e-3 abs (north-star tolerance; observed ~1e-5).  bf16 (tcgen05) mode: loose check
+against the fp32 mode — its acceptance criterion is the PSNR-drift test in test_gpu_train.py."""
+import pytest
+import torch
+
+from brdf_nerf_b200.config import named_config
+from brdf_nerf_b200.models import load_model
+from oracle import render_torch as RT
+
+pytestmark = pytest.mark.gpu
+
+
+def _models(cfg, cuda, precision="fp32", **over):
+    args = named_config(cfg, **over)
+    torch.manual_seed(0)
+    m = load_model(args, precision=precision)
+    state = {k: v.clone() for k, v in m.state_dict().items()}
+    m = m.to(cuda)
+    return args, m, state
+
+
+def _pts(n, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand(n, 3, generator=g) * 1.6 - 0.8
+
+
+@pytest.mark.parametrize("cfg,kw", [("lambertian", {}), ("rpv111", dict(apply_brdf=True)),
+                                    ("hapke_bct", dict(apply_brdf=True, apply_theta=True)),
+                                    ("microfacet", dict(apply_brdf=True)), ("rpv111_multi", dict(apply_brdf=True))])
+def test_forward_fp32(cuda, cfg, kw):
+    args, m, state = _models(cfg, cuda, normal="none")
+    x = _pts(777)
+    om = RT.OracleModel(state, args)
+    with torch.no_grad():
+        ref = om.forward(x, **kw)
+        sig = m(x.to(cuda), sigma_only=True).cpu()
+        out = m(x.to(cuda), **kw).cpu()
+    assert torch.allclose(sig, ref["sigma"], atol=1e-4), (sig - ref["sigma"]).abs().max()
+    cols = [ref["albedo"], ref["sigma"]]
+    for k in ("roughness", "rpv_k", "rpv_theta", "rpv_rhoc", "hpk_b", "hpk_c", "hpk_theta"):
+        if k in ref:
+            cols.append(ref[k])
+    want = torch.cat(cols, -1)
+    assert out.shape == want.shape, (out.shape, want.shape)
+    err = (out - want).abs().max().item()
+    assert err < 1e-4, f"{cfg}: packed output max err {err}"
+
+
+def test_forward_learned_normal_fp32(cuda):
+    args, m, state = _models("rpv111", cuda, normal="learned")
+    x = _pts(300, 2)
+    om = RT.OracleModel(state, args)
+    with torch.no_grad():
+        ref = om.forward(x, nr_lr=True, apply_brdf=True)
+        out = m(x.to(cuda), nr_lr_on=True, apply_brdf=True).cpu()
+    want = torch.cat([ref["albedo"], ref["sigma"], ref["normal_lr"], ref["rpv_k"], ref["rpv_theta"], ref["rpv_rhoc"]], -1)
+    assert (out - want).abs().max().item() < 2e-4
+
+
+@pytest.mark.parametrize("cfg,kw", [("lambertian", {}), ("rpv111", dict(apply_brdf=True)),
+                                    ("hapke_bct", dict(apply_brdf=True, apply_theta=True))])
+def test_backward_fp32(cuda, cfg, kw):
+    args, m, state = _models(cfg, cuda, normal="none")
+    x = _pts(513, 4)
+    om = RT.OracleModel(state, args, requires_grad=True)
+    ref = om.forward(x, **kw)
+    cols = [ref["albedo"], ref["sigma"]] + [ref[k] for k in ("rpv_k", "rpv_theta", "rpv_rhoc", "hpk_b", "hpk_c", "hpk_theta") if k in ref]
+    want = torch.cat(cols, -1)
+    G = torch.randn(want.shape, generator=torch.Generator().manual_seed(8))
+    (want * G).sum().backward()
+    out = m(x.to(cuda), **kw)
+    (out * G.to(cuda)).sum().backward()
+    worst = 0.0
+    for name, p in m.named_parameters():
+        r = om.p[name].grad
+        if r is None:
+            assert p.grad is None or p.grad.abs().max().item() == 0.0, name
+            continue
+        d = (p.grad.cpu() - r).abs().max().item()
+        s = r.abs().max().item()
+        worst = max(worst, d / (s + 1e-12))
+        assert d <= 2e-3 * s + 1e-6, f"{cfg} grad {name}: max diff {d} (scale {s})"
+    print(f"{cfg}: worst relative grad error {worst:.2e}")
+
+
+def test_bf16_tcgen05_close_to_fp32(cuda):
+    args, m32, state = _models("rpv111", cuda, normal="none")
+    _, m16, _ = _models("rpv111", cuda, precision="bf16", normal="none")
+    x = _pts(2000, 6).to(cuda)
+    with torch.no_grad():
+        a = m32(x, apply_brdf=True)
+        b = m16(x, apply_brdf=True)
+    err = (a - b).abs().max().item()
+    print("bf16 vs fp32 packed max abs diff", err, "mean", (a - b).abs().mean().item())
+    assert err < 0.15 and (a - b).abs().mean().item() < 0.02
+
+
+def test_bf16_backward_direction(cuda):
+    """Gradient of the bf16 path points the same way as the fp32 gradient (cosine > 0.98)."""
+    args, m32, state = _models("lambertian", cuda, normal="none")
+    _, m16, _ = _models("lambertian", cuda, precision="bf16", normal="none")
+    x = _pts(4096, 7).to(cuda)
+    G = torch.randn(4096, 4, generator=torch.Generator().manual_seed(1)).to(cuda)
+    for m in (m32, m16):
+        m.flat_grads.zero_()
+        (m(x) * G).sum().backward()
+    a, b = m32.flat_grads, m16.flat_grads
+    cos = torch.nn.functional.cosine_similarity(a, b, dim=0).item()
+    print("bf16 vs fp32 gradient cosine", cos)
+    assert cos > 0.98

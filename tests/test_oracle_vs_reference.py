@@ -1,0 +1,80 @@
+"""CPU, only where the reference tree is mounted: pin the oracle against the LIVE reference
+(forward bit-exactness of the sampler, result keys, gradients incl. the second-order normal path)."""
+import contextlib
+import io
+
+import pytest
+import torch
+
+from brdf_nerf_b200.config import named_config
+from brdf_nerf_b200.synth import make_rays
+from oracle import losses_torch as LT
+from oracle import ref_harness as RH
+from oracle import render_torch as RT
+
+pytestmark = pytest.mark.skipif(not RH.available(), reason="reference tree not mounted (GPU box)")
+
+
+def _run(cfg, n=40, mode="test", ds=False, **kw):
+    args = named_config(cfg)
+    ref_model = RH.build_model(args)
+    batch = make_rays(n, depth_supervision=ds)
+    S1, G = args.n_samples, args.guided_samples
+    S = G if kw.get("gsam_only") else S1 + G
+    draws = RT.Draws.make(n, S1, G, S, seed=77, with_gt=ds, with_sun=bool(kw.get("bTestSun_v")), s_sun=G if kw.get("gsam_only") else S1)
+    extra = dict(valid_depth=batch.valid_depth, target_depths=batch.target_depths, target_std=batch.target_std) if ds else {}
+    train = mode == "train"
+    ctx = torch.enable_grad() if train else torch.no_grad()
+    with ctx:
+        ref, bt = RH.render(ref_model, args, batch.rays, draws, mode=mode, **extra, **kw)
+        om = RT.OracleModel(ref_model.state_dict(), args, requires_grad=train)
+        ora, bt2, _ = RT.render_rays(om, args, batch.rays, draws, mode=mode, **extra, **kw)
+    return args, ref_model, om, batch, ref, ora, bt, bt2
+
+
+@pytest.mark.parametrize("cfg,kw", [
+    ("lambertian", {}), ("lambertian", dict(gsam_only=True)),
+    ("rpv111", dict(apply_brdf=True, cos_irra_on=True)), ("rpv111", dict(apply_brdf=False)),
+    ("rpv111_multi", dict(apply_brdf=True, cos_irra_on=True)),
+    ("hapke_bct", dict(apply_brdf=True, apply_theta=True, cos_irra_on=True)), ("hapke_b", dict(apply_brdf=True)),
+    ("microfacet", dict(apply_brdf=True, cos_irra_on=True)),
+    ("rpv111", dict(apply_brdf=True, cos_irra_on=True, bTestSun_v=True)),
+])
+def test_forward_keys_and_values(cfg, kw):
+    _, _, _, _, ref, ora, bt, bt2 = _run(cfg, **kw)
+    assert bt == bt2
+    assert set(ref) == set(ora), set(ref) ^ set(ora)
+    for k in ref:
+        assert ref[k].shape == ora[k].shape, k
+        if ref[k].dtype == torch.int64:
+            assert torch.equal(ref[k], ora[k]), k
+        elif k.startswith("z_vals"):
+            assert torch.equal(ref[k], ora[k]), f"{k} not bit-exact"
+        else:
+            assert (ref[k] - ora[k]).abs().max().item() <= 2e-6, k
+
+
+@pytest.mark.parametrize("cfg,ds,kw", [("lambertian_ds", True, {}), ("rpv111", False, dict(apply_brdf=True, cos_irra_on=True)),
+                                       ("hapke_bct", False, dict(apply_brdf=True, apply_theta=True, cos_irra_on=True))])
+def test_gradients(cfg, ds, kw):
+    args, ref_model, om, batch, ref, ora, _, _ = _run(cfg, n=24, mode="train", ds=ds, **kw)
+    _, _, M = RH.load()
+    with contextlib.redirect_stdout(io.StringIO()):
+        loss_r, _ = M.SNerfLoss(lambda_sc=0., lambda_rgb=args.lambda_rgb)(ref, batch.rgbs)
+        if ds:
+            dl = M.DepthLoss(lambda_ds=args.ds_lambda, GNLL=False, usealldepth=False, margin=args.margin,
+                             stdscale=args.stdscale, subset=True)
+            l2, _ = dl(ref, batch.target_depths[:, 0], batch.target_depths[:, 1], target_valid_depth=batch.valid_depth,
+                       target_std=batch.target_std)
+            loss_r = loss_r + l2
+    loss_r.backward()
+    loss_o = LT.train_loss(ora, batch, args)
+    loss_o.backward()
+    assert abs(loss_r.item() - loss_o.item()) <= 1e-6
+    for name, p in ref_model.named_parameters():
+        go = om.p[name].grad
+        if p.grad is None:
+            assert go is None or go.abs().max() == 0
+            continue
+        s = p.grad.abs().max().item()
+        assert (p.grad - go).abs().max().item() <= 1e-3 * s + 1e-9, name
