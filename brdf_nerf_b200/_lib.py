@@ -43,6 +43,9 @@ _SIGS = {
     "bn_abi_version": (C.c_int, []),
     "bn_last_error": (C.c_char_p, []),
     "bn_device_check": (C.c_int, [_I]),
+    "bn_launch_count": (C.c_ulonglong, []),
+    "bn_profile_enable": (C.c_int, [_I]),
+    "bn_profile_collect": (C.c_int, [_I, _P, _P, _P]),
     "bn_sample_stratified": (C.c_int, [_P, _P, _I, _P, _P, _P, _I, _I, _P]),
     "bn_sample_guided": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _F, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _P]),
     "bn_merge_samples": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),

@@ -13,12 +13,11 @@ class PointsFunction(torch.autograd.Function):
     A point is evaluated as a one-sample ray with origin x and z = 0 (x + d*0 is exact)."""
 
     @staticmethod
-    def forward(ctx, model, xyz, sigma_only, apply_brdf, apply_theta, nr_an_on, nr_lr_on, *params):
+    def forward(ctx, model, xyz, sigma_only, apply_brdf, apply_theta, nr_an_on, nr_lr_on, need_grad, *params):
         if not xyz.is_cuda:
             raise L.BnError("SpSBRDFNeRF.forward needs CUDA tensors: there is no CPU path")
         xyz = xyz.detach().float().contiguous()
         B = xyz.shape[0]
-        need_grad = any(p.requires_grad for p in params) and torch.is_grad_enabled()
         model.sync_weights()
         z = torch.zeros((B, 1), dtype=torch.float32, device=xyz.device)
         full_for_grad = sigma_only and need_grad
@@ -58,4 +57,4 @@ class PointsFunction(torch.autograd.Function):
             m = p.numel()
             grads.append(flat[off:off + m].view(p.shape) if p.requires_grad else None)
             off += m
-        return (None, None, None, None, None, None, None, *grads)
+        return (None, None, None, None, None, None, None, None, *grads)

@@ -17,7 +17,14 @@ int  check_cuda(cudaError_t e, const char* what);
   do { if (!(cond)) { bn::set_error("%s: %s", __func__, msg); return BN_ERR_ARG; } } while (0)
 #define BN_CUDA(call)                                                               \
   do { int _rc = bn::check_cuda((call), #call); if (_rc) return _rc; } while (0)
-#define BN_LAUNCH_CHECK() BN_CUDA(cudaGetLastError())
+// every kernel launch of the library goes through after_launch(): error check + launch counter
+int after_launch(const char* kernel);
+#define BN_LAUNCH_CHECK()                                                            \
+  do { int _rc = bn::after_launch(__func__); if (_rc) return _rc; } while (0)
+
+// optional per-launch CUDA-event timing of the GEMM family (bench.py roofline leg)
+void prof_begin(int kind, double work, cudaStream_t s);
+void prof_end(cudaStream_t s);
 
 constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xffffffffu;

@@ -218,11 +218,11 @@ __global__ void __launch_bounds__(kRaysPerBlock * kWarp) composite_bwd_kernel(Co
 
 template <int C> int launch_fwd(const CompositeFwd& a, cudaStream_t s) {
   composite_fwd_kernel<C><<<ceil_div(a.N, kRaysPerBlock), kRaysPerBlock * kWarp, 0, s>>>(a);
-  return check_cuda(cudaGetLastError(), "composite_fwd_kernel");
+  return after_launch("composite_fwd_kernel");
 }
 template <int C> int launch_bwd(const CompositeBwd& a, cudaStream_t s) {
   composite_bwd_kernel<C><<<ceil_div(a.N, kRaysPerBlock), kRaysPerBlock * kWarp, 0, s>>>(a);
-  return check_cuda(cudaGetLastError(), "composite_bwd_kernel");
+  return after_launch("composite_bwd_kernel");
 }
 
 #define BN_DISPATCH_C(C, FN, ...)                                                          \

@@ -90,12 +90,15 @@ struct EpiBias {
   }
 };
 
-// dgrad: out = (acc [+ addend]) [* mulc]   (dZ_{l-1} = (dZ_l W_l [+ direct grads]) ⊙ C_{l-1})
+// dgrad: out = (acc [+ addend]) [* mulc] [+ add2]   (dZ_{l-1} = (dZ_l W_l [+ direct grads]) ⊙ C_{l-1}
+// [+ second-order term]); raw_out optionally receives (acc + addend) before the mask.
 template <typename T>
 struct EpiDgrad {
   const T* addend; long long lda;    // nullable
   const T* mulc; long long ldm;      // nullable
   T* out; long long ld; int M, N;
+  T* raw_out = nullptr; long long ldr = 0;
+  const T* add2 = nullptr; long long ld2 = 0;
   template <int n> __device__ __forceinline__ void apply(int row, int col0, const float (&acc)[n]) const {
     if (row >= M || col0 >= N) return;
     float o[n];
@@ -106,12 +109,40 @@ struct EpiDgrad {
 #pragma unroll
       for (int j = 0; j < n; ++j) o[j] += t[j];
     }
+    if (raw_out) Pack<T, n>::store(raw_out + (long long)row * ldr + col0, o);
     if (mulc) {
       float t[n]; Pack<T, n>::load(mulc + (long long)row * ldm + col0, t);
 #pragma unroll
       for (int j = 0; j < n; ++j) o[j] *= t[j];
     }
+    if (add2) {
+      float t[n]; Pack<T, n>::load(add2 + (long long)row * ld2 + col0, t);
+#pragma unroll
+      for (int j = 0; j < n; ++j) o[j] += t[j];
+    }
     Pack<T, n>::store(out + (long long)row * ld + col0, o);
+  }
+};
+
+// second-order sweep of the analytic normals (adjoint of a_{l-1} = (a_l W_l) ⊙ c_{l-1}):
+//   acc = abar_l ;  ubar_l = abar_l ⊙ c_l  -> ubar ;  zb_l = (abar_l ⊙ u_l) * (-w0^2 h_l) -> overwrites u_l
+template <typename T>
+struct EpiSecond {
+  const T* Cc; long long ldc;
+  T* U; long long ldu;               // in: u_l, out: zb_l
+  const T* H; long long ldh;
+  T* ubar; long long ldo;
+  float neg_w0sq; int M, N;
+  template <int n> __device__ __forceinline__ void apply(int row, int col0, const float (&acc)[n]) const {
+    if (row >= M || col0 >= N) return;
+    float c[n], u[n], h[n], o[n];
+    Pack<T, n>::load(Cc + (long long)row * ldc + col0, c);
+    Pack<T, n>::load(U + (long long)row * ldu + col0, u);
+    Pack<T, n>::load(H + (long long)row * ldh + col0, h);
+#pragma unroll
+    for (int j = 0; j < n; ++j) { o[j] = acc[j] * c[j]; u[j] = acc[j] * u[j] * neg_w0sq * h[j]; }
+    Pack<T, n>::store(ubar + (long long)row * ldo + col0, o);
+    Pack<T, n>::store(U + (long long)row * ldu + col0, u);
   }
 };
 

@@ -128,7 +128,7 @@ int launch_tn_simt(const T* A, long long lda, const T* B, long long ldb, int M, 
   if (K % kSimtBK != 0 || (lda % 8) || (ldb % 8)) { set_error("gemm_tn_simt: K %% 16 / ld %% 8 alignment (K=%d)", K); return BN_ERR_ARG; }
   dim3 grid(ceil_div(N, kSimtBN), ceil_div(M, kSimtBM));
   gemm_tn_simt<T, Epi><<<grid, 256, 0, s>>>(A, lda, B, ldb, M, N, K, epi);
-  return check_cuda(cudaGetLastError(), "gemm_tn_simt");
+  return after_launch("gemm_tn_simt");
 }
 
 template <typename T, class Epi>
@@ -140,7 +140,7 @@ int launch_nt_simt(const T* A, long long lda, const T* B, long long ldb, int Nn,
   splits = (int)ceil_div_ll(P, per);
   dim3 grid(ceil_div(Kk, kSimtBN), ceil_div(Nn, kSimtBM), splits);
   gemm_nt_simt<T, Epi><<<grid, 256, 0, s>>>(A, lda, B, ldb, Nn, Kk, P, per, epi);
-  return check_cuda(cudaGetLastError(), "gemm_nt_simt");
+  return after_launch("gemm_nt_simt");
 }
 
 }  // namespace bn

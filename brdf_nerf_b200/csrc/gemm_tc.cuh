@@ -266,7 +266,7 @@ int launch_tn(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* B, lon
   BN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int items = wk.m_tiles * wk.n_tiles;
   kern<<<min(items, num_sms), kThreads, smem, s>>>(ma, mb, wk, epi);
-  return check_cuda(cudaGetLastError(), "gemm_tc_kernel<tn>");
+  return after_launch("gemm_tc_kernel<tn>");
 }
 
 // A:[P,Mo] (ld lda), B:[P,No]: C[Mo,No] = A^T B through `epi` (atomic accumulate), split over P
@@ -290,7 +290,7 @@ int launch_nt(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* B, lon
   BN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int items = tiles * wk.splits;
   kern<<<min(items, num_sms), kThreads, smem, s>>>(ma, mb, wk, epi);
-  return check_cuda(cudaGetLastError(), "gemm_tc_kernel<nt>");
+  return after_launch("gemm_tc_kernel<nt>");
 }
 
 }  // namespace tc

@@ -1,63 +1,6 @@
-// K-B: positional encoding + SIREN MLP (trunk, sigma / feature / colour / BRDF heads), forward and
-// backward, as a chain of fused GEMMs.
-//
-// Replaces (reference, paths relative to /root/reference):
-//   xyz = o + d z                        rendering.py:184,216,254,273
-//   Mapping.forward                      models/nerf.py:53-70
-//   SpSBRDFNeRF.calc_features            models/spsbrdfnerf.py:636-646 (layers :513-524)
-//   sigma / feats / rgb / BRDF heads     models/spsbrdfnerf.py:527-535,582-613,682-755
-//   autograd backward of all of it       implicit (dgrad + wgrad)
-//
-// Two precision modes share this orchestration and the epilogue functors:
-//   BN_PREC_BF16 : tcgen05.mma (gemm_tc.cuh) — bf16 activations/weights in HBM, fp32 accumulation in
-//                  TMEM, sin / cos / bias / Hadamard fused in the epilogue warps;
-//   BN_PREC_FP32 : CUDA-core fp32 (gemm_simt.cuh) — parity mode and on-device checker.
-// Activation layout in the caller's workspace (row = point, row-major, element type T):
-//   X3 [P, 64+F]  : cols 0..63 = encoding (60 real + 4 zero pad), cols 64.. = h_{skip-1}; the skip
-//                   layer reads the whole row as its K = 64+F operand (no concat copy)
-//   H_l, C_l [P,F]: h_l = sin(w0 z_l) and c_l = w0 cos(w0 z_l) (kept only when training)
-//   FE [P,F], HD / CD [P, 256*blocks]: features and the heads' hidden layer (+ cosine)
-#include <vector>
-#include <type_traits>
-#include <string.h>
-#include <math.h>
-#include "epilogues.cuh"
-#include "gemm_simt.cuh"
-#include "gemm_tc.cuh"
-
-namespace bn {
-
-constexpr int kEncPad = 64;
-constexpr int kMaxBlocks = 8;     // rgb + up to 7 BRDF heads
-constexpr int kMaxOut = 16;       // scalar outputs of the heads' second layers
-constexpr float kPiF = 3.14159265358979323846f;
-
-enum { XF_SIGMOID = 0, XF_K = 1, XF_THETA_RPV = 2, XF_THETA_H = 3 };
-
-struct OutDesc { int block; long long w_off; long long b_off; int ch; int rep; int xform; };
-struct HeadPlan {
-  int n_out; OutDesc o[kMaxOut];
-  int n_blocks;                 // blocks of the hidden layer that are evaluated
-  int HH;                       // hidden width of one block (feat / 2)
-  int ch_sigma, ch_nlr;         // packed channel of sigma / learned normal (-1 = off)
-  long long wsig, bsig, wg, bg; // offsets of sigma_from_xyz.0 / grad_from_xyz
-};
-
-}  // namespace bn
-
-struct bn_mlp {
-  bn_mlp_cfg cfg;
-  int F, L, E, HH, skip;
-  int num_sms;
-  bool bf16;
-  size_t es;
-  void* Wp[16]; void* WTp[16]; int Kpad[16]; int Kreal[16];
-  void* Wf; void* WfT;
-  void* W1; void* W1T; float* b1cat;
-  int n_blocks;
-  int blk_lin0[bn::kMaxBlocks], blk_lin2[bn::kMaxBlocks], blk_head[bn::kMaxBlocks];
-  bool synced;
-};
+// K-B: positional encoding + SIREN MLP — weight packing, encoding, heads, forward / backward
+// orchestration and the C entry points.  Shared declarations live in mlp_internal.cuh.
+#include "mlp_internal.cuh"
 
 namespace bn {
 
@@ -289,62 +232,6 @@ __global__ void __launch_bounds__(128) heads_bwd_kernel(HeadPlan hp, const float
   }
 }
 
-// out_o[i - c0_o] += sum_p D[p][o] X[p][i]   for i in [c0_o, c1_o), plus bias_o += sum_p D[p][o].
-struct SkinnyRow { float* dst; float* bias; int col; int c0, c1; };
-struct SkinnyPlan { int n; SkinnyRow r[kMaxOut]; };
-
-template <typename T>
-__global__ void __launch_bounds__(256) skinny_wgrad_kernel(SkinnyPlan sp, const T* __restrict__ D, int ldd,
-                                                           const T* __restrict__ X, long long ldx, int ncols,
-                                                           long long P, long long rows_per_block) {
-  __shared__ float sD[32][kMaxOut];
-  const int i = blockIdx.x * 256 + threadIdx.x;
-  const long long p0 = (long long)blockIdx.y * rows_per_block;
-  const long long p1 = min(P, p0 + rows_per_block);
-  float acc[kMaxOut], bacc[kMaxOut];
-#pragma unroll
-  for (int o = 0; o < kMaxOut; ++o) { acc[o] = 0.f; bacc[o] = 0.f; }
-  for (long long pb = p0; pb < p1; pb += 32) {
-    __syncthreads();
-    for (int t = threadIdx.x; t < 32 * kMaxOut; t += 256) {
-      const int pp = t / kMaxOut, o = t % kMaxOut;
-      sD[pp][o] = (pb + pp < p1 && o < sp.n) ? to_f<T>(D[(pb + pp) * ldd + sp.r[o].col]) : 0.f;
-    }
-    __syncthreads();
-    const int cnt = (int)min(32LL, p1 - pb);
-    for (int pp = 0; pp < cnt; ++pp) {
-      const float x = i < ncols ? to_f<T>(X[(pb + pp) * ldx + i]) : 0.f;
-#pragma unroll
-      for (int o = 0; o < kMaxOut; ++o) { acc[o] = fmaf(sD[pp][o], x, acc[o]); bacc[o] += sD[pp][o]; }
-    }
-  }
-#pragma unroll
-  for (int o = 0; o < kMaxOut; ++o) {
-    if (o < sp.n) {
-      if (i >= sp.r[o].c0 && i < sp.r[o].c1) atomicAdd(sp.r[o].dst + (i - sp.r[o].c0), acc[o]);
-      if (sp.r[o].bias && i == sp.r[o].c0) atomicAdd(sp.r[o].bias, bacc[o]);
-    }
-  }
-}
-
-// dst[c] += sum_p X[p][c]   (bias gradients), 8 columns per thread
-template <typename T>
-__global__ void __launch_bounds__(128) colsum_kernel(const T* __restrict__ X, long long ldx, int ncols, long long P,
-                                                     long long rows_per_block, float* __restrict__ dst) {
-  const int c = (blockIdx.x * 128 + threadIdx.x) * 8;
-  if (c >= ncols) return;
-  const long long p0 = (long long)blockIdx.y * rows_per_block;
-  const long long p1 = min(P, p0 + rows_per_block);
-  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (long long p = p0; p < p1; ++p) {
-    float v[8]; load8<T>(X + p * ldx + c, v);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] += v[j];
-  }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) atomicAdd(dst + c + j, acc[j]);
-}
-
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
                             float wd, float bc1, float bc2_sqrt, float gscale) {
@@ -358,56 +245,6 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   m[i] = mi; v[i] = vi;
   const float denom = sqrtf(vi) / bc2_sqrt + eps;
   p[i] = pi - (lr / bc1) * (mi / denom);
-}
-
-// ------------------------------------------------------------------------------------------------
-template <typename T> struct Ws {
-  T* X3; T* H[16]; long long Hld[16]; T* C[16];
-  T* FE; T* HD; T* CD; T* GHD; T* G7D; T* GFE; T* GA; T* GB; T* DPRE; T* DPRE2;
-  long long ldx3, ldhd;
-};
-
-static size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
-
-template <typename T>
-static size_t carve(const bn_mlp* h, long long P, int flags, void* base, Ws<T>* w) {
-  const bool train = flags & BN_MLP_TRAIN, sig_only = flags & BN_MLP_SIGMA_ONLY;
-  const int F = h->F, L = h->L;
-  size_t off = 0;
-  auto take = [&](long long elems) -> T* {
-    T* p = base ? reinterpret_cast<T*>(reinterpret_cast<uint8_t*>(base) + off) : nullptr;
-    off += align_up((size_t)elems * sizeof(T));
-    return p;
-  };
-  Ws<T> t{};
-  t.ldx3 = kEncPad + F;
-  t.ldhd = (long long)h->n_blocks * h->HH;
-  t.X3 = take(P * t.ldx3);
-  if (train) {
-    for (int l = 0; l < L; ++l) {
-      if (l == h->skip - 1) { t.H[l] = t.X3 ? t.X3 + kEncPad : nullptr; t.Hld[l] = t.ldx3; }
-      else { t.H[l] = take(P * F); t.Hld[l] = F; }
-      t.C[l] = take(P * F);
-    }
-  } else {
-    T* ping = take(P * F); T* pong = take(P * F);
-    for (int l = 0; l < L; ++l) {
-      if (l == h->skip - 1) { t.H[l] = t.X3 ? t.X3 + kEncPad : nullptr; t.Hld[l] = t.ldx3; }
-      else { t.H[l] = (l & 1) ? pong : ping; t.Hld[l] = F; }
-      t.C[l] = nullptr;
-    }
-  }
-  if (!sig_only) {
-    t.FE = take(P * F);
-    t.HD = take(P * t.ldhd);
-    if (train) {
-      t.CD = take(P * t.ldhd); t.GHD = take(P * t.ldhd);
-      t.G7D = take(P * F); t.GFE = take(P * F); t.GA = take(P * F); t.GB = take(P * F);
-      t.DPRE = take(P * 16); t.DPRE2 = take(P * 8);
-    }
-  }
-  if (w) *w = t;
-  return off;
 }
 
 static int build_plan(const bn_mlp* h, int flags, HeadPlan* hp, int* n_channels) {
@@ -457,40 +294,6 @@ static int build_plan(const bn_mlp* h, int flags, HeadPlan* hp, int* n_channels)
   return BN_OK;
 }
 
-// GEMM dispatch: tcgen05 for bf16, CUDA cores for fp32
-template <typename T, class Epi>
-static int gemm_tn(const bn_mlp* h, const T* A, long long lda, const T* B, long long ldb, long long M, int N, int K,
-                   const Epi& epi, cudaStream_t s) {
-  if constexpr (std::is_same<T, __nv_bfloat16>::value) {
-    if (N >= 256) return tc::launch_tn<256>(A, lda, B, ldb, M, N, K, epi, h->num_sms, s);
-    if (N >= 128) return tc::launch_tn<128>(A, lda, B, ldb, M, N, K, epi, h->num_sms, s);
-    return tc::launch_tn<64>(A, lda, B, ldb, M, N, K, epi, h->num_sms, s);
-  } else {
-    return launch_tn_simt<T, Epi>(A, lda, B, ldb, (int)M, N, K, epi, s);
-  }
-}
-template <typename T>
-static int gemm_nt(const bn_mlp* h, const T* A, long long lda, const T* B, long long ldb, int Mo, int No, long long P,
-                   const EpiWgrad& epi, cudaStream_t s) {
-  if constexpr (std::is_same<T, __nv_bfloat16>::value) {
-    if (No >= 256) return tc::launch_nt<256>(A, lda, B, ldb, Mo, No, P, epi, h->num_sms, s);
-    if (No >= 128) return tc::launch_nt<128>(A, lda, B, ldb, Mo, No, P, epi, h->num_sms, s);
-    return tc::launch_nt<64>(A, lda, B, ldb, Mo, No, P, epi, h->num_sms, s);
-  } else {
-    return launch_nt_simt<T, EpiWgrad>(A, lda, B, ldb, Mo, No, P, epi, s);
-  }
-}
-
-template <typename T>
-static int colsum(const T* X, long long ldx, int ncols, long long P, float* dst, cudaStream_t s) {
-  const int bx = ceil_div(ncols, 128 * 8);
-  int by = (int)max(1LL, min(ceil_div_ll(P, 64), (long long)(148 * 8 / bx)));
-  const long long rows = ceil_div_ll(P, by);
-  by = (int)ceil_div_ll(P, rows);
-  colsum_kernel<T><<<dim3(bx, by), 128, 0, s>>>(X, ldx, ncols, P, rows, dst);
-  return check_cuda(cudaGetLastError(), "colsum_kernel");
-}
-
 template <typename T>
 static int sync_weights_t(bn_mlp* h, const float* params, cudaStream_t s) {
   const bn_mlp_cfg& c = h->cfg;
@@ -498,7 +301,7 @@ static int sync_weights_t(bn_mlp* h, const float* params, cudaStream_t s) {
     const long long tot = (long long)N * Kpad;
     pack_weight_kernel<T><<<(unsigned)ceil_div_ll(tot, 256), 256, 0, s>>>(params + c.w_off[lin], N, Kreal, E, Kpad,
                                                                          (T*)Wp, ldp, (T*)WTp, ldt, row0);
-    return check_cuda(cudaGetLastError(), "pack_weight_kernel");
+    return after_launch("pack_weight_kernel");
   };
   for (int l = 0; l < h->L; ++l) {
     const bool enc_in = (l == 0 || l == h->skip);
@@ -521,6 +324,7 @@ static int forward_t(bn_mlp* h, const float* params, const float* origins, int o
                      cudaStream_t s) {
   const long long P = (long long)N * S;
   const bool train = flags & BN_MLP_TRAIN, sig_only = flags & BN_MLP_SIGMA_ONLY;
+  const bool keep_c = train || ((flags & BN_MLP_NORMAL_AN) && !sig_only);
   const bn_mlp_cfg& c = h->cfg;
   const int F = h->F, L = h->L;
   Ws<T> w; carve<T>(h, P, flags, wsp, &w);
@@ -536,11 +340,11 @@ static int forward_t(bn_mlp* h, const float* params, const float* origins, int o
     if (l == 0 || l == h->skip) { A = w.X3; lda = w.ldx3; } else { A = w.H[l - 1]; lda = w.Hld[l - 1]; }
     if (l == 0) {
       // first layer: sin(30 z) — accurate sincos even on the bf16 path (arguments reach |30 z|)
-      EpiSin<T, false> epi{params + c.b_off[l], 30.0f, w.H[l], w.Hld[l], train ? w.C[l] : nullptr, F, (int)P, F};
-      if (int rc = gemm_tn<T>(h, A, lda, (const T*)h->Wp[l], h->Kpad[l], P, F, h->Kpad[l], epi, s)) return rc;
+      EpiSin<T, false> epi{params + c.b_off[l], 30.0f, w.H[l], w.Hld[l], keep_c ? w.C[l] : nullptr, F, (int)P, F};
+      if (int rc = gemm_tn<T>(h, A, lda, (const T*)h->Wp[l], h->Kpad[l], P, F, h->Kpad[l], epi, s, h->Kreal[l])) return rc;
     } else {
-      EpiSin<T, kFast> epi{params + c.b_off[l], 1.0f, w.H[l], w.Hld[l], train ? w.C[l] : nullptr, F, (int)P, F};
-      if (int rc = gemm_tn<T>(h, A, lda, (const T*)h->Wp[l], h->Kpad[l], P, F, h->Kpad[l], epi, s)) return rc;
+      EpiSin<T, kFast> epi{params + c.b_off[l], 1.0f, w.H[l], w.Hld[l], keep_c ? w.C[l] : nullptr, F, (int)P, F};
+      if (int rc = gemm_tn<T>(h, A, lda, (const T*)h->Wp[l], h->Kpad[l], P, F, h->Kpad[l], epi, s, h->Kreal[l])) return rc;
     }
   }
   const T* Hl = w.H[L - 1]; const long long ldl = w.Hld[L - 1];
@@ -569,6 +373,7 @@ static int backward_t(bn_mlp* h, const float* params, const float* out, const fl
   const long long P = (long long)N * S;
   const bn_mlp_cfg& c = h->cfg;
   const int F = h->F, L = h->L;
+  const bool normals = flags & BN_MLP_NORMAL_AN;   // ZB_l (second-order terms) were left in w.U[l]
   Ws<T> w; carve<T>(h, P, flags, wsp, &w);
   HeadPlan hp; int nch;
   if (int rc = build_plan(h, flags, &hp, &nch)) return rc;
@@ -616,6 +421,7 @@ static int backward_t(bn_mlp* h, const float* params, const float* out, const fl
     if (int rc = gemm_nt<T>(h, w.GFE, F, Hl, ldl, F, F, P, ew, s)) return rc;
     if (int rc = colsum<T>(w.GFE, F, F, P, g + c.b_off[BN_LIN_FEATS], s)) return rc;
     EpiDgrad<T> ed{w.G7D, F, w.C[L - 1], F, w.GA, F, (int)P, F};
+    if (normals) { ed.add2 = w.U[L - 1]; ed.ld2 = F; }
     if (int rc = gemm_tn<T>(h, w.GFE, F, (const T*)h->WfT, F, P, F, F, ed, s)) return rc;
   }
   // trunk, last layer first.  cur = dZ_l
@@ -630,6 +436,7 @@ static int backward_t(bn_mlp* h, const float* params, const float* out, const fl
     if (l > 0) {
       const T* BT = (const T*)h->WTp[l] + (l == h->skip ? (long long)kEncPad * F : 0);
       EpiDgrad<T> ed{nullptr, 0, w.C[l - 1], F, nxt, F, (int)P, F};
+      if (normals) { ed.add2 = w.U[l - 1]; ed.ld2 = F; }
       if (int rc = gemm_tn<T>(h, cur, F, BT, F, P, F, F, ed, s)) return rc;
       T* t = cur; cur = nxt; nxt = t;
     }

@@ -1,0 +1,235 @@
+#pragma once
+// Internal declarations shared by mlp.cu and normals.cu.
+// K-B: positional encoding + SIREN MLP (trunk, sigma / feature / colour / BRDF heads), forward and
+// backward, as a chain of fused GEMMs.
+//
+// Replaces (reference, paths relative to /root/reference):
+//   xyz = o + d z                        rendering.py:184,216,254,273
+//   Mapping.forward                      models/nerf.py:53-70
+//   SpSBRDFNeRF.calc_features            models/spsbrdfnerf.py:636-646 (layers :513-524)
+//   sigma / feats / rgb / BRDF heads     models/spsbrdfnerf.py:527-535,582-613,682-755
+//   autograd backward of all of it       implicit (dgrad + wgrad)
+//
+// Two precision modes share this orchestration and the epilogue functors:
+//   BN_PREC_BF16 : tcgen05.mma (gemm_tc.cuh) — bf16 activations/weights in HBM, fp32 accumulation in
+//                  TMEM, sin / cos / bias / Hadamard fused in the epilogue warps;
+//   BN_PREC_FP32 : CUDA-core fp32 (gemm_simt.cuh) — parity mode and on-device checker.
+// Activation layout in the caller's workspace (row = point, row-major, element type T):
+//   X3 [P, 64+F]  : cols 0..63 = encoding (60 real + 4 zero pad), cols 64.. = h_{skip-1}; the skip
+//                   layer reads the whole row as its K = 64+F operand (no concat copy)
+//   H_l, C_l [P,F]: h_l = sin(w0 z_l) and c_l = w0 cos(w0 z_l) (kept only when training)
+//   FE [P,F], HD / CD [P, 256*blocks]: features and the heads' hidden layer (+ cosine)
+#include <vector>
+#include <type_traits>
+#include <string.h>
+#include <math.h>
+#include "epilogues.cuh"
+#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
+
+namespace bn {
+
+constexpr int kEncPad = 64;
+constexpr int kMaxBlocks = 8;     // rgb + up to 7 BRDF heads
+constexpr int kMaxOut = 16;       // scalar outputs of the heads' second layers
+constexpr float kPiF = 3.14159265358979323846f;
+
+enum { XF_SIGMOID = 0, XF_K = 1, XF_THETA_RPV = 2, XF_THETA_H = 3 };
+
+struct OutDesc { int block; long long w_off; long long b_off; int ch; int rep; int xform; };
+struct HeadPlan {
+  int n_out; OutDesc o[kMaxOut];
+  int n_blocks;                 // blocks of the hidden layer that are evaluated
+  int HH;                       // hidden width of one block (feat / 2)
+  int ch_sigma, ch_nlr;         // packed channel of sigma / learned normal (-1 = off)
+  long long wsig, bsig, wg, bg; // offsets of sigma_from_xyz.0 / grad_from_xyz
+};
+
+}  // namespace bn
+
+struct bn_mlp {
+  bn_mlp_cfg cfg;
+  int F, L, E, HH, skip;
+  int num_sms;
+  bool bf16;
+  size_t es;
+  void* Wp[16]; void* WTp[16]; int Kpad[16]; int Kreal[16];
+  void* Wf; void* WfT;
+  void* W1; void* W1T; float* b1cat;
+  int n_blocks;
+  int blk_lin0[bn::kMaxBlocks], blk_lin2[bn::kMaxBlocks], blk_head[bn::kMaxBlocks];
+  bool synced;
+};
+
+namespace bn {
+
+// out_o[i - c0_o] += sum_p D[p][o] X[p][i]   for i in [c0_o, c1_o), plus bias_o += sum_p D[p][o].
+struct SkinnyRow { float* dst; float* bias; int col; int c0, c1; };
+struct SkinnyPlan { int n; SkinnyRow r[kMaxOut]; };
+
+template <typename T>
+__global__ void __launch_bounds__(256) skinny_wgrad_kernel(SkinnyPlan sp, const T* __restrict__ D, int ldd,
+                                                           const T* __restrict__ X, long long ldx, int ncols,
+                                                           long long P, long long rows_per_block) {
+  __shared__ float sD[32][kMaxOut];
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  const long long p0 = (long long)blockIdx.y * rows_per_block;
+  const long long p1 = min(P, p0 + rows_per_block);
+  float acc[kMaxOut], bacc[kMaxOut];
+#pragma unroll
+  for (int o = 0; o < kMaxOut; ++o) { acc[o] = 0.f; bacc[o] = 0.f; }
+  for (long long pb = p0; pb < p1; pb += 32) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < 32 * kMaxOut; t += 256) {
+      const int pp = t / kMaxOut, o = t % kMaxOut;
+      sD[pp][o] = (pb + pp < p1 && o < sp.n) ? to_f<T>(D[(pb + pp) * ldd + sp.r[o].col]) : 0.f;
+    }
+    __syncthreads();
+    const int cnt = (int)min(32LL, p1 - pb);
+    for (int pp = 0; pp < cnt; ++pp) {
+      const float x = i < ncols ? to_f<T>(X[(pb + pp) * ldx + i]) : 0.f;
+#pragma unroll
+      for (int o = 0; o < kMaxOut; ++o) { acc[o] = fmaf(sD[pp][o], x, acc[o]); bacc[o] += sD[pp][o]; }
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < kMaxOut; ++o) {
+    if (o < sp.n) {
+      if (i >= sp.r[o].c0 && i < sp.r[o].c1) atomicAdd(sp.r[o].dst + (i - sp.r[o].c0), acc[o]);
+      if (sp.r[o].bias && i == sp.r[o].c0) atomicAdd(sp.r[o].bias, bacc[o]);
+    }
+  }
+}
+
+// dst[c] += sum_p X[p][c]   (bias gradients), 8 columns per thread
+template <typename T>
+__global__ void __launch_bounds__(128) colsum_kernel(const T* __restrict__ X, long long ldx, int ncols, long long P,
+                                                     long long rows_per_block, float* __restrict__ dst) {
+  const int c = (blockIdx.x * 128 + threadIdx.x) * 8;
+  if (c >= ncols) return;
+  const long long p0 = (long long)blockIdx.y * rows_per_block;
+  const long long p1 = min(P, p0 + rows_per_block);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (long long p = p0; p < p1; ++p) {
+    float v[8]; load8<T>(X + p * ldx + c, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += v[j];
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) atomicAdd(dst + c + j, acc[j]);
+}
+
+// ------------------------------------------------------------------------------------------------
+template <typename T> struct Ws {
+  T* X3; T* H[16]; long long Hld[16]; T* C[16];
+  T* FE; T* HD; T* CD; T* GHD; T* G7D; T* GFE; T* GA; T* GB; T* DPRE; T* DPRE2;
+  long long ldx3, ldhd;
+  // analytic-normal sweep (BN_MLP_NORMAL_AN)
+  T* A[16];        // a_l = d sigma / d lin_l            (one per layer when training, ping-pong otherwise)
+  T* U[16];        // u_l = a_l before the cosine mask; overwritten by ZB_l in the backward (training)
+  T* EE; T* EE0;   // [P,64] d sigma / d enc: skip-layer part, total
+  float* GRAW;     // [P,4] raw d sigma / d x (fp32)
+  T* UBX;          // [P,64+F]: cols 0..63 = adjoint of EE, cols 64.. = ubar_{skip-1}
+  T* UBA; T* UBB;  // ubar ping-pong
+  T* SG;           // [P,8]: col 0 = sigmoid(s_p)
+};
+
+static inline size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
+
+template <typename T>
+static inline size_t carve(const bn_mlp* h, long long P, int flags, void* base, Ws<T>* w) {
+  const bool train = flags & BN_MLP_TRAIN, sig_only = flags & BN_MLP_SIGMA_ONLY;
+  const bool normals = (flags & BN_MLP_NORMAL_AN) && !sig_only;
+  const int F = h->F, L = h->L;
+  size_t off = 0;
+  auto take = [&](long long elems) -> T* {
+    T* p = base ? reinterpret_cast<T*>(reinterpret_cast<uint8_t*>(base) + off) : nullptr;
+    off += align_up((size_t)elems * sizeof(T));
+    return p;
+  };
+  Ws<T> t{};
+  t.ldx3 = kEncPad + F;
+  t.ldhd = (long long)h->n_blocks * h->HH;
+  t.X3 = take(P * t.ldx3);
+  if (train) {
+    for (int l = 0; l < L; ++l) {
+      if (l == h->skip - 1) { t.H[l] = t.X3 ? t.X3 + kEncPad : nullptr; t.Hld[l] = t.ldx3; }
+      else { t.H[l] = take(P * F); t.Hld[l] = F; }
+      t.C[l] = take(P * F);
+    }
+  } else {
+    T* ping = take(P * F); T* pong = take(P * F);
+    for (int l = 0; l < L; ++l) {
+      if (l == h->skip - 1) { t.H[l] = t.X3 ? t.X3 + kEncPad : nullptr; t.Hld[l] = t.ldx3; }
+      else { t.H[l] = (l & 1) ? pong : ping; t.Hld[l] = F; }
+      t.C[l] = normals ? take(P * F) : nullptr;
+    }
+  }
+  if (!sig_only) {
+    t.FE = take(P * F);
+    t.HD = take(P * t.ldhd);
+    if (train) {
+      t.CD = take(P * t.ldhd); t.GHD = take(P * t.ldhd);
+      t.G7D = take(P * F); t.GFE = take(P * F); t.GA = take(P * F); t.GB = take(P * F);
+      t.DPRE = take(P * 16); t.DPRE2 = take(P * 8);
+    }
+  }
+  if (normals) {
+    if (train) {
+      for (int l = 0; l < L; ++l) { t.A[l] = take(P * F); t.U[l] = take(P * F); }
+      t.UBX = take(P * t.ldx3); t.UBA = take(P * F); t.UBB = take(P * F); t.SG = take(P * 8);
+    } else {
+      T* ping = take(P * F); T* pong = take(P * F);
+      for (int l = 0; l < L; ++l) { t.A[l] = (l & 1) ? pong : ping; t.U[l] = nullptr; }
+    }
+    t.EE = take(P * kEncPad); t.EE0 = take(P * kEncPad);
+    t.GRAW = reinterpret_cast<float*>(take(P * 4 * (long long)(sizeof(float) / sizeof(T))));
+  }
+  if (w) *w = t;
+  return off;
+}
+
+// GEMM dispatch: tcgen05 for bf16, CUDA cores for fp32
+template <typename T, class Epi>
+static int gemm_tn(const bn_mlp* h, const T* A, long long lda, const T* B, long long ldb, long long M, int N, int K,
+                   const Epi& epi, cudaStream_t s, int k_real = -1) {
+  prof_begin(0, 2.0 * (double)M * N * (k_real > 0 ? k_real : K), s);
+  int rc;
+  if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+    if (N >= 256) rc = tc::launch_tn<256>(A, lda, B, ldb, M, N, K, epi, h->num_sms, s);
+    else if (N >= 128) rc = tc::launch_tn<128>(A, lda, B, ldb, M, N, K, epi, h->num_sms, s);
+    else rc = tc::launch_tn<64>(A, lda, B, ldb, M, N, K, epi, h->num_sms, s);
+  } else {
+    rc = launch_tn_simt<T, Epi>(A, lda, B, ldb, (int)M, N, K, epi, s);
+  }
+  prof_end(s);
+  return rc;
+}
+template <typename T>
+static int gemm_nt(const bn_mlp* h, const T* A, long long lda, const T* B, long long ldb, int Mo, int No, long long P,
+                   const EpiWgrad& epi, cudaStream_t s) {
+  const int n_real = No - (epi.pad_hi - epi.pad_lo);
+  prof_begin(1, 2.0 * (double)P * Mo * n_real, s);
+  int rc;
+  if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+    if (No >= 256) rc = tc::launch_nt<256>(A, lda, B, ldb, Mo, No, P, epi, h->num_sms, s);
+    else if (No >= 128) rc = tc::launch_nt<128>(A, lda, B, ldb, Mo, No, P, epi, h->num_sms, s);
+    else rc = tc::launch_nt<64>(A, lda, B, ldb, Mo, No, P, epi, h->num_sms, s);
+  } else {
+    rc = launch_nt_simt<T, EpiWgrad>(A, lda, B, ldb, Mo, No, P, epi, s);
+  }
+  prof_end(s);
+  return rc;
+}
+
+template <typename T>
+static int colsum(const T* X, long long ldx, int ncols, long long P, float* dst, cudaStream_t s) {
+  const int bx = ceil_div(ncols, 128 * 8);
+  int by = (int)max(1LL, min(ceil_div_ll(P, 64), (long long)(148 * 8 / bx)));
+  const long long rows = ceil_div_ll(P, by);
+  by = (int)ceil_div_ll(P, rows);
+  colsum_kernel<T><<<dim3(bx, by), 128, 0, s>>>(X, ldx, ncols, P, rows, dst);
+  return after_launch("colsum_kernel");
+}
+
+}  // namespace bn

@@ -321,5 +321,6 @@ class SpSBRDFNeRF(nn.Module):
                 apply_brdf=False, apply_theta=False, nr_an_on=False, nr_lr_on=False, sun_ray=False, mode="train"):
         """Reference signature (spsbrdfnerf.py:662): (B,3) points -> (B,1) sigma or packed (B,C)."""
         from ..autograd import PointsFunction
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         return PointsFunction.apply(self, input_xyz_.contiguous(), bool(sigma_only), bool(apply_brdf),
-                                    bool(apply_theta), bool(nr_an_on), bool(nr_lr_on), *self.parameters())
+                                    bool(apply_theta), bool(nr_an_on), bool(nr_lr_on), need_grad, *self.parameters())

@@ -1,0 +1,128 @@
+"""Minimal training-step driver for the hot path (replaces the Lightning glue of the reference,
+main.py:194-353 + 147-168): forward through the CUDA pipeline, loss gradients,
+backward kernels writing straight into the flat fp32 gradient bucket, ONE all-reduce of that bucket
+over NCCL when world_size > 1, fused Adam on the flat buffers.
+
+No autograd tape is built: the step calls the forward / backward kernel chains directly
+(`rendering._forward` / `rendering._backward`).  Nothing in a step synchronises with the host, so it
+can be captured in a CUDA graph (`use_graph=True`).
+
+Losses (reference metrics.py:39-61 SNerfLoss with lambda_sc = 0, metrics.py:82-161 DepthLoss with
+subset=True, GNLL=False):
+    L = lambda_rgb * mean((rgb - target)^2)
+      + [step < ds_drop] (lambda_ds / 3) * mean_sel( n_sel/N * w_i (d_i - d*_i)^2 )
+The depth term's normaliser n_sel/N * 1/n_sel collapses to 1/N, so the selection mask is applied as
+a 0/1 weight without any host round trip (the reference syncs three times to build index lists).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import ops
+from . import rendering as R
+from .synth import RayBatch
+
+
+def loss_and_grads(args, outs, st, batch: RayBatch, use_depth: bool):
+    """Returns (loss scalar tensor, g_rgb (N,3), g_depth (N) or None)."""
+    rgb, depth, w, z = outs["rgb"], outs["depth"], outs["weights"], outs["z"]
+    n = rgb.shape[0]
+    diff = rgb - batch.rgbs
+    lam = float(args.lambda_rgb)
+    loss = lam * (diff * diff).mean()
+    g_rgb = diff * (2.0 * lam / (3 * n))
+    g_depth = None
+    if use_depth and batch.valid_depth is not None:
+        td, tw = batch.target_depths[:, 0], batch.target_depths[:, 1]
+        if getattr(args, "ds_noweights", False):
+            tw = torch.ones_like(tw)
+        ts = batch.target_std
+        pred_std = torch.sqrt((((z - depth.unsqueeze(-1)) ** 2) * w).sum(-1))
+        dd = depth - td
+        sel = batch.valid_depth > 0
+        if not getattr(args, "usealldepth", False):
+            sel = sel & (((dd.abs() - ts) > 0) | (ts < pred_std))
+        m = sel.to(rgb.dtype) * tw
+        k = float(args.ds_lambda) / 3.0 / n
+        loss = loss + k * (m * dd * dd).sum()
+        g_depth = (2.0 * k) * m * dd
+    return loss, g_rgb, g_depth
+
+
+class Trainer:
+    def __init__(self, model, args, lr: Optional[float] = None, world_size: int = 1, process_group=None,
+                 use_graph: bool = False):
+        self.model, self.args = model, args
+        self.lr = float(args.lr if lr is None else lr)
+        self.world = int(world_size)
+        self.pg = process_group
+        self.step_count = 0
+        self.use_graph = use_graph
+        flat = model.flat_params
+        self.m = torch.zeros_like(flat)
+        self.v = torch.zeros_like(flat)
+        self._graph = None
+        self._static: Optional[RayBatch] = None
+        self._loss = None
+        self._kw = None
+
+    # one optimisation step; `batch` tensors must already live on the model's device
+    def _step_impl(self, batch: RayBatch, draws, kw):
+        model, args = self.model, self.args
+        outs, st = R._forward(model, args, batch.rays, draws, train=True, mode="train",
+                              valid_depth=batch.valid_depth, target_depths=batch.target_depths,
+                              target_std=batch.target_std, **kw)
+        use_depth = float(args.ds_lambda) > 0
+        loss, g_rgb, g_depth = loss_and_grads(args, outs, st, batch, use_depth)
+        grads = model.flat_grads
+        grads.zero_()
+        R._backward(model, st, g_rgb, g_depth, None, None, grads)
+        return loss
+
+    def _reduce_and_update(self):
+        model = self.model
+        if self.world > 1:
+            torch.distributed.all_reduce(model.flat_grads, group=self.pg)      # NCCL sum over NVLink
+        self.step_count += 1
+        ops.adam_step(model.flat_params, model.flat_grads, self.m, self.v, self.lr, self.step_count,
+                      grad_scale=1.0 / self.world)
+        model._synced_version = -1            # the packed bf16 copies are stale now
+
+    def step(self, batch: RayBatch, draws=None, apply_brdf=False, apply_theta=False, cos_irra_on=False,
+             gsam_only=False):
+        kw = dict(apply_brdf=apply_brdf, bTestNormal=False, bTestSun_v=False, gsam_only=gsam_only,
+                  apply_theta=apply_theta, cos_irra_on=cos_irra_on)
+        if not self.use_graph or draws is not None:
+            loss = self._step_impl(batch, draws, kw)
+            self._reduce_and_update()
+            return loss
+        return self._graph_step(batch, kw)
+
+    # ---- CUDA-graph path: static input buffers, forward+backward captured once, replayed per step
+    def _graph_step(self, batch: RayBatch, kw):
+        if self._graph is None or self._kw != kw:
+            self._static = RayBatch(*[None if t is None else t.clone() for t in
+                                      (batch.rays, batch.rgbs, batch.valid_depth, batch.target_depths, batch.target_std)])
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                 # warm-up: fills table / workspace caches
+                for _ in range(2):
+                    self.model.sync_weights(force=True)
+                    self._step_impl(self._static, None, kw)
+            torch.cuda.current_stream().wait_stream(side)
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self.model.sync_weights(force=True)
+                self._loss = self._step_impl(self._static, None, kw)
+            self._kw = dict(kw)
+        for dst, src in zip((self._static.rays, self._static.rgbs, self._static.valid_depth,
+                             self._static.target_depths, self._static.target_std),
+                            (batch.rays, batch.rgbs, batch.valid_depth, batch.target_depths, batch.target_std)):
+            if dst is not None:
+                dst.copy_(src, non_blocking=True)
+        self._graph.replay()
+        self._reduce_and_update()
+        self.model._synced_version = self.model._flat._version   # the graph re-packs the weights itself
+        return self._loss

@@ -43,6 +43,13 @@ const char* bn_last_error(void);
 /* BN_OK iff device `device` is sm_100-class. Host-only query. */
 int bn_device_check(int device);
 
+/* number of kernels this library has launched in this process (bench.py: gpu_launches) */
+unsigned long long bn_launch_count(void);
+/* per-launch CUDA-event timing of the GEMM family (bench.py roofline leg); off by default */
+int bn_profile_enable(int on);
+/* HOST pointers: per kind (0 = TN fwd/dgrad, 1 = NT wgrad) launch count, milliseconds, flops */
+int bn_profile_collect(int n_kinds, long long* count, double* ms, double* work);
+
 /* ------------------------------------------------------------------ K-A  sample generators */
 
 /* get_z_vals (rendering.py:149-166, perturb == 1): z = lower + (upper-lower)*u over the strata of
