@@ -229,7 +229,11 @@ def run_ours(opts):
                 "peak_kind": f"{peaks['src']} sustained bf16 (kernel timed inside a long step)", "traffic": None,
                 "launches_per_step": (cnt[0] + cnt[1]) / nprof, "gemm_ms_per_step": gemm_ms,
                 "gemm_share_of_step": gemm_ms / ms, "algorithmic_gflop_per_step": gemm_flops / 1e9,
-                "survey_gflop_per_step": alg / 1e9}
+                "survey_gflop_per_step": alg / 1e9,
+                "by_kind": {"tn_fwd_dgrad": {"launches": cnt[0] / nprof, "ms": tms[0] / nprof,
+                                             "tflops": work[0] / max(tms[0], 1e-9) / 1e9},
+                            "nt_wgrad": {"launches": cnt[1] / nprof, "ms": tms[1] / nprof,
+                                         "tflops": work[1] / max(tms[1], 1e-9) / 1e9}}}
     if rank == 0:
         cpu = None
         if world == 1 and not opts.no_cpu_baseline:

@@ -1,0 +1,250 @@
+// K-B2: analytic normals n = -l2n(d sigma / d x) as an explicit reverse sweep through the trunk, and
+// the second-order backward (gradient of a loss on n w.r.t. all trunk weights).
+//
+// Replaces (reference, paths relative to /root/reference):
+//   SpSBRDFNeRF.calc_normals   models/spsbrdfnerf.py:648-660  (second trunk forward + autograd.grad
+//                              with create_graph=True) and :713-716 (normal_an = -l2_normalize)
+//   the double backward that autograd runs through that graph in training
+// The reference recomputes the trunk forward inside calc_normals; here the sweep reuses the stored
+// cosines c_l of the one forward pass.
+//
+// Notation (per point, row vectors): lin_l = W_l in_l + b_l, h_l = sin(w0 lin_l), c_l = w0 cos(w0 lin_l),
+// s = w_sigma h_{L-1} + b, sigma = softplus(s), sg = sigmoid(s) = 1 - exp(-sigma).
+//   forward sweep   a_{L-1} = sg w_sigma ⊙ c_{L-1};  u_{l-1} = a_l W_l^h;  a_{l-1} = u_{l-1} ⊙ c_{l-1}
+//                   E = a_0 W_0 + a_skip W_skip^enc (d sigma / d enc);  g = J_enc^T E;  n = -g/|g|
+//   backward sweep  Ebar = J_enc gbar;  abar_l = [Ebar | ubar_{l-1}] W_l^T;  ubar_l = abar_l ⊙ c_l;
+//                   zb_l = (abar_l ⊙ u_l)(-w0^2 h_l)  -> added to d loss/d lin_l by bn_mlp_backward;
+//                   dW_l += a_l^T [Ebar | ubar_{l-1}];  dw_sigma += sum_p sg ubar_{L-1};
+//                   d loss/d sigma += (ubar_{L-1} . w_sigma)(1 - sg)
+#include "mlp_internal.cuh"
+
+namespace bn {
+
+constexpr float kEpsF32 = 1.1920929e-07f;
+
+template <typename T>
+__global__ void sweep_init_kernel(const float* __restrict__ out, int pitch, const float* __restrict__ params,
+                                  long long wsig, const T* __restrict__ Cl, T* __restrict__ A, T* __restrict__ U,
+                                  T* __restrict__ SG, long long P, int F) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int per_row = F / 8;
+  if (idx >= P * per_row) return;
+  const long long p = idx / per_row;
+  const int i = (int)(idx % per_row) * 8;
+  const float sg = 1.0f - expf(-out[p * pitch + 3]);
+  float c[8], a[8], u[8];
+  load8<T>(Cl + p * F + i, c);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { u[j] = sg * __ldg(params + wsig + i + j); a[j] = u[j] * c[j]; }
+  Pack<T, 8>::store(A + p * F + i, a);
+  if (U) Pack<T, 8>::store(U + p * F + i, u);
+  if (SG && i == 0) { float s8[8] = {sg, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}; Pack<T, 8>::store(SG + p * 8, s8); }
+}
+
+template <typename T>
+__device__ __forceinline__ void load_row64(const T* p, float (&v)[64]) {
+#pragma unroll
+  for (int i = 0; i < 64; i += 8) { float t[8]; load8<T>(p + i, t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[i + j] = t[j]; }
+}
+
+// g = J_enc^T E, n = -g / sqrt(max(|g|^2, eps))
+template <typename T>
+__global__ void normal_from_enc_kernel(const T* __restrict__ EE, const T* __restrict__ X3, long long ldx, int n_freq,
+                                       float* __restrict__ out, int pitch, int ch, float* __restrict__ GRAW, long long P) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  float E[64], enc[64];
+  load_row64<T>(EE + p * kEncPad, E);
+  load_row64<T>(X3 + p * ldx, enc);
+  float g[3] = {0.f, 0.f, 0.f};
+  if (n_freq == 0) { g[0] = E[0]; g[1] = E[1]; g[2] = E[2]; }
+  else {
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+      if (k < n_freq) {
+        const float f = (float)(1 << k);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) g[a] += f * (E[k * 6 + a] * enc[k * 6 + 3 + a] - E[k * 6 + 3 + a] * enc[k * 6 + a]);
+      }
+    }
+  }
+  const float inv = 1.0f / sqrtf(fmaxf(g[0] * g[0] + g[1] * g[1] + g[2] * g[2], kEpsF32));
+#pragma unroll
+  for (int a = 0; a < 3; ++a) { out[p * pitch + ch + a] = -g[a] * inv; if (GRAW) GRAW[p * 4 + a] = g[a]; }
+}
+
+// gbar from d loss / d n, then Ebar = J_enc gbar into cols 0..63 of UBX
+template <typename T>
+__global__ void normal_bwd_init_kernel(const float* __restrict__ g_out, int pitch, int ch, const float* __restrict__ GRAW,
+                                       const T* __restrict__ X3, long long ldx, int n_freq, T* __restrict__ UBX,
+                                       long long ldu, long long P) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const float g[3] = {GRAW[p * 4], GRAW[p * 4 + 1], GRAW[p * 4 + 2]};
+  const float gn[3] = {g_out[p * pitch + ch], g_out[p * pitch + ch + 1], g_out[p * pitch + ch + 2]};
+  const float sq = g[0] * g[0] + g[1] * g[1] + g[2] * g[2];
+  float dg[3];
+  if (sq > kEpsF32) {
+    const float inv = 1.0f / sqrtf(sq);
+    const float u[3] = {g[0] * inv, g[1] * inv, g[2] * inv};
+    const float gu = gn[0] * u[0] + gn[1] * u[1] + gn[2] * u[2];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) dg[a] = -(gn[a] - gu * u[a]) * inv;
+  } else {
+    const float inv = 1.0f / sqrtf(kEpsF32);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) dg[a] = -gn[a] * inv;
+  }
+  float enc[64], eb[64];
+  load_row64<T>(X3 + p * ldx, enc);
+#pragma unroll
+  for (int i = 0; i < 64; ++i) eb[i] = 0.f;
+  if (n_freq == 0) { eb[0] = dg[0]; eb[1] = dg[1]; eb[2] = dg[2]; }
+  else {
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+      if (k < n_freq) {
+        const float f = (float)(1 << k);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { eb[k * 6 + a] = f * enc[k * 6 + 3 + a] * dg[a]; eb[k * 6 + 3 + a] = -f * enc[k * 6 + a] * dg[a]; }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 64; i += 8) {
+    float t[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t[j] = eb[i + j];
+    Pack<T, 8>::store(UBX + p * ldu + i, t);
+  }
+}
+
+// d loss / d sigma += (ubar_{L-1} . w_sigma)(1 - sg): one warp per point
+template <typename T>
+__global__ void __launch_bounds__(128) sigma_top_bwd_kernel(const T* __restrict__ UB, long long ld,
+                                                            const float* __restrict__ params, long long wsig,
+                                                            const T* __restrict__ SG, float* __restrict__ g_out, int pitch,
+                                                            long long P, int F) {
+  const int lane = threadIdx.x % 32;
+  const long long p = (long long)blockIdx.x * 4 + threadIdx.x / 32;
+  if (p >= P) return;
+  float acc = 0.f;
+  for (int i = lane * 8; i < F; i += 256) {
+    float u[8]; load8<T>(UB + p * ld + i, u);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc = fmaf(u[j], __ldg(params + wsig + i + j), acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    const float sg = to_f<T>(SG[p * 8]);
+    g_out[p * pitch + 3] += acc * (1.0f - sg);
+  }
+}
+
+template <typename T>
+static int normals_forward_t(bn_mlp* h, const float* params, float* out, int pitch, int N, int S, int flags, int ch,
+                             void* wsp, cudaStream_t s) {
+  const long long P = (long long)N * S;
+  const bool train = flags & BN_MLP_TRAIN;
+  const int F = h->F, L = h->L;
+  Ws<T> w; carve<T>(h, P, flags, wsp, &w);
+  const long long wsig = h->cfg.w_off[BN_LIN_SIGMA];
+  {
+    const long long tot = P * (F / 8);
+    sweep_init_kernel<T><<<(unsigned)ceil_div_ll(tot, 256), 256, 0, s>>>(out, pitch, params, wsig, w.C[L - 1], w.A[L - 1],
+                                                                       train ? w.U[L - 1] : nullptr, train ? w.SG : nullptr, P, F);
+    BN_LAUNCH_CHECK();
+  }
+  for (int l = L - 1; l >= 1; --l) {
+    const T* BT = (const T*)h->WTp[l] + (l == h->skip ? (long long)kEncPad * F : 0);
+    EpiDgrad<T> ed{nullptr, 0, w.C[l - 1], F, w.A[l - 1], F, (int)P, F};
+    if (train) { ed.raw_out = w.U[l - 1]; ed.ldr = F; }
+    if (int rc = gemm_tn<T>(h, w.A[l], F, BT, F, P, F, F, ed, s)) return rc;
+    if (l == h->skip) {
+      EpiDgrad<T> e2{nullptr, 0, nullptr, 0, w.EE, kEncPad, (int)P, kEncPad};
+      if (int rc = gemm_tn<T>(h, w.A[l], F, (const T*)h->WTp[l], F, P, kEncPad, F, e2, s)) return rc;
+    }
+  }
+  {
+    EpiDgrad<T> e0{h->skip > 0 ? w.EE : nullptr, kEncPad, nullptr, 0, w.EE0, kEncPad, (int)P, kEncPad};
+    if (int rc = gemm_tn<T>(h, w.A[0], F, (const T*)h->WTp[0], F, P, kEncPad, F, e0, s)) return rc;
+  }
+  normal_from_enc_kernel<T><<<(unsigned)ceil_div_ll(P, 128), 128, 0, s>>>(w.EE0, w.X3, w.ldx3, h->cfg.n_freq_xyz, out, pitch, ch,
+                                                                        train ? w.GRAW : nullptr, P);
+  BN_LAUNCH_CHECK();
+  return BN_OK;
+}
+
+template <typename T>
+static int normals_backward_t(bn_mlp* h, const float* params, const float* out, float* g_out, int pitch, int N, int S,
+                              int flags, int ch, float* g, void* wsp, cudaStream_t s) {
+  const long long P = (long long)N * S;
+  const int F = h->F, L = h->L;
+  const bn_mlp_cfg& c = h->cfg;
+  Ws<T> w; carve<T>(h, P, flags, wsp, &w);
+  normal_bwd_init_kernel<T><<<(unsigned)ceil_div_ll(P, 128), 128, 0, s>>>(g_out, pitch, ch, w.GRAW, w.X3, w.ldx3, c.n_freq_xyz,
+                                                                        w.UBX, w.ldx3, P);
+  BN_LAUNCH_CHECK();
+  const T* prev = nullptr; long long ldprev = 0;
+  for (int l = 0; l < L; ++l) {
+    const bool enc_in = (l == 0 || l == h->skip);
+    const T* Aop; long long lda;
+    if (enc_in) { Aop = w.UBX; lda = w.ldx3; } else { Aop = prev; lda = ldprev; }
+    T* dst; long long ldd;
+    if (l == h->skip - 1) { dst = w.UBX + kEncPad; ldd = w.ldx3; }
+    else { dst = (l & 1) ? w.UBB : w.UBA; ldd = F; }
+    const float w0 = l == 0 ? 30.0f : 1.0f;
+    EpiSecond<T> es{w.C[l], F, w.U[l], F, w.H[l], w.Hld[l], dst, ldd, -w0 * w0, (int)P, F};
+    if (int rc = gemm_tn<T>(h, Aop, lda, (const T*)h->Wp[l], h->Kpad[l], P, F, h->Kpad[l], es, s, h->Kreal[l])) return rc;
+    EpiWgrad ew{g + c.w_off[l], h->Kreal[l], F, h->Kpad[l], enc_in ? h->E : h->Kpad[l], enc_in ? kEncPad : h->Kpad[l]};
+    if (int rc = gemm_nt<T>(h, w.A[l], F, Aop, lda, F, h->Kpad[l], P, ew, s)) return rc;
+    prev = dst; ldprev = ldd;
+  }
+  const long long wsig = c.w_off[BN_LIN_SIGMA];
+  sigma_top_bwd_kernel<T><<<(unsigned)ceil_div_ll(P, 4), 128, 0, s>>>(prev, ldprev, params, wsig, w.SG, g_out, pitch, P, F);
+  BN_LAUNCH_CHECK();
+  {
+    SkinnyPlan sp{};
+    sp.r[sp.n++] = SkinnyRow{g + wsig, nullptr, 0, 0, F};
+    const int bx = ceil_div(F, 256);
+    int by = (int)max(1LL, min(ceil_div_ll(P, 128), (long long)(148 * 4 / bx)));
+    const long long rows = ceil_div_ll(ceil_div_ll(P, by), 32) * 32;
+    by = (int)ceil_div_ll(P, rows);
+    skinny_wgrad_kernel<T><<<dim3(bx, by), 256, 0, s>>>(sp, w.SG, 8, prev, ldprev, F, P, rows);
+    BN_LAUNCH_CHECK();
+  }
+  (void)out;
+  return BN_OK;
+}
+
+}  // namespace bn
+
+using namespace bn;
+
+extern "C" __attribute__((visibility("default")))
+int bn_mlp_normals_forward(bn_mlp* h, const float* params, float* out, int out_pitch, int n_rays, int n_samples,
+                           int flags, int normal_channel, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  BN_CHECK_ARG(h && params && out && workspace, "null pointer");
+  BN_CHECK_ARG((flags & BN_MLP_NORMAL_AN) && !(flags & BN_MLP_SIGMA_ONLY), "flags must carry BN_MLP_NORMAL_AN");
+  BN_CHECK_ARG(normal_channel >= 4 && normal_channel + 3 <= out_pitch, "normal_channel out of range");
+  if (workspace_bytes < bn_mlp_workspace_bytes(h, (int64_t)n_rays * n_samples, flags)) {
+    set_error("bn_mlp_normals_forward: workspace too small"); return BN_ERR_STATE;
+  }
+  return h->bf16 ? normals_forward_t<__nv_bfloat16>(h, params, out, out_pitch, n_rays, n_samples, flags, normal_channel, workspace, stream)
+                 : normals_forward_t<float>(h, params, out, out_pitch, n_rays, n_samples, flags, normal_channel, workspace, stream);
+}
+
+extern "C" __attribute__((visibility("default")))
+int bn_mlp_normals_backward(bn_mlp* h, const float* params, const float* out, float* g_out, int out_pitch, int n_rays,
+                            int n_samples, int flags, int normal_channel, float* g_params, void* workspace,
+                            size_t workspace_bytes, cudaStream_t stream) {
+  BN_CHECK_ARG(h && params && out && g_out && g_params && workspace, "null pointer");
+  BN_CHECK_ARG((flags & BN_MLP_NORMAL_AN) && (flags & BN_MLP_TRAIN), "needs a BN_MLP_TRAIN | BN_MLP_NORMAL_AN forward");
+  if (workspace_bytes < bn_mlp_workspace_bytes(h, (int64_t)n_rays * n_samples, flags)) {
+    set_error("bn_mlp_normals_backward: workspace too small"); return BN_ERR_STATE;
+  }
+  return h->bf16 ? normals_backward_t<__nv_bfloat16>(h, params, out, g_out, out_pitch, n_rays, n_samples, flags, normal_channel, g_params, workspace, stream)
+                 : normals_backward_t<float>(h, params, out, g_out, out_pitch, n_rays, n_samples, flags, normal_channel, g_params, workspace, stream);
+}

@@ -233,9 +233,9 @@ using namespace bn;
 extern "C" __attribute__((visibility("default"))) int bn_sample_stratified(const float* near_p, const float* far_p, int stride,
                                     const float* t_vals, const float* u, float* z_out,
                                     int n_rays, int n_samples, cudaStream_t stream) {
-  BN_CHECK_ARG(near_p && far_p && t_vals && u && z_out, "null pointer");
   BN_CHECK_ARG(n_rays >= 0 && n_samples >= 1 && stride >= 1, "bad sizes");
   if (n_rays == 0) return BN_OK;
+  BN_CHECK_ARG(near_p && far_p && t_vals && u && z_out, "null pointer");
   long long total = (long long)n_rays * n_samples;
   int threads = 256;
   stratified_kernel<<<(unsigned)ceil_div_ll(total, threads), threads, 0, stream>>>(

@@ -230,6 +230,21 @@ int bn_mlp_backward(bn_mlp* h, const float* params, const float* out, const floa
                     int n_rays, int n_samples, int flags, float* g_params,
                     void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
+/* Analytic normals (SpSBRDFNeRF.calc_normals, spsbrdfnerf.py:648-660,713-716): reverse sweep
+ * d sigma / d x through the trunk using the cosines stored by the preceding bn_mlp_forward on the
+ * same workspace (flags must carry BN_MLP_NORMAL_AN); writes -l2n(grad) into channels
+ * normal_channel..+2 of the packed rows. */
+int bn_mlp_normals_forward(bn_mlp* h, const float* params, float* out, int out_pitch, int n_rays,
+                           int n_samples, int flags, int normal_channel, void* workspace,
+                           size_t workspace_bytes, cudaStream_t stream);
+/* Second-order backward of the sweep (the double backward autograd runs through calc_normals):
+ * consumes d loss / d normal from g_out, accumulates weight gradients of the sweep into g_params,
+ * ADDS the induced d loss / d sigma into channel 3 of g_out and leaves the per-layer second-order
+ * terms in the workspace for the bn_mlp_backward call that must follow. */
+int bn_mlp_normals_backward(bn_mlp* h, const float* params, const float* out, float* g_out, int out_pitch,
+                            int n_rays, int n_samples, int flags, int normal_channel, float* g_params,
+                            void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
 /* fused Adam on the flat buffers (torch.optim.Adam semantics, main.py:150): one launch per step */
 int bn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                  float lr, float beta1, float beta2, float eps, float weight_decay, int step,

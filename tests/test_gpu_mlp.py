@@ -109,3 +109,65 @@ def test_bf16_backward_direction(cuda):
     cos = torch.nn.functional.cosine_similarity(a, b, dim=0).item()
     print("bf16 vs fp32 gradient cosine", cos)
     assert cos > 0.98
+
+
+def _an_cols(ref):
+    cols = [ref["albedo"], ref["sigma"], ref["normal_an"]]
+    for k in ("roughness", "rpv_k", "rpv_theta", "rpv_rhoc", "hpk_b", "hpk_c", "hpk_theta"):
+        if k in ref:
+            cols.append(ref[k])
+    return torch.cat(cols, -1)
+
+
+@pytest.mark.parametrize("cfg", ["rpv111", "lambertian"])
+def test_analytic_normals_forward_fp32(cuda, cfg):
+    """K-B2 forward sweep vs autograd.grad of the oracle (reference calc_normals).  Raw per-sample
+    normals are ill-conditioned where |grad sigma| ~ 0 (SURVEY §8a N-note): compare the raw gradient
+    direction where |grad| exceeds a floor, tolerance 1e-3."""
+    args, m, state = _models(cfg, cuda, normal="analystic")
+    x = _pts(1500, 12)
+    om = RT.OracleModel(state, args)
+    ref = om.forward(x, nr_an=True, apply_brdf=(cfg != "lambertian"))
+    ref = {k: v.detach() for k, v in ref.items()}
+    with torch.no_grad():
+        out = m(x.to(cuda), nr_an_on=True, apply_brdf=(cfg != "lambertian")).cpu()
+    want = _an_cols(ref)
+    assert out.shape == want.shape
+    # recompute the oracle's raw gradient norm to select well-conditioned points
+    xx = x.clone().requires_grad_(True)
+    sig = om.forward(xx, sigma_only=True)["sigma"]
+    (g,) = torch.autograd.grad(sig.sum(), xx)
+    ok = g.norm(dim=-1) > 1e-2
+    assert ok.float().mean() > 0.5
+    err = (out[ok] - want[ok]).abs().max().item()
+    assert err < 1e-3, f"analytic normals (well-conditioned points) max err {err}"
+    assert (out[:, :4] - want[:, :4]).abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize("cfg", ["rpv111", "hapke_bct"])
+def test_analytic_normals_second_order_backward_fp32(cuda, cfg):
+    """Gradient of a loss on [albedo, sigma, normal_an, brdf params] w.r.t. every weight: the double
+    backward through calc_normals (create_graph=True in the reference) vs the hand-derived sweep."""
+    args, m, state = _models(cfg, cuda, normal="analystic")
+    n = 384
+    x = _pts(n, 21)
+    kw = dict(apply_brdf=True, apply_theta=True) if cfg == "hapke_bct" else dict(apply_brdf=True)
+    om = RT.OracleModel(state, args, requires_grad=True)
+    ref = om.forward(x, nr_an=True, **kw)
+    want = _an_cols(ref)
+    G = torch.randn(want.shape, generator=torch.Generator().manual_seed(8))
+    G[:, 4:7] *= 0.05      # keep the ill-conditioned normal term from dominating the comparison
+    (want * G).sum().backward()
+    out = m(x.to(cuda), nr_an_on=True, **{("apply_brdf" if k == "apply_brdf" else k): v for k, v in kw.items()})
+    m.flat_grads.zero_()
+    (out * G.to(cuda)).sum().backward()
+    worst = 0.0
+    for name, p in m.named_parameters():
+        r = om.p[name].grad
+        if r is None:
+            continue
+        d = (p.grad.cpu() - r).abs().max().item()
+        s = r.abs().max().item()
+        worst = max(worst, d / (s + 1e-12))
+        assert d <= 5e-3 * s + 1e-6, f"{cfg} second-order grad {name}: max diff {d} (scale {s})"
+    print(f"{cfg}: worst relative second-order grad error {worst:.2e}")
