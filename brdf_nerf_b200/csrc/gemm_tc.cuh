@@ -54,6 +54,21 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// multicast variant: the box lands at the same CTA-relative smem offset of every CTA in `mask`, and
+// each destination CTA's mbarrier (same offset) receives the complete_tx
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_nctaid_x() { uint32_t r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -71,6 +86,11 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// commit that arrives on the barrier at the same offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
@@ -110,7 +130,11 @@ struct Work {
   int kb_total, kb_per_split;     // k-blocks (of kBK) in the reduction dimension
 };
 
-template <int BN, int STAGES, bool kNT, class Epi>
+// CL = CTAs per cluster along the output-row (M) dimension.  The CL CTAs of a cluster work on CL
+// consecutive row tiles of the SAME column tile / reduction range and share the B operand: each CTA
+// fetches 1/CL of every B stage and multicasts it to all of them, which divides the L2->SMEM traffic
+// of B (the dominant stream: the whole weight matrix per 128 points) by CL.
+template <int BN, int STAGES, bool kNT, int CL, class Epi>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Work wk, Epi epi) {
   constexpr uint32_t A_BYTES = kBM * kBK * 2;
@@ -127,20 +151,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int n_items = wk.m_tiles * wk.n_tiles * wk.splits;
+  const int m_groups = (wk.m_tiles + CL - 1) / CL;                 // row tiles are handed out CL at a time
+  const int n_items = m_groups * wk.n_tiles * wk.splits;
+  const int crank = (CL > 1) ? (int)cluster_ctarank() : 0;
+  const int item0 = (CL > 1) ? (int)cluster_id_x() : (int)blockIdx.x;
+  const int item_step = (CL > 1) ? (int)cluster_nctaid_x() : (int)gridDim.x;
+  constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
   fence_before_sync();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();          // peers' barriers are initialised before anyone signals them
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -148,26 +178,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-        const int split = it / (wk.m_tiles * wk.n_tiles);
-        const int t = it % (wk.m_tiles * wk.n_tiles);
-        const int m_blk = t / wk.n_tiles, n_blk = t % wk.n_tiles;
+      for (int it = item0; it < n_items; it += item_step) {
+        const int split = it / (m_groups * wk.n_tiles);
+        const int t = it % (m_groups * wk.n_tiles);
+        const int m_blk = (t / wk.n_tiles) * CL + crank, n_blk = t % wk.n_tiles;
         const int kb0 = split * wk.kb_per_split;
         const int kb1 = min(wk.kb_total, kb0 + wk.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_wait(&empty[stage], phase ^ 1);          // every CTA of the cluster has drained this slot
           mbar_expect_tx(&full[stage], A_BYTES + B_BYTES);
           uint8_t* a = sA + stage * A_BYTES;
           uint8_t* b = sB + stage * B_BYTES;
           if (!kNT) {
             tma_load_2d(a, &tmA, &full[stage], kb * kBK, m_blk * kBM);
-            tma_load_2d(b, &tmB, &full[stage], kb * kBK, n_blk * BN);
+            if (CL == 1) tma_load_2d(b, &tmB, &full[stage], kb * kBK, n_blk * BN);
+            else tma_load_2d_mc(b + crank * (B_BYTES / CL), &tmB, &full[stage], kb * kBK, n_blk * BN + crank * (BN / CL), kMask);
           } else {
             // boxes of 64 (contiguous MN) x 64 (reduction rows); one box per 64 output rows/cols
 #pragma unroll
             for (int c = 0; c < kBM / 64; ++c) tma_load_2d(a + c * 8192, &tmA, &full[stage], m_blk * kBM + c * 64, kb * kBK);
+            if (CL == 1) {
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c) tma_load_2d(b + c * 8192, &tmB, &full[stage], n_blk * BN + c * 64, kb * kBK);
+              for (int c = 0; c < BN / 64; ++c) tma_load_2d(b + c * 8192, &tmB, &full[stage], n_blk * BN + c * 64, kb * kBK);
+            } else {
+#pragma unroll
+              for (int c = 0; c < BN / 64 / CL; ++c) {
+                const int cc = crank * (BN / 64 / CL) + c;
+                tma_load_2d_mc(b + cc * 8192, &tmB, &full[stage], n_blk * BN + cc * 64, kb * kBK, kMask);
+              }
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -179,8 +218,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       constexpr uint32_t idesc = make_idesc(BN, kNT);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-        const int split = it / (wk.m_tiles * wk.n_tiles);
+      for (int it = item0; it < n_items; it += item_step) {
+        const int split = it / (m_groups * wk.n_tiles);
         const int kb0 = split * wk.kb_per_split;
         const int kb1 = min(wk.kb_total, kb0 + wk.kb_per_split);
         mbar_wait(&tempty[acc], acc_phase ^ 1);
@@ -203,7 +242,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty[stage]);
+          if (CL == 1) umma_commit(&empty[stage]); else umma_commit_mc(&empty[stage], kMask);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull[acc]);
@@ -214,9 +253,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== epilogue =====================
     const int q = warp - 4;                       // TMEM lane quadrant == warp % 4
     int acc = 0; uint32_t acc_phase = 0;
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-      const int t = it % (wk.m_tiles * wk.n_tiles);
-      const int m_blk = t / wk.n_tiles, n_blk = t % wk.n_tiles;
+    for (int it = item0; it < n_items; it += item_step) {
+      const int t = it % (m_groups * wk.n_tiles);
+      const int m_blk = (t / wk.n_tiles) * CL + crank, n_blk = t % wk.n_tiles;
       mbar_wait(&tfull[acc], acc_phase);
       fence_after_sync();
       const int row = m_blk * kBM + q * 32 + lane;
@@ -234,6 +273,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   fence_before_sync();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();          // no CTA leaves while a peer can still write into its smem
   if (warp == 2) { fence_after_sync(); tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
@@ -251,6 +291,27 @@ template <int BN, bool kNT> constexpr int smem_bytes(int stages) {
   return stages * (kBM * kBK * 2 + BN * kBK * 2) + (2 * stages + 4) * 8 + 16 + 1024;
 }
 
+constexpr int kClusterM = 2;       // CTAs per cluster sharing (multicasting) the B operand
+
+// persistent launch: one CTA per SM (rounded down to whole clusters), cluster dims (CL,1,1)
+template <int CL, class Kern, class Epi>
+int launch_kernel(Kern kern, int smem, int num_sms, int items, const CUtensorMap& ma, const CUtensorMap& mb, const Work& wk,
+                  const Epi& epi, cudaStream_t s, const char* name) {
+  BN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  cudaLaunchConfig_t cfg{};
+  const int clusters = min(items, num_sms / CL);
+  cfg.gridDim = dim3(clusters * CL);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  BN_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, wk, epi));
+  return after_launch(name);
+}
+
 // A:[M,K] (ld lda), B:[N,K]: C = A B^T through `epi`
 template <int BN, class Epi>
 int launch_tn(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* B, long long ldb,
@@ -261,12 +322,12 @@ int launch_tn(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* B, lon
   if (int rc = make_map_bf16(&ma, A, M, K, lda, kBK, kBM)) return rc;
   if (int rc = make_map_bf16(&mb, B, N, K, ldb, kBK, BN)) return rc;
   Work wk{(int)ceil_div_ll(M, kBM), ceil_div(N, BN), 1, K / kBK, K / kBK};
-  auto kern = gemm_tc_kernel<BN, STAGES, false, Epi>;
   constexpr int smem = smem_bytes<BN, false>(STAGES);
-  BN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  const int items = wk.m_tiles * wk.n_tiles;
-  kern<<<min(items, num_sms), kThreads, smem, s>>>(ma, mb, wk, epi);
-  return after_launch("gemm_tc_kernel<tn>");
+  if (wk.m_tiles >= 2 * kClusterM && BN >= 64 * kClusterM)
+    return launch_kernel<kClusterM>(gemm_tc_kernel<BN, STAGES, false, kClusterM, Epi>, smem, num_sms,
+                                    ceil_div(wk.m_tiles, kClusterM) * wk.n_tiles, ma, mb, wk, epi, s, "gemm_tc_kernel<tn,mc>");
+  return launch_kernel<1>(gemm_tc_kernel<BN, STAGES, false, 1, Epi>, smem, num_sms, wk.m_tiles * wk.n_tiles, ma, mb, wk, epi, s,
+                          "gemm_tc_kernel<tn>");
 }
 
 // A:[P,Mo] (ld lda), B:[P,No]: C[Mo,No] = A^T B through `epi` (atomic accumulate), split over P
@@ -285,12 +346,12 @@ int launch_nt(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* B, lon
   int splits = max(1, min(ceil_div(num_sms, tiles), ceil_div(wk.kb_total, 8)));
   wk.kb_per_split = ceil_div(wk.kb_total, splits);
   wk.splits = ceil_div(wk.kb_total, wk.kb_per_split);
-  auto kern = gemm_tc_kernel<BN, STAGES, true, Epi>;
   constexpr int smem = smem_bytes<BN, true>(STAGES);
-  BN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  const int items = tiles * wk.splits;
-  kern<<<min(items, num_sms), kThreads, smem, s>>>(ma, mb, wk, epi);
-  return after_launch("gemm_tc_kernel<nt>");
+  if (wk.m_tiles % kClusterM == 0 && BN >= 64 * kClusterM)
+    return launch_kernel<kClusterM>(gemm_tc_kernel<BN, STAGES, true, kClusterM, Epi>, smem, num_sms,
+                                    (wk.m_tiles / kClusterM) * wk.n_tiles * wk.splits, ma, mb, wk, epi, s, "gemm_tc_kernel<nt,mc>");
+  return launch_kernel<1>(gemm_tc_kernel<BN, STAGES, true, 1, Epi>, smem, num_sms, tiles * wk.splits, ma, mb, wk, epi, s,
+                          "gemm_tc_kernel<nt>");
 }
 
 }  // namespace tc

@@ -339,8 +339,9 @@ static int forward_t(bn_mlp* h, const float* params, const float* origins, int o
     const T* A; long long lda;
     if (l == 0 || l == h->skip) { A = w.X3; lda = w.ldx3; } else { A = w.H[l - 1]; lda = w.Hld[l - 1]; }
     if (l == 0) {
-      // first layer: sin(30 z) — accurate sincos even on the bf16 path (arguments reach |30 z|)
-      EpiSin<T, false> epi{params + c.b_off[l], 30.0f, w.H[l], w.Hld[l], keep_c ? w.C[l] : nullptr, F, (int)P, F};
+      // first layer: sin(30 lin), |30 lin| <= 30: the MUFU path is exact to ~2e-6 there, far below
+      // the bf16 resolution of the stored activation; the fp32 mode keeps the accurate sincosf
+      EpiSin<T, kFast> epi{params + c.b_off[l], 30.0f, w.H[l], w.Hld[l], keep_c ? w.C[l] : nullptr, F, (int)P, F};
       if (int rc = gemm_tn<T>(h, A, lda, (const T*)h->Wp[l], h->Kpad[l], P, F, h->Kpad[l], epi, s, h->Kreal[l])) return rc;
     } else {
       EpiSin<T, kFast> epi{params + c.b_off[l], 1.0f, w.H[l], w.Hld[l], keep_c ? w.C[l] : nullptr, F, (int)P, F};

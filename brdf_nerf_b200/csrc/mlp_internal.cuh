@@ -101,22 +101,40 @@ __global__ void __launch_bounds__(256) skinny_wgrad_kernel(SkinnyPlan sp, const 
   }
 }
 
-// dst[c] += sum_p X[p][c]   (bias gradients), 8 columns per thread
+// dst[c] += sum_p X[p][c]   (bias gradients).  8 columns per thread, 4 rows in flight per thread so
+// that enough 16-byte loads are outstanding to stream at HBM speed.
 template <typename T>
-__global__ void __launch_bounds__(128) colsum_kernel(const T* __restrict__ X, long long ldx, int ncols, long long P,
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ X, long long ldx, int ncols, long long P,
                                                      long long rows_per_block, float* __restrict__ dst) {
-  const int c = (blockIdx.x * 128 + threadIdx.x) * 8;
-  if (c >= ncols) return;
+  __shared__ float red[4][64 * 8];
+  const int tx = threadIdx.x % 64, ty = threadIdx.x / 64;      // 64 column groups x 4 row lanes
+  const int c = (blockIdx.x * 64 + tx) * 8;
   const long long p0 = (long long)blockIdx.y * rows_per_block;
   const long long p1 = min(P, p0 + rows_per_block);
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (long long p = p0; p < p1; ++p) {
-    float v[8]; load8<T>(X + p * ldx + c, v);
+  if (c < ncols) {
+    long long p = p0 + ty;
+    for (; p + 12 < p1; p += 16) {
+      float v0[8], v1[8], v2[8], v3[8];
+      load8<T>(X + p * ldx + c, v0); load8<T>(X + (p + 4) * ldx + c, v1);
+      load8<T>(X + (p + 8) * ldx + c, v2); load8<T>(X + (p + 12) * ldx + c, v3);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] += v[j];
+      for (int j = 0; j < 8; ++j) acc[j] += (v0[j] + v1[j]) + (v2[j] + v3[j]);
+    }
+    for (; p < p1; p += 4) {
+      float v[8]; load8<T>(X + p * ldx + c, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) atomicAdd(dst + c + j, acc[j]);
+  for (int j = 0; j < 8; ++j) red[ty][tx * 8 + j] = acc[j];
+  __syncthreads();
+  if (ty == 0 && c < ncols) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      atomicAdd(dst + c + j, (red[0][tx * 8 + j] + red[1][tx * 8 + j]) + (red[2][tx * 8 + j] + red[3][tx * 8 + j]));
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -224,11 +242,11 @@ static int gemm_nt(const bn_mlp* h, const T* A, long long lda, const T* B, long 
 
 template <typename T>
 static int colsum(const T* X, long long ldx, int ncols, long long P, float* dst, cudaStream_t s) {
-  const int bx = ceil_div(ncols, 128 * 8);
-  int by = (int)max(1LL, min(ceil_div_ll(P, 64), (long long)(148 * 8 / bx)));
+  const int bx = ceil_div(ncols, 64 * 8);
+  int by = (int)max(1LL, min(ceil_div_ll(P, 64), (long long)(148 * 4 / bx)));
   const long long rows = ceil_div_ll(P, by);
   by = (int)ceil_div_ll(P, rows);
-  colsum_kernel<T><<<dim3(bx, by), 128, 0, s>>>(X, ldx, ncols, P, rows, dst);
+  colsum_kernel<T><<<dim3(bx, by), 256, 0, s>>>(X, ldx, ncols, P, rows, dst);
   return after_launch("colsum_kernel");
 }
 

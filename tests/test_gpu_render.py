@@ -59,7 +59,10 @@ def test_against_reference_golden(cuda, name):
             assert k + "_coarse" in res, f"missing result key {k}_coarse"
             got = res[k + "_coarse"].cpu().numpy()
             assert got.shape == g["ref_" + k].shape, (k, got.shape, g["ref_" + k].shape)
-            d = np.abs(got - g["ref_" + k]).max()
+            ref = g["ref_" + k]
+            # `brdf` is unbounded (Hapke values reach 1e4 at grazing angles): relative tolerance there
+            scale = np.maximum(1.0, np.abs(ref)) if k == "brdf" else 1.0
+            d = (np.abs(got - ref) / scale).max()
             assert d <= TOL, f"{name}: {k} differs from the reference by {d}"
     for nk in ("normal_an", "normal_lr"):
         if f"ref_{nk}_acc" in g:
