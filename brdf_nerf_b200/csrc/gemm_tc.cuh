@@ -319,11 +319,13 @@ int launch_tn(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* B, lon
   constexpr int STAGES = (BN == 256) ? 4 : 6;
   if (K % kBK) { set_error("tc::launch_tn: K=%d not a multiple of 64", K); return BN_ERR_ARG; }
   CUtensorMap ma, mb;
-  if (int rc = make_map_bf16(&ma, A, M, K, lda, kBK, kBM)) return rc;
-  if (int rc = make_map_bf16(&mb, B, N, K, ldb, kBK, BN)) return rc;
   Work wk{(int)ceil_div_ll(M, kBM), ceil_div(N, BN), 1, K / kBK, K / kBK};
+  const bool clustered = wk.m_tiles >= 2 * kClusterM && BN >= 64 * kClusterM;
+  if (int rc = make_map_bf16(&ma, A, M, K, lda, kBK, kBM)) return rc;
+  // clustered: every CTA fetches (and multicasts) BN / kClusterM rows of the B tile per stage
+  if (int rc = make_map_bf16(&mb, B, N, K, ldb, kBK, clustered ? BN / kClusterM : BN)) return rc;
   constexpr int smem = smem_bytes<BN, false>(STAGES);
-  if (wk.m_tiles >= 2 * kClusterM && BN >= 64 * kClusterM)
+  if (clustered)
     return launch_kernel<kClusterM>(gemm_tc_kernel<BN, STAGES, false, kClusterM, Epi>, smem, num_sms,
                                     ceil_div(wk.m_tiles, kClusterM) * wk.n_tiles, ma, mb, wk, epi, s, "gemm_tc_kernel<tn,mc>");
   return launch_kernel<1>(gemm_tc_kernel<BN, STAGES, false, 1, Epi>, smem, num_sms, wk.m_tiles * wk.n_tiles, ma, mb, wk, epi, s,

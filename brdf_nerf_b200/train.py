@@ -51,6 +51,17 @@ def loss_and_grads(args, outs, st, batch: RayBatch, use_depth: bool):
     return loss, g_rgb, g_depth
 
 
+def allreduce_grads_(flat_grads: torch.Tensor, world_size: int, group=None) -> float:
+    """Data-parallel gradient exchange: ONE all-reduce (sum) of the flat fp32 bucket over
+    NCCL/NVLink (gloo in the CPU tests).  Returns the scale (1/world) the optimizer must apply — the
+    averaging is folded into the fused Adam kernel instead of a separate pass over the bucket.
+    Matches what DDP does in the reference (Lightning `gpus > 1`, main.py:720-731): per-rank mean loss,
+    gradients averaged over ranks."""
+    if world_size > 1:
+        torch.distributed.all_reduce(flat_grads, op=torch.distributed.ReduceOp.SUM, group=group)
+    return 1.0 / world_size
+
+
 class Trainer:
     def __init__(self, model, args, lr: Optional[float] = None, world_size: int = 1, process_group=None,
                  use_graph: bool = False):
@@ -83,11 +94,10 @@ class Trainer:
 
     def _reduce_and_update(self):
         model = self.model
-        if self.world > 1:
-            torch.distributed.all_reduce(model.flat_grads, group=self.pg)      # NCCL sum over NVLink
+        scale = allreduce_grads_(model.flat_grads, self.world, self.pg)
         self.step_count += 1
         ops.adam_step(model.flat_params, model.flat_grads, self.m, self.v, self.lr, self.step_count,
-                      grad_scale=1.0 / self.world)
+                      grad_scale=scale)
         model._synced_version = -1            # the packed bf16 copies are stale now
 
     def step(self, batch: RayBatch, draws=None, apply_brdf=False, apply_theta=False, cos_irra_on=False,
@@ -124,5 +134,4 @@ class Trainer:
                 dst.copy_(src, non_blocking=True)
         self._graph.replay()
         self._reduce_and_update()
-        self.model._synced_version = self.model._flat._version   # the graph re-packs the weights itself
         return self._loss

@@ -1,0 +1,115 @@
+"""CPU: host-side logic — config POD, synthetic rays, module surface / flat parameter storage,
+loss restatement used by the fused step, and the no-CPU-fallback rule."""
+import numpy as np
+import pytest
+import torch
+
+from brdf_nerf_b200.config import PathConfig, make_args, named_config
+from brdf_nerf_b200.models import load_model
+from brdf_nerf_b200.synth import make_rays, make_tile_rays
+
+
+def test_args_defaults_and_pod():
+    a = make_args()
+    assert (a.n_samples, a.guided_samples, a.fc_feat, a.fc_layers, a.chunk) == (64, 64, 512, 8, 5120)
+    assert a.sc_lambda == 0.0
+    with pytest.raises(TypeError):
+        make_args(not_an_option=1)
+    c = PathConfig.from_args(named_config("rpv111"))
+    assert c.brdf == "rpv" and c.normal_an and c.n_freq_xyz == 10 and c.skip_layer == 4
+    assert PathConfig.from_args(named_config("microfacet")).brdf == "microfacet"
+    assert PathConfig.from_args(named_config("hapke_bct")).hapke_theta
+
+
+def test_synthetic_rays_are_deterministic_and_well_formed():
+    a, b = make_rays(257, depth_supervision=True), make_rays(257, depth_supervision=True)
+    assert torch.equal(a.rays, b.rays) and torch.equal(a.target_depths, b.target_depths)
+    r = a.rays
+    assert r.shape == (257, 11) and r.dtype == torch.float32
+    assert torch.allclose(r[:, 3:6].norm(dim=-1), torch.ones(257), atol=1e-6)
+    assert torch.allclose(r[:, 8:11].norm(dim=-1), torch.ones(257), atol=1e-6)
+    assert (r[:, 5] < 0).all() and (r[:, 10] > 0).all() and (r[:, 6] == 0).all()
+    d = a.target_depths[:, 0]
+    assert ((d > 0) & (d < r[:, 7])).all()
+    s0, s1 = a.shard(0, 2), a.shard(1, 2)
+    assert torch.equal(torch.cat([s0.rays, s1.rays]), r[:256])
+    assert make_tile_rays(8, 16).shape == (128, 11)
+
+
+@pytest.mark.parametrize("cfg,n_params", [("lambertian", 2295812), ("rpv111", 2690567), ("rpv111_multi", 2692109),
+                                          ("hapke_bct", 2690567), ("microfacet", 2427397)])
+def test_module_surface_and_param_counts(cfg, n_params):
+    args = named_config(cfg)
+    torch.manual_seed(0)
+    m = load_model(args)
+    assert sum(p.numel() for p in m.parameters()) == n_params          # SURVEY §6 [probe]
+    keys = list(m.state_dict())
+    assert keys[:2] == ["fc_net.0.weight", "fc_net.0.bias"] and "sigma_from_xyz.0.weight" in keys
+    assert m.fc_net[8].weight.shape == (512, 572)                      # skip layer input = [PE(60) | h(512)]
+    for attr in ("number_of_outputs", "number_of_outputs_brdf", "normal", "sun_v", "indirect_light", "beta",
+                 "roughness", "RPV", "MultiBRDF", "rgb_padding", "glossy_scale", "args"):
+        assert hasattr(m, attr)
+    # flat storage: parameters are views of one buffer, state_dict round-trips through it
+    flat = m.flat_params
+    assert flat.numel() == n_params
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    off = m.offsets()
+    assert torch.equal(flat[off["fc_net.2.weight"]:off["fc_net.2.weight"] + 512 * 512].view(512, 512), sd["fc_net.2.weight"])
+    m.load_state_dict({k: v + 1 for k, v in sd.items()})
+    assert torch.equal(m.flat_params[:10], sd["fc_net.0.weight"].reshape(-1)[:10] + 1)
+    m.freeze("fc_net")
+    assert not m.fc_net[0].weight.requires_grad and m.sigma_from_xyz[0].weight.requires_grad
+
+
+def test_unsupported_model_options_fail_loudly():
+    with pytest.raises(ValueError):
+        load_model(make_args(model="sps-nerf"))
+    with pytest.raises(NotImplementedError):
+        load_model(named_config("lambertian", beta=True))
+    with pytest.raises(NotImplementedError):
+        load_model(named_config("lambertian", input_viewdir=1))
+
+
+def test_no_cpu_fallback_on_the_product_path():
+    from brdf_nerf_b200 import _lib as L
+    from brdf_nerf_b200.rendering import render_rays
+    args = named_config("lambertian")
+    torch.manual_seed(0)
+    m = load_model(args)
+    with pytest.raises(L.BnError):
+        render_rays({"coarse": m}, args, make_rays(4).rays, None)
+    with pytest.raises(L.BnError):
+        m(torch.zeros(4, 3))
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: no module of the product package may import it."""
+    import os
+    import re
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "brdf_nerf_b200")
+    for dirpath, _, files in os.walk(root):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{f} imports oracle"
+
+
+def test_fused_step_loss_equals_reference_loss_restatement():
+    """train.loss_and_grads (closed form, no host sync) == oracle losses + autograd, on CPU tensors."""
+    from brdf_nerf_b200.train import loss_and_grads
+    from oracle import losses_torch as LT
+    g = torch.Generator().manual_seed(0)
+    n, s = 64, 128
+    args = named_config("lambertian_ds")
+    batch = make_rays(n, depth_supervision=True)
+    rgb = torch.rand(n, 3, generator=g, requires_grad=True)
+    z = torch.sort(torch.rand(n, s, generator=g) * 0.6, -1)[0]
+    w = torch.softmax(torch.randn(n, s, generator=g), -1)
+    depth = ((w * z).sum(-1) + 0.05 * torch.randn(n, generator=g)).requires_grad_(True)
+    res = {"rgb_coarse": rgb, "depth_coarse": depth, "weights_coarse": w, "z_vals_coarse": z}
+    ref = LT.train_loss(res, batch, args)
+    ref.backward()
+    outs = dict(rgb=rgb.detach(), depth=depth.detach(), weights=w, z=z)
+    loss, g_rgb, g_depth = loss_and_grads(args, outs, None, batch, True)
+    assert abs(loss.item() - ref.item()) < 1e-6
+    assert torch.allclose(g_rgb, rgb.grad, atol=1e-7) and torch.allclose(g_depth, depth.grad, atol=1e-7)
