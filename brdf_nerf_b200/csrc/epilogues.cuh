@@ -92,6 +92,9 @@ struct EpiBias {
 
 // dgrad: out = (acc [+ addend]) [* mulc] [+ add2]   (dZ_{l-1} = (dZ_l W_l [+ direct grads]) ⊙ C_{l-1}
 // [+ second-order term]); raw_out optionally receives (acc + addend) before the mask.
+// colsum (tcgen05 path only, where the 32 lanes of a warp hold 32 consecutive rows of the same
+// columns): the bias gradient sum_rows(out) is reduced across the warp with a 31-shuffle butterfly
+// and added with one coalesced red.global per 32 columns — no separate pass over dZ.
 template <typename T>
 struct EpiDgrad {
   const T* addend; long long lda;    // nullable
@@ -99,28 +102,64 @@ struct EpiDgrad {
   T* out; long long ld; int M, N;
   T* raw_out = nullptr; long long ldr = 0;
   const T* add2 = nullptr; long long ld2 = 0;
+  float* colsum = nullptr;
   template <int n> __device__ __forceinline__ void apply(int row, int col0, const float (&acc)[n]) const {
-    if (row >= M || col0 >= N) return;
+    if (col0 >= N) return;                       // warp-uniform
+    const bool valid = row < M;
     float o[n];
 #pragma unroll
-    for (int j = 0; j < n; ++j) o[j] = acc[j];
-    if (addend) {
-      float t[n]; Pack<T, n>::load(addend + (long long)row * lda + col0, t);
+    for (int j = 0; j < n; ++j) o[j] = valid ? acc[j] : 0.f;
+    if (valid) {
+      if (addend) {
+        float t[n]; Pack<T, n>::load(addend + (long long)row * lda + col0, t);
 #pragma unroll
-      for (int j = 0; j < n; ++j) o[j] += t[j];
-    }
-    if (raw_out) Pack<T, n>::store(raw_out + (long long)row * ldr + col0, o);
-    if (mulc) {
-      float t[n]; Pack<T, n>::load(mulc + (long long)row * ldm + col0, t);
+        for (int j = 0; j < n; ++j) o[j] += t[j];
+      }
+      if (raw_out) Pack<T, n>::store(raw_out + (long long)row * ldr + col0, o);
+      if (mulc) {
+        float t[n]; Pack<T, n>::load(mulc + (long long)row * ldm + col0, t);
 #pragma unroll
-      for (int j = 0; j < n; ++j) o[j] *= t[j];
-    }
-    if (add2) {
-      float t[n]; Pack<T, n>::load(add2 + (long long)row * ld2 + col0, t);
+        for (int j = 0; j < n; ++j) o[j] *= t[j];
+      }
+      if (add2) {
+        float t[n]; Pack<T, n>::load(add2 + (long long)row * ld2 + col0, t);
 #pragma unroll
-      for (int j = 0; j < n; ++j) o[j] += t[j];
+        for (int j = 0; j < n; ++j) o[j] += t[j];
+      }
+      Pack<T, n>::store(out + (long long)row * ld + col0, o);
     }
-    Pack<T, n>::store(out + (long long)row * ld + col0, o);
+    if constexpr (n == 32) {
+      if (colsum) {
+        const int lane = threadIdx.x & 31;
+#pragma unroll
+        for (int s = 16; s >= 1; s >>= 1) {
+          const bool hi = (lane & s) != 0;
+#pragma unroll
+          for (int j = 0; j < s; ++j) {
+            const float send = hi ? o[j] : o[j + s];
+            const float keep = hi ? o[j + s] : o[j];
+            o[j] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+          }
+        }
+        atomicAdd(colsum + col0 + lane, o[0]);     // lane L now holds the sum of column col0 + L
+      }
+    }
+  }
+};
+
+// skinny weight gradients through the NT GEMM: output row o (< n_rows) is the gradient of one
+// head's second-layer weight row; only columns [c0, c1) of it are real and go to dst[col - c0].
+struct EpiSkinnyRow { float* dst; int c0, c1; };
+struct EpiSkinny {
+  int n_rows; EpiSkinnyRow r[16];
+  template <int n> __device__ __forceinline__ void apply(int row, int col0, const float (&acc)[n]) const {
+    if (row >= n_rows) return;
+    const EpiSkinnyRow q = r[row];
+#pragma unroll
+    for (int j = 0; j < n; ++j) {
+      const int col = col0 + j;
+      if (col >= q.c0 && col < q.c1) atomicAdd(q.dst + (col - q.c0), acc[j]);
+    }
   }
 };
 

@@ -65,65 +65,94 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf
 __device__ __forceinline__ float softplusf_(float x) { return x > 20.f ? x : log1pf(expf(x)); }
 
 // ------------------------------------------------------------------------------------------------
-// second layers of all heads + sigma + learned normal: one warp per point, lanes split K.
+// second layers of all heads + sigma + learned normal.  A warp evaluates kQP points at a time (lanes
+// split K, weights fetched once per kQP points, kQP independent load streams in flight) and walks
+// the points with a grid-stride loop.
+constexpr int kQP = 4;
+
 template <typename T>
-__global__ void __launch_bounds__(128) heads_fwd_kernel(HeadPlan hp, const float* __restrict__ params,
+__global__ void __launch_bounds__(256) heads_fwd_kernel(HeadPlan hp, const float* __restrict__ params,
                                                         const T* __restrict__ Hlast, long long ldh, int F,
                                                         const T* __restrict__ HD, long long ldd,
                                                         float* __restrict__ out, int pitch, long long P, bool sigma_only) {
   const int lane = threadIdx.x % 32;
-  const long long p = (long long)blockIdx.x * 4 + threadIdx.x / 32;
-  if (p >= P) return;
-  // sigma (+ learned normal) from the trunk's last activation
-  float s_acc = 0.f, g_acc[3] = {0.f, 0.f, 0.f};
-  for (int i = lane * 8; i < F; i += 256) {
-    float h[8]; load8g<T>(Hlast + p * ldh + i, h);
+  const long long warp = (long long)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  const long long nwarps = (long long)gridDim.x * (blockDim.x / 32);
+  for (long long p0 = warp * kQP; p0 < P; p0 += nwarps * kQP) {
+    long long pq[kQP];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      s_acc = fmaf(h[j], __ldg(params + hp.wsig + i + j), s_acc);
+    for (int q = 0; q < kQP; ++q) pq[q] = min(p0 + q, P - 1);
+    // sigma (+ learned normal) from the trunk's last activation
+    float s_acc[kQP], g_acc[kQP][3];
+#pragma unroll
+    for (int q = 0; q < kQP; ++q) { s_acc[q] = 0.f; g_acc[q][0] = g_acc[q][1] = g_acc[q][2] = 0.f; }
+    for (int i = lane * 8; i < F; i += 256) {
+      float h[kQP][8];
+#pragma unroll
+      for (int q = 0; q < kQP; ++q) load8g<T>(Hlast + pq[q] * ldh + i, h[q]);
+      float w[8];
+      load8<float>(params + hp.wsig + i, w);
+#pragma unroll
+      for (int q = 0; q < kQP; ++q)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s_acc[q] = fmaf(h[q][j], w[j], s_acc[q]);
       if (hp.ch_nlr >= 0) {
 #pragma unroll
-        for (int o = 0; o < 3; ++o) g_acc[o] = fmaf(h[j], __ldg(params + hp.wg + (long long)o * F + i + j), g_acc[o]);
-      }
-    }
-  }
-  s_acc = warp_sum(s_acc);
-  const float sigma = softplusf_(s_acc + __ldg(params + hp.bsig));
-  if (sigma_only) { if (lane == 0) out[p] = sigma; return; }
-  float* row = out + p * pitch;
-  if (lane == 0) row[hp.ch_sigma] = sigma;
-  if (hp.ch_nlr >= 0) {
-    float g[3];
+        for (int o = 0; o < 3; ++o) {
+          load8<float>(params + hp.wg + (long long)o * F + i, w);
 #pragma unroll
-    for (int o = 0; o < 3; ++o) g[o] = warp_sum(g_acc[o]) + __ldg(params + hp.bg + o);
-    const float inv = 1.0f / sqrtf(fmaxf(g[0] * g[0] + g[1] * g[1] + g[2] * g[2], 1.1920929e-07f));
-    if (lane < 3) row[hp.ch_nlr + lane] = -g[lane] * inv;
-  }
-  for (int b = 0; b < hp.n_blocks; ++b) {
-    float acc[kMaxOut];
+          for (int q = 0; q < kQP; ++q)
 #pragma unroll
-    for (int o = 0; o < kMaxOut; ++o) acc[o] = 0.f;
-    for (int i = lane * 8; i < hp.HH; i += 256) {
-      float h[8]; load8g<T>(HD + p * ldd + (long long)b * hp.HH + i, h);
-#pragma unroll
-      for (int o = 0; o < kMaxOut; ++o) {
-        if (o < hp.n_out && hp.o[o].block == b) {
-          const float* w = params + hp.o[o].w_off + i;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[o] = fmaf(h[j], __ldg(w + j), acc[o]);
+            for (int j = 0; j < 8; ++j) g_acc[q][o] = fmaf(h[q][j], w[j], g_acc[q][o]);
         }
       }
     }
+    const float bsig = __ldg(params + hp.bsig);
 #pragma unroll
-    for (int o = 0; o < kMaxOut; ++o) {
-      if (o < hp.n_out && hp.o[o].block == b) {
-        const float pre = warp_sum(acc[o]) + __ldg(params + hp.o[o].b_off);
-        const float s = sigmoidf_(pre);
+    for (int q = 0; q < kQP; ++q) {
+      const float sigma = softplusf_(warp_sum(s_acc[q]) + bsig);
+      if (lane == 0 && p0 + q < P) {
+        if (sigma_only) out[p0 + q] = sigma; else out[(p0 + q) * pitch + hp.ch_sigma] = sigma;
+      }
+    }
+    if (sigma_only) continue;
+    if (hp.ch_nlr >= 0) {
+#pragma unroll
+      for (int q = 0; q < kQP; ++q) {
+        float g[3];
+#pragma unroll
+        for (int o = 0; o < 3; ++o) g[o] = warp_sum(g_acc[q][o]) + __ldg(params + hp.bg + o);
+        const float inv = 1.0f / sqrtf(fmaxf(g[0] * g[0] + g[1] * g[1] + g[2] * g[2], 1.1920929e-07f));
+        if (lane == 0 && p0 + q < P) {
+          float* row = out + (p0 + q) * pitch + hp.ch_nlr;
+          row[0] = -g[0] * inv; row[1] = -g[1] * inv; row[2] = -g[2] * inv;
+        }
+      }
+    }
+    for (int o = 0; o < hp.n_out; ++o) {
+      const OutDesc d = hp.o[o];
+      float acc[kQP];
+#pragma unroll
+      for (int q = 0; q < kQP; ++q) acc[q] = 0.f;
+      for (int i = lane * 8; i < hp.HH; i += 256) {
+        float w[8];
+        load8<float>(params + d.w_off + i, w);
+#pragma unroll
+        for (int q = 0; q < kQP; ++q) {
+          float h[8]; load8g<T>(HD + pq[q] * ldd + (long long)d.block * hp.HH + i, h);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[q] = fmaf(h[j], w[j], acc[q]);
+        }
+      }
+      const float bo = __ldg(params + d.b_off);
+#pragma unroll
+      for (int q = 0; q < kQP; ++q) {
+        const float s = sigmoidf_(warp_sum(acc[q]) + bo);
         float v = s;
-        if (hp.o[o].xform == XF_K) v = (s - 0.5f) * 2.0f + 1.0f;
-        else if (hp.o[o].xform == XF_THETA_RPV) v = (s - 0.5f) * 2.0f;
-        else if (hp.o[o].xform == XF_THETA_H) v = s * (float)(M_PI * 30.0 / 180.0);
-        if (lane < hp.o[o].rep) row[hp.o[o].ch + lane] = v;
+        if (d.xform == XF_K) v = (s - 0.5f) * 2.0f + 1.0f;
+        else if (d.xform == XF_THETA_RPV) v = (s - 0.5f) * 2.0f;
+        else if (d.xform == XF_THETA_H) v = s * (float)(M_PI * 30.0 / 180.0);
+        if (lane < d.rep && p0 + q < P) out[(p0 + q) * pitch + d.ch + lane] = v;
       }
     }
   }
@@ -132,104 +161,172 @@ __global__ void __launch_bounds__(128) heads_fwd_kernel(HeadPlan hp, const float
 // backward of heads_fwd_kernel.  Writes, per point:
 //   GHD [P, n_blocks*HH] = (sum_o dpre_o W2_o) ⊙ CD      (dgrad operand of the heads' first layer)
 //   G7D [P, F]           = dpre_sigma w_sigma + sum_o dpre_nlr,o Wg_o   (direct grads into h_{L-1})
-//   DPRE [P, 16], DPRE2 [P, 8]  pre-activation grads (operands of the skinny weight gradients)
+//   DPRE [P, 64]         cols 0..15 head pre-activation grads, 16 sigma, 17..19 learned normal
+//                        (A operand of the skinny second-layer weight gradients)
+// and accumulates the small bias gradients (second layers, sigma, grad_from_xyz) and the bias
+// gradient of the heads' first layer (column sums of GHD) through shared memory.
 template <typename T>
-__global__ void __launch_bounds__(128) heads_bwd_kernel(HeadPlan hp, const float* __restrict__ params,
+__global__ void __launch_bounds__(256) heads_bwd_kernel(HeadPlan hp, const float* __restrict__ params,
                                                         const float* __restrict__ out, const float* __restrict__ g_out, int pitch,
                                                         const T* __restrict__ Hlast, long long ldh, int F,
                                                         const T* __restrict__ CD, long long ldd,
-                                                        T* __restrict__ GHD, T* __restrict__ G7D,
-                                                        T* __restrict__ DPRE, T* __restrict__ DPRE2, long long P) {
+                                                        T* __restrict__ GHD, T* __restrict__ G7D, T* __restrict__ DPRE,
+                                                        float* __restrict__ g_params, long long P) {
+  extern __shared__ float s_red[];              // [n_blocks*HH] column sums of GHD, then [24] small biases
+  const int HKa = hp.n_blocks * hp.HH;
+  for (int i = threadIdx.x; i < HKa + 24; i += blockDim.x) s_red[i] = 0.f;
+  __syncthreads();
   const int lane = threadIdx.x % 32;
-  const long long p = (long long)blockIdx.x * 4 + threadIdx.x / 32;
-  if (p >= P) return;
-  const float* row = out + p * pitch;
-  const float* grow = g_out + p * pitch;
-  float dpre[kMaxOut];
+  const long long warp = (long long)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  const long long nwarps = (long long)gridDim.x * (blockDim.x / 32);
+  float bsum[20];                               // per-warp sums of dpre (uniform across lanes)
 #pragma unroll
-  for (int o = 0; o < kMaxOut; ++o) {
-    dpre[o] = 0.f;
-    if (o < hp.n_out) {
-      const OutDesc& d = hp.o[o];
-      float g = 0.f;
-      for (int c = 0; c < d.rep; ++c) g += grow[d.ch + c];
-      float s, scale;
-      const float v = row[d.ch];
-      if (d.xform == XF_K) { s = (v - 1.0f) * 0.5f + 0.5f; scale = 2.0f; }
-      else if (d.xform == XF_THETA_RPV) { s = v * 0.5f + 0.5f; scale = 2.0f; }
-      else if (d.xform == XF_THETA_H) { const float k = (float)(M_PI * 30.0 / 180.0); s = v / k; scale = k; }
-      else { s = v; scale = 1.0f; }
-      dpre[o] = g * scale * s * (1.0f - s);
+  for (int o = 0; o < 20; ++o) bsum[o] = 0.f;
+  for (long long p0 = warp * kQP; p0 < P; p0 += nwarps * kQP) {
+    long long pq[kQP]; bool ok[kQP];
+#pragma unroll
+    for (int q = 0; q < kQP; ++q) { ok[q] = p0 + q < P; pq[q] = min(p0 + q, P - 1); }
+    float dpre[kQP][kMaxOut], dsig[kQP], dv[kQP][3];
+#pragma unroll
+    for (int q = 0; q < kQP; ++q) {
+      const float* row = out + pq[q] * pitch;
+      const float* grow = g_out + pq[q] * pitch;
+#pragma unroll
+      for (int o = 0; o < kMaxOut; ++o) {
+        dpre[q][o] = 0.f;
+        if (o < hp.n_out && ok[q]) {
+          const OutDesc& d = hp.o[o];
+          float g = 0.f;
+          for (int c = 0; c < d.rep; ++c) g += grow[d.ch + c];
+          float sg, scale;
+          const float v = row[d.ch];
+          if (d.xform == XF_K) { sg = (v - 1.0f) * 0.5f + 0.5f; scale = 2.0f; }
+          else if (d.xform == XF_THETA_RPV) { sg = v * 0.5f + 0.5f; scale = 2.0f; }
+          else if (d.xform == XF_THETA_H) { const float k = (float)(M_PI * 30.0 / 180.0); sg = v / k; scale = k; }
+          else { sg = v; scale = 1.0f; }
+          dpre[q][o] = g * scale * sg * (1.0f - sg);
+        }
+      }
+      // softplus'(x) = 1 - exp(-softplus(x))
+      dsig[q] = ok[q] ? grow[hp.ch_sigma] * (1.0f - expf(-row[hp.ch_sigma])) : 0.f;
+      dv[q][0] = dv[q][1] = dv[q][2] = 0.f;
     }
-  }
-  const float sigma = row[hp.ch_sigma];
-  const float dsig = grow[hp.ch_sigma] * (1.0f - expf(-sigma));      // softplus'(x) = 1 - exp(-softplus(x))
-  float dv[3] = {0.f, 0.f, 0.f};
-  if (hp.ch_nlr >= 0) {
-    // n = -v/|v| ; recompute v = Wg h + bg
-    float g_acc[3] = {0.f, 0.f, 0.f};
+    if (hp.ch_nlr >= 0) {
+      // n = -v/|v| ; recompute v = Wg h + bg
+      float g_acc[kQP][3];
+#pragma unroll
+      for (int q = 0; q < kQP; ++q) g_acc[q][0] = g_acc[q][1] = g_acc[q][2] = 0.f;
+      for (int i = lane * 8; i < F; i += 256) {
+        float h[kQP][8];
+#pragma unroll
+        for (int q = 0; q < kQP; ++q) load8g<T>(Hlast + pq[q] * ldh + i, h[q]);
+#pragma unroll
+        for (int o = 0; o < 3; ++o) {
+          float w[8]; load8<float>(params + hp.wg + (long long)o * F + i, w);
+#pragma unroll
+          for (int q = 0; q < kQP; ++q)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g_acc[q][o] = fmaf(h[q][j], w[j], g_acc[q][o]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < kQP; ++q) {
+        float v[3];
+#pragma unroll
+        for (int o = 0; o < 3; ++o) v[o] = warp_sum(g_acc[q][o]) + __ldg(params + hp.bg + o);
+        const float* grow = g_out + pq[q] * pitch;
+        const float gn[3] = {grow[hp.ch_nlr], grow[hp.ch_nlr + 1], grow[hp.ch_nlr + 2]};
+        const float sq = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+        if (sq > 1.1920929e-07f) {
+          const float inv = 1.0f / sqrtf(sq);
+          const float u[3] = {v[0] * inv, v[1] * inv, v[2] * inv};
+          const float gu = gn[0] * u[0] + gn[1] * u[1] + gn[2] * u[2];
+#pragma unroll
+          for (int o = 0; o < 3; ++o) dv[q][o] = ok[q] ? -(gn[o] - gu * u[o]) * inv : 0.f;
+        } else {
+          const float inv = 1.0f / sqrtf(1.1920929e-07f);
+#pragma unroll
+          for (int o = 0; o < 3; ++o) dv[q][o] = ok[q] ? -gn[o] * inv : 0.f;
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < kQP; ++q) {
+#pragma unroll
+      for (int o = 0; o < 16; ++o) bsum[o] += dpre[q][o];
+      bsum[16] += dsig[q]; bsum[17] += dv[q][0]; bsum[18] += dv[q][1]; bsum[19] += dv[q][2];
+      if (ok[q] && lane < 8) {
+        // row of 64: lane l writes columns 8l..8l+7
+        float t[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (lane == 0) {
+#pragma unroll
+          for (int o = 0; o < 8; ++o) t[o] = dpre[q][o];
+        } else if (lane == 1) {
+#pragma unroll
+          for (int o = 0; o < 8; ++o) t[o] = dpre[q][8 + o];
+        } else if (lane == 2) { t[0] = dsig[q]; t[1] = dv[q][0]; t[2] = dv[q][1]; t[3] = dv[q][2]; }
+        Pack<T, 8>::store(DPRE + pq[q] * 64 + lane * 8, t);
+      }
+    }
     for (int i = lane * 8; i < F; i += 256) {
-      float h[8]; load8g<T>(Hlast + p * ldh + i, h);
+      float ws[8]; load8<float>(params + hp.wsig + i, ws);
+      float g[kQP][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
+      for (int q = 0; q < kQP; ++q)
 #pragma unroll
-        for (int o = 0; o < 3; ++o) g_acc[o] = fmaf(h[j], __ldg(params + hp.wg + (long long)o * F + i + j), g_acc[o]);
+        for (int j = 0; j < 8; ++j) g[q][j] = dsig[q] * ws[j];
+      if (hp.ch_nlr >= 0) {
+#pragma unroll
+        for (int o = 0; o < 3; ++o) {
+          float w[8]; load8<float>(params + hp.wg + (long long)o * F + i, w);
+#pragma unroll
+          for (int q = 0; q < kQP; ++q)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[q][j] = fmaf(dv[q][o], w[j], g[q][j]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < kQP; ++q) if (ok[q]) Pack<T, 8>::store(G7D + pq[q] * F + i, g[q]);
     }
-    float v[3];
+    for (int b = 0; b < hp.n_blocks; ++b) {
+      for (int i = lane * 8; i < hp.HH; i += 256) {
+        float a[kQP][8];
 #pragma unroll
-    for (int o = 0; o < 3; ++o) v[o] = warp_sum(g_acc[o]) + __ldg(params + hp.bg + o);
-    const float sq = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
-    const float gn[3] = {grow[hp.ch_nlr], grow[hp.ch_nlr + 1], grow[hp.ch_nlr + 2]};
-    if (sq > 1.1920929e-07f) {
-      const float inv = 1.0f / sqrtf(sq);
-      const float u[3] = {v[0] * inv, v[1] * inv, v[2] * inv};
-      const float gu = gn[0] * u[0] + gn[1] * u[1] + gn[2] * u[2];
+        for (int q = 0; q < kQP; ++q)
 #pragma unroll
-      for (int o = 0; o < 3; ++o) dv[o] = -(gn[o] - gu * u[o]) * inv;
-    } else {
-      const float inv = 1.0f / sqrtf(1.1920929e-07f);
+          for (int j = 0; j < 8; ++j) a[q][j] = 0.f;
 #pragma unroll
-      for (int o = 0; o < 3; ++o) dv[o] = -gn[o] * inv;
+        for (int o = 0; o < kMaxOut; ++o) {
+          if (o < hp.n_out && hp.o[o].block == b) {
+            float w[8]; load8<float>(params + hp.o[o].w_off + i, w);
+#pragma unroll
+            for (int q = 0; q < kQP; ++q)
+#pragma unroll
+              for (int j = 0; j < 8; ++j) a[q][j] = fmaf(dpre[q][o], w[j], a[q][j]);
+          }
+        }
+        float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int q = 0; q < kQP; ++q) {
+          float c[8]; load8g<T>(CD + pq[q] * ldd + (long long)b * hp.HH + i, c);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { a[q][j] *= c[j]; cs[j] += ok[q] ? a[q][j] : 0.f; }
+          if (ok[q]) Pack<T, 8>::store(GHD + pq[q] * ldd + (long long)b * hp.HH + i, a[q]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(&s_red[b * hp.HH + i + j], cs[j]);
+      }
     }
   }
   if (lane == 0) {
-    float t[16];
 #pragma unroll
-    for (int o = 0; o < 16; ++o) t[o] = dpre[o];
-    Pack<T, 16>::store(DPRE + p * 16, t);
-    float u8[8] = {dsig, dv[0], dv[1], dv[2], 0.f, 0.f, 0.f, 0.f};
-    Pack<T, 8>::store(DPRE2 + p * 8, u8);
+    for (int o = 0; o < 20; ++o) atomicAdd(&s_red[HKa + o], bsum[o]);
   }
-  for (int i = lane * 8; i < F; i += 256) {
-    float g[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float a = dsig * __ldg(params + hp.wsig + i + j);
-      if (hp.ch_nlr >= 0) {
-#pragma unroll
-        for (int o = 0; o < 3; ++o) a = fmaf(dv[o], __ldg(params + hp.wg + (long long)o * F + i + j), a);
-      }
-      g[j] = a;
-    }
-    Pack<T, 8>::store(G7D + p * F + i, g);
-  }
-  for (int b = 0; b < hp.n_blocks; ++b) {
-    for (int i = lane * 8; i < hp.HH; i += 256) {
-      float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int o = 0; o < kMaxOut; ++o) {
-        if (o < hp.n_out && hp.o[o].block == b) {
-          const float* w = params + hp.o[o].w_off + i;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) a[j] = fmaf(dpre[o], __ldg(w + j), a[j]);
-        }
-      }
-      float c[8]; load8g<T>(CD + p * ldd + (long long)b * hp.HH + i, c);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) a[j] *= c[j];
-      Pack<T, 8>::store(GHD + p * ldd + (long long)b * hp.HH + i, a);
-    }
-  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < HKa; i += blockDim.x) atomicAdd(g_params + hp.b1_off[i / hp.HH] + (i % hp.HH), s_red[i]);
+  if (threadIdx.x < hp.n_out) atomicAdd(g_params + hp.o[threadIdx.x].b_off, s_red[HKa + threadIdx.x]);
+  if (threadIdx.x == 16) atomicAdd(g_params + hp.bsig, s_red[HKa + 16]);
+  if (threadIdx.x >= 17 && threadIdx.x < 20 && hp.ch_nlr >= 0) atomicAdd(g_params + hp.bg + (threadIdx.x - 17), s_red[HKa + threadIdx.x]);
 }
 
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
@@ -289,6 +386,7 @@ static int build_plan(const bn_mlp* h, int flags, HeadPlan* hp, int* n_channels)
     if (flags & BN_MLP_HAPKE_THETA) add_head(BN_HEAD_THETA, XF_THETA_H);
   }
   p.n_blocks = last_block + 1;
+  for (int b = 0; b < h->n_blocks; ++b) p.b1_off[b] = c.b_off[h->blk_lin0[b]];
   if (hp) *hp = p;
   if (n_channels) *n_channels = ch;
   return BN_OK;
@@ -316,6 +414,10 @@ static int sync_weights_t(bn_mlp* h, const float* params, cudaStream_t s) {
   }
   h->synced = true;
   return BN_OK;
+}
+
+static unsigned heads_grid(const bn_mlp* h, long long P) {
+  return (unsigned)max(1LL, min(ceil_div_ll(P, 8 * kQP), (long long)h->num_sms * 4));
 }
 
 template <typename T>
@@ -350,7 +452,7 @@ static int forward_t(bn_mlp* h, const float* params, const float* origins, int o
   }
   const T* Hl = w.H[L - 1]; const long long ldl = w.Hld[L - 1];
   if (sig_only) {
-    heads_fwd_kernel<T><<<(unsigned)ceil_div_ll(P, 4), 128, 0, s>>>(hp, params, Hl, ldl, F, nullptr, 0, out, 1, P, true);
+    heads_fwd_kernel<T><<<heads_grid(h, P), 256, 0, s>>>(hp, params, Hl, ldl, F, nullptr, 0, out, 1, P, true);
     BN_LAUNCH_CHECK();
     return BN_OK;
   }
@@ -363,7 +465,7 @@ static int forward_t(bn_mlp* h, const float* params, const float* origins, int o
     EpiSin<T, kFast> epi{h->b1cat, 1.0f, w.HD, w.ldhd, train ? w.CD : nullptr, w.ldhd, (int)P, HKa};
     if (int rc = gemm_tn<T>(h, w.FE, F, (const T*)h->W1, F, P, HKa, F, epi, s)) return rc;
   }
-  heads_fwd_kernel<T><<<(unsigned)ceil_div_ll(P, 4), 128, 0, s>>>(hp, params, Hl, ldl, F, w.HD, w.ldhd, out, pitch, P, false);
+  heads_fwd_kernel<T><<<heads_grid(h, P), 256, 0, s>>>(hp, params, Hl, ldl, F, w.HD, w.ldhd, out, pitch, P, false);
   BN_LAUNCH_CHECK();
   return BN_OK;
 }
@@ -380,49 +482,62 @@ static int backward_t(bn_mlp* h, const float* params, const float* out, const fl
   if (int rc = build_plan(h, flags, &hp, &nch)) return rc;
   const T* Hl = w.H[L - 1]; const long long ldl = w.Hld[L - 1];
   const int HKa = hp.n_blocks * h->HH;
-  heads_bwd_kernel<T><<<(unsigned)ceil_div_ll(P, 4), 128, 0, s>>>(hp, params, out, g_out, pitch, Hl, ldl, F, w.CD, w.ldhd,
-                                                               w.GHD, w.G7D, w.DPRE, w.DPRE2, P);
-  BN_LAUNCH_CHECK();
-  // second-layer weight/bias gradients of the heads, sigma and learned-normal heads (skinny reductions)
+  constexpr bool kTC = std::is_same<T, __nv_bfloat16>::value;   // bias grads fused into the tcgen05 dgrad epilogues
   {
+    const size_t smem = (size_t)(HKa + 24) * sizeof(float);
+    heads_bwd_kernel<T><<<heads_grid(h, P), 256, smem, s>>>(hp, params, out, g_out, pitch, Hl, ldl, F, w.CD, w.ldhd,
+                                                           w.GHD, w.G7D, w.DPRE, g, P);
+    BN_LAUNCH_CHECK();
+  }
+  // second-layer weight gradients of the heads / sigma / learned-normal heads: dW2[o] = DPRE[:,o]^T X
+  if constexpr (kTC) {
+    EpiSkinny e1{}; e1.n_rows = hp.n_out;
+    for (int o = 0; o < hp.n_out; ++o) e1.r[o] = EpiSkinnyRow{g + hp.o[o].w_off, hp.o[o].block * h->HH, (hp.o[o].block + 1) * h->HH};
+    if (int rc = gemm_nt<T>(h, w.DPRE, 64, w.HD, w.ldhd, 64, HKa, P, e1, s, 2.0 * P * hp.n_out * h->HH)) return rc;
+    EpiSkinny e2{}; e2.n_rows = 20;
+    e2.r[16] = EpiSkinnyRow{g + hp.wsig, 0, F};
+    if (hp.ch_nlr >= 0) for (int o = 0; o < 3; ++o) e2.r[17 + o] = EpiSkinnyRow{g + hp.wg + (long long)o * F, 0, F};
+    if (int rc = gemm_nt<T>(h, w.DPRE, 64, Hl, ldl, 64, F, P, e2, s, 2.0 * P * (hp.ch_nlr >= 0 ? 4 : 1) * F)) return rc;
+  } else {
     SkinnyPlan sp{};
     for (int o = 0; o < hp.n_out; ++o)
-      sp.r[sp.n++] = SkinnyRow{g + hp.o[o].w_off, g + hp.o[o].b_off, o, hp.o[o].block * h->HH, (hp.o[o].block + 1) * h->HH};
+      sp.r[sp.n++] = SkinnyRow{g + hp.o[o].w_off, nullptr, o, hp.o[o].block * h->HH, (hp.o[o].block + 1) * h->HH};
     const int bx = ceil_div(HKa, 256);
     int by = (int)max(1LL, min(ceil_div_ll(P, 128), (long long)(148 * 4 / bx)));
     const long long rows = ceil_div_ll(ceil_div_ll(P, by), 32) * 32;
     by = (int)ceil_div_ll(P, rows);
-    skinny_wgrad_kernel<T><<<dim3(bx, by), 256, 0, s>>>(sp, w.DPRE, 16, w.HD, w.ldhd, HKa, P, rows);
+    skinny_wgrad_kernel<T><<<dim3(bx, by), 256, 0, s>>>(sp, w.DPRE, 64, w.HD, w.ldhd, HKa, P, rows);
     BN_LAUNCH_CHECK();
     SkinnyPlan s2{};
-    s2.r[s2.n++] = SkinnyRow{g + hp.wsig, g + hp.bsig, 0, 0, F};
+    s2.r[s2.n++] = SkinnyRow{g + hp.wsig, nullptr, 16, 0, F};
     if (hp.ch_nlr >= 0)
-      for (int o = 0; o < 3; ++o) s2.r[s2.n++] = SkinnyRow{g + hp.wg + (long long)o * F, g + hp.bg + o, 1 + o, 0, F};
+      for (int o = 0; o < 3; ++o) s2.r[s2.n++] = SkinnyRow{g + hp.wg + (long long)o * F, nullptr, 17 + o, 0, F};
     const int bx2 = ceil_div(F, 256);
     int by2 = (int)max(1LL, min(ceil_div_ll(P, 128), (long long)(148 * 4 / bx2)));
     const long long rows2 = ceil_div_ll(ceil_div_ll(P, by2), 32) * 32;
     by2 = (int)ceil_div_ll(P, rows2);
-    skinny_wgrad_kernel<T><<<dim3(bx2, by2), 256, 0, s>>>(s2, w.DPRE2, 8, Hl, ldl, F, P, rows2);
+    skinny_wgrad_kernel<T><<<dim3(bx2, by2), 256, 0, s>>>(s2, w.DPRE, 64, Hl, ldl, F, P, rows2);
     BN_LAUNCH_CHECK();
   }
-  // heads' first layer: wgrad per block, bias grads, dgrad into the features
+  // heads' first layer: wgrad per block (bias grads came out of heads_bwd_kernel), dgrad into the features
   for (int b = 0; b < hp.n_blocks; ++b) {
     const int lin = h->blk_lin0[b];
     EpiWgrad ew{g + c.w_off[lin], F, h->HH, F, F, F};
     if (int rc = gemm_nt<T>(h, w.GHD + (long long)b * h->HH, w.ldhd, w.FE, F, h->HH, F, P, ew, s)) return rc;
-    if (int rc = colsum<T>(w.GHD + (long long)b * h->HH, w.ldhd, h->HH, P, g + c.b_off[lin], s)) return rc;
   }
   {
     EpiDgrad<T> ed{nullptr, 0, nullptr, 0, w.GFE, F, (int)P, F};
+    if (kTC) ed.colsum = g + c.b_off[BN_LIN_FEATS];
     if (int rc = gemm_tn<T>(h, w.GHD, w.ldhd, (const T*)h->W1T, (long long)h->n_blocks * h->HH, P, F, HKa, ed, s)) return rc;
+    if (!kTC) { if (int rc = colsum<T>(w.GFE, F, F, P, g + c.b_off[BN_LIN_FEATS], s)) return rc; }
   }
   // feature layer
   {
     EpiWgrad ew{g + c.w_off[BN_LIN_FEATS], F, F, F, F, F};
     if (int rc = gemm_nt<T>(h, w.GFE, F, Hl, ldl, F, F, P, ew, s)) return rc;
-    if (int rc = colsum<T>(w.GFE, F, F, P, g + c.b_off[BN_LIN_FEATS], s)) return rc;
     EpiDgrad<T> ed{w.G7D, F, w.C[L - 1], F, w.GA, F, (int)P, F};
     if (normals) { ed.add2 = w.U[L - 1]; ed.ld2 = F; }
+    if (kTC) ed.colsum = g + c.b_off[L - 1];
     if (int rc = gemm_tn<T>(h, w.GFE, F, (const T*)h->WfT, F, P, F, F, ed, s)) return rc;
   }
   // trunk, last layer first.  cur = dZ_l
@@ -432,12 +547,13 @@ static int backward_t(bn_mlp* h, const float* params, const float* out, const fl
     const T* In; long long ldin;
     if (enc_in) { In = w.X3; ldin = w.ldx3; } else { In = w.H[l - 1]; ldin = w.Hld[l - 1]; }
     EpiWgrad ew{g + c.w_off[l], h->Kreal[l], F, h->Kpad[l], enc_in ? h->E : h->Kpad[l], enc_in ? kEncPad : h->Kpad[l]};
-    if (int rc = gemm_nt<T>(h, cur, F, In, ldin, F, h->Kpad[l], P, ew, s)) return rc;
-    if (int rc = colsum<T>(cur, F, F, P, g + c.b_off[l], s)) return rc;
+    if (int rc = gemm_nt<T>(h, cur, F, In, ldin, F, h->Kpad[l], P, ew, s, 2.0 * P * F * h->Kreal[l])) return rc;
+    if (!kTC) { if (int rc = colsum<T>(cur, F, F, P, g + c.b_off[l], s)) return rc; }
     if (l > 0) {
       const T* BT = (const T*)h->WTp[l] + (l == h->skip ? (long long)kEncPad * F : 0);
       EpiDgrad<T> ed{nullptr, 0, w.C[l - 1], F, nxt, F, (int)P, F};
       if (normals) { ed.add2 = w.U[l - 1]; ed.ld2 = F; }
+      if (kTC) ed.colsum = g + c.b_off[l - 1];
       if (int rc = gemm_tn<T>(h, cur, F, BT, F, P, F, F, ed, s)) return rc;
       T* t = cur; cur = nxt; nxt = t;
     }

@@ -43,6 +43,7 @@ struct HeadPlan {
   int HH;                       // hidden width of one block (feat / 2)
   int ch_sigma, ch_nlr;         // packed channel of sigma / learned normal (-1 = off)
   long long wsig, bsig, wg, bg; // offsets of sigma_from_xyz.0 / grad_from_xyz
+  long long b1_off[kMaxBlocks]; // bias offset of each block's first layer ({name}.0.bias)
 };
 
 }  // namespace bn
@@ -140,7 +141,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ X, lo
 // ------------------------------------------------------------------------------------------------
 template <typename T> struct Ws {
   T* X3; T* H[16]; long long Hld[16]; T* C[16];
-  T* FE; T* HD; T* CD; T* GHD; T* G7D; T* GFE; T* GA; T* GB; T* DPRE; T* DPRE2;
+  T* FE; T* HD; T* CD; T* GHD; T* G7D; T* GFE; T* GA; T* GB; T* DPRE;
   long long ldx3, ldhd;
   // analytic-normal sweep (BN_MLP_NORMAL_AN)
   T* A[16];        // a_l = d sigma / d lin_l            (one per layer when training, ping-pong otherwise)
@@ -189,7 +190,7 @@ static inline size_t carve(const bn_mlp* h, long long P, int flags, void* base, 
     if (train) {
       t.CD = take(P * t.ldhd); t.GHD = take(P * t.ldhd);
       t.G7D = take(P * F); t.GFE = take(P * F); t.GA = take(P * F); t.GB = take(P * F);
-      t.DPRE = take(P * 16); t.DPRE2 = take(P * 8);
+      t.DPRE = take(P * 64);
     }
   }
   if (normals) {
@@ -223,18 +224,17 @@ static int gemm_tn(const bn_mlp* h, const T* A, long long lda, const T* B, long 
   prof_end(s);
   return rc;
 }
-template <typename T>
+template <typename T, class Epi>
 static int gemm_nt(const bn_mlp* h, const T* A, long long lda, const T* B, long long ldb, int Mo, int No, long long P,
-                   const EpiWgrad& epi, cudaStream_t s) {
-  const int n_real = No - (epi.pad_hi - epi.pad_lo);
-  prof_begin(1, 2.0 * (double)P * Mo * n_real, s);
+                   const Epi& epi, cudaStream_t s, double flops = -1.0) {
+  prof_begin(1, flops >= 0 ? flops : 2.0 * (double)P * Mo * No, s);
   int rc;
   if constexpr (std::is_same<T, __nv_bfloat16>::value) {
     if (No >= 256) rc = tc::launch_nt<256>(A, lda, B, ldb, Mo, No, P, epi, h->num_sms, s);
     else if (No >= 128) rc = tc::launch_nt<128>(A, lda, B, ldb, Mo, No, P, epi, h->num_sms, s);
     else rc = tc::launch_nt<64>(A, lda, B, ldb, Mo, No, P, epi, h->num_sms, s);
   } else {
-    rc = launch_nt_simt<T, EpiWgrad>(A, lda, B, ldb, Mo, No, P, epi, s);
+    rc = launch_nt_simt<T, Epi>(A, lda, B, ldb, Mo, No, P, epi, s);
   }
   prof_end(s);
   return rc;

@@ -199,7 +199,7 @@ static int normals_backward_t(bn_mlp* h, const float* params, const float* out, 
     EpiSecond<T> es{w.C[l], F, w.U[l], F, w.H[l], w.Hld[l], dst, ldd, -w0 * w0, (int)P, F};
     if (int rc = gemm_tn<T>(h, Aop, lda, (const T*)h->Wp[l], h->Kpad[l], P, F, h->Kpad[l], es, s, h->Kreal[l])) return rc;
     EpiWgrad ew{g + c.w_off[l], h->Kreal[l], F, h->Kpad[l], enc_in ? h->E : h->Kpad[l], enc_in ? kEncPad : h->Kpad[l]};
-    if (int rc = gemm_nt<T>(h, w.A[l], F, Aop, lda, F, h->Kpad[l], P, ew, s)) return rc;
+    if (int rc = gemm_nt<T>(h, w.A[l], F, Aop, lda, F, h->Kpad[l], P, ew, s, 2.0 * P * F * h->Kreal[l])) return rc;
     prev = dst; ldprev = ldd;
   }
   const long long wsig = c.w_off[BN_LIN_SIGMA];
