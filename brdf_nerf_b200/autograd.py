@@ -52,9 +52,5 @@ class PointsFunction(torch.autograd.Function):
         if ctx.flags & L.MLP_NORMAL_AN:
             ops.mlp_normals_backward(model, out, g_out, ctx.C, ctx.B, 1, ctx.flags, flat, ctx.ws)
         ops.mlp_backward(model, out, g_out, ctx.C, ctx.B, 1, ctx.flags, flat, ctx.ws)
-        grads, off = [], 0
-        for p in model.parameters():
-            m = p.numel()
-            grads.append(flat[off:off + m].view(p.shape) if p.requires_grad else None)
-            off += m
+        grads = model.grad_views(flat)
         return (None, None, None, None, None, None, None, None, *grads)

@@ -170,34 +170,40 @@ class SpSBRDFNeRF(nn.Module):
     def _param_list(self):
         return list(self.named_parameters())
 
+    _ALIGN = 8      # every tensor starts on a 32-byte boundary of the flat buffer (128-bit vector loads)
+
+    def _layout(self):
+        """[(name, param, offset)] and the padded total length of the flat buffer."""
+        out, off = [], 0
+        for name, p in self._param_list():
+            out.append((name, p, off))
+            off += -(-p.numel() // self._ALIGN) * self._ALIGN
+        return out, off
+
     def _flat_ok(self) -> bool:
         if self._flat is None:
             return False
-        off = 0
-        for _, p in self._param_list():
+        lay, total = self._layout()
+        for _, p, off in lay:
             if p.device != self._flat.device or p.data_ptr() != self._flat.data_ptr() + off * 4:
                 return False
-            off += p.numel()
-        return off == self._flat.numel()
+        return total == self._flat.numel()
 
     def _ensure_flat(self):
         """(Re)build the flat parameter / gradient buffers, e.g. after `.to(device)`."""
         if self._flat_ok():
             return
-        plist = self._param_list()
-        dev = plist[0][1].device
-        n = sum(p.numel() for _, p in plist)
-        flat = torch.empty(n, dtype=torch.float32, device=dev)
+        lay, n = self._layout()
+        dev = lay[0][1].device
+        flat = torch.zeros(n, dtype=torch.float32, device=dev)
         grad = torch.zeros(n, dtype=torch.float32, device=dev)
-        off = 0
-        for _, p in plist:
+        for _, p, off in lay:
             m = p.numel()
             flat[off:off + m].copy_(p.data.reshape(-1).to(torch.float32))
             if p.grad is not None:
                 grad[off:off + m].copy_(p.grad.reshape(-1))
             p.data = flat[off:off + m].view(p.shape)
             p.grad = grad[off:off + m].view(p.shape)
-            off += m
         self._flat, self._flat_grad = flat, grad
         self._synced_version = -1
         if self._handle is not None:
@@ -205,11 +211,11 @@ class SpSBRDFNeRF(nn.Module):
             self._handle = None
 
     def offsets(self) -> Dict[str, int]:
-        off, out = 0, {}
-        for name, p in self._param_list():
-            out[name] = off
-            off += p.numel()
-        return out
+        return {name: off for name, _, off in self._layout()[0]}
+
+    def grad_views(self, flat: torch.Tensor):
+        """Per-parameter views of a flat gradient buffer laid out like `flat_params`."""
+        return [flat[off:off + p.numel()].view(p.shape) if p.requires_grad else None for _, p, off in self._layout()[0]]
 
     # ------------------------------------------------------------------ C handle
     def _linear_names(self) -> List[Optional[str]]:

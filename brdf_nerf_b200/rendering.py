@@ -261,11 +261,7 @@ class _RenderFunction(torch.autograd.Function):
         model, st = ctx.model, ctx.st
         flat = torch.zeros_like(model.flat_params)
         _backward(model, st, g_rgb, g_depth, g_weights, g_packed, flat)
-        grads, off = [], 0
-        for p in model.parameters():
-            m = p.numel()
-            grads.append(flat[off:off + m].view(p.shape) if p.requires_grad else None)
-            off += m
+        grads = model.grad_views(flat)
         return (None, None, None, None, None, *grads)
 
 

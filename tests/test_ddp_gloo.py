@@ -43,13 +43,11 @@ def _worker(rank, world, port, n, out_q):
                                target_depths=shard.target_depths, target_std=shard.target_std)
     LT.train_loss(res, shard, args).backward()
     flat = model.flat_grads
-    off = 0
     for name, p in model.named_parameters():
-        flat[off:off + p.numel()] = om.p[name].grad.reshape(-1)
-        off += p.numel()
+        p.grad.copy_(om.p[name].grad)             # p.grad is a view into the flat bucket
     scale = allreduce_grads_(flat, world)
     if rank == 0:
-        out_q.put((flat * scale).clone())
+        out_q.put(torch.cat([p.grad.reshape(-1) for p in model.parameters()]) * scale)
     dist.destroy_process_group()
 
 

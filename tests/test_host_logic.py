@@ -51,7 +51,7 @@ def test_module_surface_and_param_counts(cfg, n_params):
         assert hasattr(m, attr)
     # flat storage: parameters are views of one buffer, state_dict round-trips through it
     flat = m.flat_params
-    assert flat.numel() == n_params
+    assert flat.numel() >= n_params and flat.numel() % 8 == 0      # tensors start on 32-byte boundaries
     sd = {k: v.clone() for k, v in m.state_dict().items()}
     off = m.offsets()
     assert torch.equal(flat[off["fc_net.2.weight"]:off["fc_net.2.weight"] + 512 * 512].view(512, 512), sd["fc_net.2.weight"])
