@@ -151,7 +151,7 @@ struct EpiDgrad {
 // head's second-layer weight row; only columns [c0, c1) of it are real and go to dst[col - c0].
 struct EpiSkinnyRow { float* dst; int c0, c1; };
 struct EpiSkinny {
-  int n_rows; EpiSkinnyRow r[16];
+  int n_rows; EpiSkinnyRow r[24];
   template <int n> __device__ __forceinline__ void apply(int row, int col0, const float (&acc)[n]) const {
     if (row >= n_rows) return;
     const EpiSkinnyRow q = r[row];

@@ -71,10 +71,21 @@ def test_against_reference_golden(cuda, name):
             assert d <= TOL, f"{name}: accumulated {nk} differs by {d}"
 
 
-@pytest.mark.parametrize("cfg,ds,kw", [("lambertian", False, {}), ("lambertian_ds", True, {})])
+@pytest.mark.parametrize("cfg,ds,kw", [
+    ("lambertian", False, {}), ("lambertian_ds", True, {}),
+    ("rpv111", False, dict(apply_brdf=True, cos_irra_on=True)),
+    ("rpv111_multi", False, dict(apply_brdf=True, cos_irra_on=True)),
+    ("hapke_bct", False, dict(apply_brdf=True, apply_theta=True, cos_irra_on=True)),
+    ("microfacet", False, dict(apply_brdf=True, cos_irra_on=True)),
+    ("rpv111", False, dict(apply_brdf=False)),
+])
 def test_training_gradients_vs_oracle(cuda, cfg, ds, kw):
+    """d loss / d every weight through the whole CUDA chain (shade -> composite -> [per-sample BRDF] ->
+    analytic-normal second-order sweep -> MLP) against autograd through the oracle."""
     args = named_config(cfg)
-    n = 96
+    if _needs_normals(args, kw) and not _has_normals():
+        pytest.skip("analytic-normal kernels not built")
+    n = 96 if cfg.startswith("lambertian") else 48
     torch.manual_seed(0)
     model = load_model(args, precision="fp32")
     state = {k: v.clone() for k, v in model.state_dict().items()}
@@ -102,8 +113,8 @@ def test_training_gradients_vs_oracle(cuda, cfg, ds, kw):
         d = (p.grad.cpu() - r).abs().max().item()
         s = r.abs().max().item()
         worst = max(worst, d / (s + 1e-12))
-        assert d <= 5e-3 * s + 1e-7, f"grad {name}: diff {d} scale {s}"
-    print(f"{cfg}: worst relative gradient error {worst:.2e}")
+        assert d <= 1e-2 * s + 1e-7, f"grad {name}: diff {d} scale {s}"
+    print(f"{cfg} {kw}: worst relative gradient error {worst:.2e}")
 
 
 def test_no_cpu_fallback():
