@@ -59,6 +59,7 @@ template <int n> struct Pack<__nv_bfloat16, n> {
 // kFast selects the MUFU sin/cos (bf16 path, hidden layers: |arg| is O(1), error << bf16 ulp).
 template <typename T, bool kFast>
 struct EpiSin {
+  static constexpr int kMode = 0, kIn = 0, kOut = 0;   // direct global-memory epilogue (tc::EPI_DIRECT)
   const float* bias; float w0;
   T* H; long long ldh;
   T* Cc; long long ldc;       // nullable
@@ -80,6 +81,7 @@ struct EpiSin {
 // out = acc + b
 template <typename T>
 struct EpiBias {
+  static constexpr int kMode = 0, kIn = 0, kOut = 0;   // direct global-memory epilogue (tc::EPI_DIRECT)
   const float* bias; T* out; long long ld; int M, N;
   template <int n> __device__ __forceinline__ void apply(int row, int col0, const float (&acc)[n]) const {
     if (row >= M || col0 >= N) return;
@@ -97,6 +99,7 @@ struct EpiBias {
 // and added with one coalesced red.global per 32 columns — no separate pass over dZ.
 template <typename T>
 struct EpiDgrad {
+  static constexpr int kMode = 0, kIn = 0, kOut = 0;   // direct global-memory epilogue (tc::EPI_DIRECT)
   const T* addend; long long lda;    // nullable
   const T* mulc; long long ldm;      // nullable
   T* out; long long ld; int M, N;
@@ -151,6 +154,7 @@ struct EpiDgrad {
 // head's second-layer weight row; only columns [c0, c1) of it are real and go to dst[col - c0].
 struct EpiSkinnyRow { float* dst; int c0, c1; };
 struct EpiSkinny {
+  static constexpr int kMode = 0, kIn = 0, kOut = 0;   // direct global-memory epilogue (tc::EPI_DIRECT)
   int n_rows; EpiSkinnyRow r[24];
   template <int n> __device__ __forceinline__ void apply(int row, int col0, const float (&acc)[n]) const {
     if (row >= n_rows) return;
@@ -167,6 +171,7 @@ struct EpiSkinny {
 //   acc = abar_l ;  ubar_l = abar_l ⊙ c_l  -> ubar ;  zb_l = (abar_l ⊙ u_l) * (-w0^2 h_l) -> overwrites u_l
 template <typename T>
 struct EpiSecond {
+  static constexpr int kMode = 0, kIn = 0, kOut = 0;   // direct global-memory epilogue (tc::EPI_DIRECT)
   const T* Cc; long long ldc;
   T* U; long long ldu;               // in: u_l, out: zb_l
   const T* H; long long ldh;
@@ -190,6 +195,7 @@ struct EpiSecond {
 // down by (pad_hi - pad_lo) — this maps the padded [enc(60)|pad(4)|h(512)] layout back to the
 // reference's Linear(572, 512) weight.
 struct EpiWgrad {
+  static constexpr int kMode = 0, kIn = 0, kOut = 0;   // direct global-memory epilogue (tc::EPI_DIRECT)
   float* dW; long long ld; int M, N; int pad_lo, pad_hi;
   template <int n> __device__ __forceinline__ void apply(int row, int col0, const float (&acc)[n]) const {
     if (row >= M) return;
@@ -205,6 +211,7 @@ struct EpiWgrad {
 
 // plain fp32 store (debug / unit-test entry point)
 struct EpiStoreF32 {
+  static constexpr int kMode = 0, kIn = 0, kOut = 0;   // direct global-memory epilogue (tc::EPI_DIRECT)
   float* out; long long ld; int M, N;
   template <int n> __device__ __forceinline__ void apply(int row, int col0, const float (&acc)[n]) const {
     if (row >= M) return;

@@ -62,6 +62,29 @@ __device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
       : "memory");
 }
+// ---- smem -> global through the TMA (epilogue staging) ----
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+// element-wise fp32 add into global memory (L2 atomics on whole lines instead of scattered red.global)
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// generic-proxy smem writes -> visible to the async proxy (TMA) that reads them next
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ uint4 lds128(const void* p) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_u32(p)));
+  return v;
+}
+__device__ __forceinline__ void sts128(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(smem_u32(p)), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t cluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t cluster_nctaid_x() { uint32_t r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
@@ -128,7 +151,37 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, bool mn_major) {
 struct Work {
   int m_tiles, n_tiles, splits;   // splits only for kNT
   int kb_total, kb_per_split;     // k-blocks (of kBK) in the reduction dimension
+  int n_cols;                     // real number of output columns (a multiple of the epilogue unit)
 };
+
+// Epilogue kinds.  An epilogue functor `Epi` declares `static constexpr int kMode`:
+//   EPI_DIRECT      : apply<32>(row, col0, acc[32]) writes global memory itself (debug / skinny paths)
+//   EPI_TMA_BF16    : the tile leaves (and its element-wise operands enter) through shared memory and
+//                     the TMA in units of 32 rows x 64 bf16 columns = one 128B-swizzled 4 KB box per
+//                     epilogue warp; kIn input streams, kOut output streams.  A thread owns one row of
+//                     the unit, so its 16-byte chunks land conflict-free in the swizzled box and every
+//                     global access is a full-line TMA transaction instead of 32 scattered sectors.
+//   EPI_TMA_RED_F32 : units of 32 rows x 32 fp32 columns leave through cp.reduce.async.bulk (add).
+// TMA functors provide
+//   template <int H> compute(row, col0, acc[32], in[kIn][32], out[kOut][16])   (EPI_TMA_BF16; H = half
+//        of the unit: acc = columns [col0, col0+32), in[i][16H..16H+15] the matching packed operands)
+//   compute(row, col0, acc[32], out[32])                                       (EPI_TMA_RED_F32)
+//   load(i, slot, bar, col0, row0) / store(o, slot, col0, row0)                issue the TMA transfers
+enum { EPI_DIRECT = 0, EPI_TMA_BF16 = 1, EPI_TMA_RED_F32 = 2 };
+
+constexpr int kSlotBytes = 4096;   // 32 rows x 128 bytes
+template <class Epi> __host__ __device__ constexpr int epi_slots() { return Epi::kMode == EPI_DIRECT ? 0 : Epi::kIn + Epi::kOut; }
+template <class Epi> __host__ __device__ constexpr int epi_smem() { return 4 * epi_slots<Epi>() * kSlotBytes; }
+
+constexpr int kMaxSmem = 232448;   // 227 KB opt-in limit per CTA
+template <int BN, class Epi> __host__ __device__ constexpr int pick_stages() {
+  constexpr int stage = kBM * kBK * 2 + BN * kBK * 2;
+  constexpr int avail = kMaxSmem - 1024 - 512 - epi_smem<Epi>();
+  return avail / stage > 6 ? 6 : avail / stage;
+}
+template <int BN, class Epi> __host__ __device__ constexpr int smem_bytes() {
+  return pick_stages<BN, Epi>() * (kBM * kBK * 2 + BN * kBK * 2) + epi_smem<Epi>() + 512 + 1024;
+}
 
 // CL = CTAs per cluster along the output-row (M) dimension.  The CL CTAs of a cluster work on CL
 // consecutive row tiles of the SAME column tile / reduction range and share the B operand: each CTA
@@ -136,19 +189,23 @@ struct Work {
 // of B (the dominant stream: the whole weight matrix per 128 points) by CL.
 template <int BN, int STAGES, bool kNT, int CL, class Epi>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Work wk, Epi epi) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Work wk,
+               const __grid_constant__ Epi epi) {
   constexpr uint32_t A_BYTES = kBM * kBK * 2;
   constexpr uint32_t B_BYTES = BN * kBK * 2;
   constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+  constexpr int NSLOT = epi_slots<Epi>();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
+  uint8_t* sEpi = sB + STAGES * B_BYTES;                       // 4 warps x NSLOT boxes of 4 KB
+  uint64_t* full = reinterpret_cast<uint64_t*>(sEpi + 4 * NSLOT * kSlotBytes);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* ibar = tempty + 2;                                 // one per epilogue warp: operand boxes landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ibar + 4);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int m_groups = (wk.m_tiles + CL - 1) / CL;                 // row tiles are handed out CL at a time
@@ -165,6 +222,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 128); }
+    for (int s = 0; s < 4; ++s) mbar_init(&ibar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -253,22 +311,113 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== epilogue =====================
     const int q = warp - 4;                       // TMEM lane quadrant == warp % 4
     int acc = 0; uint32_t acc_phase = 0;
-    for (int it = item0; it < n_items; it += item_step) {
-      const int t = it % (m_groups * wk.n_tiles);
-      const int m_blk = (t / wk.n_tiles) * CL + crank, n_blk = t % wk.n_tiles;
-      mbar_wait(&tfull[acc], acc_phase);
-      fence_after_sync();
-      const int row = m_blk * kBM + q * 32 + lane;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+    if constexpr (Epi::kMode == EPI_DIRECT) {
+      for (int it = item0; it < n_items; it += item_step) {
+        const int t = it % (m_groups * wk.n_tiles);
+        const int m_blk = (t / wk.n_tiles) * CL + crank, n_blk = t % wk.n_tiles;
+        mbar_wait(&tfull[acc], acc_phase);
+        fence_after_sync();
+        const int row = m_blk * kBM + q * 32 + lane;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        float v[32];
-        tmem_ld32(taddr + c * 32, v);
-        epi.template apply<32>(row, n_blk * BN + c * 32, v);
+        for (int c = 0; c < BN / 32; ++c) {
+          float v[32];
+          tmem_ld32(taddr + c * 32, v);
+          epi.template apply<32>(row, n_blk * BN + c * 32, v);
+        }
+        fence_before_sync();
+        mbar_arrive(&tempty[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      fence_before_sync();
-      mbar_arrive(&tempty[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    } else {
+      constexpr int KI = Epi::kIn, KO = Epi::kOut;
+      constexpr int UW = (Epi::kMode == EPI_TMA_BF16) ? 64 : 32;        // unit width in columns
+      uint8_t* slots = sEpi + q * (NSLOT * kSlotBytes);
+      uint64_t* ib = &ibar[q];
+      uint32_t iphase = 0;
+      const uint32_t row_off = lane * 128, swz = (lane & 7) << 4;
+      auto tile_of = [&](int it, int& m_blk, int& n_blk, int& n_units) {
+        const int t = it % (m_groups * wk.n_tiles);
+        m_blk = (t / wk.n_tiles) * CL + crank; n_blk = t % wk.n_tiles;
+        const int left = wk.n_cols - n_blk * BN;
+        n_units = left >= BN ? BN / UW : (left + UW - 1) / UW;
+      };
+      auto issue_in = [&](int m_blk, int n_blk, int u) {      // one lane: operand boxes of a unit
+        if constexpr (KI > 0) {
+          mbar_expect_tx(ib, KI * kSlotBytes);
+#pragma unroll
+          for (int i = 0; i < KI; ++i) epi.load(i, slots + i * kSlotBytes, ib, n_blk * BN + u * UW, m_blk * kBM + q * 32);
+        }
+      };
+      if (KI > 0 && item0 < n_items && lane == 0) {
+        int mb, nb, nu; tile_of(item0, mb, nb, nu);
+        issue_in(mb, nb, 0);
+      }
+      for (int it = item0; it < n_items; it += item_step) {
+        int m_blk, n_blk, n_units; tile_of(it, m_blk, n_blk, n_units);
+        mbar_wait(&tfull[acc], acc_phase);
+        fence_after_sync();
+        const int row0 = m_blk * kBM + q * 32;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+        for (int u = 0; u < n_units; ++u) {
+          const int col0 = n_blk * BN + u * UW;
+          [[maybe_unused]] uint32_t in[KI > 0 ? KI : 1][32];
+          if constexpr (KI > 0) {
+            mbar_wait(ib, iphase); iphase ^= 1;
+#pragma unroll
+            for (int i = 0; i < KI; ++i)
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const uint4 v = lds128(slots + i * kSlotBytes + row_off + ((j << 4) ^ swz));
+                in[i][4 * j] = v.x; in[i][4 * j + 1] = v.y; in[i][4 * j + 2] = v.z; in[i][4 * j + 3] = v.w;
+              }
+            __syncwarp();
+            if (lane == 0) {                                  // refill the operand boxes for the next unit
+              if (u + 1 < n_units) issue_in(m_blk, n_blk, u + 1);
+              else if (it + item_step < n_items) { int mb, nb, nu; tile_of(it + item_step, mb, nb, nu); issue_in(mb, nb, 0); }
+            }
+          }
+          if constexpr (Epi::kMode == EPI_TMA_BF16) {
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+              float v[32];
+              tmem_ld32(taddr + u * UW + hf * 32, v);
+              if (hf == 1 && u == n_units - 1) { fence_before_sync(); mbar_arrive(&tempty[acc]); }   // accumulator drained
+              uint32_t out[KO][16];
+              if (hf == 0) epi.template compute<0>(row0 + lane, col0, v, in, out);
+              else epi.template compute<1>(row0 + lane, col0 + 32, v, in, out);
+              if (hf == 0) { if (lane == 0) bulk_wait_read0(); __syncwarp(); }   // previous unit's boxes were read out
+#pragma unroll
+              for (int o = 0; o < KO; ++o)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  sts128(slots + (KI + o) * kSlotBytes + row_off + (((hf * 4 + j) << 4) ^ swz),
+                         out[o][4 * j], out[o][4 * j + 1], out[o][4 * j + 2], out[o][4 * j + 3]);
+            }
+          } else {
+            float v[32];
+            tmem_ld32(taddr + u * UW, v);
+            if (u == n_units - 1) { fence_before_sync(); mbar_arrive(&tempty[acc]); }
+            uint32_t out[32];
+            epi.compute(row0 + lane, col0, v, out);
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              sts128(slots + KI * kSlotBytes + row_off + ((j << 4) ^ swz), out[4 * j], out[4 * j + 1], out[4 * j + 2], out[4 * j + 3]);
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+#pragma unroll
+            for (int o = 0; o < KO; ++o) epi.store(o, slots + (KI + o) * kSlotBytes, col0, row0);
+            bulk_commit();
+          }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      if (lane == 0) bulk_wait0();               // all boxes written before the CTA may exit
     }
   }
   fence_before_sync();
@@ -286,9 +435,12 @@ EncodeTiledFn encode_fn();
 // 2-D bf16 tensor [rows, cols] with row pitch `ld` elements; box = box_cols x box_rows, 128B swizzle
 int make_map_bf16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld,
                   int box_cols, int box_rows);
-
-template <int BN, bool kNT> constexpr int smem_bytes(int stages) {
-  return stages * (kBM * kBK * 2 + BN * kBK * 2) + (2 * stages + 4) * 8 + 16 + 1024;
+// 2-D fp32 tensor, same conventions (box_cols * 4 bytes must be 128)
+int make_map_f32(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld,
+                 int box_cols, int box_rows);
+// true when (base, ld) of an element type of `es` bytes can be described by a tensor map
+inline bool tma_ok(const void* base, long long ld, int es) {
+  return (reinterpret_cast<uintptr_t>(base) & 15) == 0 && ((ld * es) & 15) == 0;
 }
 
 constexpr int kClusterM = 2;       // CTAs per cluster sharing (multicasting) the B operand
@@ -316,15 +468,17 @@ int launch_kernel(Kern kern, int smem, int num_sms, int items, const CUtensorMap
 template <int BN, class Epi>
 int launch_tn(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* B, long long ldb,
               long long M, int N, int K, const Epi& epi, int num_sms, cudaStream_t s) {
-  constexpr int STAGES = (BN == 256) ? 4 : 6;
+  constexpr int STAGES = pick_stages<BN, Epi>();
+  static_assert(STAGES >= 2, "epilogue staging leaves no room for the operand ring");
   if (K % kBK) { set_error("tc::launch_tn: K=%d not a multiple of 64", K); return BN_ERR_ARG; }
+  if (Epi::kMode != EPI_DIRECT && N % 64) { set_error("tc::launch_tn: N=%d not a multiple of 64", N); return BN_ERR_ARG; }
   CUtensorMap ma, mb;
-  Work wk{(int)ceil_div_ll(M, kBM), ceil_div(N, BN), 1, K / kBK, K / kBK};
+  Work wk{(int)ceil_div_ll(M, kBM), ceil_div(N, BN), 1, K / kBK, K / kBK, N};
   const bool clustered = wk.m_tiles >= 2 * kClusterM && BN >= 64 * kClusterM;
   if (int rc = make_map_bf16(&ma, A, M, K, lda, kBK, kBM)) return rc;
   // clustered: every CTA fetches (and multicasts) BN / kClusterM rows of the B tile per stage
   if (int rc = make_map_bf16(&mb, B, N, K, ldb, kBK, clustered ? BN / kClusterM : BN)) return rc;
-  constexpr int smem = smem_bytes<BN, false>(STAGES);
+  constexpr int smem = smem_bytes<BN, Epi>();
   if (clustered)
     return launch_kernel<kClusterM>(gemm_tc_kernel<BN, STAGES, false, kClusterM, Epi>, smem, num_sms,
                                     ceil_div(wk.m_tiles, kClusterM) * wk.n_tiles, ma, mb, wk, epi, s, "gemm_tc_kernel<tn,mc>");
@@ -336,7 +490,7 @@ int launch_tn(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* B, lon
 template <int BN, class Epi>
 int launch_nt(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* B, long long ldb,
               int Mo, int No, long long P, const Epi& epi, int num_sms, cudaStream_t s) {
-  constexpr int STAGES = (BN == 256) ? 4 : 6;
+  constexpr int STAGES = pick_stages<BN, Epi>();
   if (Mo % 64) { set_error("tc::launch_nt: Mo=%d not a multiple of 64", Mo); return BN_ERR_ARG; }
   CUtensorMap ma, mb;
   if (int rc = make_map_bf16(&ma, A, P, Mo, lda, 64, kBK)) return rc;
@@ -344,11 +498,12 @@ int launch_nt(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* B, lon
   Work wk;
   wk.m_tiles = ceil_div(Mo, kBM); wk.n_tiles = ceil_div(No, BN);
   wk.kb_total = (int)ceil_div_ll(P, kBK);
+  wk.n_cols = No;
   const int tiles = wk.m_tiles * wk.n_tiles;
   int splits = max(1, min(ceil_div(num_sms, tiles), ceil_div(wk.kb_total, 8)));
   wk.kb_per_split = ceil_div(wk.kb_total, splits);
   wk.splits = ceil_div(wk.kb_total, wk.kb_per_split);
-  constexpr int smem = smem_bytes<BN, true>(STAGES);
+  constexpr int smem = smem_bytes<BN, Epi>();
   if (wk.m_tiles % kClusterM == 0 && BN >= 64 * kClusterM)
     return launch_kernel<kClusterM>(gemm_tc_kernel<BN, STAGES, true, kClusterM, Epi>, smem, num_sms,
                                     (wk.m_tiles / kClusterM) * wk.n_tiles * wk.splits, ma, mb, wk, epi, s, "gemm_tc_kernel<nt,mc>");

@@ -436,19 +436,13 @@ static int forward_t(bn_mlp* h, const float* params, const float* origins, int o
   encode_kernel<T><<<(unsigned)ceil_div_ll(P, 128), 128, 0, s>>>(origins, o_stride, dirs, d_stride, z, S, P,
                                                                c.n_freq_xyz, w.X3, w.ldx3);
   BN_LAUNCH_CHECK();
-  constexpr bool kFast = std::is_same<T, __nv_bfloat16>::value;
   for (int l = 0; l < L; ++l) {
     const T* A; long long lda;
     if (l == 0 || l == h->skip) { A = w.X3; lda = w.ldx3; } else { A = w.H[l - 1]; lda = w.Hld[l - 1]; }
-    if (l == 0) {
-      // first layer: sin(30 lin), |30 lin| <= 30: the MUFU path is exact to ~2e-6 there, far below
-      // the bf16 resolution of the stored activation; the fp32 mode keeps the accurate sincosf
-      EpiSin<T, kFast> epi{params + c.b_off[l], 30.0f, w.H[l], w.Hld[l], keep_c ? w.C[l] : nullptr, F, (int)P, F};
-      if (int rc = gemm_tn<T>(h, A, lda, (const T*)h->Wp[l], h->Kpad[l], P, F, h->Kpad[l], epi, s, h->Kreal[l])) return rc;
-    } else {
-      EpiSin<T, kFast> epi{params + c.b_off[l], 1.0f, w.H[l], w.Hld[l], keep_c ? w.C[l] : nullptr, F, (int)P, F};
-      if (int rc = gemm_tn<T>(h, A, lda, (const T*)h->Wp[l], h->Kpad[l], P, F, h->Kpad[l], epi, s, h->Kreal[l])) return rc;
-    }
+    // first layer: sin(30 lin), |30 lin| <= 30: the MUFU path is exact to ~2e-6 there, far below
+    // the bf16 resolution of the stored activation; the fp32 mode keeps the accurate sincosf
+    if (int rc = layer_sin<T>(h, A, lda, (const T*)h->Wp[l], h->Kpad[l], P, F, h->Kpad[l], params + c.b_off[l],
+                              l == 0 ? 30.0f : 1.0f, w.H[l], w.Hld[l], keep_c ? w.C[l] : nullptr, F, s, h->Kreal[l])) return rc;
   }
   const T* Hl = w.H[L - 1]; const long long ldl = w.Hld[L - 1];
   if (sig_only) {
@@ -456,14 +450,11 @@ static int forward_t(bn_mlp* h, const float* params, const float* origins, int o
     BN_LAUNCH_CHECK();
     return BN_OK;
   }
-  {
-    EpiBias<T> epi{params + c.b_off[BN_LIN_FEATS], w.FE, F, (int)P, F};
-    if (int rc = gemm_tn<T>(h, Hl, ldl, (const T*)h->Wf, F, P, F, F, epi, s)) return rc;
-  }
+  if (int rc = layer_bias<T>(h, Hl, ldl, (const T*)h->Wf, F, P, F, F, params + c.b_off[BN_LIN_FEATS], w.FE, F, s)) return rc;
   {
     const int HKa = hp.n_blocks * h->HH;
-    EpiSin<T, kFast> epi{h->b1cat, 1.0f, w.HD, w.ldhd, train ? w.CD : nullptr, w.ldhd, (int)P, HKa};
-    if (int rc = gemm_tn<T>(h, w.FE, F, (const T*)h->W1, F, P, HKa, F, epi, s)) return rc;
+    if (int rc = layer_sin<T>(h, w.FE, F, (const T*)h->W1, F, P, HKa, F, h->b1cat, 1.0f, w.HD, w.ldhd,
+                              train ? w.CD : nullptr, w.ldhd, s)) return rc;
   }
   heads_fwd_kernel<T><<<heads_grid(h, P), 256, 0, s>>>(hp, params, Hl, ldl, F, w.HD, w.ldhd, out, pitch, P, false);
   BN_LAUNCH_CHECK();
@@ -522,23 +513,18 @@ static int backward_t(bn_mlp* h, const float* params, const float* out, const fl
   // heads' first layer: wgrad per block (bias grads came out of heads_bwd_kernel), dgrad into the features
   for (int b = 0; b < hp.n_blocks; ++b) {
     const int lin = h->blk_lin0[b];
-    EpiWgrad ew{g + c.w_off[lin], F, h->HH, F, F, F};
-    if (int rc = gemm_nt<T>(h, w.GHD + (long long)b * h->HH, w.ldhd, w.FE, F, h->HH, F, P, ew, s)) return rc;
+    if (int rc = layer_wgrad<T>(h, w.GHD + (long long)b * h->HH, w.ldhd, w.FE, F, h->HH, F, P, g + c.w_off[lin], F, F, F, s)) return rc;
   }
   {
-    EpiDgrad<T> ed{nullptr, 0, nullptr, 0, w.GFE, F, (int)P, F};
-    if (kTC) ed.colsum = g + c.b_off[BN_LIN_FEATS];
-    if (int rc = gemm_tn<T>(h, w.GHD, w.ldhd, (const T*)h->W1T, (long long)h->n_blocks * h->HH, P, F, HKa, ed, s)) return rc;
-    if (!kTC) { if (int rc = colsum<T>(w.GFE, F, F, P, g + c.b_off[BN_LIN_FEATS], s)) return rc; }
+    DgradArgs<T> a; a.bias_grad = g + c.b_off[BN_LIN_FEATS];
+    if (int rc = layer_dgrad<T>(h, w.GHD, w.ldhd, (const T*)h->W1T, (long long)h->n_blocks * h->HH, P, F, HKa, a, w.GFE, F, s)) return rc;
   }
   // feature layer
   {
-    EpiWgrad ew{g + c.w_off[BN_LIN_FEATS], F, F, F, F, F};
-    if (int rc = gemm_nt<T>(h, w.GFE, F, Hl, ldl, F, F, P, ew, s)) return rc;
-    EpiDgrad<T> ed{w.G7D, F, w.C[L - 1], F, w.GA, F, (int)P, F};
-    if (normals) { ed.add2 = w.U[L - 1]; ed.ld2 = F; }
-    if (kTC) ed.colsum = g + c.b_off[L - 1];
-    if (int rc = gemm_tn<T>(h, w.GFE, F, (const T*)h->WfT, F, P, F, F, ed, s)) return rc;
+    if (int rc = layer_wgrad<T>(h, w.GFE, F, Hl, ldl, F, F, P, g + c.w_off[BN_LIN_FEATS], F, F, F, s)) return rc;
+    DgradArgs<T> a; a.addend = w.G7D; a.lda = F; a.mulc = w.C[L - 1]; a.ldm = F; a.bias_grad = g + c.b_off[L - 1];
+    if (normals) { a.add2 = w.U[L - 1]; a.ld2 = F; }
+    if (int rc = layer_dgrad<T>(h, w.GFE, F, (const T*)h->WfT, F, P, F, F, a, w.GA, F, s)) return rc;
   }
   // trunk, last layer first.  cur = dZ_l
   T* cur = w.GA; T* nxt = w.GB;
@@ -546,15 +532,13 @@ static int backward_t(bn_mlp* h, const float* params, const float* out, const fl
     const bool enc_in = (l == 0 || l == h->skip);
     const T* In; long long ldin;
     if (enc_in) { In = w.X3; ldin = w.ldx3; } else { In = w.H[l - 1]; ldin = w.Hld[l - 1]; }
-    EpiWgrad ew{g + c.w_off[l], h->Kreal[l], F, h->Kpad[l], enc_in ? h->E : h->Kpad[l], enc_in ? kEncPad : h->Kpad[l]};
-    if (int rc = gemm_nt<T>(h, cur, F, In, ldin, F, h->Kpad[l], P, ew, s, 2.0 * P * F * h->Kreal[l])) return rc;
-    if (!kTC) { if (int rc = colsum<T>(cur, F, F, P, g + c.b_off[l], s)) return rc; }
+    if (int rc = layer_wgrad<T>(h, cur, F, In, ldin, F, h->Kpad[l], P, g + c.w_off[l], h->Kreal[l],
+                                enc_in ? h->E : h->Kpad[l], enc_in ? kEncPad : h->Kpad[l], s, 2.0 * P * F * h->Kreal[l])) return rc;
     if (l > 0) {
       const T* BT = (const T*)h->WTp[l] + (l == h->skip ? (long long)kEncPad * F : 0);
-      EpiDgrad<T> ed{nullptr, 0, w.C[l - 1], F, nxt, F, (int)P, F};
-      if (normals) { ed.add2 = w.U[l - 1]; ed.ld2 = F; }
-      if (kTC) ed.colsum = g + c.b_off[l - 1];
-      if (int rc = gemm_tn<T>(h, cur, F, BT, F, P, F, F, ed, s)) return rc;
+      DgradArgs<T> a; a.mulc = w.C[l - 1]; a.ldm = F; a.bias_grad = g + c.b_off[l - 1];
+      if (normals) { a.add2 = w.U[l - 1]; a.ld2 = F; }
+      if (int rc = layer_dgrad<T>(h, cur, F, BT, F, P, F, F, a, nxt, F, s)) return rc;
       T* t = cur; cur = nxt; nxt = t;
     }
   }
@@ -698,4 +682,21 @@ int bn_debug_gemm(int kind, int precision, const void* A, long long lda, const v
   EpiWgrad epi{out, ldo, (int)M, N, N, N};
   if (precision == BN_PREC_BF16) return gemm_nt<__nv_bfloat16>(&h, (const __nv_bfloat16*)A, lda, (const __nv_bfloat16*)B, ldb, (int)M, N, K, epi, stream);
   return gemm_nt<float>(&h, (const float*)A, lda, (const float*)B, ldb, (int)M, N, K, epi, stream);
+}
+
+extern "C" __attribute__((visibility("default")))
+int bn_debug_gemm_epi(int kind, const void* A, long long lda, const void* B, long long ldb, void* out, long long ldo,
+                      const void* add, const void* mul, float* colsum, int pad_lo, int pad_hi,
+                      long long M, int N, long long K, cudaStream_t stream) {
+  BN_CHECK_ARG(A && B && out, "null pointer");
+  int dev = 0; BN_CUDA(cudaGetDevice(&dev));
+  if (int rc = bn_device_check(dev)) return rc;
+  bn_mlp h{}; cudaDeviceProp prop; BN_CUDA(cudaGetDeviceProperties(&prop, dev)); h.num_sms = prop.multiProcessorCount;
+  typedef __nv_bfloat16 T;
+  if (kind == 0) {
+    DgradArgs<T> a; a.addend = (const T*)add; a.lda = ldo; a.mulc = (const T*)mul; a.ldm = ldo; a.bias_grad = colsum;
+    return layer_dgrad<T>(&h, (const T*)A, lda, (const T*)B, ldb, M, N, (int)K, a, (T*)out, ldo, stream);
+  }
+  BN_CHECK_ARG(tc::wgrad_tma_ok((const float*)out, ldo, N, pad_lo, pad_hi), "output not addressable by the TMA");
+  return layer_wgrad<T>(&h, (const T*)A, lda, (const T*)B, ldb, (int)M, N, K, (float*)out, ldo, pad_lo, pad_hi, stream);
 }

@@ -26,6 +26,7 @@
 #include "epilogues.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "epilogues_tc.cuh"
 
 namespace bn {
 
@@ -238,6 +239,129 @@ static int gemm_nt(const bn_mlp* h, const T* A, long long lda, const T* B, long 
   }
   prof_end(s);
   return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused layers: one call = one GEMM + epilogue.  bf16 -> tcgen05 mainloop with the TMA-staged
+// functors of epilogues_tc.cuh; fp32 -> CUDA-core mainloop with the direct functors of epilogues.cuh.
+constexpr bool is_bf16_v(const __nv_bfloat16*) { return true; }
+constexpr bool is_bf16_v(const float*) { return false; }
+
+// H = sin(w0 (A W^T + b))  [, C = w0 cos(...)]      A:[P,K] W:[N,K]
+template <typename T>
+static int layer_sin(const bn_mlp* h, const T* A, long long lda, const T* W, long long ldw, long long P, int N, int K,
+                     const float* bias, float w0, T* H, long long ldh, T* C, long long ldc, cudaStream_t s, int k_real = -1) {
+  if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+    if (C) {
+      tc::EpiSinT<true> e; e.bias = bias; e.w0 = w0;
+      if (int rc = tc::stream_map(&e.out_map[0], H, P, N, ldh)) return rc;
+      if (int rc = tc::stream_map(&e.out_map[1], C, P, N, ldc)) return rc;
+      return gemm_tn<T>(h, A, lda, W, ldw, P, N, K, e, s, k_real);
+    }
+    tc::EpiSinT<false> e; e.bias = bias; e.w0 = w0;
+    if (int rc = tc::stream_map(&e.out_map[0], H, P, N, ldh)) return rc;
+    return gemm_tn<T>(h, A, lda, W, ldw, P, N, K, e, s, k_real);
+  } else {
+    EpiSin<T, false> e{bias, w0, H, ldh, C, ldc, (int)P, N};
+    return gemm_tn<T>(h, A, lda, W, ldw, P, N, K, e, s, k_real);
+  }
+}
+
+// out = A W^T + b
+template <typename T>
+static int layer_bias(const bn_mlp* h, const T* A, long long lda, const T* W, long long ldw, long long P, int N, int K,
+                      const float* bias, T* out, long long ldo, cudaStream_t s) {
+  if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+    tc::EpiBiasT e; e.bias = bias;
+    if (int rc = tc::stream_map(&e.out_map[0], out, P, N, ldo)) return rc;
+    return gemm_tn<T>(h, A, lda, W, ldw, P, N, K, e, s);
+  } else {
+    EpiBias<T> e{bias, out, ldo, (int)P, N};
+    return gemm_tn<T>(h, A, lda, W, ldw, P, N, K, e, s);
+  }
+}
+
+// out = ((A BT^T) [+ addend]) [* mulc] [+ add2];  raw = (A BT^T) + addend.  bias_grad (nullable) += column
+// sums of out (fused into the tcgen05 epilogue; a separate pass in the fp32 mode).
+template <typename T> struct DgradArgs {
+  const T* addend = nullptr; long long lda = 0;
+  const T* mulc = nullptr; long long ldm = 0;
+  const T* add2 = nullptr; long long ld2 = 0;
+  T* raw = nullptr; long long ldr = 0;
+  float* bias_grad = nullptr;
+};
+template <bool kAdd, bool kMul, bool kAdd2, bool kRaw>
+static int dgrad_tc(const bn_mlp* h, const __nv_bfloat16* A, long long lda, const __nv_bfloat16* BT, long long ldb, long long P,
+                    int N, int K, const DgradArgs<__nv_bfloat16>& a, __nv_bfloat16* out, long long ldo, cudaStream_t s) {
+  tc::EpiDgradT<kAdd, kMul, kAdd2, kRaw> e; e.colsum = a.bias_grad;
+  int i = 0;
+  if (kAdd) { if (int rc = tc::stream_map(&e.in_map[i++], a.addend, P, N, a.lda)) return rc; }
+  if (kMul) { if (int rc = tc::stream_map(&e.in_map[i++], a.mulc, P, N, a.ldm)) return rc; }
+  if (kAdd2) { if (int rc = tc::stream_map(&e.in_map[i++], a.add2, P, N, a.ld2)) return rc; }
+  if (int rc = tc::stream_map(&e.out_map[0], out, P, N, ldo)) return rc;
+  if (kRaw) { if (int rc = tc::stream_map(&e.out_map[kRaw ? 1 : 0], a.raw, P, N, a.ldr)) return rc; }
+  return gemm_tn<__nv_bfloat16>(h, A, lda, BT, ldb, P, N, K, e, s);
+}
+
+template <typename T>
+static int colsum(const T* X, long long ldx, int ncols, long long P, float* dst, cudaStream_t s);
+
+template <typename T>
+static int layer_dgrad(const bn_mlp* h, const T* A, long long lda, const T* BT, long long ldb, long long P, int N, int K,
+                       const DgradArgs<T>& a, T* out, long long ldo, cudaStream_t s) {
+  if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+    const int code = (a.addend ? 1 : 0) | (a.mulc ? 2 : 0) | (a.add2 ? 4 : 0) | (a.raw ? 8 : 0);
+    switch (code) {
+      case 0: return dgrad_tc<false, false, false, false>(h, A, lda, BT, ldb, P, N, K, a, out, ldo, s);
+      case 1: return dgrad_tc<true, false, false, false>(h, A, lda, BT, ldb, P, N, K, a, out, ldo, s);
+      case 2: return dgrad_tc<false, true, false, false>(h, A, lda, BT, ldb, P, N, K, a, out, ldo, s);
+      case 3: return dgrad_tc<true, true, false, false>(h, A, lda, BT, ldb, P, N, K, a, out, ldo, s);
+      case 6: return dgrad_tc<false, true, true, false>(h, A, lda, BT, ldb, P, N, K, a, out, ldo, s);
+      case 7: return dgrad_tc<true, true, true, false>(h, A, lda, BT, ldb, P, N, K, a, out, ldo, s);
+      case 10: return dgrad_tc<false, true, false, true>(h, A, lda, BT, ldb, P, N, K, a, out, ldo, s);
+      default: set_error("layer_dgrad: operand combination %d has no tcgen05 epilogue", code); return BN_ERR_ARG;
+    }
+  } else {
+    EpiDgrad<T> e{a.addend, a.lda, a.mulc, a.ldm, out, ldo, (int)P, N};
+    e.raw_out = a.raw; e.ldr = a.ldr; e.add2 = a.add2; e.ld2 = a.ld2;
+    if (int rc = gemm_tn<T>(h, A, lda, BT, ldb, P, N, K, e, s)) return rc;
+    if (a.bias_grad) return colsum<T>(out, ldo, N, P, a.bias_grad, s);
+    return BN_OK;
+  }
+}
+
+// second-order sweep layer (normals.cu): ubar = (A W^T) ⊙ c ;  U <- ((A W^T) ⊙ U) (-w0^2 H)
+template <typename T>
+static int layer_second(const bn_mlp* h, const T* A, long long lda, const T* W, long long ldw, long long P, int N, int K,
+                        const T* Cc, long long ldc, T* U, long long ldu, const T* H, long long ldh, T* ubar, long long ldo,
+                        float neg_w0sq, cudaStream_t s, int k_real) {
+  if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+    tc::EpiSecondT e; e.neg_w0sq = neg_w0sq;
+    if (int rc = tc::stream_map(&e.in_map[0], Cc, P, N, ldc)) return rc;
+    if (int rc = tc::stream_map(&e.in_map[1], U, P, N, ldu)) return rc;
+    if (int rc = tc::stream_map(&e.in_map[2], H, P, N, ldh)) return rc;
+    if (int rc = tc::stream_map(&e.out_map[0], ubar, P, N, ldo)) return rc;
+    if (int rc = tc::stream_map(&e.out_map[1], U, P, N, ldu)) return rc;
+    return gemm_tn<T>(h, A, lda, W, ldw, P, N, K, e, s, k_real);
+  } else {
+    EpiSecond<T> e{Cc, ldc, U, ldu, H, ldh, ubar, ldo, neg_w0sq, (int)P, N};
+    return gemm_tn<T>(h, A, lda, W, ldw, P, N, K, e, s, k_real);
+  }
+}
+
+// dW [Mo, Kreal] += G[:, :Mo]^T In[:, :No]   (No = packed width of In with padding [pad_lo, pad_hi))
+template <typename T>
+static int layer_wgrad(const bn_mlp* h, const T* G, long long ldg, const T* In, long long ldin, int Mo, int No, long long P,
+                       float* dW, long long ldw, int pad_lo, int pad_hi, cudaStream_t s, double flops = -1.0) {
+  if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+    if (tc::wgrad_tma_ok(dW, ldw, No, pad_lo, pad_hi)) {
+      tc::EpiWgradT e;
+      if (int rc = tc::make_wgrad(&e, dW, ldw, Mo, No, pad_lo, pad_hi)) return rc;
+      return gemm_nt<T>(h, G, ldg, In, ldin, Mo, No, P, e, s, flops);
+    }
+  }
+  EpiWgrad e{dW, ldw, Mo, No, pad_lo, pad_hi};
+  return gemm_nt<T>(h, G, ldg, In, ldin, Mo, No, P, e, s, flops);
 }
 
 template <typename T>

@@ -159,17 +159,18 @@ static int normals_forward_t(bn_mlp* h, const float* params, float* out, int pit
   }
   for (int l = L - 1; l >= 1; --l) {
     const T* BT = (const T*)h->WTp[l] + (l == h->skip ? (long long)kEncPad * F : 0);
-    EpiDgrad<T> ed{nullptr, 0, w.C[l - 1], F, w.A[l - 1], F, (int)P, F};
-    if (train) { ed.raw_out = w.U[l - 1]; ed.ldr = F; }
-    if (int rc = gemm_tn<T>(h, w.A[l], F, BT, F, P, F, F, ed, s)) return rc;
+    DgradArgs<T> a; a.mulc = w.C[l - 1]; a.ldm = F;
+    if (train) { a.raw = w.U[l - 1]; a.ldr = F; }
+    if (int rc = layer_dgrad<T>(h, w.A[l], F, BT, F, P, F, F, a, w.A[l - 1], F, s)) return rc;
     if (l == h->skip) {
-      EpiDgrad<T> e2{nullptr, 0, nullptr, 0, w.EE, kEncPad, (int)P, kEncPad};
-      if (int rc = gemm_tn<T>(h, w.A[l], F, (const T*)h->WTp[l], F, P, kEncPad, F, e2, s)) return rc;
+      DgradArgs<T> a2;
+      if (int rc = layer_dgrad<T>(h, w.A[l], F, (const T*)h->WTp[l], F, P, kEncPad, F, a2, w.EE, kEncPad, s)) return rc;
     }
   }
   {
-    EpiDgrad<T> e0{h->skip > 0 ? w.EE : nullptr, kEncPad, nullptr, 0, w.EE0, kEncPad, (int)P, kEncPad};
-    if (int rc = gemm_tn<T>(h, w.A[0], F, (const T*)h->WTp[0], F, P, kEncPad, F, e0, s)) return rc;
+    DgradArgs<T> a0;
+    if (h->skip > 0) { a0.addend = w.EE; a0.lda = kEncPad; }
+    if (int rc = layer_dgrad<T>(h, w.A[0], F, (const T*)h->WTp[0], F, P, kEncPad, F, a0, w.EE0, kEncPad, s)) return rc;
   }
   normal_from_enc_kernel<T><<<(unsigned)ceil_div_ll(P, 128), 128, 0, s>>>(w.EE0, w.X3, w.ldx3, h->cfg.n_freq_xyz, out, pitch, ch,
                                                                         train ? w.GRAW : nullptr, P);
@@ -196,10 +197,10 @@ static int normals_backward_t(bn_mlp* h, const float* params, const float* out, 
     if (l == h->skip - 1) { dst = w.UBX + kEncPad; ldd = w.ldx3; }
     else { dst = (l & 1) ? w.UBB : w.UBA; ldd = F; }
     const float w0 = l == 0 ? 30.0f : 1.0f;
-    EpiSecond<T> es{w.C[l], F, w.U[l], F, w.H[l], w.Hld[l], dst, ldd, -w0 * w0, (int)P, F};
-    if (int rc = gemm_tn<T>(h, Aop, lda, (const T*)h->Wp[l], h->Kpad[l], P, F, h->Kpad[l], es, s, h->Kreal[l])) return rc;
-    EpiWgrad ew{g + c.w_off[l], h->Kreal[l], F, h->Kpad[l], enc_in ? h->E : h->Kpad[l], enc_in ? kEncPad : h->Kpad[l]};
-    if (int rc = gemm_nt<T>(h, w.A[l], F, Aop, lda, F, h->Kpad[l], P, ew, s, 2.0 * P * F * h->Kreal[l])) return rc;
+    if (int rc = layer_second<T>(h, Aop, lda, (const T*)h->Wp[l], h->Kpad[l], P, F, h->Kpad[l], w.C[l], F, w.U[l], F,
+                                 w.H[l], w.Hld[l], dst, ldd, -w0 * w0, s, h->Kreal[l])) return rc;
+    if (int rc = layer_wgrad<T>(h, w.A[l], F, Aop, lda, F, h->Kpad[l], P, g + c.w_off[l], h->Kreal[l],
+                                enc_in ? h->E : h->Kpad[l], enc_in ? kEncPad : h->Kpad[l], s, 2.0 * P * F * h->Kreal[l])) return rc;
     prev = dst; ldprev = ldd;
   }
   const long long wsig = c.w_off[BN_LIN_SIGMA];

@@ -256,6 +256,15 @@ int bn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_a
 int bn_debug_gemm(int kind, int precision, const void* A, long long lda, const void* B, long long ldb,
                   float* out, long long ldo, long long M, int N, long long K, cudaStream_t stream);
 
+/* Unit-test hook for the TMA-staged epilogues of the tcgen05 GEMM (bf16 operands only):
+ *   kind 0: out_bf16[M,N] = ((A[M,K] B[N,K]^T) + add[M,N]) * mul[M,N]   (add / mul nullable, bf16, pitch ldo);
+ *           colsum[N] (nullable, fp32) += column sums of out
+ *   kind 1: out_f32[M, N - (pad_hi - pad_lo)] += A[K,M]^T B[K,N] through 32x32 fp32 TMA reduce-add boxes,
+ *           dropping the packed columns [pad_lo, pad_hi) (pitch ldo). */
+int bn_debug_gemm_epi(int kind, const void* A, long long lda, const void* B, long long ldb, void* out, long long ldo,
+                      const void* add, const void* mul, float* colsum, int pad_lo, int pad_hi,
+                      long long M, int N, long long K, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -74,3 +74,50 @@ def test_nt_simt_fp32(cuda, Mo, No, P):
     ref = A.t() @ B
     out = _gemm(1, L.BN_PREC_FP32, A, B, Mo, No, P)
     assert (out - ref).abs().max().item() < 1e-3
+
+
+def _vp(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+@pytest.mark.parametrize("M,N,K,use_add,use_mul", [(4096, 512, 512, False, True), (1000, 512, 512, True, True), (300, 256, 64, False, False),
+                                                   (2048, 768, 512, False, True), (130, 64, 512, True, False), (20000, 512, 576, False, True)])
+def test_tn_tma_epilogue(cuda, M, N, K, use_add, use_mul):
+    """TMA-staged dgrad epilogue: operand boxes in, bf16 boxes out, fused column sums; ragged M."""
+    g = torch.Generator().manual_seed(M + N + K)
+    A = (torch.randn(M, K, generator=g) * 0.5).to(cuda).to(torch.bfloat16)
+    B = (torch.randn(N, K, generator=g) * 0.1).to(cuda).to(torch.bfloat16)
+    add = (torch.randn(M, N, generator=g)).to(cuda).to(torch.bfloat16) if use_add else None
+    mul = (torch.randn(M, N, generator=g)).to(cuda).to(torch.bfloat16) if use_mul else None
+    out = torch.full((M, N), 7.0, dtype=torch.bfloat16, device=cuda)
+    cs = torch.zeros(N, dtype=torch.float32, device=cuda)
+    L.check(L.load().bn_debug_gemm_epi(0, _vp(A), A.stride(0), _vp(B), B.stride(0), _vp(out), N, _vp(add), _vp(mul), _vp(cs),
+                                       0, 0, M, N, K, L.stream_ptr()))
+    torch.cuda.synchronize()
+    ref = A.float() @ B.float().t()
+    if use_add:
+        ref = ref + add.float()
+    if use_mul:
+        ref = ref * mul.float()
+    scale = max(1.0, ref.abs().max().item())
+    assert (out.float() - ref).abs().max().item() < 1e-2 * scale            # bf16 rounding of the output
+    assert (cs - ref.sum(0)).abs().max().item() < 2e-3 * scale * (M ** 0.5) + 1e-2 * scale
+
+
+@pytest.mark.parametrize("Mo,No,P,pad_lo,pad_hi", [(512, 512, 4096, 512, 512), (512, 576, 3000, 60, 64), (512, 64, 5000, 60, 64),
+                                                   (256, 512, 8192, 512, 512)])
+def test_nt_tma_reduce_epilogue(cuda, Mo, No, P, pad_lo, pad_hi):
+    """wgrad through cp.reduce.async.bulk (fp32 add) with the [enc|pad|h] -> Linear(572) column remap."""
+    g = torch.Generator().manual_seed(Mo + No + P)
+    A = (torch.randn(P, Mo, generator=g) * 0.1).to(cuda).to(torch.bfloat16)
+    B = (torch.randn(P, No, generator=g) * 0.5).to(cuda).to(torch.bfloat16)
+    kreal = No - (pad_hi - pad_lo)
+    base = torch.randn(Mo, kreal, generator=g).to(cuda)
+    out = base.clone()
+    L.check(L.load().bn_debug_gemm_epi(1, _vp(A), A.stride(0), _vp(B), B.stride(0), _vp(out), kreal, None, None, None,
+                                       pad_lo, pad_hi, Mo, No, P, L.stream_ptr()))
+    torch.cuda.synchronize()
+    full = A.float().t() @ B.float()
+    ref = base + torch.cat([full[:, :pad_lo], full[:, pad_hi:]], dim=1)
+    err = (out - ref).abs().max().item()
+    assert err < 2e-3 * max(1.0, ref.abs().max().item()), f"TMA reduce wgrad max err {err}"
