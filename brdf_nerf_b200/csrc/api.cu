@@ -69,11 +69,11 @@ extern "C" __attribute__((visibility("default"))) int bn_abi_version(void) { ret
 extern "C" __attribute__((visibility("default"))) const char* bn_last_error(void) { return bn::g_err; }
 
 extern "C" __attribute__((visibility("default"))) int bn_device_check(int device) {
-  cudaDeviceProp prop;
-  BN_CUDA(cudaGetDeviceProperties(&prop, device));
-  if (prop.major != 10) {
-    bn::set_error("device %d is sm_%d%d; this library only runs on sm_100-class (B200) GPUs",
-                  device, prop.major, prop.minor);
+  int major = 0, minor = 0;
+  BN_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  BN_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device));
+  if (major != 10) {
+    bn::set_error("device %d is sm_%d%d; this library only runs on sm_100-class (B200) GPUs", device, major, minor);
     return BN_ERR_DEVICE;
   }
   return BN_OK;

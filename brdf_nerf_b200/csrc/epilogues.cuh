@@ -209,6 +209,15 @@ struct EpiWgrad {
   }
 };
 
+// accumulator read back and dropped: isolates the mainloop in bench_gemm.py
+struct EpiNull {
+  static constexpr int kMode = 0, kIn = 0, kOut = 0;
+  float* sink;
+  template <int n> __device__ __forceinline__ void apply(int row, int col0, const float (&acc)[n]) const {
+    if (acc[0] == 1.2345e38f && acc[n - 1] == -1.2345e38f) sink[0] = acc[1] + row + col0;      // never true: keeps the loads alive
+  }
+};
+
 // plain fp32 store (debug / unit-test entry point)
 struct EpiStoreF32 {
   static constexpr int kMode = 0, kIn = 0, kOut = 0;   // direct global-memory epilogue (tc::EPI_DIRECT)

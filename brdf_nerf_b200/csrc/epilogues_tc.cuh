@@ -1,6 +1,6 @@
 // TMA-staged epilogue functors of the tcgen05 GEMM (gemm_tc.cuh, modes EPI_TMA_BF16 / EPI_TMA_RED_F32).
 // Same math as the direct functors of epilogues.cuh (which the fp32 CUDA-core mode keeps using); here a
-// thread owns one row of a 32-row x 64-column unit, element-wise operands arrive as packed bf16x2
+// thread owns 32 columns of one row of a 32-row x 64-column unit, element-wise operands arrive as packed bf16x2
 // registers read from the warp's swizzled operand boxes, results leave as packed bf16x2 registers.
 //
 // Reference ops fused here (paths relative to /root/reference):
@@ -34,7 +34,7 @@ struct EpiSinT {
   static constexpr int kMode = EPI_TMA_BF16, kIn = 0, kOut = kSaveC ? 2 : 1;
   CUtensorMap out_map[kOut];
   const float* bias; float w0;
-  template <int H> __device__ __forceinline__ void compute(int, int col0, const float (&acc)[32], const uint32_t (&)[1][32],
+  __device__ __forceinline__ void compute(int, int col0, const float (&acc)[32], const uint32_t (&)[1][16],
                                                            uint32_t (&out)[kOut][16]) const {
     const float4* bp = reinterpret_cast<const float4*>(bias + col0);
 #pragma unroll
@@ -59,7 +59,7 @@ struct EpiBiasT {
   static constexpr int kMode = EPI_TMA_BF16, kIn = 0, kOut = 1;
   CUtensorMap out_map[1];
   const float* bias;
-  template <int H> __device__ __forceinline__ void compute(int, int col0, const float (&acc)[32], const uint32_t (&)[1][32],
+  __device__ __forceinline__ void compute(int, int col0, const float (&acc)[32], const uint32_t (&)[1][16],
                                                            uint32_t (&out)[1][16]) const {
     const float4* bp = reinterpret_cast<const float4*>(bias + col0);
 #pragma unroll
@@ -73,27 +73,51 @@ struct EpiBiasT {
   __device__ __forceinline__ void store(int, const void* slot, int col0, int row0) const { tma_store_2d(&out_map[0], slot, col0, row0); }
 };
 
-// dgrad: out = (acc [+ addend]) [* mulc] [+ add2];  raw = acc + addend (before the mask), optional.
-// Operand streams in order [addend][mulc][add2], outputs [out][raw].  colsum (bias gradient of the
-// layer below = column sums of `out`): the 32 lanes hold 32 consecutive rows of the same 32 columns;
-// a 31-shuffle butterfly leaves lane L with the sum of column L, added with one coalesced red.global.
-// Rows past M contribute zeros (TMA zero-fills their A rows and operands).
-template <bool kAdd, bool kMul, bool kAdd2, bool kRaw>
+// dgrad: out = (acc [+ addend] [+ rank]) [* mulc] [+ add2];  raw = acc + addend (before the mask), optional.
+// Operand streams in order [addend][mulc][add2], outputs [out][raw].
+// rank (kRank): sum_k r[row][k] * v_k[col], a rank-<=4 term built from per-row scalars (bf16, 4 per row) and
+// per-column fp32 vectors — the direct gradients of sigma / the learned normal into h_{L-1}
+// (dsigma * w_sigma + sum_k dv_k * Wg_k) without ever materialising that [P, F] matrix.
+// colsum (bias gradient of the layer below = column sums of `out`): the 32 lanes hold 32 consecutive rows
+// of the same 32 columns; a 31-shuffle butterfly leaves lane L with the sum of column L, added with one
+// coalesced red.global.  Rows past M contribute zeros (TMA zero-fills their A rows and operands).
+template <bool kAdd, bool kMul, bool kAdd2, bool kRaw, bool kRank = false>
 struct EpiDgradT {
   static constexpr int kMode = EPI_TMA_BF16, kIn = (int)kAdd + (int)kMul + (int)kAdd2, kOut = 1 + (int)kRaw;
   CUtensorMap in_map[kIn > 0 ? kIn : 1];
   CUtensorMap out_map[kOut];
   float* colsum;
-  template <int H> __device__ __forceinline__ void compute(int, int col0, const float (&acc)[32],
-                                                           const uint32_t (&in)[kIn > 0 ? kIn : 1][32], uint32_t (&out)[kOut][16]) const {
+  const __nv_bfloat16* rank_rows; long long rank_ld;      // r[row][0..3]
+  const float* rank_col[4]; int n_rank; int M;
+  __device__ __forceinline__ void compute(int row, int col0, const float (&acc)[32],
+                                          const uint32_t (&in)[kIn > 0 ? kIn : 1][16], uint32_t (&out)[kOut][16]) const {
     float o[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) o[j] = acc[j];
     int s = 0;
     if constexpr (kAdd) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) { o[2 * j] += bf_lo(in[s][16 * H + j]); o[2 * j + 1] += bf_hi(in[s][16 * H + j]); }
+      for (int j = 0; j < 16; ++j) { o[2 * j] += bf_lo(in[s][j]); o[2 * j + 1] += bf_hi(in[s][j]); }
       ++s;
+    }
+    if constexpr (kRank) {
+      float rs[4] = {0.f, 0.f, 0.f, 0.f};
+      if (row < M) {
+        const uint2 r = __ldg(reinterpret_cast<const uint2*>(rank_rows + (long long)row * rank_ld));
+        rs[0] = bf_lo(r.x); rs[1] = bf_hi(r.x); rs[2] = bf_lo(r.y); rs[3] = bf_hi(r.y);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k < n_rank) {
+          const float4* wp = reinterpret_cast<const float4*>(rank_col[k] + col0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 w = __ldg(wp + j);
+            o[4 * j] = fmaf(rs[k], w.x, o[4 * j]); o[4 * j + 1] = fmaf(rs[k], w.y, o[4 * j + 1]);
+            o[4 * j + 2] = fmaf(rs[k], w.z, o[4 * j + 2]); o[4 * j + 3] = fmaf(rs[k], w.w, o[4 * j + 3]);
+          }
+        }
+      }
     }
     if constexpr (kRaw) {
 #pragma unroll
@@ -101,12 +125,12 @@ struct EpiDgradT {
     }
     if constexpr (kMul) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) { o[2 * j] *= bf_lo(in[s][16 * H + j]); o[2 * j + 1] *= bf_hi(in[s][16 * H + j]); }
+      for (int j = 0; j < 16; ++j) { o[2 * j] *= bf_lo(in[s][j]); o[2 * j + 1] *= bf_hi(in[s][j]); }
       ++s;
     }
     if constexpr (kAdd2) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) { o[2 * j] += bf_lo(in[s][16 * H + j]); o[2 * j + 1] += bf_hi(in[s][16 * H + j]); }
+      for (int j = 0; j < 16; ++j) { o[2 * j] += bf_lo(in[s][j]); o[2 * j + 1] += bf_hi(in[s][j]); }
       ++s;
     }
 #pragma unroll
@@ -138,11 +162,11 @@ struct EpiSecondT {
   CUtensorMap in_map[3];
   CUtensorMap out_map[2];
   float neg_w0sq;
-  template <int H> __device__ __forceinline__ void compute(int, int, const float (&acc)[32], const uint32_t (&in)[3][32],
-                                                           uint32_t (&out)[2][16]) const {
+  __device__ __forceinline__ void compute(int, int, const float (&acc)[32], const uint32_t (&in)[3][16],
+                                          uint32_t (&out)[2][16]) const {
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      const uint32_t c = in[0][16 * H + j], u = in[1][16 * H + j], h = in[2][16 * H + j];
+      const uint32_t c = in[0][j], u = in[1][j], h = in[2][j];
       const float a0 = acc[2 * j], a1 = acc[2 * j + 1];
       out[0][j] = bf_pack(a0 * bf_lo(c), a1 * bf_hi(c));
       out[1][j] = bf_pack(a0 * bf_lo(u) * neg_w0sq * bf_lo(h), a1 * bf_hi(u) * neg_w0sq * bf_hi(h));

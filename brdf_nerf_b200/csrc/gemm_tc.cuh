@@ -18,7 +18,7 @@ namespace tc {
 
 constexpr int kBM = 128;          // rows of the output tile (UMMA M, cta_group::1)
 constexpr int kBK = 64;           // bf16 elements per smem row = 128 bytes = one swizzle atom row
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;      // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-11: epilogue (two per TMEM quadrant)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -85,6 +85,11 @@ __device__ __forceinline__ uint4 lds128(const void* p) {
 __device__ __forceinline__ void sts128(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(smem_u32(p)), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t cluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t cluster_nctaid_x() { uint32_t r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
@@ -163,14 +168,16 @@ struct Work {
 //                     global access is a full-line TMA transaction instead of 32 scattered sectors.
 //   EPI_TMA_RED_F32 : units of 32 rows x 32 fp32 columns leave through cp.reduce.async.bulk (add).
 // TMA functors provide
-//   template <int H> compute(row, col0, acc[32], in[kIn][32], out[kOut][16])   (EPI_TMA_BF16; H = half
-//        of the unit: acc = columns [col0, col0+32), in[i][16H..16H+15] the matching packed operands)
+//   compute(row, col0, acc[32], in[kIn][16], out[kOut][16])   (EPI_TMA_BF16: the two warps of a quadrant
+//        each own 32 of the unit's 64 columns: acc = columns [col0, col0+32), in/out packed bf16x2)
 //   compute(row, col0, acc[32], out[32])                                       (EPI_TMA_RED_F32)
 //   load(i, slot, bar, col0, row0) / store(o, slot, col0, row0)                issue the TMA transfers
 enum { EPI_DIRECT = 0, EPI_TMA_BF16 = 1, EPI_TMA_RED_F32 = 2 };
 
 constexpr int kSlotBytes = 4096;   // 32 rows x 128 bytes
-template <class Epi> __host__ __device__ constexpr int epi_slots() { return Epi::kMode == EPI_DIRECT ? 0 : Epi::kIn + Epi::kOut; }
+template <class Epi> __host__ __device__ constexpr int epi_slots() {        // 4 KB boxes per TMEM quadrant (= per pair of epilogue warps)
+  return Epi::kMode == EPI_DIRECT ? 0 : (Epi::kMode == EPI_TMA_RED_F32 ? 2 : Epi::kIn + Epi::kOut);
+}
 template <class Epi> __host__ __device__ constexpr int epi_smem() { return 4 * epi_slots<Epi>() * kSlotBytes; }
 
 constexpr int kMaxSmem = 232448;   // 227 KB opt-in limit per CTA
@@ -199,7 +206,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
-  uint8_t* sEpi = sB + STAGES * B_BYTES;                       // 4 warps x NSLOT boxes of 4 KB
+  uint8_t* sEpi = sB + STAGES * B_BYTES;                       // 4 quadrants x NSLOT boxes of 4 KB
   uint64_t* full = reinterpret_cast<uint64_t*>(sEpi + 4 * NSLOT * kSlotBytes);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
@@ -221,7 +228,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 128); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 256); }
     for (int s = 0; s < 4; ++s) mbar_init(&ibar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -309,7 +316,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    const int q = warp - 4;                       // TMEM lane quadrant == warp % 4
+    // warps w and w+4 share TMEM lane quadrant q = w % 4 (a warp may only touch lanes 32(w%4)..+31) and
+    // split the columns, so that two warps per scheduler hide each other's TMEM / MUFU / smem latency
+    const int q = warp & 3;
+    const int hsel = (warp - 4) >> 2;
     int acc = 0; uint32_t acc_phase = 0;
     if constexpr (Epi::kMode == EPI_DIRECT) {
       for (int it = item0; it < n_items; it += item_step) {
@@ -320,7 +330,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int row = m_blk * kBM + q * 32 + lane;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = hsel; c < BN / 32; c += 2) {
           float v[32];
           tmem_ld32(taddr + c * 32, v);
           epi.template apply<32>(row, n_blk * BN + c * 32, v);
@@ -329,27 +339,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_arrive(&tempty[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-    } else {
+    } else if constexpr (Epi::kMode == EPI_TMA_BF16) {
       constexpr int KI = Epi::kIn, KO = Epi::kOut;
-      constexpr int UW = (Epi::kMode == EPI_TMA_BF16) ? 64 : 32;        // unit width in columns
       uint8_t* slots = sEpi + q * (NSLOT * kSlotBytes);
       uint64_t* ib = &ibar[q];
       uint32_t iphase = 0;
       const uint32_t row_off = lane * 128, swz = (lane & 7) << 4;
+      const bool leader = hsel == 0 && lane == 0;          // issues the pair's TMA traffic
       auto tile_of = [&](int it, int& m_blk, int& n_blk, int& n_units) {
         const int t = it % (m_groups * wk.n_tiles);
         m_blk = (t / wk.n_tiles) * CL + crank; n_blk = t % wk.n_tiles;
         const int left = wk.n_cols - n_blk * BN;
-        n_units = left >= BN ? BN / UW : (left + UW - 1) / UW;
+        n_units = left >= BN ? BN / 64 : (left + 63) / 64;
       };
       auto issue_in = [&](int m_blk, int n_blk, int u) {      // one lane: operand boxes of a unit
         if constexpr (KI > 0) {
           mbar_expect_tx(ib, KI * kSlotBytes);
 #pragma unroll
-          for (int i = 0; i < KI; ++i) epi.load(i, slots + i * kSlotBytes, ib, n_blk * BN + u * UW, m_blk * kBM + q * 32);
+          for (int i = 0; i < KI; ++i) epi.load(i, slots + i * kSlotBytes, ib, n_blk * BN + u * 64, m_blk * kBM + q * 32);
         }
       };
-      if (KI > 0 && item0 < n_items && lane == 0) {
+      if (KI > 0 && item0 < n_items && leader) {
         int mb, nb, nu; tile_of(item0, mb, nb, nu);
         issue_in(mb, nb, 0);
       }
@@ -358,58 +368,43 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(&tfull[acc], acc_phase);
         fence_after_sync();
         const int row0 = m_blk * kBM + q * 32;
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + hsel * 32;
 #pragma unroll 1
         for (int u = 0; u < n_units; ++u) {
-          const int col0 = n_blk * BN + u * UW;
-          [[maybe_unused]] uint32_t in[KI > 0 ? KI : 1][32];
+          const int col0 = n_blk * BN + u * 64;
+          [[maybe_unused]] uint32_t in[KI > 0 ? KI : 1][16];
           if constexpr (KI > 0) {
             mbar_wait(ib, iphase); iphase ^= 1;
 #pragma unroll
             for (int i = 0; i < KI; ++i)
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const uint4 v = lds128(slots + i * kSlotBytes + row_off + ((j << 4) ^ swz));
+              for (int j = 0; j < 4; ++j) {
+                const uint4 v = lds128(slots + i * kSlotBytes + row_off + (((hsel * 4 + j) << 4) ^ swz));
                 in[i][4 * j] = v.x; in[i][4 * j + 1] = v.y; in[i][4 * j + 2] = v.z; in[i][4 * j + 3] = v.w;
               }
-            __syncwarp();
-            if (lane == 0) {                                  // refill the operand boxes for the next unit
+          }
+          float v[32];
+          tmem_ld32(taddr + u * 64, v);
+          if (u == n_units - 1) { fence_before_sync(); mbar_arrive(&tempty[acc]); }   // this warp's share is drained
+          uint32_t out[KO][16];
+          epi.compute(row0 + lane, col0 + hsel * 32, v, in, out);
+          if (leader) bulk_wait_read0();             // the previous unit's boxes were read out by the TMA
+          named_bar_sync(1 + q, 64);                 // ... and both warps hold this unit's operands in registers
+          if constexpr (KI > 0) {
+            if (leader) {                            // refill the operand boxes for the next unit
               if (u + 1 < n_units) issue_in(m_blk, n_blk, u + 1);
               else if (it + item_step < n_items) { int mb, nb, nu; tile_of(it + item_step, mb, nb, nu); issue_in(mb, nb, 0); }
             }
           }
-          if constexpr (Epi::kMode == EPI_TMA_BF16) {
 #pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-              float v[32];
-              tmem_ld32(taddr + u * UW + hf * 32, v);
-              if (hf == 1 && u == n_units - 1) { fence_before_sync(); mbar_arrive(&tempty[acc]); }   // accumulator drained
-              uint32_t out[KO][16];
-              if (hf == 0) epi.template compute<0>(row0 + lane, col0, v, in, out);
-              else epi.template compute<1>(row0 + lane, col0 + 32, v, in, out);
-              if (hf == 0) { if (lane == 0) bulk_wait_read0(); __syncwarp(); }   // previous unit's boxes were read out
+          for (int o = 0; o < KO; ++o)
 #pragma unroll
-              for (int o = 0; o < KO; ++o)
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  sts128(slots + (KI + o) * kSlotBytes + row_off + (((hf * 4 + j) << 4) ^ swz),
-                         out[o][4 * j], out[o][4 * j + 1], out[o][4 * j + 2], out[o][4 * j + 3]);
-            }
-          } else {
-            float v[32];
-            tmem_ld32(taddr + u * UW, v);
-            if (u == n_units - 1) { fence_before_sync(); mbar_arrive(&tempty[acc]); }
-            uint32_t out[32];
-            epi.compute(row0 + lane, col0, v, out);
-            if (lane == 0) bulk_wait_read0();
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              sts128(slots + KI * kSlotBytes + row_off + ((j << 4) ^ swz), out[4 * j], out[4 * j + 1], out[4 * j + 2], out[4 * j + 3]);
-          }
+            for (int j = 0; j < 4; ++j)
+              sts128(slots + (KI + o) * kSlotBytes + row_off + (((hsel * 4 + j) << 4) ^ swz),
+                     out[o][4 * j], out[o][4 * j + 1], out[o][4 * j + 2], out[o][4 * j + 3]);
           fence_async_smem();
-          __syncwarp();
-          if (lane == 0) {
+          named_bar_sync(1 + q, 64);                 // the unit's boxes are complete
+          if (leader) {
 #pragma unroll
             for (int o = 0; o < KO; ++o) epi.store(o, slots + (KI + o) * kSlotBytes, col0, row0);
             bulk_commit();
@@ -417,7 +412,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      if (lane == 0) bulk_wait0();               // all boxes written before the CTA may exit
+      if (leader) bulk_wait0();                   // all boxes written before the CTA may exit
+    } else {
+      // fp32 reduce-add units of 32 columns: the two warps of a quadrant alternate units, one box each
+      uint8_t* slot = sEpi + (q * NSLOT + hsel) * kSlotBytes;
+      const uint32_t row_off = lane * 128, swz = (lane & 7) << 4;
+      for (int it = item0; it < n_items; it += item_step) {
+        const int t = it % (m_groups * wk.n_tiles);
+        const int m_blk = (t / wk.n_tiles) * CL + crank, n_blk = t % wk.n_tiles;
+        const int left = wk.n_cols - n_blk * BN;
+        const int n_units = left >= BN ? BN / 32 : (left + 31) / 32;
+        mbar_wait(&tfull[acc], acc_phase);
+        fence_after_sync();
+        const int row0 = m_blk * kBM + q * 32;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+        int last = n_units - 1; if ((last & 1) != hsel) --last;      // this warp's last unit (may be < 0)
+        if (last < 0) { fence_before_sync(); mbar_arrive(&tempty[acc]); }
+#pragma unroll 1
+        for (int u = hsel; u < n_units; u += 2) {
+          const int col0 = n_blk * BN + u * 32;
+          float v[32];
+          tmem_ld32(taddr + u * 32, v);
+          if (u == last) { fence_before_sync(); mbar_arrive(&tempty[acc]); }
+          uint32_t out[32];
+          epi.compute(row0 + lane, col0, v, out);
+          if (lane == 0) bulk_wait_read0();
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            sts128(slot + row_off + ((j << 4) ^ swz), out[4 * j], out[4 * j + 1], out[4 * j + 2], out[4 * j + 3]);
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) { epi.store(0, slot, col0, row0); bulk_commit(); }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      if (lane == 0) bulk_wait0();
     }
   }
   fence_before_sync();
@@ -500,11 +530,15 @@ int launch_nt(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* B, lon
   wk.kb_total = (int)ceil_div_ll(P, kBK);
   wk.n_cols = No;
   const int tiles = wk.m_tiles * wk.n_tiles;
-  int splits = max(1, min(ceil_div(num_sms, tiles), ceil_div(wk.kb_total, 8)));
+  const bool clustered = wk.m_tiles % kClusterM == 0 && BN >= 64 * kClusterM;
+  // one work item per CTA (cluster): the split count is rounded DOWN so that tiles x splits never
+  // exceeds the resident grid — a second, nearly empty round would double the kernel's duration
+  const int slots_avail = clustered ? (num_sms / kClusterM) / (tiles / kClusterM) : num_sms / tiles;
+  int splits = max(1, min(slots_avail, ceil_div(wk.kb_total, 8)));
   wk.kb_per_split = ceil_div(wk.kb_total, splits);
   wk.splits = ceil_div(wk.kb_total, wk.kb_per_split);
   constexpr int smem = smem_bytes<BN, Epi>();
-  if (wk.m_tiles % kClusterM == 0 && BN >= 64 * kClusterM)
+  if (clustered)
     return launch_kernel<kClusterM>(gemm_tc_kernel<BN, STAGES, true, kClusterM, Epi>, smem, num_sms,
                                     (wk.m_tiles / kClusterM) * wk.n_tiles * wk.splits, ma, mb, wk, epi, s, "gemm_tc_kernel<nt,mc>");
   return launch_kernel<1>(gemm_tc_kernel<BN, STAGES, true, 1, Epi>, smem, num_sms, tiles * wk.splits, ma, mb, wk, epi, s,

@@ -165,7 +165,10 @@ __global__ void __launch_bounds__(256) heads_fwd_kernel(HeadPlan hp, const float
 //                        (A operand of the skinny second-layer weight gradients)
 // and accumulates the small bias gradients (second layers, sigma, grad_from_xyz) and the bias
 // gradient of the heads' first layer (column sums of GHD) through shared memory.
-template <typename T>
+// kLight (tcgen05 mode): only DPRE and the small bias gradients are produced here; GHD comes out of a
+// K = 64 GEMM (DPRE x W2p^T, masked by CD, column sums = first-layer bias gradients) and G7D is never
+// materialised (rank-4 addend of the feature-layer dgrad epilogue).
+template <typename T, bool kLight>
 __global__ void __launch_bounds__(256) heads_bwd_kernel(HeadPlan hp, const float* __restrict__ params,
                                                         const float* __restrict__ out, const float* __restrict__ g_out, int pitch,
                                                         const T* __restrict__ Hlast, long long ldh, int F,
@@ -268,6 +271,7 @@ __global__ void __launch_bounds__(256) heads_bwd_kernel(HeadPlan hp, const float
         Pack<T, 8>::store(DPRE + pq[q] * 64 + lane * 8, t);
       }
     }
+    if constexpr (kLight) continue;
     for (int i = lane * 8; i < F; i += 256) {
       float ws[8]; load8<float>(params + hp.wsig + i, ws);
       float g[kQP][8];
@@ -323,7 +327,8 @@ __global__ void __launch_bounds__(256) heads_bwd_kernel(HeadPlan hp, const float
     for (int o = 0; o < 20; ++o) atomicAdd(&s_red[HKa + o], bsum[o]);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < HKa; i += blockDim.x) atomicAdd(g_params + hp.b1_off[i / hp.HH] + (i % hp.HH), s_red[i]);
+  if constexpr (!kLight)
+    for (int i = threadIdx.x; i < HKa; i += blockDim.x) atomicAdd(g_params + hp.b1_off[i / hp.HH] + (i % hp.HH), s_red[i]);
   if (threadIdx.x < hp.n_out) atomicAdd(g_params + hp.o[threadIdx.x].b_off, s_red[HKa + threadIdx.x]);
   if (threadIdx.x == 16) atomicAdd(g_params + hp.bsig, s_red[HKa + 16]);
   if (threadIdx.x >= 17 && threadIdx.x < 20 && hp.ch_nlr >= 0) atomicAdd(g_params + hp.bg + (threadIdx.x - 17), s_red[HKa + threadIdx.x]);
@@ -342,6 +347,17 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   m[i] = mi; v[i] = vi;
   const float denom = sqrtf(vi) / bc2_sqrt + eps;
   p[i] = pi - (lr / bc1) * (mi / denom);
+}
+
+// W2p[b*HH + i][o] = W2_o[i] when output o hangs off block b, else 0  (o < 64; [n_blocks*HH, 64] bf16)
+__global__ void pack_w2_kernel(HeadPlan hp, const float* __restrict__ params, __nv_bfloat16* __restrict__ W2p) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int rows = hp.n_blocks * hp.HH;
+  if (idx >= rows * 64) return;
+  const int r = idx / 64, o = idx % 64;
+  float v = 0.f;
+  if (o < hp.n_out && hp.o[o].block == r / hp.HH) v = params[hp.o[o].w_off + (r % hp.HH)];
+  W2p[idx] = __float2bfloat16_rn(v);
 }
 
 static int build_plan(const bn_mlp* h, int flags, HeadPlan* hp, int* n_channels) {
@@ -476,9 +492,19 @@ static int backward_t(bn_mlp* h, const float* params, const float* out, const fl
   constexpr bool kTC = std::is_same<T, __nv_bfloat16>::value;   // bias grads fused into the tcgen05 dgrad epilogues
   {
     const size_t smem = (size_t)(HKa + 24) * sizeof(float);
-    heads_bwd_kernel<T><<<heads_grid(h, P), 256, smem, s>>>(hp, params, out, g_out, pitch, Hl, ldl, F, w.CD, w.ldhd,
-                                                           w.GHD, w.G7D, w.DPRE, g, P);
+    heads_bwd_kernel<T, kTC><<<heads_grid(h, P), 256, smem, s>>>(hp, params, out, g_out, pitch, Hl, ldl, F, w.CD, w.ldhd,
+                                                                w.GHD, w.G7D, w.DPRE, g, P);
     BN_LAUNCH_CHECK();
+  }
+  if constexpr (kTC) {
+    // GHD = (DPRE W2p^T) ⊙ CD, first-layer bias gradients = its column sums
+    pack_w2_kernel<<<ceil_div(HKa * 64, 256), 256, 0, s>>>(hp, params, (__nv_bfloat16*)h->W2p);
+    BN_LAUNCH_CHECK();
+    for (int b = 0; b < hp.n_blocks; ++b) {
+      DgradArgs<T> a; a.mulc = w.CD + (long long)b * h->HH; a.ldm = w.ldhd; a.bias_grad = g + hp.b1_off[b];
+      if (int rc = layer_dgrad<T>(h, w.DPRE, 64, (const T*)h->W2p + (long long)b * h->HH * 64, 64, P, h->HH, 64, a,
+                                  w.GHD + (long long)b * h->HH, w.ldhd, s)) return rc;
+    }
   }
   // second-layer weight gradients of the heads / sigma / learned-normal heads: dW2[o] = DPRE[:,o]^T X
   if constexpr (kTC) {
@@ -522,7 +548,12 @@ static int backward_t(bn_mlp* h, const float* params, const float* out, const fl
   // feature layer
   {
     if (int rc = layer_wgrad<T>(h, w.GFE, F, Hl, ldl, F, F, P, g + c.w_off[BN_LIN_FEATS], F, F, F, s)) return rc;
-    DgradArgs<T> a; a.addend = w.G7D; a.lda = F; a.mulc = w.C[L - 1]; a.ldm = F; a.bias_grad = g + c.b_off[L - 1];
+    DgradArgs<T> a; a.mulc = w.C[L - 1]; a.ldm = F; a.bias_grad = g + c.b_off[L - 1];
+    if constexpr (kTC) {          // direct grads into h_{L-1}: dsigma w_sigma + sum_k dv_k Wg_k, DPRE cols 16..19
+      a.rank_rows = w.DPRE + 16; a.rank_ld = 64; a.n_rank = hp.ch_nlr >= 0 ? 4 : 1;
+      a.rank_col[0] = params + hp.wsig;
+      for (int k = 0; k < 3; ++k) a.rank_col[1 + k] = hp.ch_nlr >= 0 ? params + hp.wg + (long long)k * F : nullptr;
+    } else { a.addend = w.G7D; a.lda = F; }
     if (normals) { a.add2 = w.U[L - 1]; a.ld2 = F; }
     if (int rc = layer_dgrad<T>(h, w.GFE, F, (const T*)h->WfT, F, P, F, F, a, w.GA, F, s)) return rc;
   }
@@ -594,6 +625,7 @@ extern "C" __attribute__((visibility("default"))) int bn_mlp_create(const bn_mlp
   BN_CUDA(cudaMalloc(&h->W1, HK * h->F * h->es));
   BN_CUDA(cudaMalloc(&h->W1T, HK * h->F * h->es));
   BN_CUDA(cudaMalloc(&h->b1cat, HK * sizeof(float)));
+  BN_CUDA(cudaMalloc(&h->W2p, HK * 64 * sizeof(__nv_bfloat16)));
   *out = h;
   return BN_OK;
 }
@@ -601,7 +633,7 @@ extern "C" __attribute__((visibility("default"))) int bn_mlp_create(const bn_mlp
 extern "C" __attribute__((visibility("default"))) void bn_mlp_destroy(bn_mlp* h) {
   if (!h) return;
   for (int l = 0; l < h->L; ++l) { cudaFree(h->Wp[l]); cudaFree(h->WTp[l]); }
-  cudaFree(h->Wf); cudaFree(h->WfT); cudaFree(h->W1); cudaFree(h->W1T); cudaFree(h->b1cat);
+  cudaFree(h->Wf); cudaFree(h->WfT); cudaFree(h->W1); cudaFree(h->W1T); cudaFree(h->b1cat); cudaFree(h->W2p);
   delete h;
 }
 
@@ -673,11 +705,17 @@ int bn_debug_gemm(int kind, int precision, const void* A, long long lda, const v
   BN_CHECK_ARG(A && B && out, "null pointer");
   int dev = 0; BN_CUDA(cudaGetDevice(&dev));
   if (int rc = bn_device_check(dev)) return rc;
-  bn_mlp h{}; cudaDeviceProp prop; BN_CUDA(cudaGetDeviceProperties(&prop, dev)); h.num_sms = prop.multiProcessorCount;
+  static int sms = 0;
+  if (!sms) BN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  bn_mlp h{}; h.num_sms = sms;
   if (kind == 0) {
     EpiStoreF32 epi{out, ldo, (int)M, N};
     if (precision == BN_PREC_BF16) return gemm_tn<__nv_bfloat16>(&h, (const __nv_bfloat16*)A, lda, (const __nv_bfloat16*)B, ldb, M, N, (int)K, epi, stream);
     return gemm_tn<float>(&h, (const float*)A, lda, (const float*)B, ldb, M, N, (int)K, epi, stream);
+  }
+  if (kind == 2) {        // mainloop only (bf16): accumulators are read back and dropped
+    EpiNull epi{out};
+    return gemm_tn<__nv_bfloat16>(&h, (const __nv_bfloat16*)A, lda, (const __nv_bfloat16*)B, ldb, M, N, (int)K, epi, stream);
   }
   EpiWgrad epi{out, ldo, (int)M, N, N, N};
   if (precision == BN_PREC_BF16) return gemm_nt<__nv_bfloat16>(&h, (const __nv_bfloat16*)A, lda, (const __nv_bfloat16*)B, ldb, (int)M, N, K, epi, stream);
@@ -691,7 +729,9 @@ int bn_debug_gemm_epi(int kind, const void* A, long long lda, const void* B, lon
   BN_CHECK_ARG(A && B && out, "null pointer");
   int dev = 0; BN_CUDA(cudaGetDevice(&dev));
   if (int rc = bn_device_check(dev)) return rc;
-  bn_mlp h{}; cudaDeviceProp prop; BN_CUDA(cudaGetDeviceProperties(&prop, dev)); h.num_sms = prop.multiProcessorCount;
+  static int sms = 0;
+  if (!sms) BN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  bn_mlp h{}; h.num_sms = sms;
   typedef __nv_bfloat16 T;
   if (kind == 0) {
     DgradArgs<T> a; a.addend = (const T*)add; a.lda = ldo; a.mulc = (const T*)mul; a.ldm = ldo; a.bias_grad = colsum;

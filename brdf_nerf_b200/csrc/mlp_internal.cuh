@@ -58,6 +58,7 @@ struct bn_mlp {
   void* Wp[16]; void* WTp[16]; int Kpad[16]; int Kreal[16];
   void* Wf; void* WfT;
   void* W1; void* W1T; float* b1cat;
+  void* W2p;                    // [n_blocks*HH, 64] bf16: second-layer head weights as the B operand of the GHD GEMM
   int n_blocks;
   int blk_lin0[bn::kMaxBlocks], blk_lin2[bn::kMaxBlocks], blk_head[bn::kMaxBlocks];
   bool synced;
@@ -289,11 +290,15 @@ template <typename T> struct DgradArgs {
   const T* add2 = nullptr; long long ld2 = 0;
   T* raw = nullptr; long long ldr = 0;
   float* bias_grad = nullptr;
+  // rank-<=4 addend sum_k rank_rows[row][k] * rank_col[k][col] (tcgen05 mode only)
+  const T* rank_rows = nullptr; long long rank_ld = 0; const float* rank_col[4] = {nullptr, nullptr, nullptr, nullptr}; int n_rank = 0;
 };
-template <bool kAdd, bool kMul, bool kAdd2, bool kRaw>
+template <bool kAdd, bool kMul, bool kAdd2, bool kRaw, bool kRank = false>
 static int dgrad_tc(const bn_mlp* h, const __nv_bfloat16* A, long long lda, const __nv_bfloat16* BT, long long ldb, long long P,
                     int N, int K, const DgradArgs<__nv_bfloat16>& a, __nv_bfloat16* out, long long ldo, cudaStream_t s) {
-  tc::EpiDgradT<kAdd, kMul, kAdd2, kRaw> e; e.colsum = a.bias_grad;
+  tc::EpiDgradT<kAdd, kMul, kAdd2, kRaw, kRank> e; e.colsum = a.bias_grad;
+  e.rank_rows = a.rank_rows; e.rank_ld = a.rank_ld; e.n_rank = a.n_rank; e.M = (int)P;
+  for (int k = 0; k < 4; ++k) e.rank_col[k] = a.rank_col[k];
   int i = 0;
   if (kAdd) { if (int rc = tc::stream_map(&e.in_map[i++], a.addend, P, N, a.lda)) return rc; }
   if (kMul) { if (int rc = tc::stream_map(&e.in_map[i++], a.mulc, P, N, a.ldm)) return rc; }
@@ -310,8 +315,10 @@ template <typename T>
 static int layer_dgrad(const bn_mlp* h, const T* A, long long lda, const T* BT, long long ldb, long long P, int N, int K,
                        const DgradArgs<T>& a, T* out, long long ldo, cudaStream_t s) {
   if constexpr (std::is_same<T, __nv_bfloat16>::value) {
-    const int code = (a.addend ? 1 : 0) | (a.mulc ? 2 : 0) | (a.add2 ? 4 : 0) | (a.raw ? 8 : 0);
+    const int code = (a.addend ? 1 : 0) | (a.mulc ? 2 : 0) | (a.add2 ? 4 : 0) | (a.raw ? 8 : 0) | (a.n_rank > 0 ? 16 : 0);
     switch (code) {
+      case 18: return dgrad_tc<false, true, false, false, true>(h, A, lda, BT, ldb, P, N, K, a, out, ldo, s);
+      case 22: return dgrad_tc<false, true, true, false, true>(h, A, lda, BT, ldb, P, N, K, a, out, ldo, s);
       case 0: return dgrad_tc<false, false, false, false>(h, A, lda, BT, ldb, P, N, K, a, out, ldo, s);
       case 1: return dgrad_tc<true, false, false, false>(h, A, lda, BT, ldb, P, N, K, a, out, ldo, s);
       case 2: return dgrad_tc<false, true, false, false>(h, A, lda, BT, ldb, P, N, K, a, out, ldo, s);
