@@ -1,10 +1,14 @@
 // tcgen05 / TMEM / TMA GEMM for sm_100a: bf16 operands, fp32 accumulation in tensor memory,
-// fused epilogue functors (epilogues.cuh).  Persistent, warp-specialised:
-//   warp 0   TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
-//   warp 1   MMA issuer     (one elected lane issues tcgen05.mma, tcgen05.commit frees ring slots)
-//   warp 2   TMEM allocator (2 accumulator stages x BN columns)
-//   warp 4-7 epilogue       (tcgen05.ld 32x32b -> registers -> fused math -> global), overlapped
-//                            with the next tile's mainloop through the second TMEM stage
+// fused epilogue functors (epilogues.cuh, epilogues_tc.cuh).  Persistent, warp-specialised:
+//   warp 0    TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
+//   warp 1    MMA issuer     (one elected lane issues tcgen05.mma, tcgen05.commit frees ring slots)
+//   warp 2    TMEM allocator (2 accumulator stages x BN columns)
+//   warp 4-11 epilogue       (tcgen05.ld 32x32b -> registers -> fused math -> smem boxes -> TMA),
+//                             overlapped with the next tile's mainloop through the second TMEM stage
+// kPair: two CTAs of a cluster (one TPC) run ONE 256 x BN tile with tcgen05.mma.cta_group::2: each CTA
+// stages its own 128 rows of A and only HALF of B, the leader CTA issues the MMAs for both, every CTA
+// drains its own 128 x BN accumulator.  Halving the B footprint is what pays for deep operand rings and
+// double-buffered epilogue boxes inside 227 KB.
 //
 //   kNT == false : C[m][n] = sum_k A[m][k] B[n][k]   A:[M,K] B:[N,K], both K-major   (fwd, dgrad)
 //   kNT == true  : C[m][n] = sum_p A[p][m] B[p][n]   A:[P,M] B:[P,N], both MN-major  (wgrad,
@@ -97,13 +101,48 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+template <bool kPair> __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
+  if constexpr (kPair) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
 }
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+template <bool kPair> __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  if constexpr (kPair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
+// shared::cluster address of `local` (an address inside this CTA's shared window) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// pair load: lands in THIS CTA's smem, signals the mbarrier at shared::cluster address `bar_cluster`
+// (the leader CTA's "full" barrier collects the bytes of both CTAs)
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// commit of cta_group::2 MMAs: arrives on the barrier at the same offset in both CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -147,14 +186,14 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= (uint64_t)2 << 61;     // SWIZZLE_128B
   return d;
 }
-// instruction descriptor: D=f32, A=B=bf16, M=128, N=BN, majorness per operand
-__host__ __device__ constexpr uint32_t make_idesc(int n, bool mn_major) {
+// instruction descriptor: D=f32, A=B=bf16, M = 128 (one CTA) or 256 (CTA pair), N=BN, majorness per operand
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n, bool mn_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((mn_major ? 1u : 0u) << 15) | ((mn_major ? 1u : 0u) << 16) |
-         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 struct Work {
-  int m_tiles, n_tiles, splits;   // splits only for kNT
+  int m_tiles, n_tiles, splits;   // 128-row tiles, BN-column tiles; splits only for kNT
   int kb_total, kb_per_split;     // k-blocks (of kBK) in the reduction dimension
   int n_cols;                     // real number of output columns (a multiple of the epilogue unit)
 };
@@ -162,10 +201,12 @@ struct Work {
 // Epilogue kinds.  An epilogue functor `Epi` declares `static constexpr int kMode`:
 //   EPI_DIRECT      : apply<32>(row, col0, acc[32]) writes global memory itself (debug / skinny paths)
 //   EPI_TMA_BF16    : the tile leaves (and its element-wise operands enter) through shared memory and
-//                     the TMA in units of 32 rows x 64 bf16 columns = one 128B-swizzled 4 KB box per
-//                     epilogue warp; kIn input streams, kOut output streams.  A thread owns one row of
-//                     the unit, so its 16-byte chunks land conflict-free in the swizzled box and every
-//                     global access is a full-line TMA transaction instead of 32 scattered sectors.
+//                     the TMA in units of 32 rows x 64 bf16 columns = one 128B-swizzled 4 KB box per TMEM
+//                     quadrant; kIn input streams, kOut output streams.  A thread owns one row of the unit,
+//                     so its 16-byte chunks land conflict-free in the swizzled box and every global access
+//                     is a full-line TMA transaction instead of 32 scattered sectors.  Boxes are double
+//                     buffered (operands prefetched two units ahead, stores drained one unit behind)
+//                     whenever kIn + kOut <= 3.
 //   EPI_TMA_RED_F32 : units of 32 rows x 32 fp32 columns leave through cp.reduce.async.bulk (add).
 // TMA functors provide
 //   compute(row, col0, acc[32], in[kIn][16], out[kOut][16])   (EPI_TMA_BF16: the two warps of a quadrant
@@ -175,33 +216,35 @@ struct Work {
 enum { EPI_DIRECT = 0, EPI_TMA_BF16 = 1, EPI_TMA_RED_F32 = 2 };
 
 constexpr int kSlotBytes = 4096;   // 32 rows x 128 bytes
+template <class Epi> __host__ __device__ constexpr int epi_nbuf() {
+  return Epi::kMode == EPI_TMA_RED_F32 ? 2 : (Epi::kIn + Epi::kOut <= 3 ? 2 : 1);
+}
 template <class Epi> __host__ __device__ constexpr int epi_slots() {        // 4 KB boxes per TMEM quadrant (= per pair of epilogue warps)
-  return Epi::kMode == EPI_DIRECT ? 0 : (Epi::kMode == EPI_TMA_RED_F32 ? 2 : Epi::kIn + Epi::kOut);
+  return Epi::kMode == EPI_DIRECT ? 0 : (Epi::kMode == EPI_TMA_RED_F32 ? 2 * epi_nbuf<Epi>() : (Epi::kIn + Epi::kOut) * epi_nbuf<Epi>());
 }
 template <class Epi> __host__ __device__ constexpr int epi_smem() { return 4 * epi_slots<Epi>() * kSlotBytes; }
 
 constexpr int kMaxSmem = 232448;   // 227 KB opt-in limit per CTA
-template <int BN, class Epi> __host__ __device__ constexpr int pick_stages() {
-  constexpr int stage = kBM * kBK * 2 + BN * kBK * 2;
+template <int BN, bool kPair> __host__ __device__ constexpr int stage_bytes() { return kBM * kBK * 2 + (kPair ? BN / 2 : BN) * kBK * 2; }
+template <int BN, bool kPair, class Epi> __host__ __device__ constexpr int pick_stages() {
   constexpr int avail = kMaxSmem - 1024 - 512 - epi_smem<Epi>();
-  return avail / stage > 6 ? 6 : avail / stage;
+  return avail / stage_bytes<BN, kPair>() > 8 ? 8 : avail / stage_bytes<BN, kPair>();
 }
-template <int BN, class Epi> __host__ __device__ constexpr int smem_bytes() {
-  return pick_stages<BN, Epi>() * (kBM * kBK * 2 + BN * kBK * 2) + epi_smem<Epi>() + 512 + 1024;
+template <int BN, bool kPair, class Epi> __host__ __device__ constexpr int smem_bytes() {
+  return pick_stages<BN, kPair, Epi>() * stage_bytes<BN, kPair>() + epi_smem<Epi>() + 512 + 1024;
 }
 
-// CL = CTAs per cluster along the output-row (M) dimension.  The CL CTAs of a cluster work on CL
-// consecutive row tiles of the SAME column tile / reduction range and share the B operand: each CTA
-// fetches 1/CL of every B stage and multicasts it to all of them, which divides the L2->SMEM traffic
-// of B (the dominant stream: the whole weight matrix per 128 points) by CL.
-template <int BN, int STAGES, bool kNT, int CL, class Epi>
+template <int BN, int STAGES, bool kNT, bool kPair, class Epi>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Work wk,
                const __grid_constant__ Epi epi) {
+  constexpr int CL = kPair ? 2 : 1;
+  constexpr int BNL = kPair ? BN / 2 : BN;                     // B rows (output columns) staged by this CTA
   constexpr uint32_t A_BYTES = kBM * kBK * 2;
-  constexpr uint32_t B_BYTES = BN * kBK * 2;
+  constexpr uint32_t B_BYTES = BNL * kBK * 2;
   constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
   constexpr int NSLOT = epi_slots<Epi>();
+  constexpr int NBUF = epi_nbuf<Epi>();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -211,66 +254,73 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
-  uint64_t* ibar = tempty + 2;                                 // one per epilogue warp: operand boxes landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ibar + 4);
+  uint64_t* ibar = tempty + 2;                                 // [quadrant][buffer]: operand boxes landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ibar + 8);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int m_groups = (wk.m_tiles + CL - 1) / CL;                 // row tiles are handed out CL at a time
   const int n_items = m_groups * wk.n_tiles * wk.splits;
-  const int crank = (CL > 1) ? (int)cluster_ctarank() : 0;
-  const int item0 = (CL > 1) ? (int)cluster_id_x() : (int)blockIdx.x;
-  const int item_step = (CL > 1) ? (int)cluster_nctaid_x() : (int)gridDim.x;
-  constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1);
+  const int crank = kPair ? (int)cluster_ctarank() : 0;
+  const int item0 = kPair ? (int)cluster_id_x() : (int)blockIdx.x;
+  const int item_step = kPair ? (int)cluster_nctaid_x() : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 256); }
-    for (int s = 0; s < 4; ++s) mbar_init(&ibar[s], 1);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    // tempty: one arrival per epilogue warp; in a pair the leader's barrier collects both CTAs' warps
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8 * CL); }
+    for (int s = 0; s < 8; ++s) mbar_init(&ibar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 2) tmem_alloc<kPair>(tmem_slot, TMEM_COLS);
   fence_before_sync();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();          // peers' barriers are initialised before anyone signals them
+  if (kPair) cluster_sync_all();           // the peer's barriers are initialised before anyone signals them
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (every CTA stages its own A rows and its share of B) =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int it = item0; it < n_items; it += item_step) {
         const int split = it / (m_groups * wk.n_tiles);
         const int t = it % (m_groups * wk.n_tiles);
         const int m_blk = (t / wk.n_tiles) * CL + crank, n_blk = t % wk.n_tiles;
+        const int ncol0 = n_blk * BN + crank * BNL;              // first B row / output column staged by this CTA
         const int kb0 = split * wk.kb_per_split;
         const int kb1 = min(wk.kb_total, kb0 + wk.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);          // every CTA of the cluster has drained this slot
-          mbar_expect_tx(&full[stage], A_BYTES + B_BYTES);
+          mbar_wait(&empty[stage], phase ^ 1);          // the MMAs that read this slot have retired
           uint8_t* a = sA + stage * A_BYTES;
           uint8_t* b = sB + stage * B_BYTES;
-          if (!kNT) {
-            tma_load_2d(a, &tmA, &full[stage], kb * kBK, m_blk * kBM);
-            if (CL == 1) tma_load_2d(b, &tmB, &full[stage], kb * kBK, n_blk * BN);
-            else tma_load_2d_mc(b + crank * (B_BYTES / CL), &tmB, &full[stage], kb * kBK, n_blk * BN + crank * (BN / CL), kMask);
-          } else {
-            // boxes of 64 (contiguous MN) x 64 (reduction rows); one box per 64 output rows/cols
-#pragma unroll
-            for (int c = 0; c < kBM / 64; ++c) tma_load_2d(a + c * 8192, &tmA, &full[stage], m_blk * kBM + c * 64, kb * kBK);
-            if (CL == 1) {
-#pragma unroll
-              for (int c = 0; c < BN / 64; ++c) tma_load_2d(b + c * 8192, &tmB, &full[stage], n_blk * BN + c * 64, kb * kBK);
+          if constexpr (kPair) {
+            // the leader's barrier expects the bytes of both CTAs; the peer only issues its loads
+            if (crank == 0) mbar_expect_tx(&full[stage], 2 * (A_BYTES + B_BYTES));
+            const uint32_t bar = mapa_u32(smem_u32(&full[stage]), 0);
+            if (!kNT) {
+              tma_load_2d_pair(a, &tmA, bar, kb * kBK, m_blk * kBM);
+              tma_load_2d_pair(b, &tmB, bar, kb * kBK, ncol0);
             } else {
 #pragma unroll
-              for (int c = 0; c < BN / 64 / CL; ++c) {
-                const int cc = crank * (BN / 64 / CL) + c;
-                tma_load_2d_mc(b + cc * 8192, &tmB, &full[stage], n_blk * BN + cc * 64, kb * kBK, kMask);
-              }
+              for (int c = 0; c < kBM / 64; ++c) tma_load_2d_pair(a + c * 8192, &tmA, bar, m_blk * kBM + c * 64, kb * kBK);
+#pragma unroll
+              for (int c = 0; c < BNL / 64; ++c) tma_load_2d_pair(b + c * 8192, &tmB, bar, ncol0 + c * 64, kb * kBK);
+            }
+          } else {
+            mbar_expect_tx(&full[stage], A_BYTES + B_BYTES);
+            if (!kNT) {
+              tma_load_2d(a, &tmA, &full[stage], kb * kBK, m_blk * kBM);
+              tma_load_2d(b, &tmB, &full[stage], kb * kBK, ncol0);
+            } else {
+              // boxes of 64 (contiguous MN) x 64 (reduction rows); one box per 64 output rows/cols
+#pragma unroll
+              for (int c = 0; c < kBM / 64; ++c) tma_load_2d(a + c * 8192, &tmA, &full[stage], m_blk * kBM + c * 64, kb * kBK);
+#pragma unroll
+              for (int c = 0; c < BNL / 64; ++c) tma_load_2d(b + c * 8192, &tmB, &full[stage], ncol0 + c * 64, kb * kBK);
             }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -278,9 +328,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BN, kNT);
+    // ===================== MMA issuer (leader CTA of a pair only) =====================
+    if (lane == 0 && crank == 0) {
+      constexpr uint32_t idesc = make_idesc(kPair ? 256 : 128, BN, kNT);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int it = item0; it < n_items; it += item_step) {
@@ -305,12 +355,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               da = make_desc(a_addr + k * 2048, 8192, 1024);
               db = make_desc(b_addr + k * 2048, 8192, 1024);
             }
-            umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if constexpr (kPair) umma_bf16_pair(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          if (CL == 1) umma_commit(&empty[stage]); else umma_commit_mc(&empty[stage], kMask);
+          if constexpr (kPair) umma_commit_pair(&empty[stage]); else umma_commit(&empty[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull[acc]);
+        if constexpr (kPair) umma_commit_pair(&tfull[acc]); else umma_commit(&tfull[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -321,6 +372,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int q = warp & 3;
     const int hsel = (warp - 4) >> 2;
     int acc = 0; uint32_t acc_phase = 0;
+    // this warp's share of the accumulator is in registers: hand the TMEM stage back to the MMA issuer
+    auto release_acc = [&](int a) {
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (kPair) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[a]), 0));
+        else mbar_arrive(&tempty[a]);
+      }
+    };
     if constexpr (Epi::kMode == EPI_DIRECT) {
       for (int it = item0; it < n_items; it += item_step) {
         const int t = it % (m_groups * wk.n_tiles);
@@ -335,34 +395,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tmem_ld32(taddr + c * 32, v);
           epi.template apply<32>(row, n_blk * BN + c * 32, v);
         }
-        fence_before_sync();
-        mbar_arrive(&tempty[acc]);
+        release_acc(acc);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     } else if constexpr (Epi::kMode == EPI_TMA_BF16) {
       constexpr int KI = Epi::kIn, KO = Epi::kOut;
-      uint8_t* slots = sEpi + q * (NSLOT * kSlotBytes);
-      uint64_t* ib = &ibar[q];
-      uint32_t iphase = 0;
+      uint8_t* slots = sEpi + q * (NSLOT * kSlotBytes);        // [in stream][buf] then [out stream][buf]
+      uint64_t* ib = &ibar[q * 2];
       const uint32_t row_off = lane * 128, swz = (lane & 7) << 4;
-      const bool leader = hsel == 0 && lane == 0;          // issues the pair's TMA traffic
+      const bool leader = hsel == 0 && lane == 0;          // issues the quadrant's TMA traffic
       auto tile_of = [&](int it, int& m_blk, int& n_blk, int& n_units) {
         const int t = it % (m_groups * wk.n_tiles);
         m_blk = (t / wk.n_tiles) * CL + crank; n_blk = t % wk.n_tiles;
         const int left = wk.n_cols - n_blk * BN;
         n_units = left >= BN ? BN / 64 : (left + 63) / 64;
       };
-      auto issue_in = [&](int m_blk, int n_blk, int u) {      // one lane: operand boxes of a unit
+      // operand prefetch cursor (leader lane only): runs NBUF units ahead of the unit being computed
+      int pf_it = item0, pf_u = 0;
+      auto prefetch = [&](int buf) {
         if constexpr (KI > 0) {
-          mbar_expect_tx(ib, KI * kSlotBytes);
+          if (pf_it >= n_items) return;
+          int mb, nb, nu; tile_of(pf_it, mb, nb, nu);
+          mbar_expect_tx(&ib[buf], KI * kSlotBytes);
 #pragma unroll
-          for (int i = 0; i < KI; ++i) epi.load(i, slots + i * kSlotBytes, ib, n_blk * BN + u * 64, m_blk * kBM + q * 32);
+          for (int i = 0; i < KI; ++i)
+            epi.load(i, slots + (i * NBUF + buf) * kSlotBytes, &ib[buf], nb * BN + pf_u * 64, mb * kBM + q * 32);
+          if (++pf_u >= nu) { pf_u = 0; pf_it += item_step; }
         }
       };
-      if (KI > 0 && item0 < n_items && leader) {
-        int mb, nb, nu; tile_of(item0, mb, nb, nu);
-        issue_in(mb, nb, 0);
-      }
+      if (leader) { for (int b = 0; b < NBUF; ++b) prefetch(b); }
+      uint32_t g = 0;                                      // units processed so far by this quadrant
       for (int it = item0; it < n_items; it += item_step) {
         int m_blk, n_blk, n_units; tile_of(it, m_blk, n_blk, n_units);
         mbar_wait(&tfull[acc], acc_phase);
@@ -370,43 +432,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int row0 = m_blk * kBM + q * 32;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + hsel * 32;
 #pragma unroll 1
-        for (int u = 0; u < n_units; ++u) {
+        for (int u = 0; u < n_units; ++u, ++g) {
           const int col0 = n_blk * BN + u * 64;
+          const int buf = (NBUF == 2) ? (int)(g & 1) : 0;
           [[maybe_unused]] uint32_t in[KI > 0 ? KI : 1][16];
           if constexpr (KI > 0) {
-            mbar_wait(ib, iphase); iphase ^= 1;
+            mbar_wait(&ib[buf], (g / NBUF) & 1);
 #pragma unroll
             for (int i = 0; i < KI; ++i)
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const uint4 v = lds128(slots + i * kSlotBytes + row_off + (((hsel * 4 + j) << 4) ^ swz));
+                const uint4 v = lds128(slots + (i * NBUF + buf) * kSlotBytes + row_off + (((hsel * 4 + j) << 4) ^ swz));
                 in[i][4 * j] = v.x; in[i][4 * j + 1] = v.y; in[i][4 * j + 2] = v.z; in[i][4 * j + 3] = v.w;
               }
           }
           float v[32];
           tmem_ld32(taddr + u * 64, v);
-          if (u == n_units - 1) { fence_before_sync(); mbar_arrive(&tempty[acc]); }   // this warp's share is drained
+          if (u == n_units - 1) release_acc(acc);
           uint32_t out[KO][16];
           epi.compute(row0 + lane, col0 + hsel * 32, v, in, out);
-          if (leader) bulk_wait_read0();             // the previous unit's boxes were read out by the TMA
+          // the boxes this unit writes were last used NBUF units ago: their TMA stores have read them out
+          if (leader) { if (NBUF == 2) bulk_wait_read1(); else bulk_wait_read0(); }
           named_bar_sync(1 + q, 64);                 // ... and both warps hold this unit's operands in registers
-          if constexpr (KI > 0) {
-            if (leader) {                            // refill the operand boxes for the next unit
-              if (u + 1 < n_units) issue_in(m_blk, n_blk, u + 1);
-              else if (it + item_step < n_items) { int mb, nb, nu; tile_of(it + item_step, mb, nb, nu); issue_in(mb, nb, 0); }
-            }
-          }
+          if (leader) prefetch(buf);                 // refill the operand boxes just consumed
 #pragma unroll
           for (int o = 0; o < KO; ++o)
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              sts128(slots + (KI + o) * kSlotBytes + row_off + (((hsel * 4 + j) << 4) ^ swz),
+              sts128(slots + ((KI + o) * NBUF + buf) * kSlotBytes + row_off + (((hsel * 4 + j) << 4) ^ swz),
                      out[o][4 * j], out[o][4 * j + 1], out[o][4 * j + 2], out[o][4 * j + 3]);
           fence_async_smem();
           named_bar_sync(1 + q, 64);                 // the unit's boxes are complete
           if (leader) {
 #pragma unroll
-            for (int o = 0; o < KO; ++o) epi.store(o, slots + (KI + o) * kSlotBytes, col0, row0);
+            for (int o = 0; o < KO; ++o) epi.store(o, slots + ((KI + o) * NBUF + buf) * kSlotBytes, col0, row0);
             bulk_commit();
           }
         }
@@ -414,9 +473,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       if (leader) bulk_wait0();                   // all boxes written before the CTA may exit
     } else {
-      // fp32 reduce-add units of 32 columns: the two warps of a quadrant alternate units, one box each
-      uint8_t* slot = sEpi + (q * NSLOT + hsel) * kSlotBytes;
+      // fp32 reduce-add units of 32 columns: the two warps of a quadrant alternate units, two boxes each
+      uint8_t* slot = sEpi + (q * NSLOT + hsel * 2) * kSlotBytes;
       const uint32_t row_off = lane * 128, swz = (lane & 7) << 4;
+      uint32_t g = 0;
       for (int it = item0; it < n_items; it += item_step) {
         const int t = it % (m_groups * wk.n_tiles);
         const int m_blk = (t / wk.n_tiles) * CL + crank, n_blk = t % wk.n_tiles;
@@ -427,23 +487,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int row0 = m_blk * kBM + q * 32;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
         int last = n_units - 1; if ((last & 1) != hsel) --last;      // this warp's last unit (may be < 0)
-        if (last < 0) { fence_before_sync(); mbar_arrive(&tempty[acc]); }
+        if (last < 0) release_acc(acc);
 #pragma unroll 1
-        for (int u = hsel; u < n_units; u += 2) {
+        for (int u = hsel; u < n_units; u += 2, ++g) {
           const int col0 = n_blk * BN + u * 32;
+          uint8_t* sl = slot + (g & 1) * kSlotBytes;
           float v[32];
           tmem_ld32(taddr + u * 32, v);
-          if (u == last) { fence_before_sync(); mbar_arrive(&tempty[acc]); }
+          if (u == last) release_acc(acc);
           uint32_t out[32];
           epi.compute(row0 + lane, col0, v, out);
-          if (lane == 0) bulk_wait_read0();
+          if (lane == 0) bulk_wait_read1();
           __syncwarp();
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            sts128(slot + row_off + ((j << 4) ^ swz), out[4 * j], out[4 * j + 1], out[4 * j + 2], out[4 * j + 3]);
+            sts128(sl + row_off + ((j << 4) ^ swz), out[4 * j], out[4 * j + 1], out[4 * j + 2], out[4 * j + 3]);
           fence_async_smem();
           __syncwarp();
-          if (lane == 0) { epi.store(0, slot, col0, row0); bulk_commit(); }
+          if (lane == 0) { epi.store(0, sl, col0, row0); bulk_commit(); }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
@@ -452,8 +513,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   fence_before_sync();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();          // no CTA leaves while a peer can still write into its smem
-  if (warp == 2) { fence_after_sync(); tmem_dealloc(tmem_base, TMEM_COLS); }
+  if (kPair) cluster_sync_all();           // no CTA leaves while the peer can still signal / read its smem
+  if (warp == 2) { fence_after_sync(); tmem_dealloc<kPair>(tmem_base, TMEM_COLS); }
 }
 
 // ---- host side: tensor maps ------------------------------------------------------------------
@@ -473,9 +534,7 @@ inline bool tma_ok(const void* base, long long ld, int es) {
   return (reinterpret_cast<uintptr_t>(base) & 15) == 0 && ((ld * es) & 15) == 0;
 }
 
-constexpr int kClusterM = 2;       // CTAs per cluster sharing (multicasting) the B operand
-
-// persistent launch: one CTA per SM (rounded down to whole clusters), cluster dims (CL,1,1)
+// persistent launch: one CTA per SM (rounded down to whole pairs), cluster dims (CL,1,1)
 template <int CL, class Kern, class Epi>
 int launch_kernel(Kern kern, int smem, int num_sms, int items, const CUtensorMap& ma, const CUtensorMap& mb, const Work& wk,
                   const Epi& epi, cudaStream_t s, const char* name) {
@@ -498,29 +557,31 @@ int launch_kernel(Kern kern, int smem, int num_sms, int items, const CUtensorMap
 template <int BN, class Epi>
 int launch_tn(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* B, long long ldb,
               long long M, int N, int K, const Epi& epi, int num_sms, cudaStream_t s) {
-  constexpr int STAGES = pick_stages<BN, Epi>();
-  static_assert(STAGES >= 2, "epilogue staging leaves no room for the operand ring");
   if (K % kBK) { set_error("tc::launch_tn: K=%d not a multiple of 64", K); return BN_ERR_ARG; }
   if (Epi::kMode != EPI_DIRECT && N % 64) { set_error("tc::launch_tn: N=%d not a multiple of 64", N); return BN_ERR_ARG; }
   CUtensorMap ma, mb;
   Work wk{(int)ceil_div_ll(M, kBM), ceil_div(N, BN), 1, K / kBK, K / kBK, N};
-  const bool clustered = wk.m_tiles >= 2 * kClusterM && BN >= 64 * kClusterM;
   if (int rc = make_map_bf16(&ma, A, M, K, lda, kBK, kBM)) return rc;
-  // clustered: every CTA fetches (and multicasts) BN / kClusterM rows of the B tile per stage
-  if (int rc = make_map_bf16(&mb, B, N, K, ldb, kBK, clustered ? BN / kClusterM : BN)) return rc;
-  constexpr int smem = smem_bytes<BN, Epi>();
-  if (clustered)
-    return launch_kernel<kClusterM>(gemm_tc_kernel<BN, STAGES, false, kClusterM, Epi>, smem, num_sms,
-                                    ceil_div(wk.m_tiles, kClusterM) * wk.n_tiles, ma, mb, wk, epi, s, "gemm_tc_kernel<tn,mc>");
-  return launch_kernel<1>(gemm_tc_kernel<BN, STAGES, false, 1, Epi>, smem, num_sms, wk.m_tiles * wk.n_tiles, ma, mb, wk, epi, s,
-                          "gemm_tc_kernel<tn>");
+  if constexpr (BN >= 128) {
+    if (wk.m_tiles >= 4) {               // CTA pairs: every CTA stages BN/2 rows of the B tile
+      constexpr int STAGES = pick_stages<BN, true, Epi>();
+      static_assert(STAGES >= 2, "epilogue staging leaves no room for the operand ring");
+      if (int rc = make_map_bf16(&mb, B, N, K, ldb, kBK, BN / 2)) return rc;
+      return launch_kernel<2>(gemm_tc_kernel<BN, STAGES, false, true, Epi>, smem_bytes<BN, true, Epi>(), num_sms,
+                              ceil_div(wk.m_tiles, 2) * wk.n_tiles, ma, mb, wk, epi, s, "gemm_tc_kernel<tn,pair>");
+    }
+  }
+  constexpr int STAGES = pick_stages<BN, false, Epi>();
+  static_assert(STAGES >= 2, "epilogue staging leaves no room for the operand ring");
+  if (int rc = make_map_bf16(&mb, B, N, K, ldb, kBK, BN)) return rc;
+  return launch_kernel<1>(gemm_tc_kernel<BN, STAGES, false, false, Epi>, smem_bytes<BN, false, Epi>(), num_sms,
+                          wk.m_tiles * wk.n_tiles, ma, mb, wk, epi, s, "gemm_tc_kernel<tn>");
 }
 
 // A:[P,Mo] (ld lda), B:[P,No]: C[Mo,No] = A^T B through `epi` (atomic accumulate), split over P
 template <int BN, class Epi>
 int launch_nt(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* B, long long ldb,
               int Mo, int No, long long P, const Epi& epi, int num_sms, cudaStream_t s) {
-  constexpr int STAGES = pick_stages<BN, Epi>();
   if (Mo % 64) { set_error("tc::launch_nt: Mo=%d not a multiple of 64", Mo); return BN_ERR_ARG; }
   CUtensorMap ma, mb;
   if (int rc = make_map_bf16(&ma, A, P, Mo, lda, 64, kBK)) return rc;
@@ -530,19 +591,20 @@ int launch_nt(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* B, lon
   wk.kb_total = (int)ceil_div_ll(P, kBK);
   wk.n_cols = No;
   const int tiles = wk.m_tiles * wk.n_tiles;
-  const bool clustered = wk.m_tiles % kClusterM == 0 && BN >= 64 * kClusterM;
-  // one work item per CTA (cluster): the split count is rounded DOWN so that tiles x splits never
+  const bool pair = BN >= 128 && wk.m_tiles % 2 == 0;
+  // one work item per CTA (pair): the split count is rounded DOWN so that tiles x splits never
   // exceeds the resident grid — a second, nearly empty round would double the kernel's duration
-  const int slots_avail = clustered ? (num_sms / kClusterM) / (tiles / kClusterM) : num_sms / tiles;
+  const int slots_avail = pair ? (num_sms / 2) / (tiles / 2) : num_sms / tiles;
   int splits = max(1, min(slots_avail, ceil_div(wk.kb_total, 8)));
   wk.kb_per_split = ceil_div(wk.kb_total, splits);
   wk.splits = ceil_div(wk.kb_total, wk.kb_per_split);
-  constexpr int smem = smem_bytes<BN, Epi>();
-  if (clustered)
-    return launch_kernel<kClusterM>(gemm_tc_kernel<BN, STAGES, true, kClusterM, Epi>, smem, num_sms,
-                                    (wk.m_tiles / kClusterM) * wk.n_tiles * wk.splits, ma, mb, wk, epi, s, "gemm_tc_kernel<nt,mc>");
-  return launch_kernel<1>(gemm_tc_kernel<BN, STAGES, true, 1, Epi>, smem, num_sms, tiles * wk.splits, ma, mb, wk, epi, s,
-                          "gemm_tc_kernel<nt>");
+  if constexpr (BN >= 128) {
+    if (pair)
+      return launch_kernel<2>(gemm_tc_kernel<BN, pick_stages<BN, true, Epi>(), true, true, Epi>, smem_bytes<BN, true, Epi>(), num_sms,
+                              (wk.m_tiles / 2) * wk.n_tiles * wk.splits, ma, mb, wk, epi, s, "gemm_tc_kernel<nt,pair>");
+  }
+  return launch_kernel<1>(gemm_tc_kernel<BN, pick_stages<BN, false, Epi>(), true, false, Epi>, smem_bytes<BN, false, Epi>(), num_sms,
+                          tiles * wk.splits, ma, mb, wk, epi, s, "gemm_tc_kernel<nt>");
 }
 
 }  // namespace tc
