@@ -180,10 +180,13 @@ struct EpiSecondT {
 // Columns of the packed operand in [pad_lo, split) are K-padding and are clipped by map_lo's extent;
 // columns >= split land at dW[row][col - (split - pad_lo)] through map_hi — this maps the padded
 // [enc(60)|pad(4)|h(512)] layout back to the reference's Linear(572, 512) weight.
+template <bool kWithBias>
 struct EpiWgradT {
   static constexpr int kMode = EPI_TMA_RED_F32, kIn = 0, kOut = 1;
+  static constexpr bool kBias = kWithBias;   // bias gradient sum_p G[p][row] from an extra N=16 MMA against ones
   CUtensorMap map_lo, map_hi;
   int split;                              // first packed column served by map_hi
+  float* bias; int M;                     // nullable: bias[row] += sum_p G[p][row], row < M
   __device__ __forceinline__ void compute(int, int, const float (&acc)[32], uint32_t (&out)[32]) const {
 #pragma unroll
     for (int j = 0; j < 32; ++j) out[j] = __float_as_uint(acc[j]);
@@ -196,8 +199,8 @@ struct EpiWgradT {
 };
 
 // dW [M rows, Kreal cols, pitch ld] from a packed operand of N columns with padding [pad_lo, pad_hi)
-inline int make_wgrad(EpiWgradT* e, float* dW, long long ld, int M, int N, int pad_lo, int pad_hi) {
-  e->split = pad_hi;
+template <bool kB> inline int make_wgrad(EpiWgradT<kB>* e, float* dW, long long ld, int M, int N, int pad_lo, int pad_hi, float* bias) {
+  e->split = pad_hi; e->bias = bias; e->M = M;
   if (int rc = make_map_f32(&e->map_lo, dW, M, pad_lo, ld, 32, 32)) return rc;
   if (N > pad_hi) return make_map_f32(&e->map_hi, dW + pad_lo, M, N - pad_hi, ld, 32, 32);
   e->map_hi = e->map_lo;

@@ -120,8 +120,10 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
   return r;
 }
+// default semantics (release at CTA scope): the only state handed over is the TMEM stage, ordered by
+// tcgen05.fence::before_thread_sync; an explicit .release.cluster costs a MEMBAR.ALL + ERRBAR per arrive
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // pair load: lands in THIS CTA's smem, signals the mbarrier at shared::cluster address `bar_cluster`
 // (the leader CTA's "full" barrier collects the bytes of both CTAs)
@@ -216,13 +218,23 @@ struct Work {
 enum { EPI_DIRECT = 0, EPI_TMA_BF16 = 1, EPI_TMA_RED_F32 = 2 };
 
 constexpr int kSlotBytes = 4096;   // 32 rows x 128 bytes
+// NT functors with `kBias`: the kernel also accumulates sum_p A[p][m] (the bias gradient that belongs to
+// the weight gradient A^T B) with one extra N=16 MMA per K step against a tile of ones, on the CTAs of the
+// first column tile; epi.bias (nullable, fp32 [M]) receives it through red.global.
+template <class Epi, class = void> struct epi_has_bias { static constexpr bool value = false; };
+template <class Epi> struct epi_has_bias<Epi, decltype((void)Epi::kBias)> { static constexpr bool value = Epi::kBias; };
+constexpr int kOnesBytes = 8192;   // [64 K rows x 64 MN] bf16 ones, the B operand of the bias MMA
 template <class Epi> __host__ __device__ constexpr int epi_nbuf() {
-  return Epi::kMode == EPI_TMA_RED_F32 ? 2 : (Epi::kIn + Epi::kOut <= 3 ? 2 : 1);
+  // weight gradients drain once per CTA after the whole reduction: nothing to overlap, the smem is worth
+  // more as an extra operand stage
+  return Epi::kMode == EPI_TMA_RED_F32 ? 1 : (Epi::kIn + Epi::kOut <= 3 ? 2 : 1);
 }
 template <class Epi> __host__ __device__ constexpr int epi_slots() {        // 4 KB boxes per TMEM quadrant (= per pair of epilogue warps)
   return Epi::kMode == EPI_DIRECT ? 0 : (Epi::kMode == EPI_TMA_RED_F32 ? 2 * epi_nbuf<Epi>() : (Epi::kIn + Epi::kOut) * epi_nbuf<Epi>());
 }
-template <class Epi> __host__ __device__ constexpr int epi_smem() { return 4 * epi_slots<Epi>() * kSlotBytes; }
+template <class Epi> __host__ __device__ constexpr int epi_smem() {
+  return 4 * epi_slots<Epi>() * kSlotBytes + (epi_has_bias<Epi>::value ? kOnesBytes : 0);
+}
 
 constexpr int kMaxSmem = 232448;   // 227 KB opt-in limit per CTA
 template <int BN, bool kPair> __host__ __device__ constexpr int stage_bytes() { return kBM * kBK * 2 + (kPair ? BN / 2 : BN) * kBK * 2; }
@@ -242,7 +254,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr int BNL = kPair ? BN / 2 : BN;                     // B rows (output columns) staged by this CTA
   constexpr uint32_t A_BYTES = kBM * kBK * 2;
   constexpr uint32_t B_BYTES = BNL * kBK * 2;
-  constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+  constexpr bool kBias = epi_has_bias<Epi>::value;
+  // split-P weight gradients run one item per CTA: a single accumulator stage (+ 32 columns for the bias MMA)
+  constexpr int ACC = kNT ? 1 : 2;
+  constexpr int TMEM_NEED = ACC * BN + (kBias ? 32 : 0);
+  constexpr uint32_t TMEM_COLS = TMEM_NEED <= 32 ? 32 : (TMEM_NEED <= 64 ? 64 : (TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512)));
+  static_assert(TMEM_NEED <= 512, "accumulators exceed tensor memory");
   constexpr int NSLOT = epi_slots<Epi>();
   constexpr int NBUF = epi_nbuf<Epi>();
   extern __shared__ uint8_t smem_raw[];
@@ -250,7 +267,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
   uint8_t* sEpi = sB + STAGES * B_BYTES;                       // 4 quadrants x NSLOT boxes of 4 KB
-  uint64_t* full = reinterpret_cast<uint64_t*>(sEpi + 4 * NSLOT * kSlotBytes);
+  uint8_t* sOnes = sEpi + 4 * NSLOT * kSlotBytes;              // kBias only
+  uint64_t* full = reinterpret_cast<uint64_t*>(sOnes + (kBias ? kOnesBytes : 0));
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
@@ -276,6 +294,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) tmem_alloc<kPair>(tmem_slot, TMEM_COLS);
+  if constexpr (kBias) {
+    for (int i = threadIdx.x; i < kOnesBytes / 4; i += kThreads) reinterpret_cast<uint32_t*>(sOnes)[i] = 0x3F803F80u;   // bf16 1.0 x2
+    fence_async_smem();                    // read by the tensor core through the async proxy
+  }
   fence_before_sync();
   __syncthreads();
   if (kPair) cluster_sync_all();           // the peer's barriers are initialised before anyone signals them
@@ -333,14 +355,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       constexpr uint32_t idesc = make_idesc(kPair ? 256 : 128, BN, kNT);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
+      [[maybe_unused]] constexpr uint32_t idesc_bias = make_idesc(kPair ? 256 : 128, 16, kNT);
+      [[maybe_unused]] const uint32_t ones_addr = smem_u32(sOnes);
       for (int it = item0; it < n_items; it += item_step) {
         const int split = it / (m_groups * wk.n_tiles);
         const int kb0 = split * wk.kb_per_split;
         const int kb1 = min(wk.kb_total, kb0 + wk.kb_per_split);
+        // the bias MMAs are dealt round-robin over the column tiles of a row block (K block kb goes to
+        // column tile kb % n_tiles), so that no CTA carries all of the extra A-operand reads
+        [[maybe_unused]] const int n_blk = (it % (m_groups * wk.n_tiles)) % wk.n_tiles;
+        [[maybe_unused]] bool bias_on = false, bias_started = false;
+        if constexpr (kBias) bias_on = epi.bias != nullptr;
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         fence_after_sync();
         const uint32_t d_tmem = tmem_base + acc * BN;
+        [[maybe_unused]] int rot = kb0 % wk.n_tiles;               // kb % n_tiles without a division per K block
         for (int kb = kb0; kb < kb1; ++kb) {
+          [[maybe_unused]] const bool bias_now = bias_on && rot == n_blk;
+          if (++rot == wk.n_tiles) rot = 0;
           mbar_wait(&full[stage], phase);
           fence_after_sync();
           const uint32_t a_addr = smem_u32(sA + stage * A_BYTES);
@@ -357,12 +389,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             if constexpr (kPair) umma_bf16_pair(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             else umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if constexpr (kBias) {
+              if (bias_now) {     // D'[m][0..15] += sum_k A[k][m] * 1
+                const uint64_t dones = make_desc(ones_addr + k * 2048, 8192, 1024);
+                if constexpr (kPair) umma_bf16_pair(tmem_base + ACC * BN, da, dones, idesc_bias, bias_started ? 1u : 0u);
+                else umma_bf16(tmem_base + ACC * BN, da, dones, idesc_bias, bias_started ? 1u : 0u);
+                bias_started = true;
+              }
+            }
           }
           if constexpr (kPair) umma_commit_pair(&empty[stage]); else umma_commit(&empty[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         if constexpr (kPair) umma_commit_pair(&tfull[acc]); else umma_commit(&tfull[acc]);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++acc == ACC) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else if (warp >= 4) {
@@ -396,7 +436,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           epi.template apply<32>(row, n_blk * BN + c * 32, v);
         }
         release_acc(acc);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++acc == ACC) { acc = 0; acc_phase ^= 1; }
       }
     } else if constexpr (Epi::kMode == EPI_TMA_BF16) {
       constexpr int KI = Epi::kIn, KO = Epi::kOut;
@@ -469,12 +509,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             bulk_commit();
           }
         }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++acc == ACC) { acc = 0; acc_phase ^= 1; }
       }
       if (leader) bulk_wait0();                   // all boxes written before the CTA may exit
     } else {
       // fp32 reduce-add units of 32 columns: the two warps of a quadrant alternate units, two boxes each
-      uint8_t* slot = sEpi + (q * NSLOT + hsel * 2) * kSlotBytes;
+      uint8_t* slot = sEpi + (q * NSLOT + hsel * NBUF) * kSlotBytes;
       const uint32_t row_off = lane * 128, swz = (lane & 7) << 4;
       uint32_t g = 0;
       for (int it = item0; it < n_items; it += item_step) {
@@ -486,18 +526,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         fence_after_sync();
         const int row0 = m_blk * kBM + q * 32;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+        if constexpr (kBias) {
+          // row sums of A^T over this CTA's share of the K blocks (none if its range holds no block of its own)
+          const int split = it / (m_groups * wk.n_tiles);
+          const int kb0 = split * wk.kb_per_split, kb1 = min(wk.kb_total, kb0 + wk.kb_per_split);
+          const int first = kb0 + ((n_blk - kb0 % wk.n_tiles) + wk.n_tiles) % wk.n_tiles;
+          if (epi.bias != nullptr && first < kb1 && hsel == 1) {
+            float b[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + ACC * BN, b);
+            if (row0 + lane < epi.M) atomicAdd(epi.bias + row0 + lane, b[0]);
+          }
+        }
         int last = n_units - 1; if ((last & 1) != hsel) --last;      // this warp's last unit (may be < 0)
         if (last < 0) release_acc(acc);
 #pragma unroll 1
         for (int u = hsel; u < n_units; u += 2, ++g) {
           const int col0 = n_blk * BN + u * 32;
-          uint8_t* sl = slot + (g & 1) * kSlotBytes;
+          uint8_t* sl = slot + (NBUF == 2 ? (g & 1) : 0) * kSlotBytes;
           float v[32];
           tmem_ld32(taddr + u * 32, v);
           if (u == last) release_acc(acc);
           uint32_t out[32];
           epi.compute(row0 + lane, col0, v, out);
-          if (lane == 0) bulk_wait_read1();
+          if (lane == 0) { if (NBUF == 2) bulk_wait_read1(); else bulk_wait_read0(); }
           __syncwarp();
 #pragma unroll
           for (int j = 0; j < 8; ++j)
@@ -506,7 +557,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           __syncwarp();
           if (lane == 0) { epi.store(0, sl, col0, row0); bulk_commit(); }
         }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++acc == ACC) { acc = 0; acc_phase ^= 1; }
       }
       if (lane == 0) bulk_wait0();
     }

@@ -349,6 +349,70 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   p[i] = pi - (lr / bc1) * (mi / denom);
 }
 
+// tcgen05 mode, no learned normal: one thread per point turns the gradient of the packed output row into
+// the pre-activation gradients DPRE[p][0..15] (heads' second layers), DPRE[p][16] (sigma) — everything
+// else in the backward of the heads is a GEMM on DPRE.  Rows leave through shared memory so that the
+// [P,64] bf16 matrix is written with full 16-byte coalesced stores; the scalar bias gradients are
+// reduced per block.
+__global__ void __launch_bounds__(256) heads_dpre_kernel(HeadPlan hp, const float* __restrict__ out,
+                                                         const float* __restrict__ g_out, int pitch,
+                                                         __nv_bfloat16* __restrict__ DPRE, float* __restrict__ g_params,
+                                                         long long P) {
+  __shared__ __align__(16) __nv_bfloat16 rows[256][64 + 8];     // +8: rows 144 B apart -> conflict-free 16 B accesses
+  __shared__ float bred[kMaxOut + 1];
+  const int tid = threadIdx.x;
+  if (tid <= kMaxOut) bred[tid] = 0.f;
+  __syncthreads();
+  const long long p = (long long)blockIdx.x * 256 + tid;
+  float d[kMaxOut + 1];
+#pragma unroll
+  for (int o = 0; o <= kMaxOut; ++o) d[o] = 0.f;
+  if (p < P) {
+    const float* row = out + p * pitch;
+    const float* grow = g_out + p * pitch;
+#pragma unroll
+    for (int o = 0; o < kMaxOut; ++o) {
+      if (o < hp.n_out) {
+        const OutDesc& q = hp.o[o];
+        float g = 0.f;
+        for (int c = 0; c < q.rep; ++c) g += grow[q.ch + c];
+        const float v = row[q.ch];
+        float sg, scale;
+        if (q.xform == XF_K) { sg = (v - 1.0f) * 0.5f + 0.5f; scale = 2.0f; }
+        else if (q.xform == XF_THETA_RPV) { sg = v * 0.5f + 0.5f; scale = 2.0f; }
+        else if (q.xform == XF_THETA_H) { const float k = (float)(M_PI * 30.0 / 180.0); sg = v / k; scale = k; }
+        else { sg = v; scale = 1.0f; }
+        d[o] = g * scale * sg * (1.0f - sg);
+      }
+    }
+    d[kMaxOut] = grow[hp.ch_sigma] * (1.0f - expf(-row[hp.ch_sigma]));      // softplus'(x) = 1 - exp(-softplus(x))
+  }
+  uint32_t* r32 = reinterpret_cast<uint32_t*>(&rows[tid][0]);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r32[j] = tc::bf_pack(d[2 * j], d[2 * j + 1]);
+  r32[8] = tc::bf_pack(d[kMaxOut], 0.f);
+#pragma unroll
+  for (int j = 9; j < 32; ++j) r32[j] = 0u;
+  // block sums of every column that is a bias gradient
+#pragma unroll
+  for (int o = 0; o <= kMaxOut; ++o) {
+    if (o < hp.n_out || o == kMaxOut) {
+      const float sum = warp_sum(d[o]);
+      if ((tid & 31) == 0) atomicAdd(&bred[o], sum);
+    }
+  }
+  __syncthreads();
+  // 256 rows x 8 chunks of 16 B, consecutive threads write consecutive chunks
+  const long long p0 = (long long)blockIdx.x * 256;
+  for (int c = tid; c < 256 * 8; c += 256) {
+    const int r = c >> 3, j = c & 7;
+    if (p0 + r < P)
+      *reinterpret_cast<uint4*>(DPRE + (p0 + r) * 64 + j * 8) = *reinterpret_cast<const uint4*>(&rows[r][j * 8]);
+  }
+  if (tid < hp.n_out) atomicAdd(g_params + hp.o[tid].b_off, bred[tid]);
+  if (tid == kMaxOut) atomicAdd(g_params + hp.bsig, bred[kMaxOut]);
+}
+
 // W2p[b*HH + i][o] = W2_o[i] when output o hangs off block b, else 0  (o < 64; [n_blocks*HH, 64] bf16)
 __global__ void pack_w2_kernel(HeadPlan hp, const float* __restrict__ params, __nv_bfloat16* __restrict__ W2p) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -490,7 +554,12 @@ static int backward_t(bn_mlp* h, const float* params, const float* out, const fl
   const T* Hl = w.H[L - 1]; const long long ldl = w.Hld[L - 1];
   const int HKa = hp.n_blocks * h->HH;
   constexpr bool kTC = std::is_same<T, __nv_bfloat16>::value;   // bias grads fused into the tcgen05 dgrad epilogues
-  {
+  if (kTC && hp.ch_nlr < 0) {
+    if constexpr (kTC) {
+      heads_dpre_kernel<<<(unsigned)ceil_div_ll(P, 256), 256, 0, s>>>(hp, out, g_out, pitch, w.DPRE, g, P);
+      BN_LAUNCH_CHECK();
+    }
+  } else {
     const size_t smem = (size_t)(HKa + 24) * sizeof(float);
     heads_bwd_kernel<T, kTC><<<heads_grid(h, P), 256, smem, s>>>(hp, params, out, g_out, pitch, Hl, ldl, F, w.CD, w.ldhd,
                                                                 w.GHD, w.G7D, w.DPRE, g, P);
@@ -501,7 +570,7 @@ static int backward_t(bn_mlp* h, const float* params, const float* out, const fl
     pack_w2_kernel<<<ceil_div(HKa * 64, 256), 256, 0, s>>>(hp, params, (__nv_bfloat16*)h->W2p);
     BN_LAUNCH_CHECK();
     for (int b = 0; b < hp.n_blocks; ++b) {
-      DgradArgs<T> a; a.mulc = w.CD + (long long)b * h->HH; a.ldm = w.ldhd; a.bias_grad = g + hp.b1_off[b];
+      DgradArgs<T> a; a.mulc = w.CD + (long long)b * h->HH; a.ldm = w.ldhd;
       if (int rc = layer_dgrad<T>(h, w.DPRE, 64, (const T*)h->W2p + (long long)b * h->HH * 64, 64, P, h->HH, 64, a,
                                   w.GHD + (long long)b * h->HH, w.ldhd, s)) return rc;
     }
@@ -536,19 +605,20 @@ static int backward_t(bn_mlp* h, const float* params, const float* out, const fl
     skinny_wgrad_kernel<T><<<dim3(bx2, by2), 256, 0, s>>>(s2, w.DPRE, 64, Hl, ldl, F, P, rows2);
     BN_LAUNCH_CHECK();
   }
-  // heads' first layer: wgrad per block (bias grads came out of heads_bwd_kernel), dgrad into the features
+  // heads' first layer: wgrad (+ bias gradient; the fp32 mode got it from heads_bwd_kernel) per block, dgrad into the features
   for (int b = 0; b < hp.n_blocks; ++b) {
     const int lin = h->blk_lin0[b];
-    if (int rc = layer_wgrad<T>(h, w.GHD + (long long)b * h->HH, w.ldhd, w.FE, F, h->HH, F, P, g + c.w_off[lin], F, F, F, s)) return rc;
+    if (int rc = layer_wgrad<T>(h, w.GHD + (long long)b * h->HH, w.ldhd, w.FE, F, h->HH, F, P, g + c.w_off[lin], F, F, F,
+                                kTC ? g + hp.b1_off[b] : nullptr, s)) return rc;
   }
   {
-    DgradArgs<T> a; a.bias_grad = g + c.b_off[BN_LIN_FEATS];
+    DgradArgs<T> a;
     if (int rc = layer_dgrad<T>(h, w.GHD, w.ldhd, (const T*)h->W1T, (long long)h->n_blocks * h->HH, P, F, HKa, a, w.GFE, F, s)) return rc;
   }
   // feature layer
   {
-    if (int rc = layer_wgrad<T>(h, w.GFE, F, Hl, ldl, F, F, P, g + c.w_off[BN_LIN_FEATS], F, F, F, s)) return rc;
-    DgradArgs<T> a; a.mulc = w.C[L - 1]; a.ldm = F; a.bias_grad = g + c.b_off[L - 1];
+    if (int rc = layer_wgrad<T>(h, w.GFE, F, Hl, ldl, F, F, P, g + c.w_off[BN_LIN_FEATS], F, F, F, g + c.b_off[BN_LIN_FEATS], s)) return rc;
+    DgradArgs<T> a; a.mulc = w.C[L - 1]; a.ldm = F;
     if constexpr (kTC) {          // direct grads into h_{L-1}: dsigma w_sigma + sum_k dv_k Wg_k, DPRE cols 16..19
       a.rank_rows = w.DPRE + 16; a.rank_ld = 64; a.n_rank = hp.ch_nlr >= 0 ? 4 : 1;
       a.rank_col[0] = params + hp.wsig;
@@ -564,10 +634,10 @@ static int backward_t(bn_mlp* h, const float* params, const float* out, const fl
     const T* In; long long ldin;
     if (enc_in) { In = w.X3; ldin = w.ldx3; } else { In = w.H[l - 1]; ldin = w.Hld[l - 1]; }
     if (int rc = layer_wgrad<T>(h, cur, F, In, ldin, F, h->Kpad[l], P, g + c.w_off[l], h->Kreal[l],
-                                enc_in ? h->E : h->Kpad[l], enc_in ? kEncPad : h->Kpad[l], s, 2.0 * P * F * h->Kreal[l])) return rc;
+                                enc_in ? h->E : h->Kpad[l], enc_in ? kEncPad : h->Kpad[l], g + c.b_off[l], s, 2.0 * P * F * h->Kreal[l])) return rc;
     if (l > 0) {
       const T* BT = (const T*)h->WTp[l] + (l == h->skip ? (long long)kEncPad * F : 0);
-      DgradArgs<T> a; a.mulc = w.C[l - 1]; a.ldm = F; a.bias_grad = g + c.b_off[l - 1];
+      DgradArgs<T> a; a.mulc = w.C[l - 1]; a.ldm = F;
       if (normals) { a.add2 = w.U[l - 1]; a.ld2 = F; }
       if (int rc = layer_dgrad<T>(h, cur, F, BT, F, P, F, F, a, nxt, F, s)) return rc;
       T* t = cur; cur = nxt; nxt = t;
@@ -738,5 +808,5 @@ int bn_debug_gemm_epi(int kind, const void* A, long long lda, const void* B, lon
     return layer_dgrad<T>(&h, (const T*)A, lda, (const T*)B, ldb, M, N, (int)K, a, (T*)out, ldo, stream);
   }
   BN_CHECK_ARG(tc::wgrad_tma_ok((const float*)out, ldo, N, pad_lo, pad_hi), "output not addressable by the TMA");
-  return layer_wgrad<T>(&h, (const T*)A, lda, (const T*)B, ldb, (int)M, N, K, (float*)out, ldo, pad_lo, pad_hi, stream);
+  return layer_wgrad<T>(&h, (const T*)A, lda, (const T*)B, ldb, (int)M, N, K, (float*)out, ldo, pad_lo, pad_hi, colsum, stream);
 }

@@ -282,8 +282,9 @@ static int layer_bias(const bn_mlp* h, const T* A, long long lda, const T* W, lo
   }
 }
 
-// out = ((A BT^T) [+ addend]) [* mulc] [+ add2];  raw = (A BT^T) + addend.  bias_grad (nullable) += column
-// sums of out (fused into the tcgen05 epilogue; a separate pass in the fp32 mode).
+// out = ((A BT^T) [+ addend]) [* mulc] [+ add2];  raw = (A BT^T) + addend.  bias_grad (nullable, tcgen05
+// mode only, used by the unit test): column sums of out from the epilogue registers; the training path
+// takes its bias gradients from layer_wgrad instead.
 template <typename T> struct DgradArgs {
   const T* addend = nullptr; long long lda = 0;
   const T* mulc = nullptr; long long ldm = 0;
@@ -331,9 +332,7 @@ static int layer_dgrad(const bn_mlp* h, const T* A, long long lda, const T* BT, 
   } else {
     EpiDgrad<T> e{a.addend, a.lda, a.mulc, a.ldm, out, ldo, (int)P, N};
     e.raw_out = a.raw; e.ldr = a.ldr; e.add2 = a.add2; e.ld2 = a.ld2;
-    if (int rc = gemm_tn<T>(h, A, lda, BT, ldb, P, N, K, e, s)) return rc;
-    if (a.bias_grad) return colsum<T>(out, ldo, N, P, a.bias_grad, s);
-    return BN_OK;
+    return gemm_tn<T>(h, A, lda, BT, ldb, P, N, K, e, s);
   }
 }
 
@@ -356,19 +355,28 @@ static int layer_second(const bn_mlp* h, const T* A, long long lda, const T* W, 
   }
 }
 
-// dW [Mo, Kreal] += G[:, :Mo]^T In[:, :No]   (No = packed width of In with padding [pad_lo, pad_hi))
+// dW [Mo, Kreal] += G[:, :Mo]^T In[:, :No]   (No = packed width of In with padding [pad_lo, pad_hi));
+// bias_grad (nullable) [Mo] += column sums of G — fused into the tcgen05 mainloop (an N=16 MMA against a
+// tile of ones), a separate pass over G in the fp32 mode.
 template <typename T>
 static int layer_wgrad(const bn_mlp* h, const T* G, long long ldg, const T* In, long long ldin, int Mo, int No, long long P,
-                       float* dW, long long ldw, int pad_lo, int pad_hi, cudaStream_t s, double flops = -1.0) {
+                       float* dW, long long ldw, int pad_lo, int pad_hi, float* bias_grad, cudaStream_t s, double flops = -1.0) {
   if constexpr (std::is_same<T, __nv_bfloat16>::value) {
     if (tc::wgrad_tma_ok(dW, ldw, No, pad_lo, pad_hi)) {
-      tc::EpiWgradT e;
-      if (int rc = tc::make_wgrad(&e, dW, ldw, Mo, No, pad_lo, pad_hi)) return rc;
+      if (bias_grad) {
+        tc::EpiWgradT<true> e;
+        if (int rc = tc::make_wgrad(&e, dW, ldw, Mo, No, pad_lo, pad_hi, bias_grad)) return rc;
+        return gemm_nt<T>(h, G, ldg, In, ldin, Mo, No, P, e, s, flops);
+      }
+      tc::EpiWgradT<false> e;
+      if (int rc = tc::make_wgrad(&e, dW, ldw, Mo, No, pad_lo, pad_hi, nullptr)) return rc;
       return gemm_nt<T>(h, G, ldg, In, ldin, Mo, No, P, e, s, flops);
     }
   }
   EpiWgrad e{dW, ldw, Mo, No, pad_lo, pad_hi};
-  return gemm_nt<T>(h, G, ldg, In, ldin, Mo, No, P, e, s, flops);
+  if (int rc = gemm_nt<T>(h, G, ldg, In, ldin, Mo, No, P, e, s, flops)) return rc;
+  if (bias_grad) return colsum<T>(G, ldg, Mo, P, bias_grad, s);
+  return BN_OK;
 }
 
 template <typename T>

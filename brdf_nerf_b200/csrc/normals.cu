@@ -200,7 +200,7 @@ static int normals_backward_t(bn_mlp* h, const float* params, const float* out, 
     if (int rc = layer_second<T>(h, Aop, lda, (const T*)h->Wp[l], h->Kpad[l], P, F, h->Kpad[l], w.C[l], F, w.U[l], F,
                                  w.H[l], w.Hld[l], dst, ldd, -w0 * w0, s, h->Kreal[l])) return rc;
     if (int rc = layer_wgrad<T>(h, w.A[l], F, Aop, lda, F, h->Kpad[l], P, g + c.w_off[l], h->Kreal[l],
-                                enc_in ? h->E : h->Kpad[l], enc_in ? kEncPad : h->Kpad[l], s, 2.0 * P * F * h->Kreal[l])) return rc;
+                                enc_in ? h->E : h->Kpad[l], enc_in ? kEncPad : h->Kpad[l], nullptr, s, 2.0 * P * F * h->Kreal[l])) return rc;
     prev = dst; ldprev = ldd;
   }
   const long long wsig = c.w_off[BN_LIN_SIGMA];

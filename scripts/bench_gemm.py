@@ -68,12 +68,18 @@ def main():
         A, m, _ = nxt()
         L.check(lib.bn_debug_gemm_epi(1, vp(A), K, vp(m), N, vp(dW), K, None, None, None, K, K, K, N, P, L.stream_ptr()))
 
+    bias = torch.zeros(K, dtype=torch.float32, device=dev)
+
+    def wgrad_bias():
+        A, m, _ = nxt()
+        L.check(lib.bn_debug_gemm_epi(1, vp(A), K, vp(m), N, vp(dW), K, None, None, vp(bias), K, K, K, N, P, L.stream_ptr()))
+
     def cublas():
         A, _, out = nxt()
         torch.matmul(A, B.t(), out=out)
 
     for name, fn in (("mainloop only (null epilogue)", null), ("bf16 store", plain), ("mul + store (dgrad)", mul),
-                     ("mul + store + colsum", mulcs), ("wgrad NT + TMA reduce", wgrad), ("torch.matmul (cuBLAS) bf16 out", cublas)):
+                     ("mul + store + colsum", mulcs), ("wgrad NT + TMA reduce", wgrad), ("wgrad NT + TMA reduce + bias MMA", wgrad_bias), ("torch.matmul (cuBLAS) bf16 out", cublas)):
         us = timeit(fn)
         print(f"{name:34s} {us:8.1f} us  {flops / us / 1e6:7.1f} TFLOP/s", flush=True)
 

@@ -114,9 +114,13 @@ def test_nt_tma_reduce_epilogue(cuda, Mo, No, P, pad_lo, pad_hi):
     kreal = No - (pad_hi - pad_lo)
     base = torch.randn(Mo, kreal, generator=g).to(cuda)
     out = base.clone()
-    L.check(L.load().bn_debug_gemm_epi(1, _vp(A), A.stride(0), _vp(B), B.stride(0), _vp(out), kreal, None, None, None,
+    bias = torch.full((Mo,), 3.0, dtype=torch.float32, device=cuda)
+    L.check(L.load().bn_debug_gemm_epi(1, _vp(A), A.stride(0), _vp(B), B.stride(0), _vp(out), kreal, None, None, _vp(bias),
                                        pad_lo, pad_hi, Mo, No, P, L.stream_ptr()))
     torch.cuda.synchronize()
+    # bias gradient fused into the mainloop (N=16 MMA against ones): column sums of the A operand
+    bref = 3.0 + A.float().sum(0)
+    assert (bias - bref).abs().max().item() < 2e-3 * max(1.0, bref.abs().max().item())
     full = A.float().t() @ B.float()
     ref = base + torch.cat([full[:, :pad_lo], full[:, pad_hi:]], dim=1)
     err = (out - ref).abs().max().item()
