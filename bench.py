@@ -30,6 +30,11 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 RAYS_PER_GPU = 1024
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant instantiation (training-forward trunk
+# layer, EpiSinT<true>, P = 131072, K = N = 512) from profiles/r01c_ncu_full_gemm_pair.csv; algorithmic: 402.7 MB
+NCU_GEMM_DRAM_BYTES_PER_LAUNCH = 344.4e6
+NCU_GEMM_TRAFFIC_NOTE = ("ncu --set full, gemm_tc_kernel<256,5,tn,pair,EpiSinT<1>>: 134.8 MB read + 209.6 MB written per launch "
+                         "(algorithmic 128 MiB read + 256 MiB written; the tail of the writes is still in L2 when the kernel ends)")
 METRIC = "train rays/s (SpS-BRDF-NeRF, 1/2/4/8 B200); MLP tensor-pipe %; composite GB/s"
 
 
@@ -226,7 +231,8 @@ def run_ours(opts):
         achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
         roof = {"bound": "tensor", "kernel": "bn::tc::gemm_tc_kernel (all PE+SIREN fwd/dgrad/wgrad GEMMs of a step)",
                 "achieved": achieved, "peak": peaks["tf_sust"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_sust"],
-                "peak_kind": f"{peaks['src']} sustained bf16 (kernel timed inside a long step)", "traffic": None,
+                "peak_kind": f"{peaks['src']} sustained bf16 (kernel timed inside a long step)",
+                "traffic": NCU_GEMM_DRAM_BYTES_PER_LAUNCH, "traffic_note": NCU_GEMM_TRAFFIC_NOTE,
                 "launches_per_step": (cnt[0] + cnt[1]) / nprof, "gemm_ms_per_step": gemm_ms,
                 "gemm_share_of_step": gemm_ms / ms, "algorithmic_gflop_per_step": gemm_flops / 1e9,
                 "survey_gflop_per_step": alg / 1e9,
@@ -234,12 +240,26 @@ def run_ours(opts):
                                              "tflops": work[0] / max(tms[0], 1e-9) / 1e9},
                             "nt_wgrad": {"launches": cnt[1] / nprof, "ms": tms[1] / nprof,
                                          "tflops": work[1] / max(tms[1], 1e-9) / 1e9}}}
+    # ---- HBM leg: the compositing kernels (K-C) at inference-chunk size, GB/s against the measured copy peak ----
+    roof_hbm = None
+    if rank == 0 and not opts.no_composite:
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        import bench_composite
+        n_c = 65536
+        r = bench_composite.run(n_c, 128, report=lambda *_: None)
+        dom = r["composite_bwd C=16"]
+        roof_hbm = {"bound": "hbm", "kernel": "bn::composite_bwd_kernel<16> (BRDF-stage compositing backward, RPV111 channel block)",
+                    "achieved": dom["gbs"], "peak": _peaks()["hbm"], "unit": "GB/s", "frac": dom["gbs"] / _peaks()["hbm"],
+                    "peak_kind": f"{_peaks()['src']} HBM copy bandwidth (kernel timed alone, inputs rotated over 3 sets > L2)",
+                    "traffic": None, "algorithmic_bytes_per_launch": dom["bytes"], "us_per_launch": dom["us"],
+                    "workload": f"{n_c} rays x 128 samples (one inference chunk); the 1024-ray training batch moves 7 MB and is latency bound",
+                    "all": {k: {"us": v["us"], "GB/s": v["gbs"], "frac": v["frac"]} for k, v in r.items()}}
     if rank == 0:
         cpu = None
         if world == 1 and not opts.no_cpu_baseline:
-            v, cms, cores = cpu_reference_rate(args, RAYS_PER_GPU, 2, 1)
+            v, cms, cores = cpu_reference_rate(args, RAYS_PER_GPU, 6, 1)
             cpu = {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",
-                   "sample": "2 steps of 1024 rays after 1 warm-up (full step: render + loss + backward + Adam), torch CPU fp32"}
+                   "sample": "6 steps of 1024 rays after 1 warm-up (full step: render + loss + backward + Adam), torch CPU fp32"}
         line = {"metric": METRIC, "value": total_rays / (ms * 1e-3), "unit": "rays/s", "n_gpus": world, "steps": opts.steps,
                 "warmup": max(3, opts.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16" if opts.precision == "bf16" else "f32", "data": "synthetic",
@@ -250,7 +270,8 @@ def run_ours(opts):
                            "l2": "per-step working set (~3.4 GB of activations) >> 126 MB L2; no explicit flush"},
                 "e2e": {"value": total_rays / (ms_e2e * 1e-3), "unit": "rays/s", "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": host_batch.nbytes(), "d2h_bytes_per_step": 4},
-                "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+                "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "roofline_composite": roof_hbm,
+                "cpu_baseline": cpu,
                 "loss": float(loss_host)}
         print(json.dumps(line))
     if world > 1:
@@ -266,6 +287,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--graph", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-composite", action="store_true", help="skip the compositing (HBM) roofline leg")
     opts = ap.parse_args()
     if opts.impl == "reference":
         run_reference(opts)

@@ -1,6 +1,7 @@
 // K-B: positional encoding + SIREN MLP — weight packing, encoding, heads, forward / backward
 // orchestration and the C entry points.  Shared declarations live in mlp_internal.cuh.
 #include "mlp_internal.cuh"
+#include "mlp_chain.cuh"
 
 namespace bn {
 
@@ -500,6 +501,38 @@ static unsigned heads_grid(const bn_mlp* h, long long P) {
   return (unsigned)max(1LL, min(ceil_div_ll(P, 8 * kQP), (long long)h->num_sms * 4));
 }
 
+// density pass as ONE fused kernel (mlp_chain.cuh); tcgen05 mode, 512-wide trunk
+static int sigma_chain(bn_mlp* h, const float* params, const float* origins, int o_stride, const float* dirs, int d_stride,
+                       const float* z, int N, int S, float* out, cudaStream_t s) {
+  const bn_mlp_cfg& c = h->cfg;
+  chain::SigmaChainParams prm;
+  for (int l = 0; l < h->L; ++l) {
+    if (int rc = tc::make_map_bf16(&prm.wmap[l], h->Wp[l], h->F, h->Kpad[l], h->Kpad[l], 64, 128)) return rc;
+    prm.bias[l] = params + c.b_off[l];
+  }
+  prm.wsig = params + c.w_off[BN_LIN_SIGMA]; prm.bsig = params + c.b_off[BN_LIN_SIGMA];
+  prm.origins = origins; prm.dirs = dirs; prm.z = z; prm.out = out;
+  prm.P = (long long)N * S; prm.o_stride = o_stride; prm.d_stride = d_stride; prm.S = S;
+  prm.L = h->L; prm.skip = h->skip; prm.n_freq = c.n_freq_xyz;
+  const int n_blocks = (int)ceil_div_ll(prm.P, 256);
+  constexpr int smem = chain::sigma_chain_smem();
+  BN_CUDA(cudaFuncSetAttribute(chain::sigma_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * min(n_blocks, h->num_sms / 2));
+  cfg.blockDim = dim3(tc::kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  prof_begin(0, 2.0 * (double)prm.P * ((double)h->E * h->F + (double)(h->L - 2) * h->F * h->F + (double)(h->F + h->E) * h->F + h->F), s);
+  BN_CUDA(cudaLaunchKernelEx(&cfg, chain::sigma_chain_kernel, prm));
+  const int rc = after_launch("sigma_chain_kernel");
+  prof_end(s);
+  return rc;
+}
+
 template <typename T>
 static int forward_t(bn_mlp* h, const float* params, const float* origins, int o_stride, const float* dirs,
                      int d_stride, const float* z, int N, int S, int flags, float* out, int pitch, void* wsp,
@@ -509,6 +542,10 @@ static int forward_t(bn_mlp* h, const float* params, const float* origins, int o
   const bool keep_c = train || ((flags & BN_MLP_NORMAL_AN) && !sig_only);
   const bn_mlp_cfg& c = h->cfg;
   const int F = h->F, L = h->L;
+  if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+    if (sig_only && h->F == chain::kF && h->skip >= 1 && !h->no_chain)
+      return sigma_chain(h, params, origins, o_stride, dirs, d_stride, z, N, S, out, s);
+  }
   Ws<T> w; carve<T>(h, P, flags, wsp, &w);
   HeadPlan hp; int nch;
   if (int rc = build_plan(h, flags, &hp, &nch)) return rc;
@@ -670,6 +707,7 @@ extern "C" __attribute__((visibility("default"))) int bn_mlp_create(const bn_mlp
   cudaDeviceProp prop;
   BN_CUDA(cudaGetDeviceProperties(&prop, dev));
   h->num_sms = prop.multiProcessorCount;
+  h->no_chain = getenv("BN_NO_CHAIN") != nullptr;      // debugging aid: per-layer GEMMs for the density pass
   // blocks of the heads' hidden layer: rgb first, then every BRDF head that exists
   h->n_blocks = 0;
   h->blk_lin0[0] = BN_LIN_RGB0; h->blk_lin2[0] = BN_LIN_RGB2; h->blk_head[0] = -1; h->n_blocks = 1;

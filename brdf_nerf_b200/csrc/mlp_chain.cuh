@@ -1,0 +1,257 @@
+// Fused PE + SIREN trunk + sigma head: ONE persistent kernel runs all layers of the density pass
+// (reference: SpSBRDFNeRF.forward(sigma_only=True), models/spsbrdfnerf.py:677-685 = Mapping
+// nerf.py:53-70 + calc_features :636-646 + softplus(sigma_from_xyz) :682) for a block of 256 points per
+// CTA pair.  Activations never leave the SM: they live in shared memory as the 128B-swizzled K-major A
+// operand of the next layer, accumulators in tensor memory; only the weights stream (TMA, L2 resident,
+// 16 KB per CTA per K block) and 4 bytes per point are written.
+//
+//   warp 0     weight producer: one [128 x 64] tile of W_l per (layer, column half, K block), 4-stage ring;
+//              the leader CTA's barrier collects the bytes of both CTAs (tcgen05 pair protocol of gemm_tc.cuh)
+//   warp 1     MMA issuer (leader CTA): tcgen05.mma.cta_group::2, M = 256 (128 rows per CTA), N = 256;
+//              a layer = two column halves, each accumulating over the layer's K blocks into its own 256 TMEM
+//              columns.  K block kb of the input is consumed as soon as the epilogue of the previous layer
+//              has published it (act_ready[kb]), so the next layer's first half starts while the previous
+//              layer's second half is still in the epilogue.
+//   warp 2     TMEM allocator
+//   warps 4-11 epilogue: tcgen05.ld -> bias + sin (MUFU) -> bf16 -> swizzled st.shared into the K block of
+//              the NEXT layer's input (in place: the write waits until every MMA of the current layer has
+//              retired, i.e. for the second half's commit); last layer: dot with w_sigma, softplus.
+//              Before layer 0 they evaluate x = o + d z and the positional encoding into K block 0.
+// Shared memory: 9 K blocks x 16 KB activations ([PE | h], so the skip layer reads K = 576 without a concat)
+// + 4 x 16 KB weight ring.
+#pragma once
+#include "gemm_tc.cuh"
+#include "epilogues_tc.cuh"
+
+namespace bn {
+namespace chain {
+
+using namespace tc;
+
+constexpr int kF = 512;                 // trunk width this kernel is specialised for
+constexpr int kNKB = 1 + kF / 64;       // K blocks of the activation buffer: PE + 8 x 64 features
+constexpr int kWStages = 5;
+constexpr int kKBBytes = 128 * 128;     // one K block of one CTA: 128 rows x 64 bf16
+constexpr int kMaxLayers = 16;
+
+struct SigmaChainParams {
+  CUtensorMap wmap[kMaxLayers];         // packed W_l [F, Kpad_l] bf16, boxes 64 (K) x 128 (rows)
+  const float* bias[kMaxLayers];
+  const float* wsig; const float* bsig;
+  const float* origins; const float* dirs; const float* z;
+  float* out;
+  long long P;
+  int o_stride, d_stride, S, L, skip, n_freq;
+};
+
+constexpr int sigma_chain_smem() { return kNKB * kKBBytes + kWStages * kKBBytes + 1024 /*sigma exchange*/ + 512 + 1024; }
+
+__device__ __forceinline__ int layer_kb_first(int l, int skip) { return (l == 0 || l == skip) ? 0 : 1; }
+__device__ __forceinline__ int layer_kb_last(int l) { return l == 0 ? 0 : kNKB - 1; }
+// column of K block kb inside the packed weight matrix of layer l
+__device__ __forceinline__ int layer_wcol(int l, int skip, int kb) { return (l == 0) ? 0 : (l == skip ? kb * 64 : (kb - 1) * 64); }
+
+__global__ void __launch_bounds__(kThreads, 1) sigma_chain_kernel(const __grid_constant__ SigmaChainParams prm) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sAct = smem;                                        // [kNKB][128 rows][128 B], swizzled
+  uint8_t* sW = sAct + kNKB * kKBBytes;                        // [kWStages][128 rows of W][128 B]
+  float* sSig = reinterpret_cast<float*>(sW + kWStages * kKBBytes);   // [128] partial sigma of the hsel = 1 warps
+  uint64_t* wfull = reinterpret_cast<uint64_t*>(sSig + 256);
+  uint64_t* wempty = wfull + kWStages;
+  uint64_t* tfull = wempty + kWStages;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* act_ready = tempty + 2;                            // [kNKB]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(act_ready + kNKB);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int crank = (int)cluster_ctarank();
+  const int pair0 = (int)cluster_id_x(), npairs = (int)cluster_nctaid_x();
+  const int n_blocks = (int)((prm.P + 255) / 256);
+  const int L = prm.L, skip = prm.skip;
+
+  if (warp == 0 && lane == 0)
+    for (int l = 0; l < L; ++l) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&prm.wmap[l])) : "memory");
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kWStages; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 16); }     // 8 epilogue warps x 2 CTAs
+    for (int s = 0; s < kNKB; ++s) mbar_init(&act_ready[s], 16);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) tmem_alloc<true>(tmem_slot, 512);
+  fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== weight producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int blk = pair0; blk < n_blocks; blk += npairs)
+        for (int l = 0; l < L; ++l)
+          for (int n = 0; n < 2; ++n)
+            for (int kb = layer_kb_first(l, skip); kb <= layer_kb_last(l); ++kb) {
+              mbar_wait(&wempty[stage], phase ^ 1);
+              if (crank == 0) mbar_expect_tx(&wfull[stage], 2 * kKBBytes);
+              tma_load_2d_pair(sW + stage * kKBBytes, &prm.wmap[l], mapa_u32(smem_u32(&wfull[stage]), 0),
+                               layer_wcol(l, skip, kb), n * 256 + crank * 128);
+              if (++stage == kWStages) { stage = 0; phase ^= 1; }
+            }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA) =====================
+    if (lane == 0 && crank == 0) {
+      constexpr uint32_t idesc = make_idesc(256, 256, false);
+      int stage = 0; uint32_t phase = 0;
+      uint32_t te_ph[2] = {0, 0};
+      uint32_t ar_ph = 0;                                   // bit kb: parity the next wait on act_ready[kb] expects
+      for (int blk = pair0; blk < n_blocks; blk += npairs)
+        for (int l = 0; l < L; ++l)
+          for (int n = 0; n < 2; ++n) {
+            mbar_wait(&tempty[n], te_ph[n] ^ 1); te_ph[n] ^= 1;      // the epilogue has read this half out
+            fence_after_sync();
+            bool first = true;
+            for (int kb = layer_kb_first(l, skip); kb <= layer_kb_last(l); ++kb) {
+              if (n == 0 && !(kb == 0 && l > 0)) {          // K block published once per layer (PE: once per block)
+                mbar_wait(&act_ready[kb], (ar_ph >> kb) & 1); ar_ph ^= 1u << kb;
+                fence_after_sync();
+              }
+              mbar_wait(&wfull[stage], phase);
+              fence_after_sync();
+              const uint32_t a_addr = smem_u32(sAct + kb * kKBBytes);
+              const uint32_t b_addr = smem_u32(sW + stage * kKBBytes);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma_bf16_pair(tmem_base + n * 256, make_desc(a_addr + k * 32, 16, 1024), make_desc(b_addr + k * 32, 16, 1024),
+                               idesc, (first && k == 0) ? 0u : 1u);
+              }
+              first = false;
+              umma_commit_pair(&wempty[stage]);
+              if (++stage == kWStages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit_pair(&tfull[n]);
+          }
+    }
+  } else if (warp >= 4) {
+    // ===================== positional encoding + epilogues =====================
+    const int q = warp & 3, hsel = (warp - 4) >> 2;
+    const int row = q * 32 + lane;                           // row of this CTA's 128-row slab
+    const uint32_t row_off = row * 128, swz = (lane & 7) << 4;
+    const uint32_t t_lane = (uint32_t)(q * 32) << 16;
+    uint32_t tf_ph[2] = {0, 0};
+    auto arrive_leader = [&](uint64_t* bar) {               // one arrival per warp on the leader CTA's barrier
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(bar), 0));
+    };
+    for (int blk = pair0; blk < n_blocks; blk += npairs) {
+      const long long p = (long long)blk * 256 + crank * 128 + row;
+      // ---- x = o + d z, encoding into K block 0 (hsel 0 warps; one row per thread) ----
+      if (hsel == 0) {
+        const long long pc = p < prm.P ? p : prm.P - 1;
+        const long long r = pc / prm.S;
+        const float zz = prm.z[pc];
+        float x[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) x[a] = __fadd_rn(prm.origins[r * prm.o_stride + a], __fmul_rn(prm.dirs[r * prm.d_stride + a], zz));
+        float e[64];
+#pragma unroll
+        for (int i = 0; i < 64; ++i) e[i] = 0.f;
+        if (prm.n_freq == 0) { e[0] = x[0]; e[1] = x[1]; e[2] = x[2]; }
+        else {
+#pragma unroll
+          for (int k = 0; k < 10; ++k)
+            if (k < prm.n_freq) {
+              const float f = (float)(1 << k);
+#pragma unroll
+              for (int a = 0; a < 3; ++a) { float s, c; sincosf(f * x[a], &s, &c); e[k * 6 + a] = s; e[k * 6 + 3 + a] = c; }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          sts128(sAct + row_off + ((j << 4) ^ swz), bf_pack(e[8 * j], e[8 * j + 1]), bf_pack(e[8 * j + 2], e[8 * j + 3]),
+                 bf_pack(e[8 * j + 4], e[8 * j + 5]), bf_pack(e[8 * j + 6], e[8 * j + 7]));
+        fence_async_smem();
+      }
+      arrive_leader(&act_ready[0]);
+      float sig = 0.f;
+      for (int l = 0; l < L; ++l) {
+        const float w0 = l == 0 ? 30.0f : 1.0f;
+        const bool last = l == L - 1;
+        for (int n = 0; n < 2; ++n) {
+          mbar_wait(&tfull[n], tf_ph[n]); tf_ph[n] ^= 1;
+          fence_after_sync();
+          // software-pipelined TMEM reads: unit u+1 is in flight while unit u goes through the MUFU
+          uint32_t pk[4][16];
+          uint32_t va[32], vb[32];
+          const uint32_t tbase = tmem_base + t_lane + n * 256 + hsel * 32;
+          tmem_ld32_issue(tbase, va);
+          if (!last && n == 1) { /* every MMA of this layer has retired (tfull[1]): K blocks may be overwritten at once */ }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            tmem_wait_ld();
+            uint32_t (&v)[32] = (u & 1) ? vb : va;
+            if (u < 3) tmem_ld32_issue(tbase + (u + 1) * 64, (u & 1) ? va : vb);
+            else { fence_before_sync(); arrive_leader(&tempty[n]); }       // this warp's share of the half is in registers
+            const int col0 = n * 256 + u * 64 + hsel * 32;
+            const float4* bp = reinterpret_cast<const float4*>(prm.bias[l] + col0);
+            if (!last) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 b = __ldg(bp + j);
+                pk[u][2 * j] = bf_pack(__sinf(w0 * (__uint_as_float(v[4 * j]) + b.x)), __sinf(w0 * (__uint_as_float(v[4 * j + 1]) + b.y)));
+                pk[u][2 * j + 1] = bf_pack(__sinf(w0 * (__uint_as_float(v[4 * j + 2]) + b.z)), __sinf(w0 * (__uint_as_float(v[4 * j + 3]) + b.w)));
+              }
+              if (n == 1) {            // second half: publish K block 5 + u right away
+                uint8_t* kbp = sAct + (5 + u) * kKBBytes;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  sts128(kbp + row_off + (((hsel * 4 + j) << 4) ^ swz), pk[u][4 * j], pk[u][4 * j + 1], pk[u][4 * j + 2], pk[u][4 * j + 3]);
+                fence_async_smem();
+                arrive_leader(&act_ready[5 + u]);
+              }
+            } else {
+              const float4* wp = reinterpret_cast<const float4*>(prm.wsig + col0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 b = __ldg(bp + j), w = __ldg(wp + j);
+                sig = fmaf(__sinf(w0 * (__uint_as_float(v[4 * j]) + b.x)), w.x, sig); sig = fmaf(__sinf(w0 * (__uint_as_float(v[4 * j + 1]) + b.y)), w.y, sig);
+                sig = fmaf(__sinf(w0 * (__uint_as_float(v[4 * j + 2]) + b.z)), w.z, sig); sig = fmaf(__sinf(w0 * (__uint_as_float(v[4 * j + 3]) + b.w)), w.w, sig);
+              }
+            }
+          }
+          if (!last && n == 0) {
+            // in place: K blocks 1.. still feed the second half's MMAs until tfull[1] of THIS layer
+            mbar_wait(&tfull[1], tf_ph[1]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              uint8_t* kbp = sAct + (1 + u) * kKBBytes;
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                sts128(kbp + row_off + (((hsel * 4 + j) << 4) ^ swz), pk[u][4 * j], pk[u][4 * j + 1], pk[u][4 * j + 2], pk[u][4 * j + 3]);
+            }
+            fence_async_smem();
+#pragma unroll
+            for (int u = 0; u < 4; ++u) arrive_leader(&act_ready[1 + u]);
+          }
+        }
+      }
+      // ---- sigma = softplus(w_sigma . h_{L-1} + b): the two warps of a quadrant hold half of the columns each ----
+      if (hsel == 1) sSig[row] = sig;
+      named_bar_sync(1 + q, 64);
+      if (hsel == 0 && p < prm.P) {
+        const float s = sig + sSig[row] + __ldg(prm.bsig);
+        prm.out[p] = s > 20.f ? s : log1pf(expf(s));
+      }
+      named_bar_sync(1 + q, 64);                             // sSig is reused by the next block
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) { fence_after_sync(); tmem_dealloc<true>(tmem_base, 512); }
+}
+
+}  // namespace chain
+}  // namespace bn

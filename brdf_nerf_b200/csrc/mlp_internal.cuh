@@ -23,6 +23,7 @@
 #include <type_traits>
 #include <string.h>
 #include <math.h>
+#include <stdlib.h>
 #include "epilogues.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
@@ -62,6 +63,7 @@ struct bn_mlp {
   int n_blocks;
   int blk_lin0[bn::kMaxBlocks], blk_lin2[bn::kMaxBlocks], blk_head[bn::kMaxBlocks];
   bool synced;
+  bool no_chain;
 };
 
 namespace bn {

@@ -171,3 +171,25 @@ def test_analytic_normals_second_order_backward_fp32(cuda, cfg):
         worst = max(worst, d / (s + 1e-12))
         assert d <= 5e-3 * s + 1e-6, f"{cfg} second-order grad {name}: max diff {d} (scale {s})"
     print(f"{cfg}: worst relative second-order grad error {worst:.2e}")
+
+
+@pytest.mark.parametrize("n", [100, 256, 1000, 70001])
+def test_sigma_chain_bf16(cuda, n, monkeypatch):
+    """Fused density pass (mlp_chain.cuh: all trunk layers + sigma head in one tcgen05 kernel) against
+    the fp32 oracle and against the per-layer bf16 GEMM path (BN_NO_CHAIN=1), ragged point counts."""
+    args, m, state = _models("lambertian", cuda, precision="bf16")
+    x = _pts(n, 11)
+    om = RT.OracleModel(state, args)
+    with torch.no_grad():
+        ref = om.forward(x)["sigma"]
+        sig = m(x.to(cuda), sigma_only=True).cpu()
+    monkeypatch.setenv("BN_NO_CHAIN", "1")
+    args2, m2, _ = _models("lambertian", cuda, precision="bf16")
+    with torch.no_grad():
+        sig_layered = m2(x.to(cuda), sigma_only=True).cpu()
+    e_ref = (sig - ref).abs().max().item()
+    e_lay = (sig_layered - ref).abs().max().item()
+    print(f"n={n}: chain vs fp32 oracle {e_ref:.3e}   per-layer bf16 vs oracle {e_lay:.3e}   chain vs per-layer {(sig - sig_layered).abs().max().item():.3e}")
+    assert torch.isfinite(sig).all()
+    # bf16 activations: same error class as the per-layer bf16 path
+    assert e_ref <= max(2.0 * e_lay, 2e-2), (e_ref, e_lay)
