@@ -590,6 +590,9 @@ EncodeTiledFn encode_fn();
 // 2-D bf16 tensor [rows, cols] with row pitch `ld` elements; box = box_cols x box_rows, 128B swizzle
 int make_map_bf16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld,
                   int box_cols, int box_rows);
+// same with a 64-byte swizzle (boxes of 32 bf16 columns)
+int make_map_bf16_sw(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld,
+                     int box_cols, int box_rows, int swizzle_bytes);
 // 2-D fp32 tensor, same conventions (box_cols * 4 bytes must be 128)
 int make_map_f32(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld,
                  int box_cols, int box_rows);

@@ -533,6 +533,42 @@ static int sigma_chain(bn_mlp* h, const float* params, const float* origins, int
   return rc;
 }
 
+// trunk of a training (or analytic-normal) forward as ONE fused kernel: X3, H_l, C_l of every layer are
+// written for the backward pass, the layer inputs themselves never leave the SM
+static int train_chain(bn_mlp* h, const float* params, const float* origins, int o_stride, const float* dirs, int d_stride,
+                       const float* z, int N, int S, const Ws<__nv_bfloat16>& w, cudaStream_t s) {
+  const bn_mlp_cfg& c = h->cfg;
+  const long long P = (long long)N * S;
+  chain::TrainChainParams prm;
+  for (int l = 0; l < h->L; ++l) {
+    if (int rc = tc::make_map_bf16(&prm.wmap[l], h->Wp[l], h->F, h->Kpad[l], h->Kpad[l], 64, 128)) return rc;
+    if (int rc = tc::stream_map(&prm.hmap[l], w.H[l], P, h->F, w.Hld[l])) return rc;
+    if (int rc = tc::make_map_bf16_sw(&prm.cmap[l], w.C[l], P, h->F, h->F, 32, 32, 64)) return rc;
+    prm.bias[l] = params + c.b_off[l];
+  }
+  if (int rc = tc::stream_map(&prm.x3map, w.X3, P, kEncPad, w.ldx3)) return rc;
+  prm.origins = origins; prm.dirs = dirs; prm.z = z;
+  prm.P = P; prm.o_stride = o_stride; prm.d_stride = d_stride; prm.S = S;
+  prm.L = h->L; prm.skip = h->skip; prm.n_freq = c.n_freq_xyz;
+  const int n_blocks = (int)ceil_div_ll(P, 256);
+  constexpr int smem = chain::chain_smem<true>();
+  BN_CUDA(cudaFuncSetAttribute(chain::train_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * min(n_blocks, h->num_sms / 2));
+  cfg.blockDim = dim3(tc::kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  prof_begin(0, 2.0 * (double)P * ((double)h->E * h->F + (double)(h->L - 2) * h->F * h->F + (double)(h->F + h->E) * h->F), s);
+  BN_CUDA(cudaLaunchKernelEx(&cfg, chain::train_chain_kernel, prm));
+  const int rc = after_launch("train_chain_kernel");
+  prof_end(s);
+  return rc;
+}
+
 template <typename T>
 static int forward_t(bn_mlp* h, const float* params, const float* origins, int o_stride, const float* dirs,
                      int d_stride, const float* z, int N, int S, int flags, float* out, int pitch, void* wsp,
@@ -550,10 +586,19 @@ static int forward_t(bn_mlp* h, const float* params, const float* origins, int o
   HeadPlan hp; int nch;
   if (int rc = build_plan(h, flags, &hp, &nch)) return rc;
   if (!sig_only && pitch < nch) { set_error("bn_mlp_forward: out_pitch %d < %d channels", pitch, nch); return BN_ERR_ARG; }
-  encode_kernel<T><<<(unsigned)ceil_div_ll(P, 128), 128, 0, s>>>(origins, o_stride, dirs, d_stride, z, S, P,
-                                                               c.n_freq_xyz, w.X3, w.ldx3);
-  BN_LAUNCH_CHECK();
-  for (int l = 0; l < L; ++l) {
+  bool chained = false;
+  if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+    if (keep_c && h->F == chain::kF && h->skip >= 1 && !h->no_chain) {
+      if (int rc = train_chain(h, params, origins, o_stride, dirs, d_stride, z, N, S, w, s)) return rc;
+      chained = true;
+    }
+  }
+  if (!chained) {
+    encode_kernel<T><<<(unsigned)ceil_div_ll(P, 128), 128, 0, s>>>(origins, o_stride, dirs, d_stride, z, S, P,
+                                                                 c.n_freq_xyz, w.X3, w.ldx3);
+    BN_LAUNCH_CHECK();
+  }
+  for (int l = 0; l < L && !chained; ++l) {
     const T* A; long long lda;
     if (l == 0 || l == h->skip) { A = w.X3; lda = w.ldx3; } else { A = w.H[l - 1]; lda = w.Hld[l - 1]; }
     // first layer: sin(30 lin), |30 lin| <= 30: the MUFU path is exact to ~2e-6 there, far below

@@ -18,7 +18,7 @@
 //              retired, i.e. for the second half's commit); last layer: dot with w_sigma, softplus.
 //              Before layer 0 they evaluate x = o + d z and the positional encoding into K block 0.
 // Shared memory: 9 K blocks x 16 KB activations ([PE | h], so the skip layer reads K = 576 without a concat)
-// + 4 x 16 KB weight ring.
+// + 5 x 16 KB weight ring (4 in the training variant, which also stages the cosines).
 #pragma once
 #include "gemm_tc.cuh"
 #include "epilogues_tc.cuh"
@@ -30,9 +30,10 @@ using namespace tc;
 
 constexpr int kF = 512;                 // trunk width this kernel is specialised for
 constexpr int kNKB = 1 + kF / 64;       // K blocks of the activation buffer: PE + 8 x 64 features
-constexpr int kWStages = 5;
 constexpr int kKBBytes = 128 * 128;     // one K block of one CTA: 128 rows x 64 bf16
 constexpr int kMaxLayers = 16;
+// weight ring depth: the training variant gives one stage to the cosine staging boxes
+template <bool kTrain> __host__ __device__ constexpr int w_stages() { return kTrain ? 4 : 5; }
 
 struct SigmaChainParams {
   CUtensorMap wmap[kMaxLayers];         // packed W_l [F, Kpad_l] bf16, boxes 64 (K) x 128 (rows)
@@ -44,14 +45,114 @@ struct SigmaChainParams {
   int o_stride, d_stride, S, L, skip, n_freq;
 };
 
-constexpr int sigma_chain_smem() { return kNKB * kKBBytes + kWStages * kKBBytes + 1024 /*sigma exchange*/ + 512 + 1024; }
+// training forward: same chain, and every layer leaves h_l = sin(.) and c_l = w0 cos(.) in HBM for the
+// backward pass (h_l straight out of the activation K blocks in boxes of 32 rows x 64 columns, c_l through
+// one 32 x 32 staging box per epilogue warp); K block 0 (the encoding) goes to X3.
+struct TrainChainParams {
+  CUtensorMap wmap[kMaxLayers];
+  CUtensorMap hmap[kMaxLayers];         // H_l [P, F] (layer skip-1 lives inside X3, pitch 64 + F)
+  CUtensorMap cmap[kMaxLayers];         // C_l [P, F], boxes of 32 columns x 32 rows, 64-byte swizzle
+  CUtensorMap x3map;                    // X3 [P, 64] encoding columns
+  const float* bias[kMaxLayers];
+  const float* origins; const float* dirs; const float* z;
+  long long P;
+  int o_stride, d_stride, S, L, skip, n_freq;
+};
+
+template <bool kTrain> __host__ __device__ constexpr int chain_smem() {
+  return kNKB * kKBBytes + w_stages<kTrain>() * kKBBytes + (kTrain ? 4 * 4096 : 1024) + 512 + 1024;
+}
+constexpr int sigma_chain_smem() { return chain_smem<false>(); }
 
 __device__ __forceinline__ int layer_kb_first(int l, int skip) { return (l == 0 || l == skip) ? 0 : 1; }
 __device__ __forceinline__ int layer_kb_last(int l) { return l == 0 ? 0 : kNKB - 1; }
 // column of K block kb inside the packed weight matrix of layer l
 __device__ __forceinline__ int layer_wcol(int l, int skip, int kb) { return (l == 0) ? 0 : (l == skip ? kb * 64 : (kb - 1) * 64); }
 
+// ---- weight producer: one [128 x 64] tile of W_l per (block, layer, column half, K block) ----
+template <int STAGES>
+__device__ __forceinline__ void chain_producer(const CUtensorMap* wmap, uint8_t* sW, uint64_t* wfull, uint64_t* wempty,
+                                               int crank, int pair0, int npairs, int n_blocks, int L, int skip) {
+  int stage = 0; uint32_t phase = 0;
+  for (int blk = pair0; blk < n_blocks; blk += npairs)
+    for (int l = 0; l < L; ++l)
+      for (int n = 0; n < 2; ++n)
+        for (int kb = layer_kb_first(l, skip); kb <= layer_kb_last(l); ++kb) {
+          mbar_wait(&wempty[stage], phase ^ 1);
+          if (crank == 0) mbar_expect_tx(&wfull[stage], 2 * kKBBytes);
+          tma_load_2d_pair(sW + stage * kKBBytes, &wmap[l], mapa_u32(smem_u32(&wfull[stage]), 0),
+                           layer_wcol(l, skip, kb), n * 256 + crank * 128);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+}
+
+// ---- MMA issuer (leader CTA): layer = two column halves x the layer's K blocks ----
+template <int STAGES>
+__device__ __forceinline__ void chain_mma(uint8_t* sAct, uint8_t* sW, uint64_t* wfull, uint64_t* wempty, uint64_t* tfull,
+                                          uint64_t* tempty, uint64_t* act_ready, uint32_t tmem_base,
+                                          int pair0, int npairs, int n_blocks, int L, int skip) {
+  constexpr uint32_t idesc = make_idesc(256, 256, false);
+  int stage = 0; uint32_t phase = 0;
+  uint32_t te_ph[2] = {0, 0};
+  uint32_t ar_ph = 0;                                   // bit kb: parity the next wait on act_ready[kb] expects
+  for (int blk = pair0; blk < n_blocks; blk += npairs)
+    for (int l = 0; l < L; ++l)
+      for (int n = 0; n < 2; ++n) {
+        mbar_wait(&tempty[n], te_ph[n] ^ 1); te_ph[n] ^= 1;      // the epilogue has read this half out
+        fence_after_sync();
+        bool first = true;
+        for (int kb = layer_kb_first(l, skip); kb <= layer_kb_last(l); ++kb) {
+          if (n == 0 && !(kb == 0 && l > 0)) {          // K block published once per layer (PE: once per block)
+            mbar_wait(&act_ready[kb], (ar_ph >> kb) & 1); ar_ph ^= 1u << kb;
+            fence_after_sync();
+          }
+          mbar_wait(&wfull[stage], phase);
+          fence_after_sync();
+          const uint32_t a_addr = smem_u32(sAct + kb * kKBBytes);
+          const uint32_t b_addr = smem_u32(sW + stage * kKBBytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            umma_bf16_pair(tmem_base + n * 256, make_desc(a_addr + k * 32, 16, 1024), make_desc(b_addr + k * 32, 16, 1024),
+                           idesc, (first && k == 0) ? 0u : 1u);
+          }
+          first = false;
+          umma_commit_pair(&wempty[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_pair(&tfull[n]);
+      }
+}
+
+// x = o + d z (separately rounded, as the reference) and the positional encoding of one point -> one 128-byte
+// row of K block 0
+__device__ __forceinline__ void encode_row(const float* origins, int o_stride, const float* dirs, int d_stride, const float* z,
+                                           int S, long long pc, int n_freq, uint8_t* kb0, uint32_t row_off, uint32_t swz) {
+  const long long r = pc / S;
+  const float zz = z[pc];
+  float x[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) x[a] = __fadd_rn(origins[r * o_stride + a], __fmul_rn(dirs[r * d_stride + a], zz));
+  float e[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) e[i] = 0.f;
+  if (n_freq == 0) { e[0] = x[0]; e[1] = x[1]; e[2] = x[2]; }
+  else {
+#pragma unroll
+    for (int k = 0; k < 10; ++k)
+      if (k < n_freq) {
+        const float f = (float)(1 << k);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { float s, c; sincosf(f * x[a], &s, &c); e[k * 6 + a] = s; e[k * 6 + 3 + a] = c; }
+      }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    sts128(kb0 + row_off + ((j << 4) ^ swz), bf_pack(e[8 * j], e[8 * j + 1]), bf_pack(e[8 * j + 2], e[8 * j + 3]),
+           bf_pack(e[8 * j + 4], e[8 * j + 5]), bf_pack(e[8 * j + 6], e[8 * j + 7]));
+}
+
 __global__ void __launch_bounds__(kThreads, 1) sigma_chain_kernel(const __grid_constant__ SigmaChainParams prm) {
+  constexpr int kWStages = w_stages<false>();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sAct = smem;                                        // [kNKB][128 rows][128 B], swizzled
@@ -86,54 +187,10 @@ __global__ void __launch_bounds__(kThreads, 1) sigma_chain_kernel(const __grid_c
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== weight producer =====================
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int blk = pair0; blk < n_blocks; blk += npairs)
-        for (int l = 0; l < L; ++l)
-          for (int n = 0; n < 2; ++n)
-            for (int kb = layer_kb_first(l, skip); kb <= layer_kb_last(l); ++kb) {
-              mbar_wait(&wempty[stage], phase ^ 1);
-              if (crank == 0) mbar_expect_tx(&wfull[stage], 2 * kKBBytes);
-              tma_load_2d_pair(sW + stage * kKBBytes, &prm.wmap[l], mapa_u32(smem_u32(&wfull[stage]), 0),
-                               layer_wcol(l, skip, kb), n * 256 + crank * 128);
-              if (++stage == kWStages) { stage = 0; phase ^= 1; }
-            }
-    }
+    if (lane == 0) chain_producer<kWStages>(prm.wmap, sW, wfull, wempty, crank, pair0, npairs, n_blocks, L, skip);
   } else if (warp == 1) {
-    // ===================== MMA issuer (leader CTA) =====================
-    if (lane == 0 && crank == 0) {
-      constexpr uint32_t idesc = make_idesc(256, 256, false);
-      int stage = 0; uint32_t phase = 0;
-      uint32_t te_ph[2] = {0, 0};
-      uint32_t ar_ph = 0;                                   // bit kb: parity the next wait on act_ready[kb] expects
-      for (int blk = pair0; blk < n_blocks; blk += npairs)
-        for (int l = 0; l < L; ++l)
-          for (int n = 0; n < 2; ++n) {
-            mbar_wait(&tempty[n], te_ph[n] ^ 1); te_ph[n] ^= 1;      // the epilogue has read this half out
-            fence_after_sync();
-            bool first = true;
-            for (int kb = layer_kb_first(l, skip); kb <= layer_kb_last(l); ++kb) {
-              if (n == 0 && !(kb == 0 && l > 0)) {          // K block published once per layer (PE: once per block)
-                mbar_wait(&act_ready[kb], (ar_ph >> kb) & 1); ar_ph ^= 1u << kb;
-                fence_after_sync();
-              }
-              mbar_wait(&wfull[stage], phase);
-              fence_after_sync();
-              const uint32_t a_addr = smem_u32(sAct + kb * kKBBytes);
-              const uint32_t b_addr = smem_u32(sW + stage * kKBBytes);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                umma_bf16_pair(tmem_base + n * 256, make_desc(a_addr + k * 32, 16, 1024), make_desc(b_addr + k * 32, 16, 1024),
-                               idesc, (first && k == 0) ? 0u : 1u);
-              }
-              first = false;
-              umma_commit_pair(&wempty[stage]);
-              if (++stage == kWStages) { stage = 0; phase ^= 1; }
-            }
-            umma_commit_pair(&tfull[n]);
-          }
-    }
+    if (lane == 0 && crank == 0)
+      chain_mma<kWStages>(sAct, sW, wfull, wempty, tfull, tempty, act_ready, tmem_base, pair0, npairs, n_blocks, L, skip);
   } else if (warp >= 4) {
     // ===================== positional encoding + epilogues =====================
     const int q = warp & 3, hsel = (warp - 4) >> 2;
@@ -149,29 +206,8 @@ __global__ void __launch_bounds__(kThreads, 1) sigma_chain_kernel(const __grid_c
       const long long p = (long long)blk * 256 + crank * 128 + row;
       // ---- x = o + d z, encoding into K block 0 (hsel 0 warps; one row per thread) ----
       if (hsel == 0) {
-        const long long pc = p < prm.P ? p : prm.P - 1;
-        const long long r = pc / prm.S;
-        const float zz = prm.z[pc];
-        float x[3];
-#pragma unroll
-        for (int a = 0; a < 3; ++a) x[a] = __fadd_rn(prm.origins[r * prm.o_stride + a], __fmul_rn(prm.dirs[r * prm.d_stride + a], zz));
-        float e[64];
-#pragma unroll
-        for (int i = 0; i < 64; ++i) e[i] = 0.f;
-        if (prm.n_freq == 0) { e[0] = x[0]; e[1] = x[1]; e[2] = x[2]; }
-        else {
-#pragma unroll
-          for (int k = 0; k < 10; ++k)
-            if (k < prm.n_freq) {
-              const float f = (float)(1 << k);
-#pragma unroll
-              for (int a = 0; a < 3; ++a) { float s, c; sincosf(f * x[a], &s, &c); e[k * 6 + a] = s; e[k * 6 + 3 + a] = c; }
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          sts128(sAct + row_off + ((j << 4) ^ swz), bf_pack(e[8 * j], e[8 * j + 1]), bf_pack(e[8 * j + 2], e[8 * j + 3]),
-                 bf_pack(e[8 * j + 4], e[8 * j + 5]), bf_pack(e[8 * j + 6], e[8 * j + 7]));
+        encode_row(prm.origins, prm.o_stride, prm.dirs, prm.d_stride, prm.z, prm.S, p < prm.P ? p : prm.P - 1, prm.n_freq,
+                   sAct, row_off, swz);
         fence_async_smem();
       }
       arrive_leader(&act_ready[0]);
@@ -246,6 +282,158 @@ __global__ void __launch_bounds__(kThreads, 1) sigma_chain_kernel(const __grid_c
       }
       named_bar_sync(1 + q, 64);                             // sSig is reused by the next block
     }
+  }
+  fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) { fence_after_sync(); tmem_dealloc<true>(tmem_base, 512); }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Training forward of the trunk: the same chain; every layer's h_l and c_l = w0 cos(.) are written to HBM.
+__global__ void __launch_bounds__(kThreads, 1) train_chain_kernel(const __grid_constant__ TrainChainParams prm) {
+  constexpr int kWStages = w_stages<true>();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sAct = smem;
+  uint8_t* sW = sAct + kNKB * kKBBytes;
+  uint8_t* sC = sW + kWStages * kKBBytes;                      // [8 warps][32 rows][64 B] cosine staging boxes
+  uint64_t* wfull = reinterpret_cast<uint64_t*>(sC + 4 * 4096);
+  uint64_t* wempty = wfull + kWStages;
+  uint64_t* tfull = wempty + kWStages;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* act_ready = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(act_ready + kNKB);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int crank = (int)cluster_ctarank();
+  const int pair0 = (int)cluster_id_x(), npairs = (int)cluster_nctaid_x();
+  const int n_blocks = (int)((prm.P + 255) / 256);
+  const int L = prm.L, skip = prm.skip;
+
+  if (warp == 0 && lane == 0)
+    for (int l = 0; l < L; ++l) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&prm.wmap[l])) : "memory");
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kWStages; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 16); }
+    for (int s = 0; s < kNKB; ++s) mbar_init(&act_ready[s], 16);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) tmem_alloc<true>(tmem_slot, 512);
+  fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) chain_producer<kWStages>(prm.wmap, sW, wfull, wempty, crank, pair0, npairs, n_blocks, L, skip);
+  } else if (warp == 1) {
+    if (lane == 0 && crank == 0)
+      chain_mma<kWStages>(sAct, sW, wfull, wempty, tfull, tempty, act_ready, tmem_base, pair0, npairs, n_blocks, L, skip);
+  } else if (warp >= 4) {
+    const int q = warp & 3, hsel = (warp - 4) >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t row_off = row * 128, swz = (lane & 7) << 4;
+    const uint32_t t_lane = (uint32_t)(q * 32) << 16;
+    const bool leader = hsel == 0 && lane == 0;              // issues the quadrant's h_l stores (64-column boxes)
+    // cosines leave through one box per WARP (32 rows x 32 columns, 64-byte swizzle): no cross-warp hand-shake
+    uint8_t* cbox = sC + (q * 2 + hsel) * 2048;
+    const uint32_t crow_off = lane * 64, cswz = ((lane >> 1) & 3) << 4;
+    uint32_t tf_ph[2] = {0, 0};
+    auto arrive_leader = [&](uint64_t* bar) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(bar), 0));
+    };
+    for (int blk = pair0; blk < n_blocks; blk += npairs) {
+      const int grow0 = blk * 256 + crank * 128 + q * 32;      // first global row of this quadrant
+      const long long p = (long long)grow0 + lane;
+      // ---- encoding -> K block 0 -> X3 ----
+      if (hsel == 0) {
+        if (lane == 0) bulk_wait_read0();                      // this warp's earlier stores have left shared memory
+        __syncwarp();
+        encode_row(prm.origins, prm.o_stride, prm.dirs, prm.d_stride, prm.z, prm.S, p < prm.P ? p : prm.P - 1, prm.n_freq,
+                   sAct, row_off, swz);
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) { tma_store_2d(&prm.x3map, sAct + q * 4096, 0, grow0); bulk_commit(); }
+      }
+      arrive_leader(&act_ready[0]);
+      for (int l = 0; l < L; ++l) {
+        const float w0 = l == 0 ? 30.0f : 1.0f;
+        const bool last = l == L - 1;
+        for (int n = 0; n < 2; ++n) {
+          mbar_wait(&tfull[n], tf_ph[n]); tf_ph[n] ^= 1;
+          fence_after_sync();
+          uint32_t pk[4][16];
+          uint32_t va[32], vb[32];
+          const uint32_t tbase = tmem_base + t_lane + n * 256 + hsel * 32;
+          tmem_ld32_issue(tbase, va);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            tmem_wait_ld();
+            uint32_t (&v)[32] = (u & 1) ? vb : va;
+            if (u < 3) tmem_ld32_issue(tbase + (u + 1) * 64, (u & 1) ? va : vb);
+            else { fence_before_sync(); arrive_leader(&tempty[n]); }
+            const int col0 = n * 256 + u * 64 + hsel * 32;
+            const float4* bp = reinterpret_cast<const float4*>(prm.bias[l] + col0);
+            uint32_t pc[16];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = __ldg(bp + j);
+              const float a0 = w0 * (__uint_as_float(v[4 * j]) + b.x), a1 = w0 * (__uint_as_float(v[4 * j + 1]) + b.y);
+              const float a2 = w0 * (__uint_as_float(v[4 * j + 2]) + b.z), a3 = w0 * (__uint_as_float(v[4 * j + 3]) + b.w);
+              pk[u][2 * j] = bf_pack(__sinf(a0), __sinf(a1));
+              pk[u][2 * j + 1] = bf_pack(__sinf(a2), __sinf(a3));
+              pc[2 * j] = bf_pack(w0 * __cosf(a0), w0 * __cosf(a1));
+              pc[2 * j + 1] = bf_pack(w0 * __cosf(a2), w0 * __cosf(a3));
+            }
+            if (lane == 0) bulk_wait_read0();                // this warp's previous boxes were read out by the TMA
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              sts128(cbox + crow_off + ((j << 4) ^ cswz), pc[4 * j], pc[4 * j + 1], pc[4 * j + 2], pc[4 * j + 3]);
+            if (n == 1) {                                    // every MMA of this layer has retired: publish K block 5+u now
+              uint8_t* kbp = sAct + (5 + u) * kKBBytes;
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                sts128(kbp + row_off + (((hsel * 4 + j) << 4) ^ swz), pk[u][4 * j], pk[u][4 * j + 1], pk[u][4 * j + 2], pk[u][4 * j + 3]);
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) { tma_store_2d(&prm.cmap[l], cbox, col0, grow0); bulk_commit(); }
+            if (n == 1 && !last) arrive_leader(&act_ready[5 + u]);
+          }
+          if (n == 0) {
+            // in place: K blocks 1..4 still feed the second half's MMAs until tfull[1] of THIS layer
+            mbar_wait(&tfull[1], tf_ph[1]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              uint8_t* kbp = sAct + (1 + u) * kKBBytes;
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                sts128(kbp + row_off + (((hsel * 4 + j) << 4) ^ swz), pk[u][4 * j], pk[u][4 * j + 1], pk[u][4 * j + 2], pk[u][4 * j + 3]);
+            }
+            fence_async_smem();
+            if (!last) {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) arrive_leader(&act_ready[1 + u]);
+            }
+          }
+          // h_l of this half: both warps of the quadrant have written their columns -> four 64-column boxes.
+          // (The leader waits for its stores to be read out at its next unit, and the next barrier of this kind
+          // precedes every overwrite of these K blocks by the other warp.)
+          named_bar_sync(1 + q, 64);
+          if (leader) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              tma_store_2d(&prm.hmap[l], sAct + (1 + n * 4 + u) * kKBBytes + q * 4096, n * 256 + u * 64, grow0);
+            bulk_commit();
+          }
+        }
+      }
+    }
+    if (lane == 0) bulk_wait0();
   }
   fence_before_sync();
   __syncthreads();

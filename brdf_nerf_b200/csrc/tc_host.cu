@@ -22,6 +22,11 @@ EncodeTiledFn encode_fn() {
 
 int make_map_bf16(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld,
                   int box_cols, int box_rows) {
+  return make_map_bf16_sw(map, base, rows, cols, ld, box_cols, box_rows, 128);
+}
+
+int make_map_bf16_sw(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld,
+                     int box_cols, int box_rows, int swizzle_bytes) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return BN_ERR_CUDA;
   if ((reinterpret_cast<uintptr_t>(base) & 15) || ((ld * 2) & 15)) {
@@ -33,7 +38,8 @@ int make_map_bf16(CUtensorMap* map, const void* base, long long rows, long long 
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with %d (rows=%lld cols=%lld ld=%lld)", (int)r, rows, cols, ld); return BN_ERR_CUDA; }
   return BN_OK;
