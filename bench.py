@@ -30,11 +30,12 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 RAYS_PER_GPU = 1024
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant instantiation (training-forward trunk
-# layer, EpiSinT<true>, P = 131072, K = N = 512) from profiles/r01c_ncu_full_gemm_pair.csv; algorithmic: 402.7 MB
-NCU_GEMM_DRAM_BYTES_PER_LAUNCH = 344.4e6
-NCU_GEMM_TRAFFIC_NOTE = ("ncu --set full, gemm_tc_kernel<256,5,tn,pair,EpiSinT<1>>: 134.8 MB read + 209.6 MB written per launch "
-                         "(algorithmic 128 MiB read + 256 MiB written; the tail of the writes is still in L2 when the kernel ends)")
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel of the step (trunk dgrad GEMM,
+# gemm_tc_kernel<256,5,tn,pair,EpiDgradT<mul>>, P = 131072, K = N = 512) from profiles/r01c_ncu_full_gemm_pair.csv
+NCU_GEMM_DRAM_BYTES_PER_LAUNCH = 370.6e6
+NCU_GEMM_TRAFFIC_NOTE = ("ncu --set full, trunk dgrad GEMM: 269.0 MB read + 101.6 MB written per launch (algorithmic 256 MiB read "
+                         "[dZ + cos mask] + 128 MiB written; the tail of the writes is still in L2 when the kernel ends). "
+                         "train_chain_kernel (profiles/r01d): 27 MB read, 2.11 GB written = algorithmic 2.15 GB")
 METRIC = "train rays/s (SpS-BRDF-NeRF, 1/2/4/8 B200); MLP tensor-pipe %; composite GB/s"
 
 
@@ -193,7 +194,9 @@ def run_ours(opts):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1) / opts.steps
-    launches = (lib.bn_launch_count() - lc0)
+    # kernels of this library inside the timed region: eager launches counted by the library itself, plus the
+    # kernel nodes every CUDA-graph replay executes (counted once, at capture time)
+    launches = (lib.bn_launch_count() - lc0) + opts.steps * getattr(trainer, "graph_launches", 0)
     clk = clocks.stop() if clocks else None
     # ---- end to end: pinned host batch -> device every step, loss read back every step ---------
     barrier()
@@ -229,7 +232,7 @@ def run_ours(opts):
         alg = mlp_flops_per_ray(args, args.n_samples, args.n_samples + args.guided_samples) * RAYS_PER_GPU
         gemm_flops = (work[0] + work[1]) / nprof
         achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-        roof = {"bound": "tensor", "kernel": "bn::tc::gemm_tc_kernel (all PE+SIREN fwd/dgrad/wgrad GEMMs of a step)",
+        roof = {"bound": "tensor", "kernel": "bn::tc::gemm_tc_kernel + bn::chain::*_chain_kernel (all PE+SIREN fwd/dgrad/wgrad tcgen05 launches of a step)",
                 "achieved": achieved, "peak": peaks["tf_sust"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_sust"],
                 "peak_kind": f"{peaks['src']} sustained bf16 (kernel timed inside a long step)",
                 "traffic": NCU_GEMM_DRAM_BYTES_PER_LAUNCH, "traffic_note": NCU_GEMM_TRAFFIC_NOTE,

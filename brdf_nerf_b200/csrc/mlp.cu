@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(256) heads_bwd_kernel(HeadPlan hp, const float
         Pack<T, 8>::store(DPRE + pq[q] * 64 + lane * 8, t);
       }
     }
-    if constexpr (kLight) continue;
+    if constexpr (!kLight) {
     for (int i = lane * 8; i < F; i += 256) {
       float ws[8]; load8<float>(params + hp.wsig + i, ws);
       float g[kQP][8];
@@ -322,6 +322,7 @@ __global__ void __launch_bounds__(256) heads_bwd_kernel(HeadPlan hp, const float
         for (int j = 0; j < 8; ++j) atomicAdd(&s_red[b * hp.HH + i + j], cs[j]);
       }
     }
+    }  // !kLight
   }
   if (lane == 0) {
 #pragma unroll

@@ -20,6 +20,7 @@ from typing import Optional
 
 import torch
 
+from . import _lib as L
 from . import ops
 from . import rendering as R
 from .synth import RayBatch
@@ -78,6 +79,7 @@ class Trainer:
         self._static: Optional[RayBatch] = None
         self._loss = None
         self._kw = None
+        self.graph_launches = 0
 
     # one optimisation step; `batch` tensors must already live on the model's device
     def _step_impl(self, batch: RayBatch, draws, kw):
@@ -123,9 +125,12 @@ class Trainer:
                     self._step_impl(self._static, None, kw)
             torch.cuda.current_stream().wait_stream(side)
             self._graph = torch.cuda.CUDAGraph()
+            lib = L.load()
+            lc0 = lib.bn_launch_count()
             with torch.cuda.graph(self._graph):
                 self.model.sync_weights(force=True)
                 self._loss = self._step_impl(self._static, None, kw)
+            self.graph_launches = int(lib.bn_launch_count() - lc0)     # library kernels replayed by every graph launch
             self._kw = dict(kw)
         for dst, src in zip((self._static.rays, self._static.rgbs, self._static.valid_depth,
                              self._static.target_depths, self._static.target_std),
