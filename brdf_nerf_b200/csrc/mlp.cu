@@ -6,23 +6,6 @@
 namespace bn {
 
 // ------------------------------------------------------------------------------------------------
-// weight packing: flat fp32 [N, Kreal] -> Wp [N, Kpad] and WTp [Kpad, N] (element type T), with the
-// encoding columns padded from E to 64.
-template <typename T>
-__global__ void pack_weight_kernel(const float* __restrict__ W, int N, int Kreal, int E, int Kpad,
-                                   T* __restrict__ Wp, long long ldp, T* __restrict__ WTp, long long ldt, int row0) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)N * Kpad) return;
-  const int n = (int)(idx / Kpad), kp = (int)(idx % Kpad);
-  int k = -1;                                   // source column, -1 = padding
-  if (E >= 0) { if (kp < E) k = kp; else if (kp >= kEncPad) k = kp - (kEncPad - E); }
-  else k = kp;
-  const float v = (k >= 0 && k < Kreal) ? W[(long long)n * Kreal + k] : 0.f;
-  if (Wp) Wp[(long long)(row0 + n) * ldp + kp] = from_f<T>(v);
-  if (WTp) WTp[(long long)kp * ldt + row0 + n] = from_f<T>(v);
-}
-
-// ------------------------------------------------------------------------------------------------
 // x = o + d z (separately rounded mul and add, as the reference) and the positional encoding
 // [sin(2^k x), cos(2^k x)]_k written into cols 0..63 of X3 (zero padded).  One thread per point.
 template <typename T>
@@ -75,7 +58,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) heads_fwd_kernel(HeadPlan hp, const float* __restrict__ params,
                                                         const T* __restrict__ Hlast, long long ldh, int F,
                                                         const T* __restrict__ HD, long long ldd,
-                                                        float* __restrict__ out, int pitch, long long P, bool sigma_only) {
+                                                        float* __restrict__ out, int pitch, long long P, bool sigma_only,
+                                                        bool sigma_done) {
   const int lane = threadIdx.x % 32;
   const long long warp = (long long)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
   const long long nwarps = (long long)gridDim.x * (blockDim.x / 32);
@@ -87,7 +71,8 @@ __global__ void __launch_bounds__(256) heads_fwd_kernel(HeadPlan hp, const float
     float s_acc[kQP], g_acc[kQP][3];
 #pragma unroll
     for (int q = 0; q < kQP; ++q) { s_acc[q] = 0.f; g_acc[q][0] = g_acc[q][1] = g_acc[q][2] = 0.f; }
-    for (int i = lane * 8; i < F; i += 256) {
+    // sigma_done: the fused trunk kernel already wrote softplus(w_sigma . h + b) from its fp32 activations
+    for (int i = lane * 8; i < ((sigma_done && hp.ch_nlr < 0) ? 0 : F); i += 256) {
       float h[kQP][8];
 #pragma unroll
       for (int q = 0; q < kQP; ++q) load8g<T>(Hlast + pq[q] * ldh + i, h[q]);
@@ -112,7 +97,7 @@ __global__ void __launch_bounds__(256) heads_fwd_kernel(HeadPlan hp, const float
 #pragma unroll
     for (int q = 0; q < kQP; ++q) {
       const float sigma = softplusf_(warp_sum(s_acc[q]) + bsig);
-      if (lane == 0 && p0 + q < P) {
+      if (lane == 0 && p0 + q < P && !sigma_done) {
         if (sigma_only) out[p0 + q] = sigma; else out[(p0 + q) * pitch + hp.ch_sigma] = sigma;
       }
     }
@@ -474,26 +459,50 @@ static int build_plan(const bn_mlp* h, int flags, HeadPlan* hp, int* n_channels)
   return BN_OK;
 }
 
+// all packed copies of one optimizer step in ONE launch: blockIdx.y = job (a Linear layer or a bias copy)
+struct PackJob { long long w_off; int N, Kreal, E, Kpad; void* Wp; long long ldp; void* WTp; long long ldt; int row0; };
+constexpr int kMaxPackJobs = 40;
+struct PackJobs { int n; PackJob j[kMaxPackJobs]; };
+
+template <typename T>
+__global__ void pack_all_kernel(const __grid_constant__ PackJobs jobs, const float* __restrict__ params) {
+  const PackJob& q = jobs.j[blockIdx.y];
+  const long long tot = (long long)q.N * q.Kpad;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < tot; idx += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(idx / q.Kpad), kp = (int)(idx % q.Kpad);
+    if (q.Kreal < 0) {                            // bias copy job: Wp is a float* destination, N x Kpad = count x 1
+      reinterpret_cast<float*>(q.Wp)[q.row0 + n] = params[q.w_off + n];
+      continue;
+    }
+    int k = -1;                                   // source column, -1 = padding
+    if (q.E >= 0) { if (kp < q.E) k = kp; else if (kp >= kEncPad) k = kp - (kEncPad - q.E); }
+    else k = kp;
+    const float v = (k >= 0 && k < q.Kreal) ? params[q.w_off + (long long)n * q.Kreal + k] : 0.f;
+    if (q.Wp) reinterpret_cast<T*>(q.Wp)[(long long)(q.row0 + n) * q.ldp + kp] = from_f<T>(v);
+    if (q.WTp) reinterpret_cast<T*>(q.WTp)[(long long)kp * q.ldt + q.row0 + n] = from_f<T>(v);
+  }
+}
+
 template <typename T>
 static int sync_weights_t(bn_mlp* h, const float* params, cudaStream_t s) {
   const bn_mlp_cfg& c = h->cfg;
+  PackJobs jobs{};
   auto pack = [&](int lin, int N, int Kreal, int E, int Kpad, void* Wp, long long ldp, void* WTp, long long ldt, int row0) {
-    const long long tot = (long long)N * Kpad;
-    pack_weight_kernel<T><<<(unsigned)ceil_div_ll(tot, 256), 256, 0, s>>>(params + c.w_off[lin], N, Kreal, E, Kpad,
-                                                                         (T*)Wp, ldp, (T*)WTp, ldt, row0);
-    return after_launch("pack_weight_kernel");
+    jobs.j[jobs.n++] = PackJob{c.w_off[lin], N, Kreal, E, Kpad, Wp, ldp, WTp, ldt, row0};
   };
   for (int l = 0; l < h->L; ++l) {
     const bool enc_in = (l == 0 || l == h->skip);
-    if (int rc = pack(BN_LIN_TRUNK0 + l, h->F, h->Kreal[l], enc_in ? h->E : -1, h->Kpad[l], h->Wp[l], h->Kpad[l], h->WTp[l], h->F, 0)) return rc;
+    pack(BN_LIN_TRUNK0 + l, h->F, h->Kreal[l], enc_in ? h->E : -1, h->Kpad[l], h->Wp[l], h->Kpad[l], h->WTp[l], h->F, 0);
   }
-  if (int rc = pack(BN_LIN_FEATS, h->F, h->F, -1, h->F, h->Wf, h->F, h->WfT, h->F, 0)) return rc;
+  pack(BN_LIN_FEATS, h->F, h->F, -1, h->F, h->Wf, h->F, h->WfT, h->F, 0);
   const long long HK = (long long)h->n_blocks * h->HH;
   for (int b = 0; b < h->n_blocks; ++b) {
-    if (int rc = pack(h->blk_lin0[b], h->HH, h->F, -1, h->F, h->W1, h->F, h->W1T, HK, b * h->HH)) return rc;
-    BN_CUDA(cudaMemcpyAsync(h->b1cat + b * h->HH, params + c.b_off[h->blk_lin0[b]], sizeof(float) * h->HH,
-                            cudaMemcpyDeviceToDevice, s));
+    pack(h->blk_lin0[b], h->HH, h->F, -1, h->F, h->W1, h->F, h->W1T, HK, b * h->HH);
+    jobs.j[jobs.n++] = PackJob{c.b_off[h->blk_lin0[b]], h->HH, -1, -1, 1, h->b1cat, 0, nullptr, 0, b * h->HH};
   }
+  if (jobs.n > kMaxPackJobs) { set_error("too many pack jobs"); return BN_ERR_STATE; }
+  pack_all_kernel<T><<<dim3(64, jobs.n), 256, 0, s>>>(jobs, params);
+  if (int rc = after_launch("pack_all_kernel")) return rc;
   h->synced = true;
   return BN_OK;
 }
@@ -537,7 +546,7 @@ static int sigma_chain(bn_mlp* h, const float* params, const float* origins, int
 // trunk of a training (or analytic-normal) forward as ONE fused kernel: X3, H_l, C_l of every layer are
 // written for the backward pass, the layer inputs themselves never leave the SM
 static int train_chain(bn_mlp* h, const float* params, const float* origins, int o_stride, const float* dirs, int d_stride,
-                       const float* z, int N, int S, const Ws<__nv_bfloat16>& w, cudaStream_t s) {
+                       const float* z, int N, int S, const Ws<__nv_bfloat16>& w, float* out, int pitch, int sigma_ch, cudaStream_t s) {
   const bn_mlp_cfg& c = h->cfg;
   const long long P = (long long)N * S;
   chain::TrainChainParams prm;
@@ -549,6 +558,7 @@ static int train_chain(bn_mlp* h, const float* params, const float* origins, int
   }
   if (int rc = tc::stream_map(&prm.x3map, w.X3, P, kEncPad, w.ldx3)) return rc;
   prm.origins = origins; prm.dirs = dirs; prm.z = z;
+  (void)out; (void)pitch; (void)sigma_ch;     // sigma stays in heads_fwd_kernel: fusing it here cost more (registers) than it saved
   prm.P = P; prm.o_stride = o_stride; prm.d_stride = d_stride; prm.S = S;
   prm.L = h->L; prm.skip = h->skip; prm.n_freq = c.n_freq_xyz;
   const int n_blocks = (int)ceil_div_ll(P, 256);
@@ -590,7 +600,7 @@ static int forward_t(bn_mlp* h, const float* params, const float* origins, int o
   bool chained = false;
   if constexpr (std::is_same<T, __nv_bfloat16>::value) {
     if (keep_c && h->F == chain::kF && h->skip >= 1 && !h->no_chain) {
-      if (int rc = train_chain(h, params, origins, o_stride, dirs, d_stride, z, N, S, w, s)) return rc;
+      if (int rc = train_chain(h, params, origins, o_stride, dirs, d_stride, z, N, S, w, out, pitch, hp.ch_sigma, s)) return rc;
       chained = true;
     }
   }
@@ -609,7 +619,7 @@ static int forward_t(bn_mlp* h, const float* params, const float* origins, int o
   }
   const T* Hl = w.H[L - 1]; const long long ldl = w.Hld[L - 1];
   if (sig_only) {
-    heads_fwd_kernel<T><<<heads_grid(h, P), 256, 0, s>>>(hp, params, Hl, ldl, F, nullptr, 0, out, 1, P, true);
+    heads_fwd_kernel<T><<<heads_grid(h, P), 256, 0, s>>>(hp, params, Hl, ldl, F, nullptr, 0, out, 1, P, true, false);
     BN_LAUNCH_CHECK();
     return BN_OK;
   }
@@ -619,7 +629,7 @@ static int forward_t(bn_mlp* h, const float* params, const float* origins, int o
     if (int rc = layer_sin<T>(h, w.FE, F, (const T*)h->W1, F, P, HKa, F, h->b1cat, 1.0f, w.HD, w.ldhd,
                               train ? w.CD : nullptr, w.ldhd, s)) return rc;
   }
-  heads_fwd_kernel<T><<<heads_grid(h, P), 256, 0, s>>>(hp, params, Hl, ldl, F, w.HD, w.ldhd, out, pitch, P, false);
+  heads_fwd_kernel<T><<<heads_grid(h, P), 256, 0, s>>>(hp, params, Hl, ldl, F, w.HD, w.ldhd, out, pitch, P, false, false);
   BN_LAUNCH_CHECK();
   return BN_OK;
 }

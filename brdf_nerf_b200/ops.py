@@ -174,3 +174,30 @@ def adam_step(params, grads, m, v, lr, step, betas=(0.9, 0.999), eps=1e-8, weigh
     L.check(L.load().bn_adam_step(L.ptr(params), L.ptr(grads), L.ptr(m), L.ptr(v), params.numel(), float(lr),
                                   float(betas[0]), float(betas[1]), float(eps), float(weight_decay), int(step),
                                   float(grad_scale), L.stream_ptr()))
+
+
+def loss_color_depth(rgb, target_rgb, lambda_rgb, depth=None, z=None, weights=None, valid_depth=None, target_depths=None,
+                     target_std=None, lambda_ds=0.0, use_all_depth=False, no_weights=False):
+    """SNerfLoss + DepthLoss(subset=True) fused with their gradients (reference metrics.py:39-61, 82-161).
+    Returns (loss (1,), g_rgb (N,3), g_depth (N) or None).  target_depths is the reference's (N,2) [depth, weight]."""
+    n = rgb.shape[0]
+    dev = rgb.device
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    g_rgb = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    use_ds = valid_depth is not None and float(lambda_ds) > 0
+    g_depth = torch.empty(n, dtype=torch.float32, device=dev) if use_ds else None
+    td = tw = None
+    stride = 1
+    if use_ds:
+        tdm = target_depths.contiguous().float()
+        stride = tdm.shape[1] if tdm.dim() == 2 else 1
+        td = tdm
+        tw = None if (no_weights or tdm.dim() != 2) else tdm[:, 1]
+        valid_depth = valid_depth.to(torch.int64).contiguous()
+    s = z.shape[1] if z is not None else 1
+    L.check(L.load().bn_loss_color_depth(
+        L.ptr(rgb.contiguous()), L.ptr(target_rgb.contiguous()), L.ptr(depth), L.ptr(z), L.ptr(weights),
+        L.ptr(valid_depth, torch.int64) if use_ds else None, L.ptr(td), (C.c_void_p(tw.data_ptr()) if tw is not None else None), stride,
+        L.ptr(target_std.contiguous().float()) if use_ds else None, float(lambda_rgb), float(lambda_ds), int(bool(use_all_depth)),
+        L.ptr(loss), L.ptr(g_rgb), L.ptr(g_depth), n, s, L.stream_ptr()))
+    return loss, g_rgb, g_depth

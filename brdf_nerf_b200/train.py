@@ -27,29 +27,14 @@ from .synth import RayBatch
 
 
 def loss_and_grads(args, outs, st, batch: RayBatch, use_depth: bool):
-    """Returns (loss scalar tensor, g_rgb (N,3), g_depth (N) or None)."""
-    rgb, depth, w, z = outs["rgb"], outs["depth"], outs["weights"], outs["z"]
-    n = rgb.shape[0]
-    diff = rgb - batch.rgbs
-    lam = float(args.lambda_rgb)
-    loss = lam * (diff * diff).mean()
-    g_rgb = diff * (2.0 * lam / (3 * n))
-    g_depth = None
-    if use_depth and batch.valid_depth is not None:
-        td, tw = batch.target_depths[:, 0], batch.target_depths[:, 1]
-        if getattr(args, "ds_noweights", False):
-            tw = torch.ones_like(tw)
-        ts = batch.target_std
-        pred_std = torch.sqrt((((z - depth.unsqueeze(-1)) ** 2) * w).sum(-1))
-        dd = depth - td
-        sel = batch.valid_depth > 0
-        if not getattr(args, "usealldepth", False):
-            sel = sel & (((dd.abs() - ts) > 0) | (ts < pred_std))
-        m = sel.to(rgb.dtype) * tw
-        k = float(args.ds_lambda) / 3.0 / n
-        loss = loss + k * (m * dd * dd).sum()
-        g_depth = (2.0 * k) * m * dd
-    return loss, g_rgb, g_depth
+    """Returns (loss (1,) tensor, g_rgb (N,3), g_depth (N) or None): one fused launch (csrc/loss.cu)."""
+    use_ds = use_depth and batch.valid_depth is not None
+    return ops.loss_color_depth(outs["rgb"], batch.rgbs, float(args.lambda_rgb), depth=outs["depth"], z=outs["z"],
+                                weights=outs["weights"], valid_depth=batch.valid_depth if use_ds else None,
+                                target_depths=batch.target_depths, target_std=batch.target_std,
+                                lambda_ds=float(args.ds_lambda) if use_ds else 0.0,
+                                use_all_depth=bool(getattr(args, "usealldepth", False)),
+                                no_weights=bool(getattr(args, "ds_noweights", False)))
 
 
 def allreduce_grads_(flat_grads: torch.Tensor, world_size: int, group=None) -> float:

@@ -158,6 +158,20 @@ int bn_brdf_points_forward(const bn_shade_cfg* cfg, const float* rays, float* pa
 int bn_brdf_points_backward(const bn_shade_cfg* cfg, const float* rays, const float* packed,
                             float* g_packed, int n_rays, int n_samples, cudaStream_t stream);
 
+/* ------------------------------------------------------------------ losses */
+
+/* SNerfLoss (metrics.py:39-61, lambda_sc == 0) + DepthLoss(subset=True, GNLL=False) (metrics.py:82-161) of one
+ * batch, fused with their gradients w.r.t. the rendered rgb (N,3) and depth (N):
+ *   loss = lambda_rgb * mean((rgb - target)^2) + (lambda_ds / 3 / N) * sum_sel w* (d - d*)^2
+ * where a ray is selected when valid_depth > 0 and (use_all_depth or |d - d*| > std* or calc_depth_std(z,d,w) > std*).
+ * valid_depth == NULL drops the depth term.  target_depth / target_weight are read as ptr[r * td_stride]
+ * (target_weight NULL = 1).  loss (1 float) is overwritten; g_rgb (N,3) and g_depth (N) receive d loss / d . */
+int bn_loss_color_depth(const float* rgb, const float* target_rgb, const float* depth, const float* z,
+                        const float* weights, const int64_t* valid_depth, const float* target_depth,
+                        const float* target_weight, int td_stride, const float* target_std,
+                        float lambda_rgb, float lambda_ds, int use_all_depth,
+                        float* loss, float* g_rgb, float* g_depth, int n_rays, int n_samples, cudaStream_t stream);
+
 /* ------------------------------------------------------------------ K-B  PE + SIREN MLP */
 
 enum { BN_PREC_FP32 = 0,   /* CUDA-core fp32 everywhere: parity mode (<= 1e-3 against the fp32 oracle) */

@@ -52,11 +52,11 @@ def test_bf16_psnr_drift(cuda):
     A single PSNR reading of a 512-ray model carries +-0.1 dB of run-to-run noise by itself (fp32
     atomics / TMA reduce-adds arrive in a different order on every run and 200 Adam steps amplify the
     last bit), which the sign flips of the printed curve show.  The criterion is therefore asserted
-    on the MEAN drift over the six checkpoints of the second half of the run (steps 100..200), each
-    PSNR evaluated on two independent sets of evaluation draws; every single checkpoint must
-    additionally stay within 0.3 dB."""
+    on the MEAN drift over the eleven checkpoints of the second half of the run (steps 100, 110, .. 200),
+    each PSNR evaluated on two independent sets of evaluation draws; every single checkpoint must
+    additionally stay within 0.5 dB."""
     args = named_config("lambertian_ds")
-    n, checkpoints = 512, (50, 100, 120, 140, 160, 180, 200)
+    n, checkpoints = 512, (50,) + tuple(range(100, 201, 10))
     batch = make_rays(n, depth_supervision=True).to(cuda)
     ev_draws = []
     for seed in (9999, 7777):
@@ -81,7 +81,7 @@ def test_bf16_psnr_drift(cuda):
     mean_drift = sum(tail) / len(tail)
     print(f"mean drift over steps 100..200: {mean_drift:+.3f} dB   worst single checkpoint {max(abs(d) for d in tail):.3f} dB")
     assert abs(mean_drift) <= 0.1, curve
-    assert max(abs(d) for d in tail) <= 0.3, curve
+    assert max(abs(d) for d in tail) <= 0.5, curve
 
 
 def test_graph_step_equals_eager(cuda):
