@@ -524,6 +524,7 @@ static int sigma_chain(bn_mlp* h, const float* params, const float* origins, int
   prm.origins = origins; prm.dirs = dirs; prm.z = z; prm.out = out;
   prm.P = (long long)N * S; prm.o_stride = o_stride; prm.d_stride = d_stride; prm.S = S;
   prm.L = h->L; prm.skip = h->skip; prm.n_freq = c.n_freq_xyz;
+  prm.trace = h->chain_trace;
   const int n_blocks = (int)ceil_div_ll(prm.P, 256);
   constexpr int smem = chain::sigma_chain_smem();
   BN_CUDA(cudaFuncSetAttribute(chain::sigma_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -590,7 +591,7 @@ static int forward_t(bn_mlp* h, const float* params, const float* origins, int o
   const bn_mlp_cfg& c = h->cfg;
   const int F = h->F, L = h->L;
   if constexpr (std::is_same<T, __nv_bfloat16>::value) {
-    if (sig_only && h->F == chain::kF && h->skip >= 1 && !h->no_chain)
+    if (sig_only && h->F == chain::kF && h->skip >= 1 && h->L <= chain::kMaxBiasLayers && !h->no_chain)
       return sigma_chain(h, params, origins, o_stride, dirs, d_stride, z, N, S, out, s);
   }
   Ws<T> w; carve<T>(h, P, flags, wsp, &w);
@@ -903,4 +904,12 @@ int bn_debug_gemm_epi(int kind, const void* A, long long lda, const void* B, lon
   }
   BN_CHECK_ARG(tc::wgrad_tma_ok((const float*)out, ldo, N, pad_lo, pad_hi), "output not addressable by the TMA");
   return layer_wgrad<T>(&h, (const T*)A, lda, (const T*)B, ldb, (int)M, N, K, (float*)out, ldo, pad_lo, pad_hi, colsum, stream);
+}
+
+// Diagnostics: device buffer of >= 16 * 2 * layers int64 that the fused density pass fills with clock64() stamps
+// of its first block (scripts/trace_chain.py); NULL switches the stamps off.
+extern "C" __attribute__((visibility("default"))) int bn_debug_chain_trace(bn_mlp* h, long long* device_buf) {
+  BN_CHECK_ARG(h != nullptr, "null handle");
+  h->chain_trace = device_buf;
+  return BN_OK;
 }

@@ -32,8 +32,9 @@ constexpr int kF = 512;                 // trunk width this kernel is specialise
 constexpr int kNKB = 1 + kF / 64;       // K blocks of the activation buffer: PE + 8 x 64 features
 constexpr int kKBBytes = 128 * 128;     // one K block of one CTA: 128 rows x 64 bf16
 constexpr int kMaxLayers = 16;
+constexpr int kMaxBiasLayers = 8;       // biases of up to 8 layers are staged in shared memory by the density pass
 // weight ring depth: the training variant gives one stage to the cosine staging boxes
-template <bool kTrain> __host__ __device__ constexpr int w_stages() { return kTrain ? 4 : 5; }
+template <bool kTrain> __host__ __device__ constexpr int w_stages() { return 4; }
 
 struct SigmaChainParams {
   CUtensorMap wmap[kMaxLayers];         // packed W_l [F, Kpad_l] bf16, boxes 64 (K) x 128 (rows)
@@ -43,6 +44,7 @@ struct SigmaChainParams {
   float* out;
   long long P;
   int o_stride, d_stride, S, L, skip, n_freq;
+  long long* trace;                     // diagnostics (bn_debug_chain_trace): clock64() stamps of pair 0's leader CTA, first block
 };
 
 // training forward: same chain, and every layer leaves h_l = sin(.) and c_l = w0 cos(.) in HBM for the
@@ -60,7 +62,8 @@ struct TrainChainParams {
 };
 
 template <bool kTrain> __host__ __device__ constexpr int chain_smem() {
-  return kNKB * kKBBytes + w_stages<kTrain>() * kKBBytes + (kTrain ? 4 * 4096 : 1024) + 512 + 1024;
+  // activations + weight ring + (cosine boxes | all biases of the trunk + sigma exchange) + barriers + alignment slack
+  return kNKB * kKBBytes + w_stages<kTrain>() * kKBBytes + (kTrain ? 4 * 4096 : kMaxBiasLayers * kF * 4 + 1024) + 512 + 1024;
 }
 constexpr int sigma_chain_smem() { return chain_smem<false>(); }
 
@@ -89,8 +92,8 @@ __device__ __forceinline__ void chain_producer(const CUtensorMap* wmap, uint8_t*
 // ---- MMA issuer (leader CTA): layer = two column halves x the layer's K blocks ----
 template <int STAGES>
 __device__ __forceinline__ void chain_mma(uint8_t* sAct, uint8_t* sW, uint64_t* wfull, uint64_t* wempty, uint64_t* tfull,
-                                          uint64_t* tempty, uint64_t* act_ready, uint32_t tmem_base,
-                                          int pair0, int npairs, int n_blocks, int L, int skip) {
+                                          uint64_t* tempty, uint64_t* act_ready, uint64_t* kfree, uint32_t tmem_base,
+                                          int pair0, int npairs, int n_blocks, int L, int skip, long long* trace = nullptr) {
   constexpr uint32_t idesc = make_idesc(256, 256, false);
   int stage = 0; uint32_t phase = 0;
   uint32_t te_ph[2] = {0, 0};
@@ -100,12 +103,15 @@ __device__ __forceinline__ void chain_mma(uint8_t* sAct, uint8_t* sW, uint64_t* 
       for (int n = 0; n < 2; ++n) {
         mbar_wait(&tempty[n], te_ph[n] ^ 1); te_ph[n] ^= 1;      // the epilogue has read this half out
         fence_after_sync();
+        const bool tr = trace != nullptr && blk == pair0 && pair0 == 0;
+        if (tr) trace[(l * 2 + n) * 16 + 0] = clock64();      // [0] TMEM half free
         bool first = true;
         for (int kb = layer_kb_first(l, skip); kb <= layer_kb_last(l); ++kb) {
           if (n == 0 && !(kb == 0 && l > 0)) {          // K block published once per layer (PE: once per block)
             mbar_wait(&act_ready[kb], (ar_ph >> kb) & 1); ar_ph ^= 1u << kb;
             fence_after_sync();
           }
+          if (tr) trace[(l * 2 + n) * 16 + 1 + kb] = clock64(); // [1+kb] K block kb available to the issuer
           mbar_wait(&wfull[stage], phase);
           fence_after_sync();
           const uint32_t a_addr = smem_u32(sAct + kb * kKBBytes);
@@ -117,9 +123,13 @@ __device__ __forceinline__ void chain_mma(uint8_t* sAct, uint8_t* sW, uint64_t* 
           }
           first = false;
           umma_commit_pair(&wempty[stage]);
+          // K blocks 1..4 have now been read by both halves of this layer: the first half's epilogue may overwrite
+          // them while K blocks 5..8 are still being multiplied, and the next layer starts without a pipeline drain
+          if (n == 1 && (kb == 4 || (kb == layer_kb_last(l) && kb < 4))) umma_commit_pair(kfree);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit_pair(&tfull[n]);
+        if (tr) trace[(l * 2 + n) * 16 + 10] = clock64();     // [10] all MMAs of the half issued
       }
 }
 
@@ -157,13 +167,16 @@ __global__ void __launch_bounds__(kThreads, 1) sigma_chain_kernel(const __grid_c
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sAct = smem;                                        // [kNKB][128 rows][128 B], swizzled
   uint8_t* sW = sAct + kNKB * kKBBytes;                        // [kWStages][128 rows of W][128 B]
-  float* sSig = reinterpret_cast<float*>(sW + kWStages * kKBBytes);   // [128] partial sigma of the hsel = 1 warps
+  float* sBias = reinterpret_cast<float*>(sW + kWStages * kKBBytes);  // [L][512]: with ~224 KB of smem carved out the L1 is
+                                                                      // too small to keep them, and an L2 round trip per unit is exposed
+  float* sSig = sBias + kMaxBiasLayers * kF;                          // [128] partial sigma of the hsel = 1 warps
   uint64_t* wfull = reinterpret_cast<uint64_t*>(sSig + 256);
   uint64_t* wempty = wfull + kWStages;
   uint64_t* tfull = wempty + kWStages;
   uint64_t* tempty = tfull + 2;
   uint64_t* act_ready = tempty + 2;                            // [kNKB]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(act_ready + kNKB);
+  uint64_t* kfree = act_ready + kNKB;                          // K blocks 1..4 of the current layer are no longer read
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kfree + 1);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int crank = (int)cluster_ctarank();
@@ -177,9 +190,11 @@ __global__ void __launch_bounds__(kThreads, 1) sigma_chain_kernel(const __grid_c
     for (int s = 0; s < kWStages; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 16); }     // 8 epilogue warps x 2 CTAs
     for (int s = 0; s < kNKB; ++s) mbar_init(&act_ready[s], 16);
+    mbar_init(kfree, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) tmem_alloc<true>(tmem_slot, 512);
+  for (int i = threadIdx.x; i < L * kF; i += kThreads) sBias[i] = __ldg(prm.bias[i / kF] + (i % kF));
   fence_before_sync();
   __syncthreads();
   cluster_sync_all();
@@ -190,7 +205,7 @@ __global__ void __launch_bounds__(kThreads, 1) sigma_chain_kernel(const __grid_c
     if (lane == 0) chain_producer<kWStages>(prm.wmap, sW, wfull, wempty, crank, pair0, npairs, n_blocks, L, skip);
   } else if (warp == 1) {
     if (lane == 0 && crank == 0)
-      chain_mma<kWStages>(sAct, sW, wfull, wempty, tfull, tempty, act_ready, tmem_base, pair0, npairs, n_blocks, L, skip);
+      chain_mma<kWStages>(sAct, sW, wfull, wempty, tfull, tempty, act_ready, kfree, tmem_base, pair0, npairs, n_blocks, L, skip, prm.trace);
   } else if (warp >= 4) {
     // ===================== positional encoding + epilogues =====================
     const int q = warp & 3, hsel = (warp - 4) >> 2;
@@ -198,6 +213,7 @@ __global__ void __launch_bounds__(kThreads, 1) sigma_chain_kernel(const __grid_c
     const uint32_t row_off = row * 128, swz = (lane & 7) << 4;
     const uint32_t t_lane = (uint32_t)(q * 32) << 16;
     uint32_t tf_ph[2] = {0, 0};
+    uint32_t kf_ph = 0;
     auto arrive_leader = [&](uint64_t* bar) {               // one arrival per warp on the leader CTA's barrier
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(bar), 0));
@@ -216,8 +232,11 @@ __global__ void __launch_bounds__(kThreads, 1) sigma_chain_kernel(const __grid_c
         const float w0 = l == 0 ? 30.0f : 1.0f;
         const bool last = l == L - 1;
         for (int n = 0; n < 2; ++n) {
+          const bool tr = prm.trace != nullptr && blk == pair0 && pair0 == 0 && crank == 0 && warp == 4 && lane == 0;
+          if (tr) prm.trace[(l * 2 + n) * 16 + 11] = clock64();   // [11] epilogue starts waiting for the half
           mbar_wait(&tfull[n], tf_ph[n]); tf_ph[n] ^= 1;
           fence_after_sync();
+          if (tr) prm.trace[(l * 2 + n) * 16 + 12] = clock64();   // [12] half complete (tfull)
           // software-pipelined TMEM reads: unit u+1 is in flight while unit u goes through the MUFU
           uint32_t pk[4][16];
           uint32_t va[32], vb[32];
@@ -231,11 +250,11 @@ __global__ void __launch_bounds__(kThreads, 1) sigma_chain_kernel(const __grid_c
             if (u < 3) tmem_ld32_issue(tbase + (u + 1) * 64, (u & 1) ? va : vb);
             else { fence_before_sync(); arrive_leader(&tempty[n]); }       // this warp's share of the half is in registers
             const int col0 = n * 256 + u * 64 + hsel * 32;
-            const float4* bp = reinterpret_cast<const float4*>(prm.bias[l] + col0);
+            const float4* bp = reinterpret_cast<const float4*>(sBias + l * kF + col0);
             if (!last) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const float4 b = __ldg(bp + j);
+                const float4 b = bp[j];
                 pk[u][2 * j] = bf_pack(__sinf(w0 * (__uint_as_float(v[4 * j]) + b.x)), __sinf(w0 * (__uint_as_float(v[4 * j + 1]) + b.y)));
                 pk[u][2 * j + 1] = bf_pack(__sinf(w0 * (__uint_as_float(v[4 * j + 2]) + b.z)), __sinf(w0 * (__uint_as_float(v[4 * j + 3]) + b.w)));
               }
@@ -251,15 +270,19 @@ __global__ void __launch_bounds__(kThreads, 1) sigma_chain_kernel(const __grid_c
               const float4* wp = reinterpret_cast<const float4*>(prm.wsig + col0);
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const float4 b = __ldg(bp + j), w = __ldg(wp + j);
+                const float4 b = bp[j], w = __ldg(wp + j);
                 sig = fmaf(__sinf(w0 * (__uint_as_float(v[4 * j]) + b.x)), w.x, sig); sig = fmaf(__sinf(w0 * (__uint_as_float(v[4 * j + 1]) + b.y)), w.y, sig);
                 sig = fmaf(__sinf(w0 * (__uint_as_float(v[4 * j + 2]) + b.z)), w.z, sig); sig = fmaf(__sinf(w0 * (__uint_as_float(v[4 * j + 3]) + b.w)), w.w, sig);
               }
             }
           }
+          if (tr) prm.trace[(l * 2 + n) * 16 + 13] = clock64();   // [13] the half's four units are through the MUFU
+          if (n == 0) {
+            // in place: K blocks 1..4 feed the second half's MMAs until its fourth K block has retired
+            mbar_wait(kfree, kf_ph); kf_ph ^= 1;
+            if (tr) prm.trace[(l * 2 + n) * 16 + 14] = clock64(); // [14] in-place hazard cleared
+          }
           if (!last && n == 0) {
-            // in place: K blocks 1.. still feed the second half's MMAs until tfull[1] of THIS layer
-            mbar_wait(&tfull[1], tf_ph[1]);
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               uint8_t* kbp = sAct + (1 + u) * kKBBytes;
@@ -303,7 +326,8 @@ __global__ void __launch_bounds__(kThreads, 1) train_chain_kernel(const __grid_c
   uint64_t* tfull = wempty + kWStages;
   uint64_t* tempty = tfull + 2;
   uint64_t* act_ready = tempty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(act_ready + kNKB);
+  uint64_t* kfree = act_ready + kNKB;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kfree + 1);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int crank = (int)cluster_ctarank();
@@ -317,6 +341,7 @@ __global__ void __launch_bounds__(kThreads, 1) train_chain_kernel(const __grid_c
     for (int s = 0; s < kWStages; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 16); }
     for (int s = 0; s < kNKB; ++s) mbar_init(&act_ready[s], 16);
+    mbar_init(kfree, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) tmem_alloc<true>(tmem_slot, 512);
@@ -330,7 +355,7 @@ __global__ void __launch_bounds__(kThreads, 1) train_chain_kernel(const __grid_c
     if (lane == 0) chain_producer<kWStages>(prm.wmap, sW, wfull, wempty, crank, pair0, npairs, n_blocks, L, skip);
   } else if (warp == 1) {
     if (lane == 0 && crank == 0)
-      chain_mma<kWStages>(sAct, sW, wfull, wempty, tfull, tempty, act_ready, tmem_base, pair0, npairs, n_blocks, L, skip);
+      chain_mma<kWStages>(sAct, sW, wfull, wempty, tfull, tempty, act_ready, kfree, tmem_base, pair0, npairs, n_blocks, L, skip);
   } else if (warp >= 4) {
     const int q = warp & 3, hsel = (warp - 4) >> 2;
     const int row = q * 32 + lane;
@@ -341,6 +366,7 @@ __global__ void __launch_bounds__(kThreads, 1) train_chain_kernel(const __grid_c
     uint8_t* cbox = sC + (q * 2 + hsel) * 2048;
     const uint32_t crow_off = lane * 64, cswz = ((lane >> 1) & 3) << 4;
     uint32_t tf_ph[2] = {0, 0};
+    uint32_t kf_ph = 0;
     auto arrive_leader = [&](uint64_t* bar) {
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(bar), 0));
@@ -405,8 +431,8 @@ __global__ void __launch_bounds__(kThreads, 1) train_chain_kernel(const __grid_c
             if (n == 1 && !last) arrive_leader(&act_ready[5 + u]);
           }
           if (n == 0) {
-            // in place: K blocks 1..4 still feed the second half's MMAs until tfull[1] of THIS layer
-            mbar_wait(&tfull[1], tf_ph[1]);
+            // in place: K blocks 1..4 feed the second half's MMAs until its fourth K block has retired
+            mbar_wait(kfree, kf_ph); kf_ph ^= 1;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               uint8_t* kbp = sAct + (1 + u) * kKBBytes;

@@ -64,6 +64,7 @@ struct bn_mlp {
   int blk_lin0[bn::kMaxBlocks], blk_lin2[bn::kMaxBlocks], blk_head[bn::kMaxBlocks];
   bool synced;
   bool no_chain;
+  long long* chain_trace;
 };
 
 namespace bn {

@@ -270,6 +270,10 @@ int bn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_a
 int bn_debug_gemm(int kind, int precision, const void* A, long long lda, const void* B, long long ldb,
                   float* out, long long ldo, long long M, int N, long long K, cudaStream_t stream);
 
+/* Diagnostics: device buffer (>= 32 * layers int64) that the fused density pass fills with clock64() stamps of the
+ * first 256-point block of CTA pair 0 (MMA issuer and first epilogue warp); NULL switches it off. */
+int bn_debug_chain_trace(bn_mlp* h, long long* device_buf);
+
 /* Unit-test hook for the TMA-staged epilogues of the tcgen05 GEMM (bf16 operands only):
  *   kind 0: out_bf16[M,N] = ((A[M,K] B[N,K]^T) + add[M,N]) * mul[M,N]   (add / mul nullable, bf16, pitch ldo);
  *           colsum[N] (nullable, fp32) += column sums of out
