@@ -148,7 +148,8 @@ def run_reference(opts):
             "warmup": opts.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "spsbrdf-nerf Lambertian pretrain + depth supervision (ds_lambda=10, --mapping), "
-                                   f"{rps} rays x (64+64) samples per step, CPU"},
+                                   "1024 rays x (64+64) samples per GPU per step, fc 8x512, random init seed 0",
+                       "sample": f"each timed step runs {rps} of the 1024 rays on the host cores (bounded sample)"},
             "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))

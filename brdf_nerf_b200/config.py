@@ -47,9 +47,11 @@ _DEFAULTS = dict(
     indirect_light=False,
     normal="none",         # opt.py:230
     sun_v="none",          # opt.py:231
-    brdf_on=1.0,
-    gsam_only_on=1.0,
-    cos_irra_on=1.0,
+    max_train_steps=300000,  # opt.py:162
+    brdf_on=1.0,           # opt.py:242
+    nrrg_on=0.0,           # opt.py:244
+    gsam_only_on=1.0,      # opt.py:255
+    cos_irra_on=1.0,       # opt.py:257
     std_range=3.0,         # opt.py:259
     MultiBRDF=0,           # opt.py:261
     roughness=False,

@@ -65,6 +65,7 @@ class Trainer:
         self._loss = None
         self._kw = None
         self.graph_launches = 0
+        self.use_depth_loss = True          # switched off by the schedule after ds_drop (main.py:248)
 
     # one optimisation step; `batch` tensors must already live on the model's device
     def _step_impl(self, batch: RayBatch, draws, kw):
@@ -72,7 +73,7 @@ class Trainer:
         outs, st = R._forward(model, args, batch.rays, draws, train=True, mode="train",
                               valid_depth=batch.valid_depth, target_depths=batch.target_depths,
                               target_std=batch.target_std, **kw)
-        use_depth = float(args.ds_lambda) > 0
+        use_depth = float(args.ds_lambda) > 0 and self.use_depth_loss
         loss, g_rgb, g_depth = loss_and_grads(args, outs, st, batch, use_depth)
         grads = model.flat_grads
         grads.zero_()
@@ -99,22 +100,24 @@ class Trainer:
 
     # ---- CUDA-graph path: static input buffers, forward+backward captured once, replayed per step
     def _graph_step(self, batch: RayBatch, kw):
+        kw = dict(kw, _use_depth=self.use_depth_loss)
         if self._graph is None or self._kw != kw:
             self._static = RayBatch(*[None if t is None else t.clone() for t in
                                       (batch.rays, batch.rgbs, batch.valid_depth, batch.target_depths, batch.target_std)])
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):                 # warm-up: fills table / workspace caches
+                rkw = {k: v for k, v in kw.items() if not k.startswith("_")}
                 for _ in range(2):
                     self.model.sync_weights(force=True)
-                    self._step_impl(self._static, None, kw)
+                    self._step_impl(self._static, None, rkw)
             torch.cuda.current_stream().wait_stream(side)
             self._graph = torch.cuda.CUDAGraph()
             lib = L.load()
             lc0 = lib.bn_launch_count()
             with torch.cuda.graph(self._graph):
                 self.model.sync_weights(force=True)
-                self._loss = self._step_impl(self._static, None, kw)
+                self._loss = self._step_impl(self._static, None, rkw)
             self.graph_launches = int(lib.bn_launch_count() - lc0)     # library kernels replayed by every graph launch
             self._kw = dict(kw)
         for dst, src in zip((self._static.rays, self._static.rgbs, self._static.valid_depth,
@@ -125,3 +128,28 @@ class Trainer:
         self._graph.replay()
         self._reduce_and_update()
         return self._loss
+
+
+class TrainLoop:
+    """The reference's training loop around the hot path (NeRF_pl.training_step + DataLoader + StepLR,
+    main.py:147-246) without Lightning: device-resident ray pool -> schedule flags -> Trainer.step.
+    One call of `step()` = one optimisation step; nothing synchronises with the host."""
+
+    def __init__(self, model, args, pool: RayBatch, world_size: int = 1, rank: int = 0, process_group=None,
+                 use_graph: bool = True, seed: int = 0):
+        from .schedule import DeviceRayPool, Schedule
+        self.args = args
+        self.trainer = Trainer(model, args, world_size=world_size, process_group=process_group, use_graph=use_graph)
+        self.feed = DeviceRayPool(pool, int(args.batch_size), rank=rank, world_size=world_size, seed=seed)
+        self.schedule = Schedule(args, dataset_len=pool.rays.shape[0], world_size=world_size)
+        if float(args.noise_std) != 0.0 and use_graph:
+            raise ValueError("noise_std decays every step (main.py:246): run with use_graph=False when it is non-zero")
+
+    def step(self):
+        f = self.schedule.next()
+        self.trainer.lr = f.lr
+        self.trainer.use_depth_loss = f.use_depth_loss
+        self.args.noise_std = f.noise_std
+        batch = self.feed.next_batch()
+        return self.trainer.step(batch, apply_brdf=f.apply_brdf, apply_theta=f.apply_theta, cos_irra_on=f.cos_irra_on,
+                                 gsam_only=f.gsam_only)

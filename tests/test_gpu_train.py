@@ -95,3 +95,46 @@ def test_graph_step_equals_eager(cuda):
     for _ in range(5):
         l = tr.step(batch).item()
     assert math.isfinite(l) and l < l0 + 0.05
+
+
+@pytest.mark.parametrize("n,use_all", [(64, False), (1000, False), (333, True)])
+def test_fused_loss_kernel_vs_oracle_losses(cuda, n, use_all):
+    """bn_loss_color_depth (SNerfLoss + DepthLoss subset rule, fused with its gradients) == oracle losses + autograd."""
+    from brdf_nerf_b200.train import loss_and_grads
+    g = torch.Generator().manual_seed(n)
+    s = 128
+    args = named_config("lambertian_ds", usealldepth=use_all)
+    batch = make_rays(n, depth_supervision=True)
+    rgb = torch.rand(n, 3, generator=g, requires_grad=True)
+    z = torch.sort(torch.rand(n, s, generator=g) * 0.6, -1)[0]
+    w = torch.softmax(torch.randn(n, s, generator=g), -1)
+    depth = ((w * z).sum(-1) + 0.05 * torch.randn(n, generator=g)).requires_grad_(True)
+    res = {"rgb_coarse": rgb, "depth_coarse": depth, "weights_coarse": w, "z_vals_coarse": z}
+    ref = LT.train_loss(res, batch, args)
+    ref.backward()
+    outs = dict(rgb=rgb.detach().to(cuda), depth=depth.detach().to(cuda), weights=w.to(cuda), z=z.to(cuda))
+    loss, g_rgb, g_depth = loss_and_grads(args, outs, None, batch.to(cuda), True)
+    assert abs(loss.item() - ref.item()) < 1e-6 * max(1.0, abs(ref.item()))
+    assert torch.allclose(g_rgb.cpu(), rgb.grad, atol=1e-7) and torch.allclose(g_depth.cpu(), depth.grad, atol=1e-7)
+    # colour term alone
+    loss_c, g_c, g_d = loss_and_grads(args, outs, None, batch.to(cuda), False)
+    assert g_d is None and abs(loss_c.item() - LT.color_loss(res, batch.rgbs).item()) < 1e-6
+
+
+def test_train_loop_pool_and_schedule(cuda):
+    """Device-resident ray pool + step-fraction schedule + fused step: the depth loss drops at ds_drop, the learning
+    rate follows StepLR per epoch, every ray of the pool is visited once per epoch."""
+    from brdf_nerf_b200.schedule import DeviceRayPool
+    from brdf_nerf_b200.train import TrainLoop
+    args = named_config("lambertian_ds", batch_size=256, max_train_steps=12, ds_drop=0.5)
+    pool = make_rays(1024, depth_supervision=True).to(cuda)
+    feed = DeviceRayPool(pool, 256, seed=1)
+    seen = torch.cat([feed.next_batch().rays for _ in range(4)])
+    assert torch.equal(torch.sort(seen[:, 0])[0], torch.sort(pool.rays[:, 0])[0])        # one epoch = a permutation
+    torch.manual_seed(0)
+    model = load_model(args, precision="bf16").to(cuda)
+    loop = TrainLoop(model, args, pool, use_graph=True)
+    losses = [loop.step().item() for _ in range(12)]
+    assert all(math.isfinite(x) for x in losses)
+    assert loop.trainer.use_depth_loss is False and abs(loop.trainer.lr - 5e-4 * 0.9 ** 3) < 1e-12
+    assert losses[-1] < losses[0]

@@ -94,22 +94,24 @@ def test_product_never_imports_the_oracle():
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{f} imports oracle"
 
 
-def test_fused_step_loss_equals_reference_loss_restatement():
-    """train.loss_and_grads (closed form, no host sync) == oracle losses + autograd, on CPU tensors."""
-    from brdf_nerf_b200.train import loss_and_grads
-    from oracle import losses_torch as LT
-    g = torch.Generator().manual_seed(0)
-    n, s = 64, 128
-    args = named_config("lambertian_ds")
-    batch = make_rays(n, depth_supervision=True)
-    rgb = torch.rand(n, 3, generator=g, requires_grad=True)
-    z = torch.sort(torch.rand(n, s, generator=g) * 0.6, -1)[0]
-    w = torch.softmax(torch.randn(n, s, generator=g), -1)
-    depth = ((w * z).sum(-1) + 0.05 * torch.randn(n, generator=g)).requires_grad_(True)
-    res = {"rgb_coarse": rgb, "depth_coarse": depth, "weights_coarse": w, "z_vals_coarse": z}
-    ref = LT.train_loss(res, batch, args)
-    ref.backward()
-    outs = dict(rgb=rgb.detach(), depth=depth.detach(), weights=w, z=z)
-    loss, g_rgb, g_depth = loss_and_grads(args, outs, None, batch, True)
-    assert abs(loss.item() - ref.item()) < 1e-6
-    assert torch.allclose(g_rgb, rgb.grad, atol=1e-7) and torch.allclose(g_depth, depth.grad, atol=1e-7)
+def test_schedule_matches_reference_rules():
+    """Step-fraction switches of NeRF_pl.training_step (reference main.py:59-68, 196-210, 246-248) and the
+    per-epoch StepLR (train_utils.py:117-118, 153-155)."""
+    from brdf_nerf_b200.config import named_config
+    from brdf_nerf_b200.schedule import Schedule
+    args = named_config("rpv111", max_train_steps=1000, brdf_on=0.25, gsam_only_on=0.8, cos_irra_on=0.5, ds_lambda=10.0,
+                        ds_drop=0.3, noise_std=1.0, batch_size=100)
+    sc = Schedule(args, dataset_len=1000)          # 10 steps per epoch
+    seen = [sc.next() for _ in range(1000)]
+    f = lambda k: seen[k - 1]                      # flags of the step whose train_steps == k
+    assert not f(250).apply_brdf and f(251).apply_brdf
+    assert not f(500).apply_theta and f(501).apply_theta
+    assert not f(500).cos_irra_on and f(501).cos_irra_on
+    assert not f(800).gsam_only and f(801).gsam_only
+    assert f(299).use_depth_loss and not f(300).use_depth_loss
+    assert abs(f(1).lr - 5e-4) < 1e-12 and abs(f(10).lr - 5e-4 * 0.9) < 1e-12 and abs(f(25).lr - 5e-4 * 0.9 ** 2) < 1e-12
+    assert abs(f(3).noise_std - 0.81) < 1e-12
+    # data-parallel: train_steps advances by the number of GPUs (main.py:196)
+    sc4 = Schedule(args, dataset_len=1000, world_size=4)
+    flags = [sc4.next() for _ in range(70)]
+    assert not flags[61].apply_brdf and flags[62].apply_brdf        # 63 * 4 = 252 > 250
