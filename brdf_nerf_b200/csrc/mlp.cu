@@ -411,6 +411,68 @@ __global__ void pack_w2_kernel(HeadPlan hp, const float* __restrict__ params, __
   W2p[idx] = __float2bfloat16_rn(v);
 }
 
+// forward operands of the heads' second layers as tcgen05 B matrices (N = 64 padded outputs, K-major):
+//   W2pT [64, ldk] : row o = W2_o laid over the columns of its hidden block, zeros elsewhere
+//   Wsig [64, F]   : row 0 = w_sigma, rows 1..3 = grad_from_xyz (learned normal) when evaluated
+__global__ void pack_heads_fwd_kernel(HeadPlan hp, const float* __restrict__ params, __nv_bfloat16* __restrict__ W2pT,
+                                      int ldk, __nv_bfloat16* __restrict__ Wsig, int F) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int hk = hp.n_blocks * hp.HH;
+  if (idx < 64 * hk) {
+    const int o = idx / hk, cix = idx % hk;
+    float v = 0.f;
+    if (o < hp.n_out && hp.o[o].block == cix / hp.HH) v = params[hp.o[o].w_off + (cix % hp.HH)];
+    W2pT[(long long)o * ldk + cix] = __float2bfloat16_rn(v);
+  }
+  if (idx < 64 * F) {
+    const int r = idx / F, i = idx % F;
+    float v = 0.f;
+    if (r == 0) v = params[hp.wsig + i];
+    else if (r <= 3 && hp.ch_nlr >= 0) v = params[hp.wg + (long long)(r - 1) * F + i];
+    Wsig[idx] = __float2bfloat16_rn(v);
+  }
+}
+
+// direct epilogue of the heads GEMM: columns 0..n_out-1 of the accumulator row are the second-layer
+// pre-activations; bias, sigmoid and the output transforms are applied and the packed row is written
+struct EpiHeadsOut {
+  static constexpr int kMode = 0, kIn = 0, kOut = 0;
+  HeadPlan hp; const float* params; float* out; int pitch; int M;
+  template <int n> __device__ __forceinline__ void apply(int row, int col0, const float (&acc)[n]) const {
+    if (col0 != 0 || row >= M) return;
+    float* orow = out + (long long)row * pitch;
+#pragma unroll
+    for (int o = 0; o < kMaxOut; ++o) {
+      if (o < hp.n_out) {
+        const OutDesc& d = hp.o[o];
+        const float sg = 1.0f / (1.0f + expf(-(acc[o] + __ldg(params + d.b_off))));
+        float v = sg;
+        if (d.xform == XF_K) v = (sg - 0.5f) * 2.0f + 1.0f;
+        else if (d.xform == XF_THETA_RPV) v = (sg - 0.5f) * 2.0f;
+        else if (d.xform == XF_THETA_H) v = sg * (float)(M_PI * 30.0 / 180.0);
+        for (int c = 0; c < d.rep; ++c) orow[d.ch + c] = v;
+      }
+    }
+  }
+};
+
+// direct epilogue of the sigma GEMM: column 0 = w_sigma . h, columns 1..3 = grad_from_xyz . h (learned normal)
+struct EpiSigmaOut {
+  static constexpr int kMode = 0, kIn = 0, kOut = 0;
+  const float* bsig; const float* bg; float* out; int pitch, ch_sigma, ch_nlr, M;
+  template <int n> __device__ __forceinline__ void apply(int row, int col0, const float (&acc)[n]) const {
+    if (col0 != 0 || row >= M) return;
+    float* orow = out + (long long)row * pitch;
+    const float sv = acc[0] + __ldg(bsig);
+    orow[ch_sigma] = sv > 20.f ? sv : log1pf(expf(sv));
+    if (ch_nlr >= 0) {
+      const float g0 = acc[1] + __ldg(bg), g1 = acc[2] + __ldg(bg + 1), g2 = acc[3] + __ldg(bg + 2);
+      const float inv = 1.0f / sqrtf(fmaxf(g0 * g0 + g1 * g1 + g2 * g2, 1.1920929e-07f));
+      orow[ch_nlr] = -g0 * inv; orow[ch_nlr + 1] = -g1 * inv; orow[ch_nlr + 2] = -g2 * inv;
+    }
+  }
+};
+
 static int build_plan(const bn_mlp* h, int flags, HeadPlan* hp, int* n_channels) {
   HeadPlan p{};
   const bn_mlp_cfg& c = h->cfg;
@@ -630,9 +692,23 @@ static int forward_t(bn_mlp* h, const float* params, const float* origins, int o
     if (int rc = layer_sin<T>(h, w.FE, F, (const T*)h->W1, F, P, HKa, F, h->b1cat, 1.0f, w.HD, w.ldhd,
                               train ? w.CD : nullptr, w.ldhd, s)) return rc;
   }
-  heads_fwd_kernel<T><<<heads_grid(h, P), 256, 0, s>>>(hp, params, Hl, ldl, F, w.HD, w.ldhd, out, pitch, P, false, false);
-  BN_LAUNCH_CHECK();
-  return BN_OK;
+  if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+    // second layers of the heads, sigma and the learned normal as two skinny tcgen05 GEMMs (N = 64) whose
+    // epilogues write the packed fp32 rows: every activation row is read exactly once, by the TMA
+    const int HKa = hp.n_blocks * h->HH;
+    const int ldk = h->n_blocks * h->HH;
+    pack_heads_fwd_kernel<<<ceil_div(64 * max(HKa, F), 256), 256, 0, s>>>(hp, params, (__nv_bfloat16*)h->W2pT, ldk,
+                                                                          (__nv_bfloat16*)h->Wsig, F);
+    BN_LAUNCH_CHECK();
+    EpiHeadsOut eh{hp, params, out, pitch, (int)P};
+    if (int rc = gemm_tn<T>(h, w.HD, w.ldhd, (const T*)h->W2pT, ldk, P, 64, HKa, eh, s, hp.n_out * h->HH / 64)) return rc;
+    EpiSigmaOut es{params + hp.bsig, params + hp.bg, out, pitch, hp.ch_sigma, hp.ch_nlr, (int)P};
+    return gemm_tn<T>(h, Hl, ldl, (const T*)h->Wsig, F, P, 64, F, es, s, (hp.ch_nlr >= 0 ? 4 : 1) * F / 64);
+  } else {
+    heads_fwd_kernel<T><<<heads_grid(h, P), 256, 0, s>>>(hp, params, Hl, ldl, F, w.HD, w.ldhd, out, pitch, P, false, false);
+    BN_LAUNCH_CHECK();
+    return BN_OK;
+  }
 }
 
 template <typename T>
@@ -791,6 +867,8 @@ extern "C" __attribute__((visibility("default"))) int bn_mlp_create(const bn_mlp
   BN_CUDA(cudaMalloc(&h->W1T, HK * h->F * h->es));
   BN_CUDA(cudaMalloc(&h->b1cat, HK * sizeof(float)));
   BN_CUDA(cudaMalloc(&h->W2p, HK * 64 * sizeof(__nv_bfloat16)));
+  BN_CUDA(cudaMalloc(&h->W2pT, HK * 64 * sizeof(__nv_bfloat16)));
+  BN_CUDA(cudaMalloc(&h->Wsig, (size_t)64 * h->F * sizeof(__nv_bfloat16)));
   *out = h;
   return BN_OK;
 }
@@ -798,7 +876,7 @@ extern "C" __attribute__((visibility("default"))) int bn_mlp_create(const bn_mlp
 extern "C" __attribute__((visibility("default"))) void bn_mlp_destroy(bn_mlp* h) {
   if (!h) return;
   for (int l = 0; l < h->L; ++l) { cudaFree(h->Wp[l]); cudaFree(h->WTp[l]); }
-  cudaFree(h->Wf); cudaFree(h->WfT); cudaFree(h->W1); cudaFree(h->W1T); cudaFree(h->b1cat); cudaFree(h->W2p);
+  cudaFree(h->Wf); cudaFree(h->WfT); cudaFree(h->W1); cudaFree(h->W1T); cudaFree(h->b1cat); cudaFree(h->W2p); cudaFree(h->W2pT); cudaFree(h->Wsig);
   delete h;
 }
 

@@ -60,6 +60,7 @@ struct bn_mlp {
   void* Wf; void* WfT;
   void* W1; void* W1T; float* b1cat;
   void* W2p;                    // [n_blocks*HH, 64] bf16: second-layer head weights as the B operand of the GHD GEMM
+  void* W2pT; void* Wsig;       // [64, n_blocks*HH], [64, F] bf16: the same weights / w_sigma as B operands of the forward heads GEMMs
   int n_blocks;
   int blk_lin0[bn::kMaxBlocks], blk_lin2[bn::kMaxBlocks], blk_head[bn::kMaxBlocks];
   bool synced;
