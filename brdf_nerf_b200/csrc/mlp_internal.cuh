@@ -156,7 +156,7 @@ template <typename T> struct Ws {
   float* GRAW;     // [P,4] raw d sigma / d x (fp32)
   T* UBX;          // [P,64+F]: cols 0..63 = adjoint of EE, cols 64.. = ubar_{skip-1}
   T* UBA; T* UBB;  // ubar ping-pong
-  T* SG;           // [P,8]: col 0 = sigmoid(s_p)
+  T* SG;           // [P,64]: col 0 = sigmoid(s_p), other columns zero (A operand of the w_sigma second-order wgrad)
 };
 
 static inline size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
@@ -202,7 +202,7 @@ static inline size_t carve(const bn_mlp* h, long long P, int flags, void* base, 
   if (normals) {
     if (train) {
       for (int l = 0; l < L; ++l) { t.A[l] = take(P * F); t.U[l] = take(P * F); }
-      t.UBX = take(P * t.ldx3); t.UBA = take(P * F); t.UBB = take(P * F); t.SG = take(P * 8);
+      t.UBX = take(P * t.ldx3); t.UBA = take(P * F); t.UBB = take(P * F); t.SG = take(P * 64);
     } else {
       T* ping = take(P * F); T* pong = take(P * F);
       for (int l = 0; l < L; ++l) { t.A[l] = (l & 1) ? pong : ping; t.U[l] = nullptr; }

@@ -38,7 +38,10 @@ __global__ void sweep_init_kernel(const float* __restrict__ out, int pitch, cons
   for (int j = 0; j < 8; ++j) { u[j] = sg * __ldg(params + wsig + i + j); a[j] = u[j] * c[j]; }
   Pack<T, 8>::store(A + p * F + i, a);
   if (U) Pack<T, 8>::store(U + p * F + i, u);
-  if (SG && i == 0) { float s8[8] = {sg, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}; Pack<T, 8>::store(SG + p * 8, s8); }
+  if (SG && i < 64) {                // row of 64: col 0 = sg
+    float s8[8] = {i == 0 ? sg : 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    Pack<T, 8>::store(SG + p * 64 + i, s8);
+  }
 }
 
 template <typename T>
@@ -121,25 +124,33 @@ __global__ void normal_bwd_init_kernel(const float* __restrict__ g_out, int pitc
   }
 }
 
-// d loss / d sigma += (ubar_{L-1} . w_sigma)(1 - sg): one warp per point
+// d loss / d sigma += (ubar_{L-1} . w_sigma)(1 - sg): a warp handles 4 points at a time (4 independent row streams)
 template <typename T>
 __global__ void __launch_bounds__(128) sigma_top_bwd_kernel(const T* __restrict__ UB, long long ld,
                                                             const float* __restrict__ params, long long wsig,
                                                             const T* __restrict__ SG, float* __restrict__ g_out, int pitch,
                                                             long long P, int F) {
   const int lane = threadIdx.x % 32;
-  const long long p = (long long)blockIdx.x * 4 + threadIdx.x / 32;
-  if (p >= P) return;
-  float acc = 0.f;
+  const long long p0 = ((long long)blockIdx.x * 4 + threadIdx.x / 32) * 4;
+  if (p0 >= P) return;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
   for (int i = lane * 8; i < F; i += 256) {
-    float u[8]; load8<T>(UB + p * ld + i, u);
+    float wv[8]; load8<float>(params + wsig + i, wv);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc = fmaf(u[j], __ldg(params + wsig + i + j), acc);
+    for (int q = 0; q < 4; ++q) {
+      const long long p = min(p0 + q, P - 1);
+      float u[8]; load8<T>(UB + p * ld + i, u);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[q] = fmaf(u[j], wv[j], acc[q]);
+    }
   }
-  acc = warp_sum(acc);
-  if (lane == 0) {
-    const float sg = to_f<T>(SG[p * 8]);
-    g_out[p * pitch + 3] += acc * (1.0f - sg);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float a = warp_sum(acc[q]);
+    if (lane == 0 && p0 + q < P) {
+      const float sg = to_f<T>(SG[(p0 + q) * 64]);
+      g_out[(p0 + q) * pitch + 3] += a * (1.0f - sg);
+    }
   }
 }
 
@@ -204,16 +215,21 @@ static int normals_backward_t(bn_mlp* h, const float* params, const float* out, 
     prev = dst; ldprev = ldd;
   }
   const long long wsig = c.w_off[BN_LIN_SIGMA];
-  sigma_top_bwd_kernel<T><<<(unsigned)ceil_div_ll(P, 4), 128, 0, s>>>(prev, ldprev, params, wsig, w.SG, g_out, pitch, P, F);
+  sigma_top_bwd_kernel<T><<<(unsigned)ceil_div_ll(P, 16), 128, 0, s>>>(prev, ldprev, params, wsig, w.SG, g_out, pitch, P, F);
   BN_LAUNCH_CHECK();
-  {
+  if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+    // d w_sigma += SG[:,0]^T ubar_{L-1}: a skinny NT GEMM on the tensor cores (row 0 of a 64-row A operand)
+    EpiSkinny e{}; e.n_rows = 1;
+    e.r[0] = EpiSkinnyRow{g + wsig, 0, F};
+    if (int rc = gemm_nt<T>(h, w.SG, 64, prev, ldprev, 64, F, P, e, s, 2.0 * P * F)) return rc;
+  } else {
     SkinnyPlan sp{};
     sp.r[sp.n++] = SkinnyRow{g + wsig, nullptr, 0, 0, F};
     const int bx = ceil_div(F, 256);
     int by = (int)max(1LL, min(ceil_div_ll(P, 128), (long long)(148 * 4 / bx)));
     const long long rows = ceil_div_ll(ceil_div_ll(P, by), 32) * 32;
     by = (int)ceil_div_ll(P, rows);
-    skinny_wgrad_kernel<T><<<dim3(bx, by), 256, 0, s>>>(sp, w.SG, 8, prev, ldprev, F, P, rows);
+    skinny_wgrad_kernel<T><<<dim3(bx, by), 256, 0, s>>>(sp, w.SG, 64, prev, ldprev, F, P, rows);
     BN_LAUNCH_CHECK();
   }
   (void)out;
