@@ -69,11 +69,19 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
-    def stop(self):
+    def mark(self):
+        """Number of samples written so far (brackets the timed region inside the continuous log)."""
+        try:
+            self.f.flush()
+            return sum(1 for _ in open(self.f.name))
+        except Exception:
+            return 0
+
+    def stop(self, first=0, last=None):
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.p.terminate()
@@ -84,6 +92,8 @@ class ClockSampler:
         self.f.flush()
         rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
         os.unlink(self.f.name)
+        # samples of the timed regions (one sample of slack on either side: nvidia-smi stamps are ~20 ms apart)
+        rows = rows[max(0, first - 1):(None if last is None else last + 1)] or rows
         sm, mx, reasons = [], [], set()
         for r in rows:
             try:
@@ -169,6 +179,7 @@ def run_ours(opts):
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=dev)
     lib = L.load()
+    clocks = ClockSampler(local) if rank == 0 else None     # started early: nvidia-smi needs ~0.5 s to produce its first line
     args = named_config("lambertian_ds")
     torch.manual_seed(0)
     model = load_model(args, precision=opts.precision).to(dev)
@@ -185,7 +196,11 @@ def run_ours(opts):
         loss = trainer.step(batch)
     barrier()
     # ---- device-resident timing -------------------------------------------------------------
-    clocks = ClockSampler(local) if rank == 0 else None
+    if clocks is not None:
+        t_wait = time.time()
+        while clocks.mark() == 0 and time.time() - t_wait < 3.0:
+            time.sleep(0.05)
+    mark0 = clocks.mark() if clocks else 0
     lc0 = lib.bn_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -198,7 +213,6 @@ def run_ours(opts):
     # kernels of this library inside the timed region: eager launches counted by the library itself, plus the
     # kernel nodes every CUDA-graph replay executes (counted once, at capture time)
     launches = (lib.bn_launch_count() - lc0) + opts.steps * getattr(trainer, "graph_launches", 0)
-    clk = clocks.stop() if clocks else None
     # ---- end to end: pinned host batch -> device every step, loss read back every step ---------
     barrier()
     e0.record()
@@ -209,6 +223,7 @@ def run_ours(opts):
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1) / opts.steps
+    clk = clocks.stop(mark0, clocks.mark()) if clocks else None
     t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
