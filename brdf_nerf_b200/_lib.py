@@ -50,6 +50,7 @@ _SIGS = {
     "bn_sample_guided": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _F, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _P]),
     "bn_merge_samples": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "bn_sort_rows": (C.c_int, [_P, _P, _I, _I, _P]),
+    "bn_permute_samples": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "bn_composite_sigma": (C.c_int, [_P, _P, _P, _F, _P, _P, _P, _P, _P, _I, _I, _P]),
     "bn_composite_forward": (C.c_int, [_P, _P, _I, _I, _P, _F, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "bn_composite_backward": (C.c_int, [_P, _P, _I, _I, _P, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
@@ -64,6 +65,8 @@ _SIGS = {
     "bn_mlp_out_channels": (C.c_int, [_P, _I]),
     "bn_mlp_workspace_bytes": (_Z, [_P, _L, _I]),
     "bn_mlp_forward": (C.c_int, [_P, _P, _P, _I, _P, _I, _P, _I, _I, _I, _P, _I, _P, _Z, _P]),
+    "bn_mlp_trunk_forward": (C.c_int, [_P, _P, _P, _I, _P, _I, _P, _I, _I, _I, _L, _L, _P, _P, _Z, _P]),
+    "bn_mlp_heads_forward": (C.c_int, [_P, _P, _L, _I, _P, _I, _P, _Z, _P]),
     "bn_mlp_backward": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _Z, _P]),
     "bn_mlp_normals_forward": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _Z, _P]),
     "bn_mlp_normals_backward": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _Z, _P]),

@@ -562,6 +562,7 @@ static int sync_weights_t(bn_mlp* h, const float* params, cudaStream_t s) {
     pack(h->blk_lin0[b], h->HH, h->F, -1, h->F, h->W1, h->F, h->W1T, HK, b * h->HH);
     jobs.j[jobs.n++] = PackJob{c.b_off[h->blk_lin0[b]], h->HH, -1, -1, 1, h->b1cat, 0, nullptr, 0, b * h->HH};
   }
+  if (h->bf16) pack(BN_LIN_SIGMA, 1, h->F, -1, h->F, h->WsigA, h->F, nullptr, 0, 0);   // row 0 of the [64, F] density operand
   if (jobs.n > kMaxPackJobs) { set_error("too many pack jobs"); return BN_ERR_STATE; }
   pack_all_kernel<T><<<dim3(64, jobs.n), 256, 0, s>>>(jobs, params);
   if (int rc = after_launch("pack_all_kernel")) return rc;
@@ -624,6 +625,7 @@ static int train_chain(bn_mlp* h, const float* params, const float* origins, int
   (void)out; (void)pitch; (void)sigma_ch;     // sigma stays in heads_fwd_kernel: fusing it here cost more (registers) than it saved
   prm.P = P; prm.o_stride = o_stride; prm.d_stride = d_stride; prm.S = S;
   prm.L = h->L; prm.skip = h->skip; prm.n_freq = c.n_freq_xyz;
+  prm.dbg = h->chain_dbg;
   const int n_blocks = (int)ceil_div_ll(P, 256);
   constexpr int smem = chain::chain_smem<true>();
   BN_CUDA(cudaFuncSetAttribute(chain::train_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -643,36 +645,32 @@ static int train_chain(bn_mlp* h, const float* params, const float* origins, int
   return rc;
 }
 
+// rows [row0, row0 + n) of the per-point forward buffers (the workspace is carved for the whole call)
 template <typename T>
-static int forward_t(bn_mlp* h, const float* params, const float* origins, int o_stride, const float* dirs,
-                     int d_stride, const float* z, int N, int S, int flags, float* out, int pitch, void* wsp,
-                     cudaStream_t s) {
+static void offset_rows(const bn_mlp* h, Ws<T>* w, long long row0) {
+  if (row0 == 0) return;
+  w->X3 += row0 * w->ldx3;
+  for (int l = 0; l < h->L; ++l) {
+    w->H[l] += row0 * w->Hld[l];
+    if (w->C[l]) w->C[l] += row0 * h->F;
+  }
+}
+
+// PE + trunk of N*S points whose activations land in `w` (already offset to the first row of this call)
+template <typename T>
+static int trunk_t(bn_mlp* h, const float* params, const float* origins, int o_stride, const float* dirs, int d_stride,
+                   const float* z, int N, int S, bool keep_c, const Ws<T>& w, cudaStream_t s) {
   const long long P = (long long)N * S;
-  const bool train = flags & BN_MLP_TRAIN, sig_only = flags & BN_MLP_SIGMA_ONLY;
-  const bool keep_c = train || ((flags & BN_MLP_NORMAL_AN) && !sig_only);
   const bn_mlp_cfg& c = h->cfg;
   const int F = h->F, L = h->L;
   if constexpr (std::is_same<T, __nv_bfloat16>::value) {
-    if (sig_only && h->F == chain::kF && h->skip >= 1 && h->L <= chain::kMaxBiasLayers && !h->no_chain)
-      return sigma_chain(h, params, origins, o_stride, dirs, d_stride, z, N, S, out, s);
+    if (keep_c && h->F == chain::kF && h->skip >= 1 && !h->no_chain)
+      return train_chain(h, params, origins, o_stride, dirs, d_stride, z, N, S, w, nullptr, 0, 0, s);
   }
-  Ws<T> w; carve<T>(h, P, flags, wsp, &w);
-  HeadPlan hp; int nch;
-  if (int rc = build_plan(h, flags, &hp, &nch)) return rc;
-  if (!sig_only && pitch < nch) { set_error("bn_mlp_forward: out_pitch %d < %d channels", pitch, nch); return BN_ERR_ARG; }
-  bool chained = false;
-  if constexpr (std::is_same<T, __nv_bfloat16>::value) {
-    if (keep_c && h->F == chain::kF && h->skip >= 1 && !h->no_chain) {
-      if (int rc = train_chain(h, params, origins, o_stride, dirs, d_stride, z, N, S, w, out, pitch, hp.ch_sigma, s)) return rc;
-      chained = true;
-    }
-  }
-  if (!chained) {
-    encode_kernel<T><<<(unsigned)ceil_div_ll(P, 128), 128, 0, s>>>(origins, o_stride, dirs, d_stride, z, S, P,
-                                                                 c.n_freq_xyz, w.X3, w.ldx3);
-    BN_LAUNCH_CHECK();
-  }
-  for (int l = 0; l < L && !chained; ++l) {
+  encode_kernel<T><<<(unsigned)ceil_div_ll(P, 128), 128, 0, s>>>(origins, o_stride, dirs, d_stride, z, S, P,
+                                                               c.n_freq_xyz, w.X3, w.ldx3);
+  BN_LAUNCH_CHECK();
+  for (int l = 0; l < L; ++l) {
     const T* A; long long lda;
     if (l == 0 || l == h->skip) { A = w.X3; lda = w.ldx3; } else { A = w.H[l - 1]; lda = w.Hld[l - 1]; }
     // first layer: sin(30 lin), |30 lin| <= 30: the MUFU path is exact to ~2e-6 there, far below
@@ -680,12 +678,36 @@ static int forward_t(bn_mlp* h, const float* params, const float* origins, int o
     if (int rc = layer_sin<T>(h, A, lda, (const T*)h->Wp[l], h->Kpad[l], P, F, h->Kpad[l], params + c.b_off[l],
                               l == 0 ? 30.0f : 1.0f, w.H[l], w.Hld[l], keep_c ? w.C[l] : nullptr, F, s, h->Kreal[l])) return rc;
   }
-  const T* Hl = w.H[L - 1]; const long long ldl = w.Hld[L - 1];
-  if (sig_only) {
-    heads_fwd_kernel<T><<<heads_grid(h, P), 256, 0, s>>>(hp, params, Hl, ldl, F, nullptr, 0, out, 1, P, true, false);
+  return BN_OK;
+}
+
+// sigma = softplus(w_sigma . h_{L-1} + b) of P rows, written with `pitch` floats per row (density of a trunk-only call)
+template <typename T>
+static int sigma_rows_t(bn_mlp* h, const float* params, const T* Hl, long long ldl, long long P, float* out, int pitch,
+                        cudaStream_t s) {
+  const bn_mlp_cfg& c = h->cfg;
+  if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+    EpiSigmaOut es{params + c.b_off[BN_LIN_SIGMA], nullptr, out, pitch, 0, -1, (int)P};
+    return gemm_tn<T>(h, Hl, ldl, (const T*)h->WsigA, h->F, P, 64, h->F, es, s, h->F / 64);
+  } else {
+    HeadPlan hp; int nch;
+    if (int rc = build_plan(h, 0, &hp, &nch)) return rc;
+    heads_fwd_kernel<T><<<heads_grid(h, P), 256, 0, s>>>(hp, params, Hl, ldl, h->F, nullptr, 0, out, pitch, P, true, false);
     BN_LAUNCH_CHECK();
     return BN_OK;
   }
+}
+
+// feature layer + hidden layer of the heads + their second layers / sigma / learned normal for P rows
+template <typename T>
+static int heads_t(bn_mlp* h, const float* params, long long P, int flags, float* out, int pitch, const Ws<T>& w, cudaStream_t s) {
+  const bool train = flags & BN_MLP_TRAIN;
+  const bn_mlp_cfg& c = h->cfg;
+  const int F = h->F, L = h->L;
+  HeadPlan hp; int nch;
+  if (int rc = build_plan(h, flags, &hp, &nch)) return rc;
+  if (pitch < nch) { set_error("bn_mlp_forward: out_pitch %d < %d channels", pitch, nch); return BN_ERR_ARG; }
+  const T* Hl = w.H[L - 1]; const long long ldl = w.Hld[L - 1];
   if (int rc = layer_bias<T>(h, Hl, ldl, (const T*)h->Wf, F, P, F, F, params + c.b_off[BN_LIN_FEATS], w.FE, F, s)) return rc;
   {
     const int HKa = hp.n_blocks * h->HH;
@@ -709,6 +731,44 @@ static int forward_t(bn_mlp* h, const float* params, const float* origins, int o
     BN_LAUNCH_CHECK();
     return BN_OK;
   }
+}
+
+static inline bool keep_cos(int flags) {
+  return (flags & BN_MLP_TRAIN) || ((flags & BN_MLP_NORMAL_AN) && !(flags & BN_MLP_SIGMA_ONLY));
+}
+
+template <typename T>
+static int forward_t(bn_mlp* h, const float* params, const float* origins, int o_stride, const float* dirs,
+                     int d_stride, const float* z, int N, int S, int flags, float* out, int pitch, void* wsp,
+                     cudaStream_t s) {
+  const long long P = (long long)N * S;
+  const bool sig_only = flags & BN_MLP_SIGMA_ONLY;
+  if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+    if (sig_only && h->F == chain::kF && h->skip >= 1 && h->L <= chain::kMaxBiasLayers && !h->no_chain)
+      return sigma_chain(h, params, origins, o_stride, dirs, d_stride, z, N, S, out, s);
+  }
+  Ws<T> w; carve<T>(h, P, flags, wsp, &w);
+  if (int rc = trunk_t<T>(h, params, origins, o_stride, dirs, d_stride, z, N, S, keep_cos(flags), w, s)) return rc;
+  if (sig_only) {
+    HeadPlan hp; int nch;
+    if (int rc = build_plan(h, flags, &hp, &nch)) return rc;
+    heads_fwd_kernel<T><<<heads_grid(h, P), 256, 0, s>>>(hp, params, w.H[h->L - 1], w.Hld[h->L - 1], h->F, nullptr, 0, out, 1, P, true, false);
+    BN_LAUNCH_CHECK();
+    return BN_OK;
+  }
+  return heads_t<T>(h, params, P, flags, out, pitch, w, s);
+}
+
+// trunk of the rows [row0, row0 + N*S) of a workspace carved for `total` points (+ their density)
+template <typename T>
+static int trunk_rows_t(bn_mlp* h, const float* params, const float* origins, int o_stride, const float* dirs, int d_stride,
+                        const float* z, int N, int S, int flags, long long total, long long row0, float* sigma_out,
+                        void* wsp, cudaStream_t s) {
+  Ws<T> w; carve<T>(h, total, flags, wsp, &w);
+  offset_rows<T>(h, &w, row0);
+  if (int rc = trunk_t<T>(h, params, origins, o_stride, dirs, d_stride, z, N, S, keep_cos(flags), w, s)) return rc;
+  if (sigma_out) return sigma_rows_t<T>(h, params, w.H[h->L - 1], w.Hld[h->L - 1], (long long)N * S, sigma_out, 1, s);
+  return BN_OK;
 }
 
 template <typename T>
@@ -840,7 +900,8 @@ extern "C" __attribute__((visibility("default"))) int bn_mlp_create(const bn_mlp
   cudaDeviceProp prop;
   BN_CUDA(cudaGetDeviceProperties(&prop, dev));
   h->num_sms = prop.multiProcessorCount;
-  h->no_chain = getenv("BN_NO_CHAIN") != nullptr;      // debugging aid: per-layer GEMMs for the density pass
+  h->no_chain = getenv("BN_NO_CHAIN") != nullptr;
+  h->chain_dbg = getenv("BN_CHAIN_DBG") ? atoi(getenv("BN_CHAIN_DBG")) : 0;   // timing experiments (wrong results)      // debugging aid: per-layer GEMMs for the density pass
   // blocks of the heads' hidden layer: rgb first, then every BRDF head that exists
   h->n_blocks = 0;
   h->blk_lin0[0] = BN_LIN_RGB0; h->blk_lin2[0] = BN_LIN_RGB2; h->blk_head[0] = -1; h->n_blocks = 1;
@@ -869,6 +930,8 @@ extern "C" __attribute__((visibility("default"))) int bn_mlp_create(const bn_mlp
   BN_CUDA(cudaMalloc(&h->W2p, HK * 64 * sizeof(__nv_bfloat16)));
   BN_CUDA(cudaMalloc(&h->W2pT, HK * 64 * sizeof(__nv_bfloat16)));
   BN_CUDA(cudaMalloc(&h->Wsig, (size_t)64 * h->F * sizeof(__nv_bfloat16)));
+  BN_CUDA(cudaMalloc(&h->WsigA, (size_t)64 * h->F * sizeof(__nv_bfloat16)));
+  BN_CUDA(cudaMemset(h->WsigA, 0, (size_t)64 * h->F * sizeof(__nv_bfloat16)));
   *out = h;
   return BN_OK;
 }
@@ -876,7 +939,7 @@ extern "C" __attribute__((visibility("default"))) int bn_mlp_create(const bn_mlp
 extern "C" __attribute__((visibility("default"))) void bn_mlp_destroy(bn_mlp* h) {
   if (!h) return;
   for (int l = 0; l < h->L; ++l) { cudaFree(h->Wp[l]); cudaFree(h->WTp[l]); }
-  cudaFree(h->Wf); cudaFree(h->WfT); cudaFree(h->W1); cudaFree(h->W1T); cudaFree(h->b1cat); cudaFree(h->W2p); cudaFree(h->W2pT); cudaFree(h->Wsig);
+  cudaFree(h->Wf); cudaFree(h->WfT); cudaFree(h->W1); cudaFree(h->W1T); cudaFree(h->b1cat); cudaFree(h->W2p); cudaFree(h->W2pT); cudaFree(h->Wsig); cudaFree(h->WsigA);
   delete h;
 }
 
@@ -911,6 +974,41 @@ extern "C" __attribute__((visibility("default"))) int bn_mlp_forward(bn_mlp* h, 
   BN_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
   return h->bf16 ? forward_t<__nv_bfloat16>(h, params, origins, o_stride, dirs, d_stride, z, n_rays, n_samples, flags, out, out_pitch, workspace, stream)
                  : forward_t<float>(h, params, origins, o_stride, dirs, d_stride, z, n_rays, n_samples, flags, out, out_pitch, workspace, stream);
+}
+
+extern "C" __attribute__((visibility("default")))
+int bn_mlp_trunk_forward(bn_mlp* h, const float* params, const float* origins, int o_stride, const float* dirs, int d_stride,
+                         const float* z, int n_rays, int n_samples, int flags, int64_t total_points, int64_t row0,
+                         float* sigma_out, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  BN_CHECK_ARG(h && params && origins && dirs && z && workspace, "null pointer");
+  BN_CHECK_ARG(n_rays > 0 && n_samples > 0, "empty batch");
+  BN_CHECK_ARG(!(flags & BN_MLP_SIGMA_ONLY), "bn_mlp_trunk_forward keeps activations: use bn_mlp_forward for a density-only pass");
+  BN_CHECK_ARG(row0 >= 0 && row0 + (int64_t)n_rays * n_samples <= total_points, "rows out of range");
+  BN_CHECK_ARG(row0 % 128 == 0, "row0 must be a multiple of 128 (TMA boxes / MMA tiles start on 128-row boundaries)");
+  if (!h->synced) { set_error("bn_mlp_trunk_forward: call bn_mlp_sync_weights first"); return BN_ERR_STATE; }
+  if (workspace_bytes < bn_mlp_workspace_bytes(h, total_points, flags)) {
+    set_error("bn_mlp_trunk_forward: workspace too small"); return BN_ERR_STATE;
+  }
+  BN_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
+  return h->bf16 ? trunk_rows_t<__nv_bfloat16>(h, params, origins, o_stride, dirs, d_stride, z, n_rays, n_samples, flags, total_points, row0, sigma_out, workspace, stream)
+                 : trunk_rows_t<float>(h, params, origins, o_stride, dirs, d_stride, z, n_rays, n_samples, flags, total_points, row0, sigma_out, workspace, stream);
+}
+
+extern "C" __attribute__((visibility("default")))
+int bn_mlp_heads_forward(bn_mlp* h, const float* params, int64_t total_points, int flags, float* out, int out_pitch,
+                         void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  BN_CHECK_ARG(h && params && out && workspace, "null pointer");
+  BN_CHECK_ARG(total_points > 0 && !(flags & BN_MLP_SIGMA_ONLY), "bad arguments");
+  if (!h->synced) { set_error("bn_mlp_heads_forward: call bn_mlp_sync_weights first"); return BN_ERR_STATE; }
+  if (workspace_bytes < bn_mlp_workspace_bytes(h, total_points, flags)) {
+    set_error("bn_mlp_heads_forward: workspace too small"); return BN_ERR_STATE;
+  }
+  if (h->bf16) {
+    Ws<__nv_bfloat16> w; carve<__nv_bfloat16>(h, total_points, flags, workspace, &w);
+    return heads_t<__nv_bfloat16>(h, params, total_points, flags, out, out_pitch, w, stream);
+  }
+  Ws<float> w; carve<float>(h, total_points, flags, workspace, &w);
+  return heads_t<float>(h, params, total_points, flags, out, out_pitch, w, stream);
 }
 
 extern "C" __attribute__((visibility("default"))) int bn_mlp_backward(bn_mlp* h, const float* params, const float* out, const float* g_out, int out_pitch,

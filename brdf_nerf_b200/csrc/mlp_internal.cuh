@@ -61,10 +61,12 @@ struct bn_mlp {
   void* W1; void* W1T; float* b1cat;
   void* W2p;                    // [n_blocks*HH, 64] bf16: second-layer head weights as the B operand of the GHD GEMM
   void* W2pT; void* Wsig;       // [64, n_blocks*HH], [64, F] bf16: the same weights / w_sigma as B operands of the forward heads GEMMs
+  void* WsigA;                  // [64, F] bf16, row 0 = w_sigma: density of a trunk-only call (bn_mlp_trunk_forward)
   int n_blocks;
   int blk_lin0[bn::kMaxBlocks], blk_lin2[bn::kMaxBlocks], blk_head[bn::kMaxBlocks];
   bool synced;
   bool no_chain;
+  int chain_dbg;
   long long* chain_trace;
 };
 

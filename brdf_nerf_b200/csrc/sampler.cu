@@ -277,6 +277,39 @@ extern "C" __attribute__((visibility("default"))) int bn_merge_samples(const flo
   return BN_OK;
 }
 
+// Applies sort_idx to per-point rows.  The MLP evaluates the points of a ray in generation order,
+// stratified block first ([N][S1] rows) then guided block ([N][G] rows), so that the trunk activations of the
+// stratified points are computed ONCE and shared by the density pass and the full pass (the reference evaluates
+// them twice, rendering.py:225 and :274); compositing needs them in depth order (rendering.py:271-273).
+//   scatter == 0: sorted[r][s][:] = blocks[row(r, idx[r][s])][:]       (forward: packed MLP rows -> depth order)
+//   scatter == 1: blocks[row(r, idx[r][s])][:] = sorted[r][s][:]       (backward: gradients -> MLP row order)
+// row(r, j) = j < S1 ? r*S1 + j : N*S1 + r*G + (j - S1).  idx[r] is a permutation, so scatter is a bijection.
+__global__ void permute_rows_kernel(const float* __restrict__ src, const long long* __restrict__ idx, float* __restrict__ dst,
+                                    int N, int S1, int G, int pitch, int scatter) {
+  const int S = S1 + G;
+  const long long tot = (long long)N * S * pitch;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (long long)gridDim.x * blockDim.x) {
+    const long long pt = e / pitch; const int c = (int)(e % pitch);
+    const long long r = pt / S;
+    const int j = (int)idx[pt];
+    const long long row = j < S1 ? r * S1 + j : (long long)N * S1 + r * G + (j - S1);
+    if (scatter) dst[row * pitch + c] = src[e]; else dst[e] = src[row * pitch + c];
+  }
+}
+
+extern "C" __attribute__((visibility("default")))
+int bn_permute_samples(const float* src, const int64_t* sort_idx, float* dst, int n_rays, int n_samples, int n_guided,
+                       int pitch, int scatter, cudaStream_t stream) {
+  BN_CHECK_ARG(src && sort_idx && dst && src != dst, "null or aliased pointer");
+  BN_CHECK_ARG(n_samples >= 1 && n_guided >= 1 && pitch >= 1, "bad sizes");
+  if (n_rays <= 0) return n_rays == 0 ? BN_OK : BN_ERR_ARG;
+  const long long tot = (long long)n_rays * (n_samples + n_guided) * pitch;
+  const int grid = (int)min((tot + 255) / 256, (long long)148 * 16);
+  permute_rows_kernel<<<grid, 256, 0, stream>>>(src, (const long long*)sort_idx, dst, n_rays, n_samples, n_guided, pitch, scatter);
+  BN_LAUNCH_CHECK();
+  return BN_OK;
+}
+
 extern "C" __attribute__((visibility("default"))) int bn_sort_rows(const float* in, float* out, int n_rays, int n, cudaStream_t stream) {
   BN_CHECK_ARG(in && out && n >= 1 && n <= 2 * kMaxBins, "bad arguments");
   if (n_rays <= 0) return n_rays == 0 ? BN_OK : BN_ERR_ARG;

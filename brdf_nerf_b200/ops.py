@@ -154,6 +154,27 @@ def mlp_forward(model, origins, o_stride, dirs, d_stride, z, flags, out, pitch, 
                                     C.c_void_p(ws.data_ptr()), ws.numel(), L.stream_ptr()))
 
 
+def mlp_trunk_forward(model, origins, o_stride, dirs, d_stride, z, flags, total_points, row0, sigma_out, ws):
+    """PE + trunk of the points of `z` into rows [row0, row0 + z.numel()) of a workspace sized for total_points."""
+    n, s = z.shape
+    L.check(L.load().bn_mlp_trunk_forward(model.handle(), L.ptr(model.flat_params), C.c_void_p(origins.data_ptr()), o_stride,
+                                          C.c_void_p(dirs.data_ptr()), d_stride, L.ptr(z), n, s, flags, int(total_points),
+                                          int(row0), L.ptr(sigma_out), C.c_void_p(ws.data_ptr()), ws.numel(), L.stream_ptr()))
+
+
+def mlp_heads_forward(model, total_points, flags, out, pitch, ws):
+    L.check(L.load().bn_mlp_heads_forward(model.handle(), L.ptr(model.flat_params), int(total_points), flags, L.ptr(out), pitch,
+                                          C.c_void_p(ws.data_ptr()), ws.numel(), L.stream_ptr()))
+
+
+def permute_samples(src, idx, n, s1, g, pitch, scatter: bool):
+    """sort_idx applied to per-point rows: MLP row order ([N][S1] block, [N][G] block) <-> depth order (N,S1+G)."""
+    dst = torch.empty((n, s1 + g, pitch) if not scatter else (n * (s1 + g), pitch), dtype=torch.float32, device=src.device)
+    L.check(L.load().bn_permute_samples(L.ptr(src), L.ptr(idx, torch.int64), L.ptr(dst), n, s1, g, pitch, int(bool(scatter)),
+                                        L.stream_ptr()))
+    return dst
+
+
 def mlp_backward(model, out, g_out, pitch, n, s, flags, g_params, ws):
     L.check(L.load().bn_mlp_backward(model.handle(), L.ptr(model.flat_params), L.ptr(out), L.ptr(g_out), pitch, n, s, flags,
                                      L.ptr(g_params), C.c_void_p(ws.data_ptr()), ws.numel(), L.stream_ptr()))

@@ -55,6 +55,9 @@ class _State:
     rays: Optional[torch.Tensor] = None
     z: Optional[torch.Tensor] = None
     packed: Optional[torch.Tensor] = None
+    packed_rows: Optional[torch.Tensor] = None      # MLP row order when the trunk is shared between the passes
+    idx: Optional[torch.Tensor] = None
+    s1: int = 0
     noise: Optional[torch.Tensor] = None
     noise_std: float = 0.0
     irr: Optional[torch.Tensor] = None
@@ -117,11 +120,25 @@ def _forward(model, args, rays: torch.Tensor, draws: Optional[Draws], mode: str,
     t_g, gauss_g = ops.sampler_tables(G, d_range, dev)
 
     origins, dirs, sun = rays[:, 0:3], rays[:, 3:6], rays[:, 8:11]
+    nr_an = model.normal in ("analystic_learned", "analystic") or bTestNormal
+    nr_lr = model.normal in ("analystic_learned", "learned")
+    flags = model.mlp_flags(apply_brdf=apply_brdf, apply_theta=apply_theta, nr_an_on=nr_an, nr_lr_on=nr_lr, train=train)
+    # The stratified points are evaluated by BOTH passes of the reference (rendering.py:225 and :274, same weights,
+    # same points).  Here their trunk runs once: pass 1 keeps the activations in the first N*S1 rows of the pass-2
+    # workspace, pass 2 adds the guided points as rows N*S1.. and the heads run over all rows; sort_idx is applied
+    # to the packed rows afterwards (bn_permute_samples).  Needs 128-row aligned blocks.
+    share_trunk = (not gsam_only) and (N * S1) % 128 == 0 and not getattr(model, "no_trunk_sharing", False)
     # ---- pass 1: stratified samples, sigma only (no tape: the reference detaches it, rendering.py:262)
     z1 = ops.sample_stratified(rays[:, 6], rays[:, 7], 11, t_vals, draws.u_strat)
     sigma1 = torch.empty((N, S1), dtype=torch.float32, device=dev)
-    ws1 = model.workspace(N * max(S1, S_sun), L.MLP_SIGMA_ONLY, tag="ws_sigma")
-    ops.mlp_forward(model, origins, 11, dirs, 11, z1, L.MLP_SIGMA_ONLY, sigma1, 1, ws1)
+    ws = None
+    if share_trunk:
+        ws = model.workspace(N * S, flags, tag="ws_train" if train else "ws_full")
+        ops.mlp_trunk_forward(model, origins, 11, dirs, 11, z1, flags, N * S, 0, sigma1, ws)
+    if want_sun or not share_trunk:
+        ws1 = model.workspace(N * max(S1, S_sun), L.MLP_SIGMA_ONLY, tag="ws_sigma")
+    if not share_trunk:
+        ops.mlp_forward(model, origins, 11, dirs, 11, z1, L.MLP_SIGMA_ONLY, sigma1, 1, ws1)
     _, _, w1, depth1, _ = ops.composite_sigma(z1, sigma1, draws.noise1, noise_std)
 
     # ---- optional sun-visibility march from the predicted surface (rendering.py:244-259)
@@ -156,9 +173,6 @@ def _forward(model, args, rays: torch.Tensor, draws: Optional[Draws], mode: str,
         z, idx, z_unsort = ops.merge_samples(z1, z2)
 
     # ---- pass 2: full model
-    nr_an = model.normal in ("analystic_learned", "analystic") or bTestNormal
-    nr_lr = model.normal in ("analystic_learned", "learned")
-    flags = model.mlp_flags(apply_brdf=apply_brdf, apply_theta=apply_theta, nr_an_on=nr_an, nr_lr_on=nr_lr, train=train)
     C = model.out_channels(flags)
     brdf_type = _call_brdf_type(model, args, apply_brdf)
     if C == 4:
@@ -170,11 +184,20 @@ def _forward(model, args, rays: torch.Tensor, draws: Optional[Draws], mode: str,
         raise RuntimeError("apply_brdf=True without any BRDF head: unbound `brdf` in the reference (App. C.6)")
     multi = bool(model.MultiBRDF) and brdf_type != L.BN_BRDF_NONE
     pitch = C + (3 if multi else 0)
-    packed = torch.empty((N, S, pitch), dtype=torch.float32, device=dev)
-    ws = model.workspace(N * S, flags, tag="ws_train" if train else "ws_full")
-    ops.mlp_forward(model, origins, 11, dirs, 11, z, flags, packed, pitch, ws)
-    if nr_an:
-        ops.mlp_normals_forward(model, packed, pitch, N, S, flags, ws)
+    packed_rows = None
+    if share_trunk:
+        packed_rows = torch.empty((N * S, pitch), dtype=torch.float32, device=dev)
+        ops.mlp_trunk_forward(model, origins, 11, dirs, 11, z2, flags, N * S, N * S1, None, ws)
+        ops.mlp_heads_forward(model, N * S, flags, packed_rows, pitch, ws)
+        if nr_an:
+            ops.mlp_normals_forward(model, packed_rows, pitch, N, S, flags, ws)
+        packed = ops.permute_samples(packed_rows, idx, N, S1, G, pitch, scatter=False)
+    else:
+        packed = torch.empty((N, S, pitch), dtype=torch.float32, device=dev)
+        ws = model.workspace(N * S, flags, tag="ws_train" if train else "ws_full")
+        ops.mlp_forward(model, origins, 11, dirs, 11, z, flags, packed, pitch, ws)
+        if nr_an:
+            ops.mlp_normals_forward(model, packed, pitch, N, S, flags, ws)
 
     cfg = L.ShadeCfg()
     cfg.n_channels = pitch
@@ -216,7 +239,8 @@ def _forward(model, args, rays: torch.Tensor, draws: Optional[Draws], mode: str,
     sh = ops.shade_rays_forward(cfg, rays, acc, wsum, acc_irr, irr_last, want_normal=has_normal,
                                 want_brdf=brdf_type != L.BN_BRDF_NONE and not multi)
 
-    st = _State(n=N, s=S, pitch=pitch, flags=flags, cfg=cfg, rays=rays, z=z, packed=packed,
+    st = _State(n=N, s=S, pitch=pitch, flags=flags, cfg=cfg, rays=rays, z=z, packed=packed, packed_rows=packed_rows,
+                idx=idx, s1=S1,
                 noise=draws.noise2 if noise_std != 0.0 else None, noise_std=noise_std, irr=irr, irr_last=irr_last,
                 alpha=alpha, trans=trans, weights=w, wsum=wsum, acc=acc, acc_irr=acc_irr, ws=ws, multi=multi,
                 normal_an=nr_an)
@@ -239,9 +263,13 @@ def _backward(model, st: _State, g_rgb, g_depth, g_weights, g_packed, g_params: 
                                 None if g_packed is None else g_packed.contiguous())
     if st.multi:
         ops.brdf_points_backward(st.cfg, st.rays, st.packed, gp)
+    out = st.packed
+    if st.packed_rows is not None:            # gradients back into the MLP's row order (inverse of sort_idx)
+        gp = ops.permute_samples(gp, st.idx, st.n, st.s1, st.s - st.s1, st.pitch, scatter=True)
+        out = st.packed_rows
     if st.normal_an:
-        ops.mlp_normals_backward(model, st.packed, gp, st.pitch, st.n, st.s, st.flags, g_params, st.ws)
-    ops.mlp_backward(model, st.packed, gp, st.pitch, st.n, st.s, st.flags, g_params, st.ws)
+        ops.mlp_normals_backward(model, out, gp, st.pitch, st.n, st.s, st.flags, g_params, st.ws)
+    ops.mlp_backward(model, out, gp, st.pitch, st.n, st.s, st.flags, g_params, st.ws)
 
 
 class _RenderFunction(torch.autograd.Function):

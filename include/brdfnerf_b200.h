@@ -82,6 +82,14 @@ int bn_sample_guided(const float* z1, const float* depth, const float* weights,
 int bn_merge_samples(const float* z1, const float* z2, float* z_out, int64_t* idx_out,
                      float* unsort_out, int n_rays, int n_samples, int n_guided, cudaStream_t stream);
 
+/* Applies sort_idx (rendering.py:271-273) to per-point rows of `pitch` floats.  The MLP may evaluate the
+ * points of a call in generation order - all stratified samples ([N][S1] rows), then all guided samples
+ * ([N][G] rows) - so that the stratified points' trunk is evaluated once for the density pass and the full
+ * pass (bn_mlp_trunk_forward); compositing wants depth order.  scatter = 0: dst (N,S1+G,pitch) depth-ordered
+ * <- src in MLP row order; scatter = 1: the inverse (gradients).  src != dst. */
+int bn_permute_samples(const float* src, const int64_t* sort_idx, float* dst, int n_rays, int n_samples,
+                       int n_guided, int pitch, int scatter, cudaStream_t stream);
+
 /* per-row ascending sort (rendering.py:263). */
 int bn_sort_rows(const float* in, float* out, int n_rays, int n, cudaStream_t stream);
 
@@ -236,6 +244,21 @@ int bn_mlp_forward(bn_mlp* h, const float* params, const float* origins, int o_s
                    const float* dirs, int d_stride, const float* z, int n_rays, int n_samples,
                    int flags, float* out, int out_pitch, void* workspace, size_t workspace_bytes,
                    cudaStream_t stream);
+
+/* The same forward in two steps, for callers that evaluate the points of a call in several batches
+ * (render_rays: stratified samples first, guided samples once the density of the first batch is known,
+ * rendering.py:225-274) without evaluating any point twice:
+ *   bn_mlp_trunk_forward  PE + trunk of n_rays*n_samples points; their activations go to rows
+ *                         [row0, row0 + n_rays*n_samples) of a workspace sized for total_points (row0 % 128 == 0);
+ *                         sigma_out (nullable, one float per point) = softplus(sigma_from_xyz(h)), spsbrdfnerf.py:682;
+ *   bn_mlp_heads_forward  feature layer + every head + sigma for all total_points rows -> packed rows.
+ * bn_mlp_backward / bn_mlp_normals_* then run on the whole workspace (n_rays*n_samples = total_points). */
+int bn_mlp_trunk_forward(bn_mlp* h, const float* params, const float* origins, int o_stride,
+                         const float* dirs, int d_stride, const float* z, int n_rays, int n_samples, int flags,
+                         int64_t total_points, int64_t row0, float* sigma_out, void* workspace,
+                         size_t workspace_bytes, cudaStream_t stream);
+int bn_mlp_heads_forward(bn_mlp* h, const float* params, int64_t total_points, int flags, float* out,
+                         int out_pitch, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 /* backward of the last BN_MLP_TRAIN forward on `workspace`: `out` is that forward's packed output,
  * g_out (P, out_pitch) its gradient -> g_params (flat fp32, ACCUMULATED: zero it at the start of a

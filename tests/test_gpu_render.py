@@ -128,3 +128,48 @@ def test_no_cpu_fallback():
     model = load_model(args)
     with pytest.raises(L.BnError):
         render_rays({"coarse": model}, args, make_rays(4).rays, None)
+
+
+@pytest.mark.parametrize("cfg,kw", [("lambertian_ds", {}), ("rpv111", dict(apply_brdf=True, cos_irra_on=True)),
+                                    ("rpv111_multi", dict(apply_brdf=True, cos_irra_on=True))])
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("bf16", 6e-2)])
+def test_shared_trunk_matches_two_pass(cuda, cfg, kw, precision, tol):
+    """render_rays evaluates the stratified points' trunk once (bn_mlp_trunk_forward + bn_mlp_heads_forward +
+    bn_permute_samples); `no_trunk_sharing` runs the reference's literal two passes (density pass, then all points
+    again).  Same outputs and same weight gradients; also covers the odd-row-count fallback (N*S1 % 128 != 0)."""
+    args = named_config(cfg)
+    ds = cfg.endswith("_ds")
+    n = 64
+    batch = make_rays(n, depth_supervision=ds).to(cuda)
+    S1, Gs = args.n_samples, args.guided_samples
+    od = RT.Draws.make(n, S1, Gs, S1 + Gs, seed=5, with_gt=ds)
+    sup = dict(valid_depth=batch.valid_depth, target_depths=batch.target_depths, target_std=batch.target_std) if ds else {}
+    got = {}
+    for share in (True, False):
+        torch.manual_seed(0)
+        model = load_model(args, precision=precision).to(cuda)
+        model.no_trunk_sharing = not share
+        draws = Draws(u_strat=od.u_strat, u_pred=od.u_pred, u_gt=od.u_gt)
+        res, _ = render_rays({"coarse": model}, args, batch.rays, None, mode="train", _draws=draws, **sup, **kw)
+        loss = LT.train_loss(res, batch, args)
+        model.flat_grads.zero_()
+        loss.backward()
+        got[share] = ({k: v.detach().clone() for k, v in res.items()}, model.flat_grads.clone())
+    (ra, ga), (rb, gb_) = got[True], got[False]
+    assert set(ra) == set(rb)
+    for k in ("rgb_coarse", "depth_coarse", "weights_coarse", "sigmas_coarse", "albedo_coarse", "z_vals_coarse"):
+        d = (ra[k] - rb[k]).abs().max().item()
+        lim = tol * max(1.0, rb[k].abs().max().item()) if k == "sigmas_coarse" else tol
+        assert d <= lim, f"{cfg}/{precision}: {k} differs by {d}"
+    assert torch.equal(ra["sort_idx_coarse"], rb["sort_idx_coarse"]) or precision == "bf16"
+    gs = gb_.abs().max().item()
+    gd = (ga - gb_).abs().max().item()
+    assert gd <= (1e-4 if precision == "fp32" else 0.15) * gs, f"{cfg}/{precision}: gradients differ by {gd} (scale {gs})"
+    # 63 rays: N*S1 is not a multiple of 128 -> the two-pass fallback must still work
+    torch.manual_seed(0)
+    model = load_model(args, precision=precision).to(cuda)
+    b2 = make_rays(63, depth_supervision=ds).to(cuda)
+    sup2 = dict(valid_depth=b2.valid_depth, target_depths=b2.target_depths, target_std=b2.target_std) if ds else {}
+    with torch.no_grad():
+        r2, _ = render_rays({"coarse": model}, args, b2.rays, None, mode="train", **sup2, **kw)
+    assert torch.isfinite(r2["rgb_coarse"]).all() and r2["rgb_coarse"].shape == (63, 3)
