@@ -610,22 +610,22 @@ static int sigma_chain(bn_mlp* h, const float* params, const float* origins, int
 // trunk of a training (or analytic-normal) forward as ONE fused kernel: X3, H_l, C_l of every layer are
 // written for the backward pass, the layer inputs themselves never leave the SM
 static int train_chain(bn_mlp* h, const float* params, const float* origins, int o_stride, const float* dirs, int d_stride,
-                       const float* z, int N, int S, const Ws<__nv_bfloat16>& w, float* out, int pitch, int sigma_ch, cudaStream_t s) {
+                       const float* z, int N, int S, const Ws<__nv_bfloat16>& w, bool keep_c, bool train, cudaStream_t s) {
   const bn_mlp_cfg& c = h->cfg;
   const long long P = (long long)N * S;
   chain::TrainChainParams prm;
   for (int l = 0; l < h->L; ++l) {
     if (int rc = tc::make_map_bf16(&prm.wmap[l], h->Wp[l], h->F, h->Kpad[l], h->Kpad[l], 64, 128)) return rc;
     if (int rc = tc::stream_map(&prm.hmap[l], w.H[l], P, h->F, w.Hld[l])) return rc;
-    if (int rc = tc::make_map_bf16_sw(&prm.cmap[l], w.C[l], P, h->F, h->F, 32, 32, 64)) return rc;
+    if (keep_c) { if (int rc = tc::make_map_bf16_sw(&prm.cmap[l], w.C[l], P, h->F, h->F, 32, 32, 64)) return rc; }
+    else memset(&prm.cmap[l], 0, sizeof(prm.cmap[l]));
     prm.bias[l] = params + c.b_off[l];
   }
   if (int rc = tc::stream_map(&prm.x3map, w.X3, P, kEncPad, w.ldx3)) return rc;
   prm.origins = origins; prm.dirs = dirs; prm.z = z;
-  (void)out; (void)pitch; (void)sigma_ch;     // sigma stays in heads_fwd_kernel: fusing it here cost more (registers) than it saved
   prm.P = P; prm.o_stride = o_stride; prm.d_stride = d_stride; prm.S = S;
   prm.L = h->L; prm.skip = h->skip; prm.n_freq = c.n_freq_xyz;
-  prm.dbg = h->chain_dbg;
+  prm.store_c = keep_c ? 1 : 0; prm.h_from = train ? 0 : h->L - 1;
   const int n_blocks = (int)ceil_div_ll(P, 256);
   constexpr int smem = chain::chain_smem<true>();
   BN_CUDA(cudaFuncSetAttribute(chain::train_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -659,13 +659,13 @@ static void offset_rows(const bn_mlp* h, Ws<T>* w, long long row0) {
 // PE + trunk of N*S points whose activations land in `w` (already offset to the first row of this call)
 template <typename T>
 static int trunk_t(bn_mlp* h, const float* params, const float* origins, int o_stride, const float* dirs, int d_stride,
-                   const float* z, int N, int S, bool keep_c, const Ws<T>& w, cudaStream_t s) {
+                   const float* z, int N, int S, bool keep_c, bool train, const Ws<T>& w, cudaStream_t s) {
   const long long P = (long long)N * S;
   const bn_mlp_cfg& c = h->cfg;
   const int F = h->F, L = h->L;
   if constexpr (std::is_same<T, __nv_bfloat16>::value) {
-    if (keep_c && h->F == chain::kF && h->skip >= 1 && !h->no_chain)
-      return train_chain(h, params, origins, o_stride, dirs, d_stride, z, N, S, w, nullptr, 0, 0, s);
+    if (h->F == chain::kF && h->skip >= 1 && !h->no_chain)
+      return train_chain(h, params, origins, o_stride, dirs, d_stride, z, N, S, w, keep_c, train, s);
   }
   encode_kernel<T><<<(unsigned)ceil_div_ll(P, 128), 128, 0, s>>>(origins, o_stride, dirs, d_stride, z, S, P,
                                                                c.n_freq_xyz, w.X3, w.ldx3);
@@ -748,7 +748,7 @@ static int forward_t(bn_mlp* h, const float* params, const float* origins, int o
       return sigma_chain(h, params, origins, o_stride, dirs, d_stride, z, N, S, out, s);
   }
   Ws<T> w; carve<T>(h, P, flags, wsp, &w);
-  if (int rc = trunk_t<T>(h, params, origins, o_stride, dirs, d_stride, z, N, S, keep_cos(flags), w, s)) return rc;
+  if (int rc = trunk_t<T>(h, params, origins, o_stride, dirs, d_stride, z, N, S, keep_cos(flags), (flags & BN_MLP_TRAIN) != 0, w, s)) return rc;
   if (sig_only) {
     HeadPlan hp; int nch;
     if (int rc = build_plan(h, flags, &hp, &nch)) return rc;
@@ -766,7 +766,7 @@ static int trunk_rows_t(bn_mlp* h, const float* params, const float* origins, in
                         void* wsp, cudaStream_t s) {
   Ws<T> w; carve<T>(h, total, flags, wsp, &w);
   offset_rows<T>(h, &w, row0);
-  if (int rc = trunk_t<T>(h, params, origins, o_stride, dirs, d_stride, z, N, S, keep_cos(flags), w, s)) return rc;
+  if (int rc = trunk_t<T>(h, params, origins, o_stride, dirs, d_stride, z, N, S, keep_cos(flags), (flags & BN_MLP_TRAIN) != 0, w, s)) return rc;
   if (sigma_out) return sigma_rows_t<T>(h, params, w.H[h->L - 1], w.Hld[h->L - 1], (long long)N * S, sigma_out, 1, s);
   return BN_OK;
 }
@@ -901,7 +901,7 @@ extern "C" __attribute__((visibility("default"))) int bn_mlp_create(const bn_mlp
   BN_CUDA(cudaGetDeviceProperties(&prop, dev));
   h->num_sms = prop.multiProcessorCount;
   h->no_chain = getenv("BN_NO_CHAIN") != nullptr;
-  h->chain_dbg = getenv("BN_CHAIN_DBG") ? atoi(getenv("BN_CHAIN_DBG")) : 0;   // timing experiments (wrong results)      // debugging aid: per-layer GEMMs for the density pass
+      // debugging aid: per-layer GEMMs for the density pass
   // blocks of the heads' hidden layer: rgb first, then every BRDF head that exists
   h->n_blocks = 0;
   h->blk_lin0[0] = BN_LIN_RGB0; h->blk_lin2[0] = BN_LIN_RGB2; h->blk_head[0] = -1; h->n_blocks = 1;

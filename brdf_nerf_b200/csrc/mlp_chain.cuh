@@ -59,7 +59,8 @@ struct TrainChainParams {
   const float* origins; const float* dirs; const float* z;
   long long P;
   int o_stride, d_stride, S, L, skip, n_freq;
-  int dbg;                              // timing experiments only (BN_CHAIN_DBG): 1 no C store, 2 no cosine, 4 no H store, 8 no box wait
+  int store_c;                          // 0: inference without analytic normals - no cosines are computed or stored
+  int h_from;                           // h_l leaves the SM only for l >= h_from (0 when training, L-1 for inference)
 };
 
 template <bool kTrain> __host__ __device__ constexpr int chain_smem() {
@@ -412,17 +413,18 @@ __global__ void __launch_bounds__(kThreads, 1) train_chain_kernel(const __grid_c
               const float a2 = w0 * (__uint_as_float(v[4 * j + 2]) + b.z), a3 = w0 * (__uint_as_float(v[4 * j + 3]) + b.w);
               pk[u][2 * j] = bf_pack(__sinf(a0), __sinf(a1));
               pk[u][2 * j + 1] = bf_pack(__sinf(a2), __sinf(a3));
-              if (prm.dbg & 2) { pc[2 * j] = pk[u][2 * j]; pc[2 * j + 1] = pk[u][2 * j + 1]; }
-              else {
+              if (prm.store_c) {
                 pc[2 * j] = bf_pack(w0 * __cosf(a0), w0 * __cosf(a1));
                 pc[2 * j + 1] = bf_pack(w0 * __cosf(a2), w0 * __cosf(a3));
               }
             }
-            if (lane == 0 && !(prm.dbg & 8)) bulk_wait_read0();   // this warp's previous boxes were read out by the TMA
-            __syncwarp();
+            if (prm.store_c) {
+              if (lane == 0) bulk_wait_read0();              // this warp's previous boxes were read out by the TMA
+              __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              sts128(cbox + crow_off + ((j << 4) ^ cswz), pc[4 * j], pc[4 * j + 1], pc[4 * j + 2], pc[4 * j + 3]);
+              for (int j = 0; j < 4; ++j)
+                sts128(cbox + crow_off + ((j << 4) ^ cswz), pc[4 * j], pc[4 * j + 1], pc[4 * j + 2], pc[4 * j + 3]);
+            }
             if (n == 1) {                                    // every MMA of this layer has retired: publish K block 5+u now
               uint8_t* kbp = sAct + (5 + u) * kKBBytes;
 #pragma unroll
@@ -431,7 +433,7 @@ __global__ void __launch_bounds__(kThreads, 1) train_chain_kernel(const __grid_c
             }
             fence_async_smem();
             __syncwarp();
-            if (lane == 0 && !(prm.dbg & 3)) { tma_store_2d(&prm.cmap[l], cbox, col0, grow0); bulk_commit(); }
+            if (lane == 0 && prm.store_c) { tma_store_2d(&prm.cmap[l], cbox, col0, grow0); bulk_commit(); }
             if (n == 1 && !last) arrive_leader(&act_ready[5 + u]);
           }
           if (n == 0) {
@@ -454,7 +456,7 @@ __global__ void __launch_bounds__(kThreads, 1) train_chain_kernel(const __grid_c
           // (The leader waits for its stores to be read out at its next unit, and the next barrier of this kind
           // precedes every overwrite of these K blocks by the other warp.)
           named_bar_sync(1 + q, 64);
-          if (leader && !(prm.dbg & 4)) {
+          if (leader && l >= prm.h_from) {
 #pragma unroll
             for (int u = 0; u < 4; ++u)
               tma_store_2d(&prm.hmap[l], sAct + (1 + n * 4 + u) * kKBBytes + q * 4096, n * 256 + u * 64, grow0);

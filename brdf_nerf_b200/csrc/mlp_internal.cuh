@@ -66,7 +66,6 @@ struct bn_mlp {
   int blk_lin0[bn::kMaxBlocks], blk_lin2[bn::kMaxBlocks], blk_head[bn::kMaxBlocks];
   bool synced;
   bool no_chain;
-  int chain_dbg;
   long long* chain_trace;
 };
 

@@ -18,6 +18,7 @@ Differences from the reference that are visible to a caller are listed in DESIGN
 from __future__ import annotations
 
 import dataclasses
+import os
 from typing import Dict, Optional
 
 import torch
@@ -127,7 +128,8 @@ def _forward(model, args, rays: torch.Tensor, draws: Optional[Draws], mode: str,
     # same points).  Here their trunk runs once: pass 1 keeps the activations in the first N*S1 rows of the pass-2
     # workspace, pass 2 adds the guided points as rows N*S1.. and the heads run over all rows; sort_idx is applied
     # to the packed rows afterwards (bn_permute_samples).  Needs 128-row aligned blocks.
-    share_trunk = (not gsam_only) and (N * S1) % 128 == 0 and not getattr(model, "no_trunk_sharing", False)
+    share_trunk = ((not gsam_only) and (N * S1) % 128 == 0 and not getattr(model, "no_trunk_sharing", False)
+                   and not os.environ.get("BN_NO_TRUNK_SHARING"))     # env: A/B timing aid
     # ---- pass 1: stratified samples, sigma only (no tape: the reference detaches it, rendering.py:262)
     z1 = ops.sample_stratified(rays[:, 6], rays[:, 7], 11, t_vals, draws.u_strat)
     sigma1 = torch.empty((N, S1), dtype=torch.float32, device=dev)

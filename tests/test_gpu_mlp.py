@@ -193,3 +193,32 @@ def test_sigma_chain_bf16(cuda, n, monkeypatch):
     assert torch.isfinite(sig).all()
     # bf16 activations: same error class as the per-layer bf16 path
     assert e_ref <= max(2.0 * e_lay, 2e-2), (e_ref, e_lay)
+
+
+@pytest.mark.parametrize("cfg,kw,n", [("lambertian", {}, 1000), ("lambertian", {}, 70001),
+                                      ("rpv111", dict(apply_brdf=True, nr_an_on=True), 3000)])
+def test_inference_chain_bf16(cuda, cfg, kw, n, monkeypatch):
+    """Inference forward in bf16: the fused trunk kernel (train_chain_kernel with store_c = 0 / h_from = L-1: only the
+    last layer's activations and, for analytic normals, the cosines leave the SM) against the per-layer tcgen05 GEMMs
+    (BN_NO_CHAIN=1) and the fp32 mode."""
+    over = dict(normal="analystic") if kw.get("nr_an_on") else {}
+    _, m32, _ = _models(cfg, cuda, **over)
+    _, m16, _ = _models(cfg, cuda, precision="bf16", **over)
+    x = _pts(n, 21).to(cuda)
+    with torch.no_grad():
+        a = m32(x, **kw)
+        b = m16(x, **kw)
+    monkeypatch.setenv("BN_NO_CHAIN", "1")
+    _, m16l, _ = _models(cfg, cuda, precision="bf16", **over)
+    with torch.no_grad():
+        c = m16l(x, **kw)
+    assert torch.isfinite(b).all()
+    cols = [0, 1, 2, 3] + list(range(7, b.shape[1])) if kw.get("nr_an_on") else list(range(b.shape[1]))
+    e_chain = (a - b)[:, cols].abs().max().item()
+    e_layer = (a - c)[:, cols].abs().max().item()
+    print(f"{cfg} n={n}: chain vs fp32 {e_chain:.3e}, per-layer bf16 vs fp32 {e_layer:.3e}")
+    assert e_chain <= max(2.0 * e_layer, 5e-2), (e_chain, e_layer)
+    if kw.get("nr_an_on"):        # unit normals: direction agrees where the per-layer bf16 path agrees with fp32
+        na, nb, nc = a[:, 4:7], b[:, 4:7], c[:, 4:7]
+        ok = (na * nc).sum(-1) > 0.9
+        assert ((na * nb).sum(-1)[ok] > 0.8).float().mean().item() > 0.98
