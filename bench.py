@@ -30,12 +30,12 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 RAYS_PER_GPU = 1024
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel of the step (trunk dgrad GEMM,
-# gemm_tc_kernel<256,5,tn,pair,EpiDgradT<mul>>, P = 131072, K = N = 512) from profiles/r01c_ncu_full_gemm_pair.csv
-NCU_GEMM_DRAM_BYTES_PER_LAUNCH = 370.6e6
-NCU_GEMM_TRAFFIC_NOTE = ("ncu --set full, trunk dgrad GEMM: 269.0 MB read + 101.6 MB written per launch (algorithmic 256 MiB read "
-                         "[dZ + cos mask] + 128 MiB written; the tail of the writes is still in L2 when the kernel ends). "
-                         "train_chain_kernel (profiles/r01d): 27 MB read, 2.11 GB written = algorithmic 2.15 GB")
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel of the step, chain::train_chain_kernel at
+# P = 65536 points (two launches per step: stratified points, guided points), from the ncu --set full capture under profiles/
+NCU_CHAIN_DRAM_BYTES_PER_LAUNCH = 1.07e9
+NCU_TRAFFIC_NOTE = ("ncu --set full (profiles/r01d_ncu_full_chain_kernels.csv, P = 131072): 27 MB read + 2.11 GB written = the "
+                    "algorithmic 2.15 GB (h_l, c_l of 8 layers + encoding, bf16); per launch at P = 65536: half of that. "
+                    "trunk dgrad GEMM (profiles/r01c): 269 MB read + 102 MB written per launch vs 384 MiB algorithmic")
 METRIC = "train rays/s (SpS-BRDF-NeRF, 1/2/4/8 B200); MLP tensor-pipe %; composite GB/s"
 
 
@@ -47,14 +47,15 @@ def _peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
 
 
-def mlp_flops_per_ray(args, n_coarse, n_full, train=True):
+def mlp_flops_per_ray(args, n_coarse, n_full, train=True, shared_trunk=False):
     """Algorithmic MLP FLOPs of one ray: sigma-only pass over n_coarse points, full pass
-    over n_full points, backward (2x) through the full pass only."""
+    over n_full points, backward (2x) through the full pass only.  shared_trunk: what this library executes — the
+    stratified points' trunk is evaluated once and shared by both passes (the reference evaluates it twice)."""
     F, L = args.fc_feat, args.fc_layers
     enc = 60 if args.mapping else 3
     trunk = enc * F + (L - 2) * F * F + (F + enc) * F
     sig, feat, col = F, F * F, F * (F // 2) + (F // 2) * 3
-    fwd = n_coarse * (trunk + sig) + n_full * (trunk + sig + feat + col)
+    fwd = n_coarse * ((0 if shared_trunk else trunk) + sig) + n_full * (trunk + sig + feat + col)
     bwd = 2 * n_full * (trunk + sig + feat + col) if train else 0
     return 2.0 * (fwd + bwd)
 
@@ -239,26 +240,36 @@ def run_ours(opts):
         eager = Trainer(model, args, world_size=1, use_graph=False)
         eager.m, eager.v, eager.step_count = trainer.m, trainer.v, trainer.step_count
         nprof = 3
+        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pe0.record()
         for _ in range(nprof):
             eager.step(batch)
-        cnt = (C.c_longlong * 2)(); tms = (C.c_double * 2)(); work = (C.c_double * 2)()
-        lib.bn_profile_collect(2, cnt, tms, work)
+        pe1.record()
+        torch.cuda.synchronize()
+        ms_eager = pe0.elapsed_time(pe1) / nprof      # the profiled steps themselves (eager launches + per-launch events)
+        cnt = (C.c_longlong * 3)(); tms = (C.c_double * 3)(); work = (C.c_double * 3)()
+        lib.bn_profile_collect(3, cnt, tms, work)
         lib.bn_profile_enable(0)
-        gemm_ms = (tms[0] + tms[1]) / nprof
+        gemm_ms = sum(tms) / nprof
         alg = mlp_flops_per_ray(args, args.n_samples, args.n_samples + args.guided_samples) * RAYS_PER_GPU
-        gemm_flops = (work[0] + work[1]) / nprof
+        alg_shared = mlp_flops_per_ray(args, args.n_samples, args.n_samples + args.guided_samples, shared_trunk=True) * RAYS_PER_GPU
+        gemm_flops = sum(work) / nprof
         achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-        roof = {"bound": "tensor", "kernel": "bn::tc::gemm_tc_kernel + bn::chain::*_chain_kernel (all PE+SIREN fwd/dgrad/wgrad tcgen05 launches of a step)",
-                "achieved": achieved, "peak": peaks["tf_sust"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_sust"],
-                "peak_kind": f"{peaks['src']} sustained bf16 (kernel timed inside a long step)",
-                "traffic": NCU_GEMM_DRAM_BYTES_PER_LAUNCH, "traffic_note": NCU_GEMM_TRAFFIC_NOTE,
-                "launches_per_step": (cnt[0] + cnt[1]) / nprof, "gemm_ms_per_step": gemm_ms,
-                "gemm_share_of_step": gemm_ms / ms, "algorithmic_gflop_per_step": gemm_flops / 1e9,
-                "survey_gflop_per_step": alg / 1e9,
-                "by_kind": {"tn_fwd_dgrad": {"launches": cnt[0] / nprof, "ms": tms[0] / nprof,
-                                             "tflops": work[0] / max(tms[0], 1e-9) / 1e9},
-                            "nt_wgrad": {"launches": cnt[1] / nprof, "ms": tms[1] / nprof,
-                                         "tflops": work[1] / max(tms[1], 1e-9) / 1e9}}}
+        kind = lambda i: {"launches": cnt[i] / nprof, "ms": tms[i] / nprof, "tflops": work[i] / max(tms[i], 1e-9) / 1e9}
+        chain_tf = work[2] / max(tms[2], 1e-9) / 1e9
+        # the dominant kernel of the step: the fused PE + 8-layer SIREN trunk forward (chain::train_chain_kernel)
+        roof = {"bound": "tensor", "kernel": "bn::chain::train_chain_kernel (fused PE + 8 SIREN layers, forward, writes h_l / cos_l for the backward)",
+                "achieved": chain_tf, "peak": peaks["tf_sust"], "unit": "TFLOP/s", "frac": chain_tf / peaks["tf_sust"],
+                "peak_kind": f"{peaks['src']} sustained bf16 (kernel timed inside a long step; burst peak {peaks['tf_burst']})",
+                "traffic": NCU_CHAIN_DRAM_BYTES_PER_LAUNCH, "traffic_note": NCU_TRAFFIC_NOTE,
+                "launches_per_step": cnt[2] / nprof, "us_per_launch": 1e3 * tms[2] / max(cnt[2], 1),
+                "share_of_step": tms[2] / nprof / ms_eager,
+                "all_tcgen05": {"kernel": "every tcgen05 launch of a step (chain kernels + gemm_tc_kernel fwd/dgrad/wgrad)",
+                                "achieved": achieved, "frac": achieved / peaks["tf_sust"], "frac_of_burst": achieved / peaks["tf_burst"],
+                                "launches_per_step": sum(cnt) / nprof, "ms_per_step": gemm_ms, "share_of_step": gemm_ms / ms_eager, "profiled_step_ms": ms_eager,
+                                "executed_gflop_per_step": gemm_flops / 1e9, "algorithmic_gflop_per_step_shared_trunk": alg_shared / 1e9,
+                                "reference_gflop_per_step": alg / 1e9,
+                                "by_kind": {"chain_fwd": kind(2), "tn_fwd_dgrad": kind(0), "nt_wgrad": kind(1)}}}
     # ---- HBM leg: the compositing kernels (K-C) at inference-chunk size, GB/s against the measured copy peak ----
     roof_hbm = None
     if rank == 0 and not opts.no_composite:
@@ -300,7 +311,7 @@ def run_ours(opts):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])

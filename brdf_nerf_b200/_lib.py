@@ -59,6 +59,7 @@ _SIGS = {
     "bn_brdf_points_forward": (C.c_int, [C.POINTER(ShadeCfg), _P, _P, _P, _I, _I, _P]),
     "bn_brdf_points_backward": (C.c_int, [C.POINTER(ShadeCfg), _P, _P, _P, _I, _I, _P]),
     "bn_loss_color_depth": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _F, _F, _I, _P, _P, _P, _I, _I, _P]),
+    "bn_loss_regularizers": (C.c_int, [_P, _P, _P, _P, _I, _I, _F, _I, _F, _P, _F, _P, _P, _P, _P, _P, _I, _I, _P]),
     "bn_mlp_create": (C.c_int, [C.POINTER(MlpCfg), C.POINTER(_P)]),
     "bn_mlp_destroy": (None, [_P]),
     "bn_mlp_sync_weights": (C.c_int, [_P, _P, _P]),
@@ -75,6 +76,7 @@ _SIGS = {
                                     C.c_longlong, _I, C.c_longlong, _P]),
     "bn_debug_gemm": (C.c_int, [_I, _I, _P, C.c_longlong, _P, C.c_longlong, _P, C.c_longlong, C.c_longlong, _I, C.c_longlong, _P]),
     "bn_adam_step": (C.c_int, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P]),
+    "bn_adam_step_graph": (C.c_int, [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _F, _P]),
 }
 
 _lib = None

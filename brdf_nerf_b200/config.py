@@ -50,6 +50,9 @@ _DEFAULTS = dict(
     max_train_steps=300000,  # opt.py:162
     brdf_on=1.0,           # opt.py:242
     nrrg_on=0.0,           # opt.py:244
+    nr_reg_an_lambda=0.0,  # opt.py:232
+    nr_reg_lr_lambda=0.0,  # opt.py:234
+    hs_lambda=0.0,         # opt.py:240
     gsam_only_on=1.0,      # opt.py:255
     cos_irra_on=1.0,       # opt.py:257
     std_range=3.0,         # opt.py:259

@@ -89,3 +89,98 @@ int bn_loss_color_depth(const float* rgb, const float* target_rgb, const float* 
   BN_LAUNCH_CHECK();
   return BN_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Regularisers of the BRDF stage, fused with their gradients.  Replaces (reference):
+//   NormalRegLoss      metrics.py:179-216   L_n = lambda * sum_{r,s} w_rs min(0, n_rs . v_r)^2,  v_r = -d_r (main.py:269-285;
+//                      the reference flattens rays x samples before its `.sum(dim=-1)`, so the value is a SUM, not a ray mean)
+//   HardSurfaceLoss    metrics.py:263-290   L_h = lambda / N * sum_r sum_s (z_rs - depth_r)^2 w_rs   (calc_depth_std_2,
+//                      train_utils.py:38-39)
+// Gradients written for bn_composite_backward: g_weights (N,S), the normal channels of g_packed (N,S,pitch; every other
+// channel zero) and d L_h / d depth ADDED to g_depth.  One warp per ray.
+namespace bn {
+
+struct RegArgs {
+  const float* weights; const float* z; const float* depth;    // (N,S), (N,S), (N)
+  const float* packed; int pitch;                               // (N,S,pitch)
+  int ch[2]; float lambda_nr[2];                                // normal channels (analytic, learned), -1 = off
+  const float* rays;                                            // (N,11): d = rays[r*11 + 3..5]
+  float k_hs;                                                   // lambda_hs / N (0 = off)
+  float* loss; float* g_weights; float* g_packed; float* g_depth; float* bad_count;
+  int N, S;
+};
+
+__global__ void __launch_bounds__(128) reg_loss_kernel(RegArgs a) {
+  __shared__ float part[4];
+  const int lane = threadIdx.x % kWarp, wid = threadIdx.x / kWarp;
+  const int r = blockIdx.x * 4 + wid;
+  float contrib = 0.f;
+  if (r < a.N) {
+    const float vx = -a.rays[r * 11 + 3], vy = -a.rays[r * 11 + 4], vz = -a.rays[r * 11 + 5];
+    const float d = a.depth ? a.depth[r] : 0.f;
+    float gd = 0.f, bad[2] = {0.f, 0.f};
+    for (int i = lane; i < a.S; i += kWarp) {
+      const long long p = (long long)r * a.S + i;
+      const float w = a.weights[p];
+      float gw = 0.f;
+      float* grow = a.g_packed ? a.g_packed + p * a.pitch : nullptr;
+      if (grow) for (int c = 0; c < a.pitch; ++c) grow[c] = 0.f;
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        if (a.ch[t] < 0) continue;
+        const float* n = a.packed + p * a.pitch + a.ch[t];
+        const float ndv = n[0] * vx + n[1] * vy + n[2] * vz;
+        if (ndv < 0.f) bad[t] += 1.f;
+        const float m = fminf(ndv, 0.f);
+        contrib += a.lambda_nr[t] * w * m * m;
+        gw += a.lambda_nr[t] * m * m;
+        const float k = 2.0f * a.lambda_nr[t] * w * m;
+        grow[a.ch[t]] = k * vx; grow[a.ch[t] + 1] = k * vy; grow[a.ch[t] + 2] = k * vz;
+      }
+      if (a.k_hs != 0.f) {
+        const float dz = a.z[p] - d;
+        contrib += a.k_hs * dz * dz * w;
+        gw += a.k_hs * dz * dz;
+        gd -= 2.0f * a.k_hs * dz * w;
+      }
+      a.g_weights[p] = gw;
+    }
+    contrib = warp_sum(contrib);
+    if (a.k_hs != 0.f) { gd = warp_sum(gd); if (lane == 0) a.g_depth[r] += gd; }
+    if (a.bad_count) {
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const float b = warp_sum(bad[t]);
+        if (lane == 0 && a.ch[t] >= 0 && b > 0.f) atomicAdd(a.bad_count + t, b);
+      }
+    }
+  }
+  if (lane == 0) part[wid] = contrib;
+  __syncthreads();
+  if (threadIdx.x == 0) atomicAdd(a.loss, (part[0] + part[1]) + (part[2] + part[3]));
+}
+
+}  // namespace bn
+
+extern "C" __attribute__((visibility("default")))
+int bn_loss_regularizers(const float* weights, const float* z, const float* depth, const float* packed, int pitch,
+                         int normal_an_ch, float lambda_nr_an, int normal_lr_ch, float lambda_nr_lr, const float* rays,
+                         float lambda_hs, float* loss, float* g_weights, float* g_packed, float* g_depth, float* bad_count,
+                         int n_rays, int n_samples, cudaStream_t stream) {
+  BN_CHECK_ARG(weights && loss && g_weights, "null pointer");
+  BN_CHECK_ARG(n_rays > 0 && n_samples > 0, "empty batch");
+  const bool nr = (normal_an_ch >= 0 && lambda_nr_an != 0.f) || (normal_lr_ch >= 0 && lambda_nr_lr != 0.f);
+  BN_CHECK_ARG(!nr || (packed && rays && g_packed && pitch >= 7), "the normal term needs packed, rays and g_packed");
+  BN_CHECK_ARG(lambda_hs == 0.f || (z && depth && g_depth), "the hard-surface term needs z, depth and g_depth");
+  RegArgs a{};
+  a.weights = weights; a.z = z; a.depth = depth; a.packed = packed; a.pitch = pitch;
+  a.ch[0] = (normal_an_ch >= 0 && lambda_nr_an != 0.f) ? normal_an_ch : -1; a.lambda_nr[0] = lambda_nr_an;
+  a.ch[1] = (normal_lr_ch >= 0 && lambda_nr_lr != 0.f) ? normal_lr_ch : -1; a.lambda_nr[1] = lambda_nr_lr;
+  BN_CHECK_ARG((a.ch[0] < 0 || a.ch[0] + 3 <= pitch) && (a.ch[1] < 0 || a.ch[1] + 3 <= pitch), "normal channel out of range");
+  a.rays = rays; a.k_hs = lambda_hs / (float)n_rays;
+  a.loss = loss; a.g_weights = g_weights; a.g_packed = nr ? g_packed : nullptr; a.g_depth = g_depth; a.bad_count = bad_count;
+  a.N = n_rays; a.S = n_samples;
+  reg_loss_kernel<<<ceil_div(n_rays, 4), 128, 0, stream>>>(a);
+  BN_LAUNCH_CHECK();
+  return BN_OK;
+}

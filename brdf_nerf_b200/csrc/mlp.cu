@@ -336,6 +336,30 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   p[i] = pi - (lr / bc1) * (mi / denom);
 }
 
+// Graph-replayable Adam: the step counter and the learning rate live in device memory (state = {lr, step, bc1, sqrt(bc2)}),
+// so a captured training step advances them itself.
+__global__ void adam_tick_kernel(float* __restrict__ state, float b1, float b2) {
+  const double t = (double)state[1] + 1.0;
+  state[1] = (float)t;
+  state[2] = 1.0f - (float)pow((double)b1, t);
+  state[3] = sqrtf(1.0f - (float)pow((double)b2, t));
+}
+__global__ void adam_state_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                  float* __restrict__ v, long long n, const float* __restrict__ state, float b1, float b2,
+                                  float eps, float wd, float gscale) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float lr = state[0], bc1 = state[2], bc2_sqrt = state[3];
+  float gi = g[i] * gscale;
+  float pi = p[i];
+  if (wd != 0.f) gi += wd * pi;
+  const float mi = b1 * m[i] + (1.0f - b1) * gi;
+  const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+  m[i] = mi; v[i] = vi;
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;
+  p[i] = pi - (lr / bc1) * (mi / denom);
+}
+
 // tcgen05 mode, no learned normal: one thread per point turns the gradient of the packed output row into
 // the pre-activation gradients DPRE[p][0..15] (heads' second layers), DPRE[p][16] (sigma) — everything
 // else in the backward of the heads is a GEMM on DPRE.  Rows leave through shared memory so that the
@@ -600,7 +624,7 @@ static int sigma_chain(bn_mlp* h, const float* params, const float* origins, int
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  prof_begin(0, 2.0 * (double)prm.P * ((double)h->E * h->F + (double)(h->L - 2) * h->F * h->F + (double)(h->F + h->E) * h->F + h->F), s);
+  prof_begin(2, 2.0 * (double)prm.P * ((double)h->E * h->F + (double)(h->L - 2) * h->F * h->F + (double)(h->F + h->E) * h->F + h->F), s);
   BN_CUDA(cudaLaunchKernelEx(&cfg, chain::sigma_chain_kernel, prm));
   const int rc = after_launch("sigma_chain_kernel");
   prof_end(s);
@@ -638,7 +662,7 @@ static int train_chain(bn_mlp* h, const float* params, const float* origins, int
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  prof_begin(0, 2.0 * (double)P * ((double)h->E * h->F + (double)(h->L - 2) * h->F * h->F + (double)(h->F + h->E) * h->F), s);
+  prof_begin(2, 2.0 * (double)P * ((double)h->E * h->F + (double)(h->L - 2) * h->F * h->F + (double)(h->F + h->E) * h->F), s);
   BN_CUDA(cudaLaunchKernelEx(&cfg, chain::train_chain_kernel, prm));
   const int rc = after_launch("train_chain_kernel");
   prof_end(s);
@@ -1028,10 +1052,22 @@ extern "C" __attribute__((visibility("default"))) int bn_adam_step(float* params
                             float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                             float grad_scale, cudaStream_t stream) {
   BN_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && n > 0 && step >= 1, "bad arguments");
-  const float bc1 = 1.0f - powf(beta1, (float)step);
-  const float bc2 = 1.0f - powf(beta2, (float)step);
+  const float bc1 = 1.0f - (float)pow((double)beta1, (double)step);
+  const float bc2 = 1.0f - (float)pow((double)beta2, (double)step);
   adam_kernel<<<(unsigned)ceil_div_ll(n, 256), 256, 0, stream>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
                                                                 eps, weight_decay, bc1, sqrtf(bc2), grad_scale);
+  BN_LAUNCH_CHECK();
+  return BN_OK;
+}
+
+extern "C" __attribute__((visibility("default")))
+int bn_adam_step_graph(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float* state,
+                       float beta1, float beta2, float eps, float weight_decay, float grad_scale, cudaStream_t stream) {
+  BN_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && state && n > 0, "bad arguments");
+  adam_tick_kernel<<<1, 1, 0, stream>>>(state, beta1, beta2);
+  BN_LAUNCH_CHECK();
+  adam_state_kernel<<<(unsigned)ceil_div_ll(n, 256), 256, 0, stream>>>(params, grads, exp_avg, exp_avg_sq, n, state, beta1, beta2,
+                                                                      eps, weight_decay, grad_scale);
   BN_LAUNCH_CHECK();
   return BN_OK;
 }

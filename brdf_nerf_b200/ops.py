@@ -197,6 +197,13 @@ def adam_step(params, grads, m, v, lr, step, betas=(0.9, 0.999), eps=1e-8, weigh
                                   float(grad_scale), L.stream_ptr()))
 
 
+def adam_step_graph(params, grads, m, v, state, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_scale=1.0):
+    """Adam whose learning rate and step counter live on the device (`state` = [lr, step, -, -] fp32): capturable."""
+    L.check(L.load().bn_adam_step_graph(L.ptr(params), L.ptr(grads), L.ptr(m), L.ptr(v), params.numel(), L.ptr(state),
+                                        float(betas[0]), float(betas[1]), float(eps), float(weight_decay), float(grad_scale),
+                                        L.stream_ptr()))
+
+
 def loss_color_depth(rgb, target_rgb, lambda_rgb, depth=None, z=None, weights=None, valid_depth=None, target_depths=None,
                      target_std=None, lambda_ds=0.0, use_all_depth=False, no_weights=False):
     """SNerfLoss + DepthLoss(subset=True) fused with their gradients (reference metrics.py:39-61, 82-161).
@@ -222,3 +229,23 @@ def loss_color_depth(rgb, target_rgb, lambda_rgb, depth=None, z=None, weights=No
         L.ptr(target_std.contiguous().float()) if use_ds else None, float(lambda_rgb), float(lambda_ds), int(bool(use_all_depth)),
         L.ptr(loss), L.ptr(g_rgb), L.ptr(g_depth), n, s, L.stream_ptr()))
     return loss, g_rgb, g_depth
+
+
+def loss_regularizers(loss, weights, z, depth, packed, rays, normal_an_ch=-1, lambda_nr_an=0.0, normal_lr_ch=-1,
+                      lambda_nr_lr=0.0, lambda_hs=0.0, g_depth=None, want_bad_count=False):
+    """NormalRegLoss / HardSurfaceLoss (metrics.py:179-216, 263-290) fused with their gradients.  ADDS to `loss` (1,) and
+    to `g_depth` (N); returns (g_weights (N,S), g_packed (N,S,pitch) or None, g_depth, bad_count (2,) or None)."""
+    n, s = weights.shape
+    dev = weights.device
+    pitch = packed.shape[-1]
+    nr = (normal_an_ch >= 0 and lambda_nr_an != 0.0) or (normal_lr_ch >= 0 and lambda_nr_lr != 0.0)
+    g_weights = torch.empty_like(weights)
+    g_packed = torch.empty((n, s, pitch), dtype=torch.float32, device=dev) if nr else None
+    if lambda_hs != 0.0 and g_depth is None:
+        g_depth = torch.zeros(n, dtype=torch.float32, device=dev)
+    bad = torch.zeros(2, dtype=torch.float32, device=dev) if want_bad_count else None
+    L.check(L.load().bn_loss_regularizers(L.ptr(weights), L.ptr(z), L.ptr(depth), L.ptr(packed), pitch, int(normal_an_ch),
+                                          float(lambda_nr_an), int(normal_lr_ch), float(lambda_nr_lr), L.ptr(rays),
+                                          float(lambda_hs), L.ptr(loss), L.ptr(g_weights), L.ptr(g_packed), L.ptr(g_depth),
+                                          L.ptr(bad), n, s, L.stream_ptr()))
+    return g_weights, g_packed, g_depth, bad

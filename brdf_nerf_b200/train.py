@@ -66,6 +66,13 @@ class Trainer:
         self._kw = None
         self.graph_launches = 0
         self.use_depth_loss = True          # switched off by the schedule after ds_drop (main.py:248)
+        self.use_normal_reg = True          # NormalRegLoss once train_steps > nrrg_on (main.py:272,280); needs nr_reg_*_lambda > 0
+        self.use_hard_surface = False       # HardSurfaceLoss once epoch > 2 (main.py:292); needs hs_lambda > 0
+        # the captured graph includes Adam (one host launch per step).  With world_size > 1 the NCCL all-reduce stays
+        # outside the graph: captured, it ran slower on 2 B200s (2.80 vs 2.53 ms/step) and stalled process-group teardown
+        self.whole_step_graph = self.world == 1
+        self._opt_state = None              # device [lr, step, bc1, sqrt(bc2)] of the graph-captured Adam
+        self._dev_lr, self._dev_step, self._graph_updates = None, 0, False
 
     # one optimisation step; `batch` tensors must already live on the model's device
     def _step_impl(self, batch: RayBatch, draws, kw):
@@ -75,9 +82,20 @@ class Trainer:
                               target_std=batch.target_std, **kw)
         use_depth = float(args.ds_lambda) > 0 and self.use_depth_loss
         loss, g_rgb, g_depth = loss_and_grads(args, outs, st, batch, use_depth)
+        g_weights = g_packed = None
+        # optional regularisers (main.py:269-299): normals facing away from the camera, hard surface
+        lam_an = float(getattr(args, "nr_reg_an_lambda", 0.0)) if (outs["nr_an"] and self.use_normal_reg) else 0.0
+        lam_lr = float(getattr(args, "nr_reg_lr_lambda", 0.0)) if (outs["nr_lr"] and self.use_normal_reg) else 0.0
+        lam_hs = float(getattr(args, "hs_lambda", 0.0)) if self.use_hard_surface else 0.0
+        if lam_an != 0.0 or lam_lr != 0.0 or lam_hs != 0.0:
+            ch_an = 4 if outs["nr_an"] else -1
+            ch_lr = (7 if outs["nr_an"] else 4) if outs["nr_lr"] else -1
+            g_weights, g_packed, g_depth, _ = ops.loss_regularizers(
+                loss, outs["weights"], outs["z"], outs["depth"], outs["packed"], st.rays, ch_an, lam_an, ch_lr, lam_lr,
+                lam_hs, g_depth=g_depth)
         grads = model.flat_grads
         grads.zero_()
-        R._backward(model, st, g_rgb, g_depth, None, None, grads)
+        R._backward(model, st, g_rgb, g_depth, g_weights, g_packed, grads)
         return loss
 
     def _reduce_and_update(self):
@@ -98,35 +116,65 @@ class Trainer:
             return loss
         return self._graph_step(batch, kw)
 
-    # ---- CUDA-graph path: static input buffers, forward+backward captured once, replayed per step
+    # ---- CUDA-graph path: static input buffers; forward + losses + backward + gradient all-reduce + Adam are captured
+    # once and replayed per step (ONE host launch per step; lr and the Adam step counter live in device memory)
+    def _capture(self, rkw, whole_step: bool):
+        model = self.model
+        g = torch.cuda.CUDAGraph()
+        lib = L.load()
+        lc0 = lib.bn_launch_count()
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
+            model.sync_weights(force=True)
+            self._loss = self._step_impl(self._static, None, rkw)
+            if whole_step:
+                scale = allreduce_grads_(model.flat_grads, self.world, self.pg)
+                ops.adam_step_graph(model.flat_params, model.flat_grads, self.m, self.v, self._opt_state, grad_scale=scale)
+        self.graph_launches = int(lib.bn_launch_count() - lc0)     # library kernels replayed by every graph launch
+        return g
+
     def _graph_step(self, batch: RayBatch, kw):
-        kw = dict(kw, _use_depth=self.use_depth_loss)
+        kw = dict(kw, _use_depth=self.use_depth_loss, _use_nr=self.use_normal_reg, _use_hs=self.use_hard_surface)
         if self._graph is None or self._kw != kw:
             self._static = RayBatch(*[None if t is None else t.clone() for t in
                                       (batch.rays, batch.rgbs, batch.valid_depth, batch.target_depths, batch.target_std)])
+            rkw = {k: v for k, v in kw.items() if not k.startswith("_")}
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):                 # warm-up: fills table / workspace caches
-                rkw = {k: v for k, v in kw.items() if not k.startswith("_")}
                 for _ in range(2):
                     self.model.sync_weights(force=True)
                     self._step_impl(self._static, None, rkw)
             torch.cuda.current_stream().wait_stream(side)
-            self._graph = torch.cuda.CUDAGraph()
-            lib = L.load()
-            lc0 = lib.bn_launch_count()
-            with torch.cuda.graph(self._graph):
-                self.model.sync_weights(force=True)
-                self._loss = self._step_impl(self._static, None, rkw)
-            self.graph_launches = int(lib.bn_launch_count() - lc0)     # library kernels replayed by every graph launch
+            if self._opt_state is None:
+                self._opt_state = torch.zeros(4, dtype=torch.float32, device=self.model.flat_params.device)
+            self._graph_updates = self.whole_step_graph
+            try:
+                self._graph = self._capture(rkw, self._graph_updates)
+            except Exception:                             # a collective that cannot be captured here: exchange + Adam stay eager
+                if not self._graph_updates:
+                    raise
+                torch.cuda.synchronize()
+                self._graph_updates = False
+                self._graph = self._capture(rkw, False)
             self._kw = dict(kw)
         for dst, src in zip((self._static.rays, self._static.rgbs, self._static.valid_depth,
                              self._static.target_depths, self._static.target_std),
                             (batch.rays, batch.rgbs, batch.valid_depth, batch.target_depths, batch.target_std)):
             if dst is not None:
                 dst.copy_(src, non_blocking=True)
+        if not self._graph_updates:
+            self._graph.replay()
+            self._reduce_and_update()
+            return self._loss
+        if self._dev_lr != self.lr:                       # StepLR: changes once per epoch
+            self._opt_state[0:1].fill_(self.lr)
+            self._dev_lr = self.lr
+        if self._dev_step != self.step_count:             # eager steps were taken in between
+            self._opt_state[1:2].fill_(float(self.step_count))
         self._graph.replay()
-        self._reduce_and_update()
+        self.step_count += 1
+        self._dev_step = self.step_count
+        self.model._synced_version = -1
         return self._loss
 
 
@@ -149,6 +197,8 @@ class TrainLoop:
         f = self.schedule.next()
         self.trainer.lr = f.lr
         self.trainer.use_depth_loss = f.use_depth_loss
+        self.trainer.use_normal_reg = f.use_normal_reg
+        self.trainer.use_hard_surface = self.schedule.epoch() > 2
         self.args.noise_std = f.noise_std
         batch = self.feed.next_batch()
         return self.trainer.step(batch, apply_brdf=f.apply_brdf, apply_theta=f.apply_theta, cos_irra_on=f.cos_irra_on,

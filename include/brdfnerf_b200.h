@@ -47,7 +47,8 @@ int bn_device_check(int device);
 unsigned long long bn_launch_count(void);
 /* per-launch CUDA-event timing of the GEMM family (bench.py roofline leg); off by default */
 int bn_profile_enable(int on);
-/* HOST pointers: per kind (0 = TN fwd/dgrad, 1 = NT wgrad) launch count, milliseconds, flops */
+/* HOST pointers: per kind (0 = TN fwd/dgrad GEMM, 1 = NT wgrad GEMM, 2 = fused PE + trunk chain kernel) launch count,
+ * milliseconds, flops */
 int bn_profile_collect(int n_kinds, long long* count, double* ms, double* work);
 
 /* ------------------------------------------------------------------ K-A  sample generators */
@@ -180,6 +181,19 @@ int bn_loss_color_depth(const float* rgb, const float* target_rgb, const float* 
                         float lambda_rgb, float lambda_ds, int use_all_depth,
                         float* loss, float* g_rgb, float* g_depth, int n_rays, int n_samples, cudaStream_t stream);
 
+/* Optional regularisers of the BRDF stage (main.py:269-299), fused with their gradients:
+ *   NormalRegLoss   (metrics.py:179-216)  lambda_nr * sum_{r,s} w_rs min(0, n_rs . v_r)^2, v_r = -d_r, once per normal
+ *                   kind (analytic: channel normal_an_ch, learned: normal_lr_ch; channel < 0 or lambda == 0 = off);
+ *   HardSurfaceLoss (metrics.py:263-290, train_utils.py:38-39)  lambda_hs / N * sum_r sum_s (z_rs - depth_r)^2 w_rs.
+ * loss (1 float) and g_depth (N) are ACCUMULATED (call after bn_loss_color_depth, or zero them first); g_weights (N,S)
+ * and g_packed (N,S,pitch: normal channels, zeros elsewhere; only touched when a normal term is on) are overwritten and
+ * are the g_weights / g_packed_direct operands of bn_composite_backward.  bad_count (2 floats, nullable, ACCUMULATED):
+ * number of samples with n . v < 0 per normal kind (the reference's `perc_ng_nr` numerator, metrics.py:196-198). */
+int bn_loss_regularizers(const float* weights, const float* z, const float* depth, const float* packed, int pitch,
+                         int normal_an_ch, float lambda_nr_an, int normal_lr_ch, float lambda_nr_lr,
+                         const float* rays, float lambda_hs, float* loss, float* g_weights, float* g_packed,
+                         float* g_depth, float* bad_count, int n_rays, int n_samples, cudaStream_t stream);
+
 /* ------------------------------------------------------------------ K-B  PE + SIREN MLP */
 
 enum { BN_PREC_FP32 = 0,   /* CUDA-core fp32 everywhere: parity mode (<= 1e-3 against the fp32 oracle) */
@@ -286,6 +300,13 @@ int bn_mlp_normals_backward(bn_mlp* h, const float* params, const float* out, fl
 int bn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                  float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                  float grad_scale, cudaStream_t stream);
+
+/* The same update for a CUDA-graph-captured training step: the learning rate and the step counter live in DEVICE memory,
+ * state = {lr, step (number of updates done so far, as a float), scratch, scratch}; the call increments step, derives the
+ * bias corrections on the device and applies the update, so replaying the captured graph advances the optimizer. */
+int bn_adam_step_graph(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                       float* state, float beta1, float beta2, float eps, float weight_decay, float grad_scale,
+                       cudaStream_t stream);
 
 /* Unit-test hook: one GEMM of the MLP engine in isolation (kind 0: out[M,N] = A[M,K] B[N,K]^T;
  * kind 1: out[M,N] += A[K,M]^T B[K,N], fp32 atomics). precision selects tcgen05 (bf16 operands)

@@ -138,3 +138,132 @@ def test_train_loop_pool_and_schedule(cuda):
     assert all(math.isfinite(x) for x in losses)
     assert loop.trainer.use_depth_loss is False and abs(loop.trainer.lr - 5e-4 * 0.9 ** 3) < 1e-12
     assert losses[-1] < losses[0]
+
+
+@pytest.mark.parametrize("n,s,lam", [(64, 128, (0.1, 0.0, 0.0)), (333, 64, (0.1, 0.05, 0.5)), (100, 128, (0.0, 0.0, 0.5))])
+def test_fused_regularizer_kernel_vs_oracle_losses(cuda, n, s, lam):
+    """bn_loss_regularizers (NormalRegLoss metrics.py:179-216 for analytic / learned normals + HardSurfaceLoss
+    metrics.py:263-290, fused with their gradients) == the oracle restatements + autograd."""
+    from brdf_nerf_b200 import ops
+    g = torch.Generator().manual_seed(n + s)
+    lam_an, lam_lr, lam_hs = lam
+    pitch = 13
+    rays = make_rays(n).rays
+    z = torch.sort(torch.rand(n, s, generator=g) * 0.6, -1)[0]
+    w = torch.softmax(torch.randn(n, s, generator=g), -1).requires_grad_(True)
+    depth = ((w.detach() * z).sum(-1) + 0.05 * torch.randn(n, generator=g)).requires_grad_(True)
+    packed = torch.randn(n, s, pitch, generator=g).requires_grad_(True)
+    res = {"weights_coarse": w, "z_vals_coarse": z, "depth_coarse": depth, "rays_d_coarse": (-rays[:, 3:6]).reshape(n, 1, 3),
+           "normal_an_coarse": packed[..., 4:7], "normal_lr_coarse": packed[..., 7:10]}
+    ref = torch.zeros(())
+    percs = [0.0, 0.0]
+    if lam_an:
+        l, percs[0] = LT.normal_reg_loss(res, lam_an, "normal_an"); ref = ref + l
+    if lam_lr:
+        l, percs[1] = LT.normal_reg_loss(res, lam_lr, "normal_lr"); ref = ref + l
+    if lam_hs:
+        ref = ref + LT.hard_surface_loss(res, lam_hs)
+    ref.backward()
+    loss = torch.full((1,), 0.25, device=cuda)            # accumulated on top of the colour / depth loss
+    g_depth0 = torch.full((n,), 0.5, device=cuda)
+    gw, gp, gd, bad = ops.loss_regularizers(loss, w.detach().to(cuda), z.to(cuda), depth.detach().to(cuda),
+                                            packed.detach().to(cuda), rays.to(cuda), 4, lam_an, 7, lam_lr, lam_hs,
+                                            g_depth=g_depth0.clone(), want_bad_count=True)
+    assert abs(loss.item() - 0.25 - ref.item()) <= 1e-5 * max(1.0, abs(ref.item()))
+    assert torch.allclose(gw.cpu(), w.grad, atol=1e-6, rtol=1e-5)
+    if lam_an or lam_lr:
+        assert torch.allclose(gp.cpu(), packed.grad, atol=1e-6, rtol=1e-5)
+    else:
+        assert gp is None
+    if lam_hs:
+        assert torch.allclose(gd.cpu() - 0.5, depth.grad, atol=1e-6, rtol=1e-5)
+    tot = n * s
+    if lam_an:
+        assert abs(100.0 * bad[0].item() / tot - percs[0]) < 1e-3
+    if lam_lr:
+        assert abs(100.0 * bad[1].item() / tot - percs[1]) < 1e-3
+
+
+def test_trainer_with_regularizers_matches_autograd(cuda):
+    """Trainer step with NormalRegLoss + HardSurfaceLoss switched on == render_rays autograd + oracle losses (fp32)."""
+    from brdf_nerf_b200.train import Trainer
+    args = named_config("rpv111", nr_reg_an_lambda=0.1, hs_lambda=0.5)
+    n = 64
+    batch = make_rays(n).to(cuda)
+    S1, Gs = args.n_samples, args.guided_samples
+    od = RT.Draws.make(n, S1, Gs, S1 + Gs, seed=3)
+    kw = dict(apply_brdf=True, cos_irra_on=True)
+    torch.manual_seed(0)
+    m1 = load_model(args, precision="fp32").to(cuda)
+    res, _ = render_rays({"coarse": m1}, args, batch.rays, None, mode="train",
+                         _draws=Draws(u_strat=od.u_strat, u_pred=od.u_pred), **kw)
+    loss = LT.color_loss(res, batch.rgbs, args.lambda_rgb) + LT.normal_reg_loss(res, 0.1)[0] + LT.hard_surface_loss(res, 0.5)
+    m1.flat_grads.zero_()
+    loss.backward()
+    g_ref = m1.flat_grads.clone()
+    torch.manual_seed(0)
+    m2 = load_model(args, precision="fp32").to(cuda)
+    tr = Trainer(m2, args, use_graph=False)
+    tr.use_hard_surface = True
+    p0 = m2.flat_params.clone()
+    loss2 = tr.step(batch, draws=Draws(u_strat=od.u_strat, u_pred=od.u_pred), **kw)
+    assert abs(loss2.item() - loss.item()) <= 1e-5 * max(1.0, abs(loss.item()))
+    g = m2.flat_grads
+    assert (g - g_ref).abs().max().item() <= 1e-4 * g_ref.abs().max().item() + 1e-8
+    assert not torch.equal(p0, m2.flat_params)
+
+
+def test_graph_adam_matches_eager_adam(cuda):
+    """bn_adam_step_graph (lr / step counter in device memory, bias corrections derived on the device) == bn_adam_step,
+    including after a learning-rate change and when it is replayed from a captured CUDA graph."""
+    from brdf_nerf_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    n = 10007
+    p0 = torch.randn(n, generator=g).to(cuda)
+    grads = [torch.randn(n, generator=g).to(cuda) * 0.1 for _ in range(6)]
+    pa, ma, va = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0)
+    pb, mb, vb = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0)
+    state = torch.zeros(4, device=cuda)
+    gbuf = torch.zeros_like(p0)
+    graph = None
+    for t, gr in enumerate(grads, start=1):
+        lr = 5e-4 if t < 4 else 4.5e-4
+        ops.adam_step(pa, gr, ma, va, lr, t, grad_scale=0.5)
+        state[0:1].fill_(lr)
+        gbuf.copy_(gr)
+        if t < 3:
+            ops.adam_step_graph(pb, gbuf, mb, vb, state, grad_scale=0.5)
+        else:
+            if graph is None:
+                torch.cuda.synchronize()
+                keep = (pb.clone(), mb.clone(), vb.clone(), state.clone())
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    ops.adam_step_graph(pb, gbuf, mb, vb, state, grad_scale=0.5)
+                for dst, src in zip((pb, mb, vb, state), keep):      # capture does not execute; restore in case it did
+                    dst.copy_(src)
+            graph.replay()
+        assert state[1].item() == float(t)
+        assert torch.allclose(pa, pb, atol=1e-7, rtol=1e-6), (t, (pa - pb).abs().max().item())
+    assert torch.allclose(ma, mb) and torch.allclose(va, vb)
+
+
+def test_whole_step_graph_advances_optimizer(cuda):
+    """The captured step contains the parameter update: step counter, learning-rate changes and eager steps in between
+    stay consistent with the device-side optimizer state."""
+    args = named_config("lambertian_ds")
+    batch = make_rays(256, depth_supervision=True).to(cuda)
+    torch.manual_seed(0)
+    m = load_model(args, precision="bf16").to(cuda)
+    tr = Trainer(m, args, use_graph=True)
+    p0 = m.flat_params.clone()
+    losses = [tr.step(batch).item() for _ in range(4)]
+    assert tr._graph_updates and tr.step_count == 4 and tr._opt_state[1].item() == 4.0
+    assert not torch.equal(p0, m.flat_params)
+    od = RT.Draws.make(256, args.n_samples, args.guided_samples, args.n_samples + args.guided_samples, seed=2, with_gt=True)
+    tr.step(batch, draws=Draws(u_strat=od.u_strat, u_pred=od.u_pred, u_gt=od.u_gt))     # eager step (injected draws)
+    assert tr.step_count == 5
+    tr.lr = 4e-4
+    losses.append(tr.step(batch).item())
+    assert tr.step_count == 6 and tr._opt_state[1].item() == 6.0 and abs(tr._opt_state[0].item() - 4e-4) < 1e-10
+    assert all(math.isfinite(x) for x in losses) and losses[-1] < losses[0]

@@ -78,3 +78,30 @@ def test_gradients(cfg, ds, kw):
             continue
         s = p.grad.abs().max().item()
         assert (p.grad - go).abs().max().item() <= 1e-3 * s + 1e-9, name
+
+
+def test_regularizer_losses_vs_reference():
+    """NormalRegLoss (metrics.py:179-216) and HardSurfaceLoss (metrics.py:263-290) of the live reference on a live
+    reference render == the oracle restatements (value, bad-normal percentage, gradients w.r.t. the weights)."""
+    args, ref_model, om, batch, ref, ora, _, _ = _run("rpv111", n=24, mode="train", apply_brdf=True, cos_irra_on=True)
+    _, _, M = RH.load()
+    with contextlib.redirect_stdout(io.StringIO()):
+        l_nr, _, perc = M.NormalRegLoss(lambda_nr_reg=0.1, keyword="normal_an")(ref)
+        l_hs, _ = M.HardSurfaceLoss(lambda_hs=0.5)(ref)
+    o_nr, o_perc = LT.normal_reg_loss(ora, 0.1, "normal_an")
+    o_hs = LT.hard_surface_loss(ora, 0.5)
+    assert abs(l_nr.item() - o_nr.item()) <= 1e-6 * max(1.0, abs(l_nr.item()))
+    assert abs(l_hs.item() - o_hs.item()) <= 1e-7
+    assert abs(float(perc) - o_perc) < 1e-4
+    (l_nr + l_hs).backward()
+    (o_nr + o_hs).backward()
+    for name, p in ref_model.named_parameters():
+        go = om.p[name].grad
+        if p.grad is None:
+            assert go is None or go.abs().max() == 0
+            continue
+        if go is None:                     # autograd of the reference leaves exact zeros where the oracle leaves None
+            assert p.grad.abs().max() == 0, name
+            continue
+        s = p.grad.abs().max().item()
+        assert (p.grad - go).abs().max().item() <= 2e-3 * s + 1e-9, name
