@@ -32,10 +32,11 @@ import torch  # noqa: E402
 RAYS_PER_GPU = 1024
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel of the step, chain::train_chain_kernel at
 # P = 65536 points (two launches per step: stratified points, guided points), from the ncu --set full capture under profiles/
-NCU_CHAIN_DRAM_BYTES_PER_LAUNCH = 1.07e9
-NCU_TRAFFIC_NOTE = ("ncu --set full (profiles/r01d_ncu_full_chain_kernels.csv, P = 131072): 27 MB read + 2.11 GB written = the "
-                    "algorithmic 2.15 GB (h_l, c_l of 8 layers + encoding, bf16); per launch at P = 65536: half of that. "
-                    "trunk dgrad GEMM (profiles/r01c): 269 MB read + 102 MB written per launch vs 384 MiB algorithmic")
+NCU_CHAIN_DRAM_BYTES_PER_LAUNCH = 15.6e6 + 1026.8e6
+NCU_TRAFFIC_NOTE = ("ncu --set full (profiles/r01e_ncu_full_train_chain.csv, P = 65536): 15.6 MB read + 1026.8 MB written per launch "
+                    "= the algorithmic 1.07 GB (h_l, c_l of 8 layers + encoding, bf16; nothing is read back). "
+                    "trunk dgrad GEMM (profiles/r01e_ncu_full_gemm.csv): 269 MB read + 105 MB written per launch vs 384 MiB algorithmic "
+                    "(the tail of the writes is still in L2 at kernel end); trunk wgrad GEMM: 269.5 MB read vs 256 MiB algorithmic")
 METRIC = "train rays/s (SpS-BRDF-NeRF, 1/2/4/8 B200); MLP tensor-pipe %; composite GB/s"
 
 
@@ -95,17 +96,18 @@ class ClockSampler:
         os.unlink(self.f.name)
         # samples of the timed regions (one sample of slack on either side: nvidia-smi stamps are ~20 ms apart)
         rows = rows[max(0, first - 1):(None if last is None else last + 1)] or rows
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         for r in rows:
             try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
                 for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                     if val.strip().lower().startswith("active"):
                         reasons.add(name)
             except Exception:
                 continue
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "power_w_median": statistics.median(pw) if pw else None,
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons)}
 
 
 def _dist_env():

@@ -612,6 +612,7 @@ static int sigma_chain(bn_mlp* h, const float* params, const float* origins, int
   prm.P = (long long)N * S; prm.o_stride = o_stride; prm.d_stride = d_stride; prm.S = S;
   prm.L = h->L; prm.skip = h->skip; prm.n_freq = c.n_freq_xyz;
   prm.trace = h->chain_trace;
+  prm.noload = getenv("BN_CHAIN_NOLOAD") != nullptr;
   const int n_blocks = (int)ceil_div_ll(prm.P, 256);
   constexpr int smem = chain::sigma_chain_smem();
   BN_CUDA(cudaFuncSetAttribute(chain::sigma_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -620,10 +621,12 @@ static int sigma_chain(bn_mlp* h, const float* params, const float* origins, int
   cfg.blockDim = dim3(tc::kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = tc::pdl_enabled() ? 2 : 1;
   prof_begin(2, 2.0 * (double)prm.P * ((double)h->E * h->F + (double)(h->L - 2) * h->F * h->F + (double)(h->F + h->E) * h->F + h->F), s);
   BN_CUDA(cudaLaunchKernelEx(&cfg, chain::sigma_chain_kernel, prm));
   const int rc = after_launch("sigma_chain_kernel");
@@ -658,10 +661,12 @@ static int train_chain(bn_mlp* h, const float* params, const float* origins, int
   cfg.blockDim = dim3(tc::kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = tc::pdl_enabled() ? 2 : 1;
   prof_begin(2, 2.0 * (double)P * ((double)h->E * h->F + (double)(h->L - 2) * h->F * h->F + (double)(h->F + h->E) * h->F), s);
   BN_CUDA(cudaLaunchKernelEx(&cfg, chain::train_chain_kernel, prm));
   const int rc = after_launch("train_chain_kernel");

@@ -44,6 +44,7 @@ struct SigmaChainParams {
   float* out;
   long long P;
   int o_stride, d_stride, S, L, skip, n_freq;
+  int noload;                           // timing experiment (BN_CHAIN_NOLOAD): the weight TMA loads are skipped, results are garbage
   long long* trace;                     // diagnostics (bn_debug_chain_trace): clock64() stamps of pair 0's leader CTA, first block
 };
 
@@ -77,16 +78,20 @@ __device__ __forceinline__ int layer_wcol(int l, int skip, int kb) { return (l =
 // ---- weight producer: one [128 x 64] tile of W_l per (block, layer, column half, K block) ----
 template <int STAGES>
 __device__ __forceinline__ void chain_producer(const CUtensorMap* wmap, uint8_t* sW, uint64_t* wfull, uint64_t* wempty,
-                                               int crank, int pair0, int npairs, int n_blocks, int L, int skip) {
+                                               int crank, int pair0, int npairs, int n_blocks, int L, int skip, bool noload = false) {
   int stage = 0; uint32_t phase = 0;
   for (int blk = pair0; blk < n_blocks; blk += npairs)
     for (int l = 0; l < L; ++l)
       for (int n = 0; n < 2; ++n)
         for (int kb = layer_kb_first(l, skip); kb <= layer_kb_last(l); ++kb) {
           mbar_wait(&wempty[stage], phase ^ 1);
-          if (crank == 0) mbar_expect_tx(&wfull[stage], 2 * kKBBytes);
-          tma_load_2d_pair(sW + stage * kKBBytes, &wmap[l], mapa_u32(smem_u32(&wfull[stage]), 0),
-                           layer_wcol(l, skip, kb), n * 256 + crank * 128);
+          if (noload) {                                  // timing experiment: MMAs run on whatever the slot holds
+            if (crank == 0) mbar_expect_tx(&wfull[stage], 0);
+          } else {
+            if (crank == 0) mbar_expect_tx(&wfull[stage], 2 * kKBBytes);
+            tma_load_2d_pair(sW + stage * kKBBytes, &wmap[l], mapa_u32(smem_u32(&wfull[stage]), 0),
+                             layer_wcol(l, skip, kb), n * 256 + crank * 128);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
 }
@@ -165,6 +170,7 @@ __device__ __forceinline__ void encode_row(const float* origins, int o_stride, c
 
 __global__ void __launch_bounds__(kThreads, 1) sigma_chain_kernel(const __grid_constant__ SigmaChainParams prm) {
   constexpr int kWStages = w_stages<false>();
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sAct = smem;                                        // [kNKB][128 rows][128 B], swizzled
@@ -196,6 +202,7 @@ __global__ void __launch_bounds__(kThreads, 1) sigma_chain_kernel(const __grid_c
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) tmem_alloc<true>(tmem_slot, 512);
+  pdl_wait();                                                  // the weights may come from the optimizer kernel just before
   for (int i = threadIdx.x; i < L * kF; i += kThreads) sBias[i] = __ldg(prm.bias[i / kF] + (i % kF));
   fence_before_sync();
   __syncthreads();
@@ -204,7 +211,7 @@ __global__ void __launch_bounds__(kThreads, 1) sigma_chain_kernel(const __grid_c
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) chain_producer<kWStages>(prm.wmap, sW, wfull, wempty, crank, pair0, npairs, n_blocks, L, skip);
+    if (lane == 0) chain_producer<kWStages>(prm.wmap, sW, wfull, wempty, crank, pair0, npairs, n_blocks, L, skip, prm.noload != 0);
   } else if (warp == 1) {
     if (lane == 0 && crank == 0)
       chain_mma<kWStages>(sAct, sW, wfull, wempty, tfull, tempty, act_ready, kfree, tmem_base, pair0, npairs, n_blocks, L, skip, prm.trace);
@@ -318,6 +325,7 @@ __global__ void __launch_bounds__(kThreads, 1) sigma_chain_kernel(const __grid_c
 // Training forward of the trunk: the same chain; every layer's h_l and c_l = w0 cos(.) are written to HBM.
 __global__ void __launch_bounds__(kThreads, 1) train_chain_kernel(const __grid_constant__ TrainChainParams prm) {
   constexpr int kWStages = w_stages<true>();
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sAct = smem;
@@ -352,6 +360,7 @@ __global__ void __launch_bounds__(kThreads, 1) train_chain_kernel(const __grid_c
   cluster_sync_all();
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) chain_producer<kWStages>(prm.wmap, sW, wfull, wempty, crank, pair0, npairs, n_blocks, L, skip);
@@ -391,6 +400,12 @@ __global__ void __launch_bounds__(kThreads, 1) train_chain_kernel(const __grid_c
         const float w0 = l == 0 ? 30.0f : 1.0f;
         const bool last = l == L - 1;
         for (int n = 0; n < 2; ++n) {
+          // this half's biases: lane i fetches column i of each of the warp's four units BEFORE waiting for the
+          // accumulator (the L2 round trip hides behind the MMAs) and the unit loop broadcasts them by shuffle —
+          // there is no shared memory left to stage them and no registers for 32 values per lane
+          float breg[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) breg[u] = __ldg(prm.bias[l] + n * 256 + u * 64 + hsel * 32 + lane);
           mbar_wait(&tfull[n], tf_ph[n]); tf_ph[n] ^= 1;
           fence_after_sync();
           uint32_t pk[4][16];
@@ -404,11 +419,12 @@ __global__ void __launch_bounds__(kThreads, 1) train_chain_kernel(const __grid_c
             if (u < 3) tmem_ld32_issue(tbase + (u + 1) * 64, (u & 1) ? va : vb);
             else { fence_before_sync(); arrive_leader(&tempty[n]); }
             const int col0 = n * 256 + u * 64 + hsel * 32;
-            const float4* bp = reinterpret_cast<const float4*>(prm.bias[l] + col0);
             uint32_t pc[16];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float4 b = __ldg(bp + j);
+              float4 b;
+              b.x = __shfl_sync(0xffffffffu, breg[u], 4 * j); b.y = __shfl_sync(0xffffffffu, breg[u], 4 * j + 1);
+              b.z = __shfl_sync(0xffffffffu, breg[u], 4 * j + 2); b.w = __shfl_sync(0xffffffffu, breg[u], 4 * j + 3);
               const float a0 = w0 * (__uint_as_float(v[4 * j]) + b.x), a1 = w0 * (__uint_as_float(v[4 * j + 1]) + b.y);
               const float a2 = w0 * (__uint_as_float(v[4 * j + 2]) + b.z), a3 = w0 * (__uint_as_float(v[4 * j + 3]) + b.w);
               pk[u][2 * j] = bf_pack(__sinf(a0), __sinf(a1));
