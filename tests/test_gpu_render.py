@@ -173,3 +173,62 @@ def test_shared_trunk_matches_two_pass(cuda, cfg, kw, precision, tol):
     with torch.no_grad():
         r2, _ = render_rays({"coarse": model}, args, b2.rays, None, mode="train", **sup2, **kw)
     assert torch.isfinite(r2["rgb_coarse"]).all() and r2["rgb_coarse"].shape == (63, 3)
+
+
+@pytest.mark.parametrize("cfg,n,mode,kw", [
+    ("lambertian_ds", 1024, "train", {}),                                                    # BASELINE configs[1]
+    ("rpv111", 1024, "train", dict(apply_brdf=True, cos_irra_on=True)),                      # configs[2]
+    ("hapke_bct", 8192, "train", dict(apply_brdf=True, apply_theta=True, cos_irra_on=True)),  # configs[3]
+    ("microfacet", 8192, "train", dict(apply_brdf=True, cos_irra_on=True)),                   # configs[3]
+    ("rpv111", 5120, "test", dict(apply_brdf=True, cos_irra_on=True)),                        # configs[4], one chunk
+])
+def test_full_size_properties(cuda, cfg, n, mode, kw):
+    """BASELINE.json's full sizes in the production (bf16 tcgen05) mode, where the oracle would take minutes:
+    size-independent properties of the reference's algorithm — sortedness and permutation of the merged samples,
+    compositing identities (alpha/T/w/depth recomputed from the returned sigmas in fp32), value ranges, unit normals,
+    determinism of the forward given the draws, finite gradients."""
+    args = named_config(cfg)
+    ds = cfg.endswith("_ds")
+    batch = make_rays(n, depth_supervision=ds).to(cuda)
+    S1, Gs = args.n_samples, args.guided_samples
+    S = S1 + Gs
+    gen = torch.Generator().manual_seed(n)
+    draws = Draws(u_strat=torch.rand(n, S1, generator=gen), u_pred=torch.rand(n, Gs, generator=gen),
+                  u_gt=torch.rand(n, Gs, generator=gen) if ds else None)
+    sup = dict(valid_depth=batch.valid_depth, target_depths=batch.target_depths, target_std=batch.target_std) if ds else {}
+    torch.manual_seed(0)
+    model = load_model(args, precision="bf16").to(cuda)
+    train = mode == "train"
+    with (torch.enable_grad() if train else torch.no_grad()):
+        res, _ = render_rays({"coarse": model}, args, batch.rays, None, mode=mode, _draws=draws, **sup, **kw)
+    z, idx, zu = res["z_vals_coarse"], res["sort_idx_coarse"], res["z_vals_unsort_coarse"]
+    assert z.shape == (n, S) and (z[:, 1:] >= z[:, :-1]).all(), "z_vals not sorted"
+    assert torch.equal(torch.sort(idx, -1)[0], torch.arange(S, device=cuda).expand(n, S)), "sort_idx is not a permutation"
+    assert torch.equal(torch.gather(zu, 1, idx), z), "z_vals != z_vals_unsort[sort_idx]"
+    near, far = batch.rays[:, 6:7], batch.rays[:, 7:8]
+    assert (zu[:, :S1] >= near).all() and (zu[:, :S1] <= far).all()
+    sig, w, al, T = res["sigmas_coarse"].squeeze(-1), res["weights_coarse"], res["alphas_coarse"], res["transparency_coarse"]
+    for t in (res["rgb_coarse"], res["depth_coarse"], sig, w, al, T, res["albedo_coarse"]):
+        assert torch.isfinite(t).all()
+    delta = torch.cat([z[:, 1:] - z[:, :-1], torch.full((n, 1), 1e10, device=cuda)], -1)
+    al_ref = 1 - torch.exp(-delta * torch.relu(sig))
+    T_ref = torch.cumprod(torch.cat([torch.ones(n, 1, device=cuda), 1 - al_ref + 1e-10], -1), -1)[:, :-1]
+    assert (al - al_ref).abs().max().item() <= 1e-5
+    assert (T - T_ref).abs().max().item() <= 1e-4 and (w - al_ref * T_ref).abs().max().item() <= 1e-4
+    assert (res["depth_coarse"] - (w * z).sum(-1)).abs().max().item() <= 1e-4
+    assert (w >= 0).all() and (w.sum(-1) <= 1 + 1e-3).all()
+    assert (res["rgb_coarse"] >= 0).all() and (res["rgb_coarse"] <= 1).all()
+    assert (res["albedo_coarse"] >= 0).all() and (res["albedo_coarse"] <= 1).all() and (sig >= 0).all()
+    if "normal_an_coarse" in res:
+        nrm = res["normal_an_coarse"].norm(dim=-1)
+        assert (nrm <= 1 + 1e-3).all() and (nrm[nrm > 0.5] - 1).abs().max().item() <= 1e-3
+    # determinism: the forward is a pure function of (weights, rays, draws)
+    with torch.no_grad():
+        res2, _ = render_rays({"coarse": model}, args, batch.rays, None, mode=mode, _draws=draws, **sup, **kw)
+    assert torch.equal(res2["z_vals_coarse"], z) and torch.equal(res2["rgb_coarse"], res["rgb_coarse"].detach())
+    if train:
+        loss = LT.train_loss(res, batch, args)
+        model.flat_grads.zero_()
+        loss.backward()
+        g = model.flat_grads
+        assert torch.isfinite(g).all() and g.abs().sum().item() > 0
