@@ -33,7 +33,7 @@ class ShadeCfg(C.Structure):
 
 class MlpCfg(C.Structure):
     _fields_ = [("feat", C.c_int), ("layers", C.c_int), ("skip_layer", C.c_int), ("n_freq_xyz", C.c_int),
-                ("normal_lr", C.c_int), ("head_dim", C.c_int * BN_NUM_HEADS), ("precision", C.c_int),
+                ("normal_lr", C.c_int), ("viewdir", C.c_int), ("n_freq_dir", C.c_int), ("head_dim", C.c_int * BN_NUM_HEADS), ("precision", C.c_int),
                 ("w_off", C.c_int64 * BN_NUM_LINEAR), ("b_off", C.c_int64 * BN_NUM_LINEAR), ("n_params", C.c_int64)]
 
 

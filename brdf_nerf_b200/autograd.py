@@ -10,13 +10,15 @@ from . import ops
 
 class PointsFunction(torch.autograd.Function):
     """(B,3) points -> (B,1) sigma or packed (B,C) (reference spsbrdfnerf.py:662-757).
-    A point is evaluated as a one-sample ray with origin x and z = 0 (x + d*0 is exact)."""
+    A point is evaluated as a one-sample ray with origin x and z = 0 (x + d*0 is exact); `dirs` (B,3) is the view
+    direction of each point for models built with input_viewdir=1 (None otherwise)."""
 
     @staticmethod
-    def forward(ctx, model, xyz, sigma_only, apply_brdf, apply_theta, nr_an_on, nr_lr_on, need_grad, *params):
+    def forward(ctx, model, xyz, dirs, sigma_only, apply_brdf, apply_theta, nr_an_on, nr_lr_on, need_grad, *params):
         if not xyz.is_cuda:
             raise L.BnError("SpSBRDFNeRF.forward needs CUDA tensors: there is no CPU path")
         xyz = xyz.detach().float().contiguous()
+        dirs = xyz if dirs is None else dirs.detach().float().contiguous()
         B = xyz.shape[0]
         model.sync_weights()
         z = torch.zeros((B, 1), dtype=torch.float32, device=xyz.device)
@@ -24,14 +26,14 @@ class PointsFunction(torch.autograd.Function):
         if sigma_only and not full_for_grad:
             flags = L.MLP_SIGMA_ONLY
             out = torch.empty((B, 1), dtype=torch.float32, device=xyz.device)
-            ops.mlp_forward(model, xyz, 3, xyz, 3, z, flags, out, 1, model.workspace(B, flags, "ws_points"))
+            ops.mlp_forward(model, xyz, 3, dirs, 3, z, flags, out, 1, model.workspace(B, flags, "ws_points"))
             return out
         flags = model.mlp_flags(apply_brdf=apply_brdf, apply_theta=apply_theta, nr_an_on=nr_an_on and not sigma_only,
                                 nr_lr_on=nr_lr_on and not sigma_only, train=need_grad)
         C = model.out_channels(flags)
         out = torch.empty((B, C), dtype=torch.float32, device=xyz.device)
         ws = model.workspace(B, flags, "ws_points")
-        ops.mlp_forward(model, xyz, 3, xyz, 3, z, flags, out, C, ws)
+        ops.mlp_forward(model, xyz, 3, dirs, 3, z, flags, out, C, ws)
         if flags & L.MLP_NORMAL_AN:
             ops.mlp_normals_forward(model, out, C, B, 1, flags, ws)
         ctx.model, ctx.flags, ctx.B, ctx.C, ctx.sigma_col = model, flags, B, C, full_for_grad
@@ -53,4 +55,4 @@ class PointsFunction(torch.autograd.Function):
             ops.mlp_normals_backward(model, out, g_out, ctx.C, ctx.B, 1, ctx.flags, flat, ctx.ws)
         ops.mlp_backward(model, out, g_out, ctx.C, ctx.B, 1, ctx.flags, flat, ctx.ws)
         grads = model.grad_views(flat)
-        return (None, None, None, None, None, None, None, None, *grads)
+        return (None, None, None, None, None, None, None, None, None, *grads)

@@ -90,6 +90,8 @@ def named_config(name: str, **overrides) -> argparse.Namespace:
     table = {
         "lambertian": {},
         "lambertian_ds": dict(ds_lambda=10.0),
+        "lambertian_viewdir": dict(input_viewdir=1),
+        "rpv111_viewdir": dict(funcM=1, funcF=1, funcH=1, dim_RPV=1, normal="analystic", input_viewdir=1),
         "rpv111": dict(funcM=1, funcF=1, funcH=1, dim_RPV=1, normal="analystic"),
         "rpv111_multi": dict(funcM=1, funcF=1, funcH=1, dim_RPV=3, normal="analystic", MultiBRDF=1),
         "hapke_bct": dict(b=1, c=1, theta=1, normal="analystic"),

@@ -43,6 +43,41 @@ __global__ void encode_kernel(const float* __restrict__ origins, int o_stride, c
   }
 }
 
+// Mapping(ray direction) (nerf.py:53-70, mapping_sizes[1] frequencies; raw direction without --mapping) into the 64
+// columns behind the features: the colour head's first layer reads [features | dir enc | 0] as one K = F + 64 operand
+template <typename T>
+__global__ void dir_encode_kernel(const float* __restrict__ dirs, int d_stride, int S, long long P, int n_freq,
+                                  T* __restrict__ dst, long long ld) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const long long r = p / S;
+  float d[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) d[a] = dirs[r * d_stride + a];
+  float e[kEncPad];
+#pragma unroll
+  for (int i = 0; i < kEncPad; ++i) e[i] = 0.f;
+  if (n_freq == 0) { e[0] = d[0]; e[1] = d[1]; e[2] = d[2]; }
+  else {
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+      if (k < n_freq) {
+        const float f = (float)(1 << k);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { float sn, cs; sincosf(f * d[a], &sn, &cs); e[k * 6 + a] = sn; e[k * 6 + 3 + a] = cs; }
+      }
+    }
+  }
+  T* o = dst + p * ld;
+#pragma unroll
+  for (int i = 0; i < kEncPad; i += 8) {
+    float t[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t[j] = e[i + j];
+    Pack<T, 8>::store(o + i, t);
+  }
+}
+
 template <typename T> __device__ __forceinline__ void load8g(const T* p, float (&v)[8]) { load8<T>(p, v); }
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
@@ -583,7 +618,7 @@ static int sync_weights_t(bn_mlp* h, const float* params, cudaStream_t s) {
   pack(BN_LIN_FEATS, h->F, h->F, -1, h->F, h->Wf, h->F, h->WfT, h->F, 0);
   const long long HK = (long long)h->n_blocks * h->HH;
   for (int b = 0; b < h->n_blocks; ++b) {
-    pack(h->blk_lin0[b], h->HH, h->F, -1, h->F, h->W1, h->F, h->W1T, HK, b * h->HH);
+    pack(h->blk_lin0[b], h->HH, h->F + (b == 0 ? h->DE : 0), -1, h->ldfe, h->W1, h->ldfe, h->W1T, HK, b * h->HH);
     jobs.j[jobs.n++] = PackJob{c.b_off[h->blk_lin0[b]], h->HH, -1, -1, 1, h->b1cat, 0, nullptr, 0, b * h->HH};
   }
   if (h->bf16) pack(BN_LIN_SIGMA, 1, h->F, -1, h->F, h->WsigA, h->F, nullptr, 0, 0);   // row 0 of the [64, F] density operand
@@ -679,6 +714,7 @@ template <typename T>
 static void offset_rows(const bn_mlp* h, Ws<T>* w, long long row0) {
   if (row0 == 0) return;
   w->X3 += row0 * w->ldx3;
+  if (w->FE) w->FE += row0 * w->ldfe;
   for (int l = 0; l < h->L; ++l) {
     w->H[l] += row0 * w->Hld[l];
     if (w->C[l]) w->C[l] += row0 * h->F;
@@ -692,6 +728,10 @@ static int trunk_t(bn_mlp* h, const float* params, const float* origins, int o_s
   const long long P = (long long)N * S;
   const bn_mlp_cfg& c = h->cfg;
   const int F = h->F, L = h->L;
+  if (h->DE > 0 && w.FE) {      // --input_viewdir: the encoded ray direction of these rows, next to their (later) features
+    dir_encode_kernel<T><<<(unsigned)ceil_div_ll(P, 128), 128, 0, s>>>(dirs, d_stride, S, P, c.n_freq_dir, w.FE + F, w.ldfe);
+    BN_LAUNCH_CHECK();
+  }
   if constexpr (std::is_same<T, __nv_bfloat16>::value) {
     if (h->F == chain::kF && h->skip >= 1 && !h->no_chain)
       return train_chain(h, params, origins, o_stride, dirs, d_stride, z, N, S, w, keep_c, train, s);
@@ -737,10 +777,10 @@ static int heads_t(bn_mlp* h, const float* params, long long P, int flags, float
   if (int rc = build_plan(h, flags, &hp, &nch)) return rc;
   if (pitch < nch) { set_error("bn_mlp_forward: out_pitch %d < %d channels", pitch, nch); return BN_ERR_ARG; }
   const T* Hl = w.H[L - 1]; const long long ldl = w.Hld[L - 1];
-  if (int rc = layer_bias<T>(h, Hl, ldl, (const T*)h->Wf, F, P, F, F, params + c.b_off[BN_LIN_FEATS], w.FE, F, s)) return rc;
+  if (int rc = layer_bias<T>(h, Hl, ldl, (const T*)h->Wf, F, P, F, F, params + c.b_off[BN_LIN_FEATS], w.FE, w.ldfe, s)) return rc;
   {
     const int HKa = hp.n_blocks * h->HH;
-    if (int rc = layer_sin<T>(h, w.FE, F, (const T*)h->W1, F, P, HKa, F, h->b1cat, 1.0f, w.HD, w.ldhd,
+    if (int rc = layer_sin<T>(h, w.FE, w.ldfe, (const T*)h->W1, h->ldfe, P, HKa, h->ldfe, h->b1cat, 1.0f, w.HD, w.ldhd,
                               train ? w.CD : nullptr, w.ldhd, s)) return rc;
   }
   if constexpr (std::is_same<T, __nv_bfloat16>::value) {
@@ -867,7 +907,9 @@ static int backward_t(bn_mlp* h, const float* params, const float* out, const fl
   // heads' first layer: wgrad (+ bias gradient; the fp32 mode got it from heads_bwd_kernel) per block, dgrad into the features
   for (int b = 0; b < hp.n_blocks; ++b) {
     const int lin = h->blk_lin0[b];
-    if (int rc = layer_wgrad<T>(h, w.GHD + (long long)b * h->HH, w.ldhd, w.FE, F, h->HH, F, P, g + c.w_off[lin], F, F, F,
+    // the colour head (block 0) also reads the encoded view direction: In = [features | dir enc | pad], dW is [HH, F + DE]
+    const int kin = F + (b == 0 ? h->DE : 0), no = (b == 0 && h->DE) ? h->ldfe : F;
+    if (int rc = layer_wgrad<T>(h, w.GHD + (long long)b * h->HH, w.ldhd, w.FE, w.ldfe, h->HH, no, P, g + c.w_off[lin], kin, kin, no,
                                 kTC ? g + hp.b1_off[b] : nullptr, s)) return rc;
   }
   {
@@ -915,6 +957,7 @@ extern "C" __attribute__((visibility("default"))) int bn_mlp_create(const bn_mlp
   BN_CHECK_ARG(cfg->layers >= 2 && cfg->layers <= 16, "layers must be in [2, 16]");
   BN_CHECK_ARG(cfg->skip_layer == -1 || (cfg->skip_layer >= 1 && cfg->skip_layer < cfg->layers), "skip_layer out of range");
   BN_CHECK_ARG(cfg->n_freq_xyz >= 0 && cfg->n_freq_xyz <= 10, "n_freq_xyz must be in [0, 10]");
+  BN_CHECK_ARG(cfg->n_freq_dir >= 0 && cfg->n_freq_dir <= 10, "n_freq_dir must be in [0, 10]");
   BN_CHECK_ARG(cfg->precision == BN_PREC_FP32 || cfg->precision == BN_PREC_BF16, "unknown precision");
   int dev = 0;
   BN_CUDA(cudaGetDevice(&dev));
@@ -924,13 +967,14 @@ extern "C" __attribute__((visibility("default"))) int bn_mlp_create(const bn_mlp
   h->cfg = *cfg;
   h->F = cfg->feat; h->L = cfg->layers; h->HH = cfg->feat / 2; h->skip = cfg->skip_layer;
   h->E = cfg->n_freq_xyz == 0 ? 3 : 6 * cfg->n_freq_xyz;
+  h->DE = cfg->viewdir ? (cfg->n_freq_dir == 0 ? 3 : 6 * cfg->n_freq_dir) : 0;
+  h->ldfe = h->F + (h->DE ? kEncPad : 0);
   h->bf16 = cfg->precision == BN_PREC_BF16;
   h->es = h->bf16 ? 2 : 4;
   cudaDeviceProp prop;
   BN_CUDA(cudaGetDeviceProperties(&prop, dev));
   h->num_sms = prop.multiProcessorCount;
-  h->no_chain = getenv("BN_NO_CHAIN") != nullptr;
-      // debugging aid: per-layer GEMMs for the density pass
+  h->no_chain = getenv("BN_NO_CHAIN") != nullptr;      // debugging aid: per-layer GEMMs instead of the fused trunk kernels
   // blocks of the heads' hidden layer: rgb first, then every BRDF head that exists
   h->n_blocks = 0;
   h->blk_lin0[0] = BN_LIN_RGB0; h->blk_lin2[0] = BN_LIN_RGB2; h->blk_head[0] = -1; h->n_blocks = 1;
@@ -953,8 +997,8 @@ extern "C" __attribute__((visibility("default"))) int bn_mlp_create(const bn_mlp
   const size_t HK = (size_t)h->n_blocks * h->HH;
   BN_CUDA(cudaMalloc(&h->Wf, (size_t)h->F * h->F * h->es));
   BN_CUDA(cudaMalloc(&h->WfT, (size_t)h->F * h->F * h->es));
-  BN_CUDA(cudaMalloc(&h->W1, HK * h->F * h->es));
-  BN_CUDA(cudaMalloc(&h->W1T, HK * h->F * h->es));
+  BN_CUDA(cudaMalloc(&h->W1, HK * h->ldfe * h->es));
+  BN_CUDA(cudaMalloc(&h->W1T, HK * h->ldfe * h->es));
   BN_CUDA(cudaMalloc(&h->b1cat, HK * sizeof(float)));
   BN_CUDA(cudaMalloc(&h->W2p, HK * 64 * sizeof(__nv_bfloat16)));
   BN_CUDA(cudaMalloc(&h->W2pT, HK * 64 * sizeof(__nv_bfloat16)));

@@ -18,7 +18,8 @@
 //   X3 [P, 64+F]  : cols 0..63 = encoding (60 real + 4 zero pad), cols 64.. = h_{skip-1}; the skip
 //                   layer reads the whole row as its K = 64+F operand (no concat copy)
 //   H_l, C_l [P,F]: h_l = sin(w0 z_l) and c_l = w0 cos(w0 z_l) (kept only when training)
-//   FE [P,F], HD / CD [P, 256*blocks]: features and the heads' hidden layer (+ cosine)
+//   FE [P,F (+64)], HD / CD [P, 256*blocks]: features (+ the encoded view direction when --input_viewdir: the colour
+//                   head reads the whole row, like the skip layer reads X3) and the heads' hidden layer (+ cosine)
 #include <vector>
 #include <type_traits>
 #include <string.h>
@@ -53,6 +54,7 @@ struct HeadPlan {
 struct bn_mlp {
   bn_mlp_cfg cfg;
   int F, L, E, HH, skip;
+  int DE, ldfe;                 // view-direction encoding width (0 = off) and the pitch of FE = [features | dir enc | pad]
   int num_sms;
   bool bf16;
   size_t es;
@@ -148,7 +150,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ X, lo
 // ------------------------------------------------------------------------------------------------
 template <typename T> struct Ws {
   T* X3; T* H[16]; long long Hld[16]; T* C[16];
-  T* FE; T* HD; T* CD; T* GHD; T* G7D; T* GFE; T* GA; T* GB; T* DPRE;
+  T* FE; long long ldfe; T* HD; T* CD; T* GHD; T* G7D; T* GFE; T* GA; T* GB; T* DPRE;
   long long ldx3, ldhd;
   // analytic-normal sweep (BN_MLP_NORMAL_AN)
   T* A[16];        // a_l = d sigma / d lin_l            (one per layer when training, ping-pong otherwise)
@@ -192,7 +194,8 @@ static inline size_t carve(const bn_mlp* h, long long P, int flags, void* base, 
     }
   }
   if (!sig_only) {
-    t.FE = take(P * F);
+    t.ldfe = h->ldfe;
+    t.FE = take(P * t.ldfe);
     t.HD = take(P * t.ldhd);
     if (train) {
       t.CD = take(P * t.ldhd); t.GHD = take(P * t.ldhd);

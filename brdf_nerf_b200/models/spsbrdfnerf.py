@@ -60,13 +60,12 @@ class SpSBRDFNeRF(nn.Module):
         if beta or indirect_light or sun_v == "learned":
             raise NotImplementedError("beta / indirect_light / sun_v='learned' are not on the CUDA hot path "
                                       "(sun_v='learned' is broken in the reference itself, SURVEY App. C.2)")
-        if getattr(args, "input_viewdir", 0):
-            raise NotImplementedError("input_viewdir=1 is not implemented on the CUDA path yet")
         if len(skips) > 1:
             raise NotImplementedError("one skip connection is supported")
         self.layers, self.skips, self.feat = layers, list(skips), feat
         self.t_embedding_dims = t_embedding_dims
-        self.input_sizes = [3, 0]
+        self.viewdir = bool(getattr(args, "input_viewdir", 0))
+        self.input_sizes = [3, 3] if self.viewdir else [3, 0]          # spsbrdfnerf.py:458
         self.rgb_padding = 0.001
         self.beta, self.roughness, self.sun_v = beta, roughness, sun_v
         self.indirect_light, self.normal = indirect_light, normal
@@ -75,6 +74,7 @@ class SpSBRDFNeRF(nn.Module):
         self.dim_RPV = dim_RPV
         self.mapping_sizes = list(mapping_sizes)
         self.n_freq = mapping_sizes[0] if mapping else 0
+        self.n_freq_dir = mapping_sizes[1] if mapping else 0
         self.precision = precision
 
         self.number_of_outputs = 4
@@ -94,7 +94,8 @@ class SpSBRDFNeRF(nn.Module):
         self.fc_net = nn.Sequential(*fc)
         self.sigma_from_xyz = nn.Sequential(nn.Linear(feat, 1), nn.Softplus())
         self.feats_from_xyz = nn.Linear(feat, feat)
-        self.rgb_from_xyzdir = nn.Sequential(nn.Linear(feat, feat // 2), Sine(), nn.Linear(feat // 2, 3), nn.Sigmoid())
+        dir_in = (2 * mapping_sizes[1] * 3 if mapping else 3) if self.viewdir else 0      # spsbrdfnerf.py:505-509, 534
+        self.rgb_from_xyzdir = nn.Sequential(nn.Linear(feat + dir_in, feat // 2), Sine(), nn.Linear(feat // 2, 3), nn.Sigmoid())
         for i in range(layers):                     # fc_net.apply(sine_init)
             _siren_uniform(self.fc_net[2 * i], first=False)
         _siren_uniform(self.fc_net[0], first=True)  # fc_net[0].apply(first_layer_sine_init)
@@ -246,6 +247,7 @@ class SpSBRDFNeRF(nn.Module):
             cfg.skip_layer = self.skips[0] if self.skips else -1
             cfg.n_freq_xyz = self.n_freq
             cfg.normal_lr = int(hasattr(self, "grad_from_xyz"))
+            cfg.viewdir, cfg.n_freq_dir = int(self.viewdir), int(self.n_freq_dir)
             for h, hn in enumerate(L.HEAD_NAMES):
                 mod = getattr(self, f"{hn}_from_xyz", None)
                 cfg.head_dim[h] = mod[2].out_features if mod is not None else 0
@@ -328,5 +330,8 @@ class SpSBRDFNeRF(nn.Module):
         """Reference signature (spsbrdfnerf.py:662): (B,3) points -> (B,1) sigma or packed (B,C)."""
         from ..autograd import PointsFunction
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
-        return PointsFunction.apply(self, input_xyz_.contiguous(), bool(sigma_only), bool(apply_brdf),
+        if self.viewdir and not sigma_only and input_dir is None:
+            raise ValueError("this model was built with input_viewdir=1: forward needs input_dir (spsbrdfnerf.py:689-690)")
+        dirs = input_dir.contiguous() if (self.viewdir and input_dir is not None) else None
+        return PointsFunction.apply(self, input_xyz_.contiguous(), dirs, bool(sigma_only), bool(apply_brdf),
                                     bool(apply_theta), bool(nr_an_on), bool(nr_lr_on), need_grad, *self.parameters())

@@ -221,6 +221,8 @@ typedef struct bn_mlp_cfg {
   int skip_layer;         /* layer whose input is [PE | h], -1 = none (reference: 4) */
   int n_freq_xyz;         /* positional-encoding frequencies, 0 = raw xyz (no --mapping) */
   int normal_lr;          /* grad_from_xyz head exists */
+  int viewdir;            /* --input_viewdir: the colour head reads [features | Mapping(ray direction)] (spsbrdfnerf.py:689-690) */
+  int n_freq_dir;         /* frequencies of the direction encoding (mapping_sizes[1] = 4), 0 = raw direction (no --mapping) */
   int head_dim[BN_NUM_HEADS];   /* output width of each BRDF head that exists (0 = absent) */
   int precision;          /* BN_PREC_* */
   int64_t w_off[BN_NUM_LINEAR]; /* element offset of each weight / bias in the flat buffer, -1 = absent */

@@ -40,6 +40,7 @@ CASES = {
     "hapke_b_brdf": ("hapke_b", {}, dict(mode="test", apply_brdf=True), False, False),
     "microfacet_brdf": ("microfacet", {}, dict(mode="test", apply_brdf=True, cos_irra_on=True), False, False),
     "rpv111_learned_normal": ("rpv111", dict(normal="learned"), dict(mode="test", apply_brdf=True), False, False),
+    "lambertian_viewdir_test": ("lambertian_viewdir", {}, dict(mode="test"), False, False),
     "rpv111_sunvis_test": ("rpv111", {}, dict(mode="test", apply_brdf=True, cos_irra_on=True, bTestSun_v=True), False, False),
 }
 KEEP = ("z_vals", "z_vals_unsort", "sort_idx", "depth", "rgb", "weights", "albedo_accu", "sigmas", "nr_vw", "nr_sun",
@@ -55,8 +56,11 @@ def weights_digest(state) -> str:
 
 
 def main():
+    only = set(sys.argv[1:])            # optional: regenerate only the named cases
     os.makedirs(OUT, exist_ok=True)
     for name, (cfg, over, kw, ds, zero_std) in CASES.items():
+        if only and name not in only:
+            continue
         args = named_config(cfg, **over)
         model = RH.build_model(args, seed=0)
         batch = make_rays(N, depth_supervision=ds, zero_std=zero_std)

@@ -22,6 +22,7 @@ CASES = {
     "hapke_b_brdf": ("hapke_b", {}, dict(mode="test", apply_brdf=True), False),
     "microfacet_brdf": ("microfacet", {}, dict(mode="test", apply_brdf=True, cos_irra_on=True), False),
     "rpv111_learned_normal": ("rpv111", dict(normal="learned"), dict(mode="test", apply_brdf=True), False),
+    "lambertian_viewdir_test": ("lambertian_viewdir", {}, dict(mode="test"), False),
     "rpv111_sunvis_test": ("rpv111", {}, dict(mode="test", apply_brdf=True, cos_irra_on=True, bTestSun_v=True), False),
 }
 

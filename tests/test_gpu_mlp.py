@@ -222,3 +222,32 @@ def test_inference_chain_bf16(cuda, cfg, kw, n, monkeypatch):
         na, nb, nc = a[:, 4:7], b[:, 4:7], c[:, 4:7]
         ok = (na * nc).sum(-1) > 0.9
         assert ((na * nb).sum(-1)[ok] > 0.8).float().mean().item() > 0.98
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 6e-2)])
+@pytest.mark.parametrize("mapping", [True, False])
+def test_viewdir_colour_head(cuda, precision, tol, mapping):
+    """--input_viewdir: rgb_from_xyzdir reads [features | Mapping(direction)] (spsbrdfnerf.py:689-690); forward against the
+    oracle and, in fp32, the gradient of the colour head's first layer (its direction columns included)."""
+    args, m, state = _models("lambertian", cuda, precision=precision, input_viewdir=1, mapping=mapping)
+    x = _pts(777, 31)
+    g = torch.Generator().manual_seed(32)
+    d = torch.nn.functional.normalize(torch.randn(777, 3, generator=g), dim=-1)
+    om = RT.OracleModel(state, args, requires_grad=True)
+    ref = om.forward(x, d=d)
+    want = torch.cat([ref["albedo"], ref["sigma"]], -1)
+    out = m(x.to(cuda), input_dir=d.to(cuda))
+    assert out.shape == want.shape
+    err = (out.detach().cpu() - want.detach()).abs().max().item()
+    assert err <= tol * max(1.0, want.detach().abs().max().item()), err
+    with pytest.raises(ValueError):
+        m(x.to(cuda))
+    if precision == "fp32":
+        w = torch.randn(777, 4, generator=g)
+        (want * w).sum().backward()
+        m.flat_grads.zero_()
+        (out * w.to(cuda)).sum().backward()
+        for name, p in m.named_parameters():
+            r = om.p[name].grad
+            s = r.abs().max().item()
+            assert (p.grad.cpu() - r).abs().max().item() <= 2e-3 * s + 1e-7, name

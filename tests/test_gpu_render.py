@@ -78,6 +78,7 @@ def test_against_reference_golden(cuda, name):
     ("hapke_bct", False, dict(apply_brdf=True, apply_theta=True, cos_irra_on=True)),
     ("microfacet", False, dict(apply_brdf=True, cos_irra_on=True)),
     ("rpv111", False, dict(apply_brdf=False)),
+    ("lambertian_viewdir", False, {}), ("rpv111_viewdir", False, dict(apply_brdf=True, cos_irra_on=True)),
 ])
 def test_training_gradients_vs_oracle(cuda, cfg, ds, kw):
     """d loss / d every weight through the whole CUDA chain (shade -> composite -> [per-sample BRDF] ->
@@ -131,7 +132,7 @@ def test_no_cpu_fallback():
 
 
 @pytest.mark.parametrize("cfg,kw", [("lambertian_ds", {}), ("rpv111", dict(apply_brdf=True, cos_irra_on=True)),
-                                    ("rpv111_multi", dict(apply_brdf=True, cos_irra_on=True))])
+                                    ("rpv111_multi", dict(apply_brdf=True, cos_irra_on=True)), ("lambertian_viewdir", {})])
 @pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("bf16", 6e-2)])
 def test_shared_trunk_matches_two_pass(cuda, cfg, kw, precision, tol):
     """render_rays evaluates the stratified points' trunk once (bn_mlp_trunk_forward + bn_mlp_heads_forward +

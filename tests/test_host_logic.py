@@ -66,8 +66,10 @@ def test_unsupported_model_options_fail_loudly():
         load_model(make_args(model="sps-nerf"))
     with pytest.raises(NotImplementedError):
         load_model(named_config("lambertian", beta=True))
-    with pytest.raises(NotImplementedError):
-        load_model(named_config("lambertian", input_viewdir=1))
+    m = load_model(named_config("lambertian", input_viewdir=1))            # colour head reads [features | Mapping(d)]
+    assert tuple(m.rgb_from_xyzdir[0].weight.shape) == (256, 512 + 24)
+    m = load_model(named_config("lambertian", input_viewdir=1, mapping=False))
+    assert tuple(m.rgb_from_xyzdir[0].weight.shape) == (256, 512 + 3)
 
 
 def test_no_cpu_fallback_on_the_product_path():

@@ -39,6 +39,7 @@ def _run(cfg, n=40, mode="test", ds=False, **kw):
     ("hapke_bct", dict(apply_brdf=True, apply_theta=True, cos_irra_on=True)), ("hapke_b", dict(apply_brdf=True)),
     ("microfacet", dict(apply_brdf=True, cos_irra_on=True)),
     ("rpv111", dict(apply_brdf=True, cos_irra_on=True, bTestSun_v=True)),
+    ("lambertian_viewdir", {}), ("rpv111_viewdir", dict(apply_brdf=True, cos_irra_on=True)),
 ])
 def test_forward_keys_and_values(cfg, kw):
     _, _, _, _, ref, ora, bt, bt2 = _run(cfg, **kw)
@@ -55,7 +56,8 @@ def test_forward_keys_and_values(cfg, kw):
 
 
 @pytest.mark.parametrize("cfg,ds,kw", [("lambertian_ds", True, {}), ("rpv111", False, dict(apply_brdf=True, cos_irra_on=True)),
-                                       ("hapke_bct", False, dict(apply_brdf=True, apply_theta=True, cos_irra_on=True))])
+                                       ("hapke_bct", False, dict(apply_brdf=True, apply_theta=True, cos_irra_on=True)),
+                                       ("lambertian_viewdir", False, {})])
 def test_gradients(cfg, ds, kw):
     args, ref_model, om, batch, ref, ora, _, _ = _run(cfg, n=24, mode="train", ds=ds, **kw)
     _, _, M = RH.load()
