@@ -30,6 +30,7 @@ class RayBatch:
     valid_depth: Optional[torch.Tensor] = None     # (N,) int64
     target_depths: Optional[torch.Tensor] = None   # (N, 2) [depth, correlation weight]
     target_std: Optional[torch.Tensor] = None      # (N,)
+    flat = None                                    # set by packed(): the single buffer behind all tensors
 
     def to(self, device, non_blocking=False):
         mv = lambda t: None if t is None else t.to(device, non_blocking=non_blocking)
@@ -40,6 +41,31 @@ class RayBatch:
         pn = lambda t: None if t is None else t.pin_memory()
         return RayBatch(pn(self.rays), pn(self.rgbs), pn(self.valid_depth),
                         pn(self.target_depths), pn(self.target_std))
+
+    def packed(self, device=None, pin=False) -> "RayBatch":
+        """The same batch with all its tensors laid out back to back in ONE buffer (`.flat`, bytes), so that a host
+        batch reaches the device with a single copy (`dst.flat.copy_(src.flat)`) instead of one per tensor."""
+        ts = [self.rays, self.rgbs, self.valid_depth, self.target_depths, self.target_std]
+        dev = ts[0].device if device is None else torch.device(device)
+        offs, total = [], 0
+        for t in ts:
+            offs.append(total)
+            if t is not None:
+                total += -(-t.numel() * t.element_size() // 16) * 16
+        flat = torch.empty(total, dtype=torch.uint8, device=dev)
+        if pin:
+            flat = flat.pin_memory()
+        views = []
+        for t, o in zip(ts, offs):
+            if t is None:
+                views.append(None)
+                continue
+            v = flat[o:o + t.numel() * t.element_size()].view(t.dtype).view(t.shape)
+            v.copy_(t)
+            views.append(v)
+        out = RayBatch(*views)
+        out.flat = flat
+        return out
 
     def nbytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in

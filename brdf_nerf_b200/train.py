@@ -108,6 +108,9 @@ class Trainer:
 
     def step(self, batch: RayBatch, draws=None, apply_brdf=False, apply_theta=False, cos_irra_on=False,
              gsam_only=False):
+        """One optimisation step.  With `use_graph` the batch may live in (pinned) host memory: its tensors are copied
+        straight into the graph's static input buffers (one async H2D copy per tensor); passing `static_batch()` itself
+        skips the copies."""
         kw = dict(apply_brdf=apply_brdf, bTestNormal=False, bTestSun_v=False, gsam_only=gsam_only,
                   apply_theta=apply_theta, cos_irra_on=cos_irra_on)
         if not self.use_graph or draws is not None:
@@ -115,6 +118,11 @@ class Trainer:
             self._reduce_and_update()
             return loss
         return self._graph_step(batch, kw)
+
+    def static_batch(self) -> Optional[RayBatch]:
+        """The captured graph's input buffers (None before the first graph step): producers may write the next batch
+        into them directly and pass this object to `step()`."""
+        return self._static
 
     # ---- CUDA-graph path: static input buffers; forward + losses + backward + gradient all-reduce + Adam are captured
     # once and replayed per step (ONE host launch per step; lr and the Adam step counter live in device memory)
@@ -135,8 +143,8 @@ class Trainer:
     def _graph_step(self, batch: RayBatch, kw):
         kw = dict(kw, _use_depth=self.use_depth_loss, _use_nr=self.use_normal_reg, _use_hs=self.use_hard_surface)
         if self._graph is None or self._kw != kw:
-            self._static = RayBatch(*[None if t is None else t.clone() for t in
-                                      (batch.rays, batch.rgbs, batch.valid_depth, batch.target_depths, batch.target_std)])
+            dev = self.model.flat_params.device
+            self._static = batch.packed(device=dev)       # one buffer: a packed host batch arrives with a single copy
             rkw = {k: v for k, v in kw.items() if not k.startswith("_")}
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
@@ -157,11 +165,16 @@ class Trainer:
                 self._graph_updates = False
                 self._graph = self._capture(rkw, False)
             self._kw = dict(kw)
-        for dst, src in zip((self._static.rays, self._static.rgbs, self._static.valid_depth,
-                             self._static.target_depths, self._static.target_std),
-                            (batch.rays, batch.rgbs, batch.valid_depth, batch.target_depths, batch.target_std)):
-            if dst is not None:
-                dst.copy_(src, non_blocking=True)
+        if batch is self._static:
+            pass
+        elif batch.flat is not None and batch.flat.numel() == self._static.flat.numel():
+            self._static.flat.copy_(batch.flat, non_blocking=True)
+        else:
+            for dst, src in zip((self._static.rays, self._static.rgbs, self._static.valid_depth,
+                                 self._static.target_depths, self._static.target_std),
+                                (batch.rays, batch.rgbs, batch.valid_depth, batch.target_depths, batch.target_std)):
+                if dst is not None:
+                    dst.copy_(src, non_blocking=True)
         if not self._graph_updates:
             self._graph.replay()
             self._reduce_and_update()
