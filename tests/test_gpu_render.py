@@ -233,3 +233,45 @@ def test_full_size_properties(cuda, cfg, n, mode, kw):
         loss.backward()
         g = model.flat_grads
         assert torch.isfinite(g).all() and g.abs().sum().item() > 0
+
+
+def test_batched_inference_and_tile_shards(cuda):
+    """batched_inference (eval.py:56-76) == a manual loop of render_rays over chunks; render_tile over emulated ranks
+    (shards cut on chunk boundaries) reproduces the single-process tile chunk for chunk (same draws per chunk)."""
+    from brdf_nerf_b200.inference import batched_inference, render_tile, tile_shards
+    args = named_config("rpv111", chunk=256)
+    n = 256 * 5 + 100                                   # ragged last chunk
+    rays = make_rays(n).rays.to(cuda)
+    torch.manual_seed(0)
+    model = load_model(args, precision="fp32").to(cuda)
+    models = {"coarse": model}
+    kw = dict(apply_brdf=True, cos_irra_on=True)
+
+    def seeded(fn):
+        torch.manual_seed(123)
+        return fn()
+
+    full, bt = seeded(lambda: batched_inference(models, rays, None, args, **kw))
+    assert bt == "RPV" and full["rgb_coarse"].shape == (n, 3) and full["weights_coarse"].shape == (n, 128)
+
+    def manual():
+        outs = []
+        with torch.no_grad():
+            for i in range(0, n, 256):
+                outs.append(render_rays(models, args, rays[i:i + 256], None, **kw)[0])
+        return {k: torch.cat([o[k] for o in outs], 0) for k in outs[0]}
+    man = seeded(manual)
+    for k in ("rgb_coarse", "depth_coarse", "z_vals_coarse", "normal_an_coarse"):
+        assert torch.equal(full[k], man[k]), k
+    # 3 emulated ranks: every rank consumes the generator from the state its first chunk would see in the full render
+    world = 3
+    shards = tile_shards(n, 256, world)
+    assert shards == [(0, 512), (512, 1024), (1024, n)]
+    for r, (lo, hi) in enumerate(shards):
+        torch.manual_seed(123)
+        with torch.no_grad():
+            for i in range(0, lo, 256):                 # advance the generator exactly as the earlier chunks would
+                render_rays(models, args, rays[i:i + 256], None, **kw)
+        part, _ = render_tile(models, rays, args, rank=r, world_size=world, keys=("rgb_coarse", "depth_coarse"), **kw)
+        assert set(part) == {"rgb_coarse", "depth_coarse"}
+        assert torch.equal(part["rgb_coarse"], full["rgb_coarse"][lo:hi]) and torch.equal(part["depth_coarse"], full["depth_coarse"][lo:hi])

@@ -117,3 +117,43 @@ def test_schedule_matches_reference_rules():
     sc4 = Schedule(args, dataset_len=1000, world_size=4)
     flags = [sc4.next() for _ in range(70)]
     assert not flags[61].apply_brdf and flags[62].apply_brdf        # 63 * 4 = 252 > 250
+
+
+def test_checkpoint_hand_off_by_prefix():
+    """load_ckpt / warm_start (eval.py:26-54, main.py:96-104): stage-2 model takes trunk + sigma + feats (+ rgb unless
+    Hapke) from a Lightning-style stage-1 checkpoint; BRDF heads keep their own init; parameters stay flat-buffer views."""
+    from brdf_nerf_b200.inference import load_ckpt, warm_start
+    torch.manual_seed(1)
+    stage1 = load_model(named_config("lambertian"))
+    ckpt = {"state_dict": {f"nerf_coarse.{k}": v.clone() for k, v in stage1.state_dict().items()}}
+    ckpt["state_dict"]["embedding_t.weight"] = torch.zeros(3, 4)
+    for cfg, takes_rgb in (("rpv111", True), ("hapke_b", False)):
+        torch.manual_seed(2)
+        args = named_config(cfg)
+        m = load_model(args)
+        before = {k: v.clone() for k, v in m.state_dict().items()}
+        loaded = warm_start(m, ckpt, args)
+        after = m.state_dict()
+        for k in after:
+            src = stage1.state_dict().get(k)
+            taken = k.startswith(("fc_net", "sigma_from_xyz", "feats_from_xyz")) or (takes_rgb and k.startswith("rgb_from_xyzdir"))
+            if taken:
+                assert torch.equal(after[k], src) and k in loaded, k
+            else:
+                assert torch.equal(after[k], before[k]) and k not in loaded, k
+        flat = m.flat_params                              # parameters are still views of ONE buffer
+        assert all(p.data_ptr() >= flat.data_ptr() and p.data_ptr() < flat.data_ptr() + flat.numel() * 4 for p in m.parameters())
+    m = load_model(named_config("lambertian"))
+    assert set(load_ckpt(m, ckpt, model_name="nerf_coarse")) == set(stage1.state_dict())
+
+
+def test_tile_shards_cover_the_tile_on_chunk_boundaries():
+    from brdf_nerf_b200.inference import tile_shards
+    for n, chunk, world in ((2048 * 2048, 5120, 8), (10, 4, 3), (5120, 5120, 8), (12345, 100, 5), (7, 8, 2)):
+        sh = tile_shards(n, chunk, world)
+        assert len(sh) == world and sh[0][0] == 0 and sh[-1][1] == n
+        for (a, b), (c, d) in zip(sh[:-1], sh[1:]):
+            assert b == c and a <= b
+        assert all(a % chunk == 0 for a, _ in sh if a < n)
+        counts = [-(-(b - a) // chunk) for a, b in sh]
+        assert max(counts) - min(counts) <= 1
