@@ -853,6 +853,17 @@ static int backward_t(bn_mlp* h, const float* params, const float* out, const fl
   const T* Hl = w.H[L - 1]; const long long ldl = w.Hld[L - 1];
   const int HKa = hp.n_blocks * h->HH;
   constexpr bool kTC = std::is_same<T, __nv_bfloat16>::value;   // bias grads fused into the tcgen05 dgrad epilogues
+  // every weight gradient only shares its inputs with the data-gradient chain: in tcgen05 mode they run on the handle's
+  // side stream (forked from `s` by an event each time their input is ready, joined back before returning)
+  const bool overlap = kTC && h->s2 != nullptr && h->overlap;
+  int n_fork = 0;
+  auto fork = [&]() -> cudaStream_t {             // the side stream, ordered after everything enqueued on s so far
+    if (!overlap) return s;
+    cudaEventRecord(h->ev_h[n_fork], s);
+    cudaStreamWaitEvent(h->s2, h->ev_h[n_fork], 0);
+    ++n_fork;
+    return h->s2;
+  };
   if (kTC && hp.ch_nlr < 0) {
     if constexpr (kTC) {
       heads_dpre_kernel<<<(unsigned)ceil_div_ll(P, 256), 256, 0, s>>>(hp, out, g_out, pitch, w.DPRE, g, P);
@@ -878,11 +889,12 @@ static int backward_t(bn_mlp* h, const float* params, const float* out, const fl
   if constexpr (kTC) {
     EpiSkinny e1{}; e1.n_rows = hp.n_out;
     for (int o = 0; o < hp.n_out; ++o) e1.r[o] = EpiSkinnyRow{g + hp.o[o].w_off, hp.o[o].block * h->HH, (hp.o[o].block + 1) * h->HH};
-    if (int rc = gemm_nt<T>(h, w.DPRE, 64, w.HD, w.ldhd, 64, HKa, P, e1, s, 2.0 * P * hp.n_out * h->HH)) return rc;
+    cudaStream_t sw = fork();
+    if (int rc = gemm_nt<T>(h, w.DPRE, 64, w.HD, w.ldhd, 64, HKa, P, e1, sw, 2.0 * P * hp.n_out * h->HH)) return rc;
     EpiSkinny e2{}; e2.n_rows = 20;
     e2.r[16] = EpiSkinnyRow{g + hp.wsig, 0, F};
     if (hp.ch_nlr >= 0) for (int o = 0; o < 3; ++o) e2.r[17 + o] = EpiSkinnyRow{g + hp.wg + (long long)o * F, 0, F};
-    if (int rc = gemm_nt<T>(h, w.DPRE, 64, Hl, ldl, 64, F, P, e2, s, 2.0 * P * (hp.ch_nlr >= 0 ? 4 : 1) * F)) return rc;
+    if (int rc = gemm_nt<T>(h, w.DPRE, 64, Hl, ldl, 64, F, P, e2, sw, 2.0 * P * (hp.ch_nlr >= 0 ? 4 : 1) * F)) return rc;
   } else {
     SkinnyPlan sp{};
     for (int o = 0; o < hp.n_out; ++o)
@@ -905,12 +917,13 @@ static int backward_t(bn_mlp* h, const float* params, const float* out, const fl
     BN_LAUNCH_CHECK();
   }
   // heads' first layer: wgrad (+ bias gradient; the fp32 mode got it from heads_bwd_kernel) per block, dgrad into the features
+  cudaStream_t sw1 = fork();
   for (int b = 0; b < hp.n_blocks; ++b) {
     const int lin = h->blk_lin0[b];
     // the colour head (block 0) also reads the encoded view direction: In = [features | dir enc | pad], dW is [HH, F + DE]
     const int kin = F + (b == 0 ? h->DE : 0), no = (b == 0 && h->DE) ? h->ldfe : F;
     if (int rc = layer_wgrad<T>(h, w.GHD + (long long)b * h->HH, w.ldhd, w.FE, w.ldfe, h->HH, no, P, g + c.w_off[lin], kin, kin, no,
-                                kTC ? g + hp.b1_off[b] : nullptr, s)) return rc;
+                                kTC ? g + hp.b1_off[b] : nullptr, sw1)) return rc;
   }
   {
     DgradArgs<T> a;
@@ -918,7 +931,7 @@ static int backward_t(bn_mlp* h, const float* params, const float* out, const fl
   }
   // feature layer
   {
-    if (int rc = layer_wgrad<T>(h, w.GFE, F, Hl, ldl, F, F, P, g + c.w_off[BN_LIN_FEATS], F, F, F, g + c.b_off[BN_LIN_FEATS], s)) return rc;
+    if (int rc = layer_wgrad<T>(h, w.GFE, F, Hl, ldl, F, F, P, g + c.w_off[BN_LIN_FEATS], F, F, F, g + c.b_off[BN_LIN_FEATS], fork())) return rc;
     DgradArgs<T> a; a.mulc = w.C[L - 1]; a.ldm = F;
     if constexpr (kTC) {          // direct grads into h_{L-1}: dsigma w_sigma + sum_k dv_k Wg_k, DPRE cols 16..19
       a.rank_rows = w.DPRE + 16; a.rank_ld = 64; a.n_rank = hp.ch_nlr >= 0 ? 4 : 1;
@@ -928,21 +941,41 @@ static int backward_t(bn_mlp* h, const float* params, const float* out, const fl
     if (normals) { a.add2 = w.U[L - 1]; a.ld2 = F; }
     if (int rc = layer_dgrad<T>(h, w.GFE, F, (const T*)h->WfT, F, P, F, F, a, w.GA, F, s)) return rc;
   }
-  // trunk, last layer first.  cur = dZ_l
-  T* cur = w.GA; T* nxt = w.GB;
+  // trunk, last layer first.  buf[ci] = dZ_l.  The weight gradient of layer l and the data gradient that produces dZ_{l-1}
+  // only share their input, so (tcgen05 mode) the wgrads run on the handle's side stream: their epilogue-only tails and
+  // the ramp of the next dgrad overlap instead of leaving the SMs idle between two persistent kernels.  dZ rotates through
+  // three buffers; a buffer is rewritten only after the wgrad that read it has finished (ev_w), and the side stream
+  // is joined back into `s` before returning (the whole pattern is stream-capturable).
+  T* buf[3] = {w.GA, w.GB, kTC ? w.G7D : nullptr};       // G7D is unused in tcgen05 mode (rank-4 epilogue addend instead)
+  int ci = 0;
+  int reader[3] = {-1, -1, -1};                           // layer whose wgrad (on s2) last read buf[i]
   for (int l = L - 1; l >= 0; --l) {
+    const T* cur = buf[ci];
     const bool enc_in = (l == 0 || l == h->skip);
     const T* In; long long ldin;
     if (enc_in) { In = w.X3; ldin = w.ldx3; } else { In = w.H[l - 1]; ldin = w.Hld[l - 1]; }
+    cudaStream_t sw = s;
+    if (overlap) {
+      BN_CUDA(cudaEventRecord(h->ev_dz[l], s));
+      BN_CUDA(cudaStreamWaitEvent(h->s2, h->ev_dz[l], 0));
+      sw = h->s2;
+    }
     if (int rc = layer_wgrad<T>(h, cur, F, In, ldin, F, h->Kpad[l], P, g + c.w_off[l], h->Kreal[l],
-                                enc_in ? h->E : h->Kpad[l], enc_in ? kEncPad : h->Kpad[l], g + c.b_off[l], s, 2.0 * P * F * h->Kreal[l])) return rc;
+                                enc_in ? h->E : h->Kpad[l], enc_in ? kEncPad : h->Kpad[l], g + c.b_off[l], sw, 2.0 * P * F * h->Kreal[l])) return rc;
+    if (overlap) { BN_CUDA(cudaEventRecord(h->ev_w[l], h->s2)); reader[ci] = l; }
     if (l > 0) {
+      const int ni = overlap ? (ci + 1) % 3 : (ci ^ 1);
+      if (overlap && reader[ni] >= 0) { BN_CUDA(cudaStreamWaitEvent(s, h->ev_w[reader[ni]], 0)); reader[ni] = -1; }
       const T* BT = (const T*)h->WTp[l] + (l == h->skip ? (long long)kEncPad * F : 0);
       DgradArgs<T> a; a.mulc = w.C[l - 1]; a.ldm = F;
       if (normals) { a.add2 = w.U[l - 1]; a.ld2 = F; }
-      if (int rc = layer_dgrad<T>(h, cur, F, BT, F, P, F, F, a, nxt, F, s)) return rc;
-      T* t = cur; cur = nxt; nxt = t;
+      if (int rc = layer_dgrad<T>(h, cur, F, BT, F, P, F, F, a, buf[ni], F, s)) return rc;
+      ci = ni;
     }
+  }
+  if (overlap) {                                          // join: the side stream is in order, its last event covers all of it
+    BN_CUDA(cudaEventRecord(h->ev_h[7], h->s2));
+    BN_CUDA(cudaStreamWaitEvent(s, h->ev_h[7], 0));
   }
   return BN_OK;
 }
@@ -1003,6 +1036,13 @@ extern "C" __attribute__((visibility("default"))) int bn_mlp_create(const bn_mlp
   BN_CUDA(cudaMalloc(&h->W2p, HK * 64 * sizeof(__nv_bfloat16)));
   BN_CUDA(cudaMalloc(&h->W2pT, HK * 64 * sizeof(__nv_bfloat16)));
   BN_CUDA(cudaMalloc(&h->Wsig, (size_t)64 * h->F * sizeof(__nv_bfloat16)));
+  BN_CUDA(cudaStreamCreateWithFlags(&h->s2, cudaStreamNonBlocking));
+  for (int l = 0; l < 16; ++l) {
+    BN_CUDA(cudaEventCreateWithFlags(&h->ev_dz[l], cudaEventDisableTiming));
+    BN_CUDA(cudaEventCreateWithFlags(&h->ev_w[l], cudaEventDisableTiming));
+  }
+  for (int i = 0; i < 8; ++i) BN_CUDA(cudaEventCreateWithFlags(&h->ev_h[i], cudaEventDisableTiming));
+  h->overlap = getenv("BN_NO_OVERLAP") == nullptr;       // A/B timing aid: serial backward on the caller's stream
   BN_CUDA(cudaMalloc(&h->WsigA, (size_t)64 * h->F * sizeof(__nv_bfloat16)));
   BN_CUDA(cudaMemset(h->WsigA, 0, (size_t)64 * h->F * sizeof(__nv_bfloat16)));
   *out = h;
@@ -1012,6 +1052,9 @@ extern "C" __attribute__((visibility("default"))) int bn_mlp_create(const bn_mlp
 extern "C" __attribute__((visibility("default"))) void bn_mlp_destroy(bn_mlp* h) {
   if (!h) return;
   for (int l = 0; l < h->L; ++l) { cudaFree(h->Wp[l]); cudaFree(h->WTp[l]); }
+  if (h->s2) cudaStreamDestroy(h->s2);
+  for (int l = 0; l < 16; ++l) { if (h->ev_dz[l]) cudaEventDestroy(h->ev_dz[l]); if (h->ev_w[l]) cudaEventDestroy(h->ev_w[l]); }
+  for (int i = 0; i < 8; ++i) if (h->ev_h[i]) cudaEventDestroy(h->ev_h[i]);
   cudaFree(h->Wf); cudaFree(h->WfT); cudaFree(h->W1); cudaFree(h->W1T); cudaFree(h->b1cat); cudaFree(h->W2p); cudaFree(h->W2pT); cudaFree(h->Wsig); cudaFree(h->WsigA);
   delete h;
 }

@@ -68,6 +68,8 @@ struct bn_mlp {
   int blk_lin0[bn::kMaxBlocks], blk_lin2[bn::kMaxBlocks], blk_head[bn::kMaxBlocks];
   bool synced;
   bool no_chain;
+  // backward: weight gradients run on a side stream next to the data-gradient chain (forked from / joined into the caller's stream)
+  cudaStream_t s2; cudaEvent_t ev_dz[16]; cudaEvent_t ev_w[16]; cudaEvent_t ev_h[8]; bool overlap;
   long long* chain_trace;
 };
 
