@@ -67,10 +67,60 @@ def infer_cfg(steps):
                       "note": "820 chunks per 2048^2 tile; ray-sharded over 8 GPUs with no collective"}), flush=True)
 
 
+def tile_cfg(side):
+    """configs[4]: one side x side tile (row-major pixel rays) rendered by render_tile, ray-sharded over the ranks of a
+    torchrun launch (no collective on the data path; the timing is the slowest rank's, taken on the device)."""
+    from brdf_nerf_b200.inference import render_tile, tile_shards
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    args = named_config("rpv111")
+    torch.manual_seed(0)
+    model = load_model(args, precision="bf16").to(dev)
+    n = side * side
+    lo, hi = tile_shards(n, args.chunk, world)[rank]
+    rays = make_rays(hi - lo, seed=rank).rays.to(dev)          # this rank's pixels (synthetic rays; only the count matters)
+
+    class _View:                                                # render_tile slices [lo:hi] of the tile's ray list
+        shape = (n, 11)
+
+        def __getitem__(self, sl):
+            return rays
+    keys = ("rgb_coarse", "depth_coarse", "albedo_accu_coarse", "nr_vw_coarse")
+    fn = lambda: render_tile({"coarse": model}, _View(), args, rank=rank, world_size=world, keys=keys,
+                             apply_brdf=True, cos_irra_on=True)
+    fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    res, _ = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    if rank == 0:
+        ms = float(t[0])
+        print(json.dumps({"config": f"cfg5 tile {side}x{side} RGB+depth+normals+albedo, ray-sharded over {world} GPU(s)",
+                          "n_gpus": world, "rays": n, "ms": ms, "rays_per_s": n / ms * 1e3,
+                          "tile_2048x2048_seconds": 2048 * 2048 / (n / ms * 1e3), "chunk": int(args.chunk)}), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--tile", type=int, default=0, help="render one tile of this side with render_tile (torchrun-aware) and exit")
     o = ap.parse_args()
+    if o.tile:
+        tile_cfg(o.tile)
+        return
     train_cfg("cfg3 BRDF stage RPV111 + analytic normals + cos_irra_on", "rpv111", 1024, o.steps, apply_brdf=True, cos_irra_on=True)
     train_cfg("cfg4 Hapke b,c,theta, 8192 rays", "hapke_bct", 8192, max(3, o.steps // 3), apply_brdf=True, apply_theta=True, cos_irra_on=True)
     train_cfg("cfg4 microfacet, 8192 rays", "microfacet", 8192, max(3, o.steps // 3), apply_brdf=True, cos_irra_on=True)
