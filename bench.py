@@ -218,22 +218,38 @@ def run_ours(opts):
     # kernels of this library inside the timed region: eager launches counted by the library itself, plus the
     # kernel nodes every CUDA-graph replay executes (counted once, at capture time)
     launches = (lib.bn_launch_count() - lc0) + opts.steps * getattr(trainer, "graph_launches", 0)
-    # ---- end to end through the public API: every step copies its batch from pinned host memory into the device (H2D,
-    # inside Trainer.step) and reads its loss back (D2H).  The read of step k is issued right after step k and awaited
-    # after step k+1 has been enqueued, the way a training loop logs its loss without stalling the device.
-    pin = torch.empty(2, dtype=torch.float32).pin_memory()
-    evs = [torch.cuda.Event(), torch.cuda.Event()]
+    # ---- end to end through the public API: every step's batch starts in pinned host memory and is copied into the device
+    # (H2D), every step's loss is read back into host memory (D2H), both inside the timed region.  --feed prefetch (default):
+    # Trainer.prefetch() copies batch k+1 on the trainer's copy stream while step k computes and read_loss_async() moves the
+    # loss on that same stream; --feed inline: both copies are issued on the compute stream between two graph replays.
+    # The host awaits the loss of step k after step k+1 has been enqueued, the way a training loop logs without stalling.
+    pin = torch.empty(4, dtype=torch.float32).pin_memory()
+    evs = [None] * 4
     barrier()
     e0.record()
     prev = None
-    for i in range(opts.steps):
-        loss = trainer.step(host_batch if opts.graph else host_batch.to(dev, non_blocking=True))
-        pin[i % 2:i % 2 + 1].copy_(loss.reshape(1), non_blocking=True)
-        evs[i % 2].record()
-        if prev is not None:
-            evs[prev].synchronize()
-            loss_host = float(pin[prev])
-        prev = i % 2
+    loss_host = float("nan")
+    if opts.feed == "prefetch":
+        staged = trainer.prefetch(host_batch)
+        for i in range(opts.steps):
+            loss = trainer.step(staged)
+            if i + 1 < opts.steps:
+                staged = trainer.prefetch(host_batch)
+            evs[i % 4] = trainer.read_loss_async(loss, pin[i % 4:i % 4 + 1])
+            if prev is not None:
+                evs[prev].synchronize()
+                loss_host = float(pin[prev])
+            prev = i % 4
+    else:
+        for i in range(opts.steps):
+            loss = trainer.step(host_batch if opts.graph else host_batch.to(dev, non_blocking=True))
+            pin[i % 4:i % 4 + 1].copy_(loss.reshape(1), non_blocking=True)
+            evs[i % 4] = torch.cuda.Event()
+            evs[i % 4].record()
+            if prev is not None:
+                evs[prev].synchronize()
+                loss_host = float(pin[prev])
+            prev = i % 4
     evs[prev].synchronize()
     loss_host = float(pin[prev])
     e1.record()
@@ -311,7 +327,7 @@ def run_ours(opts):
                 "config": {"workload": "spsbrdf-nerf Lambertian pretrain + depth supervision (ds_lambda=10, --mapping), "
                                        "1024 rays x (64+64) samples per GPU per step, fc 8x512, random init seed 0",
                            "rays_per_gpu": RAYS_PER_GPU, "global_rays": total_rays, "parallelism": f"ray-sharded dp{world}",
-                           "cuda_graph": bool(opts.graph),
+                           "cuda_graph": bool(opts.graph), "e2e_feed": opts.feed,
                            "l2": "per-step working set (~3.4 GB of activations) >> 126 MB L2; no explicit flush"},
                 "e2e": {"value": total_rays / (ms_e2e * 1e-3), "unit": "rays/s", "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": int(host_batch.flat.numel()), "d2h_bytes_per_step": 4},
@@ -331,6 +347,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--graph", type=int, default=1)
+    ap.add_argument("--feed", default="prefetch", choices=["prefetch", "inline"],
+                    help="e2e leg: host batches through Trainer.prefetch() on a copy stream, or copied on the compute stream")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-composite", action="store_true", help="skip the compositing (HBM) roofline leg")
     opts = ap.parse_args()

@@ -31,6 +31,8 @@ class RayBatch:
     target_depths: Optional[torch.Tensor] = None   # (N, 2) [depth, correlation weight]
     target_std: Optional[torch.Tensor] = None      # (N,)
     flat = None                                    # set by packed(): the single buffer behind all tensors
+    _ready = None                                  # set by Trainer.prefetch(): events guarding a staging batch
+    _free = None
 
     def to(self, device, non_blocking=False):
         mv = lambda t: None if t is None else t.to(device, non_blocking=non_blocking)

@@ -73,6 +73,10 @@ class Trainer:
         self.whole_step_graph = self.world == 1
         self._opt_state = None              # device [lr, step, bc1, sqrt(bc2)] of the graph-captured Adam
         self._dev_lr, self._dev_step, self._graph_updates = None, 0, False
+        # host feed (prefetch / read_loss_async): a copy stream next to the compute stream, two staging batches
+        self._copy_stream = None
+        self._stage, self._stage_ready, self._stage_free, self._stage_i = [None, None], [None, None], [None, None], 0
+        self._loss_ring, self._loss_i = None, 0
 
     # one optimisation step; `batch` tensors must already live on the model's device
     def _step_impl(self, batch: RayBatch, draws, kw):
@@ -114,10 +118,63 @@ class Trainer:
         kw = dict(apply_brdf=apply_brdf, bTestNormal=False, bTestSun_v=False, gsam_only=gsam_only,
                   apply_theta=apply_theta, cos_irra_on=cos_irra_on)
         if not self.use_graph or draws is not None:
+            ready = getattr(batch, "_ready", None)
+            if ready is not None:                         # prefetch()ed staging batch, consumed in place by the eager step
+                torch.cuda.current_stream().wait_event(ready)
             loss = self._step_impl(batch, draws, kw)
             self._reduce_and_update()
+            if ready is not None:
+                batch._free.record()
             return loss
         return self._graph_step(batch, kw)
+
+    # ---- host feed: the H2D copy of step k+1's batch and the D2H read of step k's loss run on a copy stream, so the compute
+    # stream sees kernels only (no copy-engine hop between two graph replays).  Event order, per staging buffer b:
+    #   copy stream:    wait free[b] -> H2D host batch -> record ready[b]
+    #   compute stream: wait ready[b] -> static <- staging[b] (device copy) -> record free[b] -> graph replay
+    def prefetch(self, host_batch: RayBatch) -> RayBatch:
+        """Starts the host->device copy of a packed (ideally pinned) host batch on the trainer's copy stream and returns
+        the device-side staging batch to hand to `step()`; call it for batch k+1 right after enqueuing step k.  At most
+        two prefetched batches may be outstanding (two staging buffers)."""
+        if host_batch.flat is None:
+            raise ValueError("prefetch() needs a packed host batch: RayBatch.packed(pin=True)")
+        dev = self.model.flat_params.device
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        b = self._stage_i
+        self._stage_i ^= 1
+        st = self._stage[b]
+        if st is None or st.flat.numel() != host_batch.flat.numel():
+            st = self._stage[b] = host_batch.packed(device=dev)
+            self._stage_ready[b], self._stage_free[b] = torch.cuda.Event(), torch.cuda.Event()
+            self._stage_free[b].record()
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._stage_free[b])
+            st.flat.copy_(host_batch.flat, non_blocking=True)
+            self._stage_ready[b].record()
+        st._ready, st._free = self._stage_ready[b], self._stage_free[b]
+        return st
+
+    def read_loss_async(self, loss: torch.Tensor, pinned_out: torch.Tensor) -> "torch.cuda.Event":
+        """Copies a step's loss into pinned host memory on the copy stream; returns the event that marks the value valid.
+        The value is first parked in a 4-slot device ring (the graph's loss tensor is rewritten by the next replay), so
+        the caller may run up to three steps ahead of the read."""
+        dev = self.model.flat_params.device
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        if self._loss_ring is None:
+            self._loss_ring = torch.zeros(4, 1, dtype=torch.float32, device=dev)
+        slot = self._loss_ring[self._loss_i % 4]
+        self._loss_i += 1
+        torch.add(loss.reshape(1), 0.0, out=slot)         # an elementwise kernel on the compute stream, not a memcpy
+        parked = torch.cuda.Event()
+        parked.record()
+        done = torch.cuda.Event()
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(parked)
+            pinned_out.copy_(slot, non_blocking=True)
+            done.record()
+        return done
 
     def static_batch(self) -> Optional[RayBatch]:
         """The captured graph's input buffers (None before the first graph step): producers may write the next batch
@@ -142,6 +199,9 @@ class Trainer:
 
     def _graph_step(self, batch: RayBatch, kw):
         kw = dict(kw, _use_depth=self.use_depth_loss, _use_nr=self.use_normal_reg, _use_hs=self.use_hard_surface)
+        ready = getattr(batch, "_ready", None)
+        if ready is not None:                             # a prefetch()ed staging batch: its H2D copy runs on the copy stream
+            torch.cuda.current_stream().wait_event(ready)
         if self._graph is None or self._kw != kw:
             dev = self.model.flat_params.device
             self._static = batch.packed(device=dev)       # one buffer: a packed host batch arrives with a single copy
@@ -175,6 +235,8 @@ class Trainer:
                                 (batch.rays, batch.rgbs, batch.valid_depth, batch.target_depths, batch.target_std)):
                 if dst is not None:
                     dst.copy_(src, non_blocking=True)
+        if ready is not None:
+            batch._free.record()                          # the staging buffer may be refilled from here on
         if not self._graph_updates:
             self._graph.replay()
             self._reduce_and_update()

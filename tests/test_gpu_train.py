@@ -267,3 +267,35 @@ def test_whole_step_graph_advances_optimizer(cuda):
     losses.append(tr.step(batch).item())
     assert tr.step_count == 6 and tr._opt_state[1].item() == 6.0 and abs(tr._opt_state[0].item() - 4e-4) < 1e-10
     assert all(math.isfinite(x) for x in losses) and losses[-1] < losses[0]
+
+
+@pytest.mark.parametrize("use_graph", [True, False])
+def test_prefetch_feed_delivers_batches_and_losses(cuda, use_graph):
+    """Host feed on the copy stream (Trainer.prefetch / read_loss_async): every step consumes exactly the host batch that was
+    prefetched for it, and the loss that arrives in pinned memory is that step's loss."""
+    args = named_config("lambertian_ds")
+    n = 256
+    hosts = [make_rays(n, seed=100 + k, depth_supervision=True).packed(pin=True) for k in range(3)]
+    torch.manual_seed(0)
+    m = load_model(args, precision="bf16").to(cuda)
+    tr = Trainer(m, args, use_graph=use_graph)
+    pin = torch.full((8,), float("nan")).pin_memory()
+    direct, evs, seen = [], [], []
+    staged = tr.prefetch(hosts[0])
+    for i in range(8):
+        if use_graph:                                      # the graph reads its static buffers, refilled inside step()
+            loss = tr.step(staged)
+            snap = (tr.static_batch().rays.clone(), tr.static_batch().rgbs.clone())
+        else:                                              # the eager step reads the staging batch in place
+            torch.cuda.current_stream().wait_event(staged._ready)
+            snap = (staged.rays.clone(), staged.rgbs.clone())
+            loss = tr.step(staged)
+        seen.append(snap)
+        direct.append(loss.clone())
+        staged = tr.prefetch(hosts[(i + 1) % 3])
+        evs.append(tr.read_loss_async(loss, pin[i:i + 1]))
+    for i, ev in enumerate(evs):
+        ev.synchronize()
+        assert torch.equal(seen[i][0].cpu(), hosts[i % 3].rays) and torch.equal(seen[i][1].cpu(), hosts[i % 3].rgbs)
+        assert pin[i].item() == direct[i].item() and math.isfinite(pin[i].item())
+    assert tr.step_count == 8
