@@ -37,7 +37,7 @@ class MlpCfg(C.Structure):
                 ("w_off", C.c_int64 * BN_NUM_LINEAR), ("b_off", C.c_int64 * BN_NUM_LINEAR), ("n_params", C.c_int64)]
 
 
-_P, _I, _F, _L, _Z = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_size_t
+_P, _I, _F, _L, _Z, _D = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_size_t, C.c_double
 
 _SIGS = {
     "bn_abi_version": (C.c_int, []),
@@ -77,6 +77,12 @@ _SIGS = {
     "bn_debug_gemm": (C.c_int, [_I, _I, _P, C.c_longlong, _P, C.c_longlong, _P, C.c_longlong, C.c_longlong, _I, C.c_longlong, _P]),
     "bn_adam_step": (C.c_int, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P]),
     "bn_adam_step_graph": (C.c_int, [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _F, _P]),
+    "bn_dsm_points": (C.c_int, [_P, _I, _P, C.c_longlong, _D, _D, _D, _D, _P, _P, _P, _P, _P]),
+    "bn_dsm_workspace_bytes": (_Z, [_I, _I, _I, _F]),
+    "bn_dsm_rasterize": (C.c_int, [_P, _I, _I, C.c_longlong, _D, _D, _D, _I, _I, _I, _F, _P, _P, _P, _Z, _P]),
+    "bn_dsm_accumulate": (C.c_int, [_P, _I, _I, C.c_longlong, _D, _D, _D, _I, _I, _I, _F, _I, _P, _Z, _P]),
+    "bn_dsm_finalize": (C.c_int, [_I, _I, _I, _F, _P, _Z, _P, _P, _P]),
+    "bn_dsm_normals_from_points": (C.c_int, [_P, _I, _I, _P, _P]),
 }
 
 _lib = None

@@ -149,3 +149,16 @@ def make_tile_rays(h: int, w: int, view: int = 0) -> torch.Tensor:
     far = torch.full((n, 1), _SLAB_THICKNESS / abs(float(d0[2])), dtype=torch.float64)
     rays = torch.cat([o, d, torch.zeros(n, 1, dtype=torch.float64), far, s0.expand(n, 3)], -1)
     return rays.to(torch.float32).contiguous()
+
+
+def tile_surface_depth(rays: torch.Tensor) -> torch.Tensor:
+    """Depth (distance along each ray, float32) at which the rays of a tile meet the synthetic height field
+    z = -0.1 + 0.1 sin(3x) cos(2y): stands in for the rendered `depth_coarse` of a tile in the DSM tests / benchmarks."""
+    r = rays.to(torch.float64).cpu()
+    return _surface_depth(r[:, 0:3], r[:, 3:6]).to(torch.float32)
+
+
+# georeferencing of the synthetic scene (stands in for scene.loc, satellite_rgb_dep.py:163-165): a 2048-pixel tile at a
+# ground sampling distance of ~0.3 m spans 2 * 307.2 m; UTM-sized offsets so that float32 / float64 effects are realistic
+SCENE_RANGE = 307.2
+SCENE_CENTER = (368123.4, 3459876.5, 35.2)

@@ -310,6 +310,48 @@ int bn_adam_step_graph(float* params, const float* grads, float* exp_avg, float*
                        float* state, float beta1, float beta2, float eps, float weight_decay, float grad_scale,
                        cudaStream_t stream);
 
+/* ------------------------------------------------------------------ tile inference -> DSM */
+
+/* get_latlonalt_from_nerf_prediction with cs == 'utm' (datasets/satellite_rgb_dep.py:601-634; callers eval.py:170,
+ * main.py:621): point = ((double)o + (double)d * (double)depth) * scene_range + center, every operation rounded separately
+ * in float64 — bit-exact against the reference's torch/numpy result.  rays: n_rays records of ray_stride floats
+ * [o(3), d(3), ...] (6 <= ray_stride <= 16); depth (n_rays); scene_range / center_*: the dataset's float32 `range` /
+ * `center` values (satellite_rgb_dep.py:164-165) widened to double.  cloud (n_rays,3) float64 [east, north, alt];
+ * points_f32 (n_rays,3) nullable: the same points rounded to float32 (the `pts3d` operand of calc_normal_from_depth_v2,
+ * satellite_rgb_dep.py:578-585); bounds nullable: 4 doubles [xmin, xmax, ymin, ymax] of the finite points (the operands
+ * of the grid derivation :666-671) with bounds_scratch = 4 uint64 of device scratch (both or neither). */
+int bn_dsm_points(const float* rays, int ray_stride, const float* depth, long long n_rays, double scene_range,
+                  double center_x, double center_y, double center_z, double* cloud, float* points_f32, double* bounds,
+                  unsigned long long* bounds_scratch, cudaStream_t stream);
+
+/* Host-only query: bytes of device workspace bn_dsm_rasterize needs for this raster. */
+size_t bn_dsm_workspace_bytes(int xsize, int ysize, int radius, float sigma);
+
+/* plyflatten(cloud, xoff, yoff, resolution, xsize, ysize, radius, sigma) as called at satellite_rgb_dep.py:680 (radius=1,
+ * sigma=inf; third-party plyflatten==0.2.0, requirements.txt:11): point p falls into cell i = floor((x-xoff)/resolution),
+ * j = floor((yoff-y)/resolution) and adds its value with weight w (1 when sigma is +inf, else exp(-dist^2/(2 sigma^2)) of
+ * its distance to the cell centre) to every cell of the (2 radius+1)^2 window that lies inside the raster; raster
+ * (ysize,xsize) float32 = weighted mean, NaN where no point contributed; count (ysize,xsize) nullable = weight sums.
+ * cloud: n_points rows of cloud_stride doubles [x, y, ...], value_col (>= 2) selects the rasterised column.  Sums are
+ * float64 atomics (the reference keeps an order-dependent float32 running mean: rasters agree to ~1e-4, counts exactly). */
+int bn_dsm_rasterize(const double* cloud, int cloud_stride, int value_col, long long n_points, double xoff, double yoff,
+                     double resolution, int xsize, int ysize, int radius, float sigma, float* raster, float* count,
+                     void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+/* The two halves of bn_dsm_rasterize, for a tile whose rays are sharded over several GPUs (pixel blocks per
+ * rank): every rank accumulates its own points into its workspace (zero_first = 1 on the first call), the workspaces are
+ * summed across ranks (one all-reduce of workspace_bytes viewed as cells float64 followed by cells float32,
+ * cells = bn_dsm_workspace_bytes / 12), then bn_dsm_finalize turns the accumulators into the raster on every rank. */
+int bn_dsm_accumulate(const double* cloud, int cloud_stride, int value_col, long long n_points, double xoff, double yoff,
+                      double resolution, int xsize, int ysize, int radius, float sigma, int zero_first,
+                      void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int bn_dsm_finalize(int xsize, int ysize, int radius, float sigma, const void* workspace, size_t workspace_bytes,
+                    float* raster, float* count, cudaStream_t stream);
+
+/* calc_normal_from_pts3d with valid_depth=None (sat_utils.py:16-50): normals (height,width,3) of a float32 point image
+ * (height,width,3) from the four normalised cross products of its neighbour differences; zero on the border. */
+int bn_dsm_normals_from_points(const float* points, int height, int width, float* normals, cudaStream_t stream);
+
 /* Unit-test hook: one GEMM of the MLP engine in isolation (kind 0: out[M,N] = A[M,K] B[N,K]^T;
  * kind 1: out[M,N] += A[K,M]^T B[K,N], fp32 atomics). precision selects tcgen05 (bf16 operands)
  * or CUDA cores (fp32 operands). */

@@ -110,3 +110,48 @@ def render(model, args, rays, draws, dtype=torch.float32, **kw):
     if rest:
         raise RuntimeError(f"{len(rest)} queued draws were not consumed")
     return res, btype
+
+
+_ds_mod = None
+
+
+def load_dataset_module():
+    """Import (once) the live reference's `datasets/satellite_rgb_dep.py` WITHOUT running `datasets/__init__.py` (which
+    pulls in every dataset and their absent dependencies).  Only the pure-arithmetic methods of `SatelliteRGBDEPDataset`
+    are used (`get_latlonalt_from_nerf_prediction`, `calc_normal_from_depth`), called unbound with a stand-in `self`
+    that carries `range`, `center`, `cs`.  Stubs: rasterio, rpcm, pytorch3d.transforms (imported at module top, unused by
+    those methods) and the sibling `cal_rmse_depth` module (needs matplotlib / plyflatten)."""
+    global _ds_mod
+    if _ds_mod is not None:
+        return _ds_mod
+    load()
+    import importlib
+    for name in ("rpcm", "pytorch3d", "pytorch3d.transforms", "datasets.cal_rmse_depth"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["pytorch3d.transforms"].axis_angle_to_matrix = None
+    sys.modules["datasets.cal_rmse_depth"].cal_rmse_depth = None
+    if "datasets" not in sys.modules or not hasattr(sys.modules["datasets"], "__path__"):
+        pkg = types.ModuleType("datasets")
+        pkg.__path__ = [os.path.join(REF_ROOT, "datasets")]
+        sys.modules["datasets"] = pkg
+    with contextlib.redirect_stdout(io.StringIO()):
+        _ds_mod = importlib.import_module("datasets.satellite_rgb_dep")
+    return _ds_mod
+
+
+def ref_latlonalt(rays, depth, scene_range, center, cs="utm"):
+    """The live reference's get_latlonalt_from_nerf_prediction (satellite_rgb_dep.py:601-634)."""
+    mod = load_dataset_module()
+    me = types.SimpleNamespace(range=torch.tensor(float(scene_range)), center=torch.tensor([float(c) for c in center]), cs=cs)
+    return mod.SatelliteRGBDEPDataset.get_latlonalt_from_nerf_prediction(me, rays, depth)
+
+
+def ref_normals_from_pts3d(pts3d):
+    """The live reference's sat_utils.calc_normal_from_pts3d(pts3d, valid_depth=None, Flatten=False)[0] (sat_utils.py:16-50)."""
+    load_dataset_module()
+    import warnings
+    import sat_utils as ref_sat_utils
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")          # torch.cross without dim= is deprecated
+        return ref_sat_utils.calc_normal_from_pts3d(pts3d, None, False)[0]

@@ -107,3 +107,22 @@ def test_regularizer_losses_vs_reference():
             continue
         s = p.grad.abs().max().item()
         assert (p.grad - go).abs().max().item() <= 2e-3 * s + 1e-9, name
+
+
+def test_dsm_cloud_and_normals_vs_reference():
+    """the DSM oracle's float64 point cloud and the neighbour-cross-product normals are bit-identical to the
+    live reference methods (get_latlonalt_from_nerf_prediction, sat_utils.calc_normal_from_pts3d)."""
+    import numpy as np
+    from brdf_nerf_b200.synth import SCENE_CENTER, make_tile_rays, tile_surface_depth
+    from oracle import dsm_np as D
+    h, w = 21, 34
+    rays = make_tile_rays(h, w, view=2)
+    depth = tile_surface_depth(rays) + 0.01 * torch.rand(h * w, generator=torch.Generator().manual_seed(1))
+    rng = 9.75
+    e, n, a = RH.ref_latlonalt(rays, depth, rng, SCENE_CENTER)
+    e2, n2, a2 = D.latlonalt_from_nerf_prediction(rays.numpy(), depth.numpy(), rng, SCENE_CENTER)
+    assert np.array_equal(e, e2) and np.array_equal(n, n2) and np.array_equal(a, a2)
+    pts = torch.from_numpy(np.vstack([e, n, a]).T).type(torch.FloatTensor).reshape(h, w, 3)
+    assert torch.equal(RH.ref_normals_from_pts3d(pts), D.calc_normal_from_pts3d(pts))
+    assert torch.equal(D.normal_from_depth_v2(rays.numpy(), depth.numpy(), h, w, rng, SCENE_CENTER).reshape(h, w, 3),
+                       RH.ref_normals_from_pts3d(pts))
