@@ -219,9 +219,11 @@ def run_ours(opts):
     # kernel nodes every CUDA-graph replay executes (counted once, at capture time)
     launches = (lib.bn_launch_count() - lc0) + opts.steps * getattr(trainer, "graph_launches", 0)
     # ---- end to end through the public API: every step's batch starts in pinned host memory and is copied into the device
-    # (H2D), every step's loss is read back into host memory (D2H), both inside the timed region.  --feed prefetch (default):
-    # Trainer.prefetch() copies batch k+1 on the trainer's copy stream while step k computes and read_loss_async() moves the
-    # loss on that same stream; --feed inline: both copies are issued on the compute stream between two graph replays.
+    # (H2D), every step's loss is read back into host memory (D2H), both inside the timed region.  --feed inline (default):
+    # both copies are issued on the compute stream between two graph replays; --feed prefetch: Trainer.prefetch() copies batch
+    # k+1 on the trainer's copy stream while step k computes and read_loss_async() moves the loss on that same stream
+    # (measured on B200, profiles/r01f_exp_e2e.log: no gain, the two copies cost ~5 us each; the e2e leg differs from the
+    # resident leg mainly by running later, on a GPU that has reached its power cap).
     # The host awaits the loss of step k after step k+1 has been enqueued, the way a training loop logs without stalling.
     pin = torch.empty(4, dtype=torch.float32).pin_memory()
     evs = [None] * 4
@@ -347,7 +349,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--graph", type=int, default=1)
-    ap.add_argument("--feed", default="prefetch", choices=["prefetch", "inline"],
+    ap.add_argument("--feed", default="inline", choices=["prefetch", "inline"],
                     help="e2e leg: host batches through Trainer.prefetch() on a copy stream, or copied on the compute stream")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-composite", action="store_true", help="skip the compositing (HBM) roofline leg")

@@ -81,9 +81,18 @@ __global__ void __launch_bounds__(kPtsBlock) dsm_points_kernel(const float* __re
     if (pts_f32) pts_f32[base * 3 + t] = (float)v;
   }
   if (keys) {
+    // block maximum through shared memory, then ONE conditional atomic per key and block: same-address atomics serialise in
+    // L2 (measured: a per-warp atomicMax made this kernel 375 us for 4.2 M rays), and after the first few blocks almost no
+    // block still raises a bound, which a plain (possibly stale, hence conservative) read detects
+    __shared__ unsigned long long s_key[kPtsBlock / 32][4];
     k0 = warp_max_u64(k0); k1 = warp_max_u64(k1); k2 = warp_max_u64(k2); k3 = warp_max_u64(k3);
-    if ((tid & 31) == 0 && k0 != 0) {
-      atomicMax(keys + 0, k0); atomicMax(keys + 1, k1); atomicMax(keys + 2, k2); atomicMax(keys + 3, k3);
+    if ((tid & 31) == 0) { s_key[tid >> 5][0] = k0; s_key[tid >> 5][1] = k1; s_key[tid >> 5][2] = k2; s_key[tid >> 5][3] = k3; }
+    __syncthreads();
+    if (tid < 4) {
+      unsigned long long m = 0;
+#pragma unroll
+      for (int wi = 0; wi < kPtsBlock / 32; ++wi) m = s_key[wi][tid] > m ? s_key[wi][tid] : m;
+      if (m != 0 && m > *(volatile unsigned long long*)(keys + tid)) atomicMax(keys + tid, m);
     }
   }
 }
@@ -165,8 +174,8 @@ __global__ void __launch_bounds__(256) dsm_finalize_kernel(DsmGrid g, const doub
 // l2_normalize (train_utils.py:28-33): x / sqrt(max(sum x^2, eps)), eps = float32 machine epsilon
 __device__ __forceinline__ float3 l2n(float3 a) {
   const float n = fmaxf(a.x * a.x + a.y * a.y + a.z * a.z, 1.1920928955078125e-07f);
-  const float s = sqrtf(n);
-  return make_float3(a.x / s, a.y / s, a.z / s);
+  const float inv = 1.0f / sqrtf(n);        // one division per vector (x * (1/s) vs the reference's x / s: <= 1 ulp apart)
+  return make_float3(a.x * inv, a.y * inv, a.z * inv);
 }
 __device__ __forceinline__ float3 sub3(float3 a, float3 b) { return make_float3(a.x - b.x, a.y - b.y, a.z - b.z); }
 __device__ __forceinline__ float3 cross3(float3 a, float3 b) {
