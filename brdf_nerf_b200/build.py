@@ -19,8 +19,8 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
           "-diag-suppress", "177"]
 # per-file extra flags: the sample generator must round after every operation (bit-exact contract)
-EXTRA = {"sampler.cu": ["-fmad=false"], "dsm.cu": ["-fmad=false"]}
-SOURCES = ["api.cu", "sampler.cu", "composite.cu", "shade.cu", "loss.cu", "mlp.cu", "normals.cu", "tc_host.cu", "dsm.cu"]
+EXTRA = {"sampler.cu": ["-fmad=false"], "dsm.cu": ["-fmad=false"], "georays.cu": ["-fmad=false"]}
+SOURCES = ["api.cu", "sampler.cu", "composite.cu", "shade.cu", "loss.cu", "mlp.cu", "normals.cu", "tc_host.cu", "dsm.cu", "georays.cu"]
 
 
 def _digest() -> str:

@@ -56,13 +56,20 @@ constexpr int kMaxRayStride = 16;
 __global__ void __launch_bounds__(kPtsBlock) dsm_points_kernel(const float* __restrict__ rays, int ray_stride,
                                                                const float* __restrict__ depth, long long n, double range,
                                                                double cx, double cy, double cz, double* __restrict__ cloud,
-                                                               float* __restrict__ pts_f32, unsigned long long* __restrict__ keys) {
-  __shared__ float s_ray[kPtsBlock * kMaxRayStride];
-  __shared__ double s_out[kPtsBlock * 3];
+                                                               float* __restrict__ pts_f32, unsigned long long* __restrict__ keys,
+                                                               int vec_ok) {
+  __shared__ __align__(16) float s_ray[kPtsBlock * kMaxRayStride];
+  __shared__ __align__(16) double s_out[kPtsBlock * 3];
   const long long base = (long long)blockIdx.x * kPtsBlock;
   const int cnt = (int)((n - base) < kPtsBlock ? (n - base) : kPtsBlock);
   const int tid = threadIdx.x;
-  for (int t = tid; t < cnt * ray_stride; t += kPtsBlock) s_ray[t] = rays[base * ray_stride + t];
+  const bool full = cnt == kPtsBlock && vec_ok;                       // full blocks move 16-byte vectors (block bases are 16 B aligned)
+  if (full) {
+    const float4* src = reinterpret_cast<const float4*>(rays + base * ray_stride);
+    for (int t = tid; t < kPtsBlock * ray_stride / 4; t += kPtsBlock) reinterpret_cast<float4*>(s_ray)[t] = src[t];
+  } else {
+    for (int t = tid; t < cnt * ray_stride; t += kPtsBlock) s_ray[t] = rays[base * ray_stride + t];
+  }
   __syncthreads();
   unsigned long long k0 = 0, k1 = 0, k2 = 0, k3 = 0;                   // 0 is below the key of every double
   if (tid < cnt) {
@@ -75,10 +82,18 @@ __global__ void __launch_bounds__(kPtsBlock) dsm_points_kernel(const float* __re
     if (isfinite(x) && isfinite(y)) { k0 = dkey(x); k1 = dkey(y); k2 = dkey(-x); k3 = dkey(-y); }
   }
   __syncthreads();
-  for (int t = tid; t < cnt * 3; t += kPtsBlock) {
-    const double v = s_out[t];
-    cloud[base * 3 + t] = v;
-    if (pts_f32) pts_f32[base * 3 + t] = (float)v;
+  if (full) {
+    double2* dst = reinterpret_cast<double2*>(cloud + base * 3);
+    for (int t = tid; t < kPtsBlock * 3 / 2; t += kPtsBlock) dst[t] = reinterpret_cast<const double2*>(s_out)[t];
+    if (pts_f32 && tid < kPtsBlock * 3 / 4)
+      reinterpret_cast<float4*>(pts_f32 + base * 3)[tid] = make_float4((float)s_out[4 * tid], (float)s_out[4 * tid + 1],
+                                                                        (float)s_out[4 * tid + 2], (float)s_out[4 * tid + 3]);
+  } else {
+    for (int t = tid; t < cnt * 3; t += kPtsBlock) {
+      const double v = s_out[t];
+      cloud[base * 3 + t] = v;
+      if (pts_f32) pts_f32[base * 3 + t] = (float)v;
+    }
   }
   if (keys) {
     // block maximum through shared memory, then ONE conditional atomic per key and block: same-address atomics serialise in
@@ -223,8 +238,9 @@ int bn_dsm_points(const float* rays, int ray_stride, const float* depth, long lo
   if (bounds) BN_CUDA(cudaMemsetAsync(bounds_scratch, 0, 4 * sizeof(unsigned long long), stream));
   const long long blocks = ceil_div_ll(n_rays, kPtsBlock);
   BN_CHECK_ARG(blocks < (1ll << 31), "too many rays for one launch");
+  const int vec_ok = ((uintptr_t)rays % 16 == 0) && ((uintptr_t)cloud % 16 == 0) && ((uintptr_t)points_f32 % 16 == 0);
   dsm_points_kernel<<<(unsigned)blocks, kPtsBlock, 0, stream>>>(rays, ray_stride, depth, n_rays, scene_range, center_x, center_y,
-                                                          center_z, cloud, points_f32, bounds_scratch);
+                                                          center_z, cloud, points_f32, bounds_scratch, vec_ok);
   BN_LAUNCH_CHECK();
   if (bounds) {
     dsm_bounds_kernel<<<1, 32, 0, stream>>>(bounds_scratch, bounds);

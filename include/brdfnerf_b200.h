@@ -352,6 +352,31 @@ int bn_dsm_finalize(int xsize, int ysize, int radius, float sigma, const void* w
  * (height,width,3) from the four normalised cross products of its neighbour differences; zero on the border. */
 int bn_dsm_normals_from_points(const float* points, int height, int width, float* normals, cudaStream_t stream);
 
+/* ------------------------------------------------------------------ ray feed: RPC camera -> ray records */
+
+/* The attributes of rpcm.RPCModel the path reads (dict_format "rpcm": scene JSON "rpc" entries, satellite_rgb_dep.py:246);
+ * rescale_rpc (sat_utils.py:90-108) multiplies row/col scale and offset by alpha.  HOST struct, passed by pointer. */
+typedef struct bn_rpc {
+  double row_offset, col_offset, lat_offset, lon_offset, alt_offset;
+  double row_scale, col_scale, lat_scale, lon_scale, alt_scale;
+  double row_num[20], row_den[20], col_num[20], col_den[20];
+} bn_rpc;
+
+/* get_rays (datasets/satellite_rgb_dep.py:23-78) [+ normalize_rays :550-559 when `normalize`, + the sun-direction
+ * columns of get_sun_dirs :561-576 / hstack :390 when sun_dir != NULL]: for every pixel, rpc.localization at max_alt
+ * (ray origin) and at min_alt (far point) by the iterative RPC inversion of the third-party `rpcm` package, mapped to
+ * ECEF (cs = 0, sat_utils.py:110-125) or UTM (cs = 1, sat_utils.py:148-162 via pyproj: zone utm_zone, GRS80, northern
+ * formula), o = near, d = unit(far - near), bounds [0, |far - near|], cast to float32 like the reference, then
+ * (o - center) / scene_range, near / scene_range, far / scene_range in float32.
+ * cols / rows: DEVICE (n_rays) float64 pixel coordinates, or both NULL = the row-major pixel grid of an image `width`
+ * pixels wide (np.meshgrid(arange(w), arange(h)) flattened, :353).  sun_dir: HOST 3 floats or NULL.  rays_out: DEVICE
+ * (n_rays, out_stride) float32, out_stride = 8, or 11 with sun_dir.  fail_count: DEVICE int (nullable), incremented for
+ * every ray whose localisation did not converge in 100 iterations (the reference raises). */
+int bn_rays_from_rpc(const bn_rpc* rpc, const double* cols, const double* rows, long long n_rays, int width,
+                     double min_alt, double max_alt, int cs, int utm_zone, int normalize, float center_x, float center_y,
+                     float center_z, float scene_range, const float* sun_dir, float* rays_out, int out_stride,
+                     int* fail_count, cudaStream_t stream);
+
 /* Unit-test hook: one GEMM of the MLP engine in isolation (kind 0: out[M,N] = A[M,K] B[N,K]^T;
  * kind 1: out[M,N] += A[K,M]^T B[K,N], fp32 atomics). precision selects tcgen05 (bf16 operands)
  * or CUDA cores (fp32 operands). */

@@ -155,3 +155,28 @@ def ref_normals_from_pts3d(pts3d):
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")          # torch.cross without dim= is deprecated
         return ref_sat_utils.calc_normal_from_pts3d(pts3d, None, False)[0]
+
+
+def ref_get_rays(cols, rows, rpc, min_alt, max_alt, cs="ecef"):
+    """The live reference's module-level get_rays (satellite_rgb_dep.py:23-78), driven by a duck-typed RPC object (anything
+    with `.localization(cols, rows, alts) -> (lons, lats)`; rpcm itself is not installed).  Only cs='ecef' runs here: the
+    'utm' branch calls pyproj."""
+    mod = load_dataset_module()
+    return mod.get_rays(cols, rows, rpc, min_alt, max_alt, cs=cs)
+
+
+def ref_normalize_rays(rays, scene_range, center):
+    mod = load_dataset_module()
+    me = types.SimpleNamespace(range=torch.tensor(float(scene_range)), center=torch.tensor([float(c) for c in center]))
+    return mod.SatelliteRGBDEPDataset.normalize_rays(me, rays.clone())
+
+
+def ref_sun_dirs(sun_elevation_deg, sun_azimuth_deg, n_rays):
+    mod = load_dataset_module()
+    return mod.SatelliteRGBDEPDataset.get_sun_dirs(None, sun_elevation_deg, sun_azimuth_deg, n_rays)
+
+
+def ref_latlon_to_ecef(lat, lon, alt):
+    load_dataset_module()
+    import sat_utils as ref_sat_utils
+    return ref_sat_utils.latlon_to_ecef_custom(lat, lon, alt)

@@ -126,3 +126,22 @@ def test_dsm_cloud_and_normals_vs_reference():
     assert torch.equal(RH.ref_normals_from_pts3d(pts), D.calc_normal_from_pts3d(pts))
     assert torch.equal(D.normal_from_depth_v2(rays.numpy(), depth.numpy(), h, w, rng, SCENE_CENTER).reshape(h, w, 3),
                        RH.ref_normals_from_pts3d(pts))
+
+
+def test_georays_pinned_parts_vs_reference():
+    """everything of get_rays / normalize_rays / get_sun_dirs / latlon_to_ecef_custom that lives in the
+    reference tree is bit-identical in the oracle (the RPC inversion itself is rpcm's: restated, unpinned)."""
+    import numpy as np
+    from oracle import georays_np as G
+    rpc = G.synthetic_rpc(2)
+    rng = np.random.default_rng(3)
+    cols, rows = rng.uniform(0, 2047, 300), rng.uniform(0, 2047, 300)
+    ref = RH.ref_get_rays(cols, rows, rpc, -10.0, 70.0, cs="ecef")
+    mine = G.get_rays(cols, rows, rpc, -10.0, 70.0, cs="ecef")
+    assert np.array_equal(ref.numpy(), mine)
+    c, r = (799000.0, -5452800.0, 3200200.0), 412.3
+    assert np.array_equal(RH.ref_normalize_rays(ref, r, c).numpy(), G.normalize_rays(mine, c, r))
+    assert np.array_equal(RH.ref_sun_dirs(41.0, 163.5, 7).numpy(), G.get_sun_dirs(41.0, 163.5, 7))
+    lat, lon, alt = rng.uniform(-80, 80, 100), rng.uniform(-180, 180, 100), rng.uniform(-100, 9000, 100)
+    for a, b in zip(RH.ref_latlon_to_ecef(lat, lon, alt), G.latlon_to_ecef_custom(lat, lon, alt)):
+        assert np.array_equal(a, b)
