@@ -141,6 +141,7 @@ def _launch(rpc: RPCModel, cols, rows, n, width, min_alt, max_alt, cs, device, n
     stride = 11 if sun_dir is not None else 8
     out = torch.empty(n, stride, dtype=torch.float32, device=dev)
     fail = torch.zeros(1, dtype=torch.int32, device=dev)
+    iters = torch.empty(2, dtype=torch.int32, device=dev)
     sun = (C.c_float * 3)(*[float(v) for v in sun_dir]) if sun_dir is not None else None
     c = [float(np.float32(v)) for v in (center if center is not None else (0.0, 0.0, 0.0))]
     s = rpc.as_struct()
@@ -148,7 +149,7 @@ def _launch(rpc: RPCModel, cols, rows, n, width, min_alt, max_alt, cs, device, n
         L.check(lib.bn_rays_from_rpc(C.byref(s), L.ptr(cols, torch.float64), L.ptr(rows, torch.float64), n, int(width),
                                      float(min_alt), float(max_alt), 0 if cs == "ecef" else 1, zones[0], 1 if normalize else 0,
                                      c[0], c[1], c[2], float(np.float32(scene_range)), sun, L.ptr(out), stride,
-                                     L.ptr(fail, torch.int32), L.stream_ptr()))
+                                     L.ptr(fail, torch.int32), L.ptr(iters, torch.int32), L.stream_ptr()))
     return out, fail
 
 

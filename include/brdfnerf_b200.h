@@ -371,11 +371,14 @@ typedef struct bn_rpc {
  * cols / rows: DEVICE (n_rays) float64 pixel coordinates, or both NULL = the row-major pixel grid of an image `width`
  * pixels wide (np.meshgrid(arange(w), arange(h)) flattened, :353).  sun_dir: HOST 3 floats or NULL.  rays_out: DEVICE
  * (n_rays, out_stride) float32, out_stride = 8, or 11 with sun_dir.  fail_count: DEVICE int (nullable), incremented for
- * every ray whose localisation did not converge in 100 iterations (the reference raises). */
+ * every ray whose localisation did not converge in 100 iterations (the reference raises).  iterations: DEVICE 2 ints of
+ * scratch / output: the iteration counts of the two localisation calls (max_alt, min_alt).  The reference's loop runs until
+ * the slowest pixel of a call has converged and applies that many iterations to every pixel; a first launch finds the two
+ * counts, a second one builds the rays with exactly those counts (no host round trip in between). */
 int bn_rays_from_rpc(const bn_rpc* rpc, const double* cols, const double* rows, long long n_rays, int width,
                      double min_alt, double max_alt, int cs, int utm_zone, int normalize, float center_x, float center_y,
                      float center_z, float scene_range, const float* sun_dir, float* rays_out, int out_stride,
-                     int* fail_count, cudaStream_t stream);
+                     int* fail_count, int* iterations, cudaStream_t stream);
 
 /* Unit-test hook: one GEMM of the MLP engine in isolation (kind 0: out[M,N] = A[M,K] B[N,K]^T;
  * kind 1: out[M,N] += A[K,M]^T B[K,N], fp32 atomics). precision selects tcgen05 (bf16 operands)

@@ -108,7 +108,7 @@ def test_georays_abi_argument_validation():
     call = lambda **kw: lib.bn_rays_from_rpc(*[kw.get(k, dflt) for k, dflt in (
         ("rpc", C.byref(s)), ("cols", None), ("rows", None), ("n", 16), ("width", 4), ("min_alt", 0.0), ("max_alt", 50.0),
         ("cs", 1), ("zone", 17), ("normalize", 0), ("cx", 0.0), ("cy", 0.0), ("cz", 0.0), ("range", 1.0), ("sun", None),
-        ("out", None), ("stride", 8), ("fail", None), ("stream", None))])
+        ("out", None), ("stride", 8), ("fail", None), ("iters", C.c_void_p(512)), ("stream", None))])
     assert call() == -1 and b"null pointer" in lib.bn_last_error()
     dummy = C.c_void_p(256)                                               # never dereferenced: validation fails first
     assert call(out=dummy, cs=2) == -1 and call(out=dummy, zone=0) == -1 and call(out=dummy, stride=11) == -1
