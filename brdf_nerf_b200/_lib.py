@@ -78,7 +78,7 @@ _SIGS = {
     "bn_adam_step": (C.c_int, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P]),
     "bn_adam_step_graph": (C.c_int, [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _F, _P]),
     "bn_rays_from_rpc": (C.c_int, [_P, _P, _P, C.c_longlong, _I, _D, _D, _I, _I, _I, _F, _F, _F, _F, _P, _P, _I, _P, _P, _P]),
-    "bn_dsm_points": (C.c_int, [_P, _I, _P, C.c_longlong, _D, _D, _D, _D, _P, _P, _P, _P, _P]),
+    "bn_dsm_points": (C.c_int, [_P, _I, _P, C.c_longlong, _D, _D, _D, _D, _I, _I, _P, _P, _P, _P, _P]),
     "bn_dsm_workspace_bytes": (_Z, [_I, _I, _I, _F]),
     "bn_dsm_rasterize": (C.c_int, [_P, _I, _I, C.c_longlong, _D, _D, _D, _I, _I, _I, _F, _P, _P, _P, _Z, _P]),
     "bn_dsm_accumulate": (C.c_int, [_P, _I, _I, C.c_longlong, _D, _D, _D, _I, _I, _I, _F, _I, _P, _Z, _P]),

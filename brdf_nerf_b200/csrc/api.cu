@@ -28,6 +28,7 @@ int after_launch(const char* kernel) {
 struct ProfRec { cudaEvent_t a, b; int kind; double work; };
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
+bool prof_enabled() { return g_prof_on; }
 void prof_begin(int kind, double work, cudaStream_t s) {
   if (!g_prof_on) return;
   ProfRec r; r.kind = kind; r.work = work;

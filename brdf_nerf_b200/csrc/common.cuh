@@ -25,6 +25,7 @@ int after_launch(const char* kernel);
 // optional per-launch CUDA-event timing of the GEMM family (bench.py roofline leg)
 void prof_begin(int kind, double work, cudaStream_t s);
 void prof_end(cudaStream_t s);
+bool prof_enabled();
 
 constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xffffffffu;

@@ -2,8 +2,10 @@
 // whole tile without leaving the GPU.
 //
 // Replaces (reference, paths relative to /root/reference):
-//   get_latlonalt_from_nerf_prediction   datasets/satellite_rgb_dep.py:601-634  (cs == 'utm', the default: opt.py:252)
-//       xyz = ((double)o + (double)d * (double)depth) * range + center      float64, every operation rounded separately
+//   get_latlonalt_from_nerf_prediction   datasets/satellite_rgb_dep.py:601-634
+//       xyz = ((double)o + (double)d * (double)depth) * range + center      float64, every operation rounded separately;
+//       cs == 'utm' (the default, opt.py:252): that is (east, north, alt); cs == 'ecef': ecef_to_latlon_custom
+//       (sat_utils.py:127-146) then the UTM projection of sat_utils.py:148-162 (geodesy.cuh)
 //   get_dsm_from_nerf_prediction         datasets/satellite_rgb_dep.py:636-697
 //       cloud bounds -> raster grid (:666-671, four scalars on the host), then plyflatten(cloud, xoff, yoff, resolution,
 //       xsize, ysize, radius=1, sigma=inf) (:680; plyflatten==0.2.0, requirements.txt:11): every point adds its height
@@ -25,6 +27,7 @@
 // whose value depends on the point order, so rasters agree to ~1e-4 m, the count image exactly.
 // Compiled with -fmad=false: the float64 point cloud is bit-exact against the reference's torch/numpy result.
 #include "common.cuh"
+#include "geodesy.cuh"
 
 #include <math.h>
 
@@ -57,7 +60,7 @@ __global__ void __launch_bounds__(kPtsBlock) dsm_points_kernel(const float* __re
                                                                const float* __restrict__ depth, long long n, double range,
                                                                double cx, double cy, double cz, double* __restrict__ cloud,
                                                                float* __restrict__ pts_f32, unsigned long long* __restrict__ keys,
-                                                               int vec_ok) {
+                                                               int vec_ok, int ecef, const __grid_constant__ UtmParams utm) {
   __shared__ __align__(16) float s_ray[kPtsBlock * kMaxRayStride];
   __shared__ __align__(16) double s_out[kPtsBlock * 3];
   const long long base = (long long)blockIdx.x * kPtsBlock;
@@ -75,9 +78,15 @@ __global__ void __launch_bounds__(kPtsBlock) dsm_points_kernel(const float* __re
   if (tid < cnt) {
     const float* ray = s_ray + tid * ray_stride;                        // odd stride (11): conflict free
     const double dep = (double)depth[base + tid];
-    const double x = ((double)ray[0] + (double)ray[3] * dep) * range + cx;
-    const double y = ((double)ray[1] + (double)ray[4] * dep) * range + cy;
-    const double z = ((double)ray[2] + (double)ray[5] * dep) * range + cz;
+    double x = ((double)ray[0] + (double)ray[3] * dep) * range + cx;
+    double y = ((double)ray[1] + (double)ray[4] * dep) * range + cy;
+    double z = ((double)ray[2] + (double)ray[5] * dep) * range + cz;
+    if (ecef) {                                                         // cs == 'ecef' (satellite_rgb_dep.py:629-631)
+      double lat, lon, alt;
+      from_ecef(x, y, z, lat, lon, alt);
+      to_utm(utm, lat, lon, x, y);
+      z = alt;
+    }
     s_out[tid * 3 + 0] = x; s_out[tid * 3 + 1] = y; s_out[tid * 3 + 2] = z;
     if (isfinite(x) && isfinite(y)) { k0 = dkey(x); k1 = dkey(y); k2 = dkey(-x); k3 = dkey(-y); }
   }
@@ -230,8 +239,10 @@ using namespace bn;
 
 extern "C" __attribute__((visibility("default")))
 int bn_dsm_points(const float* rays, int ray_stride, const float* depth, long long n_rays, double scene_range,
-                  double center_x, double center_y, double center_z, double* cloud, float* points_f32, double* bounds,
-                  unsigned long long* bounds_scratch, cudaStream_t stream) {
+                  double center_x, double center_y, double center_z, int cs, int utm_zone, double* cloud, float* points_f32,
+                  double* bounds, unsigned long long* bounds_scratch, cudaStream_t stream) {
+  BN_CHECK_ARG(cs == 0 || cs == 1, "cs must be 0 (ecef) or 1 (utm)");
+  BN_CHECK_ARG(cs == 1 || (utm_zone >= 1 && utm_zone <= 60), "utm_zone must be 1..60 when cs is ecef");
   BN_CHECK_ARG(rays && depth && cloud, "null pointer");
   BN_CHECK_ARG(n_rays > 0 && ray_stride >= 6 && ray_stride <= kMaxRayStride, "n_rays must be > 0 and 6 <= ray_stride <= 16");
   BN_CHECK_ARG((bounds == nullptr) == (bounds_scratch == nullptr), "bounds and bounds_scratch go together");
@@ -240,7 +251,8 @@ int bn_dsm_points(const float* rays, int ray_stride, const float* depth, long lo
   BN_CHECK_ARG(blocks < (1ll << 31), "too many rays for one launch");
   const int vec_ok = ((uintptr_t)rays % 16 == 0) && ((uintptr_t)cloud % 16 == 0) && ((uintptr_t)points_f32 % 16 == 0);
   dsm_points_kernel<<<(unsigned)blocks, kPtsBlock, 0, stream>>>(rays, ray_stride, depth, n_rays, scene_range, center_x, center_y,
-                                                          center_z, cloud, points_f32, bounds_scratch, vec_ok);
+                                                          center_z, cloud, points_f32, bounds_scratch, vec_ok, cs == 0 ? 1 : 0,
+                                                          make_utm_params(cs == 0 ? utm_zone : 1));
   BN_LAUNCH_CHECK();
   if (bounds) {
     dsm_bounds_kernel<<<1, 32, 0, stream>>>(bounds_scratch, bounds);

@@ -20,6 +20,7 @@
 // maximum + conditional atomicMax), rays_from_rpc_kernel then iterates every pixel exactly that often.
 // Compiled with -fmad=false so that the float64 arithmetic matches the oracle's operation for operation (libm aside).
 #include "common.cuh"
+#include "geodesy.cuh"
 
 #include <math.h>
 
@@ -37,8 +38,7 @@ struct RaysArgs {
   long long n; int width;
   double min_alt, max_alt;
   int cs;                                      // 0 ecef, 1 utm
-  double utm_lon0_deg, utm_A, utm_e;           // central meridian, k0 * rectifying radius, eccentricity
-  double alpha[6];                             // Krueger series coefficients
+  UtmParams utm;
   int normalize; float cx, cy, cz, range;
   int with_sun; float sx, sy, sz;
   float* out; int out_stride;
@@ -101,36 +101,6 @@ __device__ bool rpc_localize(const RpcDev& r, double col, double row, double alt
   return ok;
 }
 
-constexpr double kPi = 3.141592653589793;
-
-__device__ void to_ecef(double lat, double lon, double alt, double& x, double& y, double& z) {   // sat_utils.py:110-125
-  const double rad_lat = lat * (kPi / 180.0), rad_lon = lon * (kPi / 180.0);
-  const double a = 6378137.0, finv = 298.257223563, f = 1 / finv, e2 = 1 - (1 - f) * (1 - f);
-  const double sl = sin(rad_lat), cl = cos(rad_lat);
-  const double v = a / sqrt(1 - e2 * sl * sl);
-  x = (v + alt) * cl * cos(rad_lon);
-  y = (v + alt) * cl * sin(rad_lon);
-  z = (v * (1 - e2) + alt) * sl;
-}
-
-__device__ void to_utm(const RaysArgs& a, double lat, double lon, double& east, double& north) {
-  const double phi = lat * (kPi / 180.0), lam = (lon - a.utm_lon0_deg) * (kPi / 180.0);
-  const double tau = tan(phi);
-  const double sigma = sinh(a.utm_e * atanh(a.utm_e * tau / sqrt(1 + tau * tau)));
-  const double taup = tau * sqrt(1 + sigma * sigma) - sigma * sqrt(1 + tau * tau);
-  const double cl = cos(lam);
-  const double xip = atan2(taup, cl);
-  const double etap = asinh(sin(lam) / sqrt(taup * taup + cl * cl));
-  double xi = xip, eta = etap;
-#pragma unroll
-  for (int j = 1; j <= 6; ++j) {
-    xi = xi + a.alpha[j - 1] * sin(2 * j * xip) * cosh(2 * j * etap);
-    eta = eta + a.alpha[j - 1] * cos(2 * j * xip) * sinh(2 * j * etap);
-  }
-  east = 500000.0 + a.utm_A * eta;
-  north = a.utm_A * xi;
-}
-
 constexpr int kRaysBlock = 128;
 
 __device__ __forceinline__ void pixel_of(const RaysArgs& a, long long p, double& col, double& row) {
@@ -178,9 +148,9 @@ __global__ void __launch_bounds__(kRaysBlock) rays_from_rpc_kernel(const __grid_
     int n_unused;
     pixel_of(a, p, col, row);
     rpc_localize(a.rpc, col, row, a.max_alt, it_max, lon, lat, n_unused);  // nearest to the camera: maximum altitude
-    if (a.cs == 0) to_ecef(lat, lon, a.max_alt, nx, ny, nz); else { to_utm(a, lat, lon, nx, ny); nz = a.max_alt; }
+    if (a.cs == 0) to_ecef(lat, lon, a.max_alt, nx, ny, nz); else { to_utm(a.utm, lat, lon, nx, ny); nz = a.max_alt; }
     rpc_localize(a.rpc, col, row, a.min_alt, it_min, lon, lat, n_unused);
-    if (a.cs == 0) to_ecef(lat, lon, a.min_alt, fx, fy, fz); else { to_utm(a, lat, lon, fx, fy); fz = a.min_alt; }
+    if (a.cs == 0) to_ecef(lat, lon, a.min_alt, fx, fy, fz); else { to_utm(a.utm, lat, lon, fx, fy); fz = a.min_alt; }
     const double dx = fx - nx, dy = fy - ny, dz = fz - nz;
     const double len = sqrt((dx * dx + dy * dy) + dz * dz);
     float o0 = (float)nx, o1 = (float)ny, o2 = (float)nz, near = 0.f, far = (float)len;
@@ -218,19 +188,7 @@ int bn_rays_from_rpc(const bn_rpc* rpc, const double* cols, const double* rows, 
   RaysArgs a;
   memcpy(&a.rpc, rpc, sizeof(RpcDev));
   a.cols = cols; a.rows = rows; a.n = n_rays; a.width = width; a.min_alt = min_alt; a.max_alt = max_alt; a.cs = cs;
-  {                                                                       // GRS80 transverse Mercator constants
-    const double f = 1.0 / 298.257222101, n = f / (2 - f);
-    const double n2 = n * n, n3 = n2 * n, n4 = n3 * n, n5 = n4 * n, n6 = n5 * n;
-    a.utm_e = sqrt(f * (2 - f));
-    a.utm_A = 0.9996 * (6378137.0 / (1 + n) * (1 + n2 / 4 + n4 / 64 + n6 / 256));
-    a.utm_lon0_deg = (double)((utm_zone - 1) * 6 - 180 + 3);
-    a.alpha[0] = n / 2 - 2 * n2 / 3 + 5 * n3 / 16 + 41 * n4 / 180 - 127 * n5 / 288 + 7891 * n6 / 37800;
-    a.alpha[1] = 13 * n2 / 48 - 3 * n3 / 5 + 557 * n4 / 1440 + 281 * n5 / 630 - 1983433 * n6 / 1935360;
-    a.alpha[2] = 61 * n3 / 240 - 103 * n4 / 140 + 15061 * n5 / 26880 + 167603 * n6 / 181440;
-    a.alpha[3] = 49561 * n4 / 161280 - 179 * n5 / 168 + 6601661 * n6 / 7257600;
-    a.alpha[4] = 34729 * n5 / 80640 - 3418889 * n6 / 1995840;
-    a.alpha[5] = 212378941 * n6 / 319334400;
-  }
+  a.utm = make_utm_params(cs == 1 ? utm_zone : 1);
   a.normalize = normalize; a.cx = center_x; a.cy = center_y; a.cz = center_z; a.range = scene_range;
   a.with_sun = sun_dir != nullptr;
   a.sx = sun_dir ? sun_dir[0] : 0.f; a.sy = sun_dir ? sun_dir[1] : 0.f; a.sz = sun_dir ? sun_dir[2] : 0.f;

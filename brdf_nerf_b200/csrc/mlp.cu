@@ -855,7 +855,8 @@ static int backward_t(bn_mlp* h, const float* params, const float* out, const fl
   constexpr bool kTC = std::is_same<T, __nv_bfloat16>::value;   // bias grads fused into the tcgen05 dgrad epilogues
   // every weight gradient only shares its inputs with the data-gradient chain: in tcgen05 mode they run on the handle's
   // side stream (forked from `s` by an event each time their input is ready, joined back before returning)
-  const bool overlap = kTC && h->s2 != nullptr && h->overlap;
+  // per-launch profiling (bench.py roofline leg) times each kernel alone: no concurrent weight-gradient stream then
+  const bool overlap = kTC && h->s2 != nullptr && h->overlap && !prof_enabled();
   int n_fork = 0;
   auto fork = [&]() -> cudaStream_t {             // the side stream, ordered after everything enqueued on s so far
     if (!overlap) return s;

@@ -12,8 +12,10 @@ meaning.  Inputs and outputs are CUDA tensors: the depth of a 2048x2048 tile nev
 moves rays and depth to the CPU, builds the cloud in numpy and rasterises it single-threaded in C).  Kernels:
 `csrc/dsm.cu` through the C ABI (`bn_dsm_*`); there is no CPU path.
 
-Not mirrored: `cs == 'ecef'` (needs pyproj's UTM projection, sat_utils.py:148-162, an absent third-party package; the
-reference default is 'utm', opt.py:252) and the GeoTIFF write (`dsm_path`, rasterio) — file I/O is out of scope.
+`cs == 'ecef'` (geocentric scene coordinates) is supported for the point cloud: ecef_to_latlon_custom (sat_utils.py:127-146)
+followed by the UTM projection of sat_utils.py:148-162 (pyproj in the reference, restated in csrc/geodesy.cuh).  Not mirrored:
+the GeoTIFF write (`dsm_path`, rasterio; file I/O is out of scope) and `get_dsm_from_nerf_prediction` with cs='ecef', a
+reference defect path (it projects the already projected coordinates a second time).
 """
 from __future__ import annotations
 
@@ -72,6 +74,8 @@ def accumulate_cloud(cloud: torch.Tensor, grid: DsmGrid, radius: int = 1, sigma:
     cloud = cloud.contiguous()
     nbytes = lib.bn_dsm_workspace_bytes(grid.xsize, grid.ysize, radius, sigma)
     fresh = workspace is None
+    if cloud.shape[0] == 0:           # an empty shard contributes nothing
+        return torch.zeros(nbytes, dtype=torch.uint8, device=cloud.device) if fresh else workspace
     if fresh:
         workspace = torch.empty(nbytes, dtype=torch.uint8, device=cloud.device)
     L.check(lib.bn_dsm_accumulate(L.ptr(cloud, torch.float64), cloud.shape[1], value_col, cloud.shape[0], grid.xoff, grid.yoff,
@@ -148,9 +152,6 @@ class DsmGeoref:
         self.cs = cs
 
     def _points(self, rays: torch.Tensor, depth: torch.Tensor, want_f32: bool, want_bounds: bool):
-        if self.cs != "utm":
-            raise NotImplementedError("cs='ecef' needs pyproj's UTM projection (sat_utils.py:148-162), a third-party "
-                                      "package that is not part of the path; the reference default is cs='utm' (opt.py:252)")
         if not rays.is_cuda:
             raise L.BnError("brdf_nerf_b200.dsm needs CUDA tensors (there is no CPU path)")
         rays = rays.contiguous()
@@ -159,14 +160,43 @@ class DsmGeoref:
         if depth.shape[0] != n:
             raise ValueError(f"rays ({n}) and depth ({depth.shape[0]}) disagree")
         dev = rays.device
+        if n == 0:                    # an empty ray shard: no points, neutral bounds for the MAX all-reduce
+            inf = float("inf")
+            return (torch.empty(0, 3, dtype=torch.float64, device=dev),
+                    torch.empty(0, 3, dtype=torch.float32, device=dev) if want_f32 else None,
+                    torch.tensor([inf, -inf, inf, -inf], dtype=torch.float64, device=dev) if want_bounds else None)
         cloud = torch.empty(n, 3, dtype=torch.float64, device=dev)
         pts = torch.empty(n, 3, dtype=torch.float32, device=dev) if want_f32 else None
         bounds = torch.empty(4, dtype=torch.float64, device=dev) if want_bounds else None
         scratch = torch.empty(4, dtype=torch.int64, device=dev) if want_bounds else None
+        zone = self._first_point_zone(rays, depth) if self.cs == "ecef" else 0
         L.check(L.load().bn_dsm_points(L.ptr(rays), rays.shape[1], L.ptr(depth), n, self.range, *self.center,
-                                       L.ptr(cloud, torch.float64), L.ptr(pts), L.ptr(bounds, torch.float64),
+                                       1 if self.cs == "utm" else 0, zone, L.ptr(cloud, torch.float64), L.ptr(pts), L.ptr(bounds, torch.float64),
                                        L.ptr(scratch, torch.int64), L.stream_ptr()))
         return cloud, pts, bounds
+
+    def _first_point_zone(self, rays: torch.Tensor, depth: torch.Tensor) -> int:
+        """cs == 'ecef': the reference projects with the UTM zone of the FIRST point (`utm.latlon_to_zone_number(lats[0],
+        lons[0])`, sat_utils.py:155).  One 28-byte read-back, then ecef_to_latlon_custom (sat_utils.py:127-146) in host floats."""
+        from .georays import utm_zone_number
+        r0 = rays[0, :6].to(torch.float64).cpu().tolist()
+        d0 = float(depth[0].to(torch.float64).cpu())
+        x, y, z = ((r0[k] + r0[3 + k] * d0) * self.range + self.center[k] for k in range(3))
+        a, e = 6378137.0, 8.1819190842622e-2
+        b = math.sqrt(a * a * (1 - e * e))
+        ep = math.sqrt((a * a - b * b) / (b * b))
+        p = math.sqrt(x * x + y * y)
+        th = math.atan2(a * z, b * p)
+        lon = math.atan2(y, x)
+        lat = math.atan2(z + ep * ep * b * math.sin(th) ** 3, p - e * e * a * math.cos(th) ** 3)
+        return utm_zone_number(math.degrees(lat), math.degrees(lon))
+
+    def _dsm_cs_check(self):
+        if self.cs != "utm":
+            raise NotImplementedError(
+                "get_dsm_from_nerf_prediction with cs='ecef' is a reference defect path: it feeds the (east, north) that "
+                "get_latlonalt_from_nerf_prediction returns into utm_from_latlon a second time as if they were (lat, lon) "
+                "(satellite_rgb_dep.py:649-651).  Use get_latlonalt_from_nerf_prediction + rasterize_cloud, or cs='utm'.")
 
     def get_latlonalt_from_nerf_prediction(self, rays: torch.Tensor, depth: torch.Tensor, bPrint: bool = False
                                            ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
@@ -181,6 +211,7 @@ class DsmGeoref:
         profile, satellite_rgb_dep.py:694: Affine(res, 0, xoff, 0, -res, yoff))."""
         if dsm_path is not None:
             raise NotImplementedError("writing the GeoTIFF (rasterio) is outside the hot path: save the returned tensor")
+        self._dsm_cs_check()
         if roi_txt is not None:
             roi = np.loadtxt(roi_txt) if isinstance(roi_txt, (str, bytes)) else np.asarray(roi_txt, dtype=np.float64)
             cloud, _, _ = self._points(rays, depth, False, False)
@@ -201,6 +232,7 @@ class DsmGeoref:
         all-reduced bounds, each rank accumulates its points, the accumulators are summed over NCCL (two all-reduces:
         float64 sums, float32 counts), and every rank finalises the full raster.  The depth image is never gathered."""
         import torch.distributed as dist
+        self._dsm_cs_check()
         if roi_txt is not None:
             roi = np.loadtxt(roi_txt) if isinstance(roi_txt, (str, bytes)) else np.asarray(roi_txt, dtype=np.float64)
             cloud, _, _ = self._points(rays, depth, False, False)

@@ -4,6 +4,7 @@ ray-sharded tile rendering.
   extract_model_state_dict / load_ckpt   reference eval.py:26-54 (Lightning checkpoints: keys `nerf_coarse.<param>`)
   warm_start                             reference main.py:96-104 (stage-2 BRDF training starts from the stage-1 trunk)
   batched_inference                      reference eval.py:56-76 (render_rays over chunks of `args.chunk` rays, concatenated)
+  render_tile_to_dsm                     render_tile -> depth -> DSM without gathering the depth image (eval.py:153-182)
   tile_shards / render_tile              ray-sharded full-tile inference: every rank renders whole chunks, no collective
                                          on the data path; an optional all_gather assembles the image
 
@@ -110,3 +111,20 @@ def render_tile(models, rays, args, rank=0, world_size=1, keys: Optional[Iterabl
         torch.distributed.all_gather(parts, v, group=group)
         full[k] = torch.cat(parts, 0)
     return full, brdf_type
+
+
+@torch.no_grad()
+def render_tile_to_dsm(models, rays, args, georef, rank=0, world_size=1, group=None, roi_txt=None, **kw):
+    """The evaluation product of a tile (reference eval.py:153-182: render -> depth -> get_dsm_from_nerf_prediction) with
+    the rays sharded over ranks: each rank renders its run of chunks (`render_tile`, no gather), turns ITS depths into
+    points and accumulators (`brdf_nerf_b200.dsm`), and the ranks all-reduce the raster bounds and the accumulators — a few
+    MB instead of the tile's depth image.  Returns (dsm (ysize, xsize, 1) float32 on every rank, DsmGrid, this rank's result
+    dict).  `georef` is a `dsm.DsmGeoref`."""
+    res, _ = render_tile(models, rays, args, rank=rank, world_size=world_size, gather=False, **kw)
+    lo, hi = tile_shards(rays.shape[0], int(args.chunk), world_size)[rank]
+    depth = res["depth_coarse"] if hi > lo else rays.new_zeros(0)
+    if world_size == 1:
+        dsm, grid = georef.get_dsm_from_nerf_prediction(rays[lo:hi], depth, roi_txt=roi_txt, return_grid=True)
+    else:
+        dsm, grid = georef.get_dsm_from_nerf_prediction_sharded(rays[lo:hi], depth, group=group, roi_txt=roi_txt, return_grid=True)
+    return dsm, grid, res

@@ -312,17 +312,19 @@ int bn_adam_step_graph(float* params, const float* grads, float* exp_avg, float*
 
 /* ------------------------------------------------------------------ tile inference -> DSM */
 
-/* get_latlonalt_from_nerf_prediction with cs == 'utm' (datasets/satellite_rgb_dep.py:601-634; callers eval.py:170,
- * main.py:621): point = ((double)o + (double)d * (double)depth) * scene_range + center, every operation rounded separately
- * in float64 — bit-exact against the reference's torch/numpy result.  rays: n_rays records of ray_stride floats
+/* get_latlonalt_from_nerf_prediction (datasets/satellite_rgb_dep.py:601-634; callers eval.py:170, main.py:621):
+ * point = ((double)o + (double)d * (double)depth) * scene_range + center, every operation rounded separately in float64 —
+ * bit-exact against the reference's torch/numpy result.  cs = 1 ('utm', the reference default): the point is
+ * (east, north, alt).  cs = 0 ('ecef'): the point is geocentric and goes through ecef_to_latlon_custom (sat_utils.py:127-146)
+ * and the UTM projection of zone utm_zone (sat_utils.py:148-162: the zone of the FIRST point, which the caller supplies).  rays: n_rays records of ray_stride floats
  * [o(3), d(3), ...] (6 <= ray_stride <= 16); depth (n_rays); scene_range / center_*: the dataset's float32 `range` /
  * `center` values (satellite_rgb_dep.py:164-165) widened to double.  cloud (n_rays,3) float64 [east, north, alt];
  * points_f32 (n_rays,3) nullable: the same points rounded to float32 (the `pts3d` operand of calc_normal_from_depth_v2,
  * satellite_rgb_dep.py:578-585); bounds nullable: 4 doubles [xmin, xmax, ymin, ymax] of the finite points (the operands
  * of the grid derivation :666-671) with bounds_scratch = 4 uint64 of device scratch (both or neither). */
 int bn_dsm_points(const float* rays, int ray_stride, const float* depth, long long n_rays, double scene_range,
-                  double center_x, double center_y, double center_z, double* cloud, float* points_f32, double* bounds,
-                  unsigned long long* bounds_scratch, cudaStream_t stream);
+                  double center_x, double center_y, double center_z, int cs, int utm_zone, double* cloud, float* points_f32,
+                  double* bounds, unsigned long long* bounds_scratch, cudaStream_t stream);
 
 /* Host-only query: bytes of device workspace bn_dsm_rasterize needs for this raster. */
 size_t bn_dsm_workspace_bytes(int xsize, int ysize, int radius, float sigma);

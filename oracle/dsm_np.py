@@ -30,8 +30,29 @@ _OUT_DIR = os.path.join(_HERE, "_build")
 _SO = os.path.join(_OUT_DIR, "libplyflatten_restated.so")
 
 
-def latlonalt_from_nerf_prediction(rays, depth, scene_range, center):
-    """satellite_rgb_dep.py:614-634 with cs == 'utm'.  rays (N,11) float32, depth (N,) float32; `scene_range` and
+def ecef_to_latlon_custom(x, y, z):
+    """sat_utils.py:127-146 (pinned bit-exact against the live reference)."""
+    a = 6378137.0
+    e = 8.1819190842622e-2
+    asq = a ** 2
+    esq = e ** 2
+    b = np.sqrt(asq * (1 - esq))
+    bsq = b ** 2
+    ep = np.sqrt((asq - bsq) / bsq)
+    p = np.sqrt((x ** 2) + (y ** 2))
+    th = np.arctan2(a * z, b * p)
+    lon = np.arctan2(y, x)
+    lat = np.arctan2((z + (ep ** 2) * b * (np.sin(th) ** 3)), (p - esq * a * (np.cos(th) ** 3)))
+    N = a / (np.sqrt(1 - esq * (np.sin(lat) ** 2)))
+    alt = p / np.cos(lat) - N
+    lon = lon * 180 / np.pi
+    lat = lat * 180 / np.pi
+    return lat, lon, alt
+
+
+def latlonalt_from_nerf_prediction(rays, depth, scene_range, center, cs="utm"):
+    """satellite_rgb_dep.py:614-634.  cs == 'utm' (default): pinned.  cs == 'ecef': ecef_to_latlon_custom (pinned) followed by
+    sat_utils.utm_from_latlon (pyproj: restated in oracle/georays_np.py, unpinned).  rays (N,11) float32, depth (N,) float32; `scene_range` and
     `center` are the dataset's float32 values (`self.range` 0-dim float32 tensor :165, `self.center` float32 (3,) :164).
     Returns easts, norths, alts as float64 vectors."""
     rays = np.asarray(rays, dtype=np.float32).astype(np.float64)          # :614  rays.double()
@@ -42,6 +63,11 @@ def latlonalt_from_nerf_prediction(rays, depth, scene_range, center):
     xyz[:, 0] += c[0]                                                      # :623-625
     xyz[:, 1] += c[1]
     xyz[:, 2] += c[2]
+    if cs == "ecef":                                                       # :629-631
+        from oracle.georays_np import utm_from_latlon
+        lats, lons, alts = ecef_to_latlon_custom(xyz[:, 0], xyz[:, 1], xyz[:, 2])
+        easts, norths = utm_from_latlon(lats, lons)
+        return easts, norths, alts
     return xyz[:, 0].copy(), xyz[:, 1].copy(), xyz[:, 2].copy()            # :632-633 (cs == 'utm')
 
 

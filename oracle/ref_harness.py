@@ -180,3 +180,9 @@ def ref_latlon_to_ecef(lat, lon, alt):
     load_dataset_module()
     import sat_utils as ref_sat_utils
     return ref_sat_utils.latlon_to_ecef_custom(lat, lon, alt)
+
+
+def ref_ecef_to_latlon(x, y, z):
+    load_dataset_module()
+    import sat_utils as ref_sat_utils
+    return ref_sat_utils.ecef_to_latlon_custom(x, y, z)

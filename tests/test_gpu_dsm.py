@@ -159,3 +159,51 @@ def test_full_tile_2048_properties_and_full_size_oracle(cuda):
     assert np.array_equal(cnt.cpu().numpy(), wc)
     got = dsm.cpu().numpy()
     assert np.array_equal(np.isnan(got), np.isnan(want)) and np.nanmax(np.abs(got - want)) <= RASTER_TOL
+
+
+def test_render_tile_to_dsm_end_to_end(cuda):
+    """render_tile -> depth -> DSM through the real renderer (random-init weights): the DSM of the rendered depths equals the
+    oracle's DSM of the same depths; an empty ray shard contributes neutral bounds and zero accumulators."""
+    from brdf_nerf_b200.config import named_config
+    from brdf_nerf_b200.inference import render_tile_to_dsm
+    from brdf_nerf_b200.models import load_model
+    args = named_config("lambertian", chunk=1024)
+    h, w = 40, 48
+    rays = make_tile_rays(h, w, view=0).to(cuda)
+    torch.manual_seed(0)
+    models = {"coarse": load_model(args, precision="bf16").to(cuda)}
+    geo = PD.DsmGeoref(10.0, SCENE_CENTER)
+    torch.manual_seed(5)
+    dsm, grid, res = render_tile_to_dsm(models, rays, args, geo)
+    depth = res["depth_coarse"]
+    assert depth.shape == (h * w,) and dsm.shape == (grid.ysize, grid.xsize, 1)
+    want, og = D.dsm_from_nerf_prediction(rays.cpu().numpy(), depth.cpu().numpy(), 10.0, SCENE_CENTER)
+    assert (grid.xoff, grid.yoff, grid.resolution, grid.xsize, grid.ysize) == og
+    got = dsm.cpu().numpy()
+    assert np.array_equal(np.isnan(got), np.isnan(want)) and np.nanmax(np.abs(got - want)) <= RASTER_TOL
+    # empty shard
+    cloud, pts, bounds = geo._points(rays[:0], depth[:0], True, True)
+    assert cloud.shape == (0, 3) and pts.shape == (0, 3) and bounds.tolist() == [math.inf, -math.inf, math.inf, -math.inf]
+    ws = PD.accumulate_cloud(cloud, grid)
+    assert not ws.any()
+    full_ws = PD.accumulate_cloud(geo._points(rays, depth, False, False)[0], grid)
+    before = full_ws.clone()
+    assert PD.accumulate_cloud(cloud, grid, workspace=full_ws) is full_ws and torch.equal(before, full_ws)
+
+
+def test_cloud_ecef_scene_vs_oracle(cuda):
+    """cs == 'ecef': geocentric scene coordinates -> ecef_to_latlon_custom -> UTM of the first point's zone.  CUDA libm vs
+    numpy differ in the last bits of the trigonometry: float64 results within 1e-6 m (measured ~1e-9)."""
+    from oracle import georays_np as G
+    n = 3000
+    gen = torch.Generator().manual_seed(4)
+    rays = torch.rand(n, 11, generator=gen) * 2 - 1
+    depth = torch.rand(n, generator=gen)
+    cx, cy, cz = (float(v) for v in G.latlon_to_ecef_custom(np.float64(30.31), np.float64(-81.66), np.float64(20.0)))
+    geo = PD.DsmGeoref(300.0, (cx, cy, cz), cs="ecef")
+    e, no, a = geo.get_latlonalt_from_nerf_prediction(rays.to(cuda), depth.to(cuda))
+    we, wn, wa = D.latlonalt_from_nerf_prediction(rays.numpy(), depth.numpy(), 300.0, (cx, cy, cz), cs="ecef")
+    assert geo._first_point_zone(rays.to(cuda), depth.to(cuda)) == 17
+    assert np.abs(e.cpu().numpy() - we).max() < 1e-6 and np.abs(no.cpu().numpy() - wn).max() < 1e-6
+    assert np.abs(a.cpu().numpy() - wa).max() < 1e-6
+    assert 4.3e5 < we.mean() < 4.4e5 and 3.35e6 < wn.mean() < 3.36e6          # Jacksonville, UTM 17N

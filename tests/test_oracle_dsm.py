@@ -2,6 +2,7 @@
 (tests/golden/dsm_tile.npz: live-reference point cloud and normals), the C restatement of the rasteriser against its
 pure-Python twin, the host-side grid logic of the product, the scatter/box-filter factorisation the CUDA kernels rely on,
 the two-rank accumulator all-reduce rule (gloo), and argument validation through the C ABI (no GPU needed)."""
+import ctypes
 import math
 import os
 import socket
@@ -167,7 +168,7 @@ def test_dsm_abi_argument_validation():
     """Through the C ABI without a GPU: bad arguments are refused before any CUDA call."""
     from brdf_nerf_b200 import _lib
     lib = _lib.load()
-    assert lib.bn_dsm_points(None, 11, None, 10, 1.0, 0.0, 0.0, 0.0, None, None, None, None, None) == -1
+    assert lib.bn_dsm_points(None, 11, None, 10, 1.0, 0.0, 0.0, 0.0, 1, 0, None, None, None, None, None) == -1
     assert b"null pointer" in lib.bn_last_error()
     assert lib.bn_dsm_workspace_bytes(100, 50, 1, float("inf")) == 102 * 52 * 12
     assert lib.bn_dsm_workspace_bytes(100, 50, 1, 0.5) == 100 * 50 * 12
@@ -176,5 +177,8 @@ def test_dsm_abi_argument_validation():
     assert lib.bn_dsm_normals_from_points(None, 4, 4, None, None) == -1
     with pytest.raises(_lib.BnError):
         PD.DsmGeoref(1.0, (0, 0, 0)).get_latlonalt_from_nerf_prediction(torch.zeros(4, 11), torch.zeros(4))
-    with pytest.raises(NotImplementedError):
-        PD.DsmGeoref(1.0, (0, 0, 0), cs="ecef").get_latlonalt_from_nerf_prediction(torch.zeros(4, 11), torch.zeros(4))
+    dummy = ctypes.c_void_p(256)                                          # never dereferenced: validation fails first
+    assert lib.bn_dsm_points(dummy, 11, dummy, 10, 1.0, 0.0, 0.0, 0.0, 2, 0, dummy, None, None, None, None) == -1
+    assert lib.bn_dsm_points(dummy, 11, dummy, 10, 1.0, 0.0, 0.0, 0.0, 0, 0, dummy, None, None, None, None) == -1   # ecef needs a zone
+    with pytest.raises(NotImplementedError, match="defect"):
+        PD.DsmGeoref(1.0, (0, 0, 0), cs="ecef").get_dsm_from_nerf_prediction(torch.zeros(4, 11), torch.zeros(4))

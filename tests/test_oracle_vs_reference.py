@@ -145,3 +145,17 @@ def test_georays_pinned_parts_vs_reference():
     lat, lon, alt = rng.uniform(-80, 80, 100), rng.uniform(-180, 180, 100), rng.uniform(-100, 9000, 100)
     for a, b in zip(RH.ref_latlon_to_ecef(lat, lon, alt), G.latlon_to_ecef_custom(lat, lon, alt)):
         assert np.array_equal(a, b)
+
+
+def test_dsm_ecef_to_latlon_vs_reference():
+    """cs='ecef' leg of get_latlonalt_from_nerf_prediction: ecef_to_latlon_custom (sat_utils.py:127-146) bit-exact."""
+    import numpy as np
+    from oracle import dsm_np as D
+    from oracle import georays_np as G
+    rng = np.random.default_rng(8)
+    lat, lon, alt = rng.uniform(-85, 85, 500), rng.uniform(-180, 180, 500), rng.uniform(-100, 5000, 500)
+    x, y, z = G.latlon_to_ecef_custom(lat, lon, alt)
+    for a, b in zip(RH.ref_ecef_to_latlon(x, y, z), D.ecef_to_latlon_custom(x, y, z)):
+        assert np.array_equal(a, b)
+    la, lo, al = D.ecef_to_latlon_custom(x, y, z)
+    assert np.abs(la - lat).max() < 1e-7 and np.abs(lo - lon).max() < 1e-9 and np.abs(al - alt).max() < 1e-2     # Bowring, one step
