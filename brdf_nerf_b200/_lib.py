@@ -60,6 +60,7 @@ _SIGS = {
     "bn_brdf_points_backward": (C.c_int, [C.POINTER(ShadeCfg), _P, _P, _P, _I, _I, _P]),
     "bn_loss_color_depth": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _F, _F, _I, _P, _P, _P, _I, _I, _P]),
     "bn_loss_regularizers": (C.c_int, [_P, _P, _P, _P, _I, _I, _F, _I, _F, _P, _F, _P, _P, _P, _P, _P, _I, _I, _P]),
+    "bn_count_nan": (C.c_int, [_P, C.c_longlong, _P, _P]),
     "bn_mlp_create": (C.c_int, [C.POINTER(MlpCfg), C.POINTER(_P)]),
     "bn_mlp_destroy": (None, [_P]),
     "bn_mlp_sync_weights": (C.c_int, [_P, _P, _P]),

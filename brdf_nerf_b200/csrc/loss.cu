@@ -69,6 +69,23 @@ __global__ void __launch_bounds__(128) loss_kernel(LossArgs a) {
   if (threadIdx.x == 0) atomicAdd(a.loss, (part[0] + part[1]) + (part[2] + part[3]));
 }
 
+// Device-side NaN counter ("Errors"): the reference's train_utils.check_nan (train_utils.py:61-78) counts NaNs
+// with torch.isnan(x).sum() and a host round trip per tensor (three per render_rays call, rendering.py:121-123).  Here the
+// count is accumulated into a caller buffer with no synchronisation; the caller reads it when (and if) it wants to report.
+__global__ void __launch_bounds__(256) count_nan_kernel(const float* __restrict__ x, long long n, int* __restrict__ counter) {
+  int c = 0;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long n4 = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) ? n / 4 : 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = ld_stream4(x + 4 * i);
+    c += (v.x != v.x) + (v.y != v.y) + (v.z != v.z) + (v.w != v.w);
+  }
+  for (long long i = 4 * n4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) c += x[i] != x[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(kFull, c, o);
+  if ((threadIdx.x & 31) == 0 && c != 0) atomicAdd(counter, c);
+}
+
 }  // namespace bn
 
 using namespace bn;
@@ -181,6 +198,16 @@ int bn_loss_regularizers(const float* weights, const float* z, const float* dept
   a.loss = loss; a.g_weights = g_weights; a.g_packed = nr ? g_packed : nullptr; a.g_depth = g_depth; a.bad_count = bad_count;
   a.N = n_rays; a.S = n_samples;
   reg_loss_kernel<<<ceil_div(n_rays, 4), 128, 0, stream>>>(a);
+  BN_LAUNCH_CHECK();
+  return BN_OK;
+}
+
+extern "C" __attribute__((visibility("default")))
+int bn_count_nan(const float* x, long long n, int* counter, cudaStream_t stream) {
+  BN_CHECK_ARG(x && counter, "null pointer");
+  BN_CHECK_ARG(n > 0, "n must be > 0");
+  const long long blocks = ceil_div_ll(ceil_div_ll(n, 4), 256);
+  count_nan_kernel<<<(unsigned)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, stream>>>(x, n, counter);
   BN_LAUNCH_CHECK();
   return BN_OK;
 }

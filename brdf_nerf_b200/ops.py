@@ -49,6 +49,19 @@ def sample_guided(z1, depth, weights, t_vals, gauss_w, u_pred, near0, far0, d_ra
     return (z2, std) if want_std else z2
 
 
+def count_nan(tensors, counters=None):
+    """Accumulates the NaN count of each tensor into one slot of an int32 device buffer (allocated zeroed when None) without
+    synchronising: the device-side stand-in for train_utils.check_nan's torch.isnan(x).sum() (train_utils.py:61-78)."""
+    tensors = list(tensors)
+    if counters is None:
+        counters = torch.zeros(len(tensors), dtype=torch.int32, device=tensors[0].device)
+    for i, t in enumerate(tensors):
+        t = t.contiguous()
+        if t.numel():
+            L.check(L.load().bn_count_nan(L.ptr(t), t.numel(), C.c_void_p(counters.data_ptr() + 4 * i), L.stream_ptr()))
+    return counters
+
+
 def merge_samples(z1, z2):
     n, s1 = z1.shape
     g = z2.shape[1]

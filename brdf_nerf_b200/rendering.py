@@ -87,7 +87,7 @@ def _call_brdf_type(model, args, apply_brdf: bool) -> int:
 
 def _forward(model, args, rays: torch.Tensor, draws: Optional[Draws], mode: str, valid_depth, target_depths,
              target_std, apply_brdf: bool, bTestNormal: bool, bTestSun_v: bool, gsam_only: bool, apply_theta: bool,
-             cos_irra_on: bool, train: bool):
+             cos_irra_on: bool, train: bool, debug_nan: bool = False):
     if args.model != "spsbrdf-nerf":
         raise NotImplementedError("only --model spsbrdf-nerf is implemented (BASELINE north star)")
     if args.n_importance > 0:
@@ -168,7 +168,11 @@ def _forward(model, args, rays: torch.Tensor, draws: Optional[Draws], mode: str,
         gt_std = target_std.to(device=dev, dtype=torch.float32).contiguous()
     z2 = ops.sample_guided(z1, depth1, w1, t_g, gauss_g, draws.u_pred, rays[0:1, 6], rays[0:1, 7], d_range,
                            valid_depth=vd, gt_depth=gt_depth, gt_depth_stride=gt_stride, gt_std=gt_std,
-                           u_gt=draws.u_gt if use_gt else None)
+                           u_gt=draws.u_gt if use_gt else None, want_std=debug_nan)
+    nan_counts = None
+    if debug_nan:       # check_nan(pred_depth / pred_weight / sampling_std) of rendering.py:121-123, counted on the device
+        z2, std1 = z2
+        nan_counts = (ops.count_nan([depth1, w1, std1]), (depth1.numel(), w1.numel(), std1.numel()))
     if gsam_only:
         z, idx, z_unsort = z2, None, z2
     else:
@@ -248,7 +252,7 @@ def _forward(model, args, rays: torch.Tensor, draws: Optional[Draws], mode: str,
                 normal_an=nr_an)
     outs = dict(rgb=sh["rgb"], depth=depth, weights=w, packed=packed, alpha=alpha, trans=trans, z=z,
                 z_unsort=z_unsort, idx=idx, shade=sh, sun_res=sun_res, aux_pts=aux_pts, C=C, nr_an=nr_an, nr_lr=nr_lr,
-                brdf_type=brdf_type, extras=dict(z1=z1, z2=z2, sigma1=sigma1, weights1=w1, depth1=depth1))
+                brdf_type=brdf_type, extras=dict(z1=z1, z2=z2, sigma1=sigma1, weights1=w1, depth1=depth1, nan_counts=nan_counts))
     return outs, st
 
 
@@ -395,8 +399,9 @@ def render_rays(models, args, rays, ts, mode="test", valid_depth=None, target_de
         outs = _RenderFunction._last
         _RenderFunction._last = None
     else:
-        outs, _ = _forward(model, args, rays, _draws, train=False, **kw)
+        outs, _ = _forward(model, args, rays, _draws, train=False, debug_nan=bool(print_debuginfo), **kw)
         rgb, depth, weights, packed = outs["rgb"], outs["depth"], outs["weights"], outs["packed"]
+        _report_nans(outs["extras"].get("nan_counts"))
     outs["irr_mode"] = _irr_mode_of(outs, model, cos_irra_on)
     res = _assemble(model, args, rays.float(), outs, rgb, depth, weights, packed, bool(apply_brdf), bool(apply_theta))
     if rows is not None and cols is not None:
@@ -408,6 +413,16 @@ def render_rays(models, args, rays, ts, mode="test", valid_depth=None, target_de
     if _return_extras:
         return result, names[outs["brdf_type"]], outs["extras"]
     return result, names[outs["brdf_type"]]
+
+
+def _report_nans(nan_counts):
+    """`print_debuginfo=True`: the lines train_utils.check_nan prints for pred_depth / pred_weight / sampling_std
+    (rendering.py:121-123) — one read-back of three device counters instead of three isnan().sum() round trips."""
+    if nan_counts is None:
+        return
+    counts, totals = nan_counts
+    for name, c, t in zip(("pred_depth", "pred_weight", "sampling_std"), counts.cpu().tolist(), totals):
+        print("----nan nb in {}, val_in: {:.0f} / {:.0f}".format(name, c, t))
 
 
 def _irr_mode_of(outs, model, cos_irra_on):

@@ -194,6 +194,11 @@ int bn_loss_regularizers(const float* weights, const float* z, const float* dept
                          const float* rays, float lambda_hs, float* loss, float* g_weights, float* g_packed,
                          float* g_depth, float* bad_count, int n_rays, int n_samples, cudaStream_t stream);
 
+/* Device-side NaN counter: *counter (DEVICE int, ACCUMULATED: zero it first) += number of NaNs in x[0..n).  Stands in for
+ * the host-synchronising torch.isnan(x).sum() of train_utils.check_nan (train_utils.py:61-78; three calls per render_rays,
+ * rendering.py:121-123): nothing here synchronises, the caller reads the counters when it wants to report. */
+int bn_count_nan(const float* x, long long n, int* counter, cudaStream_t stream);
+
 /* ------------------------------------------------------------------ K-B  PE + SIREN MLP */
 
 enum { BN_PREC_FP32 = 0,   /* CUDA-core fp32 everywhere: parity mode (<= 1e-3 against the fp32 oracle) */

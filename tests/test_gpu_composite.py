@@ -67,3 +67,20 @@ def test_composite_forward_backward(cuda, n, s, c, noise_std, with_irr):
     err = (gp.cpu() - ref).abs().max().item()
     scale = ref.abs().max().item()
     assert err <= 2e-5 * max(1.0, scale), f"composite backward max err {err} (scale {scale})"
+
+
+@pytest.mark.parametrize("n", [1, 3, 4, 1023, 4096 * 33 + 5])
+def test_device_nan_counter(cuda, n):
+    """bn_count_nan == torch.isnan(x).sum() (train_utils.check_nan, train_utils.py:61-78), accumulated without a host sync;
+    ragged sizes, unaligned views, infinities do not count."""
+    from brdf_nerf_b200 import ops
+    g = torch.Generator().manual_seed(n)
+    x = torch.randn(n + 1, generator=g)
+    x[torch.rand(n + 1, generator=g) < 0.1] = float("nan")
+    x[torch.rand(n + 1, generator=g) < 0.05] = float("inf")
+    xd = x.to(cuda)
+    a, b = xd[:n], xd[1:]                                     # b is 4-byte aligned only
+    counters = ops.count_nan([a, b, a])
+    assert counters.tolist() == [int(torch.isnan(x[:n]).sum()), int(torch.isnan(x[1:]).sum()), int(torch.isnan(x[:n]).sum())]
+    ops.count_nan([a], counters)                              # accumulates into slot 0
+    assert counters[0].item() == 2 * int(torch.isnan(x[:n]).sum())

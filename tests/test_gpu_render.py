@@ -275,3 +275,16 @@ def test_batched_inference_and_tile_shards(cuda):
         part, _ = render_tile(models, rays, args, rank=r, world_size=world, keys=("rgb_coarse", "depth_coarse"), **kw)
         assert set(part) == {"rgb_coarse", "depth_coarse"}
         assert torch.equal(part["rgb_coarse"], full["rgb_coarse"][lo:hi]) and torch.equal(part["depth_coarse"], full["depth_coarse"][lo:hi])
+
+
+def test_print_debuginfo_reports_nan_counts(cuda, capsys):
+    """print_debuginfo=True: the reference's check_nan lines (rendering.py:121-123) from device-side counters."""
+    args = named_config("lambertian")
+    rays = make_rays(64).rays.to(cuda)
+    torch.manual_seed(0)
+    model = load_model(args, precision="fp32").to(cuda)
+    with torch.no_grad():
+        render_rays({"coarse": model}, args, rays, None, print_debuginfo=True)
+    out = capsys.readouterr().out
+    assert "----nan nb in pred_depth, val_in: 0 / 64" in out and "----nan nb in pred_weight, val_in: 0 / 4096" in out
+    assert "----nan nb in sampling_std, val_in: 0 / 64" in out
