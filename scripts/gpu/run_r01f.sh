@@ -2,7 +2,7 @@
 # Round-1 (session f) GPU pass: every GPU test file in its own process, the e2e feed experiment, the DSM micro-benchmark,
 # smoke(), the default bench line and the reference arm.  Outputs under gpurun_out/.
 mkdir -p gpurun_out
-bash run_gpu_tests.sh tests/test_gpu_dsm.py tests/test_gpu_train.py tests/test_gpu_sampler.py tests/test_gpu_composite.py \
+bash scripts/gpu/run_gpu_tests.sh tests/test_gpu_dsm.py tests/test_gpu_train.py tests/test_gpu_sampler.py tests/test_gpu_composite.py \
      tests/test_gpu_gemm.py tests/test_gpu_mlp.py tests/test_gpu_render.py
 echo "tests rc=$?"
 timeout 300 python scripts/exp_e2e.py 60 > gpurun_out/exp_e2e.log 2>&1; echo "exp_e2e rc=$?"; tail -3 gpurun_out/exp_e2e.log
