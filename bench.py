@@ -148,6 +148,42 @@ def cpu_reference_rate(args, rays_per_step, steps, warmup, seed=0):
     return rays_per_step / (ms / 1e3), ms, torch.get_num_threads()
 
 
+def tile_products_leg(cpu=True):
+    """The callers either side of the hot path at BASELINE config 5 size, one 2048 x 2048 tile: RPC camera ->
+    ray records and rendered depth -> DSM, per-kernel time and algorithmic GB/s (scripts/bench_georays.py, bench_dsm.py),
+    with the reference's CPU path (oracle port: numpy + the C restatement of plyflatten, one thread like the reference)
+    timed beside them on a bounded sample.  Never fails the bench line: an error is reported as a string."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        import bench_dsm
+        import bench_georays
+        out = {"dsm": bench_dsm.run(2048, 2048), "georays": bench_georays.run(2048, 2048)}
+        if cpu:
+            import numpy as np
+            from brdf_nerf_b200.synth import SCENE_CENTER, SCENE_RANGE, make_tile_rays, tile_surface_depth
+            from oracle import dsm_np as D
+            from oracle import georays_np as G
+            h = w = 1024                                           # a quarter tile: ~0.2 s of CPU work
+            rays = make_tile_rays(h, w, view=0)
+            depth = tile_surface_depth(rays)
+            t0 = time.perf_counter()
+            D.dsm_from_nerf_prediction(rays.numpy(), depth.numpy(), SCENE_RANGE * w / 2048, SCENE_CENTER)
+            dt = time.perf_counter() - t0
+            out["dsm"]["cpu_baseline"] = {"value": h * w / dt / 1e6, "unit": "Mrays/s", "cores": 1, "kind": "port",
+                                          "sample": "1024 x 1024 tile: numpy float64 cloud + grid + C restatement of plyflatten"}
+            n = 200_000
+            idx = np.arange(0, 2048 * 2048, (2048 * 2048) // n)[:n]
+            o = G.synthetic_rpc(0)
+            t0 = time.perf_counter()
+            G.get_rays((idx % 2048).astype(np.float64), (idx // 2048).astype(np.float64), o, -25.0, 95.0, cs="utm")
+            dt = time.perf_counter() - t0
+            out["georays"]["cpu_baseline"] = {"value": n / dt / 1e6, "unit": "Mrays/s", "cores": 1, "kind": "port",
+                                              "sample": f"{n} strided pixels of the 2048 x 2048 image, numpy float64 restatement of rpcm + get_rays"}
+        return out
+    except Exception as e:                                          # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {e}"}
+
+
 def run_reference(opts):
     rank, _, world = _dist_env()
     if rank != 0:
@@ -339,6 +375,7 @@ def run_ours(opts):
                         "h2d_bytes_per_step": int(host_batch.flat.numel()), "d2h_bytes_per_step": 4},
                 "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "roofline_composite": roof_hbm,
                 "cpu_baseline": cpu,
+                "tile_products": tile_products_leg(cpu=not opts.no_cpu_baseline) if (world == 1 and not opts.no_tile_products) else None,
                 "loss": float(loss_host)}
         print(json.dumps(line))
     if world > 1:
@@ -357,6 +394,7 @@ def main():
                     help="e2e leg: host batches through Trainer.prefetch() on a copy stream, or copied on the compute stream")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-composite", action="store_true", help="skip the compositing (HBM) roofline leg")
+    ap.add_argument("--no-tile-products", action="store_true", help="skip the ray-feed / DSM leg (SURVEY 8f-3/4 kernels)")
     opts = ap.parse_args()
     if opts.impl == "reference":
         run_reference(opts)

@@ -162,3 +162,20 @@ def tile_surface_depth(rays: torch.Tensor) -> torch.Tensor:
 # ground sampling distance of ~0.3 m spans 2 * 307.2 m; UTM-sized offsets so that float32 / float64 effects are realistic
 SCENE_RANGE = 307.2
 SCENE_CENTER = (368123.4, 3459876.5, 35.2)
+
+
+def synthetic_rpc_dict(view: int = 0) -> dict:
+    """A well-conditioned RPC00B camera model ("rpcm" dict layout, as in the scene JSON files) of a 2048 x 2048 pushbroom image
+    over Jacksonville-like coordinates (the DFC2019 area the reference trains on): near-affine numerators with small second /
+    third order terms, denominators close to 1.  Polynomial variables: x = lat (index 2), y = lon (index 1), z = alt (index 3)."""
+    tilt = (0.06, -0.11, 0.17)[view % 3]
+    num_c, den_c, num_r, den_r = [0.0] * 20, [0.0] * 20, [0.0] * 20, [0.0] * 20
+    num_c[0], num_c[1], num_c[2], num_c[3] = 0.002, 1.01, 0.015, tilt
+    num_c[4], num_c[7], num_c[8], num_c[5], num_c[11] = 3e-3, -1.5e-3, 8e-4, 2e-3, 4e-4
+    den_c[0], den_c[1], den_c[2], den_c[3], den_c[8] = 1.0, 1.2e-3, -8e-4, 5e-4, 2e-4
+    num_r[0], num_r[1], num_r[2], num_r[3] = -0.003, 0.02, -0.99, 0.5 * tilt + 0.04
+    num_r[4], num_r[7], num_r[8], num_r[6], num_r[15] = -2e-3, 9e-4, 1.1e-3, -1.5e-3, -3e-4
+    den_r[0], den_r[1], den_r[2], den_r[3], den_r[7] = 1.0, -9e-4, 1.1e-3, -4e-4, 1.5e-4
+    return dict(row_offset=1023.5, col_offset=1023.5, lat_offset=30.3105, lon_offset=-81.6632, alt_offset=5.0,
+                row_scale=1024.0, col_scale=1024.0, lat_scale=0.0031, lon_scale=0.0036, alt_scale=120.0,
+                row_num=num_r, row_den=den_r, col_num=num_c, col_den=den_c)

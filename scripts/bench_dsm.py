@@ -1,12 +1,11 @@
 """Tile inference -> DSM micro-benchmark on one B200 (BASELINE config 5 size: 2048 x 2048 rays):
-per-kernel time and algorithmic GB/s of bn_dsm_points / bn_dsm_rasterize / bn_dsm_normals_from_points, the end-to-end
-depth -> DSM call (including its one 32-byte host round trip), and the reference's CPU path beside it (numpy float64 cloud
-+ the C restatement of plyflatten, single-threaded like the reference's).
+per-kernel time and algorithmic GB/s of bn_dsm_points / bn_dsm_rasterize / bn_dsm_normals_from_points and the end-to-end
+depth -> DSM call (including its one 32-byte host round trip).  The reference's CPU path is timed beside it by bench.py
+(`tile_products` leg), the only place outside tests/ that may execute the oracle.
     python scripts/bench_dsm.py [H W]       prints one JSON line"""
 import json
 import os
 import sys
-import time
 
 import numpy as np
 import torch
@@ -35,7 +34,7 @@ def timeit(fn, iters=20):
     return e0.elapsed_time(e1) / iters * 1e3
 
 
-def run(h=2048, w=2048, cpu=True):
+def run(h=2048, w=2048):
     dev = torch.device("cuda:0")
     n = h * w
     rays = make_tile_rays(h, w, view=0)
@@ -61,18 +60,6 @@ def run(h=2048, w=2048, cpu=True):
         out[name] = {"us": us, "GB/s": nbytes / us / 1e3, "frac_of_hbm_peak": nbytes / us / 1e3 / peak, "bytes": nbytes}
     us = timeit(lambda: geo.get_dsm_from_nerf_prediction(rd, dd), iters=10)
     out["depth -> DSM end to end (incl. 32 B host round trip)"] = {"us": us, "Mrays/s": n / us}
-    if cpu:
-        from oracle import dsm_np as D
-        t0 = time.perf_counter()
-        e, no, a = D.latlonalt_from_nerf_prediction(rays.numpy(), depth.numpy(), SCENE_RANGE, SCENE_CENTER)
-        cl = np.vstack([e, no, a]).T
-        og = D.dsm_grid(e, no, 0.5)
-        t1 = time.perf_counter()
-        D.plyflatten(cl, *og)
-        t2 = time.perf_counter()
-        out["cpu_baseline"] = {"kind": "port", "cores": 1, "cloud_ms": (t1 - t0) * 1e3, "rasterise_ms": (t2 - t1) * 1e3,
-                               "Mrays/s": n / ((t2 - t0) * 1e6),
-                               "sample": "whole tile: numpy float64 cloud + grid, C restatement of plyflatten (single thread, as the reference)"}
     return out
 
 

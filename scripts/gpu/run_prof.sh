@@ -2,7 +2,7 @@
 # ncu launch list of one training step (graph replay), then ONE --set full capture of the dominant kernels:
 # the fused trunk forward (train_chain_kernel), one trunk dgrad and one trunk wgrad GEMM.
 mkdir -p gpurun_out
-CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-composite"
+CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-composite --no-tile-products"
 $CMD > gpurun_out/plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 420 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu1.log 2>&1
 tail -2 gpurun_out/ncu1.log | cut -c1-300

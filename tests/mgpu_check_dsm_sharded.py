@@ -1,7 +1,8 @@
-"""Ray-sharded tile -> DSM over NCCL: every rank owns a contiguous pixel block of the tile, builds its
+"""Multi-GPU check (test infrastructure; not collected by pytest, which the driver runs on one GPU).
+Ray-sharded tile -> DSM over NCCL: every rank owns a contiguous pixel block of the tile, builds its
 part of the cloud, and the ranks all-reduce the raster bounds and the (sum, count) accumulators; every rank ends with the
 full raster.  Rank 0 checks it against the unsharded GPU result and the CPU oracle and prints one JSON line.
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 scripts/check_dsm_sharded.py [H W]"""
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tests/mgpu_check_dsm_sharded.py [H W]"""
 import json
 import os
 import sys
