@@ -41,19 +41,20 @@ def resident():
         tr.step(static)
 
 
-def inline(h2d=True, d2h=True):
+def inline(h2d=True, d2h=True, lag=1):
+    """lag = how many steps the host runs ahead of the loss it waits for"""
     def body():
-        evs, prev = [None] * 4, None
+        evs = [None] * 8
+        pin8 = torch.empty(8).pin_memory()
         for i in range(steps):
             loss = tr.step(host if h2d else static)
             if d2h:
-                pin[i % 4:i % 4 + 1].copy_(loss.reshape(1), non_blocking=True)
-            evs[i % 4] = torch.cuda.Event()
-            evs[i % 4].record()
-            if prev is not None:
-                evs[prev].synchronize()
-            prev = i % 4
-        evs[prev].synchronize()
+                pin8[i % 8:i % 8 + 1].copy_(loss.reshape(1), non_blocking=True)
+            evs[i % 8] = torch.cuda.Event()
+            evs[i % 8].record()
+            if i >= lag:
+                evs[(i - lag) % 8].synchronize()
+        evs[(steps - 1) % 8].synchronize()
     return body
 
 
@@ -74,4 +75,5 @@ def prefetch():
 for rep in range(2):
     print(f"rep {rep}: resident {timed(resident):.4f} ms | inline h2d+d2h {timed(inline()):.4f} | prefetch feed {timed(prefetch):.4f} | "
           f"inline h2d only {timed(inline(True, False)):.4f} | inline d2h only {timed(inline(False, True)):.4f} | "
-          f"event-sync only {timed(inline(False, False)):.4f}", flush=True)
+          f"event-sync only {timed(inline(False, False)):.4f} | inline lag 2 {timed(inline(lag=2)):.4f} | inline lag 4 {timed(inline(lag=4)):.4f} | "
+          f"resident again {timed(resident):.4f}", flush=True)
