@@ -128,6 +128,63 @@ class Trainer:
             return loss
         return self._graph_step(batch, kw)
 
+    # ---- checkpoint / resume (reference: Lightning ModelCheckpoint + resume_from_checkpoint, main.py:709-723).  The layout
+    # is the Lightning checkpoint's: "state_dict" with the module under its LightningModule attribute name
+    # (`nerf_coarse.<param>`, the prefix eval.py:26-54 / main.py:97-104 cut), "optimizer_states" = [torch.optim.Adam
+    # state_dict] over the parameters in registration order (main.py:147-150), "global_step".  A checkpoint written by the
+    # reference therefore resumes here and vice versa.
+    CKPT_PREFIX = "nerf_coarse"
+
+    def _param_slices(self):
+        flat = self.model.flat_params
+        out = []
+        for name, p in self.model.named_parameters():
+            off = (p.data_ptr() - flat.data_ptr()) // flat.element_size()
+            out.append((name, p, int(off), p.numel()))
+        return out
+
+    def state_dict(self) -> dict:
+        slices = self._param_slices()
+        state = {}
+        if self.step_count > 0:                            # torch.optim.Adam creates its state lazily, at the first step
+            for i, (_, p, off, n) in enumerate(slices):
+                state[i] = {"step": torch.tensor(float(self.step_count)),
+                            "exp_avg": self.m[off:off + n].view_as(p).detach().clone(),
+                            "exp_avg_sq": self.v[off:off + n].view_as(p).detach().clone()}
+        group = {"lr": self.lr, "betas": (0.9, 0.999), "eps": 1e-8, "weight_decay": 0, "amsgrad": False,
+                 "params": list(range(len(slices)))}
+        return {"state_dict": {f"{self.CKPT_PREFIX}.{k}": v.detach().clone() for k, v in self.model.state_dict().items()},
+                "optimizer_states": [{"state": state, "param_groups": [group]}], "global_step": self.step_count}
+
+    def load_state_dict(self, ckpt: dict, load_model: bool = True, strict: bool = True):
+        """Resume from `state_dict()` or from a Lightning checkpoint of the reference (`torch.load(path)`)."""
+        if load_model:
+            prefix = self.CKPT_PREFIX + "."
+            sd = {k[len(prefix):]: v for k, v in ckpt["state_dict"].items() if k.startswith(prefix)}
+            self.model.load_state_dict(sd, strict=strict)   # copies in place: parameters stay views of the flat buffer
+        opt = ckpt["optimizer_states"][0]
+        slices = self._param_slices()
+        ids = opt["param_groups"][0]["params"]
+        if len(ids) != len(slices):
+            raise ValueError(f"optimizer state covers {len(ids)} parameters, the model has {len(slices)}")
+        self.m.zero_()
+        self.v.zero_()
+        step = 0
+        for pid, (name, p, off, n) in zip(ids, slices):
+            st = opt["state"].get(pid)
+            if st is None:
+                continue
+            if tuple(st["exp_avg"].shape) != tuple(p.shape):
+                raise ValueError(f"optimizer state of {name}: shape {tuple(st['exp_avg'].shape)} != {tuple(p.shape)}")
+            self.m[off:off + n].copy_(st["exp_avg"].reshape(-1))
+            self.v[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+            step = max(step, int(float(st["step"])))
+        self.lr = float(opt["param_groups"][0]["lr"])
+        self.step_count = step
+        self.model._synced_version = -1                    # packed bf16 copies are stale
+        # the graph-captured Adam keeps lr / step on the device: step() refreshes them when they differ from the host's
+        self._dev_lr, self._dev_step = None, -1
+
     # ---- host feed: the H2D copy of step k+1's batch and the D2H read of step k's loss run on a copy stream, so the compute
     # stream sees kernels only (no copy-engine hop between two graph replays).  Event order, per staging buffer b:
     #   copy stream:    wait free[b] -> H2D host batch -> record ready[b]
@@ -267,6 +324,28 @@ class TrainLoop:
         self.schedule = Schedule(args, dataset_len=pool.rays.shape[0], world_size=world_size)
         if float(args.noise_std) != 0.0 and use_graph:
             raise ValueError("noise_std decays every step (main.py:246): run with use_graph=False when it is non-zero")
+
+    def state_dict(self) -> dict:
+        """Trainer checkpoint + the loop's own position: schedule step, noise level, ray-pool epoch / cursor / generator."""
+        sd = self.trainer.state_dict()
+        feed = self.feed
+        sd["loop"] = {"train_steps": self.schedule.train_steps, "noise_std": self.schedule.noise_std, "epoch": feed.epoch,
+                      "pos": feed._pos, "perm": None if feed._perm is None else feed._perm.clone(),
+                      "generator": feed.gen.get_state()}
+        sd["epoch"] = self.schedule.epoch()
+        return sd
+
+    def load_state_dict(self, ckpt: dict, load_model: bool = True):
+        self.trainer.load_state_dict(ckpt, load_model=load_model)
+        loop = ckpt.get("loop")
+        if loop is not None:
+            self.schedule.train_steps, self.schedule.noise_std = int(loop["train_steps"]), float(loop["noise_std"])
+            feed = self.feed
+            feed.epoch, feed._pos = int(loop["epoch"]), int(loop["pos"])
+            feed._perm = None if loop["perm"] is None else loop["perm"].to(feed.pool.rays.device)
+            feed.gen.set_state(loop["generator"])
+        else:                                              # a reference checkpoint: only the global step is known
+            self.schedule.train_steps = int(ckpt.get("global_step", self.trainer.step_count)) * self.schedule.world
 
     def step(self):
         f = self.schedule.next()

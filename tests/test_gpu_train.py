@@ -299,3 +299,62 @@ def test_prefetch_feed_delivers_batches_and_losses(cuda, use_graph):
         assert torch.equal(seen[i][0].cpu(), hosts[i % 3].rays) and torch.equal(seen[i][1].cpu(), hosts[i % 3].rgbs)
         assert pin[i].item() == direct[i].item() and math.isfinite(pin[i].item())
     assert tr.step_count == 8
+
+
+def test_checkpoint_resume_continues_training(cuda):
+    """Trainer.state_dict() / load_state_dict(): 3 steps + checkpoint + 2 steps == restore into a fresh model + the same 2
+    steps (injected draws; fp32-atomic ordering in the weight gradients allows 1e-6), in eager and in graph mode the device-
+    side optimizer state follows the restored step counter."""
+    args = named_config("lambertian_ds")
+    n = 128
+    batch = make_rays(n, depth_supervision=True).to(cuda)
+    S1, G = args.n_samples, args.guided_samples
+
+    def draws(i):
+        od = RT.Draws.make(n, S1, G, S1 + G, seed=50 + i, with_gt=True)
+        return Draws(u_strat=od.u_strat, u_pred=od.u_pred, u_gt=od.u_gt)
+
+    torch.manual_seed(0)
+    m1 = load_model(args, precision="fp32").to(cuda)
+    t1 = Trainer(m1, args)
+    for i in range(3):
+        t1.step(batch, draws=draws(i))
+    ckpt = t1.state_dict()
+    for i in range(3, 5):
+        t1.step(batch, draws=draws(i))
+    torch.manual_seed(9)                                               # different init: everything must come from the checkpoint
+    m2 = load_model(args, precision="fp32").to(cuda)
+    t2 = Trainer(m2, args)
+    t2.load_state_dict(ckpt)
+    assert t2.step_count == 3
+    for i in range(3, 5):
+        t2.step(batch, draws=draws(i))
+    assert t2.step_count == 5
+    assert (m1.flat_params - m2.flat_params).abs().max().item() <= 1e-6
+    assert (t1.m - t2.m).abs().max().item() <= 1e-6 and (t1.v - t2.v).abs().max().item() <= 1e-7
+    # graph mode: the captured Adam reads lr / step from device memory, refreshed after a restore
+    m3 = load_model(args, precision="bf16").to(cuda)
+    t3 = Trainer(m3, args, use_graph=True)
+    t3.step(batch)
+    t3.load_state_dict(ckpt)
+    t3.step(batch)
+    assert t3.step_count == 4 and t3._opt_state[1].item() == 4.0 and abs(t3._opt_state[0].item() - t3.lr) < 1e-10
+
+
+def test_train_loop_checkpoint_restores_schedule_and_feed(cuda):
+    from brdf_nerf_b200.train import TrainLoop
+    args = named_config("lambertian_ds", batch_size=64, max_train_steps=100)
+    pool = make_rays(640, depth_supervision=True).to(cuda)
+    torch.manual_seed(0)
+    loop = TrainLoop(load_model(args, precision="bf16").to(cuda), args, pool, use_graph=False, seed=4)
+    for _ in range(12):                                                # crosses an epoch boundary (10 batches per epoch)
+        loop.step()
+    ckpt = loop.state_dict()
+    want = [loop.feed.next_batch().rays.clone() for _ in range(10)]   # the batches the original loop would see next
+    torch.manual_seed(1)
+    loop2 = TrainLoop(load_model(args, precision="bf16").to(cuda), args, pool, use_graph=False, seed=99)
+    loop2.load_state_dict(ckpt)
+    assert loop2.schedule.train_steps == 12 and loop2.trainer.step_count == 12 and loop2.feed.epoch == 1 and loop2.feed._pos == 128
+    got = [loop2.feed.next_batch().rays.clone() for _ in range(10)]
+    assert all(torch.equal(a, b) for a, b in zip(want, got))
+    assert ckpt["epoch"] == 1 and abs(loop2.schedule.next().lr - args.lr * 0.9) < 1e-12

@@ -157,3 +157,50 @@ def test_tile_shards_cover_the_tile_on_chunk_boundaries():
         assert all(a % chunk == 0 for a, _ in sh if a < n)
         counts = [-(-(b - a) // chunk) for a, b in sh]
         assert max(counts) - min(counts) <= 1
+
+
+def test_trainer_checkpoint_layout_is_a_lightning_adam_checkpoint():
+    """Trainer.state_dict(): "state_dict" under the `nerf_coarse.` prefix + a torch.optim.Adam state dict over the parameters
+    in registration order — torch's own Adam loads it, and a checkpoint built from torch's Adam resumes the Trainer (CPU:
+    only the host-side bookkeeping runs, no kernel)."""
+    import torch
+    from brdf_nerf_b200.config import named_config
+    from brdf_nerf_b200.models import load_model
+    from brdf_nerf_b200.train import Trainer
+    args = named_config("rpv111")
+    torch.manual_seed(0)
+    model = load_model(args)
+    tr = Trainer(model, args)
+    sd0 = tr.state_dict()
+    assert sd0["optimizer_states"][0]["state"] == {} and sd0["global_step"] == 0
+    assert set(sd0["state_dict"]) == {f"nerf_coarse.{k}" for k in model.state_dict()}
+    # pretend 7 steps were taken
+    g = torch.Generator().manual_seed(1)
+    tr.m.copy_(torch.randn(tr.m.shape, generator=g)); tr.v.copy_(torch.rand(tr.v.shape, generator=g)); tr.step_count = 7; tr.lr = 3e-4
+    sd = tr.state_dict()
+    params = list(model.parameters())
+    opt = torch.optim.Adam(params, lr=1.0)
+    opt.load_state_dict(sd["optimizer_states"][0])                     # torch accepts the layout
+    assert opt.param_groups[0]["lr"] == 3e-4 and len(opt.state) == len(params)
+    flat = model.flat_params
+    for p in params:
+        off = (p.data_ptr() - flat.data_ptr()) // 4
+        assert torch.equal(opt.state[p]["exp_avg"].reshape(-1), tr.m[off:off + p.numel()])
+        assert float(opt.state[p]["step"]) == 7.0
+    # and back: a checkpoint made of torch's Adam state resumes a fresh Trainer
+    torch.manual_seed(5)
+    model2 = load_model(args)
+    tr2 = Trainer(model2, args)
+    ckpt = {"state_dict": sd["state_dict"], "optimizer_states": [opt.state_dict()], "global_step": 7}
+    tr2.load_state_dict(ckpt)
+    assert tr2.step_count == 7 and tr2.lr == 3e-4
+    assert torch.equal(model2.flat_params, model.flat_params)
+    flat2 = model2.flat_params
+    for p, q in zip(params, model2.parameters()):                      # padding between tensors stays zero
+        o1, o2 = (p.data_ptr() - flat.data_ptr()) // 4, (q.data_ptr() - flat2.data_ptr()) // 4
+        assert o1 == o2 and torch.equal(tr2.m[o2:o2 + q.numel()], tr.m[o1:o1 + p.numel()])
+        assert torch.equal(tr2.v[o2:o2 + q.numel()], tr.v[o1:o1 + p.numel()])
+    import pytest
+    bad = {"state_dict": sd["state_dict"], "optimizer_states": [{"state": {}, "param_groups": [{"lr": 1e-3, "params": [0, 1]}]}]}
+    with pytest.raises(ValueError):
+        tr2.load_state_dict(bad)

@@ -159,3 +159,31 @@ def test_dsm_ecef_to_latlon_vs_reference():
         assert np.array_equal(a, b)
     la, lo, al = D.ecef_to_latlon_custom(x, y, z)
     assert np.abs(la - lat).max() < 1e-7 and np.abs(lo - lon).max() < 1e-9 and np.abs(al - alt).max() < 1e-2     # Bowring, one step
+
+
+def test_reference_checkpoint_resumes_the_trainer():
+    """A Lightning-style checkpoint of the LIVE reference module + torch.optim.Adam (main.py:147-150: Adam over
+    model.parameters() in registration order) loads into Trainer.load_state_dict: same parameter order, names and shapes."""
+    from brdf_nerf_b200.models import load_model
+    from brdf_nerf_b200.train import Trainer
+    args = named_config("rpv111")
+    ref = RH.build_model(args, seed=3)
+    opt = torch.optim.Adam([p for p in ref.parameters() if p.requires_grad], lr=5e-4, weight_decay=0)
+    g = torch.Generator().manual_seed(2)
+    for p in ref.parameters():
+        p.grad = torch.randn(p.shape, generator=g) * 1e-3
+    opt.step(); opt.step()
+    ckpt = {"state_dict": {f"nerf_coarse.{k}": v for k, v in ref.state_dict().items()}, "optimizer_states": [opt.state_dict()],
+            "global_step": 2, "epoch": 0}
+    torch.manual_seed(0)
+    model = load_model(args)
+    tr = Trainer(model, args)
+    tr.load_state_dict(ckpt)
+    assert tr.step_count == 2 and abs(tr.lr - 5e-4) < 1e-12
+    assert [k for k, _ in model.named_parameters()] == [k for k, _ in ref.named_parameters()]
+    flat = model.flat_params
+    for (name, p), q in zip(model.named_parameters(), ref.parameters()):
+        off = (p.data_ptr() - flat.data_ptr()) // 4
+        assert torch.equal(p.detach(), q.detach()), name
+        assert torch.equal(tr.m[off:off + p.numel()].view_as(p), opt.state[q]["exp_avg"]), name
+        assert torch.equal(tr.v[off:off + p.numel()].view_as(p), opt.state[q]["exp_avg_sq"]), name
