@@ -31,23 +31,21 @@ _SO = os.path.join(_OUT_DIR, "libplyflatten_restated.so")
 
 
 def ecef_to_latlon_custom(x, y, z):
-    """sat_utils.py:127-146 (pinned bit-exact against the live reference)."""
-    a = 6378137.0
-    e = 8.1819190842622e-2
-    asq = a ** 2
-    esq = e ** 2
-    b = np.sqrt(asq * (1 - esq))
-    bsq = b ** 2
-    ep = np.sqrt((asq - bsq) / bsq)
+    """Geocentric metres -> geodetic (lat deg, lon deg, alt m): one Bowring step, same operation order as
+    sat_utils.py:127-146 (pinned bit-exact against the live reference).  Note the constants: the eccentricity is given as a
+    literal, the semi-minor axis derived from it."""
+    a, ecc = 6378137.0, 8.1819190842622e-2
+    a2, ecc2 = a ** 2, ecc ** 2
+    b = np.sqrt(a2 * (1 - ecc2))
+    b2 = b ** 2
+    ecc_prime = np.sqrt((a2 - b2) / b2)
     p = np.sqrt((x ** 2) + (y ** 2))
-    th = np.arctan2(a * z, b * p)
+    theta = np.arctan2(a * z, b * p)
     lon = np.arctan2(y, x)
-    lat = np.arctan2((z + (ep ** 2) * b * (np.sin(th) ** 3)), (p - esq * a * (np.cos(th) ** 3)))
-    N = a / (np.sqrt(1 - esq * (np.sin(lat) ** 2)))
-    alt = p / np.cos(lat) - N
-    lon = lon * 180 / np.pi
-    lat = lat * 180 / np.pi
-    return lat, lon, alt
+    lat = np.arctan2((z + (ecc_prime ** 2) * b * (np.sin(theta) ** 3)), (p - ecc2 * a * (np.cos(theta) ** 3)))
+    prime_vertical = a / (np.sqrt(1 - ecc2 * (np.sin(lat) ** 2)))
+    alt = p / np.cos(lat) - prime_vertical
+    return lat * 180 / np.pi, lon * 180 / np.pi, alt
 
 
 def latlonalt_from_nerf_prediction(rays, depth, scene_range, center, cs="utm"):

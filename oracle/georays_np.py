@@ -142,19 +142,21 @@ def synthetic_rpc(view: int = 0) -> RPCModel:
 
 
 # ------------------------------------------------------------------------------------------ geodesy
+WGS84_A = 6378137.0
+WGS84_FINV = 298.257223563
+
+
 def latlon_to_ecef_custom(lat, lon, alt):
-    """sat_utils.py:110-125 (pinned)."""
-    rad_lat = lat * (np.pi / 180.0)
-    rad_lon = lon * (np.pi / 180.0)
-    a = 6378137.0
-    finv = 298.257223563
-    f = 1 / finv
-    e2 = 1 - (1 - f) * (1 - f)
-    v = a / np.sqrt(1 - e2 * np.sin(rad_lat) * np.sin(rad_lat))
-    x = (v + alt) * np.cos(rad_lat) * np.cos(rad_lon)
-    y = (v + alt) * np.cos(rad_lat) * np.sin(rad_lon)
-    z = (v * (1 - e2) + alt) * np.sin(rad_lat)
-    return x, y, z
+    """Geodetic degrees / metres -> geocentric metres, same operation order as sat_utils.py:110-125 (pinned bit-exact):
+    prime-vertical radius v = a / sqrt(1 - e2 sin^2 phi), then (v + h) cos phi cos lam, (v + h) cos phi sin lam,
+    (v (1 - e2) + h) sin phi with e2 = 1 - (1 - f)^2."""
+    phi, lam = lat * (np.pi / 180.0), lon * (np.pi / 180.0)
+    flattening = 1 / WGS84_FINV
+    ecc2 = 1 - (1 - flattening) * (1 - flattening)
+    sin_phi = np.sin(phi)
+    v = WGS84_A / np.sqrt(1 - ecc2 * sin_phi * sin_phi)
+    ring = (v + alt) * np.cos(phi)
+    return ring * np.cos(lam), ring * np.sin(lam), (v * (1 - ecc2) + alt) * sin_phi
 
 
 def utm_zone_number(latitude: float, longitude: float) -> int:
@@ -218,32 +220,27 @@ def utm_from_latlon(lats, lons):
 
 
 # ------------------------------------------------------------------------------------------ the path
+def _ground_points(cols, rows, rpc, alt, cs):
+    """All pixels localised on the altitude plane `alt`, in scene coordinates (satellite_rgb_dep.py:46-52 / 55-61)."""
+    alts = float(alt) * np.ones(cols.shape)
+    lons, lats = rpc.localization(cols, rows, alts)
+    if cs == "ecef":
+        return np.vstack(latlon_to_ecef_custom(lats, lons, alts)).T
+    east, north = utm_from_latlon(lats, lons)
+    return np.vstack([east, north, alts]).T
+
+
 def get_rays(cols, rows, rpc, min_alt, max_alt, cs="ecef"):
-    """satellite_rgb_dep.py:23-78: (N, 8) float32 [o(3), d(3), near = 0, far]."""
+    """satellite_rgb_dep.py:23-78: (N, 8) float32 [o(3), d(3), near = 0, far].  The points of maximum altitude are the ones
+    nearest to the camera (ray origins, :46-52, :64), those of minimum altitude the far ends (:55-61); d = unit(far - near)
+    (:67-68), bounds [0, |far - near|] (:72-73), everything cast to float32 at the end (:76-77)."""
     cols, rows = np.asarray(cols), np.asarray(rows)
-    min_alts = float(min_alt) * np.ones(cols.shape)                      # :43
-    max_alts = float(max_alt) * np.ones(cols.shape)                      # :44
-    lons, lats = rpc.localization(cols, rows, max_alts)                  # :46
-    if cs == "ecef":
-        x_near, y_near, z_near = latlon_to_ecef_custom(lats, lons, max_alts)       # :48
-    else:
-        x_near, y_near = utm_from_latlon(lats, lons)                     # :50
-        z_near = max_alts
-    xyz_near = np.vstack([x_near, y_near, z_near]).T
-    lons, lats = rpc.localization(cols, rows, min_alts)                  # :55
-    if cs == "ecef":
-        x_far, y_far, z_far = latlon_to_ecef_custom(lats, lons, min_alts)
-    else:
-        x_far, y_far = utm_from_latlon(lats, lons)
-        z_far = min_alts
-    xyz_far = np.vstack([x_far, y_far, z_far]).T
-    rays_o = xyz_near                                                    # :64
-    d = xyz_far - xyz_near                                               # :67
-    rays_d = d / np.linalg.norm(d, axis=1)[:, np.newaxis]                # :68
-    fars = np.linalg.norm(d, axis=1)                                     # :72
-    nears = float(0) * np.ones(fars.shape)                               # :73
-    rays = np.hstack([rays_o, rays_d, nears[:, np.newaxis], fars[:, np.newaxis]])
-    return rays.astype(np.float32)                                       # :77 .type(torch.FloatTensor)
+    near_pts = _ground_points(cols, rows, rpc, max_alt, cs)
+    far_pts = _ground_points(cols, rows, rpc, min_alt, cs)
+    delta = far_pts - near_pts
+    length = np.linalg.norm(delta, axis=1)
+    rays = np.hstack([near_pts, delta / length[:, np.newaxis], np.zeros((len(length), 1)), length[:, np.newaxis]])
+    return rays.astype(np.float32)
 
 
 def normalize_rays(rays, center, scene_range):
