@@ -217,7 +217,13 @@ struct Work {
   int m_tiles, n_tiles, splits;   // 128-row tiles, BN-column tiles; splits only for kNT
   int kb_total, kb_per_split;     // k-blocks (of kBK) in the reduction dimension
   int n_cols;                     // real number of output columns (a multiple of the epilogue unit)
+  int reverse;                    // TN only: walk the row tiles from the last to the first (see tile_reverse())
 };
+
+// Tile order of the NEXT tn launches on this thread (experiment knob).  Idea: in a chain of GEMMs in which each one consumes
+// the [P, F] tensor its predecessor has just written, let the consumer start with the rows the producer wrote last, which
+// should still be in the 126 MB L2 (a [131072, 512] bf16 tensor is 134 MB).  Measured on B200: slower (see mlp.cu), off by default.
+inline bool& tile_reverse() { static thread_local bool r = false; return r; }
 
 // Epilogue kinds.  An epilogue functor `Epi` declares `static constexpr int kMode`:
 //   EPI_DIRECT      : apply<32>(row, col0, acc[32]) writes global memory itself (debug / skinny paths)
@@ -298,6 +304,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int m_groups = (wk.m_tiles + CL - 1) / CL;                 // row tiles are handed out CL at a time
   const int n_items = m_groups * wk.n_tiles * wk.splits;
+  const int t_count = m_groups * wk.n_tiles;
+  // item -> (row group, column tile): every role (producer, MMA issuer, epilogue warps) maps through this one function
+  auto item_tile = [&](int it) {
+    const int t = it % t_count;
+    if (!kNT && wk.reverse) return (m_groups - 1 - t / wk.n_tiles) * wk.n_tiles + t % wk.n_tiles;
+    return t;
+  };
   const int crank = kPair ? (int)cluster_ctarank() : 0;
   const int item0 = kPair ? (int)cluster_id_x() : (int)blockIdx.x;
   const int item_step = kPair ? (int)cluster_nctaid_x() : (int)gridDim.x;
@@ -331,7 +344,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0; uint32_t phase = 0;
       for (int it = item0; it < n_items; it += item_step) {
         const int split = it / (m_groups * wk.n_tiles);
-        const int t = it % (m_groups * wk.n_tiles);
+        const int t = item_tile(it);
         const int m_blk = (t / wk.n_tiles) * CL + crank, n_blk = t % wk.n_tiles;
         const int ncol0 = n_blk * BN + crank * BNL;              // first B row / output column staged by this CTA
         const int kb0 = split * wk.kb_per_split;
@@ -384,7 +397,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int kb1 = min(wk.kb_total, kb0 + wk.kb_per_split);
         // the bias MMAs are dealt round-robin over the column tiles of a row block (K block kb goes to
         // column tile kb % n_tiles), so that no CTA carries all of the extra A-operand reads
-        [[maybe_unused]] const int n_blk = (it % (m_groups * wk.n_tiles)) % wk.n_tiles;
+        [[maybe_unused]] const int n_blk = item_tile(it) % wk.n_tiles;
         [[maybe_unused]] bool bias_on = false, bias_started = false;
         if constexpr (kBias) bias_on = epi.bias != nullptr;
         mbar_wait(&tempty[acc], acc_phase ^ 1);
@@ -444,7 +457,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     };
     if constexpr (Epi::kMode == EPI_DIRECT) {
       for (int it = item0; it < n_items; it += item_step) {
-        const int t = it % (m_groups * wk.n_tiles);
+        const int t = item_tile(it);
         const int m_blk = (t / wk.n_tiles) * CL + crank, n_blk = t % wk.n_tiles;
         mbar_wait(&tfull[acc], acc_phase);
         fence_after_sync();
@@ -466,7 +479,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t row_off = lane * 128, swz = (lane & 7) << 4;
       const bool leader = hsel == 0 && lane == 0;          // issues the quadrant's TMA traffic
       auto tile_of = [&](int it, int& m_blk, int& n_blk, int& n_units) {
-        const int t = it % (m_groups * wk.n_tiles);
+        const int t = item_tile(it);
         m_blk = (t / wk.n_tiles) * CL + crank; n_blk = t % wk.n_tiles;
         const int left = wk.n_cols - n_blk * BN;
         n_units = left >= BN ? BN / 64 : (left + 63) / 64;
@@ -539,7 +552,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t row_off = lane * 128, swz = (lane & 7) << 4;
       uint32_t g = 0;
       for (int it = item0; it < n_items; it += item_step) {
-        const int t = it % (m_groups * wk.n_tiles);
+        const int t = item_tile(it);
         const int m_blk = (t / wk.n_tiles) * CL + crank, n_blk = t % wk.n_tiles;
         const int left = wk.n_cols - n_blk * BN;
         const int n_units = left >= BN ? BN / 32 : (left + 31) / 32;
@@ -642,7 +655,7 @@ int launch_tn(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* B, lon
   if (K % kBK) { set_error("tc::launch_tn: K=%d not a multiple of 64", K); return BN_ERR_ARG; }
   if (Epi::kMode != EPI_DIRECT && N % 64) { set_error("tc::launch_tn: N=%d not a multiple of 64", N); return BN_ERR_ARG; }
   CUtensorMap ma, mb;
-  Work wk{(int)ceil_div_ll(M, kBM), ceil_div(N, BN), 1, K / kBK, K / kBK, N};
+  Work wk{(int)ceil_div_ll(M, kBM), ceil_div(N, BN), 1, K / kBK, K / kBK, N, tile_reverse() ? 1 : 0};
   if (int rc = make_map_bf16(&ma, A, M, K, lda, kBK, kBM)) return rc;
   if constexpr (BN >= 128) {
     if (wk.m_tiles >= 4) {               // CTA pairs: every CTA stages BN/2 rows of the B tile
@@ -669,6 +682,7 @@ int launch_nt(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* B, lon
   if (int rc = make_map_bf16(&ma, A, P, Mo, lda, 64, kBK)) return rc;
   if (int rc = make_map_bf16(&mb, B, P, No, ldb, 64, kBK)) return rc;
   Work wk;
+  wk.reverse = 0;
   wk.m_tiles = ceil_div(Mo, kBM); wk.n_tiles = ceil_div(No, BN);
   wk.kb_total = (int)ceil_div_ll(P, kBK);
   wk.n_cols = No;

@@ -951,9 +951,17 @@ static int backward_t(bn_mlp* h, const float* params, const float* out, const fl
     if (int rc = layer_wgrad<T>(h, w.GHD + (long long)b * h->HH, w.ldhd, w.FE, w.ldfe, h->HH, no, P, g + c.w_off[lin], kin, kin, no,
                                 kTC ? g + hp.b1_off[b] : nullptr, sw1)) return rc;
   }
+  // Every data-gradient GEMM from here down consumes the [P, *] tensor its predecessor has just written.  Alternating the row-
+  // tile direction (tc::tile_reverse()), so that each one starts with the rows that should still be in L2, was measured on
+  // B200 and LOST: 2.50 vs 2.43 ms per step, the dgrad GEMMs 0.91-0.98 vs 0.87 ms (profiles/r01f_zigzag_ab.txt) — descending
+  // row order costs the HBM streams more than the L2 hits return.  Kept as an opt-in knob (BN_TILE_ZIGZAG=1).
+  static const bool zigzag = kTC && getenv("BN_TILE_ZIGZAG") != nullptr;
   {
     DgradArgs<T> a;
-    if (int rc = layer_dgrad<T>(h, w.GHD, w.ldhd, (const T*)h->W1T, (long long)h->n_blocks * h->HH, P, F, HKa, a, w.GFE, F, s)) return rc;
+    tc::tile_reverse() = zigzag;                            // GHD was written first row tile first
+    const int rc = layer_dgrad<T>(h, w.GHD, w.ldhd, (const T*)h->W1T, (long long)h->n_blocks * h->HH, P, F, HKa, a, w.GFE, F, s);
+    tc::tile_reverse() = false;
+    if (rc) return rc;
   }
   // feature layer
   {
@@ -995,7 +1003,10 @@ static int backward_t(bn_mlp* h, const float* params, const float* out, const fl
       const T* BT = (const T*)h->WTp[l] + (l == h->skip ? (long long)kEncPad * F : 0);
       DgradArgs<T> a; a.mulc = w.C[l - 1]; a.ldm = F;
       if (normals) { a.add2 = w.U[l - 1]; a.ld2 = F; }
-      if (int rc = layer_dgrad<T>(h, cur, F, BT, F, P, F, F, a, buf[ni], F, s)) return rc;
+      tc::tile_reverse() = zigzag && ((L - 1 - l) % 2 == 0);   // the feature-layer dgrad wrote dZ_{L-1} first tile first
+      const int rc = layer_dgrad<T>(h, cur, F, BT, F, P, F, F, a, buf[ni], F, s);
+      tc::tile_reverse() = false;
+      if (rc) return rc;
       ci = ni;
     }
   }
