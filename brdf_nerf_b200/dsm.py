@@ -128,6 +128,18 @@ def reduce_bounds(bounds: torch.Tensor, group=None) -> torch.Tensor:
     return v * sign
 
 
+def valid_normal_mask(height: int, width: int, device, valid_depth: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """The `valid_normal` output of sat_utils.calc_normal_from_pts3d (sat_utils.py:19-24), flattened: ones without a mask;
+    with an (H, W) depth-validity image, a pixel below 1e-5 keeps its own value and an interior pixel becomes the product of
+    its four neighbours' validities.  Element-wise torch on the device (a few bytes per pixel of mask algebra)."""
+    if valid_depth is None:
+        return torch.ones(height * width, dtype=torch.float32, device=device)
+    vd = valid_depth.to(device).reshape(height, width)
+    out = torch.where(vd < 1e-5, vd, torch.ones_like(vd))
+    out[1:-1, 1:-1] = vd[2:, 1:-1] * vd[:-2, 1:-1] * vd[1:-1, 2:] * vd[1:-1, :-2]
+    return out.flatten()
+
+
 def normals_from_points(points: torch.Tensor) -> torch.Tensor:
     """sat_utils.calc_normal_from_pts3d(pts3d, valid_depth=None, Flatten=False)[0]: (H, W, 3) float32 -> (H, W, 3)."""
     if points.dim() != 3 or points.shape[-1] != 3:
@@ -250,10 +262,9 @@ class DsmGeoref:
 
     def calc_normal_from_depth_v2(self, rays: torch.Tensor, depth: torch.Tensor, height: int, width: int,
                                   valid_depth=None):
-        """-> (normals (h*w, 3) float32, valid_normal (h*w,) ones): satellite_rgb_dep.py:578-585 with valid_depth=None
-        (the only way the reference calls it: eval.py:434, main.py:477)."""
-        if valid_depth is not None:
-            raise NotImplementedError("valid_depth masks are never passed by the reference's callers")
+        """-> (normals (h*w, 3) float32, valid_normal (h*w,)): satellite_rgb_dep.py:578-585.  The reference's callers pass no
+        `valid_depth` (eval.py:434, main.py:477: the mask is all ones); with an (h, w) mask the validity image follows
+        sat_utils.py:19-24 (the normals themselves do not depend on it)."""
         _, pts, _ = self._points(rays, depth, True, False)
         normals = normals_from_points(pts.view(height, width, 3)).reshape(-1, 3)
-        return normals, torch.ones(height * width, dtype=torch.float32, device=rays.device)
+        return normals, valid_normal_mask(height, width, rays.device, valid_depth)

@@ -124,6 +124,24 @@ def utm_zone_number(latitude: float, longitude: float) -> int:
     return int((longitude + 180) / 6) + 1
 
 
+ZONE_LETTERS = "CDEFGHJKLMNPQRSTUVWXX"
+
+
+def utm_zone_letter(latitude: float):
+    """`utm.latitude_to_zone_letter` (utm==0.7.0): 8-degree bands C..X from 80 S to 84 N, None outside."""
+    if -80 <= latitude <= 84:
+        return ZONE_LETTERS[int(latitude + 80) >> 3]
+    return None
+
+
+def get_zone(cols, rows, rpc: RPCModel, min_alt):
+    """datasets/satellite_rgb_dep.py:80-85: UTM zone number and band letter of the image's first pixel at `min_alt` (what the
+    reference writes into the DSM GeoTIFF's CRS, satellite_rgb_dep.py:150,464,682)."""
+    c0, r0 = float(np.asarray(cols).reshape(-1)[0]), float(np.asarray(rows).reshape(-1)[0])
+    lon, lat = localize_one(rpc, c0, r0, float(min_alt))
+    return utm_zone_number(lat, lon), utm_zone_letter(lat)
+
+
 def _launch(rpc: RPCModel, cols, rows, n, width, min_alt, max_alt, cs, device, normalize, center, scene_range, sun_dir):
     if cs not in ("ecef", "utm"):
         raise ValueError(f"cs must be 'ecef' or 'utm', got {cs!r}")

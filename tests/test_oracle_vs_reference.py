@@ -187,3 +187,29 @@ def test_reference_checkpoint_resumes_the_trainer():
         assert torch.equal(p.detach(), q.detach()), name
         assert torch.equal(tr.m[off:off + p.numel()].view_as(p), opt.state[q]["exp_avg"]), name
         assert torch.equal(tr.v[off:off + p.numel()].view_as(p), opt.state[q]["exp_avg_sq"]), name
+
+
+def test_valid_normal_mask_and_zone_letter_vs_reference():
+    """Host-side pieces of the tile products against the live reference: the `valid_normal` image of
+    sat_utils.calc_normal_from_pts3d (sat_utils.py:19-24) and get_zone's band letter rule."""
+    from brdf_nerf_b200 import dsm as PD
+    from brdf_nerf_b200 import georays as PG
+    RH.load_dataset_module()
+    import sat_utils as ref_sat_utils
+    g = torch.Generator().manual_seed(6)
+    pts = torch.rand(9, 11, 3, generator=g)
+    vd = (torch.rand(9, 11, generator=g) > 0.3).float()
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        _, want = ref_sat_utils.calc_normal_from_pts3d(pts, vd, True)
+    assert torch.equal(PD.valid_normal_mask(9, 11, "cpu", vd), want)
+    assert torch.equal(PD.valid_normal_mask(9, 11, "cpu"), torch.ones(99))
+    # utm 0.7.0 letters: C..X in 8-degree bands, X extended to 84 N
+    for lat, letter in ((-80.0, "C"), (-72.1, "C"), (-72.0, "D"), (-0.1, "M"), (0.0, "N"), (30.3, "R"), (71.9, "W"), (72.0, "X"), (84.0, "X")):
+        assert PG.utm_zone_letter(lat) == letter
+    assert PG.utm_zone_letter(-80.1) is None and PG.utm_zone_letter(84.1) is None
+    from oracle import georays_np as G
+    o = G.synthetic_rpc(0)
+    rpc = PG.RPCModel.from_dict({k: getattr(o, k) for k in PG._KEYS + PG._POLYS})
+    assert PG.get_zone([0, 5], [0, 7], rpc, -25.0) == (17, "R")
