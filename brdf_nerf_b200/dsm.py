@@ -19,7 +19,6 @@ reference defect path (it projects the already projected coordinates a second ti
 """
 from __future__ import annotations
 
-import ctypes as C
 import math
 from dataclasses import dataclass
 from typing import Optional, Sequence, Tuple

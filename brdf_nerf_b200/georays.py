@@ -16,7 +16,6 @@ from __future__ import annotations
 
 import copy
 import ctypes as C
-import math
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence
 

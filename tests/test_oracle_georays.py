@@ -8,7 +8,6 @@ import os
 
 import numpy as np
 import pytest
-import torch
 
 from brdf_nerf_b200 import georays as PG
 from oracle import georays_np as G
