@@ -288,3 +288,42 @@ def test_print_debuginfo_reports_nan_counts(cuda, capsys):
     out = capsys.readouterr().out
     assert "----nan nb in pred_depth, val_in: 0 / 64" in out and "----nan nb in pred_weight, val_in: 0 / 4096" in out
     assert "----nan nb in sampling_std, val_in: 0 / 64" in out
+
+
+@pytest.mark.parametrize("cfg,over,kw", [
+    ("hapke_b", dict(b=0, shell_hapke=1), dict(apply_brdf=True)),
+    ("hapke_b", dict(b=0, shell_hapke=2), dict(apply_brdf=True)),
+    ("hapke_b", dict(b=0, shell_hapke=3), dict(apply_brdf=True, cos_irra_on=True)),
+    ("lambertian", dict(mapping=False), {}),
+    ("rpv111", dict(mapping=False), dict(apply_brdf=True, cos_irra_on=True)),
+    ("rpv111", dict(normal="analystic_learned"), dict(apply_brdf=True, cos_irra_on=True)),
+])
+def test_option_variants_vs_oracle(cuda, cfg, over, kw):
+    """Model options outside the BASELINE configs (shell-Hapke 1-3, no --mapping, analytic + learned normals): CUDA fp32
+    against the oracle (itself pinned against the live reference for the same variants in tests/test_oracle_vs_reference.py)."""
+    args = named_config(cfg, **over)
+    if _needs_normals(args, kw) and not _has_normals():
+        pytest.skip("analytic-normal kernels not built")
+    n = 96
+    batch = make_rays(n)
+    S1, G = args.n_samples, args.guided_samples
+    od = RT.Draws.make(n, S1, G, S1 + G, seed=31)
+    torch.manual_seed(0)
+    model = load_model(args, precision="fp32")
+    with torch.no_grad():
+        ora, bt_o, _ = RT.render_rays(RT.OracleModel(model.state_dict(), args), args, batch.rays, od, mode="test", **kw)
+    model = model.to(cuda)
+    with torch.no_grad():
+        res, bt = render_rays({"coarse": model}, args, batch.rays.to(cuda), None,
+                              _draws=Draws(u_strat=od.u_strat, u_pred=od.u_pred), **kw)
+    assert bt == bt_o
+    assert set(res) == {f"{k}_coarse" for k in ora}, set(res) ^ {f"{k}_coarse" for k in ora}
+    for k in ("rgb", "depth", "weights", "albedo_accu", "nr_vw", "nr_sun"):
+        if k in ora:
+            d = (res[k + "_coarse"].cpu() - ora[k]).abs().max().item()
+            assert d <= TOL, f"{cfg} {over}: {k} differs from the oracle by {d}"
+    for nk in ("normal_an", "normal_lr"):
+        if nk in ora:
+            acc_g = (res["weights_coarse"].unsqueeze(-1) * res[f"{nk}_coarse"]).sum(1).cpu()
+            acc_o = (ora["weights"].unsqueeze(-1) * ora[nk]).sum(1)
+            assert (acc_g - acc_o).abs().max().item() <= TOL, nk

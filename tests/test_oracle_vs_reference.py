@@ -213,3 +213,33 @@ def test_valid_normal_mask_and_zone_letter_vs_reference():
     o = G.synthetic_rpc(0)
     rpc = PG.RPCModel.from_dict({k: getattr(o, k) for k in PG._KEYS + PG._POLYS})
     assert PG.get_zone([0, 5], [0, 7], rpc, -25.0) == (17, "R")
+
+
+OPTION_VARIANTS = [
+    ("hapke_b", dict(b=0, shell_hapke=1), dict(apply_brdf=True)),
+    ("hapke_b", dict(b=0, shell_hapke=2), dict(apply_brdf=True)),
+    ("hapke_b", dict(b=0, shell_hapke=3), dict(apply_brdf=True, cos_irra_on=True)),
+    ("lambertian", dict(mapping=False), {}),
+    ("rpv111", dict(mapping=False), dict(apply_brdf=True, cos_irra_on=True)),
+    ("rpv111", dict(normal="analystic_learned"), dict(apply_brdf=True, cos_irra_on=True)),
+]
+
+
+@pytest.mark.parametrize("cfg,over,kw", OPTION_VARIANTS)
+def test_option_variants_vs_reference(cfg, over, kw):
+    """Model options outside the BASELINE configs that the CUDA path claims: shell-Hapke 1-3, no --mapping,
+    analytic + learned normals together — oracle == live reference on every result key."""
+    args = named_config(cfg, **over)
+    ref_model = RH.build_model(args)
+    batch = make_rays(24)
+    S1, G = args.n_samples, args.guided_samples
+    draws = RT.Draws.make(24, S1, G, S1 + G, seed=77)
+    with torch.no_grad():
+        ref, bt = RH.render(ref_model, args, batch.rays, draws, mode="test", **kw)
+        ora, bt2, _ = RT.render_rays(RT.OracleModel(ref_model.state_dict(), args), args, batch.rays, draws, mode="test", **kw)
+    assert bt == bt2 and set(ref) == set(ora)
+    for k in ref:
+        if ref[k].dtype == torch.int64 or k.startswith("z_vals"):
+            assert torch.equal(ref[k], ora[k]), k
+        else:
+            assert (ref[k] - ora[k]).abs().max().item() <= 2e-6, k
