@@ -317,9 +317,7 @@ def test_option_variants_vs_oracle(cuda, cfg, over, kw):
         res, bt = render_rays({"coarse": model}, args, batch.rays.to(cuda), None,
                               _draws=Draws(u_strat=od.u_strat, u_pred=od.u_pred), **kw)
     assert bt == bt_o
-    missing = set(ora) - set(res)                                       # both carry the reference's `_coarse` suffix
-    assert not missing, f"result keys of the reference that the CUDA path does not return: {sorted(missing)}"
-    print(f"{cfg} {over}: extra keys {sorted(set(res) - set(ora))}")
+    assert set(res) == set(ora), set(res) ^ set(ora)                   # the reference's result keys, no more, no less
     for k in ("rgb", "depth", "weights", "albedo_accu", "nr_vw", "nr_sun"):
         if k + "_coarse" in ora:
             d = (res[k + "_coarse"].cpu() - ora[k + "_coarse"]).abs().max().item()
