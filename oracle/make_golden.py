@@ -42,6 +42,13 @@ CASES = {
     "rpv111_learned_normal": ("rpv111", dict(normal="learned"), dict(mode="test", apply_brdf=True), False, False),
     "lambertian_viewdir_test": ("lambertian_viewdir", {}, dict(mode="test"), False, False),
     "rpv111_sunvis_test": ("rpv111", {}, dict(mode="test", apply_brdf=True, cos_irra_on=True, bTestSun_v=True), False, False),
+    # model options outside the BASELINE configs
+    "hapke_shell1_brdf": ("hapke_b", dict(b=0, shell_hapke=1), dict(mode="test", apply_brdf=True), False, False),
+    "hapke_shell2_brdf": ("hapke_b", dict(b=0, shell_hapke=2), dict(mode="test", apply_brdf=True), False, False),
+    "hapke_shell3_brdf": ("hapke_b", dict(b=0, shell_hapke=3), dict(mode="test", apply_brdf=True, cos_irra_on=True), False, False),
+    "lambertian_nomapping_test": ("lambertian", dict(mapping=False), dict(mode="test"), False, False),
+    "rpv111_nomapping_brdf": ("rpv111", dict(mapping=False), dict(mode="test", apply_brdf=True, cos_irra_on=True), False, False),
+    "rpv111_an_lr_normals": ("rpv111", dict(normal="analystic_learned"), dict(mode="test", apply_brdf=True, cos_irra_on=True), False, False),
 }
 KEEP = ("z_vals", "z_vals_unsort", "sort_idx", "depth", "rgb", "weights", "albedo_accu", "sigmas", "nr_vw", "nr_sun",
         "brdf", "hpk_scl", "sun", "weights_sc")

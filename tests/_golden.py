@@ -24,6 +24,12 @@ CASES = {
     "rpv111_learned_normal": ("rpv111", dict(normal="learned"), dict(mode="test", apply_brdf=True), False),
     "lambertian_viewdir_test": ("lambertian_viewdir", {}, dict(mode="test"), False),
     "rpv111_sunvis_test": ("rpv111", {}, dict(mode="test", apply_brdf=True, cos_irra_on=True, bTestSun_v=True), False),
+    "hapke_shell1_brdf": ("hapke_b", dict(b=0, shell_hapke=1), dict(mode="test", apply_brdf=True), False),
+    "hapke_shell2_brdf": ("hapke_b", dict(b=0, shell_hapke=2), dict(mode="test", apply_brdf=True), False),
+    "hapke_shell3_brdf": ("hapke_b", dict(b=0, shell_hapke=3), dict(mode="test", apply_brdf=True, cos_irra_on=True), False),
+    "lambertian_nomapping_test": ("lambertian", dict(mapping=False), dict(mode="test"), False),
+    "rpv111_nomapping_brdf": ("rpv111", dict(mapping=False), dict(mode="test", apply_brdf=True, cos_irra_on=True), False),
+    "rpv111_an_lr_normals": ("rpv111", dict(normal="analystic_learned"), dict(mode="test", apply_brdf=True, cos_irra_on=True), False),
 }
 
 
