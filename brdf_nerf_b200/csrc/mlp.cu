@@ -715,7 +715,10 @@ static int train_chain(bn_mlp* h, const float* params, const float* origins, int
   prm.store_c = keep_c ? 1 : 0; prm.h_from = train ? 0 : h->L - 1;
   const int n_blocks = (int)ceil_div_ll(P, 256);
   constexpr int smem = chain::chain_smem<true>();
-  BN_CUDA(cudaFuncSetAttribute(chain::train_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  // experiment knob: one weight stage traded for a second cosine staging box per epilogue warp
+  static const bool cbox2 = getenv("BN_CHAIN_CBOX2") != nullptr;
+  auto chain_kernel = cbox2 ? chain::train_chain_kernel<true> : chain::train_chain_kernel<false>;
+  BN_CUDA(cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * min(n_blocks, h->num_sms / 2));
   cfg.blockDim = dim3(tc::kThreads);
@@ -728,7 +731,7 @@ static int train_chain(bn_mlp* h, const float* params, const float* origins, int
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = tc::pdl_enabled() ? 2 : 1;
   prof_begin(2, 2.0 * (double)P * ((double)h->E * h->F + (double)(h->L - 2) * h->F * h->F + (double)(h->F + h->E) * h->F), s);
-  BN_CUDA(cudaLaunchKernelEx(&cfg, chain::train_chain_kernel, prm));
+  BN_CUDA(cudaLaunchKernelEx(&cfg, chain_kernel, prm));
   const int rc = after_launch("train_chain_kernel");
   prof_end(s);
   return rc;

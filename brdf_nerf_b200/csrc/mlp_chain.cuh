@@ -34,7 +34,8 @@ constexpr int kKBBytes = 128 * 128;     // one K block of one CTA: 128 rows x 64
 constexpr int kMaxLayers = 16;
 constexpr int kMaxBiasLayers = 8;       // biases of up to 8 layers are staged in shared memory by the density pass
 // weight ring depth: the training variant gives one stage to the cosine staging boxes
-template <bool kTrain> __host__ __device__ constexpr int w_stages() { return 4; }
+// kCBox2 (experiment, BN_CHAIN_CBOX2=1): the training variant trades one weight stage for a second cosine box per warp
+template <bool kTrain, bool kCBox2 = false> __host__ __device__ constexpr int w_stages() { return (kTrain && kCBox2) ? 3 : 4; }
 
 struct SigmaChainParams {
   CUtensorMap wmap[kMaxLayers];         // packed W_l [F, Kpad_l] bf16, boxes 64 (K) x 128 (rows)
@@ -323,15 +324,17 @@ __global__ void __launch_bounds__(kThreads, 1) sigma_chain_kernel(const __grid_c
 
 // ---------------------------------------------------------------------------------------------------------
 // Training forward of the trunk: the same chain; every layer's h_l and c_l = w0 cos(.) are written to HBM.
+template <bool kCBox2>
 __global__ void __launch_bounds__(kThreads, 1) train_chain_kernel(const __grid_constant__ TrainChainParams prm) {
-  constexpr int kWStages = w_stages<true>();
+  constexpr int kWStages = w_stages<true, kCBox2>();
+  constexpr int kCBytes = (kCBox2 ? 8 : 4) * 4096;            // 3 stages + 32 KB of boxes == 4 stages + 16 KB
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sAct = smem;
   uint8_t* sW = sAct + kNKB * kKBBytes;
   uint8_t* sC = sW + kWStages * kKBBytes;                      // [8 warps][32 rows][64 B] cosine staging boxes
-  uint64_t* wfull = reinterpret_cast<uint64_t*>(sC + 4 * 4096);
+  uint64_t* wfull = reinterpret_cast<uint64_t*>(sC + kCBytes);
   uint64_t* wempty = wfull + kWStages;
   uint64_t* tfull = wempty + kWStages;
   uint64_t* tempty = tfull + 2;
@@ -374,7 +377,8 @@ __global__ void __launch_bounds__(kThreads, 1) train_chain_kernel(const __grid_c
     const uint32_t t_lane = (uint32_t)(q * 32) << 16;
     const bool leader = hsel == 0 && lane == 0;              // issues the quadrant's h_l stores (64-column boxes)
     // cosines leave through one box per WARP (32 rows x 32 columns, 64-byte swizzle): no cross-warp hand-shake
-    uint8_t* cbox = sC + (q * 2 + hsel) * 2048;
+    uint8_t* cbox = sC + (q * 2 + hsel) * (kCBox2 ? 4096 : 2048);
+    uint32_t cu = 0;                                         // cosine units stored so far by this warp (box parity)
     const uint32_t crow_off = lane * 64, cswz = ((lane >> 1) & 3) << 4;
     uint32_t tf_ph[2] = {0, 0};
     uint32_t kf_ph = 0;
@@ -434,12 +438,17 @@ __global__ void __launch_bounds__(kThreads, 1) train_chain_kernel(const __grid_c
                 pc[2 * j + 1] = bf_pack(w0 * __cosf(a2), w0 * __cosf(a3));
               }
             }
+            uint8_t* box = cbox + (kCBox2 ? (cu & 1) * 2048 : 0);
             if (prm.store_c) {
-              if (lane == 0) bulk_wait_read0();              // this warp's previous boxes were read out by the TMA
+              // this box was read out by the TMA: with two boxes only the store before the previous one must be done — except
+              // on the leader's first unit of a half, whose wait also covers the h_l boxes it committed at the end of the
+              // previous half (they must be read out before those K blocks are rewritten)
+              if (lane == 0) { if (kCBox2 && !(hsel == 0 && u == 0)) bulk_wait_read1(); else bulk_wait_read0(); }
               __syncwarp();
 #pragma unroll
               for (int j = 0; j < 4; ++j)
-                sts128(cbox + crow_off + ((j << 4) ^ cswz), pc[4 * j], pc[4 * j + 1], pc[4 * j + 2], pc[4 * j + 3]);
+                sts128(box + crow_off + ((j << 4) ^ cswz), pc[4 * j], pc[4 * j + 1], pc[4 * j + 2], pc[4 * j + 3]);
+              ++cu;
             }
             if (n == 1) {                                    // every MMA of this layer has retired: publish K block 5+u now
               uint8_t* kbp = sAct + (5 + u) * kKBBytes;
@@ -449,7 +458,7 @@ __global__ void __launch_bounds__(kThreads, 1) train_chain_kernel(const __grid_c
             }
             fence_async_smem();
             __syncwarp();
-            if (lane == 0 && prm.store_c) { tma_store_2d(&prm.cmap[l], cbox, col0, grow0); bulk_commit(); }
+            if (lane == 0 && prm.store_c) { tma_store_2d(&prm.cmap[l], box, col0, grow0); bulk_commit(); }
             if (n == 1 && !last) arrive_leader(&act_ready[5 + u]);
           }
           if (n == 0) {
