@@ -1,5 +1,6 @@
 """CPU: host-side logic — config POD, synthetic rays, module surface / flat parameter storage,
 loss restatement used by the fused step, and the no-CPU-fallback rule."""
+import os
 import numpy as np
 import pytest
 import torch
@@ -204,3 +205,41 @@ def test_trainer_checkpoint_layout_is_a_lightning_adam_checkpoint():
     bad = {"state_dict": sd["state_dict"], "optimizer_states": [{"state": {}, "param_groups": [{"lr": 1e-3, "params": [0, 1]}]}]}
     with pytest.raises(ValueError):
         tr2.load_state_dict(bad)
+
+
+def test_bench_reference_arm_contract_and_no_cpu_fallback():
+    """bench.py on a box without a GPU: the reference arm (oracle port on the host cores) prints ONE JSON line with the
+    contract's keys; the product arm refuses to run (there is no CPU fallback)."""
+    import json
+    import subprocess
+    import sys
+    import torch
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-500:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "rays/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and d["metric"].startswith("train rays/s")
+    if not torch.cuda.is_available():
+        r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1"], capture_output=True, text=True, timeout=300)
+        assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_algorithmic_flops_match_the_survey():
+    """bench.py's per-ray work model == SURVEY §8d: 2.00 GFLOP per ray for the Lambertian training step."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    from brdf_nerf_b200.config import named_config
+    args = named_config("lambertian_ds")
+    per_ray = bench.mlp_flops_per_ray(args, 64, 128)
+    assert abs(per_ray / 2 - 1.001e9) < 2e6                              # 1.001 G MAC per ray (fwd 414.6 M + bwd 586.5 M)
+    shared = bench.mlp_flops_per_ray(args, 64, 128, shared_trunk=True)
+    assert abs((per_ray - shared) / 2 - 64 * 1_896_448) < 1                # one trunk evaluation of the 64 stratified points saved
