@@ -182,3 +182,29 @@ def test_dsm_abi_argument_validation():
     assert lib.bn_dsm_points(dummy, 11, dummy, 10, 1.0, 0.0, 0.0, 0.0, 0, 0, dummy, None, None, None, None) == -1   # ecef needs a zone
     with pytest.raises(NotImplementedError, match="defect"):
         PD.DsmGeoref(1.0, (0, 0, 0), cs="ecef").get_dsm_from_nerf_prediction(torch.zeros(4, 11), torch.zeros(4))
+
+
+def test_box_filter_factorisation_random_grids():
+    """Randomised version of the factorisation check: any radius 0..3, grids that cut through the cloud, points exactly on cell
+    borders and far outside — count images identical, heights within the float32 running-mean error."""
+    rng = np.random.default_rng(2024)
+    for trial in range(60):
+        radius = int(rng.integers(0, 4))
+        res = float(rng.choice([0.25, 0.5, 1.0, 2.0]))
+        xs, ys = int(rng.integers(1, 40)), int(rng.integers(1, 40))
+        xoff = float(np.round(rng.uniform(-500, 500) / res) * res)
+        yoff = float(np.round(rng.uniform(-500, 500) / res) * res)
+        n = int(rng.integers(1, 600))
+        x = rng.uniform(xoff - 3 * res, xoff + (xs + 3) * res, n)
+        y = rng.uniform(yoff - (ys + 3) * res, yoff + 3 * res, n)
+        snap = rng.random(n) < 0.2                                       # a fifth of the points exactly on cell borders
+        x[snap] = xoff + np.round((x[snap] - xoff) / res) * res
+        y[snap] = yoff - np.round((yoff - y[snap]) / res) * res
+        cloud = np.stack([x, y, rng.normal(50.0, 20.0, n)], 1)
+        grid = (xoff, yoff, res, xs, ys)
+        want, wc = D.plyflatten(cloud, *grid, radius=radius, return_count=True)
+        got, gc, _ = _emulate_cuda_box_path(cloud, grid, radius=radius)
+        assert np.array_equal(gc, wc), (trial, radius, grid)
+        assert np.array_equal(np.isnan(got), np.isnan(want[..., 0]))
+        if (~np.isnan(got)).any():
+            assert np.nanmax(np.abs(got - want[..., 0])) <= 2e-4, (trial, np.nanmax(np.abs(got - want[..., 0])))
