@@ -44,3 +44,37 @@ def test_oracle_matches_reference_golden(name):
         if "ref_" + k in g:
             d = np.abs(res[k + "_coarse"].numpy() - g["ref_" + k]).max()
             assert d <= 2e-6, f"{name}: {k} differs from the reference by {d}"
+
+
+@pytest.mark.parametrize("cfg,kw", [("lambertian", {}), ("rpv111", dict(apply_brdf=True, cos_irra_on=True)),
+                                    ("hapke_bct", dict(apply_brdf=True, apply_theta=True, cos_irra_on=True))])
+def test_fp64_arbiter_noise_floor(cfg, kw):
+    """The float64 run of the oracle is the arbiter for the tolerance statement (SURVEY §8a N-note): the reference
+    algorithm's OWN float32 rounding moves rgb by ~1e-5..1e-4 and the accumulated normal by ~5e-5 — two orders below the
+    1e-3 bar the CUDA path is held to — while the RAW per-sample analytic normal differs by more than 1e-3 where |grad sigma|
+    is tiny, which is why parity on normals is stated on sum_s w n (and on nr_vw / nr_sun), not per sample."""
+    import torch
+    from brdf_nerf_b200.config import named_config
+    from brdf_nerf_b200.models import load_model
+    from brdf_nerf_b200.synth import make_rays
+    from oracle import render_torch as RT
+    args = named_config(cfg)
+    n = 64
+    torch.manual_seed(0)
+    state = load_model(args).state_dict()
+    batch = make_rays(n)
+    S1, G = args.n_samples, args.guided_samples
+    draws = RT.Draws.make(n, S1, G, S1 + G, seed=3)
+    with torch.no_grad():
+        o32, _, _ = RT.render_rays(RT.OracleModel(state, args), args, batch.rays, draws, mode="test", **kw)
+        o64, _, _ = RT.render_rays(RT.OracleModel(state, args, dtype=torch.float64), args, batch.rays, draws, mode="test", **kw)
+    assert o64["rgb_coarse"].dtype == torch.float64
+    for k in ("rgb_coarse", "depth_coarse", "weights_coarse", "albedo_accu_coarse"):
+        d = (o32[k].double() - o64[k]).abs().max().item()
+        assert d <= 2e-4, f"{k}: float32 vs float64 {d}"
+    if "normal_an_coarse" in o32:
+        acc32 = (o32["weights_coarse"].unsqueeze(-1) * o32["normal_an_coarse"]).sum(1).double()
+        acc64 = (o64["weights_coarse"].unsqueeze(-1) * o64["normal_an_coarse"]).sum(1)
+        assert (acc32 - acc64).abs().max().item() <= 2e-4
+        raw = (o32["normal_an_coarse"].double() - o64["normal_an_coarse"]).abs().max().item()
+        assert raw > 1e-4                                           # the raw normals are NOT reproducible to the accumulated level
