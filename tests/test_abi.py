@@ -59,3 +59,19 @@ def test_sm100a_sass_has_tcgen05_and_tma(lib_path):
     assert "sm_100a" in sass
     for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
         assert mnemonic in sass, f"{mnemonic} missing from the SASS"
+
+
+def test_binding_arity_matches_header():
+    """Every ctypes signature in brdf_nerf_b200/_lib.py has as many arguments as the header's prototype (ABI drift guard)."""
+    from brdf_nerf_b200 import _lib
+    text = open(os.path.join(ROOT, "include", "brdfnerf_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = dict(re.findall(r"\b(bn_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S))
+    checked = 0
+    for name, (_, argtypes) in _lib._SIGS.items():
+        assert name in protos, f"{name} is bound but not declared in the header"
+        params = protos[name].strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert n == len(argtypes), f"{name}: header has {n} parameters, the binding {len(argtypes)}"
+        checked += 1
+    assert checked >= 40
