@@ -32,7 +32,7 @@ RAYS_PER_GPU = 1024
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel of the step, chain::train_chain_kernel at
 # P = 65536 points (two launches per step: stratified points, guided points), from the ncu --set full capture under profiles/
 NCU_CHAIN_DRAM_BYTES_PER_LAUNCH = 15.6e6 + 1026.8e6
-NCU_TRAFFIC_NOTE = ("ncu --set full (profiles/r01e_ncu_full_train_chain.csv, P = 65536): 15.6 MB read + 1026.8 MB written per launch "
+NCU_TRAFFIC_NOTE = ("ncu --set full (profiles/r01f_ncu_full_train_chain.csv and r01e_ncu_full_train_chain.csv, P = 65536): 15.7 MB read + 1026.7 MB written per launch "
                     "= the algorithmic 1.07 GB (h_l, c_l of 8 layers + encoding, bf16; nothing is read back). "
                     "trunk dgrad GEMM (profiles/r01e_ncu_full_gemm.csv): 269 MB read + 105 MB written per launch vs 384 MiB algorithmic "
                     "(the tail of the writes is still in L2 at kernel end); trunk wgrad GEMM: 269.5 MB read vs 256 MiB algorithmic")
