@@ -84,6 +84,7 @@ class ClockSampler:
 
     def stop(self, first=0, last=None):
         if self.p is None:
+            self.rows = None
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.p.terminate()
         try:
@@ -91,10 +92,16 @@ class ClockSampler:
         except Exception:
             self.p.kill()
         self.f.flush()
-        rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
+        self.rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
         os.unlink(self.f.name)
-        # samples of the timed regions (one sample of slack on either side: nvidia-smi stamps are ~20 ms apart)
-        rows = rows[max(0, first - 1):(None if last is None else last + 1)] or rows
+        return self.summary(first, last)
+
+    def summary(self, first=0, last=None):
+        """Clocks / power / throttle reasons of the samples [first, last) of the log (after stop())."""
+        if getattr(self, "rows", None) is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        # one sample of slack on either side: nvidia-smi stamps are ~20 ms apart
+        rows = self.rows[max(0, first - 1):(None if last is None else last + 1)] or self.rows
         sm, mx, pw, reasons = [], [], [], set()
         for r in rows:
             try:
@@ -116,19 +123,36 @@ def _dist_env():
     return rank, local, world
 
 
-def cpu_reference_rate(args, rays_per_step, steps, warmup, seed=0):
-    """The reference algorithm (oracle port: torch CPU fp32, all host threads): rays/s of a full
-    training step (render_rays + loss + backward + Adam)."""
-    from brdf_nerf_b200.models import load_model
+def reference_available():
+    """The unmodified reference (live tree in the build container, oracle/_ref staged by oracle/stage_ref.py on the GPU box)."""
+    try:
+        from oracle import ref_harness as RH
+        return RH.kind() != "absent"
+    except Exception:                                                    # noqa: BLE001
+        return False
+
+
+def cpu_reference_rate(args, rays_per_step, steps, warmup, seed=0, device="cpu"):
+    """rays/s of a full training step (render_rays + losses + backward + Adam) of the reference algorithm on `device`.
+    kind "reference": the UNMODIFIED reference files (oracle/ref_step.py drives rendering.render_rays, metrics.SNerfLoss /
+    DepthLoss and torch.optim.Adam exactly as main.py:194-268 does); kind "port": the oracle restatement, only when the
+    reference files are not available.  Returns (rays/s, ms/step, threads, kind)."""
     from brdf_nerf_b200.synth import make_rays
+    torch.set_num_threads(os.cpu_count() or 1)
+    batch = make_rays(rays_per_step, depth_supervision=True)
+    if reference_available():
+        from oracle import ref_step
+        v, ms = ref_step.rate(args, batch, steps, warmup, device=device)
+        return v, ms, torch.get_num_threads(), "reference"
+    if device != "cpu":
+        raise RuntimeError("the oracle port runs on the CPU only")
+    from brdf_nerf_b200.models import load_model
     from oracle import losses_torch as LT
     from oracle import render_torch as RT
-    torch.set_num_threads(os.cpu_count() or 1)
     torch.manual_seed(seed)
     state = load_model(args).state_dict()
     om = RT.OracleModel(state, args, requires_grad=True)
     opt = torch.optim.Adam(om.parameters(), lr=args.lr)
-    batch = make_rays(rays_per_step, depth_supervision=True)
     S1, G = args.n_samples, args.guided_samples
     times = []
     for i in range(warmup + steps):
@@ -144,7 +168,7 @@ def cpu_reference_rate(args, rays_per_step, steps, warmup, seed=0):
         if i >= warmup:
             times.append(dt)
     ms = 1e3 * sum(times) / len(times)
-    return rays_per_step / (ms / 1e3), ms, torch.get_num_threads()
+    return rays_per_step / (ms / 1e3), ms, torch.get_num_threads(), "port"
 
 
 def tile_products_leg(cpu=True):
@@ -183,24 +207,101 @@ def tile_products_leg(cpu=True):
         return {"error": f"{type(e).__name__}: {e}"}
 
 
+WORKLOAD = ("spsbrdf-nerf Lambertian pretrain + depth supervision (ds_lambda=10, --mapping), "
+            "1024 rays x (64+64) samples per GPU per step, fc 8x512, random init seed 0")
+
+
 def run_reference(opts):
+    """The reference arm: the reference's own implementation of the path on this box's host cores, all threads, same
+    workload (1024 rays per step, so that `config` equals our arm's)."""
     rank, _, world = _dist_env()
     if rank != 0:
         return
     from brdf_nerf_b200.config import named_config
     args = named_config("lambertian_ds")
-    rps = RAYS_PER_GPU if (opts.steps + opts.warmup) <= 12 else 256
-    value, ms, cores = cpu_reference_rate(args, rps, opts.steps, opts.warmup)
-    sample = f"{opts.steps} steps of {rps} rays after {opts.warmup} warm-up, torch CPU fp32 oracle port"
+    value, ms, cores, kind = cpu_reference_rate(args, RAYS_PER_GPU, opts.steps, opts.warmup)
+    what = ("the UNMODIFIED reference files (oracle/_ref: rendering.render_rays + metrics.SNerfLoss / DepthLoss + torch.optim.Adam)"
+            if kind == "reference" else "torch CPU fp32 oracle port (reference files not staged)")
+    sample = f"{opts.steps} steps of {RAYS_PER_GPU} rays after {opts.warmup} warm-up, {what}, torch CPU fp32, {cores} threads"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": opts.gpus, "steps": opts.steps,
             "warmup": opts.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "spsbrdf-nerf Lambertian pretrain + depth supervision (ds_lambda=10, --mapping), "
-                                   "1024 rays x (64+64) samples per GPU per step, fc 8x512, random init seed 0",
-                       "sample": f"each timed step runs {rps} of the 1024 rays on the host cores (bounded sample)"},
-            "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": {"workload": WORKLOAD, "rays_per_gpu": RAYS_PER_GPU, "global_rays": RAYS_PER_GPU,
+                       "sample": "every timed step is the full 1024-ray step on the host cores (rank 0 only)"},
+            "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def other_configs_leg(opts, dev, rank, world, barrier):
+    """The other BASELINE.json configurations on the same launch (every rank takes part: the training ones all-reduce):
+      configs[2]  BRDF stage RPV111 + analytic normals (second-order backward) + cos_irra_on, 1024 rays per GPU (weak)
+      configs[3]  Hapke b,c,theta / microfacet, 8192 rays per step ray-sharded over the ranks (strong: 8192 / N per GPU)
+      configs[4]  inference RGB + depth + normals + albedo in chunks of 5120 rays (eval.py:56-76), rays/s per job (weak)
+    A few graph-replayed steps each, device-timed, max over ranks."""
+    from brdf_nerf_b200.config import named_config
+    from brdf_nerf_b200.models import load_model
+    from brdf_nerf_b200.rendering import render_rays
+    from brdf_nerf_b200.synth import make_rays
+    from brdf_nerf_b200.train import Trainer
+    out = {}
+
+    def timed(fn, steps, warmup=3):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
+        if world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t[0])
+
+    def train(key, cfg, rays_per_gpu, steps, scaling, **kw):
+        args = named_config(cfg)
+        torch.manual_seed(0)
+        model = load_model(args, precision=opts.precision).to(dev)
+        tr = Trainer(model, args, world_size=world, use_graph=bool(opts.graph))
+        batch = make_rays(rays_per_gpu, seed=20240912 + rank).to(dev)
+        ms = timed(lambda: tr.step(batch, **kw), steps)
+        total = rays_per_gpu * world
+        out[key] = {"model": cfg, "kwargs": kw, "rays_per_gpu": rays_per_gpu, "global_rays": total, "n_gpus": world,
+                    "scaling": scaling, "steps": steps, "ms_per_step": ms, "rays_per_s": total / ms * 1e3,
+                    "gpu_launches_per_step": int(getattr(tr, "graph_launches", 0))}
+        del tr, model, batch
+        torch.cuda.empty_cache()
+
+    train("configs[2] BRDF stage RPV111 funcM/F/H=1, normal=analystic, cos_irra_on", "rpv111", RAYS_PER_GPU, 10, "weak",
+          apply_brdf=True, cos_irra_on=True)
+    per = max(128, (8192 // world) // 128 * 128)
+    train("configs[3] Hapke b,c,theta, 8192 rays ray-sharded", "hapke_bct", per, 4, "strong",
+          apply_brdf=True, apply_theta=True, cos_irra_on=True)
+    train("configs[3] microfacet, 8192 rays ray-sharded", "microfacet", per, 4, "strong", apply_brdf=True, cos_irra_on=True)
+    # inference: independent chunks, no collective
+    args = named_config("rpv111")
+    torch.manual_seed(0)
+    model = load_model(args, precision=opts.precision).to(dev)
+    chunk, n_chunks = int(args.chunk), 4
+    rays = make_rays(chunk * n_chunks, seed=rank).rays.to(dev)
+
+    def infer():
+        with torch.no_grad():
+            for c in range(n_chunks):
+                render_rays({"coarse": model}, args, rays[c * chunk:(c + 1) * chunk], None, mode="test", apply_brdf=True,
+                            cos_irra_on=True)
+
+    ms = timed(infer, 3, warmup=2)
+    rps = chunk * n_chunks * world / ms * 1e3
+    out["configs[4] inference RGB+depth+normals+albedo, 5120-ray chunks, ray-sharded"] = {
+        "model": "rpv111", "chunk_rays": chunk, "chunks_per_gpu": n_chunks, "n_gpus": world, "scaling": "weak",
+        "ms_per_chunk": ms / n_chunks, "rays_per_s": rps, "tile_2048x2048_seconds": 2048 * 2048 / rps}
+    del model
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_ours(opts):
@@ -292,11 +393,36 @@ def run_ours(opts):
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1) / opts.steps
-    clk = clocks.stop(mark0, clocks.mark()) if clocks else None
+    mark1 = clocks.mark() if clocks else 0
+    # ---- sustained leg: the same resident step for >= opts.sustain seconds back to back.  The K timed steps above last a few
+    # tens of milliseconds (a burst: the GPU has not reached its 1 kW power cap); a training run lives here instead.
     t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
     ms, ms_e2e = float(t[0]), float(t[1])
+    ms_sus, n_sus = None, 0
+    if opts.sustain > 0:
+        n_sus = max(opts.steps, int(opts.sustain * 1e3 / max(ms, 1e-3)))      # from the max-over-ranks time: same count everywhere
+        barrier()
+        e0.record()
+        for _ in range(n_sus):
+            loss = trainer.step(batch)
+        e1.record()
+        barrier()
+        ms_sus = e0.elapsed_time(e1) / n_sus
+    mark2 = clocks.mark() if clocks else 0
+    clk_sus = None
+    if clocks:
+        clocks.stop()
+        clk = clocks.summary(mark0, mark1)
+        clk_sus = clocks.summary(mark1, mark2) if ms_sus is not None else None
+    else:
+        clk = None
+    if ms_sus is not None:
+        t = torch.tensor([ms_sus], device=dev, dtype=torch.float64)
+        if world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms_sus = float(t[0])
     total_rays = RAYS_PER_GPU * world
 
     # ---- roofline leg: per-launch CUDA-event timing of the GEMM family on the launching stream ----
@@ -326,15 +452,18 @@ def run_ours(opts):
         kind = lambda i: {"launches": cnt[i] / nprof, "ms": tms[i] / nprof, "tflops": work[i] / max(tms[i], 1e-9) / 1e9}
         chain_tf = work[2] / max(tms[2], 1e-9) / 1e9
         # the dominant kernel of the step: the fused PE + 8-layer SIREN trunk forward (chain::train_chain_kernel)
+        # denominator: the BURST cuBLAS figure — the profiled region is three eager steps (~10 ms), nowhere near the seconds it
+        # takes to reach the power cap; the fraction against the sustained figure is given beside it
         roof = {"bound": "tensor", "kernel": "bn::chain::train_chain_kernel (fused PE + 8 SIREN layers, forward, writes h_l / cos_l for the backward)",
-                "achieved": chain_tf, "peak": peaks["tf_sust"], "unit": "TFLOP/s", "frac": chain_tf / peaks["tf_sust"],
-                "peak_kind": f"{peaks['src']} sustained bf16 (kernel timed inside a long step; burst peak {peaks['tf_burst']})",
+                "achieved": chain_tf, "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": chain_tf / peaks["tf_burst"],
+                "frac_of_sustained_peak": chain_tf / peaks["tf_sust"],
+                "peak_kind": f"{peaks['src']} burst bf16 cuBLAS (kernel timed per launch inside a ~10 ms region; sustained peak {peaks['tf_sust']})",
                 "traffic": NCU_CHAIN_DRAM_BYTES_PER_LAUNCH, "traffic_note": NCU_TRAFFIC_NOTE,
                 "launches_per_step": cnt[2] / nprof, "us_per_launch": 1e3 * tms[2] / max(cnt[2], 1),
                 "share_of_step": tms[2] / nprof / ms,      # of the timed (graph-replayed) step; compare with the ncu launch list
 
                 "all_tcgen05": {"kernel": "every tcgen05 launch of a step (chain kernels + gemm_tc_kernel fwd/dgrad/wgrad)",
-                                "achieved": achieved, "frac": achieved / peaks["tf_sust"], "frac_of_burst": achieved / peaks["tf_burst"],
+                                "achieved": achieved, "frac": achieved / peaks["tf_burst"], "frac_of_sustained_peak": achieved / peaks["tf_sust"],
                                 "launches_per_step": sum(cnt) / nprof, "ms_per_step": gemm_ms, "share_of_step": gemm_ms / ms,
                                 "share_note": "per-launch times are taken with the backward serialised (no concurrent weight-gradient stream), "
                                               "the timed step overlaps them: the sum may exceed the step",
@@ -356,24 +485,42 @@ def run_ours(opts):
                     "traffic": None, "algorithmic_bytes_per_launch": dom["bytes"], "us_per_launch": dom["us"],
                     "workload": f"{n_c} rays x 128 samples (one inference chunk); the 1024-ray training batch moves 7 MB and is latency bound",
                     "all": {k: {"us": v["us"], "GB/s": v["gbs"], "frac": v["frac"]} for k, v in r.items()}}
+    other = None
+    if not opts.no_other_configs:
+        del trainer
+        torch.cuda.empty_cache()
+        other = other_configs_leg(opts, dev, rank, world, barrier)
     if rank == 0:
-        cpu = None
+        cpu = cuda_eager = None
         if world == 1 and not opts.no_cpu_baseline:
-            v, cms, cores = cpu_reference_rate(args, RAYS_PER_GPU, 6, 1)
-            cpu = {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",
-                   "sample": "6 steps of 1024 rays after 1 warm-up (full step: render + loss + backward + Adam), torch CPU fp32"}
+            v, cms, cores, kind = cpu_reference_rate(args, RAYS_PER_GPU, 4, 1)
+            cpu = {"value": v, "unit": "rays/s", "cores": cores, "kind": kind, "ms_per_step": cms,
+                   "sample": "4 steps of 1024 rays after 1 warm-up (full step: render + loss + backward + Adam), torch CPU fp32, "
+                             + ("the unmodified reference files staged in oracle/_ref" if kind == "reference" else "oracle port")}
+            if kind == "reference":
+                # the same unmodified reference code on THIS B200 through torch's eager CUDA kernels (strict fp32, allow_tf32 off):
+                # the same-box comparator of SURVEY 8d.  A reported baseline like cpu_baseline, not the target.
+                try:
+                    v2, ms2, _, _ = cpu_reference_rate(args, RAYS_PER_GPU, 5, 2, device="cuda")
+                    cuda_eager = {"value": v2, "unit": "rays/s", "ms_per_step": ms2, "kind": "reference", "device": "cuda:0 (torch eager, fp32, allow_tf32=False)",
+                                  "sample": "5 steps of 1024 rays after 2 warm-up, the unmodified reference files on the B200"}
+                except Exception as e:                                   # noqa: BLE001
+                    cuda_eager = {"error": f"{type(e).__name__}: {e}"}
         line = {"metric": METRIC, "value": total_rays / (ms * 1e-3), "unit": "rays/s", "n_gpus": world, "steps": opts.steps,
                 "warmup": max(3, opts.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16" if opts.precision == "bf16" else "f32", "data": "synthetic",
-                "config": {"workload": "spsbrdf-nerf Lambertian pretrain + depth supervision (ds_lambda=10, --mapping), "
-                                       "1024 rays x (64+64) samples per GPU per step, fc 8x512, random init seed 0",
+                "config": {"workload": WORKLOAD,
                            "rays_per_gpu": RAYS_PER_GPU, "global_rays": total_rays, "parallelism": f"ray-sharded dp{world}",
                            "cuda_graph": bool(opts.graph), "e2e_feed": opts.feed,
                            "l2": "per-step working set (~3.4 GB of activations) >> 126 MB L2; no explicit flush"},
                 "e2e": {"value": total_rays / (ms_e2e * 1e-3), "unit": "rays/s", "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": int(host_batch.flat.numel()), "d2h_bytes_per_step": 4},
                 "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "roofline_composite": roof_hbm,
-                "cpu_baseline": cpu,
+                "sustained": None if ms_sus is None else {
+                    "value": total_rays / (ms_sus * 1e-3), "unit": "rays/s", "ms_per_step": ms_sus, "steps": n_sus,
+                    "seconds": ms_sus * n_sus * 1e-3, "clocks": clk_sus,
+                    "note": "same resident step back to back for >= --sustain seconds (power-capped steady state); `value` above is the K-step burst"},
+                "cpu_baseline": cpu, "reference_cuda_eager": cuda_eager, "other_configs": other,
                 "tile_products": tile_products_leg(cpu=not opts.no_cpu_baseline) if (world == 1 and not opts.no_tile_products) else None,
                 "loss": float(loss_host)}
         print(json.dumps(line))
@@ -392,6 +539,8 @@ def main():
     ap.add_argument("--feed", default="inline", choices=["prefetch", "inline"],
                     help="e2e leg: host batches through Trainer.prefetch() on a copy stream, or copied on the compute stream")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the configs[2..4] leg")
+    ap.add_argument("--sustain", type=float, default=2.0, help="seconds of back-to-back steps for the sustained figure (0 = off)")
     ap.add_argument("--no-composite", action="store_true", help="skip the compositing (HBM) roofline leg")
     ap.add_argument("--no-tile-products", action="store_true", help="skip the ray-feed / DSM leg (SURVEY 8f-3/4 kernels)")
     opts = ap.parse_args()

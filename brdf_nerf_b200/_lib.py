@@ -73,6 +73,7 @@ _SIGS = {
     "bn_mlp_normals_forward": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _Z, _P]),
     "bn_mlp_normals_backward": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _Z, _P]),
     "bn_debug_chain_trace": (C.c_int, [_P, _P]),
+    "bn_debug_ws_tensor": (C.c_int, [_P, _L, _I, _I, _I, _P, _P]),
     "bn_debug_gemm_epi": (C.c_int, [_I, _P, C.c_longlong, _P, C.c_longlong, _P, C.c_longlong, _P, _P, _P, _I, _I,
                                     C.c_longlong, _I, C.c_longlong, _P]),
     "bn_debug_gemm": (C.c_int, [_I, _I, _P, C.c_longlong, _P, C.c_longlong, _P, C.c_longlong, C.c_longlong, _I, C.c_longlong, _P]),

@@ -32,7 +32,9 @@ class PointsFunction(torch.autograd.Function):
                                 nr_lr_on=nr_lr_on and not sigma_only, train=need_grad)
         C = model.out_channels(flags)
         out = torch.empty((B, C), dtype=torch.float32, device=xyz.device)
-        ws = model.workspace(B, flags, "ws_points")
+        # a call that will be differentiated owns its workspace (kept alive by ctx): the reference calls the module once per
+        # chunk and runs backward afterwards, so a shared buffer would be overwritten before it is read
+        ws = model.workspace(B, flags, None if need_grad else "ws_points")
         ops.mlp_forward(model, xyz, 3, dirs, 3, z, flags, out, C, ws)
         if flags & L.MLP_NORMAL_AN:
             ops.mlp_normals_forward(model, out, C, B, 1, flags, ws)

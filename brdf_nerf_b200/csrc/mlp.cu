@@ -1257,3 +1257,25 @@ extern "C" __attribute__((visibility("default"))) int bn_debug_chain_trace(bn_ml
   h->chain_trace = device_buf;
   return BN_OK;
 }
+
+// Unit-test hook: offset / pitch of X3, H_l, C_l inside a workspace carved for (n_points, flags)
+extern "C" __attribute__((visibility("default")))
+int bn_debug_ws_tensor(const bn_mlp* h, int64_t n_points, int flags, int which, int layer, int64_t* offset_bytes,
+                       int64_t* pitch_elems) {
+  BN_CHECK_ARG(h && offset_bytes && pitch_elems, "null pointer");
+  BN_CHECK_ARG(which >= 0 && which <= 2 && layer >= 0 && layer < h->L, "which / layer out of range");
+  uint8_t* const base = reinterpret_cast<uint8_t*>(uintptr_t(4096));      // carve() only does pointer arithmetic on it
+  const uint8_t* p = nullptr; long long ld = 0;
+  if (h->bf16) {
+    Ws<__nv_bfloat16> w; carve<__nv_bfloat16>(h, n_points, flags, base, &w);
+    if (which == 0) { p = (const uint8_t*)w.X3; ld = w.ldx3; } else if (which == 1) { p = (const uint8_t*)w.H[layer]; ld = w.Hld[layer]; }
+    else { p = (const uint8_t*)w.C[layer]; ld = h->F; }
+  } else {
+    Ws<float> w; carve<float>(h, n_points, flags, base, &w);
+    if (which == 0) { p = (const uint8_t*)w.X3; ld = w.ldx3; } else if (which == 1) { p = (const uint8_t*)w.H[layer]; ld = w.Hld[layer]; }
+    else { p = (const uint8_t*)w.C[layer]; ld = h->F; }
+  }
+  BN_CHECK_ARG(p != nullptr, "this tensor is not kept for these flags");
+  *offset_bytes = (int64_t)(p - base); *pitch_elems = ld;
+  return BN_OK;
+}

@@ -251,6 +251,8 @@ class DsmGeoref:
         else:
             cloud, _, bounds = self._points(rays, depth, False, True)
             b = reduce_bounds(bounds, group).cpu().tolist()
+            if not all(math.isfinite(v) for v in b):        # same on every rank (the bounds are all-reduced): all raise together
+                raise ValueError("no finite point in the predicted cloud")
             grid = grid_from_bounds(b[0], b[1], b[2], b[3], 0.5)
         ws = accumulate_cloud(cloud, grid, radius=1, sigma=float("inf"))
         sums, counts = workspace_views(ws)

@@ -98,7 +98,15 @@ def render_tile(models, rays, args, rank=0, world_size=1, keys: Optional[Iterabl
     the per-rank results are all-gathered into full (H*W, ...) tensors on every rank — the only collective, and off the
     compute path; otherwise each rank returns its own slice."""
     lo, hi = tile_shards(rays.shape[0], int(args.chunk), world_size)[rank]
-    res, brdf_type = batched_inference(models, rays[lo:hi], None, args, **kw) if hi > lo else ({}, None)
+    if hi > lo:
+        res, brdf_type = batched_inference(models, rays[lo:hi], None, args, **kw)
+    elif gather and world_size > 1 and rays.shape[0] > 0:
+        # fewer chunks than ranks: this rank still has to join every all_gather below with a zero-length part of the right
+        # key set / trailing shape / dtype (and report the same brdf_type) — one dummy ray tells it all three
+        res, brdf_type = batched_inference(models, rays[0:1], None, args, **kw)
+        res = {k: v[0:0] for k, v in res.items()}
+    else:
+        res, brdf_type = {}, None
     if keys is not None:
         res = {k: res[k] for k in keys if k in res}
     if not gather or world_size == 1:

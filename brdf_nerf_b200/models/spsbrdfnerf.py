@@ -120,6 +120,7 @@ class SpSBRDFNeRF(nn.Module):
         self._flat_grad: Optional[torch.Tensor] = None
         self._handle = None
         self._synced_version = -1
+        self._dirty = 0
         self._ws_cache: Dict[str, torch.Tensor] = {}
 
     # ------------------------------------------------------------------ reference utility surface
@@ -264,13 +265,28 @@ class SpSBRDFNeRF(nn.Module):
             self._synced_version = -1
         return self._handle
 
+    def _weights_version(self):
+        """Changes whenever a parameter is written in place through autograd-visible tensors: `opt.step()`, `p.add_()`,
+        `load_state_dict` (copy_ into the views).  The flat buffer's own counter does NOT move when a parameter view is
+        updated (every view has its own counter), so the views' counters are part of the key.  Writes through `p.data`
+        bypass every counter: call `mark_weights_dirty()` after those."""
+        return (self._flat._version, sum(p._version for p in self.parameters()), self._dirty)
+
+    def mark_weights_dirty(self):
+        """The master weights were changed behind torch's version counters (raw kernels, `p.data` writes)."""
+        self._dirty += 1
+
     def sync_weights(self, force=False):
         """Refresh the packed (bf16 / transposed) weight copies if the master weights changed."""
         h = self.handle()
-        v = self._flat._version
+        v = self._weights_version()
         if force or v != self._synced_version:
             L.check(L.load().bn_mlp_sync_weights(h, L.ptr(self._flat), L.stream_ptr()))
             self._synced_version = v
+
+    def _load_from_state_dict(self, *a, **kw):
+        super()._load_from_state_dict(*a, **kw)
+        self._dirty += 1
 
     def set_precision(self, precision: str):
         if precision not in ("fp32", "bf16"):
@@ -305,9 +321,11 @@ class SpSBRDFNeRF(nn.Module):
                 f |= L.MLP_ROUGH
             elif self.RPV:
                 f |= L.MLP_RPV
-            elif self.args.b == True or self.args.c == True:      # noqa: E712
-                f |= L.MLP_HAPKE
-                if apply_theta and self.args.theta == True:       # noqa: E712
+            else:               # reference else-branch (spsbrdfnerf.py:742-755): b, c and theta are emitted independently,
+                want_theta = bool(apply_theta and self.args.theta == True)       # noqa: E712  e.g. shell_hapke + theta only
+                if self.args.b == True or self.args.c == True or want_theta:     # noqa: E712
+                    f |= L.MLP_HAPKE
+                if want_theta:
                     f |= L.MLP_HAPKE_THETA
         return f
 
@@ -317,8 +335,13 @@ class SpSBRDFNeRF(nn.Module):
             L.check(n)
         return n
 
-    def workspace(self, n_points: int, flags: int, tag: str = "ws") -> torch.Tensor:
+    def workspace(self, n_points: int, flags: int, tag: Optional[str] = "ws") -> torch.Tensor:
+        """MLP workspace of a call.  `tag=None`: a fresh buffer owned by the caller (the autograd bridges keep it alive in
+        their ctx, so a later forward cannot overwrite the activations an earlier backward still needs); a tag names a
+        cached buffer that is reused by every call with that tag (tape-free Trainer path, no-grad inference)."""
         need = L.load().bn_mlp_workspace_bytes(self.handle(), n_points, flags)
+        if tag is None:
+            return torch.empty(int(need) + 256, dtype=torch.uint8, device=self._flat.device)
         ws = self._ws_cache.get(tag)
         if ws is None or ws.numel() < need or ws.device != self._flat.device:
             ws = torch.empty(int(need * 1.0) + 256, dtype=torch.uint8, device=self._flat.device)

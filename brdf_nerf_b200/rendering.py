@@ -87,7 +87,14 @@ def _call_brdf_type(model, args, apply_brdf: bool) -> int:
 
 def _forward(model, args, rays: torch.Tensor, draws: Optional[Draws], mode: str, valid_depth, target_depths,
              target_std, apply_brdf: bool, bTestNormal: bool, bTestSun_v: bool, gsam_only: bool, apply_theta: bool,
-             cos_irra_on: bool, train: bool, debug_nan: bool = False):
+             cos_irra_on: bool, train: bool, debug_nan: bool = False, own_ws: bool = False, sync: bool = True,
+             reference_rng: bool = False):
+    """`own_ws`: the MLP workspace is allocated for this call and owned by the returned state (autograd bridge: several
+    forwards may be alive before their backwards run); otherwise the model's cached per-tag buffer is reused.
+    `sync=False`: the caller (Trainer) has refreshed the packed weight copies itself.
+    `reference_rng`: draw from torch's generator exactly like the reference does: the sigma-noise
+    `randn`s are drawn even when `noise_std == 0` (spsbrdfnerf.py:58) and the ground-truth guided draw has the
+    data-dependent shape (n_valid, G) (rendering.py:144) — one host sync; not CUDA-graph capturable."""
     if args.model != "spsbrdf-nerf":
         raise NotImplementedError("only --model spsbrdf-nerf is implemented (BASELINE north star)")
     if args.n_importance > 0:
@@ -110,13 +117,27 @@ def _forward(model, args, rays: torch.Tensor, draws: Optional[Draws], mode: str,
     S_sun = G if gsam_only else S1
     if draws is None:
         rnd = lambda *sh: torch.rand(sh, device=dev, dtype=torch.float32)
-        rndn = lambda *sh: torch.randn(sh, device=dev, dtype=torch.float32) if noise_std != 0.0 else None
+        if reference_rng:
+            def rndn(*sh):                       # drawn (and the generator advanced) even when the noise is switched off
+                t = torch.randn(sh, device=dev, dtype=torch.float32)
+                return t if noise_std != 0.0 else None
+
+            def rnd_gt():                        # (n_valid, G) draws scattered to the valid rows, in row order
+                valid = valid_depth.to(dev).reshape(-1) > 0
+                u = torch.zeros((N, G), device=dev, dtype=torch.float32)
+                u[valid] = torch.rand((int(valid.sum().item()), G), device=dev, dtype=torch.float32)
+                return u
+        else:
+            rndn = lambda *sh: torch.randn(sh, device=dev, dtype=torch.float32) if noise_std != 0.0 else None
+            rnd_gt = lambda: rnd(N, G)
+        # keyword arguments are evaluated left to right: the order below is the reference's draw order (App. B)
         draws = Draws(u_strat=rnd(N, S1), noise1=rndn(N, S1),
                       u_sun=rnd(N, S_sun) if want_sun else None, noise_sun=rndn(N, S_sun) if want_sun else None,
-                      u_pred=rnd(N, G), u_gt=rnd(N, G) if use_gt else None, noise2=rndn(N, S))
+                      u_pred=rnd(N, G), u_gt=rnd_gt() if use_gt else None, noise2=rndn(N, S))
     else:
         draws = draws.to(dev)
-    model.sync_weights()
+    if sync:
+        model.sync_weights()
     t_vals, gauss = ops.sampler_tables(S1, d_range, dev)
     t_g, gauss_g = ops.sampler_tables(G, d_range, dev)
 
@@ -135,7 +156,7 @@ def _forward(model, args, rays: torch.Tensor, draws: Optional[Draws], mode: str,
     sigma1 = torch.empty((N, S1), dtype=torch.float32, device=dev)
     ws = None
     if share_trunk:
-        ws = model.workspace(N * S, flags, tag="ws_train" if train else "ws_full")
+        ws = model.workspace(N * S, flags, tag=None if own_ws else ("ws_train" if train else "ws_full"))
         ops.mlp_trunk_forward(model, origins, 11, dirs, 11, z1, flags, N * S, 0, sigma1, ws)
     if want_sun or not share_trunk:
         ws1 = model.workspace(N * max(S1, S_sun), L.MLP_SIGMA_ONLY, tag="ws_sigma")
@@ -200,7 +221,7 @@ def _forward(model, args, rays: torch.Tensor, draws: Optional[Draws], mode: str,
         packed = ops.permute_samples(packed_rows, idx, N, S1, G, pitch, scatter=False)
     else:
         packed = torch.empty((N, S, pitch), dtype=torch.float32, device=dev)
-        ws = model.workspace(N * S, flags, tag="ws_train" if train else "ws_full")
+        ws = model.workspace(N * S, flags, tag=None if own_ws else ("ws_train" if train else "ws_full"))
         ops.mlp_forward(model, origins, 11, dirs, 11, z, flags, packed, pitch, ws)
         if nr_an:
             ops.mlp_normals_forward(model, packed, pitch, N, S, flags, ws)
@@ -282,12 +303,13 @@ class _RenderFunction(torch.autograd.Function):
     """Autograd bridge: parameters in, (rgb, depth, weights, packed) out."""
 
     @staticmethod
-    def forward(ctx, model, args, rays, draws, kw, *params):
-        outs, st = _forward(model, args, rays, draws, train=True, **kw)
+    def forward(ctx, model, args, rays, draws, kw, holder, *params):
+        # own_ws: this call's activations stay alive (in ctx.st) until ITS backward has run, however many other forwards
+        # (chunks, other models, other streams) happen in between; `holder` hands the non-tensor results back to the caller
+        outs, st = _forward(model, args, rays, draws, train=True, own_ws=True, **kw)
         ctx.model, ctx.st = model, st
-        ctx.holder = outs
+        holder["outs"] = outs
         ctx.mark_non_differentiable(outs["alpha"], outs["trans"], outs["z"])
-        _RenderFunction._last = outs
         return outs["rgb"], outs["depth"], outs["weights"], outs["packed"], outs["alpha"], outs["trans"], outs["z"]
 
     @staticmethod
@@ -296,7 +318,7 @@ class _RenderFunction(torch.autograd.Function):
         flat = torch.zeros_like(model.flat_params)
         _backward(model, st, g_rgb, g_depth, g_weights, g_packed, flat)
         grads = model.grad_views(flat)
-        return (None, None, None, None, None, *grads)
+        return (None, None, None, None, None, None, *grads)
 
 
 def _assemble(model, args, rays, outs, rgb, depth, weights, packed, apply_brdf, apply_theta) -> Dict[str, torch.Tensor]:
@@ -385,19 +407,22 @@ def _assemble(model, args, rays, outs, rgb, depth, weights, packed, apply_brdf, 
 def render_rays(models, args, rays, ts, mode="test", valid_depth=None, target_depths=None, target_std=None,
                 apply_brdf=False, print_debuginfo=False, bTestNormal=False, bTestSun_v=False, gsam_only=False,
                 rows=None, cols=None, percent=0, apply_theta=False, cos_irra_on=False, _draws: Optional[Draws] = None,
-                _return_extras=False):
+                _return_extras=False, _reference_rng: bool = False):
     """Same signature / return as the reference (rendering.py:168,334): (dict with `_coarse` keys, brdf_type).
-    `_draws` (extension) injects the random draws for deterministic parity runs."""
+    `_draws` (extension) injects the random draws for deterministic parity runs; `_reference_rng=True` (extension) consumes
+    torch's CUDA generator in exactly the reference's order and shapes (see `_forward`), so that a seeded reference run on
+    the same device sees the same draws."""
     model = models["coarse"]
     kw = dict(mode=mode, valid_depth=valid_depth, target_depths=target_depths, target_std=target_std,
               apply_brdf=bool(apply_brdf), bTestNormal=bool(bTestNormal), bTestSun_v=bool(bTestSun_v),
-              gsam_only=bool(gsam_only), apply_theta=bool(apply_theta), cos_irra_on=bool(cos_irra_on))
+              gsam_only=bool(gsam_only), apply_theta=bool(apply_theta), cos_irra_on=bool(cos_irra_on),
+              reference_rng=bool(_reference_rng))
     need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in model.parameters())
     if need_grad:
-        rgb, depth, weights, packed, alpha, trans, z = _RenderFunction.apply(model, args, rays, _draws, kw,
+        holder = {}
+        rgb, depth, weights, packed, alpha, trans, z = _RenderFunction.apply(model, args, rays, _draws, kw, holder,
                                                                              *model.parameters())
-        outs = _RenderFunction._last
-        _RenderFunction._last = None
+        outs = holder["outs"]
     else:
         outs, _ = _forward(model, args, rays, _draws, train=False, debug_nan=bool(print_debuginfo), **kw)
         rgb, depth, weights, packed = outs["rgb"], outs["depth"], outs["weights"], outs["packed"]

@@ -77,6 +77,11 @@ class Trainer:
         self._copy_stream = None
         self._stage, self._stage_ready, self._stage_free, self._stage_i = [None, None], [None, None], [None, None], 0
         self._loss_ring, self._loss_i = None, 0
+        # NormalLoss (nr_spv_lambda / nr_spv_type, main.py:301-327: supervision by normals derived from the depth maps) is
+        # not part of this driver: refuse instead of silently training without it
+        if abs(float(getattr(args, "nr_spv_lambda", 0.0) or 0.0)) > 1e-5:
+            raise NotImplementedError("nr_spv_lambda != 0 (NormalLoss, main.py:301-327) is not implemented by Trainer")
+        self._frozen = None                 # [(offset, length)] of the parameters with requires_grad == False
 
     # one optimisation step; `batch` tensors must already live on the model's device
     def _step_impl(self, batch: RayBatch, draws, kw):
@@ -100,7 +105,30 @@ class Trainer:
         grads = model.flat_grads
         grads.zero_()
         R._backward(model, st, g_rgb, g_depth, g_weights, g_packed, grads)
+        self._mask_frozen(grads)
         return loss
+
+    def frozen_ranges(self):
+        """Merged [offset, offset+length) runs of the flat buffer whose parameters have requires_grad == False
+        (model.freeze / freeze_rest).  The reference hands only `filter(requires_grad)` to Adam (main.py:148-150)."""
+        runs = []
+        for _, p, off, n in self._param_slices():
+            if not p.requires_grad:
+                if runs and runs[-1][0] + runs[-1][1] >= off:
+                    runs[-1][1] = off + n - runs[-1][0]
+                else:
+                    runs.append([off, n])
+        return [tuple(r) for r in runs]
+
+    def _mask_frozen(self, grads):
+        """Frozen parameters take no optimizer step: their gradient and Adam moments are zeroed before the fused Adam, whose
+        update m / (sqrt(v) + eps) is then exactly 0 for them.  The set is read once per graph capture / eager step."""
+        runs = self.frozen_ranges()
+        for off, n in runs:
+            grads[off:off + n].zero_()
+            self.m[off:off + n].zero_()
+            self.v[off:off + n].zero_()
+        self._frozen = runs
 
     def _reduce_and_update(self):
         model = self.model
@@ -255,7 +283,8 @@ class Trainer:
         return g
 
     def _graph_step(self, batch: RayBatch, kw):
-        kw = dict(kw, _use_depth=self.use_depth_loss, _use_nr=self.use_normal_reg, _use_hs=self.use_hard_surface)
+        kw = dict(kw, _use_depth=self.use_depth_loss, _use_nr=self.use_normal_reg, _use_hs=self.use_hard_surface,
+                  _frozen=tuple(self.frozen_ranges()))        # the frozen set is baked into the captured graph
         ready = getattr(batch, "_ready", None)
         if ready is not None:                             # a prefetch()ed staging batch: its H2D copy runs on the copy stream
             torch.cuda.current_stream().wait_event(ready)
@@ -273,14 +302,7 @@ class Trainer:
             if self._opt_state is None:
                 self._opt_state = torch.zeros(4, dtype=torch.float32, device=self.model.flat_params.device)
             self._graph_updates = self.whole_step_graph
-            try:
-                self._graph = self._capture(rkw, self._graph_updates)
-            except Exception:                             # a collective that cannot be captured here: exchange + Adam stay eager
-                if not self._graph_updates:
-                    raise
-                torch.cuda.synchronize()
-                self._graph_updates = False
-                self._graph = self._capture(rkw, False)
+            self._graph = self._capture(rkw, self._graph_updates)
             self._kw = dict(kw)
         if batch is self._static:
             pass

@@ -406,6 +406,15 @@ int bn_debug_gemm_epi(int kind, const void* A, long long lda, const void* B, lon
                       const void* add, const void* mul, float* colsum, int pad_lo, int pad_hi,
                       long long M, int N, long long K, cudaStream_t stream);
 
+/* Unit-test hook: where a per-point activation tensor of a forward call lives inside the caller's MLP workspace
+ * (the layout bn_mlp_workspace_bytes sizes for `n_points`, `flags`).  which 0: the encoding X3 (64 columns),
+ * 1: h_l = sin(.) of trunk layer `layer`, 2: c_l = w0 cos(.) of trunk layer `layer` (training / analytic normals only).
+ * Writes the byte offset from the workspace base and the row pitch in elements (bf16 in BN_PREC_BF16 mode, else fp32);
+ * BN_ERR_ARG when the tensor does not exist for these flags.  Lets tests compare the fused trunk kernel's stored
+ * activations with the reference's per-layer values (models/spsbrdfnerf.py:636-646). */
+int bn_debug_ws_tensor(const bn_mlp* h, int64_t n_points, int flags, int which, int layer, int64_t* offset_bytes,
+                       int64_t* pitch_elems);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,11 +20,30 @@ from typing import List
 
 import torch
 
-REF_ROOT = os.environ.get("BRDFNERF_REF", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")     # written by oracle/stage_ref.py
+
+
+def _pick_root() -> str:
+    """The live read-only tree when it exists (this container), else the byte-identical staged copy of the path's files
+    (oracle/_ref, the GPU box)."""
+    live = os.environ.get("BRDFNERF_REF", "/root/reference")
+    if os.path.isfile(os.path.join(live, "rendering.py")):
+        return live
+    return _STAGED
+
+
+REF_ROOT = _pick_root()
 
 
 def available() -> bool:
     return os.path.isfile(os.path.join(REF_ROOT, "rendering.py"))
+
+
+def kind() -> str:
+    """'live' (/root/reference), 'staged' (oracle/_ref) or 'absent'."""
+    if not available():
+        return "absent"
+    return "staged" if os.path.abspath(REF_ROOT) == os.path.abspath(_STAGED) else "live"
 
 
 _mods = None

@@ -208,8 +208,9 @@ def test_trainer_checkpoint_layout_is_a_lightning_adam_checkpoint():
 
 
 def test_bench_reference_arm_contract_and_no_cpu_fallback():
-    """bench.py on a box without a GPU: the reference arm (oracle port on the host cores) prints ONE JSON line with the
-    contract's keys; the product arm refuses to run (there is no CPU fallback)."""
+    """bench.py on a box without a GPU: the reference arm (the unmodified reference files on the host cores when they are
+    available — live tree here, oracle/_ref on the GPU box — else the oracle port) prints ONE JSON line with the contract's
+    keys, at the SAME 1024-ray step as the product arm; the product arm refuses to run (there is no CPU fallback)."""
     import json
     import subprocess
     import sys
@@ -222,7 +223,10 @@ def test_bench_reference_arm_contract_and_no_cpu_fallback():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "rays/s" and d["higher_is_better"] is True and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    from oracle import ref_harness as RH
+    assert d["cpu_baseline"]["kind"] == ("reference" if RH.kind() != "absent" else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["config"]["rays_per_gpu"] == 1024 and "1024 rays" in d["cpu_baseline"]["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and d["metric"].startswith("train rays/s")
     if not torch.cuda.is_available():
