@@ -629,6 +629,26 @@ __global__ void __launch_bounds__(256) pack_all_kernel(const __grid_constant__ P
   }
 }
 
+// bias blocks of the fused trunk kernels (see mlp_chain.cuh): one thread per (layer row, column) of Wb [L * F, 64]
+__global__ void __launch_bounds__(256) pack_bias_blocks_kernel(const float* __restrict__ params, __nv_bfloat16* __restrict__ Wb,
+                                                               int L, int F, int E, int skip, const long long* __restrict__ offs) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= L * F * 64) return;
+  const int col = idx & 63, row = (idx >> 6) % F, l = idx / (64 * F);
+  const long long w_off = offs[2 * l], b_off = offs[2 * l + 1];
+  float v = 0.f;
+  if (col < E && (l == 0 || l == skip)) {
+    const int kreal = l == 0 ? E : E + F;                    // the encoding is the FIRST E input columns of both layers
+    v = params[w_off + (long long)row * kreal + col];
+  } else if (col == chain::kOneCol) {
+    v = params[b_off + row];
+  } else if (col == chain::kOneCol + 1) {
+    const float b = params[b_off + row];
+    v = b - __bfloat162float(__float2bfloat16(b));
+  }
+  Wb[idx] = __float2bfloat16(v);
+}
+
 template <typename T>
 static int sync_weights_t(bn_mlp* h, const float* params, cudaStream_t s) {
   const bn_mlp_cfg& c = h->cfg;
@@ -650,6 +670,10 @@ static int sync_weights_t(bn_mlp* h, const float* params, cudaStream_t s) {
   if (jobs.n > kMaxPackJobs) { set_error("too many pack jobs"); return BN_ERR_STATE; }
   pack_all_kernel<T><<<dim3(64, jobs.n), 256, 0, s>>>(jobs, params);
   if (int rc = after_launch("pack_all_kernel")) return rc;
+  if (h->bf16 && h->Wb) {
+    pack_bias_blocks_kernel<<<ceil_div(h->L * h->F * 64, 256), 256, 0, s>>>(params, (__nv_bfloat16*)h->Wb, h->L, h->F, h->E, h->skip, h->Wb_offs);
+    if (int rc = after_launch("pack_bias_blocks_kernel")) return rc;
+  }
   h->synced = true;
   return BN_OK;
 }
@@ -665,8 +689,8 @@ static int sigma_chain(bn_mlp* h, const float* params, const float* origins, int
   chain::SigmaChainParams prm;
   for (int l = 0; l < h->L; ++l) {
     if (int rc = tc::make_map_bf16(&prm.wmap[l], h->Wp[l], h->F, h->Kpad[l], h->Kpad[l], 64, 128)) return rc;
-    prm.bias[l] = params + c.b_off[l];
   }
+  if (int rc = tc::make_map_bf16(&prm.bmap, h->Wb, (long long)h->L * h->F, 64, 64, 64, 128)) return rc;
   prm.wsig = params + c.w_off[BN_LIN_SIGMA]; prm.bsig = params + c.b_off[BN_LIN_SIGMA];
   prm.origins = origins; prm.dirs = dirs; prm.z = z; prm.out = out;
   prm.P = (long long)N * S; prm.o_stride = o_stride; prm.d_stride = d_stride; prm.S = S;
@@ -706,13 +730,14 @@ static int train_chain(bn_mlp* h, const float* params, const float* origins, int
     if (int rc = tc::stream_map(&prm.hmap[l], w.H[l], P, h->F, w.Hld[l])) return rc;
     if (keep_c) { if (int rc = tc::make_map_bf16_sw(&prm.cmap[l], w.C[l], P, h->F, h->F, 32, 32, 64)) return rc; }
     else memset(&prm.cmap[l], 0, sizeof(prm.cmap[l]));
-    prm.bias[l] = params + c.b_off[l];
   }
+  if (int rc = tc::make_map_bf16(&prm.bmap, h->Wb, (long long)h->L * h->F, 64, 64, 64, 128)) return rc;
   if (int rc = tc::stream_map(&prm.x3map, w.X3, P, kEncPad, w.ldx3)) return rc;
   prm.origins = origins; prm.dirs = dirs; prm.z = z;
   prm.P = P; prm.o_stride = o_stride; prm.d_stride = d_stride; prm.S = S;
   prm.L = h->L; prm.skip = h->skip; prm.n_freq = c.n_freq_xyz;
   prm.store_c = keep_c ? 1 : 0; prm.h_from = train ? 0 : h->L - 1;
+  prm.trace = h->chain_trace;
   const int n_blocks = (int)ceil_div_ll(P, 256);
   constexpr int smem = chain::chain_smem<true>();
   // experiment knob: one weight stage traded for a second cosine staging box per epilogue warp
@@ -841,7 +866,7 @@ static int forward_t(bn_mlp* h, const float* params, const float* origins, int o
   const long long P = (long long)N * S;
   const bool sig_only = flags & BN_MLP_SIGMA_ONLY;
   if constexpr (std::is_same<T, __nv_bfloat16>::value) {
-    if (sig_only && h->F == chain::kF && h->skip >= 1 && h->L <= chain::kMaxBiasLayers && !h->no_chain)
+    if (sig_only && h->F == chain::kF && h->skip >= 1 && h->L <= chain::kMaxLayers && !h->no_chain)
       return sigma_chain(h, params, origins, o_stride, dirs, d_stride, z, N, S, out, s);
   }
   Ws<T> w; carve<T>(h, P, flags, wsp, &w);
@@ -1085,6 +1110,13 @@ extern "C" __attribute__((visibility("default"))) int bn_mlp_create(const bn_mlp
   h->overlap = getenv("BN_NO_OVERLAP") == nullptr;       // A/B timing aid: serial backward on the caller's stream
   BN_CUDA(cudaMalloc(&h->WsigA, (size_t)64 * h->F * sizeof(__nv_bfloat16)));
   BN_CUDA(cudaMemset(h->WsigA, 0, (size_t)64 * h->F * sizeof(__nv_bfloat16)));
+  if (h->bf16) {
+    BN_CUDA(cudaMalloc(&h->Wb, (size_t)h->L * h->F * 64 * sizeof(__nv_bfloat16)));
+    long long offs[32];
+    for (int l = 0; l < h->L; ++l) { offs[2 * l] = cfg->w_off[BN_LIN_TRUNK0 + l]; offs[2 * l + 1] = cfg->b_off[BN_LIN_TRUNK0 + l]; }
+    BN_CUDA(cudaMalloc(&h->Wb_offs, sizeof(offs)));
+    BN_CUDA(cudaMemcpy(h->Wb_offs, offs, sizeof(long long) * 2 * h->L, cudaMemcpyHostToDevice));
+  }
   *out = h;
   return BN_OK;
 }
@@ -1096,6 +1128,7 @@ extern "C" __attribute__((visibility("default"))) void bn_mlp_destroy(bn_mlp* h)
   for (int l = 0; l < 16; ++l) { if (h->ev_dz[l]) cudaEventDestroy(h->ev_dz[l]); if (h->ev_w[l]) cudaEventDestroy(h->ev_w[l]); }
   for (int i = 0; i < 8; ++i) if (h->ev_h[i]) cudaEventDestroy(h->ev_h[i]);
   cudaFree(h->Wf); cudaFree(h->WfT); cudaFree(h->W1); cudaFree(h->W1T); cudaFree(h->b1cat); cudaFree(h->W2p); cudaFree(h->W2pT); cudaFree(h->Wsig); cudaFree(h->WsigA);
+  cudaFree(h->Wb); cudaFree(h->Wb_offs);
   delete h;
 }
 

@@ -19,6 +19,13 @@
 //              Before layer 0 they evaluate x = o + d z and the positional encoding into K block 0.
 // Shared memory: 9 K blocks x 16 KB activations ([PE | h], so the skip layer reads K = 576 without a concat)
 // + 5 x 16 KB weight ring (4 in the training variant, which also stages the cosines).
+//
+// Biases ride on the tensor core: K block 0 (the encoding, 60 real columns) carries the constant 1 in its pad columns 60
+// and 61, and every layer's weight sequence starts with a [512 x 64] "bias block" Wb_l whose columns 60 / 61 hold
+// bf16(b) and bf16(b - bf16(b)) (the bias to ~2^-17 relative), columns 0..59 the encoding weights of the layers that read
+// the encoding (layer 0, skip layer) and zeros otherwise.  Layers that do not read the encoding issue ONE extra
+// 256 x 256 x 16 MMA per half (the K slice of columns 48..63) — 3 % more tensor work — and the epilogue no longer
+// fetches, broadcasts (32 shuffles per unit) or adds biases: the accumulator IS the pre-activation.
 #pragma once
 #include "gemm_tc.cuh"
 #include "epilogues_tc.cuh"
@@ -32,14 +39,14 @@ constexpr int kF = 512;                 // trunk width this kernel is specialise
 constexpr int kNKB = 1 + kF / 64;       // K blocks of the activation buffer: PE + 8 x 64 features
 constexpr int kKBBytes = 128 * 128;     // one K block of one CTA: 128 rows x 64 bf16
 constexpr int kMaxLayers = 16;
-constexpr int kMaxBiasLayers = 8;       // biases of up to 8 layers are staged in shared memory by the density pass
+constexpr int kOneCol = 60;             // columns 60, 61 of K block 0 hold 1.0: the A operand of the bias MMA
 // weight ring depth: the training variant gives one stage to the cosine staging boxes
 // kCBox2 (experiment, BN_CHAIN_CBOX2=1): the training variant trades one weight stage for a second cosine box per warp
-template <bool kTrain, bool kCBox2 = false> __host__ __device__ constexpr int w_stages() { return (kTrain && kCBox2) ? 3 : 4; }
+template <bool kTrain, bool kCBox2 = false> __host__ __device__ constexpr int w_stages() { return kTrain ? (kCBox2 ? 3 : 4) : 5; }
 
 struct SigmaChainParams {
   CUtensorMap wmap[kMaxLayers];         // packed W_l [F, Kpad_l] bf16, boxes 64 (K) x 128 (rows)
-  const float* bias[kMaxLayers];
+  CUtensorMap bmap;                     // bias blocks Wb [L * F, 64] bf16 (see the header comment), same boxes
   const float* wsig; const float* bsig;
   const float* origins; const float* dirs; const float* z;
   float* out;
@@ -54,44 +61,48 @@ struct SigmaChainParams {
 // one 32 x 32 staging box per epilogue warp); K block 0 (the encoding) goes to X3.
 struct TrainChainParams {
   CUtensorMap wmap[kMaxLayers];
+  CUtensorMap bmap;                     // bias blocks Wb [L * F, 64]
   CUtensorMap hmap[kMaxLayers];         // H_l [P, F] (layer skip-1 lives inside X3, pitch 64 + F)
   CUtensorMap cmap[kMaxLayers];         // C_l [P, F], boxes of 32 columns x 32 rows, 64-byte swizzle
   CUtensorMap x3map;                    // X3 [P, 64] encoding columns
-  const float* bias[kMaxLayers];
   const float* origins; const float* dirs; const float* z;
   long long P;
   int o_stride, d_stride, S, L, skip, n_freq;
   int store_c;                          // 0: inference without analytic normals - no cosines are computed or stored
   int h_from;                           // h_l leaves the SM only for l >= h_from (0 when training, L-1 for inference)
+  long long* trace;                     // diagnostics (bn_debug_chain_trace): clock64() stamps of pair 0's leader CTA, first block
 };
 
 template <bool kTrain> __host__ __device__ constexpr int chain_smem() {
-  // activations + weight ring + (cosine boxes | all biases of the trunk + sigma exchange) + barriers + alignment slack
-  return kNKB * kKBBytes + w_stages<kTrain>() * kKBBytes + (kTrain ? 4 * 4096 : kMaxBiasLayers * kF * 4 + 1024) + 512 + 1024;
+  // activations + weight ring + (cosine boxes | sigma exchange) + barriers + alignment slack
+  return kNKB * kKBBytes + w_stages<kTrain>() * kKBBytes + (kTrain ? 4 * 4096 : 1024) + 512 + 1024;
 }
 constexpr int sigma_chain_smem() { return chain_smem<false>(); }
 
-__device__ __forceinline__ int layer_kb_first(int l, int skip) { return (l == 0 || l == skip) ? 0 : 1; }
+// every layer starts with K block 0 against its bias block; layers that do not read the encoding use only its last K slice
+__device__ __forceinline__ bool layer_reads_enc(int l, int skip) { return l == 0 || l == skip; }
 __device__ __forceinline__ int layer_kb_last(int l) { return l == 0 ? 0 : kNKB - 1; }
 // column of K block kb inside the packed weight matrix of layer l
 __device__ __forceinline__ int layer_wcol(int l, int skip, int kb) { return (l == 0) ? 0 : (l == skip ? kb * 64 : (kb - 1) * 64); }
 
 // ---- weight producer: one [128 x 64] tile of W_l per (block, layer, column half, K block) ----
 template <int STAGES>
-__device__ __forceinline__ void chain_producer(const CUtensorMap* wmap, uint8_t* sW, uint64_t* wfull, uint64_t* wempty,
-                                               int crank, int pair0, int npairs, int n_blocks, int L, int skip, bool noload = false) {
+__device__ __forceinline__ void chain_producer(const CUtensorMap* wmap, const CUtensorMap* bmap, uint8_t* sW, uint64_t* wfull,
+                                               uint64_t* wempty, int crank, int pair0, int npairs, int n_blocks, int L, int skip,
+                                               bool noload = false) {
   int stage = 0; uint32_t phase = 0;
   for (int blk = pair0; blk < n_blocks; blk += npairs)
     for (int l = 0; l < L; ++l)
       for (int n = 0; n < 2; ++n)
-        for (int kb = layer_kb_first(l, skip); kb <= layer_kb_last(l); ++kb) {
+        for (int kb = 0; kb <= layer_kb_last(l); ++kb) {
           mbar_wait(&wempty[stage], phase ^ 1);
           if (noload) {                                  // timing experiment: MMAs run on whatever the slot holds
             if (crank == 0) mbar_expect_tx(&wfull[stage], 0);
           } else {
             if (crank == 0) mbar_expect_tx(&wfull[stage], 2 * kKBBytes);
-            tma_load_2d_pair(sW + stage * kKBBytes, &wmap[l], mapa_u32(smem_u32(&wfull[stage]), 0),
-                             layer_wcol(l, skip, kb), n * 256 + crank * 128);
+            const uint32_t bar = mapa_u32(smem_u32(&wfull[stage]), 0);
+            if (kb == 0) tma_load_2d_pair(sW + stage * kKBBytes, bmap, bar, 0, l * kF + n * 256 + crank * 128);
+            else tma_load_2d_pair(sW + stage * kKBBytes, &wmap[l], bar, layer_wcol(l, skip, kb), n * 256 + crank * 128);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -114,7 +125,8 @@ __device__ __forceinline__ void chain_mma(uint8_t* sAct, uint8_t* sW, uint64_t* 
         const bool tr = trace != nullptr && blk == pair0 && pair0 == 0;
         if (tr) trace[(l * 2 + n) * 16 + 0] = clock64();      // [0] TMEM half free
         bool first = true;
-        for (int kb = layer_kb_first(l, skip); kb <= layer_kb_last(l); ++kb) {
+        const int k_first0 = layer_reads_enc(l, skip) ? 0 : 3;   // K block 0: all of it, or only the slice with the constant 1
+        for (int kb = 0; kb <= layer_kb_last(l); ++kb) {
           if (n == 0 && !(kb == 0 && l > 0)) {          // K block published once per layer (PE: once per block)
             mbar_wait(&act_ready[kb], (ar_ph >> kb) & 1); ar_ph ^= 1u << kb;
             fence_after_sync();
@@ -126,10 +138,11 @@ __device__ __forceinline__ void chain_mma(uint8_t* sAct, uint8_t* sW, uint64_t* 
           const uint32_t b_addr = smem_u32(sW + stage * kKBBytes);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
+            if (kb == 0 && k < k_first0) continue;
             umma_bf16_pair(tmem_base + n * 256, make_desc(a_addr + k * 32, 16, 1024), make_desc(b_addr + k * 32, 16, 1024),
-                           idesc, (first && k == 0) ? 0u : 1u);
+                           idesc, first ? 0u : 1u);
+            first = false;
           }
-          first = false;
           umma_commit_pair(&wempty[stage]);
           // K blocks 1..4 have now been read by both halves of this layer: the first half's epilogue may overwrite
           // them while K blocks 5..8 are still being multiplied, and the next layer starts without a pipeline drain
@@ -153,6 +166,7 @@ __device__ __forceinline__ void encode_row(const float* origins, int o_stride, c
   float e[64];
 #pragma unroll
   for (int i = 0; i < 64; ++i) e[i] = 0.f;
+  e[kOneCol] = 1.0f; e[kOneCol + 1] = 1.0f;            // A operand of the bias MMAs (hi and lo part of every bias)
   if (n_freq == 0) { e[0] = x[0]; e[1] = x[1]; e[2] = x[2]; }
   else {
 #pragma unroll
@@ -176,9 +190,7 @@ __global__ void __launch_bounds__(kThreads, 1) sigma_chain_kernel(const __grid_c
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sAct = smem;                                        // [kNKB][128 rows][128 B], swizzled
   uint8_t* sW = sAct + kNKB * kKBBytes;                        // [kWStages][128 rows of W][128 B]
-  float* sBias = reinterpret_cast<float*>(sW + kWStages * kKBBytes);  // [L][512]: with ~224 KB of smem carved out the L1 is
-                                                                      // too small to keep them, and an L2 round trip per unit is exposed
-  float* sSig = sBias + kMaxBiasLayers * kF;                          // [128] partial sigma of the hsel = 1 warps
+  float* sSig = reinterpret_cast<float*>(sW + kWStages * kKBBytes);   // [128] partial sigma of the hsel = 1 warps
   uint64_t* wfull = reinterpret_cast<uint64_t*>(sSig + 256);
   uint64_t* wempty = wfull + kWStages;
   uint64_t* tfull = wempty + kWStages;
@@ -193,8 +205,10 @@ __global__ void __launch_bounds__(kThreads, 1) sigma_chain_kernel(const __grid_c
   const int n_blocks = (int)((prm.P + 255) / 256);
   const int L = prm.L, skip = prm.skip;
 
-  if (warp == 0 && lane == 0)
+  if (warp == 0 && lane == 0) {
     for (int l = 0; l < L; ++l) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&prm.wmap[l])) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&prm.bmap)) : "memory");
+  }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kWStages; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 16); }     // 8 epilogue warps x 2 CTAs
@@ -204,7 +218,6 @@ __global__ void __launch_bounds__(kThreads, 1) sigma_chain_kernel(const __grid_c
   }
   if (warp == 2) tmem_alloc<true>(tmem_slot, 512);
   pdl_wait();                                                  // the weights may come from the optimizer kernel just before
-  for (int i = threadIdx.x; i < L * kF; i += kThreads) sBias[i] = __ldg(prm.bias[i / kF] + (i % kF));
   fence_before_sync();
   __syncthreads();
   cluster_sync_all();
@@ -212,7 +225,7 @@ __global__ void __launch_bounds__(kThreads, 1) sigma_chain_kernel(const __grid_c
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) chain_producer<kWStages>(prm.wmap, sW, wfull, wempty, crank, pair0, npairs, n_blocks, L, skip, prm.noload != 0);
+    if (lane == 0) chain_producer<kWStages>(prm.wmap, &prm.bmap, sW, wfull, wempty, crank, pair0, npairs, n_blocks, L, skip, prm.noload != 0);
   } else if (warp == 1) {
     if (lane == 0 && crank == 0)
       chain_mma<kWStages>(sAct, sW, wfull, wempty, tfull, tempty, act_ready, kfree, tmem_base, pair0, npairs, n_blocks, L, skip, prm.trace);
@@ -260,13 +273,11 @@ __global__ void __launch_bounds__(kThreads, 1) sigma_chain_kernel(const __grid_c
             if (u < 3) tmem_ld32_issue(tbase + (u + 1) * 64, (u & 1) ? va : vb);
             else { fence_before_sync(); arrive_leader(&tempty[n]); }       // this warp's share of the half is in registers
             const int col0 = n * 256 + u * 64 + hsel * 32;
-            const float4* bp = reinterpret_cast<const float4*>(sBias + l * kF + col0);
-            if (!last) {
+            if (!last) {                 // the accumulator is the pre-activation: the bias came in through the MMA
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const float4 b = bp[j];
-                pk[u][2 * j] = bf_pack(__sinf(w0 * (__uint_as_float(v[4 * j]) + b.x)), __sinf(w0 * (__uint_as_float(v[4 * j + 1]) + b.y)));
-                pk[u][2 * j + 1] = bf_pack(__sinf(w0 * (__uint_as_float(v[4 * j + 2]) + b.z)), __sinf(w0 * (__uint_as_float(v[4 * j + 3]) + b.w)));
+                pk[u][2 * j] = bf_pack(__sinf(w0 * __uint_as_float(v[4 * j])), __sinf(w0 * __uint_as_float(v[4 * j + 1])));
+                pk[u][2 * j + 1] = bf_pack(__sinf(w0 * __uint_as_float(v[4 * j + 2])), __sinf(w0 * __uint_as_float(v[4 * j + 3])));
               }
               if (n == 1) {            // second half: publish K block 5 + u right away
                 uint8_t* kbp = sAct + (5 + u) * kKBBytes;
@@ -280,9 +291,9 @@ __global__ void __launch_bounds__(kThreads, 1) sigma_chain_kernel(const __grid_c
               const float4* wp = reinterpret_cast<const float4*>(prm.wsig + col0);
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const float4 b = bp[j], w = __ldg(wp + j);
-                sig = fmaf(__sinf(w0 * (__uint_as_float(v[4 * j]) + b.x)), w.x, sig); sig = fmaf(__sinf(w0 * (__uint_as_float(v[4 * j + 1]) + b.y)), w.y, sig);
-                sig = fmaf(__sinf(w0 * (__uint_as_float(v[4 * j + 2]) + b.z)), w.z, sig); sig = fmaf(__sinf(w0 * (__uint_as_float(v[4 * j + 3]) + b.w)), w.w, sig);
+                const float4 w = __ldg(wp + j);
+                sig = fmaf(__sinf(w0 * __uint_as_float(v[4 * j])), w.x, sig); sig = fmaf(__sinf(w0 * __uint_as_float(v[4 * j + 1])), w.y, sig);
+                sig = fmaf(__sinf(w0 * __uint_as_float(v[4 * j + 2])), w.z, sig); sig = fmaf(__sinf(w0 * __uint_as_float(v[4 * j + 3])), w.w, sig);
               }
             }
           }
@@ -348,8 +359,10 @@ __global__ void __launch_bounds__(kThreads, 1) train_chain_kernel(const __grid_c
   const int n_blocks = (int)((prm.P + 255) / 256);
   const int L = prm.L, skip = prm.skip;
 
-  if (warp == 0 && lane == 0)
+  if (warp == 0 && lane == 0) {
     for (int l = 0; l < L; ++l) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&prm.wmap[l])) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&prm.bmap)) : "memory");
+  }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kWStages; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 16); }
@@ -366,10 +379,10 @@ __global__ void __launch_bounds__(kThreads, 1) train_chain_kernel(const __grid_c
   pdl_wait();
 
   if (warp == 0) {
-    if (lane == 0) chain_producer<kWStages>(prm.wmap, sW, wfull, wempty, crank, pair0, npairs, n_blocks, L, skip);
+    if (lane == 0) chain_producer<kWStages>(prm.wmap, &prm.bmap, sW, wfull, wempty, crank, pair0, npairs, n_blocks, L, skip);
   } else if (warp == 1) {
     if (lane == 0 && crank == 0)
-      chain_mma<kWStages>(sAct, sW, wfull, wempty, tfull, tempty, act_ready, kfree, tmem_base, pair0, npairs, n_blocks, L, skip);
+      chain_mma<kWStages>(sAct, sW, wfull, wempty, tfull, tempty, act_ready, kfree, tmem_base, pair0, npairs, n_blocks, L, skip, prm.trace);
   } else if (warp >= 4) {
     const int q = warp & 3, hsel = (warp - 4) >> 2;
     const int row = q * 32 + lane;
@@ -401,17 +414,13 @@ __global__ void __launch_bounds__(kThreads, 1) train_chain_kernel(const __grid_c
       }
       arrive_leader(&act_ready[0]);
       for (int l = 0; l < L; ++l) {
-        const float w0 = l == 0 ? 30.0f : 1.0f;
         const bool last = l == L - 1;
         for (int n = 0; n < 2; ++n) {
-          // this half's biases: lane i fetches column i of each of the warp's four units BEFORE waiting for the
-          // accumulator (the L2 round trip hides behind the MMAs) and the unit loop broadcasts them by shuffle —
-          // there is no shared memory left to stage them and no registers for 32 values per lane
-          float breg[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) breg[u] = __ldg(prm.bias[l] + n * 256 + u * 64 + hsel * 32 + lane);
+          const bool tr = prm.trace != nullptr && blk == pair0 && pair0 == 0 && crank == 0 && warp == 4 && lane == 0;
+          if (tr) prm.trace[(l * 2 + n) * 16 + 11] = clock64();   // [11] epilogue starts waiting for the half
           mbar_wait(&tfull[n], tf_ph[n]); tf_ph[n] ^= 1;
           fence_after_sync();
+          if (tr) prm.trace[(l * 2 + n) * 16 + 12] = clock64();   // [12] half complete (tfull)
           uint32_t pk[4][16];
           uint32_t va[32], vb[32];
           const uint32_t tbase = tmem_base + t_lane + n * 256 + hsel * 32;
@@ -423,19 +432,22 @@ __global__ void __launch_bounds__(kThreads, 1) train_chain_kernel(const __grid_c
             if (u < 3) tmem_ld32_issue(tbase + (u + 1) * 64, (u & 1) ? va : vb);
             else { fence_before_sync(); arrive_leader(&tempty[n]); }
             const int col0 = n * 256 + u * 64 + hsel * 32;
+            // the accumulator is the pre-activation (bias added by the tensor core): per element one range reduction feeds
+            // both MUFU.SIN and MUFU.COS; w0 = 30 only exists in layer 0, every other layer skips both multiplies
             uint32_t pc[16];
+            if (l == 0) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 b;
-              b.x = __shfl_sync(0xffffffffu, breg[u], 4 * j); b.y = __shfl_sync(0xffffffffu, breg[u], 4 * j + 1);
-              b.z = __shfl_sync(0xffffffffu, breg[u], 4 * j + 2); b.w = __shfl_sync(0xffffffffu, breg[u], 4 * j + 3);
-              const float a0 = w0 * (__uint_as_float(v[4 * j]) + b.x), a1 = w0 * (__uint_as_float(v[4 * j + 1]) + b.y);
-              const float a2 = w0 * (__uint_as_float(v[4 * j + 2]) + b.z), a3 = w0 * (__uint_as_float(v[4 * j + 3]) + b.w);
-              pk[u][2 * j] = bf_pack(__sinf(a0), __sinf(a1));
-              pk[u][2 * j + 1] = bf_pack(__sinf(a2), __sinf(a3));
-              if (prm.store_c) {
-                pc[2 * j] = bf_pack(w0 * __cosf(a0), w0 * __cosf(a1));
-                pc[2 * j + 1] = bf_pack(w0 * __cosf(a2), w0 * __cosf(a3));
+              for (int j = 0; j < 16; ++j) {
+                const float a0 = 30.0f * __uint_as_float(v[2 * j]), a1 = 30.0f * __uint_as_float(v[2 * j + 1]);
+                pk[u][j] = bf_pack(__sinf(a0), __sinf(a1));
+                if (prm.store_c) pc[j] = bf_pack(30.0f * __cosf(a0), 30.0f * __cosf(a1));
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float a0 = __uint_as_float(v[2 * j]), a1 = __uint_as_float(v[2 * j + 1]);
+                pk[u][j] = bf_pack(__sinf(a0), __sinf(a1));
+                if (prm.store_c) pc[j] = bf_pack(__cosf(a0), __cosf(a1));
               }
             }
             uint8_t* box = cbox + (kCBox2 ? (cu & 1) * 2048 : 0);
@@ -461,9 +473,11 @@ __global__ void __launch_bounds__(kThreads, 1) train_chain_kernel(const __grid_c
             if (lane == 0 && prm.store_c) { tma_store_2d(&prm.cmap[l], box, col0, grow0); bulk_commit(); }
             if (n == 1 && !last) arrive_leader(&act_ready[5 + u]);
           }
+          if (tr) prm.trace[(l * 2 + n) * 16 + 13] = clock64();   // [13] the half's four units are through the MUFU / cosine stores
           if (n == 0) {
             // in place: K blocks 1..4 feed the second half's MMAs until its fourth K block has retired
             mbar_wait(kfree, kf_ph); kf_ph ^= 1;
+            if (tr) prm.trace[(l * 2 + n) * 16 + 14] = clock64(); // [14] in-place hazard cleared
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               uint8_t* kbp = sAct + (1 + u) * kKBBytes;

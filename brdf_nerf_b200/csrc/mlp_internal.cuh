@@ -64,6 +64,9 @@ struct bn_mlp {
   void* W2p;                    // [n_blocks*HH, 64] bf16: second-layer head weights as the B operand of the GHD GEMM
   void* W2pT; void* Wsig;       // [64, n_blocks*HH], [64, F] bf16: the same weights / w_sigma as B operands of the forward heads GEMMs
   void* WsigA;                  // [64, F] bf16, row 0 = w_sigma: density of a trunk-only call (bn_mlp_trunk_forward)
+  long long* Wb_offs;           // device: (weight, bias) offsets of the trunk layers in the flat parameter buffer
+  void* Wb;                     // [L * F, 64] bf16 bias blocks of the fused trunk kernels (mlp_chain.cuh): cols 0..59 = encoding
+                                // weights of layer 0 / the skip layer (zero elsewhere), col 60 = bf16(b), col 61 = bf16(b - col 60)
   int n_blocks;
   int blk_lin0[bn::kMaxBlocks], blk_lin2[bn::kMaxBlocks], blk_head[bn::kMaxBlocks];
   bool synced;

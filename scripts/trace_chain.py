@@ -1,5 +1,6 @@
-"""Timeline of the fused density pass (mlp_chain.cuh): clock64() stamps of the first 256-point block of CTA pair 0.
-    python scripts/trace_chain.py      prints, per layer and column half, cycles relative to the start of layer 0"""
+"""Timeline of the fused trunk kernels (mlp_chain.cuh): clock64() stamps of the first 256-point block of CTA pair 0.
+    python scripts/trace_chain.py [train]     density pass (default) or the TRAINING forward (h_l / c_l stored);
+                                              prints, per layer and column half, cycles relative to the start of layer 0"""
 import ctypes as C
 import os
 import sys
@@ -24,9 +25,17 @@ def main():
     torch.manual_seed(0)
     m = load_model(args, precision="bf16").to(dev)
     m.sync_weights()
-    sig = torch.empty((n, S), dtype=torch.float32, device=dev)
-    ws = m.workspace(n * S, L.MLP_SIGMA_ONLY, tag="ws_sigma")
-    fn = lambda: ops.mlp_forward(m, rays[:, 0:3], 11, rays[:, 3:6], 11, z, L.MLP_SIGMA_ONLY, sig, 1, ws)
+    train = len(sys.argv) > 1 and sys.argv[1] == "train"
+    if train:
+        flags = m.mlp_flags(train=True)
+        sig = torch.empty((n, S), dtype=torch.float32, device=dev)
+        ws = m.workspace(n * S, flags, tag="ws_train")
+        fn = lambda: ops.mlp_trunk_forward(m, rays[:, 0:3], 11, rays[:, 3:6], 11, z, flags, n * S, 0, sig, ws)
+    else:
+        sig = torch.empty((n, S), dtype=torch.float32, device=dev)
+        ws = m.workspace(n * S, L.MLP_SIGMA_ONLY, tag="ws_sigma")
+        fn = lambda: ops.mlp_forward(m, rays[:, 0:3], 11, rays[:, 3:6], 11, z, L.MLP_SIGMA_ONLY, sig, 1, ws)
+    print("kernel:", "chain::train_chain_kernel (training forward)" if train else "chain::sigma_chain_kernel (density pass)")
     for _ in range(3):
         fn()
     buf = torch.zeros(16 * 2 * 16, dtype=torch.int64, device=dev)
@@ -45,7 +54,7 @@ def main():
             print(f"layer {l} half {h}: " + "  ".join(f"{k}={v}" for k, v in row.items()))
         tf1 = int(t[l, 1, 12]) - t0
         if prev_tfull1 is not None:
-            print(f"   -> layer period (tfull[1] to tfull[1]) = {tf1 - prev_tfull1} cycles (MMA floor 8192)")
+            print(f"   -> layer period (tfull[1] to tfull[1]) = {tf1 - prev_tfull1} cycles (MMA floor 8192 nominal, ~12500 at the measured 195 cycles per pair-MMA)")
         prev_tfull1 = tf1
 
 
