@@ -144,9 +144,13 @@ __device__ __forceinline__ void chain_mma(uint8_t* sAct, uint8_t* sW, uint64_t* 
             first = false;
           }
           umma_commit_pair(&wempty[stage]);
-          // K blocks 1..4 have now been read by both halves of this layer: the first half's epilogue may overwrite
-          // them while K blocks 5..8 are still being multiplied, and the next layer starts without a pipeline drain
-          if (n == 1 && (kb == 4 || (kb == layer_kb_last(l) && kb < 4))) umma_commit_pair(kfree);
+          // K block kb (1..4) has now been read by both halves of this layer: the first half's epilogue may overwrite it
+          // (one barrier per K block, so that its units publish their results one by one while K blocks 5..8 are still
+          // being multiplied); a layer that reads no activation K block at all (layer 0) releases the four at once
+          if (n == 1) {
+            if (kb >= 1 && kb <= 4) umma_commit_pair(&kfree[kb - 1]);
+            else if (kb == 0 && layer_kb_last(l) == 0) { for (int j = 0; j < 4; ++j) umma_commit_pair(&kfree[j]); }
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit_pair(&tfull[n]);
@@ -196,8 +200,8 @@ __global__ void __launch_bounds__(kThreads, 1) sigma_chain_kernel(const __grid_c
   uint64_t* tfull = wempty + kWStages;
   uint64_t* tempty = tfull + 2;
   uint64_t* act_ready = tempty + 2;                            // [kNKB]
-  uint64_t* kfree = act_ready + kNKB;                          // K blocks 1..4 of the current layer are no longer read
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kfree + 1);
+  uint64_t* kfree = act_ready + kNKB;                          // [4]: K block 1 + j of the current layer is no longer read
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kfree + 4);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int crank = (int)cluster_ctarank();
@@ -213,7 +217,7 @@ __global__ void __launch_bounds__(kThreads, 1) sigma_chain_kernel(const __grid_c
     for (int s = 0; s < kWStages; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 16); }     // 8 epilogue warps x 2 CTAs
     for (int s = 0; s < kNKB; ++s) mbar_init(&act_ready[s], 16);
-    mbar_init(kfree, 1);
+    for (int s = 0; s < 4; ++s) mbar_init(&kfree[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) tmem_alloc<true>(tmem_slot, 512);
@@ -261,11 +265,9 @@ __global__ void __launch_bounds__(kThreads, 1) sigma_chain_kernel(const __grid_c
           fence_after_sync();
           if (tr) prm.trace[(l * 2 + n) * 16 + 12] = clock64();   // [12] half complete (tfull)
           // software-pipelined TMEM reads: unit u+1 is in flight while unit u goes through the MUFU
-          uint32_t pk[4][16];
           uint32_t va[32], vb[32];
           const uint32_t tbase = tmem_base + t_lane + n * 256 + hsel * 32;
           tmem_ld32_issue(tbase, va);
-          if (!last && n == 1) { /* every MMA of this layer has retired (tfull[1]): K blocks may be overwritten at once */ }
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             tmem_wait_ld();
@@ -274,19 +276,19 @@ __global__ void __launch_bounds__(kThreads, 1) sigma_chain_kernel(const __grid_c
             else { fence_before_sync(); arrive_leader(&tempty[n]); }       // this warp's share of the half is in registers
             const int col0 = n * 256 + u * 64 + hsel * 32;
             if (!last) {                 // the accumulator is the pre-activation: the bias came in through the MMA
+              uint32_t pk[16];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                pk[u][2 * j] = bf_pack(__sinf(w0 * __uint_as_float(v[4 * j])), __sinf(w0 * __uint_as_float(v[4 * j + 1])));
-                pk[u][2 * j + 1] = bf_pack(__sinf(w0 * __uint_as_float(v[4 * j + 2])), __sinf(w0 * __uint_as_float(v[4 * j + 3])));
-              }
-              if (n == 1) {            // second half: publish K block 5 + u right away
-                uint8_t* kbp = sAct + (5 + u) * kKBBytes;
+              for (int j = 0; j < 16; ++j)
+                pk[j] = bf_pack(__sinf(w0 * __uint_as_float(v[2 * j])), __sinf(w0 * __uint_as_float(v[2 * j + 1])));
+              // in place: the unit becomes K block 1 + 4n + u of the next layer.  Second half: every MMA of this layer has
+              // retired (tfull[1]).  First half: K block 1 + u still feeds the second half's MMAs until kfree[u]
+              if (n == 0) mbar_wait(&kfree[u], kf_ph);
+              uint8_t* kbp = sAct + (1 + 4 * n + u) * kKBBytes;
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  sts128(kbp + row_off + (((hsel * 4 + j) << 4) ^ swz), pk[u][4 * j], pk[u][4 * j + 1], pk[u][4 * j + 2], pk[u][4 * j + 3]);
-                fence_async_smem();
-                arrive_leader(&act_ready[5 + u]);
-              }
+              for (int j = 0; j < 4; ++j)
+                sts128(kbp + row_off + (((hsel * 4 + j) << 4) ^ swz), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+              fence_async_smem();
+              arrive_leader(&act_ready[1 + 4 * n + u]);
             } else {
               const float4* wp = reinterpret_cast<const float4*>(prm.wsig + col0);
 #pragma unroll
@@ -295,26 +297,11 @@ __global__ void __launch_bounds__(kThreads, 1) sigma_chain_kernel(const __grid_c
                 sig = fmaf(__sinf(w0 * __uint_as_float(v[4 * j])), w.x, sig); sig = fmaf(__sinf(w0 * __uint_as_float(v[4 * j + 1])), w.y, sig);
                 sig = fmaf(__sinf(w0 * __uint_as_float(v[4 * j + 2])), w.z, sig); sig = fmaf(__sinf(w0 * __uint_as_float(v[4 * j + 3])), w.w, sig);
               }
+              if (n == 0) mbar_wait(&kfree[u], kf_ph);     // keep the barrier phases in step with the issuer
             }
           }
+          if (n == 0) kf_ph ^= 1;
           if (tr) prm.trace[(l * 2 + n) * 16 + 13] = clock64();   // [13] the half's four units are through the MUFU
-          if (n == 0) {
-            // in place: K blocks 1..4 feed the second half's MMAs until its fourth K block has retired
-            mbar_wait(kfree, kf_ph); kf_ph ^= 1;
-            if (tr) prm.trace[(l * 2 + n) * 16 + 14] = clock64(); // [14] in-place hazard cleared
-          }
-          if (!last && n == 0) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              uint8_t* kbp = sAct + (1 + u) * kKBBytes;
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                sts128(kbp + row_off + (((hsel * 4 + j) << 4) ^ swz), pk[u][4 * j], pk[u][4 * j + 1], pk[u][4 * j + 2], pk[u][4 * j + 3]);
-            }
-            fence_async_smem();
-#pragma unroll
-            for (int u = 0; u < 4; ++u) arrive_leader(&act_ready[1 + u]);
-          }
         }
       }
       // ---- sigma = softplus(w_sigma . h_{L-1} + b): the two warps of a quadrant hold half of the columns each ----
@@ -350,8 +337,8 @@ __global__ void __launch_bounds__(kThreads, 1) train_chain_kernel(const __grid_c
   uint64_t* tfull = wempty + kWStages;
   uint64_t* tempty = tfull + 2;
   uint64_t* act_ready = tempty + 2;
-  uint64_t* kfree = act_ready + kNKB;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kfree + 1);
+  uint64_t* kfree = act_ready + kNKB;                          // [4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kfree + 4);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int crank = (int)cluster_ctarank();
@@ -367,7 +354,7 @@ __global__ void __launch_bounds__(kThreads, 1) train_chain_kernel(const __grid_c
     for (int s = 0; s < kWStages; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 16); }
     for (int s = 0; s < kNKB; ++s) mbar_init(&act_ready[s], 16);
-    mbar_init(kfree, 1);
+    for (int s = 0; s < 4; ++s) mbar_init(&kfree[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) tmem_alloc<true>(tmem_slot, 512);
@@ -421,10 +408,10 @@ __global__ void __launch_bounds__(kThreads, 1) train_chain_kernel(const __grid_c
           mbar_wait(&tfull[n], tf_ph[n]); tf_ph[n] ^= 1;
           fence_after_sync();
           if (tr) prm.trace[(l * 2 + n) * 16 + 12] = clock64();   // [12] half complete (tfull)
-          uint32_t pk[4][16];
           uint32_t va[32], vb[32];
           const uint32_t tbase = tmem_base + t_lane + n * 256 + hsel * 32;
           tmem_ld32_issue(tbase, va);
+          const bool store_h = l >= prm.h_from;
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             tmem_wait_ld();
@@ -434,73 +421,54 @@ __global__ void __launch_bounds__(kThreads, 1) train_chain_kernel(const __grid_c
             const int col0 = n * 256 + u * 64 + hsel * 32;
             // the accumulator is the pre-activation (bias added by the tensor core): per element one range reduction feeds
             // both MUFU.SIN and MUFU.COS; w0 = 30 only exists in layer 0, every other layer skips both multiplies
-            uint32_t pc[16];
+            uint32_t pk[16], pc[16];
             if (l == 0) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
                 const float a0 = 30.0f * __uint_as_float(v[2 * j]), a1 = 30.0f * __uint_as_float(v[2 * j + 1]);
-                pk[u][j] = bf_pack(__sinf(a0), __sinf(a1));
+                pk[j] = bf_pack(__sinf(a0), __sinf(a1));
                 if (prm.store_c) pc[j] = bf_pack(30.0f * __cosf(a0), 30.0f * __cosf(a1));
               }
             } else {
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
                 const float a0 = __uint_as_float(v[2 * j]), a1 = __uint_as_float(v[2 * j + 1]);
-                pk[u][j] = bf_pack(__sinf(a0), __sinf(a1));
+                pk[j] = bf_pack(__sinf(a0), __sinf(a1));
                 if (prm.store_c) pc[j] = bf_pack(__cosf(a0), __cosf(a1));
               }
             }
             uint8_t* box = cbox + (kCBox2 ? (cu & 1) * 2048 : 0);
+            // this warp's earlier TMA stores have read their shared memory: the cosine box of the previous unit and, for the
+            // quadrant leader, the h_l box it stored then (with two cosine boxes only the store before the previous one
+            // must be done — except for the leader, whose wait also covers that h_l box)
+            if (lane == 0 && (prm.store_c || leader)) { if (kCBox2 && !leader) bulk_wait_read1(); else bulk_wait_read0(); }
+            __syncwarp();
             if (prm.store_c) {
-              // this box was read out by the TMA: with two boxes only the store before the previous one must be done — except
-              // on the leader's first unit of a half, whose wait also covers the h_l boxes it committed at the end of the
-              // previous half (they must be read out before those K blocks are rewritten)
-              if (lane == 0) { if (kCBox2 && !(hsel == 0 && u == 0)) bulk_wait_read1(); else bulk_wait_read0(); }
-              __syncwarp();
 #pragma unroll
               for (int j = 0; j < 4; ++j)
                 sts128(box + crow_off + ((j << 4) ^ cswz), pc[4 * j], pc[4 * j + 1], pc[4 * j + 2], pc[4 * j + 3]);
               ++cu;
             }
-            if (n == 1) {                                    // every MMA of this layer has retired: publish K block 5+u now
-              uint8_t* kbp = sAct + (5 + u) * kKBBytes;
+            // in place: the unit becomes K block 1 + 4n + u of the next layer.  Second half: every MMA of this layer has
+            // retired (tfull[1]).  First half: K block 1 + u still feeds the second half's MMAs until kfree[u]
+            if (n == 0) mbar_wait(&kfree[u], kf_ph);
+            uint8_t* kbp = sAct + (1 + 4 * n + u) * kKBBytes;
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                sts128(kbp + row_off + (((hsel * 4 + j) << 4) ^ swz), pk[u][4 * j], pk[u][4 * j + 1], pk[u][4 * j + 2], pk[u][4 * j + 3]);
-            }
+            for (int j = 0; j < 4; ++j)
+              sts128(kbp + row_off + (((hsel * 4 + j) << 4) ^ swz), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
             fence_async_smem();
             __syncwarp();
             if (lane == 0 && prm.store_c) { tma_store_2d(&prm.cmap[l], box, col0, grow0); bulk_commit(); }
-            if (n == 1 && !last) arrive_leader(&act_ready[5 + u]);
-          }
-          if (tr) prm.trace[(l * 2 + n) * 16 + 13] = clock64();   // [13] the half's four units are through the MUFU / cosine stores
-          if (n == 0) {
-            // in place: K blocks 1..4 feed the second half's MMAs until its fourth K block has retired
-            mbar_wait(kfree, kf_ph); kf_ph ^= 1;
-            if (tr) prm.trace[(l * 2 + n) * 16 + 14] = clock64(); // [14] in-place hazard cleared
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              uint8_t* kbp = sAct + (1 + u) * kKBBytes;
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                sts128(kbp + row_off + (((hsel * 4 + j) << 4) ^ swz), pk[u][4 * j], pk[u][4 * j + 1], pk[u][4 * j + 2], pk[u][4 * j + 3]);
-            }
-            fence_async_smem();
-            if (!last) {
-#pragma unroll
-              for (int u = 0; u < 4; ++u) arrive_leader(&act_ready[1 + u]);
+            if (!last) arrive_leader(&act_ready[1 + 4 * n + u]);
+            if (store_h) {
+              // h_l of this unit: both warps of the quadrant have written their 32 columns -> one 64-column box, now,
+              // instead of a 64 KB burst of stores at the end of the half that the weight loads would queue behind
+              named_bar_sync(1 + q, 64);
+              if (leader) { tma_store_2d(&prm.hmap[l], kbp + q * 4096, n * 256 + u * 64, grow0); bulk_commit(); }
             }
           }
-          // h_l of this half: both warps of the quadrant have written their columns -> four 64-column boxes.
-          // (The leader waits for its stores to be read out at its next unit, and the next barrier of this kind
-          // precedes every overwrite of these K blocks by the other warp.)
-          named_bar_sync(1 + q, 64);
-          if (leader && l >= prm.h_from) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              tma_store_2d(&prm.hmap[l], sAct + (1 + n * 4 + u) * kKBBytes + q * 4096, n * 256 + u * 64, grow0);
-            bulk_commit();
-          }
+          if (n == 0) kf_ph ^= 1;
+          if (tr) prm.trace[(l * 2 + n) * 16 + 13] = clock64();   // [13] the half's four units are through the MUFU / stores
         }
       }
     }

@@ -98,9 +98,45 @@ def part2():
                 print(f"   drift bf16 - fp32          {[round(b - a, 3) for a, b in zip(r['fp32'][1], r['bf16'][1])]}", flush=True)
 
 
+def part3():
+    """Gentler BRDF stage from a COMMON fp32-pretrained checkpoint: is there a protocol whose fp32-vs-fp32 floor is below
+    0.1 dB, so that the north-star criterion can be resolved?  lr of the BRDF stage 5e-4 (reference default), 1e-4, 2e-5."""
+    import copy
+    n = 256
+    for cfg, kw in CASES.items():
+        for seed in (0, 1):
+            batch = make_rays(n, seed=20240912 + seed, depth_supervision=True).to(dev)
+            evs = [mk_draws(n, 9999 + seed), mk_draws(n, 7777 + seed)]
+            args = named_config(cfg, ds_lambda=10.0)
+            torch.manual_seed(seed)
+            model = load_model(args, precision="fp32").to(dev)
+            tr = Trainer(model, args)
+            for i in range(150):
+                tr.step(batch, draws=mk_draws(n, 1000 * seed + i, with_gt=True))
+            ckpt = copy.deepcopy(tr.state_dict())
+            for lr in (5e-4, 1e-4, 2e-5):
+                res = {}
+                for tag, prec in (("fp32", "fp32"), ("fp32b", "fp32"), ("bf16", "bf16")):
+                    torch.manual_seed(seed)
+                    m = load_model(args, precision=prec).to(dev)
+                    t2 = Trainer(m, args)
+                    t2.load_state_dict(ckpt)
+                    t2.lr = lr
+                    curve = []
+                    for i in range(60):
+                        t2.step(batch, draws=mk_draws(n, 1000 * seed + 500 + i, with_gt=True), **kw)
+                        if (i + 1) % 20 == 0:
+                            curve.append(round(psnr(m, args, batch, evs, kw), 3))
+                    res[tag] = curve
+                print(f"{cfg} seed {seed} lr {lr:g}: fp32 {res['fp32']}  floor {[round(a - b, 3) for a, b in zip(res['fp32b'], res['fp32'])]}"
+                      f"  drift {[round(a - b, 3) for a, b in zip(res['bf16'], res['fp32'])]}", flush=True)
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     if which in ("1", "all"):
         part1()
     if which in ("2", "all"):
         part2()
+    if which in ("3", "all"):
+        part3()
