@@ -354,6 +354,55 @@ def run_ours(opts):
     # kernels of this library inside the timed region: eager launches counted by the library itself, plus the
     # kernel nodes every CUDA-graph replay executes (counted once, at capture time)
     launches = (lib.bn_launch_count() - lc0) + opts.steps * getattr(trainer, "graph_launches", 0)
+    mark_main = clocks.mark() if clocks else 0
+    # ---- roofline leg: per-launch CUDA-event timing of the GEMM family on the launching stream, taken right after the
+    # timed steps (same thermal state: before the e2e and the seconds-long sustained leg push the GPU into its power cap) ----
+    roof = None
+    if rank == 0:
+        peaks = _peaks()
+        lib.bn_profile_enable.restype = C.c_int
+        lib.bn_profile_enable(1)
+        eager = Trainer(model, args, world_size=1, use_graph=False)
+        eager.m, eager.v, eager.step_count = trainer.m, trainer.v, trainer.step_count
+        nprof = 3
+        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pe0.record()
+        for _ in range(nprof):
+            eager.step(batch)
+        pe1.record()
+        torch.cuda.synchronize()
+        ms_eager = pe0.elapsed_time(pe1) / nprof      # the profiled steps themselves (eager launches + per-launch events)
+        cnt = (C.c_longlong * 3)(); tms = (C.c_double * 3)(); work = (C.c_double * 3)()
+        lib.bn_profile_collect(3, cnt, tms, work)
+        lib.bn_profile_enable(0)
+        gemm_ms = sum(tms) / nprof
+        alg = mlp_flops_per_ray(args, args.n_samples, args.n_samples + args.guided_samples) * RAYS_PER_GPU
+        alg_shared = mlp_flops_per_ray(args, args.n_samples, args.n_samples + args.guided_samples, shared_trunk=True) * RAYS_PER_GPU
+        gemm_flops = sum(work) / nprof
+        achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+        kind = lambda i: {"launches": cnt[i] / nprof, "ms": tms[i] / nprof, "tflops": work[i] / max(tms[i], 1e-9) / 1e9}
+        chain_tf = work[2] / max(tms[2], 1e-9) / 1e9
+        # the dominant kernel of the step: the fused PE + 8-layer SIREN trunk forward (chain::train_chain_kernel)
+        # denominator: the BURST cuBLAS figure — the profiled region is three eager steps (~10 ms), nowhere near the seconds it
+        # takes to reach the power cap; the fraction against the sustained figure is given beside it
+        roof = {"bound": "tensor", "kernel": "bn::chain::train_chain_kernel (fused PE + 8 SIREN layers, forward, writes h_l / cos_l for the backward)",
+                "achieved": chain_tf, "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": chain_tf / peaks["tf_burst"],
+                "frac_of_sustained_peak": chain_tf / peaks["tf_sust"],
+                "peak_kind": f"{peaks['src']} burst bf16 cuBLAS (kernel timed per launch inside a ~10 ms region; sustained peak {peaks['tf_sust']})",
+                "traffic": NCU_CHAIN_DRAM_BYTES_PER_LAUNCH, "traffic_note": NCU_TRAFFIC_NOTE,
+                "launches_per_step": cnt[2] / nprof, "us_per_launch": 1e3 * tms[2] / max(cnt[2], 1),
+                "share_of_step": tms[2] / nprof / ms,      # of the timed (graph-replayed) step; compare with the ncu launch list
+
+                "all_tcgen05": {"kernel": "every tcgen05 launch of a step (chain kernels + gemm_tc_kernel fwd/dgrad/wgrad)",
+                                "achieved": achieved, "frac": achieved / peaks["tf_burst"], "frac_of_sustained_peak": achieved / peaks["tf_sust"],
+                                "launches_per_step": sum(cnt) / nprof, "ms_per_step": gemm_ms, "share_of_step": gemm_ms / ms,
+                                "share_note": "per-launch times are taken with the backward serialised (no concurrent weight-gradient stream), "
+                                              "the timed step overlaps them: the sum may exceed the step",
+                                "profiled_step_ms": ms_eager,
+                                "executed_gflop_per_step": gemm_flops / 1e9, "algorithmic_gflop_per_step_shared_trunk": alg_shared / 1e9,
+                                "reference_gflop_per_step": alg / 1e9,
+                                "by_kind": {"chain_fwd": kind(2), "tn_fwd_dgrad": kind(0), "nt_wgrad": kind(1)}}}
+    total_rays = RAYS_PER_GPU * world
     # ---- end to end through the public API: every step's batch starts in pinned host memory and is copied into the device
     # (H2D), every step's loss is read back into host memory (D2H), both inside the timed region.  --feed inline (default):
     # both copies are issued on the compute stream between two graph replays; --feed prefetch: Trainer.prefetch() copies batch
@@ -414,7 +463,7 @@ def run_ours(opts):
     clk_sus = None
     if clocks:
         clocks.stop()
-        clk = clocks.summary(mark0, mark1)
+        clk = clocks.summary(mark0, mark_main)
         clk_sus = clocks.summary(mark1, mark2) if ms_sus is not None else None
     else:
         clk = None
@@ -423,54 +472,7 @@ def run_ours(opts):
         if world > 1:
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         ms_sus = float(t[0])
-    total_rays = RAYS_PER_GPU * world
 
-    # ---- roofline leg: per-launch CUDA-event timing of the GEMM family on the launching stream ----
-    roof = None
-    if rank == 0:
-        peaks = _peaks()
-        lib.bn_profile_enable.restype = C.c_int
-        lib.bn_profile_enable(1)
-        eager = Trainer(model, args, world_size=1, use_graph=False)
-        eager.m, eager.v, eager.step_count = trainer.m, trainer.v, trainer.step_count
-        nprof = 3
-        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        pe0.record()
-        for _ in range(nprof):
-            eager.step(batch)
-        pe1.record()
-        torch.cuda.synchronize()
-        ms_eager = pe0.elapsed_time(pe1) / nprof      # the profiled steps themselves (eager launches + per-launch events)
-        cnt = (C.c_longlong * 3)(); tms = (C.c_double * 3)(); work = (C.c_double * 3)()
-        lib.bn_profile_collect(3, cnt, tms, work)
-        lib.bn_profile_enable(0)
-        gemm_ms = sum(tms) / nprof
-        alg = mlp_flops_per_ray(args, args.n_samples, args.n_samples + args.guided_samples) * RAYS_PER_GPU
-        alg_shared = mlp_flops_per_ray(args, args.n_samples, args.n_samples + args.guided_samples, shared_trunk=True) * RAYS_PER_GPU
-        gemm_flops = sum(work) / nprof
-        achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-        kind = lambda i: {"launches": cnt[i] / nprof, "ms": tms[i] / nprof, "tflops": work[i] / max(tms[i], 1e-9) / 1e9}
-        chain_tf = work[2] / max(tms[2], 1e-9) / 1e9
-        # the dominant kernel of the step: the fused PE + 8-layer SIREN trunk forward (chain::train_chain_kernel)
-        # denominator: the BURST cuBLAS figure — the profiled region is three eager steps (~10 ms), nowhere near the seconds it
-        # takes to reach the power cap; the fraction against the sustained figure is given beside it
-        roof = {"bound": "tensor", "kernel": "bn::chain::train_chain_kernel (fused PE + 8 SIREN layers, forward, writes h_l / cos_l for the backward)",
-                "achieved": chain_tf, "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": chain_tf / peaks["tf_burst"],
-                "frac_of_sustained_peak": chain_tf / peaks["tf_sust"],
-                "peak_kind": f"{peaks['src']} burst bf16 cuBLAS (kernel timed per launch inside a ~10 ms region; sustained peak {peaks['tf_sust']})",
-                "traffic": NCU_CHAIN_DRAM_BYTES_PER_LAUNCH, "traffic_note": NCU_TRAFFIC_NOTE,
-                "launches_per_step": cnt[2] / nprof, "us_per_launch": 1e3 * tms[2] / max(cnt[2], 1),
-                "share_of_step": tms[2] / nprof / ms,      # of the timed (graph-replayed) step; compare with the ncu launch list
-
-                "all_tcgen05": {"kernel": "every tcgen05 launch of a step (chain kernels + gemm_tc_kernel fwd/dgrad/wgrad)",
-                                "achieved": achieved, "frac": achieved / peaks["tf_burst"], "frac_of_sustained_peak": achieved / peaks["tf_sust"],
-                                "launches_per_step": sum(cnt) / nprof, "ms_per_step": gemm_ms, "share_of_step": gemm_ms / ms,
-                                "share_note": "per-launch times are taken with the backward serialised (no concurrent weight-gradient stream), "
-                                              "the timed step overlaps them: the sum may exceed the step",
-                                "profiled_step_ms": ms_eager,
-                                "executed_gflop_per_step": gemm_flops / 1e9, "algorithmic_gflop_per_step_shared_trunk": alg_shared / 1e9,
-                                "reference_gflop_per_step": alg / 1e9,
-                                "by_kind": {"chain_fwd": kind(2), "tn_fwd_dgrad": kind(0), "nt_wgrad": kind(1)}}}
     # ---- HBM leg: the compositing kernels (K-C) at inference-chunk size, GB/s against the measured copy peak ----
     roof_hbm = None
     if rank == 0 and not opts.no_composite:

@@ -410,65 +410,102 @@ __global__ void __launch_bounds__(kThreads, 1) train_chain_kernel(const __grid_c
           if (tr) prm.trace[(l * 2 + n) * 16 + 12] = clock64();   // [12] half complete (tfull)
           uint32_t va[32], vb[32];
           const uint32_t tbase = tmem_base + t_lane + n * 256 + hsel * 32;
-          tmem_ld32_issue(tbase, va);
           const bool store_h = l >= prm.h_from;
+          const bool l0 = l == 0;
+          // ---- cosine of one unit: registers -> this warp's staging box -> TMA (own bulk group) ----
+          auto store_cos = [&](const uint32_t (&v)[32], int u) {
+            uint32_t pc[16];
+            if (l0) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            tmem_wait_ld();
-            uint32_t (&v)[32] = (u & 1) ? vb : va;
-            if (u < 3) tmem_ld32_issue(tbase + (u + 1) * 64, (u & 1) ? va : vb);
-            else { fence_before_sync(); arrive_leader(&tempty[n]); }
-            const int col0 = n * 256 + u * 64 + hsel * 32;
-            // the accumulator is the pre-activation (bias added by the tensor core): per element one range reduction feeds
-            // both MUFU.SIN and MUFU.COS; w0 = 30 only exists in layer 0, every other layer skips both multiplies
-            uint32_t pk[16], pc[16];
-            if (l == 0) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float a0 = 30.0f * __uint_as_float(v[2 * j]), a1 = 30.0f * __uint_as_float(v[2 * j + 1]);
-                pk[j] = bf_pack(__sinf(a0), __sinf(a1));
-                if (prm.store_c) pc[j] = bf_pack(30.0f * __cosf(a0), 30.0f * __cosf(a1));
-              }
+              for (int j = 0; j < 16; ++j)
+                pc[j] = bf_pack(30.0f * __cosf(30.0f * __uint_as_float(v[2 * j])), 30.0f * __cosf(30.0f * __uint_as_float(v[2 * j + 1])));
             } else {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float a0 = __uint_as_float(v[2 * j]), a1 = __uint_as_float(v[2 * j + 1]);
-                pk[j] = bf_pack(__sinf(a0), __sinf(a1));
-                if (prm.store_c) pc[j] = bf_pack(__cosf(a0), __cosf(a1));
-              }
+              for (int j = 0; j < 16; ++j) pc[j] = bf_pack(__cosf(__uint_as_float(v[2 * j])), __cosf(__uint_as_float(v[2 * j + 1])));
             }
             uint8_t* box = cbox + (kCBox2 ? (cu & 1) * 2048 : 0);
-            // this warp's earlier TMA stores have read their shared memory: the cosine box of the previous unit and, for the
-            // quadrant leader, the h_l box it stored then (with two cosine boxes only the store before the previous one
-            // must be done — except for the leader, whose wait also covers that h_l box)
-            if (lane == 0 && (prm.store_c || leader)) { if (kCBox2 && !leader) bulk_wait_read1(); else bulk_wait_read0(); }
+            // the box was read out by the TMA (with two boxes: the store before the previous one); the leader's wait also
+            // covers the h_l boxes it committed at the end of the previous half
+            if (lane == 0) { if (kCBox2 && !leader) bulk_wait_read1(); else bulk_wait_read0(); }
             __syncwarp();
-            if (prm.store_c) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                sts128(box + crow_off + ((j << 4) ^ cswz), pc[4 * j], pc[4 * j + 1], pc[4 * j + 2], pc[4 * j + 3]);
-              ++cu;
+            for (int j = 0; j < 4; ++j)
+              sts128(box + crow_off + ((j << 4) ^ cswz), pc[4 * j], pc[4 * j + 1], pc[4 * j + 2], pc[4 * j + 3]);
+            ++cu;
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) { tma_store_2d(&prm.cmap[l], box, n * 256 + u * 64 + hsel * 32, grow0); bulk_commit(); }
+          };
+          // ---- sine of one unit: registers -> in place into K block 1 + 4n + u of the next layer, published at once ----
+          auto publish_sin = [&](const uint32_t (&v)[32], int u) {
+            uint32_t pk[16];
+            if (l0) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) pk[j] = bf_pack(__sinf(30.0f * __uint_as_float(v[2 * j])), __sinf(30.0f * __uint_as_float(v[2 * j + 1])));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) pk[j] = bf_pack(__sinf(__uint_as_float(v[2 * j])), __sinf(__uint_as_float(v[2 * j + 1])));
             }
-            // in place: the unit becomes K block 1 + 4n + u of the next layer.  Second half: every MMA of this layer has
-            // retired (tfull[1]).  First half: K block 1 + u still feeds the second half's MMAs until kfree[u]
+            // second half: every MMA of this layer has retired (tfull[1]); first half: K block 1 + u still feeds the second
+            // half's MMAs until kfree[u].  The leader's h_l stores of the previous layer out of this K block were read out
+            // long ago (it waits for them before its next cosine store)
             if (n == 0) mbar_wait(&kfree[u], kf_ph);
             uint8_t* kbp = sAct + (1 + 4 * n + u) * kKBBytes;
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               sts128(kbp + row_off + (((hsel * 4 + j) << 4) ^ swz), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
             fence_async_smem();
-            __syncwarp();
-            if (lane == 0 && prm.store_c) { tma_store_2d(&prm.cmap[l], box, col0, grow0); bulk_commit(); }
             if (!last) arrive_leader(&act_ready[1 + 4 * n + u]);
-            if (store_h) {
-              // h_l of this unit: both warps of the quadrant have written their 32 columns -> one 64-column box, now,
-              // instead of a 64 KB burst of stores at the end of the half that the weight loads would queue behind
-              named_bar_sync(1 + q, 64);
-              if (leader) { tma_store_2d(&prm.hmap[l], kbp + q * 4096, n * 256 + u * 64, grow0); bulk_commit(); }
+          };
+          if (n == 0 || !prm.store_c) {
+            // one pass: sine and cosine of a unit share the range reduction.  (First half: off the critical path, it runs in
+            // the shadow of the second half's MMAs.  Inference without cosines: nothing else to do.)
+            tmem_ld32_issue(tbase, va);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              tmem_wait_ld();
+              uint32_t (&v)[32] = (u & 1) ? vb : va;
+              if (u < 3) tmem_ld32_issue(tbase + (u + 1) * 64, (u & 1) ? va : vb);
+              else { fence_before_sync(); arrive_leader(&tempty[n]); }
+              publish_sin(v, u);
+              if (prm.store_c) store_cos(v, u);
+            }
+          } else {
+            // Second half, training: the next layer's first half can only finish once K blocks 5..8 are published, and
+            // this half's MMAs could not start before the previous layer's did the same — the chain's critical path runs
+            // through THIS epilogue.  Pass A does only what the next layer waits for (sine -> K block -> publish, half of
+            // the MUFU work and none of the store hand-shakes); pass B reads the accumulator again (TMEM reads are cheap)
+            // for the cosines, off the critical path, while the next layer's first half is being multiplied.
+            tmem_ld32_issue(tbase, va);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              tmem_wait_ld();
+              uint32_t (&v)[32] = (u & 1) ? vb : va;
+              tmem_ld32_issue(tbase + ((u + 1) & 3) * 64, (u & 1) ? va : vb);      // u == 3: unit 0 again, for pass B
+              publish_sin(v, u);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              tmem_wait_ld();
+              uint32_t (&v)[32] = (u & 1) ? vb : va;
+              if (u < 3) tmem_ld32_issue(tbase + (u + 1) * 64, (u & 1) ? va : vb);
+              else { fence_before_sync(); arrive_leader(&tempty[n]); }
+              store_cos(v, u);
             }
           }
           if (n == 0) kf_ph ^= 1;
-          if (tr) prm.trace[(l * 2 + n) * 16 + 13] = clock64();   // [13] the half's four units are through the MUFU / stores
+          if (tr) prm.trace[(l * 2 + n) * 16 + 13] = clock64();   // [13] the half's units are through the MUFU / cosine stores
+          if (store_h) {
+            // h_l of this half: both warps of the quadrant have written their columns -> four 64-column boxes straight out
+            // of the K blocks (read-only for everyone until the next layer's epilogue of the same half)
+            named_bar_sync(1 + q, 64);
+            if (leader) {
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                tma_store_2d(&prm.hmap[l], sAct + (1 + n * 4 + u) * kKBBytes + q * 4096, n * 256 + u * 64, grow0);
+              bulk_commit();
+            }
+          }
         }
       }
     }

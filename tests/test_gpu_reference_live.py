@@ -24,7 +24,7 @@ CASES = [("lambertian_ds", True, dict(mode="train")),
 @pytest.mark.parametrize("cfg,ds,kw", CASES)
 def test_cuda_path_vs_unmodified_reference(cuda, cfg, ds, kw):
     args = named_config(cfg)
-    n = 256
+    n = 512
     batch = make_rays(n, seed=777, depth_supervision=ds)
     S1, G = args.n_samples, args.guided_samples
     draws = RT.Draws.make(n, S1, G, S1 + G, seed=2468, with_gt=ds)
@@ -35,19 +35,32 @@ def test_cuda_path_vs_unmodified_reference(cuda, cfg, ds, kw):
     gb = batch.to(cuda)
     supg = dict(valid_depth=gb.valid_depth, target_depths=gb.target_depths, target_std=gb.target_std) if ds else {}
     d = Draws(u_strat=draws.u_strat, u_pred=draws.u_pred, u_gt=draws.u_gt if ds else None)
-    for precision, tol in (("fp32", dict(rgb=1e-3, depth=1e-3, weights=1e-3, albedo_accu=1e-3, z_vals=1e-4)),
-                           ("bf16", dict(rgb=2e-2, depth=1.5e-2, weights=8e-2, albedo_accu=2e-2, z_vals=2e-2))):
+    # (max abs, mean abs); for the bf16 path the quantities behind the per-sample analytic normal are bounded on the mean
+    # and on the 99th percentile (ill-conditioned outliers where |grad sigma| ~ 0, see test_gpu_bf16_parity.py)
+    TOL = {"fp32": dict(rgb=(1e-3, 1e-3), depth=(1e-3, 1e-3), weights=(1e-3, 1e-3), albedo_accu=(1e-3, 1e-3), z_vals=(1e-4, 1e-4)),
+           "bf16": dict(rgb=(None, 4e-3), depth=(2e-3, 2e-4), weights=(8e-3, 2e-4), albedo_accu=(5e-3, 1e-3), z_vals=(3e-3, 2e-4))}
+    for precision in ("fp32", "bf16"):
         torch.manual_seed(0)
         model = load_model(args, precision=precision).to(cuda)
         with torch.no_grad():
             res, btype = render_rays({"coarse": model}, args, gb.rays, None, _draws=d, **kw, **supg)
         assert btype == ref_type
         assert set(res) == set(ref), (sorted(set(res) ^ set(ref)))
-        for k, t in tol.items():
-            err = (res[k + "_coarse"].cpu() - ref[k + "_coarse"]).abs().max().item()
-            print(f"{cfg} [{precision}] {k}: max abs err vs the unmodified reference {err:.3e} (tolerance {t})")
-            assert err <= t, (cfg, precision, k, err)
-        if precision == "fp32" and "normal_an_coarse" in ref:
+        for k, (tmax, tmean) in TOL[precision].items():
+            e = (res[k + "_coarse"].cpu() - ref[k + "_coarse"]).abs()
+            p99 = torch.quantile(e.flatten()[:4_000_000].float(), 0.99).item()
+            print(f"{cfg} [{precision}] {k} vs the unmodified reference: max {e.max().item():.3e}  p99 {p99:.3e}  mean {e.mean().item():.3e}")
+            if tmax is not None:
+                assert e.max().item() <= tmax, (cfg, precision, k, e.max().item())
+            else:
+                assert p99 <= 5e-2, (cfg, precision, k, p99)
+            assert e.mean().item() <= tmean, (cfg, precision, k, e.mean().item())
+        if "normal_an_coarse" in ref:
             acc = (res["weights_coarse"].unsqueeze(-1) * res["normal_an_coarse"]).sum(1).cpu()
             want = (ref["weights_coarse"].unsqueeze(-1) * ref["normal_an_coarse"]).sum(1)
-            assert (acc - want).abs().max().item() <= 1e-3
+            e = (acc - want).abs()
+            print(f"{cfg} [{precision}] accumulated normal: max {e.max().item():.3e} mean {e.mean().item():.3e}")
+            if precision == "fp32":
+                assert e.max().item() <= 1e-3
+            else:
+                assert e.mean().item() <= 8e-3

