@@ -372,8 +372,8 @@ def run_ours(opts):
         pe1.record()
         torch.cuda.synchronize()
         ms_eager = pe0.elapsed_time(pe1) / nprof      # the profiled steps themselves (eager launches + per-launch events)
-        cnt = (C.c_longlong * 3)(); tms = (C.c_double * 3)(); work = (C.c_double * 3)()
-        lib.bn_profile_collect(3, cnt, tms, work)
+        cnt = (C.c_longlong * 4)(); tms = (C.c_double * 4)(); work = (C.c_double * 4)()
+        lib.bn_profile_collect(4, cnt, tms, work)
         lib.bn_profile_enable(0)
         gemm_ms = sum(tms) / nprof
         alg = mlp_flops_per_ray(args, args.n_samples, args.n_samples + args.guided_samples) * RAYS_PER_GPU
@@ -401,7 +401,7 @@ def run_ours(opts):
                                 "profiled_step_ms": ms_eager,
                                 "executed_gflop_per_step": gemm_flops / 1e9, "algorithmic_gflop_per_step_shared_trunk": alg_shared / 1e9,
                                 "reference_gflop_per_step": alg / 1e9,
-                                "by_kind": {"chain_fwd": kind(2), "tn_fwd_dgrad": kind(0), "nt_wgrad": kind(1)}}}
+                                "by_kind": {"chain_fwd": kind(2), "chain_dgrad": kind(3), "tn_fwd_dgrad": kind(0), "nt_wgrad": kind(1)}}}
     total_rays = RAYS_PER_GPU * world
     # ---- end to end through the public API: every step's batch starts in pinned host memory and is copied into the device
     # (H2D), every step's loss is read back into host memory (D2H), both inside the timed region.  --feed inline (default):

@@ -2,6 +2,7 @@
 // orchestration and the C entry points.  Shared declarations live in mlp_internal.cuh.
 #include "mlp_internal.cuh"
 #include "mlp_chain.cuh"
+#include "mlp_dgrad_chain.cuh"
 
 namespace bn {
 
@@ -738,6 +739,7 @@ static int train_chain(bn_mlp* h, const float* params, const float* origins, int
   prm.L = h->L; prm.skip = h->skip; prm.n_freq = c.n_freq_xyz;
   prm.store_c = keep_c ? 1 : 0; prm.h_from = train ? 0 : h->L - 1;
   prm.trace = h->chain_trace;
+  prm.two_pass = getenv("BN_CHAIN_ONEPASS") == nullptr;        // A/B timing aid, read per launch
   const int n_blocks = (int)ceil_div_ll(P, 256);
   constexpr int smem = chain::chain_smem<true>();
   // experiment knob: one weight stage traded for a second cosine staging box per epilogue warp
@@ -893,6 +895,38 @@ static int trunk_rows_t(bn_mlp* h, const float* params, const float* origins, in
   return BN_OK;
 }
 
+// data gradients of the whole trunk as ONE fused kernel (mlp_dgrad_chain.cuh): dZ_{L-1} = w.GA in, dZ_l -> w.GZ[l], l < L-1
+static int dgrad_chain(bn_mlp* h, const Ws<__nv_bfloat16>& w, long long P, cudaStream_t s) {
+  chain::DgradChainParams prm;
+  memset(&prm, 0, sizeof(prm));
+  const int F = h->F;
+  for (int l = 1; l < h->L; ++l) {
+    const __nv_bfloat16* BT = (const __nv_bfloat16*)h->WTp[l] + (l == h->skip ? (long long)kEncPad * F : 0);
+    if (int rc = tc::make_map_bf16(&prm.wmap[l], BT, F, F, F, 64, 128)) return rc;
+    if (int rc = tc::stream_map(&prm.cmap[l], w.C[l - 1], P, F, F)) return rc;
+    if (int rc = tc::stream_map(&prm.gout[l], w.GZ[l - 1], P, F, F)) return rc;
+  }
+  if (int rc = tc::make_map_bf16(&prm.gin, w.GA, P, F, F, 64, 128)) return rc;
+  prm.P = P; prm.L = h->L;
+  const int n_blocks = (int)ceil_div_ll(P, 256);
+  constexpr int smem = chain::dgrad_chain_smem();
+  BN_CUDA(cudaFuncSetAttribute(chain::dgrad_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * min(n_blocks, h->num_sms / 2));
+  cfg.blockDim = dim3(tc::kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  prof_begin(3, 2.0 * (double)P * (double)(h->L - 1) * F * F, s);
+  BN_CUDA(cudaLaunchKernelEx(&cfg, chain::dgrad_chain_kernel, prm));
+  const int rc = after_launch("dgrad_chain_kernel");
+  prof_end(s);
+  return rc;
+}
+
 template <typename T>
 static int backward_t(bn_mlp* h, const float* params, const float* out, const float* g_out, int pitch, int N, int S,
                       int flags, float* g, void* wsp, cudaStream_t s) {
@@ -1008,6 +1042,27 @@ static int backward_t(bn_mlp* h, const float* params, const float* out, const fl
   // the ramp of the next dgrad overlap instead of leaving the SMs idle between two persistent kernels.  dZ rotates through
   // three buffers; a buffer is rewritten only after the wgrad that read it has finished (ev_w), and the side stream
   // is joined back into `s` before returning (the whole pattern is stream-capturable).
+  if constexpr (kTC) {
+    if (dgrad_chain_ok(h) && !normals) {
+      // every trunk data gradient in one launch; the weight gradients follow, each reading the dZ_l the chain left in HBM
+      // and the layer input the forward left there (they share nothing with each other: side stream next to the chain's tail)
+      if (int rc = dgrad_chain(h, w, P, s)) return rc;
+      cudaStream_t sw = fork();
+      for (int l = L - 1; l >= 0; --l) {
+        const bool enc_in = (l == 0 || l == h->skip);
+        const T* In; long long ldin;
+        if (enc_in) { In = w.X3; ldin = w.ldx3; } else { In = w.H[l - 1]; ldin = w.Hld[l - 1]; }
+        const T* dZ = (l == L - 1) ? w.GA : w.GZ[l];
+        if (int rc = layer_wgrad<T>(h, dZ, F, In, ldin, F, h->Kpad[l], P, g + c.w_off[l], h->Kreal[l],
+                                    enc_in ? h->E : h->Kpad[l], enc_in ? kEncPad : h->Kpad[l], g + c.b_off[l], sw, 2.0 * P * F * h->Kreal[l])) return rc;
+      }
+      if (overlap) {
+        BN_CUDA(cudaEventRecord(h->ev_h[7], h->s2));
+        BN_CUDA(cudaStreamWaitEvent(s, h->ev_h[7], 0));
+      }
+      return BN_OK;
+    }
+  }
   T* buf[3] = {w.GA, w.GB, kTC ? w.G7D : nullptr};       // G7D is unused in tcgen05 mode (rank-4 epilogue addend instead)
   int ci = 0;
   int reader[3] = {-1, -1, -1};                           // layer whose wgrad (on s2) last read buf[i]
@@ -1073,6 +1128,7 @@ extern "C" __attribute__((visibility("default"))) int bn_mlp_create(const bn_mlp
   BN_CUDA(cudaGetDeviceProperties(&prop, dev));
   h->num_sms = prop.multiProcessorCount;
   h->no_chain = getenv("BN_NO_CHAIN") != nullptr;      // debugging aid: per-layer GEMMs instead of the fused trunk kernels
+  h->no_dchain = getenv("BN_NO_DGRAD_CHAIN") != nullptr;
   // blocks of the heads' hidden layer: rgb first, then every BRDF head that exists
   h->n_blocks = 0;
   h->blk_lin0[0] = BN_LIN_RGB0; h->blk_lin2[0] = BN_LIN_RGB2; h->blk_head[0] = -1; h->n_blocks = 1;

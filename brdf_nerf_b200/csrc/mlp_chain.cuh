@@ -71,6 +71,7 @@ struct TrainChainParams {
   int store_c;                          // 0: inference without analytic normals - no cosines are computed or stored
   int h_from;                           // h_l leaves the SM only for l >= h_from (0 when training, L-1 for inference)
   long long* trace;                     // diagnostics (bn_debug_chain_trace): clock64() stamps of pair 0's leader CTA, first block
+  int two_pass;                         // second-half epilogue: sines first, cosines from a second TMEM read (A/B knob BN_CHAIN_ONEPASS)
 };
 
 template <bool kTrain> __host__ __device__ constexpr int chain_smem() {
@@ -126,13 +127,20 @@ __device__ __forceinline__ void chain_mma(uint8_t* sAct, uint8_t* sW, uint64_t* 
         if (tr) trace[(l * 2 + n) * 16 + 0] = clock64();      // [0] TMEM half free
         bool first = true;
         const int k_first0 = layer_reads_enc(l, skip) ? 0 : 3;   // K block 0: all of it, or only the slice with the constant 1
+        long long t_act = 0, t_w = 0;                            // trace: cycles spent waiting for activations / weights
         for (int kb = 0; kb <= layer_kb_last(l); ++kb) {
           if (n == 0 && !(kb == 0 && l > 0)) {          // K block published once per layer (PE: once per block)
+            const long long t0 = tr ? clock64() : 0;
             mbar_wait(&act_ready[kb], (ar_ph >> kb) & 1); ar_ph ^= 1u << kb;
             fence_after_sync();
+            if (tr) t_act += clock64() - t0;
           }
           if (tr) trace[(l * 2 + n) * 16 + 1 + kb] = clock64(); // [1+kb] K block kb available to the issuer
-          mbar_wait(&wfull[stage], phase);
+          {
+            const long long t0 = tr ? clock64() : 0;
+            mbar_wait(&wfull[stage], phase);
+            if (tr) t_w += clock64() - t0;
+          }
           fence_after_sync();
           const uint32_t a_addr = smem_u32(sAct + kb * kKBBytes);
           const uint32_t b_addr = smem_u32(sW + stage * kKBBytes);
@@ -154,7 +162,11 @@ __device__ __forceinline__ void chain_mma(uint8_t* sAct, uint8_t* sW, uint64_t* 
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit_pair(&tfull[n]);
-        if (tr) trace[(l * 2 + n) * 16 + 10] = clock64();     // [10] all MMAs of the half issued
+        if (tr) {
+          trace[(l * 2 + n) * 16 + 10] = clock64();           // [10] all MMAs of the half issued
+          trace[(l * 2 + n) * 16 + 14] = t_act;               // [14] cycles the issuer waited for activation K blocks
+          trace[(l * 2 + n) * 16 + 15] = t_w;                 // [15] cycles the issuer waited for weight tiles
+        }
       }
 }
 
@@ -457,7 +469,7 @@ __global__ void __launch_bounds__(kThreads, 1) train_chain_kernel(const __grid_c
             fence_async_smem();
             if (!last) arrive_leader(&act_ready[1 + 4 * n + u]);
           };
-          if (n == 0 || !prm.store_c) {
+          if (n == 0 || !prm.store_c || !prm.two_pass) {
             // one pass: sine and cosine of a unit share the range reduction.  (First half: off the critical path, it runs in
             // the shadow of the second half's MMAs.  Inference without cosines: nothing else to do.)
             tmem_ld32_issue(tbase, va);

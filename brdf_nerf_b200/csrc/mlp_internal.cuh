@@ -71,6 +71,7 @@ struct bn_mlp {
   int blk_lin0[bn::kMaxBlocks], blk_lin2[bn::kMaxBlocks], blk_head[bn::kMaxBlocks];
   bool synced;
   bool no_chain;
+  bool no_dchain;               // BN_NO_DGRAD_CHAIN=1: per-layer data-gradient GEMMs instead of the fused chain (A/B timing aid)
   // backward: weight gradients run on a side stream next to the data-gradient chain (forked from / joined into the caller's stream)
   cudaStream_t s2; cudaEvent_t ev_dz[16]; cudaEvent_t ev_w[16]; cudaEvent_t ev_h[8]; bool overlap;
   long long* chain_trace;
@@ -156,6 +157,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ X, lo
 template <typename T> struct Ws {
   T* X3; T* H[16]; long long Hld[16]; T* C[16];
   T* FE; long long ldfe; T* HD; T* CD; T* GHD; T* G7D; T* GFE; T* GA; T* GB; T* DPRE;
+  T* GZ[16];       // fused data-gradient chain (tcgen05 mode): dZ_l of every trunk layer l < L-1 (dZ_{L-1} = GA)
   long long ldx3, ldhd;
   // analytic-normal sweep (BN_MLP_NORMAL_AN)
   T* A[16];        // a_l = d sigma / d lin_l            (one per layer when training, ping-pong otherwise)
@@ -168,6 +170,9 @@ template <typename T> struct Ws {
 };
 
 static inline size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
+
+// the fused data-gradient chain (mlp_dgrad_chain.cuh) is specialised like the forward chain: bf16, 512-wide trunk
+static inline bool dgrad_chain_ok(const bn_mlp* h) { return h->bf16 && h->F == 512 && h->L >= 3 && !h->no_chain && !h->no_dchain; }
 
 template <typename T>
 static inline size_t carve(const bn_mlp* h, long long P, int flags, void* base, Ws<T>* w) {
@@ -206,6 +211,9 @@ static inline size_t carve(const bn_mlp* h, long long P, int flags, void* base, 
       t.CD = take(P * t.ldhd); t.GHD = take(P * t.ldhd);
       t.G7D = take(P * F); t.GFE = take(P * F); t.GA = take(P * F); t.GB = take(P * F);
       t.DPRE = take(P * 64);
+      if (dgrad_chain_ok(h)) {       // one buffer per layer: the chain produces them all in one launch, the wgrads read them later
+        for (int l = 0; l < L - 1; ++l) t.GZ[l] = (l == L - 2) ? t.GB : (l == L - 3 ? t.G7D : take(P * F));
+      }
     }
   }
   if (normals) {

@@ -45,13 +45,15 @@ def main():
     L.check(L.load().bn_debug_chain_trace(m.handle(), None))
     t = buf.cpu().view(16, 2, 16)
     t0 = int(t[0, 0, 0])
-    names = ["tmem_free", "kb0", "kb1", "kb2", "kb3", "kb4", "kb5", "kb6", "kb7", "kb8", "issued", "epi_wait", "epi_tfull", "epi_done", "hazard_clr"]
+    names = ["tmem_free", "kb0", "kb1", "kb2", "kb3", "kb4", "kb5", "kb6", "kb7", "kb8", "issued", "epi_wait", "epi_tfull", "epi_done"]
+    durations = {14: "wait_act", 15: "wait_w"}        # cycle counts, not stamps
     print("cycles relative to the first stamp; MMA issuer: tmem_free, kb*, issued; epilogue warp 4: epi_*")
     prev_tfull1 = None
     for l in range(8):
         for h in range(2):
             row = {nm: int(t[l, h, i]) - t0 for i, nm in enumerate(names) if int(t[l, h, i]) != 0}
-            print(f"layer {l} half {h}: " + "  ".join(f"{k}={v}" for k, v in row.items()))
+            dur = "  ".join(f"{nm}={int(t[l, h, i])}" for i, nm in durations.items())
+            print(f"layer {l} half {h}: " + "  ".join(f"{k}={v}" for k, v in row.items()) + "  | " + dur)
         tf1 = int(t[l, 1, 12]) - t0
         if prev_tfull1 is not None:
             print(f"   -> layer period (tfull[1] to tfull[1]) = {tf1 - prev_tfull1} cycles (MMA floor 8192 nominal, ~12500 at the measured 195 cycles per pair-MMA)")
