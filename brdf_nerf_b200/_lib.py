@@ -77,6 +77,13 @@ _SIGS = {
     "bn_debug_gemm_epi": (C.c_int, [_I, _P, C.c_longlong, _P, C.c_longlong, _P, C.c_longlong, _P, _P, _P, _I, _I,
                                     C.c_longlong, _I, C.c_longlong, _P]),
     "bn_debug_gemm": (C.c_int, [_I, _I, _P, C.c_longlong, _P, C.c_longlong, _P, C.c_longlong, C.c_longlong, _I, C.c_longlong, _P]),
+    "bn_allreduce_p2p": (C.c_int, [_P, _P, _P, _L, _I, _I, _I, _P]),
+    "bn_allreduce_p2p_flag_words": (C.c_int, []),
+    "bn_peer_alloc": (C.c_int, [_Z, C.POINTER(_P)]),
+    "bn_peer_free": (C.c_int, [_P]),
+    "bn_peer_export": (C.c_int, [_P, _P]),
+    "bn_peer_open": (C.c_int, [_P, C.POINTER(_P)]),
+    "bn_peer_close": (C.c_int, [_P]),
     "bn_adam_step": (C.c_int, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P]),
     "bn_adam_step_graph": (C.c_int, [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _F, _P]),
     "bn_rays_from_rpc": (C.c_int, [_P, _P, _P, C.c_longlong, _I, _D, _D, _I, _I, _I, _F, _F, _F, _F, _P, _P, _I, _P, _P, _P]),

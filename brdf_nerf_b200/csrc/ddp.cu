@@ -1,0 +1,141 @@
+// Data-parallel gradient exchange over NVLink peer memory (the per-step all-reduce of the flat fp32
+// gradient bucket; reference: DDP's bucketed all-reduce under Lightning, main.py:720-731).
+//
+// One kernel, no library collective: every rank's gradient bucket lives in peer-mapped ("symmetric") memory, so the kernel
+// reads its peers' buckets and writes into them directly through NVLink / NVSwitch:
+//   barrier A   every rank's backward has finished writing its bucket              (flag exchange, system scope)
+//   reduce      rank r sums slice r of all W buckets in rank order (bit-identical on every rank) ...
+//   broadcast   ... and stores the sum into slice r of EVERY rank's bucket          (two-shot: 2 (W-1)/W of the bucket per rank
+//   barrier B   all slices have arrived in this rank's bucket                        crosses the links, in each direction)
+// The kernel has no host-side state (its epoch counters live in device memory), so it is CUDA-graph capturable: with it
+// the whole multi-GPU step — forward, backward, exchange, Adam — replays as ONE graph launch per rank.
+// Flags: `flags` is a per-rank symmetric uint32 array [2][kMaxBlocks][kMaxWorld] (zero-initialised once); block b of rank r
+// raises flag [phase][b][r] = epoch in every peer's array and waits for [phase][b][p] == epoch for all p in its own.
+#include <string.h>
+#include "common.cuh"
+
+namespace bn {
+
+constexpr int kDdpMaxWorld = 16;
+constexpr int kDdpMaxBlocks = 128;
+
+struct DdpArgs {
+  float* buf[kDdpMaxWorld];            // peer-mapped gradient buckets, index = rank
+  uint32_t* flags[kDdpMaxWorld];       // peer-mapped flag arrays, index = rank
+  uint32_t* epoch;                     // local [kDdpMaxBlocks]: per-block call counter
+  long long n;                         // bucket length in floats (a multiple of 4)
+  int rank, world;
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// all threads of the block have finished their part; afterwards every peer's block `b` has reached the same point
+__device__ __forceinline__ void cross_gpu_barrier(const DdpArgs& a, int phase, uint32_t epoch) {
+  __syncthreads();
+  const int t = threadIdx.x;
+  if (t < a.world) {
+    const int slot = (phase * kDdpMaxBlocks + blockIdx.x) * kDdpMaxWorld;
+    __threadfence_system();                                       // this block's peer writes are visible before the flag
+    st_release_sys(a.flags[t] + slot + a.rank, epoch);
+    const uint32_t* mine = a.flags[a.rank] + slot + t;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(mine) != epoch) {
+      if (clock64() - t0 > 20000000000LL) { printf("bn::ddp barrier timeout rank %d block %d peer %d\n", a.rank, blockIdx.x, t); __trap(); }
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(512) allreduce_p2p_kernel(const __grid_constant__ DdpArgs a) {
+  const uint32_t epoch = a.epoch[blockIdx.x] + 1;
+  cross_gpu_barrier(a, 0, epoch);
+  const int W = a.world;
+  // slice of this rank, in float4 units
+  const long long n4 = a.n / 4;
+  const long long per = (n4 + W - 1) / W;
+  const long long lo = per * a.rank, hi = min(n4, lo + per);
+  const float4* src[kDdpMaxWorld];
+  float4* dst[kDdpMaxWorld];
+#pragma unroll
+  for (int p = 0; p < kDdpMaxWorld; ++p) {
+    src[p] = reinterpret_cast<const float4*>(a.buf[p < W ? p : 0]);
+    dst[p] = reinterpret_cast<float4*>(a.buf[p < W ? p : 0]);
+  }
+  for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (long long)gridDim.x * blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 v[kDdpMaxWorld];
+#pragma unroll
+    for (int p = 0; p < kDdpMaxWorld; ++p)
+      if (p < W) v[p] = __ldcv(src[p] + i);                       // all W loads in flight (never cached: peers rewrite it every step)
+#pragma unroll
+    for (int p = 0; p < kDdpMaxWorld; ++p)
+      if (p < W) { acc.x += v[p].x; acc.y += v[p].y; acc.z += v[p].z; acc.w += v[p].w; }   // rank order: the same sum everywhere
+#pragma unroll
+    for (int p = 0; p < kDdpMaxWorld; ++p)
+      if (p < W) dst[p][i] = acc;
+  }
+  cross_gpu_barrier(a, 1, epoch);
+  if (threadIdx.x == 0) a.epoch[blockIdx.x] = epoch;
+}
+
+}  // namespace bn
+
+using namespace bn;
+
+extern "C" __attribute__((visibility("default")))
+int bn_allreduce_p2p(void* const* peer_bufs, void* const* peer_flags, uint32_t* epoch, int64_t n, int rank, int world,
+                     int n_blocks, cudaStream_t stream) {
+  BN_CHECK_ARG(peer_bufs && peer_flags && epoch, "null pointer");
+  BN_CHECK_ARG(world >= 1 && world <= kDdpMaxWorld && rank >= 0 && rank < world, "rank / world out of range");
+  BN_CHECK_ARG(n > 0 && n % 4 == 0, "bucket length must be a positive multiple of 4 floats");
+  BN_CHECK_ARG(n_blocks >= 1 && n_blocks <= kDdpMaxBlocks, "n_blocks out of range");
+  DdpArgs a{};
+  for (int p = 0; p < world; ++p) {
+    BN_CHECK_ARG(peer_bufs[p] && peer_flags[p], "null peer pointer");
+    a.buf[p] = static_cast<float*>(peer_bufs[p]); a.flags[p] = static_cast<uint32_t*>(peer_flags[p]);
+  }
+  a.epoch = epoch; a.n = n; a.rank = rank; a.world = world;
+  allreduce_p2p_kernel<<<n_blocks, 512, 0, stream>>>(a);
+  return after_launch("allreduce_p2p_kernel");
+}
+
+extern "C" __attribute__((visibility("default"))) int bn_allreduce_p2p_flag_words(void) { return 2 * kDdpMaxBlocks * kDdpMaxWorld; }
+
+// ---- peer-mapped memory for the exchange (CUDA IPC: one allocation per rank, opened by every other rank) ----------------
+extern "C" __attribute__((visibility("default"))) int bn_peer_alloc(size_t bytes, void** ptr) {
+  BN_CHECK_ARG(ptr && bytes > 0, "bad arguments");
+  BN_CUDA(cudaMalloc(ptr, bytes));
+  BN_CUDA(cudaMemset(*ptr, 0, bytes));
+  return BN_OK;
+}
+extern "C" __attribute__((visibility("default"))) int bn_peer_free(void* ptr) {
+  if (ptr) BN_CUDA(cudaFree(ptr));
+  return BN_OK;
+}
+// handle64: 64 bytes (cudaIpcMemHandle_t) to be sent to the other ranks
+extern "C" __attribute__((visibility("default"))) int bn_peer_export(void* ptr, void* handle64) {
+  BN_CHECK_ARG(ptr && handle64, "null pointer");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  BN_CUDA(cudaIpcGetMemHandle(&h, ptr));
+  memcpy(handle64, &h, 64);
+  return BN_OK;
+}
+extern "C" __attribute__((visibility("default"))) int bn_peer_open(const void* handle64, void** ptr) {
+  BN_CHECK_ARG(ptr && handle64, "null pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  BN_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return BN_OK;
+}
+extern "C" __attribute__((visibility("default"))) int bn_peer_close(void* ptr) {
+  if (ptr) BN_CUDA(cudaIpcCloseMemHandle(ptr));
+  return BN_OK;
+}

@@ -82,6 +82,25 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const 
   asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
 }
+// L2 eviction-priority hints of the TMA (createpolicy encodings): the packed weights (2-3 MB, re-read by every block of every
+// CTA) must survive in the 126 MB L2 next to GBs of activations that stream through it once — without the hints the
+// activation stores of the fused trunk evicted the weight tiles and the MMA issuer waited ~4.5 k cycles per layer for them
+constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;   // streaming: activations written / read once per kernel
+constexpr uint64_t kEvictLast = 0x14F0000000000000ull;    // resident: weights
+constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
+// BN_NO_L2_HINTS=1 (A/B timing aid, read per launch): every transfer with the default policy
+inline uint64_t pol_weights() { return getenv("BN_NO_L2_HINTS") ? kEvictNormal : kEvictLast; }
+inline uint64_t pol_stream() { return getenv("BN_NO_L2_HINTS") ? kEvictNormal : kEvictFirst; }
+__device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(pol)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* map, const void* smem_src, int c0, int c1, uint64_t pol) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -137,6 +156,12 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair_hint(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1), "l"(pol)
       : "memory");
 }
 __device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -218,6 +243,7 @@ struct Work {
   int kb_total, kb_per_split;     // k-blocks (of kBK) in the reduction dimension
   int n_cols;                     // real number of output columns (a multiple of the epilogue unit)
   int reverse;                    // TN only: walk the row tiles from the last to the first (see tile_reverse())
+  uint64_t pol_a, pol_b;          // TN only: L2 eviction policies of the A (activation) and B (weight) tiles
 };
 
 // Tile order of the NEXT tn launches on this thread (experiment knob).  Idea: in a chain of GEMMs in which each one consumes
@@ -357,9 +383,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // the leader's barrier expects the bytes of both CTAs; the peer only issues its loads
             if (crank == 0) mbar_expect_tx(&full[stage], 2 * (A_BYTES + B_BYTES));
             const uint32_t bar = mapa_u32(smem_u32(&full[stage]), 0);
-            if (!kNT) {
-              tma_load_2d_pair(a, &tmA, bar, kb * kBK, m_blk * kBM);
-              tma_load_2d_pair(b, &tmB, bar, kb * kBK, ncol0);
+            if (!kNT) {                      // A: activations streaming through once; B: weights, re-read by every row tile
+              tma_load_2d_pair_hint(a, &tmA, bar, kb * kBK, m_blk * kBM, wk.pol_a);
+              tma_load_2d_pair_hint(b, &tmB, bar, kb * kBK, ncol0, wk.pol_b);
             } else {
 #pragma unroll
               for (int c = 0; c < kBM / 64; ++c) tma_load_2d_pair(a + c * 8192, &tmA, bar, m_blk * kBM + c * 64, kb * kBK);
@@ -369,8 +395,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           } else {
             mbar_expect_tx(&full[stage], A_BYTES + B_BYTES);
             if (!kNT) {
-              tma_load_2d(a, &tmA, &full[stage], kb * kBK, m_blk * kBM);
-              tma_load_2d(b, &tmB, &full[stage], kb * kBK, ncol0);
+              tma_load_2d_hint(a, &tmA, &full[stage], kb * kBK, m_blk * kBM, wk.pol_a);
+              tma_load_2d_hint(b, &tmB, &full[stage], kb * kBK, ncol0, wk.pol_b);
             } else {
               // boxes of 64 (contiguous MN) x 64 (reduction rows); one box per 64 output rows/cols
 #pragma unroll
@@ -655,7 +681,7 @@ int launch_tn(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* B, lon
   if (K % kBK) { set_error("tc::launch_tn: K=%d not a multiple of 64", K); return BN_ERR_ARG; }
   if (Epi::kMode != EPI_DIRECT && N % 64) { set_error("tc::launch_tn: N=%d not a multiple of 64", N); return BN_ERR_ARG; }
   CUtensorMap ma, mb;
-  Work wk{(int)ceil_div_ll(M, kBM), ceil_div(N, BN), 1, K / kBK, K / kBK, N, tile_reverse() ? 1 : 0};
+  Work wk{(int)ceil_div_ll(M, kBM), ceil_div(N, BN), 1, K / kBK, K / kBK, N, tile_reverse() ? 1 : 0, pol_stream(), pol_weights()};
   if (int rc = make_map_bf16(&ma, A, M, K, lda, kBK, kBM)) return rc;
   if constexpr (BN >= 128) {
     if (wk.m_tiles >= 4) {               // CTA pairs: every CTA stages BN/2 rows of the B tile
@@ -682,7 +708,7 @@ int launch_nt(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* B, lon
   if (int rc = make_map_bf16(&ma, A, P, Mo, lda, 64, kBK)) return rc;
   if (int rc = make_map_bf16(&mb, B, P, No, ldb, 64, kBK)) return rc;
   Work wk;
-  wk.reverse = 0;
+  wk.reverse = 0; wk.pol_a = wk.pol_b = kEvictNormal;
   wk.m_tiles = ceil_div(Mo, kBM); wk.n_tiles = ceil_div(No, BN);
   wk.kb_total = (int)ceil_div_ll(P, kBK);
   wk.n_cols = No;

@@ -697,6 +697,7 @@ static int sigma_chain(bn_mlp* h, const float* params, const float* origins, int
   prm.P = (long long)N * S; prm.o_stride = o_stride; prm.d_stride = d_stride; prm.S = S;
   prm.L = h->L; prm.skip = h->skip; prm.n_freq = c.n_freq_xyz;
   prm.trace = h->chain_trace;
+  prm.pol_w = tc::pol_weights(); prm.pol_s = tc::pol_stream();
   prm.noload = getenv("BN_CHAIN_NOLOAD") != nullptr;
   const int n_blocks = (int)ceil_div_ll(prm.P, 256);
   constexpr int smem = chain::sigma_chain_smem();
@@ -739,7 +740,8 @@ static int train_chain(bn_mlp* h, const float* params, const float* origins, int
   prm.L = h->L; prm.skip = h->skip; prm.n_freq = c.n_freq_xyz;
   prm.store_c = keep_c ? 1 : 0; prm.h_from = train ? 0 : h->L - 1;
   prm.trace = h->chain_trace;
-  prm.two_pass = getenv("BN_CHAIN_ONEPASS") == nullptr;        // A/B timing aid, read per launch
+  prm.two_pass = getenv("BN_CHAIN_TWOPASS") != nullptr;        // experiment knob (measured slower: 392 vs 355 us), read per launch
+  prm.pol_w = tc::pol_weights(); prm.pol_s = tc::pol_stream();
   const int n_blocks = (int)ceil_div_ll(P, 256);
   constexpr int smem = chain::chain_smem<true>();
   // experiment knob: one weight stage traded for a second cosine staging box per epilogue warp
@@ -908,6 +910,7 @@ static int dgrad_chain(bn_mlp* h, const Ws<__nv_bfloat16>& w, long long P, cudaS
   }
   if (int rc = tc::make_map_bf16(&prm.gin, w.GA, P, F, F, 64, 128)) return rc;
   prm.P = P; prm.L = h->L;
+  prm.pol_w = tc::pol_weights(); prm.pol_s = tc::pol_stream();
   const int n_blocks = (int)ceil_div_ll(P, 256);
   constexpr int smem = chain::dgrad_chain_smem();
   BN_CUDA(cudaFuncSetAttribute(chain::dgrad_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -52,6 +52,7 @@ struct SigmaChainParams {
   float* out;
   long long P;
   int o_stride, d_stride, S, L, skip, n_freq;
+  uint64_t pol_w, pol_s;                // L2 eviction policies: weight tiles (resident), activation stores (streaming)
   int noload;                           // timing experiment (BN_CHAIN_NOLOAD): the weight TMA loads are skipped, results are garbage
   long long* trace;                     // diagnostics (bn_debug_chain_trace): clock64() stamps of pair 0's leader CTA, first block
 };
@@ -71,6 +72,7 @@ struct TrainChainParams {
   int store_c;                          // 0: inference without analytic normals - no cosines are computed or stored
   int h_from;                           // h_l leaves the SM only for l >= h_from (0 when training, L-1 for inference)
   long long* trace;                     // diagnostics (bn_debug_chain_trace): clock64() stamps of pair 0's leader CTA, first block
+  uint64_t pol_w, pol_s;                // L2 eviction policies: weight tiles (resident), activation stores (streaming)
   int two_pass;                         // second-half epilogue: sines first, cosines from a second TMEM read (A/B knob BN_CHAIN_ONEPASS)
 };
 
@@ -90,7 +92,7 @@ __device__ __forceinline__ int layer_wcol(int l, int skip, int kb) { return (l =
 template <int STAGES>
 __device__ __forceinline__ void chain_producer(const CUtensorMap* wmap, const CUtensorMap* bmap, uint8_t* sW, uint64_t* wfull,
                                                uint64_t* wempty, int crank, int pair0, int npairs, int n_blocks, int L, int skip,
-                                               bool noload = false) {
+                                               uint64_t pol_w, bool noload = false) {
   int stage = 0; uint32_t phase = 0;
   for (int blk = pair0; blk < n_blocks; blk += npairs)
     for (int l = 0; l < L; ++l)
@@ -102,8 +104,8 @@ __device__ __forceinline__ void chain_producer(const CUtensorMap* wmap, const CU
           } else {
             if (crank == 0) mbar_expect_tx(&wfull[stage], 2 * kKBBytes);
             const uint32_t bar = mapa_u32(smem_u32(&wfull[stage]), 0);
-            if (kb == 0) tma_load_2d_pair(sW + stage * kKBBytes, bmap, bar, 0, l * kF + n * 256 + crank * 128);
-            else tma_load_2d_pair(sW + stage * kKBBytes, &wmap[l], bar, layer_wcol(l, skip, kb), n * 256 + crank * 128);
+            if (kb == 0) tma_load_2d_pair_hint(sW + stage * kKBBytes, bmap, bar, 0, l * kF + n * 256 + crank * 128, pol_w);
+            else tma_load_2d_pair_hint(sW + stage * kKBBytes, &wmap[l], bar, layer_wcol(l, skip, kb), n * 256 + crank * 128, pol_w);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -241,7 +243,7 @@ __global__ void __launch_bounds__(kThreads, 1) sigma_chain_kernel(const __grid_c
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) chain_producer<kWStages>(prm.wmap, &prm.bmap, sW, wfull, wempty, crank, pair0, npairs, n_blocks, L, skip, prm.noload != 0);
+    if (lane == 0) chain_producer<kWStages>(prm.wmap, &prm.bmap, sW, wfull, wempty, crank, pair0, npairs, n_blocks, L, skip, prm.pol_w, prm.noload != 0);
   } else if (warp == 1) {
     if (lane == 0 && crank == 0)
       chain_mma<kWStages>(sAct, sW, wfull, wempty, tfull, tempty, act_ready, kfree, tmem_base, pair0, npairs, n_blocks, L, skip, prm.trace);
@@ -378,7 +380,7 @@ __global__ void __launch_bounds__(kThreads, 1) train_chain_kernel(const __grid_c
   pdl_wait();
 
   if (warp == 0) {
-    if (lane == 0) chain_producer<kWStages>(prm.wmap, &prm.bmap, sW, wfull, wempty, crank, pair0, npairs, n_blocks, L, skip);
+    if (lane == 0) chain_producer<kWStages>(prm.wmap, &prm.bmap, sW, wfull, wempty, crank, pair0, npairs, n_blocks, L, skip, prm.pol_w);
   } else if (warp == 1) {
     if (lane == 0 && crank == 0)
       chain_mma<kWStages>(sAct, sW, wfull, wempty, tfull, tempty, act_ready, kfree, tmem_base, pair0, npairs, n_blocks, L, skip, prm.trace);
@@ -409,7 +411,7 @@ __global__ void __launch_bounds__(kThreads, 1) train_chain_kernel(const __grid_c
                    sAct, row_off, swz);
         fence_async_smem();
         __syncwarp();
-        if (lane == 0) { tma_store_2d(&prm.x3map, sAct + q * 4096, 0, grow0); bulk_commit(); }
+        if (lane == 0) { tma_store_2d_hint(&prm.x3map, sAct + q * 4096, 0, grow0, prm.pol_s); bulk_commit(); }
       }
       arrive_leader(&act_ready[0]);
       for (int l = 0; l < L; ++l) {
@@ -446,7 +448,7 @@ __global__ void __launch_bounds__(kThreads, 1) train_chain_kernel(const __grid_c
             ++cu;
             fence_async_smem();
             __syncwarp();
-            if (lane == 0) { tma_store_2d(&prm.cmap[l], box, n * 256 + u * 64 + hsel * 32, grow0); bulk_commit(); }
+            if (lane == 0) { tma_store_2d_hint(&prm.cmap[l], box, n * 256 + u * 64 + hsel * 32, grow0, prm.pol_s); bulk_commit(); }
           };
           // ---- sine of one unit: registers -> in place into K block 1 + 4n + u of the next layer, published at once ----
           auto publish_sin = [&](const uint32_t (&v)[32], int u) {
@@ -514,7 +516,7 @@ __global__ void __launch_bounds__(kThreads, 1) train_chain_kernel(const __grid_c
             if (leader) {
 #pragma unroll
               for (int u = 0; u < 4; ++u)
-                tma_store_2d(&prm.hmap[l], sAct + (1 + n * 4 + u) * kKBBytes + q * 4096, n * 256 + u * 64, grow0);
+                tma_store_2d_hint(&prm.hmap[l], sAct + (1 + n * 4 + u) * kKBBytes + q * 4096, n * 256 + u * 64, grow0, prm.pol_s);
               bulk_commit();
             }
           }

@@ -31,6 +31,7 @@ struct DgradChainParams {
   CUtensorMap cmap[kMaxLayers];          // [l]: c_{l-1} [P, F], boxes 64 columns x 32 rows
   CUtensorMap gout[kMaxLayers];          // [l]: dZ_{l-1} [P, F], boxes 64 columns x 32 rows
   CUtensorMap gin;                       // dZ_{L-1} [P, F], boxes 64 columns x 128 rows
+  uint64_t pol_w, pol_s;                 // L2 eviction policies: weight tiles (resident), streamed activations
   long long P;
   int L;
 };
@@ -97,7 +98,7 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad_chain_kernel(const __grid_c
             for (int kb = 0; kb < kDKB; ++kb) {
               mbar_wait(&wempty[stage], phase ^ 1);
               if (crank == 0) mbar_expect_tx(&wfull[stage], 2 * kKBBytes);
-              tma_load_2d_pair(sW + stage * kKBBytes, &prm.wmap[l], mapa_u32(smem_u32(&wfull[stage]), 0), kb * 64, n * 256 + crank * 128);
+              tma_load_2d_pair_hint(sW + stage * kKBBytes, &prm.wmap[l], mapa_u32(smem_u32(&wfull[stage]), 0), kb * 64, n * 256 + crank * 128, prm.pol_w);
               if (++stage == kDWStages) { stage = 0; phase ^= 1; }
             }
     }
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad_chain_kernel(const __grid_c
         mbar_wait(blk_free, bf_ph ^ 1); bf_ph ^= 1;              // the previous block's stores out of the K blocks are done
         for (int kb = 0; kb < kDKB; ++kb) {
           if (crank == 0) mbar_expect_tx(&gin_full[kb], 2 * kKBBytes);
-          tma_load_2d_pair(sAct + kb * kKBBytes, &prm.gin, mapa_u32(smem_u32(&gin_full[kb]), 0), kb * 64, row0);
+          tma_load_2d_pair_hint(sAct + kb * kKBBytes, &prm.gin, mapa_u32(smem_u32(&gin_full[kb]), 0), kb * 64, row0, prm.pol_s);
         }
         for (int l = L - 1; l >= 1; --l)
           for (int n = 0; n < 2; ++n)
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad_chain_kernel(const __grid_c
                 uint64_t* full = &cfull[q * kDCBoxes + cslot];
                 mbar_wait(&cempty[q * kDCBoxes + cslot], cphase ^ 1);
                 mbar_expect_tx(full, 4096);
-                tma_load_2d(sC + (q * kDCBoxes + cslot) * 4096, &prm.cmap[l], full, n * 256 + u * 64, row0 + q * 32);
+                tma_load_2d_hint(sC + (q * kDCBoxes + cslot) * 4096, &prm.cmap[l], full, n * 256 + u * 64, row0 + q * 32, prm.pol_s);
               }
               if (++cslot == kDCBoxes) { cslot = 0; cphase ^= 1; }
             }
@@ -231,7 +232,7 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad_chain_kernel(const __grid_c
           if (leader) {
 #pragma unroll
             for (int u = 0; u < 4; ++u)
-              tma_store_2d(&prm.gout[l], sAct + (4 * n + u) * kKBBytes + q * 4096, n * 256 + u * 64, grow0);
+              tma_store_2d_hint(&prm.gout[l], sAct + (4 * n + u) * kKBBytes + q * 4096, n * 256 + u * 64, grow0, prm.pol_s);
             bulk_commit();
           }
         }

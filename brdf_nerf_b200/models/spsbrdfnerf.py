@@ -212,6 +212,17 @@ class SpSBRDFNeRF(nn.Module):
             L.load().bn_mlp_destroy(self._handle)
             self._handle = None
 
+    def rebind_grads(self, bucket: torch.Tensor):
+        """Make `bucket` (fp32, same length and device as `flat_params`) the flat gradient buffer: every p.grad becomes a
+        view of it.  Used by the data-parallel trainer to place the bucket in peer-mapped memory (brdf_nerf_b200.ddp)."""
+        self._ensure_flat()
+        if bucket.numel() != self._flat.numel() or bucket.device != self._flat.device or bucket.dtype != torch.float32:
+            raise ValueError("gradient bucket must match flat_params in length, device and dtype")
+        bucket.copy_(self._flat_grad)
+        for _, p, off in self._layout()[0]:
+            p.grad = bucket[off:off + p.numel()].view(p.shape)
+        self._flat_grad = bucket
+
     def offsets(self) -> Dict[str, int]:
         return {name: off for name, _, off in self._layout()[0]}
 

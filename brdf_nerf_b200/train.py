@@ -68,9 +68,15 @@ class Trainer:
         self.use_depth_loss = True          # switched off by the schedule after ds_drop (main.py:248)
         self.use_normal_reg = True          # NormalRegLoss once train_steps > nrrg_on (main.py:272,280); needs nr_reg_*_lambda > 0
         self.use_hard_surface = False       # HardSurfaceLoss once epoch > 2 (main.py:292); needs hs_lambda > 0
-        # the captured graph includes Adam (one host launch per step).  With world_size > 1 the NCCL all-reduce stays
-        # outside the graph: captured, it ran slower on 2 B200s (2.80 vs 2.53 ms/step) and stalled process-group teardown
-        self.whole_step_graph = self.world == 1
+        # the captured graph includes Adam (one host launch per step).  A torch.distributed (NCCL) all-reduce stays outside
+        # the graph: captured, it ran slower on 2 B200s (2.80 vs 2.53 ms/step) and stalled process-group teardown.
+        # With world_size > 1 on one NVLink node the bucket lives in peer-mapped memory and the exchange is a kernel of this
+        # library (brdf_nerf_b200.ddp.PeerExchange, csrc/ddp.cu): capturable, so the graph again holds the whole step.
+        self._exchange = None
+        if self.world > 1:
+            from . import ddp
+            self._exchange = ddp.make_exchange(model, process_group)
+        self.whole_step_graph = self.world == 1 or self._exchange is not None
         self._opt_state = None              # device [lr, step, bc1, sqrt(bc2)] of the graph-captured Adam
         self._dev_lr, self._dev_step, self._graph_updates = None, 0, False
         # host feed (prefetch / read_loss_async): a copy stream next to the compute stream, two staging batches
@@ -130,9 +136,16 @@ class Trainer:
             self.v[off:off + n].zero_()
         self._frozen = runs
 
+    def _exchange_grads(self) -> float:
+        """Sum the gradient bucket over the ranks; returns the scale (1 / world) the optimizer applies."""
+        if self._exchange is not None:
+            self._exchange.all_reduce_()
+            return 1.0 / self.world
+        return allreduce_grads_(self.model.flat_grads, self.world, self.pg)
+
     def _reduce_and_update(self):
         model = self.model
-        scale = allreduce_grads_(model.flat_grads, self.world, self.pg)
+        scale = self._exchange_grads()
         self.step_count += 1
         ops.adam_step(model.flat_params, model.flat_grads, self.m, self.v, self.lr, self.step_count,
                       grad_scale=scale)
@@ -277,7 +290,7 @@ class Trainer:
             model.sync_weights(force=True)
             self._loss = self._step_impl(self._static, None, rkw)
             if whole_step:
-                scale = allreduce_grads_(model.flat_grads, self.world, self.pg)
+                scale = self._exchange_grads()
                 ops.adam_step_graph(model.flat_params, model.flat_grads, self.m, self.v, self._opt_state, grad_scale=scale)
         self.graph_launches = int(lib.bn_launch_count() - lc0)     # library kernels replayed by every graph launch
         return g

@@ -406,6 +406,25 @@ int bn_debug_gemm_epi(int kind, const void* A, long long lda, const void* B, lon
                       const void* add, const void* mul, float* colsum, int pad_lo, int pad_hi,
                       long long M, int N, long long K, cudaStream_t stream);
 
+/* Data-parallel gradient exchange over NVLink peer memory (csrc/ddp.cu): in-place two-shot all-reduce (sum) of the flat fp32
+ * gradient bucket, one kernel, CUDA-graph capturable.  Replaces the DDP all-reduce that Lightning runs for the reference
+ * (main.py:720-731).  peer_bufs[p] / peer_flags[p]: rank p's bucket / flag array as mapped into THIS process (symmetric
+ * memory: e.g. torch.distributed._symmetric_memory rendezvous), host arrays of `world` pointers; every rank's flag array
+ * holds bn_allreduce_p2p_flag_words() uint32, zero-initialised once; epoch: local device array of 128 uint32, zero-
+ * initialised once; n: bucket length in floats (multiple of 4); n_blocks (<= 128) must be equal on all ranks.  Every rank
+ * must launch the call once per step; the sum is formed in rank order, so all ranks end with bit-identical buckets. */
+int bn_allreduce_p2p(void* const* peer_bufs, void* const* peer_flags, uint32_t* epoch, int64_t n, int rank, int world,
+                     int n_blocks, cudaStream_t stream);
+int bn_allreduce_p2p_flag_words(void);
+/* Peer-mapped device memory for bn_allreduce_p2p (CUDA IPC): every rank allocates its bucket with bn_peer_alloc (zeroed),
+ * exports a 64-byte handle (bn_peer_export), sends it to the other ranks (any host channel: torch.distributed
+ * all_gather), and opens theirs (bn_peer_open: the mapping is usable by kernels of this process, peer access over NVLink). */
+int bn_peer_alloc(size_t bytes, void** ptr);
+int bn_peer_free(void* ptr);
+int bn_peer_export(void* ptr, void* handle64);
+int bn_peer_open(const void* handle64, void** ptr);
+int bn_peer_close(void* ptr);
+
 /* Unit-test hook: where a per-point activation tensor of a forward call lives inside the caller's MLP workspace
  * (the layout bn_mlp_workspace_bytes sizes for `n_points`, `flags`).  which 0: the encoding X3 (64 columns),
  * 1: h_l = sin(.) of trunk layer `layer`, 2: c_l = w0 cos(.) of trunk layer `layer` (training / analytic normals only).

@@ -47,14 +47,14 @@ def main():
         sig = torch.empty((n, S), dtype=torch.float32, device=dev)
         fn = lambda: ops.mlp_trunk_forward(m, rays[:, 0:3], 11, rays[:, 3:6], 11, z, flags, n * S, 0, None, ws)
         for rep in range(3):
-            for tag, env in (("two-pass", None), ("one-pass", "1")):
+            for tag, env in (("L2 hints", None), ("no hints", "1")):
                 if env:
-                    os.environ["BN_CHAIN_ONEPASS"] = env
+                    os.environ["BN_NO_L2_HINTS"] = env
                 else:
-                    os.environ.pop("BN_CHAIN_ONEPASS", None)
+                    os.environ.pop("BN_NO_L2_HINTS", None)
                 us = timeit(fn)
                 print(f"train chain {tag:9s} P={n * S:7d} rep {rep}: {us:8.1f} us  {flops / us / 1e6:7.1f} TFLOP/s", flush=True)
-        os.environ.pop("BN_CHAIN_ONEPASS", None)
+        os.environ.pop("BN_NO_L2_HINTS", None)
         ws1 = m.workspace(n * S, L.MLP_SIGMA_ONLY, tag="ws_sigma")
         fs = lambda: ops.mlp_forward(m, rays[:, 0:3], 11, rays[:, 3:6], 11, z, L.MLP_SIGMA_ONLY, sig, 1, ws1)
         us = timeit(fs)
@@ -63,19 +63,32 @@ def main():
     batch = make_rays(n, depth_supervision=True).to(dev)
     res = {}
     for rep in range(2):
-        for tag, env in (("dgrad chain", None), ("per-layer dgrad", "1")):
-            if env:
-                os.environ["BN_NO_DGRAD_CHAIN"] = env
-            else:
-                os.environ.pop("BN_NO_DGRAD_CHAIN", None)
+        for tag, env, env2 in (("dgrad chain", None, None), ("per-layer dgrad", "1", None), ("chain, no L2 hints", None, "1"),
+                               ("per-layer, no hints", "1", "1")):
+            for k, v in (("BN_NO_DGRAD_CHAIN", env), ("BN_NO_L2_HINTS", env2)):
+                if v:
+                    os.environ[k] = v
+                else:
+                    os.environ.pop(k, None)
             torch.manual_seed(0)
             mm = load_model(args, precision="bf16").to(dev)
             tr = Trainer(mm, args, use_graph=True)
             us = timeit(lambda: tr.step(batch), iters=30, warm=5)
-            print(f"training step, {tag:16s} rep {rep}: {us:8.1f} us/step  {n / us * 1e3:8.1f} k rays/s", flush=True)
+            lib = L.load()
+            lib.bn_profile_enable(1)
+            eager = Trainer(mm, args, use_graph=False)
+            for _ in range(3):
+                eager.step(batch)
+            import ctypes as C_
+            cnt = (C_.c_longlong * 4)(); tms = (C_.c_double * 4)(); work = (C_.c_double * 4)()
+            lib.bn_profile_collect(4, cnt, tms, work)
+            lib.bn_profile_enable(0)
+            kinds = "  ".join(f"{nm} {tms[i] / 3 * 1e3:7.1f} us ({cnt[i] // 3})" for i, nm in enumerate(("tn", "nt_wgrad", "chain_fwd", "chain_dgrad")))
+            print(f"training step, {tag:20s} rep {rep}: {us:8.1f} us/step  {n / us * 1e3:8.1f} k rays/s | per step (serialised): {kinds}", flush=True)
             del tr, mm
             torch.cuda.empty_cache()
     os.environ.pop("BN_NO_DGRAD_CHAIN", None)
+    os.environ.pop("BN_NO_L2_HINTS", None)
 
 
 if __name__ == "__main__":
