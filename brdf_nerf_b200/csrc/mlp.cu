@@ -740,7 +740,8 @@ static int train_chain(bn_mlp* h, const float* params, const float* origins, int
   prm.L = h->L; prm.skip = h->skip; prm.n_freq = c.n_freq_xyz;
   prm.store_c = keep_c ? 1 : 0; prm.h_from = train ? 0 : h->L - 1;
   prm.trace = h->chain_trace;
-  prm.two_pass = getenv("BN_CHAIN_TWOPASS") != nullptr;        // experiment knob (measured slower: 392 vs 355 us), read per launch
+  prm.c_stg = getenv("BN_CHAIN_CSTG") != nullptr;             // experiment knob, read per launch
+  for (int l = 0; l < h->L; ++l) prm.cptr[l] = keep_c ? w.C[l] : nullptr;
   prm.pol_w = tc::pol_weights(); prm.pol_s = tc::pol_stream();
   const int n_blocks = (int)ceil_div_ll(P, 256);
   constexpr int smem = chain::chain_smem<true>();
@@ -912,8 +913,11 @@ static int dgrad_chain(bn_mlp* h, const Ws<__nv_bfloat16>& w, long long P, cudaS
   prm.P = P; prm.L = h->L;
   prm.pol_w = tc::pol_weights(); prm.pol_s = tc::pol_stream();
   const int n_blocks = (int)ceil_div_ll(P, 256);
-  constexpr int smem = chain::dgrad_chain_smem();
-  BN_CUDA(cudaFuncSetAttribute(chain::dgrad_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  static_assert(chain::dgrad_chain_smem<3, 3>() == chain::dgrad_chain_smem<4, 2>(), "both variants fill the same shared memory");
+  constexpr int smem = chain::dgrad_chain_smem<3, 3>();
+  const bool deep_w = getenv("BN_DCHAIN_W4C2") != nullptr;      // A/B knob: 4 weight stages + 2 c boxes instead of 3 + 3
+  auto kern = deep_w ? chain::dgrad_chain_kernel<4, 2> : chain::dgrad_chain_kernel<3, 3>;
+  BN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * min(n_blocks, h->num_sms / 2));
   cfg.blockDim = dim3(tc::kThreads);
@@ -924,7 +928,7 @@ static int dgrad_chain(bn_mlp* h, const Ws<__nv_bfloat16>& w, long long P, cudaS
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   prof_begin(3, 2.0 * (double)P * (double)(h->L - 1) * F * F, s);
-  BN_CUDA(cudaLaunchKernelEx(&cfg, chain::dgrad_chain_kernel, prm));
+  BN_CUDA(cudaLaunchKernelEx(&cfg, kern, prm));
   const int rc = after_launch("dgrad_chain_kernel");
   prof_end(s);
   return rc;

@@ -73,7 +73,8 @@ struct TrainChainParams {
   int h_from;                           // h_l leaves the SM only for l >= h_from (0 when training, L-1 for inference)
   long long* trace;                     // diagnostics (bn_debug_chain_trace): clock64() stamps of pair 0's leader CTA, first block
   uint64_t pol_w, pol_s;                // L2 eviction policies: weight tiles (resident), activation stores (streaming)
-  int two_pass;                         // second-half epilogue: sines first, cosines from a second TMEM read (A/B knob BN_CHAIN_ONEPASS)
+  __nv_bfloat16* cptr[kMaxLayers];      // C_l base pointers (c_stg experiment: direct global stores)
+  int c_stg;                            // 1: cosines leave through st.global instead of staging box + TMA (BN_CHAIN_CSTG)
 };
 
 template <bool kTrain> __host__ __device__ constexpr int chain_smem() {
@@ -426,85 +427,66 @@ __global__ void __launch_bounds__(kThreads, 1) train_chain_kernel(const __grid_c
           const uint32_t tbase = tmem_base + t_lane + n * 256 + hsel * 32;
           const bool store_h = l >= prm.h_from;
           const bool l0 = l == 0;
-          // ---- cosine of one unit: registers -> this warp's staging box -> TMA (own bulk group) ----
-          auto store_cos = [&](const uint32_t (&v)[32], int u) {
-            uint32_t pc[16];
+          __nv_bfloat16* const crow = prm.cptr[l] + (long long)(grow0 + lane) * kF + n * 256 + hsel * 32;   // c_stg only
+          const bool row_ok = (long long)grow0 + lane < prm.P;
+          tmem_ld32_issue(tbase, va);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            tmem_wait_ld();
+            uint32_t (&v)[32] = (u & 1) ? vb : va;
+            if (u < 3) tmem_ld32_issue(tbase + (u + 1) * 64, (u & 1) ? va : vb);
+            else { fence_before_sync(); arrive_leader(&tempty[n]); }
+            // the accumulator is the pre-activation (bias added by the tensor core): per element ONE range reduction feeds
+            // both MUFU.SIN and MUFU.COS; w0 = 30 only exists in layer 0, every other layer skips both multiplies
+            uint32_t pk[16], pc[16];
             if (l0) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j)
-                pc[j] = bf_pack(30.0f * __cosf(30.0f * __uint_as_float(v[2 * j])), 30.0f * __cosf(30.0f * __uint_as_float(v[2 * j + 1])));
+              for (int j = 0; j < 16; ++j) {
+                const float a0 = 30.0f * __uint_as_float(v[2 * j]), a1 = 30.0f * __uint_as_float(v[2 * j + 1]);
+                pk[j] = bf_pack(__sinf(a0), __sinf(a1));
+                if (prm.store_c) pc[j] = bf_pack(30.0f * __cosf(a0), 30.0f * __cosf(a1));
+              }
             } else {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) pc[j] = bf_pack(__cosf(__uint_as_float(v[2 * j])), __cosf(__uint_as_float(v[2 * j + 1])));
+              for (int j = 0; j < 16; ++j) {
+                const float a0 = __uint_as_float(v[2 * j]), a1 = __uint_as_float(v[2 * j + 1]);
+                pk[j] = bf_pack(__sinf(a0), __sinf(a1));
+                if (prm.store_c) pc[j] = bf_pack(__cosf(a0), __cosf(a1));
+              }
             }
             uint8_t* box = cbox + (kCBox2 ? (cu & 1) * 2048 : 0);
-            // the box was read out by the TMA (with two boxes: the store before the previous one); the leader's wait also
-            // covers the h_l boxes it committed at the end of the previous half
-            if (lane == 0) { if (kCBox2 && !leader) bulk_wait_read1(); else bulk_wait_read0(); }
-            __syncwarp();
+            if (prm.store_c && !prm.c_stg) {
+              // cosines: registers -> this warp's staging box -> TMA.  The box was read out by the TMA (with two boxes: the
+              // store before the previous one); the leader's wait also covers the h_l boxes of the previous half
+              if (lane == 0) { if (kCBox2 && !leader) bulk_wait_read1(); else bulk_wait_read0(); }
+              __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              sts128(box + crow_off + ((j << 4) ^ cswz), pc[4 * j], pc[4 * j + 1], pc[4 * j + 2], pc[4 * j + 3]);
-            ++cu;
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) { tma_store_2d_hint(&prm.cmap[l], box, n * 256 + u * 64 + hsel * 32, grow0, prm.pol_s); bulk_commit(); }
-          };
-          // ---- sine of one unit: registers -> in place into K block 1 + 4n + u of the next layer, published at once ----
-          auto publish_sin = [&](const uint32_t (&v)[32], int u) {
-            uint32_t pk[16];
-            if (l0) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) pk[j] = bf_pack(__sinf(30.0f * __uint_as_float(v[2 * j])), __sinf(30.0f * __uint_as_float(v[2 * j + 1])));
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) pk[j] = bf_pack(__sinf(__uint_as_float(v[2 * j])), __sinf(__uint_as_float(v[2 * j + 1])));
+              for (int j = 0; j < 4; ++j)
+                sts128(box + crow_off + ((j << 4) ^ cswz), pc[4 * j], pc[4 * j + 1], pc[4 * j + 2], pc[4 * j + 3]);
+              ++cu;
             }
-            // second half: every MMA of this layer has retired (tfull[1]); first half: K block 1 + u still feeds the second
-            // half's MMAs until kfree[u].  The leader's h_l stores of the previous layer out of this K block were read out
-            // long ago (it waits for them before its next cosine store)
+            // sines: in place into K block 1 + 4n + u of the next layer.  Second half: every MMA of this layer has retired
+            // (tfull[1]); first half: K block 1 + u still feeds the second half's MMAs until kfree[u].  (The leader's h_l
+            // stores of the previous layer out of this K block were read out long ago: it waits for them at every cosine box.)
             if (n == 0) mbar_wait(&kfree[u], kf_ph);
             uint8_t* kbp = sAct + (1 + 4 * n + u) * kKBBytes;
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               sts128(kbp + row_off + (((hsel * 4 + j) << 4) ^ swz), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-            fence_async_smem();
-            if (!last) arrive_leader(&act_ready[1 + 4 * n + u]);
-          };
-          if (n == 0 || !prm.store_c || !prm.two_pass) {
-            // one pass: sine and cosine of a unit share the range reduction.  (First half: off the critical path, it runs in
-            // the shadow of the second half's MMAs.  Inference without cosines: nothing else to do.)
-            tmem_ld32_issue(tbase, va);
+            fence_async_smem();                                  // ONE proxy fence covers both the K block and the cosine box
+            if (!last) arrive_leader(&act_ready[1 + 4 * n + u]); else __syncwarp();
+            if (prm.store_c) {
+              if (prm.c_stg) {
+                // experiment (BN_CHAIN_CSTG=1): cosines straight from registers, 64 contiguous bytes per row — no staging box,
+                // no wait for the previous store's read-out, at the price of 128 LSU wavefronts per unit
+                if (row_ok) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              tmem_wait_ld();
-              uint32_t (&v)[32] = (u & 1) ? vb : va;
-              if (u < 3) tmem_ld32_issue(tbase + (u + 1) * 64, (u & 1) ? va : vb);
-              else { fence_before_sync(); arrive_leader(&tempty[n]); }
-              publish_sin(v, u);
-              if (prm.store_c) store_cos(v, u);
-            }
-          } else {
-            // Second half, training: the next layer's first half can only finish once K blocks 5..8 are published, and
-            // this half's MMAs could not start before the previous layer's did the same — the chain's critical path runs
-            // through THIS epilogue.  Pass A does only what the next layer waits for (sine -> K block -> publish, half of
-            // the MUFU work and none of the store hand-shakes); pass B reads the accumulator again (TMEM reads are cheap)
-            // for the cosines, off the critical path, while the next layer's first half is being multiplied.
-            tmem_ld32_issue(tbase, va);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              tmem_wait_ld();
-              uint32_t (&v)[32] = (u & 1) ? vb : va;
-              tmem_ld32_issue(tbase + ((u + 1) & 3) * 64, (u & 1) ? va : vb);      // u == 3: unit 0 again, for pass B
-              publish_sin(v, u);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              tmem_wait_ld();
-              uint32_t (&v)[32] = (u & 1) ? vb : va;
-              if (u < 3) tmem_ld32_issue(tbase + (u + 1) * 64, (u & 1) ? va : vb);
-              else { fence_before_sync(); arrive_leader(&tempty[n]); }
-              store_cos(v, u);
+                  for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<uint4*>(crow + u * 64 + j * 8) = make_uint4(pc[4 * j], pc[4 * j + 1], pc[4 * j + 2], pc[4 * j + 3]);
+                }
+              } else if (lane == 0) {
+                tma_store_2d_hint(&prm.cmap[l], box, n * 256 + u * 64 + hsel * 32, grow0, prm.pol_s); bulk_commit();
+              }
             }
           }
           if (n == 0) kf_ph ^= 1;

@@ -23,8 +23,8 @@ namespace bn {
 namespace chain {
 
 constexpr int kDKB = kF / 64;            // 8 activation K blocks (no encoding block: gradients w.r.t. the inputs are not needed)
-constexpr int kDWStages = 3;             // weight ring
-constexpr int kDCBoxes = 3;              // c boxes per TMEM quadrant (4 KB each): two units of prefetch
+// weight ring depth kDWStages and c boxes per TMEM quadrant kDCBoxes (4 KB each) are template parameters: (3, 3) = two units
+// of c prefetch, (4, 2) = a deeper weight ring; both fill the 227 KB
 
 struct DgradChainParams {
   CUtensorMap wmap[kMaxLayers];          // [l]: W_l^T restricted to the h-part rows: [F (in), F (out)] bf16, boxes 64 x 128
@@ -36,10 +36,11 @@ struct DgradChainParams {
   int L;
 };
 
-__host__ __device__ constexpr int dgrad_chain_smem() {
+template <int kDWStages, int kDCBoxes> __host__ __device__ constexpr int dgrad_chain_smem() {
   return kDKB * kKBBytes + kDWStages * kKBBytes + 4 * kDCBoxes * 4096 + 1024 + 1024;
 }
 
+template <int kDWStages, int kDCBoxes>
 __global__ void __launch_bounds__(kThreads, 1) dgrad_chain_kernel(const __grid_constant__ DgradChainParams prm) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));

@@ -47,14 +47,17 @@ def main():
         sig = torch.empty((n, S), dtype=torch.float32, device=dev)
         fn = lambda: ops.mlp_trunk_forward(m, rays[:, 0:3], 11, rays[:, 3:6], 11, z, flags, n * S, 0, None, ws)
         for rep in range(3):
-            for tag, env in (("L2 hints", None), ("no hints", "1")):
-                if env:
-                    os.environ["BN_NO_L2_HINTS"] = env
-                else:
-                    os.environ.pop("BN_NO_L2_HINTS", None)
+            for tag, envs in (("default", {}), ("c via st.global", {"BN_CHAIN_CSTG": "1"}), ("two c boxes", {"BN_CHAIN_CBOX2": "1"}),
+                              ("no L2 hints", {"BN_NO_L2_HINTS": "1"})):
+                for k in ("BN_CHAIN_CSTG", "BN_NO_L2_HINTS"):
+                    os.environ.pop(k, None)
+                if "BN_CHAIN_CBOX2" in envs:
+                    continue          # read once per process (static): timed by its own run of this script
+                os.environ.update(envs)
                 us = timeit(fn)
-                print(f"train chain {tag:9s} P={n * S:7d} rep {rep}: {us:8.1f} us  {flops / us / 1e6:7.1f} TFLOP/s", flush=True)
-        os.environ.pop("BN_NO_L2_HINTS", None)
+                print(f"train chain {tag:16s} P={n * S:7d} rep {rep}: {us:8.1f} us  {flops / us / 1e6:7.1f} TFLOP/s", flush=True)
+        for k in ("BN_CHAIN_CSTG", "BN_NO_L2_HINTS"):
+            os.environ.pop(k, None)
         ws1 = m.workspace(n * S, L.MLP_SIGMA_ONLY, tag="ws_sigma")
         fs = lambda: ops.mlp_forward(m, rays[:, 0:3], 11, rays[:, 3:6], 11, z, L.MLP_SIGMA_ONLY, sig, 1, ws1)
         us = timeit(fs)
@@ -63,9 +66,8 @@ def main():
     batch = make_rays(n, depth_supervision=True).to(dev)
     res = {}
     for rep in range(2):
-        for tag, env, env2 in (("dgrad chain", None, None), ("per-layer dgrad", "1", None), ("chain, no L2 hints", None, "1"),
-                               ("per-layer, no hints", "1", "1")):
-            for k, v in (("BN_NO_DGRAD_CHAIN", env), ("BN_NO_L2_HINTS", env2)):
+        for tag, env, env2 in (("dgrad chain W3C3", None, None), ("per-layer dgrad", "1", None), ("dgrad chain W4C2", None, "1")):
+            for k, v in (("BN_NO_DGRAD_CHAIN", env), ("BN_DCHAIN_W4C2", env2)):
                 if v:
                     os.environ[k] = v
                 else:
@@ -88,7 +90,7 @@ def main():
             del tr, mm
             torch.cuda.empty_cache()
     os.environ.pop("BN_NO_DGRAD_CHAIN", None)
-    os.environ.pop("BN_NO_L2_HINTS", None)
+    os.environ.pop("BN_DCHAIN_W4C2", None)
 
 
 if __name__ == "__main__":
