@@ -915,8 +915,10 @@ static int dgrad_chain(bn_mlp* h, const Ws<__nv_bfloat16>& w, long long P, cudaS
   const int n_blocks = (int)ceil_div_ll(P, 256);
   static_assert(chain::dgrad_chain_smem<3, 3>() == chain::dgrad_chain_smem<4, 2>(), "both variants fill the same shared memory");
   constexpr int smem = chain::dgrad_chain_smem<3, 3>();
-  const bool deep_w = getenv("BN_DCHAIN_W4C2") != nullptr;      // A/B knob: 4 weight stages + 2 c boxes instead of 3 + 3
-  auto kern = deep_w ? chain::dgrad_chain_kernel<4, 2> : chain::dgrad_chain_kernel<3, 3>;
+  // 4 weight stages + 2 c boxes per quadrant measured faster than 3 + 3 (459-498 vs 538-557 us per launch at P = 131 072,
+  // profiles/r02h_ab.txt); BN_DCHAIN_W3C3=1 selects the other split for A/B runs
+  const bool w3c3 = getenv("BN_DCHAIN_W3C3") != nullptr;
+  auto kern = w3c3 ? chain::dgrad_chain_kernel<3, 3> : chain::dgrad_chain_kernel<4, 2>;
   BN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * min(n_blocks, h->num_sms / 2));

@@ -57,9 +57,20 @@ class SpSBRDFNeRF(nn.Module):
         super().__init__()
         if not siren:
             raise NotImplementedError("siren=0 (ReLU trunk) is outside the CUDA hot path")
-        if beta or indirect_light or sun_v == "learned":
-            raise NotImplementedError("beta / indirect_light / sun_v='learned' are not on the CUDA hot path "
-                                      "(sun_v='learned' is broken in the reference itself, SURVEY App. C.2)")
+        # R19 of SURVEY §8a is knowingly partial: three optional output channels are refused
+        if sun_v == "learned":
+            raise NotImplementedError("sun_v='learned' raises NameError in the reference itself (spsbrdfnerf.py:697 reads the "
+                                      "undefined `xyz_features_`, SURVEY App. C.2): there is no behaviour to mirror")
+        if beta:
+            raise NotImplementedError("beta=True (transient-uncertainty channel: beta_from_xyz on [features | t-embedding], "
+                                      "spsbrdfnerf.py:571-575,708-711) is not built: no loss of the spsbrdf-nerf recipe reads it "
+                                      "(metrics.load_loss returns SNerfLoss for this model, metrics.py:170-171) and the README "
+                                      "recipes never pass --beta; `ts` is therefore accepted and ignored by render_rays")
+        if indirect_light:
+            raise NotImplementedError("indirect_light=True (sky_color head, spsbrdfnerf.py:562-568,704-706) is not built: the "
+                                      "reference reads it from the hard-coded channels out[..., 5:8] (spsbrdfnerf.py:154), which "
+                                      "is only the sky colour when sun_v='learned' (itself broken, App. C.2); with "
+                                      "sun_v='analystic' those channels are sky g, sky b and the next head's first output")
         if len(skips) > 1:
             raise NotImplementedError("one skip connection is supported")
         self.layers, self.skips, self.feat = layers, list(skips), feat

@@ -66,8 +66,8 @@ def main():
     batch = make_rays(n, depth_supervision=True).to(dev)
     res = {}
     for rep in range(2):
-        for tag, env, env2 in (("dgrad chain W3C3", None, None), ("per-layer dgrad", "1", None), ("dgrad chain W4C2", None, "1")):
-            for k, v in (("BN_NO_DGRAD_CHAIN", env), ("BN_DCHAIN_W4C2", env2)):
+        for tag, env, env2 in (("dgrad chain W4C2", None, None), ("per-layer dgrad", "1", None), ("dgrad chain W3C3", None, "1")):
+            for k, v in (("BN_NO_DGRAD_CHAIN", env), ("BN_DCHAIN_W3C3", env2)):
                 if v:
                     os.environ[k] = v
                 else:
@@ -90,7 +90,7 @@ def main():
             del tr, mm
             torch.cuda.empty_cache()
     os.environ.pop("BN_NO_DGRAD_CHAIN", None)
-    os.environ.pop("BN_DCHAIN_W4C2", None)
+    os.environ.pop("BN_DCHAIN_W3C3", None)
 
 
 if __name__ == "__main__":

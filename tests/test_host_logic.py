@@ -247,3 +247,19 @@ def test_algorithmic_flops_match_the_survey():
     assert abs(per_ray / 2 - 1.001e9) < 2e6                              # 1.001 G MAC per ray (fwd 414.6 M + bwd 586.5 M)
     shared = bench.mlp_flops_per_ray(args, 64, 128, shared_trunk=True)
     assert abs((per_ray - shared) / 2 - 64 * 1_896_448) < 1                # one trunk evaluation of the 64 stratified points saved
+
+
+def test_refused_options_cite_their_reason():
+    """R19 is knowingly partial: the three optional channels that are not built are refused at construction
+    with the reference lines that justify it (not silently ignored)."""
+    import pytest
+    import torch
+    from brdf_nerf_b200.config import named_config
+    from brdf_nerf_b200.models import load_model
+    for over, needle in ((dict(beta=True), "spsbrdfnerf.py:571-575"), (dict(indirect_light=True), "out[..., 5:8]"),
+                         (dict(sun_v="learned"), "NameError")):
+        args = named_config("lambertian", **over)
+        torch.manual_seed(0)
+        with pytest.raises(NotImplementedError) as e:
+            load_model(args)
+        assert needle in str(e.value), str(e.value)
