@@ -59,6 +59,88 @@ __device__ __forceinline__ void store_row(float* __restrict__ p, const float (&x
   }
 }
 
+// Narrow rows (Lambertian: C = 4, density pass: C = 1) at the path's standard ray length S = 128: the whole ray is loaded
+// up front — four 32-sample rows x (z + C channels) per lane, 2.6 KB in flight per warp — and then composited out of
+// registers.  The generic kernel below keeps two rows in flight (3.95 -> 4.4 TB/s at 65 536 rays); this one exists because
+// the Lambertian forward is the one on the headline configuration and was the furthest from the HBM roofline.
+template <int C>
+__global__ void __launch_bounds__(kRaysPerBlock * kWarp) composite_fwd128_kernel(CompositeFwd a) {
+  static_assert(C <= 4, "register budget: 4 rows x C channels per lane");
+  const int lane = threadIdx.x % kWarp;
+  const int r = blockIdx.x * kRaysPerBlock + threadIdx.x / kWarp;
+  if (r >= a.N) return;
+  constexpr int S = 128, R = S / kWarp;
+  const long long base = (long long)r * S;
+  constexpr int kSig = (C == 1) ? 0 : 3;
+  float z[R], nz[R], ir[R], x[R][C];
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+    const int i = k * kWarp + lane;
+    z[k] = __ldg(a.z + base + i);
+    load_row<C>(a.packed + (base + i) * C, x[k]);
+    nz[k] = a.noise ? __ldg(a.noise + base + i) : 0.f;
+    ir[k] = 0.f;
+    if constexpr (C > 1) { if (a.irr) ir[k] = __ldg(a.irr + base + i); }
+  }
+  float acc[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) acc[c] = 0.f;
+  float acc_i[4] = {0.f, 0.f, 0.f, 0.f};
+  float depth = 0.f, wsum = 0.f, carry = 1.0f;
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+    const int i = k * kWarp + lane;
+    float znext = __shfl_down_sync(kFull, z[k], 1);
+    const float zfirst_next = __shfl_sync(kFull, z[k + 1 < R ? k + 1 : k], 0);
+    if (lane == kWarp - 1) znext = zfirst_next;
+    float sg = x[k][kSig];
+    if (a.noise) sg += nz[k] * a.noise_std;
+    const float delta = (i + 1 < S) ? (znext - z[k]) : 1e10f;
+    const float al = 1.0f - expf(-delta * fmaxf(sg, 0.f));       // accurate expf: alpha feeds the guided sampler
+    const float f = 1.0f - al + 1e-10f;
+    float incl = warp_scan_mul(f, lane);
+    float excl = __shfl_up_sync(kFull, incl, 1);
+    if (lane == 0) excl = 1.0f;
+    const float T = carry * excl;
+    const float w = al * T;
+    carry *= __shfl_sync(kFull, incl, kWarp - 1);
+    if (a.alpha) a.alpha[base + i] = al;
+    if (a.trans) a.trans[base + i] = T;
+    a.weights[base + i] = w;
+    depth += w * z[k]; wsum += w;
+    if constexpr (C > 1) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) acc[c] += w * x[k][c];
+      if (a.irr) {
+        const float wi = w * ir[k];
+        acc_i[0] += wi * x[k][0]; acc_i[1] += wi * x[k][1]; acc_i[2] += wi * x[k][2]; acc_i[3] += wi;
+      }
+    }
+  }
+  depth = warp_sum(depth); wsum = warp_sum(wsum);
+  if (a.std) {
+    float s2 = 0.f;                                              // Σ w (z-d)² out of registers, same order as the generic kernel
+    __syncwarp();
+    for (int i = lane; i < S; i += kWarp) { float dz = a.z[base + i] - depth; s2 += dz * dz * a.weights[base + i]; }
+    s2 = warp_sum(s2);
+    if (lane == 0) a.std[r] = sqrtf(s2);
+  }
+  if constexpr (C > 1) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = warp_sum(acc[c]);
+    if (a.irr) { for (int c = 0; c < 4; ++c) acc_i[c] = warp_sum(acc_i[c]); }
+  }
+  if (lane == 0) {
+    a.depth[r] = depth;
+    if (a.wsum) a.wsum[r] = wsum;
+    if constexpr (C > 1) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) a.acc[(long long)r * C + c] = acc[c];
+      if (a.irr && a.acc_irr) { for (int c = 0; c < 4; ++c) a.acc_irr[r * 4 + c] = acc_i[c]; }
+    }
+  }
+}
+
 // C == 1 is the sigma-only pass (packed == sigma, nothing but depth accumulated).
 template <int C>
 __global__ void __launch_bounds__(kRaysPerBlock * kWarp) composite_fwd_kernel(CompositeFwd a) {
@@ -237,6 +319,12 @@ __global__ void __launch_bounds__(kRaysPerBlock * kWarp) composite_bwd_kernel(Co
 }
 
 template <int C> int launch_fwd(const CompositeFwd& a, cudaStream_t s) {
+  if constexpr (C <= 4) {
+    if (a.S == 128) {        // standard ray length of the full pass (64 stratified + 64 guided): whole ray in registers
+      composite_fwd128_kernel<C><<<ceil_div(a.N, kRaysPerBlock), kRaysPerBlock * kWarp, 0, s>>>(a);
+      return after_launch("composite_fwd128_kernel");
+    }
+  }
   composite_fwd_kernel<C><<<ceil_div(a.N, kRaysPerBlock), kRaysPerBlock * kWarp, 0, s>>>(a);
   return after_launch("composite_fwd_kernel");
 }

@@ -16,7 +16,7 @@
 
 namespace bn {
 
-constexpr int kDdpMaxWorld = 16;
+constexpr int kDdpMaxWorld = 8;      // one NVLink / NVSwitch node
 constexpr int kDdpMaxBlocks = 128;
 
 struct DdpArgs {
@@ -68,18 +68,26 @@ __global__ void __launch_bounds__(512) allreduce_p2p_kernel(const __grid_constan
     src[p] = reinterpret_cast<const float4*>(a.buf[p < W ? p : 0]);
     dst[p] = reinterpret_cast<float4*>(a.buf[p < W ? p : 0]);
   }
-  for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (long long)gridDim.x * blockDim.x) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 v[kDdpMaxWorld];
+  // two float4 per thread and iteration: 2 W remote loads in flight per thread (a peer load is a 2-4 us round trip over
+  // NVLink; the first version with one float4 per iteration took 41 us for 9.2 MB on 2 GPUs, latency bound)
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += 2 * stride) {
+    const long long j = i + stride;
+    const bool two = j < hi;
+    float4 v0[kDdpMaxWorld], v1[kDdpMaxWorld];
 #pragma unroll
     for (int p = 0; p < kDdpMaxWorld; ++p)
-      if (p < W) v[p] = __ldcv(src[p] + i);                       // all W loads in flight (never cached: peers rewrite it every step)
+      if (p < W) { v0[p] = __ldcv(src[p] + i); if (two) v1[p] = __ldcv(src[p] + j); }   // never cached: peers rewrite it every step
+    float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
 #pragma unroll
     for (int p = 0; p < kDdpMaxWorld; ++p)
-      if (p < W) { acc.x += v[p].x; acc.y += v[p].y; acc.z += v[p].z; acc.w += v[p].w; }   // rank order: the same sum everywhere
+      if (p < W) {                                                 // rank order: the same sum on every rank
+        s0.x += v0[p].x; s0.y += v0[p].y; s0.z += v0[p].z; s0.w += v0[p].w;
+        if (two) { s1.x += v1[p].x; s1.y += v1[p].y; s1.z += v1[p].z; s1.w += v1[p].w; }
+      }
 #pragma unroll
     for (int p = 0; p < kDdpMaxWorld; ++p)
-      if (p < W) dst[p][i] = acc;
+      if (p < W) { dst[p][i] = s0; if (two) dst[p][j] = s1; }
   }
   cross_gpu_barrier(a, 1, epoch);
   if (threadIdx.x == 0) a.epoch[blockIdx.x] = epoch;

@@ -30,7 +30,7 @@ class _RawCuda:
 class PeerExchange:
     """In-place sum of `bucket` (n fp32) over the ranks of `group` through NVLink peer memory."""
 
-    N_BLOCKS = 64
+    N_BLOCKS = 128
 
     def __init__(self, n_floats: int, device: torch.device, group=None):
         import torch.distributed as dist
@@ -89,6 +89,8 @@ def make_exchange(model, group=None) -> Optional[PeerExchange]:
     import os
     import torch.distributed as dist
     if os.environ.get("BN_NO_P2P") or not dist.is_initialized() or dist.get_backend(group) != "nccl":
+        return None
+    if dist.get_world_size(group) > 8:                      # the kernel addresses one NVLink / NVSwitch node (<= 8 peers)
         return None
     flat = model.flat_params
     if not flat.is_cuda:
