@@ -17,7 +17,7 @@ def main(path):
     for r in csv.DictReader(lines):
         if r.get("Metric Name") == "gpu__time_duration.sum":
             rows.append((r["Kernel Name"], float(r["Metric Value"]) / 1e3))
-    adam = [i for i, (k, _) in enumerate(rows) if "adam_kernel" in k]
+    adam = [i for i, (k, _) in enumerate(rows) if "adam_kernel" in k or "adam_state_kernel" in k]
     if len(adam) >= 2:
         step = rows[adam[0] + 1:adam[1] + 1]     # the first complete step of the capture window
     else:
