@@ -480,13 +480,23 @@ def run_ours(opts):
         import bench_composite
         n_c = 65536
         r = bench_composite.run(n_c, 128, report=lambda *_: None)
-        dom = r["composite_bwd C=16"]
-        roof_hbm = {"bound": "hbm", "kernel": "bn::composite_bwd_kernel<16> (BRDF-stage compositing backward, RPV111 channel block)",
+        # lead with the kernel of the HEADLINE configuration (Lambertian forward, C = 4); byte model = SURVEY 8d: read z + packed
+        # row, write alpha / T / w (32 B per sample at C = 4) + the per-ray outputs.  The backward's byte model (re-read z, row,
+        # alpha, T, w; write the row gradient) is this library's own count; SURVEY's coarser 92 B/sample figure is given beside it.
+        dom = r["composite_fwd C=4"]
+        surv = {"composite_fwd C=4": 32, "composite_fwd C=16": 56, "composite_bwd C=4": 92, "composite_bwd C=16": 92}
+        roof_hbm = {"bound": "hbm", "kernel": "bn::composite_fwd128_kernel<4> (Lambertian compositing forward: the K-C kernel of the headline configuration)",
                     "achieved": dom["gbs"], "peak": _peaks()["hbm"], "unit": "GB/s", "frac": dom["gbs"] / _peaks()["hbm"],
                     "peak_kind": f"{_peaks()['src']} HBM copy bandwidth (kernel timed alone, inputs rotated over 3 sets > L2)",
-                    "traffic": None, "algorithmic_bytes_per_launch": dom["bytes"], "us_per_launch": dom["us"],
+                    "traffic": NCU_KC_DRAM_BYTES["composite_fwd C=4"],
+                    "traffic_note": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/r02_ncu_full_kc_kernels.csv); "
+                                    "below the algorithmic bytes because the tail of the writes is still in L2 when the kernel ends",
+                    "algorithmic_bytes_per_launch": dom["bytes"], "us_per_launch": dom["us"],
                     "workload": f"{n_c} rays x 128 samples (one inference chunk); the 1024-ray training batch moves 7 MB and is latency bound",
-                    "all": {k: {"us": v["us"], "GB/s": v["gbs"], "frac": v["frac"]} for k, v in r.items()}}
+                    "all": {k: {"us": v["us"], "GB/s": v["gbs"], "frac": v["frac"], "algorithmic_bytes": v["bytes"],
+                                "ncu_dram_bytes": NCU_KC_DRAM_BYTES.get(k),
+                                "frac_at_survey_bytes_per_sample": surv[k] * n_c * 128 / (v["us"] * 1e-6) / 1e9 / _peaks()["hbm"]}
+                            for k, v in r.items()}}
     other = None
     if not opts.no_other_configs:
         del trainer
