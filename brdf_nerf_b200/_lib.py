@@ -13,15 +13,15 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbrdfnerf_b200.so")
 
-BN_NUM_LINEAR = 35
-BN_NUM_HEADS = 7
+BN_NUM_LINEAR = 37
+BN_NUM_HEADS = 8
 BN_LIN_SIGMA, BN_LIN_FEATS, BN_LIN_RGB0, BN_LIN_RGB2, BN_LIN_GRAD, BN_LIN_HEAD0 = 16, 17, 18, 19, 20, 21
 BN_PREC_FP32, BN_PREC_BF16 = 0, 1
 BN_BRDF_NONE, BN_BRDF_MICROFACET, BN_BRDF_RPV, BN_BRDF_HAPKE = 0, 1, 2, 3
 BN_IRR_ONES, BN_IRR_COS, BN_IRR_SUNVIS = 0, 1, 2
 MLP_SIGMA_ONLY, MLP_TRAIN, MLP_NORMAL_AN, MLP_NORMAL_LR = 1, 2, 4, 8
-MLP_ROUGH, MLP_RPV, MLP_HAPKE, MLP_HAPKE_THETA = 16, 32, 64, 128
-HEAD_NAMES = ("roughness", "k", "theta_rpv", "rhoc", "b", "c", "theta")     # BN_HEAD_* order
+MLP_ROUGH, MLP_RPV, MLP_HAPKE, MLP_HAPKE_THETA, MLP_BETA = 16, 32, 64, 128, 256
+HEAD_NAMES = ("roughness", "k", "theta_rpv", "rhoc", "b", "c", "theta", "beta")     # BN_HEAD_* order
 
 
 class ShadeCfg(C.Structure):
@@ -33,7 +33,7 @@ class ShadeCfg(C.Structure):
 
 class MlpCfg(C.Structure):
     _fields_ = [("feat", C.c_int), ("layers", C.c_int), ("skip_layer", C.c_int), ("n_freq_xyz", C.c_int),
-                ("normal_lr", C.c_int), ("viewdir", C.c_int), ("n_freq_dir", C.c_int), ("head_dim", C.c_int * BN_NUM_HEADS), ("precision", C.c_int),
+                ("normal_lr", C.c_int), ("viewdir", C.c_int), ("n_freq_dir", C.c_int), ("t_dims", C.c_int), ("head_dim", C.c_int * BN_NUM_HEADS), ("precision", C.c_int),
                 ("w_off", C.c_int64 * BN_NUM_LINEAR), ("b_off", C.c_int64 * BN_NUM_LINEAR), ("n_params", C.c_int64)]
 
 
@@ -68,6 +68,7 @@ _SIGS = {
     "bn_mlp_workspace_bytes": (_Z, [_P, _L, _I]),
     "bn_mlp_forward": (C.c_int, [_P, _P, _P, _I, _P, _I, _P, _I, _I, _I, _P, _I, _P, _Z, _P]),
     "bn_mlp_trunk_forward": (C.c_int, [_P, _P, _P, _I, _P, _I, _P, _I, _I, _I, _L, _L, _P, _P, _Z, _P]),
+    "bn_mlp_write_t": (C.c_int, [_P, _P, _I, _I, _I, _L, _L, _P, _Z, _P]),
     "bn_mlp_heads_forward": (C.c_int, [_P, _P, _L, _I, _P, _I, _P, _Z, _P]),
     "bn_mlp_backward": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _Z, _P]),
     "bn_mlp_normals_forward": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _Z, _P]),

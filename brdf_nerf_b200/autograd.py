@@ -14,7 +14,7 @@ class PointsFunction(torch.autograd.Function):
     direction of each point for models built with input_viewdir=1 (None otherwise)."""
 
     @staticmethod
-    def forward(ctx, model, xyz, dirs, sigma_only, apply_brdf, apply_theta, nr_an_on, nr_lr_on, need_grad, *params):
+    def forward(ctx, model, xyz, dirs, t_rows, sigma_only, apply_brdf, apply_theta, nr_an_on, nr_lr_on, need_grad, *params):
         if not xyz.is_cuda:
             raise L.BnError("SpSBRDFNeRF.forward needs CUDA tensors: there is no CPU path")
         xyz = xyz.detach().float().contiguous()
@@ -30,11 +30,15 @@ class PointsFunction(torch.autograd.Function):
             return out
         flags = model.mlp_flags(apply_brdf=apply_brdf, apply_theta=apply_theta, nr_an_on=nr_an_on and not sigma_only,
                                 nr_lr_on=nr_lr_on and not sigma_only, train=need_grad)
+        if sigma_only:
+            flags &= ~L.MLP_BETA                    # the density does not depend on the time embedding
         C = model.out_channels(flags)
         out = torch.empty((B, C), dtype=torch.float32, device=xyz.device)
         # a call that will be differentiated owns its workspace (kept alive by ctx): the reference calls the module once per
         # chunk and runs backward afterwards, so a shared buffer would be overwritten before it is read
         ws = model.workspace(B, flags, None if need_grad else "ws_points")
+        if flags & L.MLP_BETA:                       # every point is its own one-sample ray: t row i belongs to point i
+            ops.mlp_write_t(model, t_rows, B, 1, flags, B, 0, ws)
         ops.mlp_forward(model, xyz, 3, dirs, 3, z, flags, out, C, ws)
         if flags & L.MLP_NORMAL_AN:
             ops.mlp_normals_forward(model, out, C, B, 1, flags, ws)
@@ -57,4 +61,4 @@ class PointsFunction(torch.autograd.Function):
             ops.mlp_normals_backward(model, out, g_out, ctx.C, ctx.B, 1, ctx.flags, flat, ctx.ws)
         ops.mlp_backward(model, out, g_out, ctx.C, ctx.B, 1, ctx.flags, flat, ctx.ws)
         grads = model.grad_views(flat)
-        return (None, None, None, None, None, None, None, None, None, *grads)
+        return (None, None, None, None, None, None, None, None, None, None, *grads)

@@ -48,7 +48,7 @@ __global__ void encode_kernel(const float* __restrict__ origins, int o_stride, c
 // columns behind the features: the colour head's first layer reads [features | dir enc | 0] as one K = F + 64 operand
 template <typename T>
 __global__ void dir_encode_kernel(const float* __restrict__ dirs, int d_stride, int S, long long P, int n_freq,
-                                  T* __restrict__ dst, long long ld) {
+                                  T* __restrict__ dst, long long ld, int ncols) {
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
   const long long r = p / S;
@@ -72,9 +72,29 @@ __global__ void dir_encode_kernel(const float* __restrict__ dirs, int d_stride, 
   T* o = dst + p * ld;
 #pragma unroll
   for (int i = 0; i < kEncPad; i += 8) {
+    if (i >= ncols) continue;               // the columns behind belong to the time embedding (bn_mlp_write_t)
     float t[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) t[j] = e[i + j];
+    Pack<T, 8>::store(o + i, t);
+  }
+}
+
+// time embedding of the rays into FE columns [F + kTOff, F + 64) of their points' rows (zeros behind the TE real columns);
+// without a view direction the columns [F, F + kTOff) are zeroed here as well (nothing else writes them)
+template <typename T>
+__global__ void t_embed_kernel(const float* __restrict__ t_rows, int te, int S, long long P, bool zero_front,
+                               T* __restrict__ dst, long long ld) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const long long r = p / S;
+  T* o = dst + p * ld;
+#pragma unroll
+  for (int i = 0; i < kEncPad; i += 8) {
+    if (i < kTOff && !zero_front) continue;
+    float t[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const int c = i + j - kTOff; t[j] = (c >= 0 && c < te) ? t_rows[r * te + c] : 0.f; }
     Pack<T, 8>::store(o + i, t);
   }
 }
@@ -169,9 +189,11 @@ __global__ void __launch_bounds__(256) heads_fwd_kernel(HeadPlan hp, const float
       const float bo = __ldg(params + d.b_off);
 #pragma unroll
       for (int q = 0; q < kQP; ++q) {
-        const float s = sigmoidf_(warp_sum(acc[q]) + bo);
+        const float pre = warp_sum(acc[q]) + bo;
+        const float s = sigmoidf_(pre);
         float v = s;
-        if (d.xform == XF_K) v = (s - 0.5f) * 2.0f + 1.0f;
+        if (d.xform == XF_SOFTPLUS) v = softplusf_(pre);
+        else if (d.xform == XF_K) v = (s - 0.5f) * 2.0f + 1.0f;
         else if (d.xform == XF_THETA_RPV) v = (s - 0.5f) * 2.0f;
         else if (d.xform == XF_THETA_H) v = s * (float)(M_PI * 30.0 / 180.0);
         if (lane < d.rep && p0 + q < P) out[(p0 + q) * pitch + d.ch + lane] = v;
@@ -229,7 +251,7 @@ __global__ void __launch_bounds__(256) heads_bwd_kernel(HeadPlan hp, const float
           else if (d.xform == XF_THETA_RPV) { sg = v * 0.5f + 0.5f; scale = 2.0f; }
           else if (d.xform == XF_THETA_H) { const float k = (float)(M_PI * 30.0 / 180.0); sg = v / k; scale = k; }
           else { sg = v; scale = 1.0f; }
-          dpre[q][o] = g * scale * sg * (1.0f - sg);
+          dpre[q][o] = d.xform == XF_SOFTPLUS ? g * (1.0f - expf(-v)) : g * scale * sg * (1.0f - sg);
         }
       }
       // softplus'(x) = 1 - exp(-softplus(x))
@@ -429,7 +451,7 @@ __global__ void __launch_bounds__(256) heads_dpre_kernel(HeadPlan hp, const floa
         else if (q.xform == XF_THETA_RPV) { sg = v * 0.5f + 0.5f; scale = 2.0f; }
         else if (q.xform == XF_THETA_H) { const float k = (float)(M_PI * 30.0 / 180.0); sg = v / k; scale = k; }
         else { sg = v; scale = 1.0f; }
-        d[o] = g * scale * sg * (1.0f - sg);
+        d[o] = q.xform == XF_SOFTPLUS ? g * (1.0f - expf(-v)) : g * scale * sg * (1.0f - sg);
       }
     }
     d[kMaxOut] = grow[hp.ch_sigma] * (1.0f - expf(-row[hp.ch_sigma]));      // softplus'(x) = 1 - exp(-softplus(x))
@@ -505,9 +527,11 @@ struct EpiHeadsOut {
     for (int o = 0; o < kMaxOut; ++o) {
       if (o < hp.n_out) {
         const OutDesc& d = hp.o[o];
-        const float sg = 1.0f / (1.0f + expf(-(acc[o] + __ldg(params + d.b_off))));
+        const float pre = acc[o] + __ldg(params + d.b_off);
+        const float sg = 1.0f / (1.0f + expf(-pre));
         float v = sg;
-        if (d.xform == XF_K) v = (sg - 0.5f) * 2.0f + 1.0f;
+        if (d.xform == XF_SOFTPLUS) v = pre > 20.f ? pre : log1pf(expf(pre));
+        else if (d.xform == XF_K) v = (sg - 0.5f) * 2.0f + 1.0f;
         else if (d.xform == XF_THETA_RPV) v = (sg - 0.5f) * 2.0f;
         else if (d.xform == XF_THETA_H) v = sg * (float)(M_PI * 30.0 / 180.0);
         for (int c = 0; c < d.rep; ++c) orow[d.ch + c] = v;
@@ -544,6 +568,9 @@ static int build_plan(const bn_mlp* h, int flags, HeadPlan* hp, int* n_channels)
   for (int o = 0; o < 3; ++o)
     p.o[p.n_out++] = OutDesc{0, c.w_off[BN_LIN_RGB2] + (long long)o * h->HH, c.b_off[BN_LIN_RGB2] + o, ch++, 1, XF_SIGMOID};
   p.ch_sigma = ch++;
+  const bool want_beta = (flags & BN_MLP_BETA) != 0;
+  if (want_beta && c.head_dim[BN_HEAD_BETA] <= 0) { set_error("BN_MLP_BETA requested but the model has no beta_from_xyz head"); return BN_ERR_ARG; }
+  const int ch_beta = want_beta ? ch++ : -1;    // spsbrdfnerf.py:156-158: the uncertainty channel precedes the normals
   if (flags & BN_MLP_NORMAL_AN) ch += 3;        // written by the analytic-normal sweep
   p.ch_nlr = -1;
   if (flags & BN_MLP_NORMAL_LR) {
@@ -557,7 +584,9 @@ static int build_plan(const bn_mlp* h, int flags, HeadPlan* hp, int* n_channels)
     if (blk < 0) return;
     const int dim = c.head_dim[head];
     const int lin2 = h->blk_lin2[blk];
-    if (head == BN_HEAD_ROUGH || head == BN_HEAD_THETA) {
+    if (head == BN_HEAD_BETA) {
+      p.o[p.n_out++] = OutDesc{blk, c.w_off[lin2], c.b_off[lin2], ch_beta, 1, xform};
+    } else if (head == BN_HEAD_ROUGH || head == BN_HEAD_THETA) {
       p.o[p.n_out++] = OutDesc{blk, c.w_off[lin2], c.b_off[lin2], ch, 1, xform}; ch += 1;
     } else if (dim == 1) {
       p.o[p.n_out++] = OutDesc{blk, c.w_off[lin2], c.b_off[lin2], ch, 3, xform}; ch += 3;
@@ -568,6 +597,7 @@ static int build_plan(const bn_mlp* h, int flags, HeadPlan* hp, int* n_channels)
     }
     last_block = max(last_block, blk);
   };
+  if (want_beta) add_head(BN_HEAD_BETA, XF_SOFTPLUS);
   if (flags & BN_MLP_ROUGH) add_head(BN_HEAD_ROUGH, XF_SIGMOID);
   else if (flags & BN_MLP_RPV) { add_head(BN_HEAD_K, XF_K); add_head(BN_HEAD_THETA_RPV, XF_THETA_RPV); add_head(BN_HEAD_RHOC, XF_SIGMOID); }
   else if (flags & BN_MLP_HAPKE) {
@@ -582,7 +612,7 @@ static int build_plan(const bn_mlp* h, int flags, HeadPlan* hp, int* n_channels)
 }
 
 // all packed copies of one optimizer step in ONE launch: blockIdx.y = job (a Linear layer or a bias copy)
-struct PackJob { long long w_off; int N, Kreal, E, Kpad; void* Wp; long long ldp; void* WTp; long long ldt; int row0; };
+struct PackJob { long long w_off; int N, Kreal, E, Kpad; void* Wp; long long ldp; void* WTp; long long ldt; int row0; int Epad; };
 constexpr int kMaxPackJobs = 40;
 struct PackJobs { int n; PackJob j[kMaxPackJobs]; };
 
@@ -606,7 +636,7 @@ __global__ void __launch_bounds__(256) pack_all_kernel(const __grid_constant__ P
     const int kp = k0 + tx;
     int k = -1;                                   // source column of padded column kp, -1 = padding
     if (kp < q.Kpad) {
-      if (q.E >= 0) { if (kp < q.E) k = kp; else if (kp >= kEncPad) k = kp - (kEncPad - q.E); }
+      if (q.E >= 0) { if (kp < q.E) k = kp; else if (kp >= q.Epad) k = kp - (q.Epad - q.E); }     // E real columns, padding up to Epad
       else k = kp;
       if (k >= q.Kreal) k = -1;
     }
@@ -655,7 +685,7 @@ static int sync_weights_t(bn_mlp* h, const float* params, cudaStream_t s) {
   const bn_mlp_cfg& c = h->cfg;
   PackJobs jobs{};
   auto pack = [&](int lin, int N, int Kreal, int E, int Kpad, void* Wp, long long ldp, void* WTp, long long ldt, int row0) {
-    jobs.j[jobs.n++] = PackJob{c.w_off[lin], N, Kreal, E, Kpad, Wp, ldp, WTp, ldt, row0};
+    jobs.j[jobs.n++] = PackJob{c.w_off[lin], N, Kreal, E, Kpad, Wp, ldp, WTp, ldt, row0, kEncPad};
   };
   for (int l = 0; l < h->L; ++l) {
     const bool enc_in = (l == 0 || l == h->skip);
@@ -664,8 +694,13 @@ static int sync_weights_t(bn_mlp* h, const float* params, cudaStream_t s) {
   pack(BN_LIN_FEATS, h->F, h->F, -1, h->F, h->Wf, h->F, h->WfT, h->F, 0);
   const long long HK = (long long)h->n_blocks * h->HH;
   for (int b = 0; b < h->n_blocks; ++b) {
-    pack(h->blk_lin0[b], h->HH, h->F + (b == 0 ? h->DE : 0), -1, h->ldfe, h->W1, h->ldfe, h->W1T, HK, b * h->HH);
-    jobs.j[jobs.n++] = PackJob{c.b_off[h->blk_lin0[b]], h->HH, -1, -1, 1, h->b1cat, 0, nullptr, 0, b * h->HH};
+    if (h->blk_head[b] == BN_HEAD_BETA) {       // [features | t]: the time embedding sits kTOff columns behind the features
+      pack(h->blk_lin0[b], h->HH, h->F + h->TE, h->F, h->ldfe, h->W1, h->ldfe, h->W1T, HK, b * h->HH);
+      jobs.j[jobs.n - 1].Epad = h->F + kTOff;
+    } else {
+      pack(h->blk_lin0[b], h->HH, h->F + (b == 0 ? h->DE : 0), -1, h->ldfe, h->W1, h->ldfe, h->W1T, HK, b * h->HH);
+    }
+    jobs.j[jobs.n++] = PackJob{c.b_off[h->blk_lin0[b]], h->HH, -1, -1, 1, h->b1cat, 0, nullptr, 0, b * h->HH, kEncPad};
   }
   if (h->bf16) pack(BN_LIN_SIGMA, 1, h->F, -1, h->F, h->WsigA, h->F, nullptr, 0, 0);   // row 0 of the [64, F] density operand
   if (jobs.n > kMaxPackJobs) { set_error("too many pack jobs"); return BN_ERR_STATE; }
@@ -787,7 +822,8 @@ static int trunk_t(bn_mlp* h, const float* params, const float* origins, int o_s
   const bn_mlp_cfg& c = h->cfg;
   const int F = h->F, L = h->L;
   if (h->DE > 0 && w.FE) {      // --input_viewdir: the encoded ray direction of these rows, next to their (later) features
-    dir_encode_kernel<T><<<(unsigned)ceil_div_ll(P, 128), 128, 0, s>>>(dirs, d_stride, S, P, c.n_freq_dir, w.FE + F, w.ldfe);
+    dir_encode_kernel<T><<<(unsigned)ceil_div_ll(P, 128), 128, 0, s>>>(dirs, d_stride, S, P, c.n_freq_dir, w.FE + F, w.ldfe,
+                                                                       h->TE > 0 ? kTOff : kEncPad);
     BN_LAUNCH_CHECK();
   }
   if constexpr (std::is_same<T, __nv_bfloat16>::value) {
@@ -1018,6 +1054,12 @@ static int backward_t(bn_mlp* h, const float* params, const float* out, const fl
   for (int b = 0; b < hp.n_blocks; ++b) {
     const int lin = h->blk_lin0[b];
     // the colour head (block 0) also reads the encoded view direction: In = [features | dir enc | pad], dW is [HH, F + DE]
+    if (h->blk_head[b] == BN_HEAD_BETA) {
+      // dW is [HH, F + TE]: packed columns [F, F + kTOff) are padding, [F + kTOff, F + kTOff + TE) the time embedding
+      if (int rc = layer_wgrad<T>(h, w.GHD + (long long)b * h->HH, w.ldhd, w.FE, w.ldfe, h->HH, F + kTOff + h->TE, P, g + c.w_off[lin],
+                                  F + h->TE, F, F + kTOff, kTC ? g + hp.b1_off[b] : nullptr, sw1)) return rc;
+      continue;
+    }
     const int kin = F + (b == 0 ? h->DE : 0), no = (b == 0 && h->DE) ? h->ldfe : F;
     if (int rc = layer_wgrad<T>(h, w.GHD + (long long)b * h->HH, w.ldhd, w.FE, w.ldfe, h->HH, no, P, g + c.w_off[lin], kin, kin, no,
                                 kTC ? g + hp.b1_off[b] : nullptr, sw1)) return rc;
@@ -1121,6 +1163,9 @@ extern "C" __attribute__((visibility("default"))) int bn_mlp_create(const bn_mlp
   BN_CHECK_ARG(cfg->n_freq_xyz >= 0 && cfg->n_freq_xyz <= 10, "n_freq_xyz must be in [0, 10]");
   BN_CHECK_ARG(cfg->n_freq_dir >= 0 && cfg->n_freq_dir <= 10, "n_freq_dir must be in [0, 10]");
   BN_CHECK_ARG(cfg->precision == BN_PREC_FP32 || cfg->precision == BN_PREC_BF16, "unknown precision");
+  BN_CHECK_ARG(cfg->head_dim[BN_HEAD_BETA] <= 0 || (cfg->t_dims >= 1 && cfg->t_dims <= kEncPad - kTOff && cfg->t_dims % 4 == 0),
+               "beta head: t_dims must be a multiple of 4 in [4, 32]");
+  BN_CHECK_ARG(!cfg->viewdir || cfg->n_freq_dir * 6 <= kTOff || cfg->head_dim[BN_HEAD_BETA] <= 0, "direction encoding overlaps the time embedding");
   int dev = 0;
   BN_CUDA(cudaGetDevice(&dev));
   if (int rc = bn_device_check(dev)) return rc;
@@ -1130,7 +1175,8 @@ extern "C" __attribute__((visibility("default"))) int bn_mlp_create(const bn_mlp
   h->F = cfg->feat; h->L = cfg->layers; h->HH = cfg->feat / 2; h->skip = cfg->skip_layer;
   h->E = cfg->n_freq_xyz == 0 ? 3 : 6 * cfg->n_freq_xyz;
   h->DE = cfg->viewdir ? (cfg->n_freq_dir == 0 ? 3 : 6 * cfg->n_freq_dir) : 0;
-  h->ldfe = h->F + (h->DE ? kEncPad : 0);
+  h->TE = cfg->head_dim[BN_HEAD_BETA] > 0 ? cfg->t_dims : 0;
+  h->ldfe = h->F + ((h->DE || h->TE) ? kEncPad : 0);
   h->bf16 = cfg->precision == BN_PREC_BF16;
   h->es = h->bf16 ? 2 : 4;
   cudaDeviceProp prop;
@@ -1141,7 +1187,10 @@ extern "C" __attribute__((visibility("default"))) int bn_mlp_create(const bn_mlp
   // blocks of the heads' hidden layer: rgb first, then every BRDF head that exists
   h->n_blocks = 0;
   h->blk_lin0[0] = BN_LIN_RGB0; h->blk_lin2[0] = BN_LIN_RGB2; h->blk_head[0] = -1; h->n_blocks = 1;
-  for (int hd = 0; hd < BN_NUM_HEADS; ++hd) {
+  // the beta head is evaluated in every full forward (not only with apply_brdf): its block comes right after the colour block,
+  // so that a Lambertian-stage call of a model with BRDF heads stops after two blocks
+  for (int i = 0; i < BN_NUM_HEADS; ++i) {
+    const int hd = i == 0 ? BN_HEAD_BETA : i - 1;
     if (cfg->head_dim[hd] > 0) {
       h->blk_lin0[h->n_blocks] = BN_LIN_HEAD0 + 2 * hd;
       h->blk_lin2[h->n_blocks] = BN_LIN_HEAD0 + 2 * hd + 1;
@@ -1246,6 +1295,26 @@ int bn_mlp_trunk_forward(bn_mlp* h, const float* params, const float* origins, i
   BN_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
   return h->bf16 ? trunk_rows_t<__nv_bfloat16>(h, params, origins, o_stride, dirs, d_stride, z, n_rays, n_samples, flags, total_points, row0, sigma_out, workspace, stream)
                  : trunk_rows_t<float>(h, params, origins, o_stride, dirs, d_stride, z, n_rays, n_samples, flags, total_points, row0, sigma_out, workspace, stream);
+}
+
+extern "C" __attribute__((visibility("default")))
+int bn_mlp_write_t(bn_mlp* h, const float* t_rows, int n_rays, int n_samples, int flags, int64_t total_points, int64_t row0,
+                   void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  BN_CHECK_ARG(h && t_rows && workspace, "null pointer");
+  BN_CHECK_ARG(n_rays > 0 && n_samples > 0 && row0 >= 0 && row0 + (int64_t)n_rays * n_samples <= total_points, "row range out of bounds");
+  BN_CHECK_ARG(h->TE > 0 && (flags & BN_MLP_BETA) && !(flags & BN_MLP_SIGMA_ONLY), "bn_mlp_write_t needs a model with a beta head and BN_MLP_BETA");
+  if (workspace_bytes < bn_mlp_workspace_bytes(h, total_points, flags)) { set_error("bn_mlp_write_t: workspace too small"); return BN_ERR_STATE; }
+  const long long P = (long long)n_rays * n_samples;
+  if (h->bf16) {
+    Ws<__nv_bfloat16> w; carve<__nv_bfloat16>(h, total_points, flags, workspace, &w);
+    t_embed_kernel<__nv_bfloat16><<<(unsigned)ceil_div_ll(P, 128), 128, 0, stream>>>(t_rows, h->TE, n_samples, P, h->DE == 0,
+                                                                                      w.FE + row0 * w.ldfe + h->F, w.ldfe);
+  } else {
+    Ws<float> w; carve<float>(h, total_points, flags, workspace, &w);
+    t_embed_kernel<float><<<(unsigned)ceil_div_ll(P, 128), 128, 0, stream>>>(t_rows, h->TE, n_samples, P, h->DE == 0,
+                                                                             w.FE + row0 * w.ldfe + h->F, w.ldfe);
+  }
+  return after_launch("t_embed_kernel");
 }
 
 extern "C" __attribute__((visibility("default")))

@@ -33,11 +33,12 @@
 namespace bn {
 
 constexpr int kEncPad = 64;
-constexpr int kMaxBlocks = 8;     // rgb + up to 7 BRDF heads
+constexpr int kMaxBlocks = 9;     // rgb + beta + up to 7 BRDF heads
 constexpr int kMaxOut = 16;       // scalar outputs of the heads' second layers
 constexpr float kPiF = 3.14159265358979323846f;
 
-enum { XF_SIGMOID = 0, XF_K = 1, XF_THETA_RPV = 2, XF_THETA_H = 3 };
+enum { XF_SIGMOID = 0, XF_K = 1, XF_THETA_RPV = 2, XF_THETA_H = 3, XF_SOFTPLUS = 4 };
+constexpr int kTOff = 32;         // the time embedding sits kTOff columns behind the features (after the direction encoding)
 
 struct OutDesc { int block; long long w_off; long long b_off; int ch; int rep; int xform; };
 struct HeadPlan {
@@ -54,7 +55,8 @@ struct HeadPlan {
 struct bn_mlp {
   bn_mlp_cfg cfg;
   int F, L, E, HH, skip;
-  int DE, ldfe;                 // view-direction encoding width (0 = off) and the pitch of FE = [features | dir enc | pad]
+  int DE, ldfe;                 // view-direction encoding width (0 = off) and the pitch of FE = [features | dir enc | pad | t | pad]
+  int TE;                       // width of the time embedding read by the beta head (0 = no beta head): FE cols F + kTOff ..
   int num_sms;
   bool bf16;
   size_t es;

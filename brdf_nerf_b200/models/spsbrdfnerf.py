@@ -57,15 +57,10 @@ class SpSBRDFNeRF(nn.Module):
         super().__init__()
         if not siren:
             raise NotImplementedError("siren=0 (ReLU trunk) is outside the CUDA hot path")
-        # R19 of SURVEY §8a is knowingly partial: three optional output channels are refused
+        # R19 of SURVEY §8a: `beta` is built; two optional output channels are refused
         if sun_v == "learned":
             raise NotImplementedError("sun_v='learned' raises NameError in the reference itself (spsbrdfnerf.py:697 reads the "
                                       "undefined `xyz_features_`, SURVEY App. C.2): there is no behaviour to mirror")
-        if beta:
-            raise NotImplementedError("beta=True (transient-uncertainty channel: beta_from_xyz on [features | t-embedding], "
-                                      "spsbrdfnerf.py:571-575,708-711) is not built: no loss of the spsbrdf-nerf recipe reads it "
-                                      "(metrics.load_loss returns SNerfLoss for this model, metrics.py:170-171) and the README "
-                                      "recipes never pass --beta; `ts` is therefore accepted and ignored by render_rays")
         if indirect_light:
             raise NotImplementedError("indirect_light=True (sky_color head, spsbrdfnerf.py:562-568,704-706) is not built: the "
                                       "reference reads it from the hard-coded channels out[..., 5:8] (spsbrdfnerf.py:154), which "
@@ -88,8 +83,8 @@ class SpSBRDFNeRF(nn.Module):
         self.n_freq_dir = mapping_sizes[1] if mapping else 0
         self.precision = precision
 
-        self.number_of_outputs = 4
-        self.number_of_outputs_brdf = 4
+        self.number_of_outputs = 4 + int(beta == True)            # noqa: E712  (+ beta, spsbrdfnerf.py:476-477)
+        self.number_of_outputs_brdf = self.number_of_outputs
         if self.roughness == True:                                # noqa: E712
             self.number_of_outputs_brdf += 1
         elif self.RPV:
@@ -110,6 +105,9 @@ class SpSBRDFNeRF(nn.Module):
         for i in range(layers):                     # fc_net.apply(sine_init)
             _siren_uniform(self.fc_net[2 * i], first=False)
         _siren_uniform(self.fc_net[0], first=True)  # fc_net[0].apply(first_layer_sine_init)
+        if beta == True:                                          # noqa: E712  spsbrdfnerf.py:571-575: [features | t] -> beta
+            self.beta_from_xyz = nn.Sequential(nn.Linear(t_embedding_dims + feat, feat // 2), Sine(),
+                                               nn.Linear(feat // 2, 1), nn.Softplus())
         if normal in ("analystic_learned", "learned"):
             self.grad_from_xyz = nn.Linear(feat, 3)
         if self.roughness == True:                                # noqa: E712
@@ -271,6 +269,7 @@ class SpSBRDFNeRF(nn.Module):
             cfg.n_freq_xyz = self.n_freq
             cfg.normal_lr = int(hasattr(self, "grad_from_xyz"))
             cfg.viewdir, cfg.n_freq_dir = int(self.viewdir), int(self.n_freq_dir)
+            cfg.t_dims = int(self.t_embedding_dims) if self.beta == True else 0      # noqa: E712
             for h, hn in enumerate(L.HEAD_NAMES):
                 mod = getattr(self, f"{hn}_from_xyz", None)
                 cfg.head_dim[h] = mod[2].out_features if mod is not None else 0
@@ -334,6 +333,8 @@ class SpSBRDFNeRF(nn.Module):
             return L.MLP_SIGMA_ONLY
         if train:
             f |= L.MLP_TRAIN
+        if self.beta == True:                                     # noqa: E712  every full forward emits the channel (:708-711)
+            f |= L.MLP_BETA
         if nr_an_on:
             f |= L.MLP_NORMAL_AN
         if nr_lr_on:
@@ -378,5 +379,8 @@ class SpSBRDFNeRF(nn.Module):
         if self.viewdir and not sigma_only and input_dir is None:
             raise ValueError("this model was built with input_viewdir=1: forward needs input_dir (spsbrdfnerf.py:689-690)")
         dirs = input_dir.contiguous() if (self.viewdir and input_dir is not None) else None
-        return PointsFunction.apply(self, input_xyz_.contiguous(), dirs, bool(sigma_only), bool(apply_brdf),
+        if self.beta == True and not sigma_only and input_t is None:      # noqa: E712
+            raise ValueError("this model was built with beta=True: forward needs input_t (spsbrdfnerf.py:708-709)")
+        t = input_t.detach().float().contiguous() if (self.beta == True and input_t is not None) else None   # noqa: E712
+        return PointsFunction.apply(self, input_xyz_.contiguous(), dirs, t, bool(sigma_only), bool(apply_brdf),
                                     bool(apply_theta), bool(nr_an_on), bool(nr_lr_on), need_grad, *self.parameters())

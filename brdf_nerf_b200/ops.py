@@ -175,6 +175,16 @@ def mlp_trunk_forward(model, origins, o_stride, dirs, d_stride, z, flags, total_
                                           int(row0), L.ptr(sigma_out), C.c_void_p(ws.data_ptr()), ws.numel(), L.stream_ptr()))
 
 
+def mlp_write_t(model, t_rows, n, s, flags, total_points, row0, ws):
+    """Time embedding of n rays (t_rows (n, t_dims) fp32) into the workspace rows of their n*s points (bn_mlp_write_t)."""
+    if t_rows is None:
+        raise L.BnError("this model has a beta head: the time embedding of the rays (models['t'](ts)) is required")
+    if t_rows.shape != (n, model.t_embedding_dims):
+        raise L.BnError(f"time embedding must be ({n}, {model.t_embedding_dims}), got {tuple(t_rows.shape)}")
+    L.check(L.load().bn_mlp_write_t(model.handle(), L.ptr(t_rows), n, s, flags, int(total_points), int(row0),
+                                    C.c_void_p(ws.data_ptr()), ws.numel(), L.stream_ptr()))
+
+
 def mlp_heads_forward(model, total_points, flags, out, pitch, ws):
     L.check(L.load().bn_mlp_heads_forward(model.handle(), L.ptr(model.flat_params), int(total_points), flags, L.ptr(out), pitch,
                                           C.c_void_p(ws.data_ptr()), ws.numel(), L.stream_ptr()))
@@ -194,13 +204,14 @@ def mlp_backward(model, out, g_out, pitch, n, s, flags, g_params, ws):
 
 
 def mlp_normals_forward(model, out, pitch, n, s, flags, ws):
-    L.check(L.load().bn_mlp_normals_forward(model.handle(), L.ptr(model.flat_params), L.ptr(out), pitch, n, s, flags, 4,
+    L.check(L.load().bn_mlp_normals_forward(model.handle(), L.ptr(model.flat_params), L.ptr(out), pitch, n, s, flags,
+                                            4 + int(bool(flags & L.MLP_BETA)),        # the beta channel precedes the normals
                                             C.c_void_p(ws.data_ptr()), ws.numel(), L.stream_ptr()))
 
 
 def mlp_normals_backward(model, out, g_out, pitch, n, s, flags, g_params, ws):
     L.check(L.load().bn_mlp_normals_backward(model.handle(), L.ptr(model.flat_params), L.ptr(out), L.ptr(g_out), pitch, n, s,
-                                             flags, 4, L.ptr(g_params), C.c_void_p(ws.data_ptr()), ws.numel(),
+                                             flags, 4 + int(bool(flags & L.MLP_BETA)), L.ptr(g_params), C.c_void_p(ws.data_ptr()), ws.numel(),
                                              L.stream_ptr()))
 
 

@@ -88,7 +88,7 @@ def _call_brdf_type(model, args, apply_brdf: bool) -> int:
 def _forward(model, args, rays: torch.Tensor, draws: Optional[Draws], mode: str, valid_depth, target_depths,
              target_std, apply_brdf: bool, bTestNormal: bool, bTestSun_v: bool, gsam_only: bool, apply_theta: bool,
              cos_irra_on: bool, train: bool, debug_nan: bool = False, own_ws: bool = False, sync: bool = True,
-             reference_rng: bool = False):
+             reference_rng: bool = False, rays_t: Optional[torch.Tensor] = None):
     """`own_ws`: the MLP workspace is allocated for this call and owned by the returned state (autograd bridge: several
     forwards may be alive before their backwards run); otherwise the model's cached per-tag buffer is reused.
     `sync=False`: the caller (Trainer) has refreshed the packed weight copies itself.
@@ -212,9 +212,17 @@ def _forward(model, args, rays: torch.Tensor, draws: Optional[Draws], mode: str,
     multi = bool(model.MultiBRDF) and brdf_type != L.BN_BRDF_NONE
     pitch = C + (3 if multi else 0)
     packed_rows = None
+    has_beta = bool(flags & L.MLP_BETA)
+    if has_beta:
+        if rays_t is None:
+            raise ValueError("model.beta is True: render_rays needs `ts` and models['t'] (rendering.py:228-229)")
+        rays_t = rays_t.detach().to(device=dev, dtype=torch.float32).contiguous()
     if share_trunk:
         packed_rows = torch.empty((N * S, pitch), dtype=torch.float32, device=dev)
         ops.mlp_trunk_forward(model, origins, 11, dirs, 11, z2, flags, N * S, N * S1, None, ws)
+        if has_beta:         # the rays' time embedding next to the features of their stratified and of their guided rows
+            ops.mlp_write_t(model, rays_t, N, S1, flags, N * S, 0, ws)
+            ops.mlp_write_t(model, rays_t, N, G, flags, N * S, N * S1, ws)
         ops.mlp_heads_forward(model, N * S, flags, packed_rows, pitch, ws)
         if nr_an:
             ops.mlp_normals_forward(model, packed_rows, pitch, N, S, flags, ws)
@@ -222,13 +230,15 @@ def _forward(model, args, rays: torch.Tensor, draws: Optional[Draws], mode: str,
     else:
         packed = torch.empty((N, S, pitch), dtype=torch.float32, device=dev)
         ws = model.workspace(N * S, flags, tag=None if own_ws else ("ws_train" if train else "ws_full"))
+        if has_beta:
+            ops.mlp_write_t(model, rays_t, N, S, flags, N * S, 0, ws)
         ops.mlp_forward(model, origins, 11, dirs, 11, z, flags, packed, pitch, ws)
         if nr_an:
             ops.mlp_normals_forward(model, packed, pitch, N, S, flags, ws)
 
     cfg = L.ShadeCfg()
     cfg.n_channels = pitch
-    ch = 4
+    ch = 4 + int(has_beta)                     # the uncertainty channel sits between sigma and the normals (:156-158)
     cfg.normal_ch = -1
     if nr_an:
         cfg.normal_ch = ch; ch += 3
@@ -273,6 +283,7 @@ def _forward(model, args, rays: torch.Tensor, draws: Optional[Draws], mode: str,
                 normal_an=nr_an)
     outs = dict(rgb=sh["rgb"], depth=depth, weights=w, packed=packed, alpha=alpha, trans=trans, z=z,
                 z_unsort=z_unsort, idx=idx, shade=sh, sun_res=sun_res, aux_pts=aux_pts, C=C, nr_an=nr_an, nr_lr=nr_lr,
+                has_beta=has_beta,
                 brdf_type=brdf_type, extras=dict(z1=z1, z2=z2, sigma1=sigma1, weights1=w1, depth1=depth1, nan_counts=nan_counts))
     return outs, st
 
@@ -335,6 +346,8 @@ def _assemble(model, args, rays, outs, rgb, depth, weights, packed, apply_brdf, 
         res["sort_idx"] = outs["idx"]
     res["z_vals_unsort"] = outs["z_unsort"]
     ch = 4
+    if outs.get("has_beta"):
+        res["beta"] = packed[..., ch:ch + 1]; ch += 1          # spsbrdfnerf.py:225-226
     if outs["nr_an"]:
         res["normal_an"] = packed[..., ch:ch + 3]; ch += 3
     if outs["nr_lr"]:
@@ -413,7 +426,11 @@ def render_rays(models, args, rays, ts, mode="test", valid_depth=None, target_de
     torch's CUDA generator in exactly the reference's order and shapes (see `_forward`), so that a seeded reference run on
     the same device sees the same draws."""
     model = models["coarse"]
-    kw = dict(mode=mode, valid_depth=valid_depth, target_depths=target_depths, target_std=target_std,
+    rays_t = None
+    if getattr(args, "beta", False) == True and ts is not None:          # noqa: E712  rendering.py:228-229
+        with torch.no_grad():         # the embedding is an input here: no gradient flows back into models['t'] (DESIGN.md §0)
+            rays_t = models["t"](ts.to(rays.device).reshape(-1).long())
+    kw = dict(mode=mode, valid_depth=valid_depth, target_depths=target_depths, target_std=target_std, rays_t=rays_t,
               apply_brdf=bool(apply_brdf), bTestNormal=bool(bTestNormal), bTestSun_v=bool(bTestSun_v),
               gsam_only=bool(gsam_only), apply_theta=bool(apply_theta), cos_irra_on=bool(cos_irra_on),
               reference_rng=bool(_reference_rng))

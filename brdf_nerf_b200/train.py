@@ -87,6 +87,9 @@ class Trainer:
         # not part of this driver: refuse instead of silently training without it
         if abs(float(getattr(args, "nr_spv_lambda", 0.0) or 0.0)) > 1e-5:
             raise NotImplementedError("nr_spv_lambda != 0 (NormalLoss, main.py:301-327) is not implemented by Trainer")
+        if getattr(model, "beta", False) == True:           # noqa: E712
+            raise NotImplementedError("Trainer drives the spsbrdf-nerf recipe, which never trains with --beta (no loss reads the "
+                                      "channel, metrics.py:170-171); render beta models through render_rays + autograd")
         self._frozen = None                 # [(offset, length)] of the parameters with requires_grad == False
 
     # one optimisation step; `batch` tensors must already live on the model's device

@@ -214,11 +214,12 @@ enum {
   BN_LIN_RGB2 = 19,         /* rgb_from_xyzdir.2 */
   BN_LIN_GRAD = 20,         /* grad_from_xyz (learned normal) */
   BN_LIN_HEAD0 = 21,        /* head h: 21+2h = {name}.0, 22+2h = {name}.2 */
-  BN_NUM_LINEAR = 35
+  BN_NUM_LINEAR = 37
 };
-/* optional BRDF heads, in the reference's output-channel order */
+/* optional heads on the feature vector: the BRDF heads in the reference's output-channel order, then the transient-
+ * uncertainty head beta_from_xyz (spsbrdfnerf.py:571-575), whose first layer also reads the ray's time embedding */
 enum { BN_HEAD_ROUGH = 0, BN_HEAD_K = 1, BN_HEAD_THETA_RPV = 2, BN_HEAD_RHOC = 3,
-       BN_HEAD_B = 4, BN_HEAD_C = 5, BN_HEAD_THETA = 6, BN_NUM_HEADS = 7 };
+       BN_HEAD_B = 4, BN_HEAD_C = 5, BN_HEAD_THETA = 6, BN_HEAD_BETA = 7, BN_NUM_HEADS = 8 };
 
 typedef struct bn_mlp_cfg {
   int feat;               /* fc_feat (multiple of 64; 512 in the reference recipe) */
@@ -228,7 +229,8 @@ typedef struct bn_mlp_cfg {
   int normal_lr;          /* grad_from_xyz head exists */
   int viewdir;            /* --input_viewdir: the colour head reads [features | Mapping(ray direction)] (spsbrdfnerf.py:689-690) */
   int n_freq_dir;         /* frequencies of the direction encoding (mapping_sizes[1] = 4), 0 = raw direction (no --mapping) */
-  int head_dim[BN_NUM_HEADS];   /* output width of each BRDF head that exists (0 = absent) */
+  int t_dims;             /* width of the per-ray time embedding read by the beta head (args.t_embbeding_tau, <= 32); 0 without beta */
+  int head_dim[BN_NUM_HEADS];   /* output width of each head that exists (0 = absent) */
   int precision;          /* BN_PREC_* */
   int64_t w_off[BN_NUM_LINEAR]; /* element offset of each weight / bias in the flat buffer, -1 = absent */
   int64_t b_off[BN_NUM_LINEAR];
@@ -246,7 +248,9 @@ enum {
   BN_MLP_ROUGH = 16,       /* evaluate the roughness head (microfacet, apply_brdf) */
   BN_MLP_RPV = 32,         /* evaluate k / theta_rpv / rhoc heads that exist */
   BN_MLP_HAPKE = 64,       /* evaluate b / c heads that exist */
-  BN_MLP_HAPKE_THETA = 128 /* ... and the Hapke theta head (apply_theta) */
+  BN_MLP_HAPKE_THETA = 128,/* ... and the Hapke theta head (apply_theta) */
+  BN_MLP_BETA = 256        /* model.beta: channel 4 = softplus(beta_from_xyz([features | t])) (spsbrdfnerf.py:708-711); the time
+                            * embedding of the rows must have been written with bn_mlp_write_t */
 };
 
 int bn_mlp_create(const bn_mlp_cfg* cfg, bn_mlp** out);
@@ -278,6 +282,11 @@ int bn_mlp_trunk_forward(bn_mlp* h, const float* params, const float* origins, i
                          const float* dirs, int d_stride, const float* z, int n_rays, int n_samples, int flags,
                          int64_t total_points, int64_t row0, float* sigma_out, void* workspace,
                          size_t workspace_bytes, cudaStream_t stream);
+/* Time embedding of the rays (rays_t = models['t'](ts), rendering.py:208-209, repeated per sample spsbrdfnerf.py:98) into the
+ * workspace rows [row0, row0 + n_rays*n_samples) of a forward sized for total_points: t_rows (n_rays, t_dims) fp32, row r
+ * serves the n_samples points of ray r.  Call it before bn_mlp_heads_forward / bn_mlp_forward with BN_MLP_BETA. */
+int bn_mlp_write_t(bn_mlp* h, const float* t_rows, int n_rays, int n_samples, int flags, int64_t total_points, int64_t row0,
+                   void* workspace, size_t workspace_bytes, cudaStream_t stream);
 int bn_mlp_heads_forward(bn_mlp* h, const float* params, int64_t total_points, int flags, float* out,
                          int out_pitch, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 

@@ -49,9 +49,20 @@ CASES = {
     "lambertian_nomapping_test": ("lambertian", dict(mapping=False), dict(mode="test"), False, False),
     "rpv111_nomapping_brdf": ("rpv111", dict(mapping=False), dict(mode="test", apply_brdf=True, cos_irra_on=True), False, False),
     "rpv111_an_lr_normals": ("rpv111", dict(normal="analystic_learned"), dict(mode="test", apply_brdf=True, cos_irra_on=True), False, False),
+    # transient-uncertainty channel: beta head on [features | t-embedding], rays_t = models['t'](ts) (rendering.py:228-229)
+    "lambertian_beta_test": ("lambertian", dict(beta=True), dict(mode="test"), False, False),
+    "rpv111_beta_brdf": ("rpv111", dict(beta=True), dict(mode="test", apply_brdf=True, cos_irra_on=True), False, False),
 }
 KEEP = ("z_vals", "z_vals_unsort", "sort_idx", "depth", "rgb", "weights", "albedo_accu", "sigmas", "nr_vw", "nr_sun",
-        "brdf", "hpk_scl", "sun", "weights_sc")
+        "brdf", "hpk_scl", "sun", "weights_sc", "beta")
+
+
+def time_inputs(args, n):
+    """ts (view index of every ray) and the embedding table models['t'] of a beta case: nn.Embedding seeded with 1,
+    created after the model (main.py:113-118)."""
+    torch.manual_seed(1)
+    emb = torch.nn.Embedding(args.t_embbeding_vocab, args.t_embbeding_tau)
+    return torch.arange(n) % 3, emb
 
 
 def weights_digest(state) -> str:
@@ -77,8 +88,12 @@ def main():
         sun = bool(kw.get("bTestSun_v"))
         draws = RT.Draws.make(N, S1, G, S, seed=4321, with_gt=ds, with_sun=sun, s_sun=G if gs else S1)
         extra = dict(valid_depth=batch.valid_depth, target_depths=batch.target_depths, target_std=batch.target_std) if ds else {}
+        tkw = {}
+        if args.beta:
+            ts, emb = time_inputs(args, N)
+            tkw = dict(ts=ts, embedding=emb)
         with torch.no_grad():
-            res, btype = RH.render(model, args, batch.rays, draws, **kw, **extra)
+            res, btype = RH.render(model, args, batch.rays, draws, **tkw, **kw, **extra)
         # normal accumulation used for the tolerance statement on normals (SURVEY §8a N-note)
         out = {"rays": batch.rays.numpy(), "u_strat": draws.u_strat.numpy(), "u_pred": draws.u_pred.numpy(),
                "brdf_type": np.array(btype), "weights_sha256": np.array(weights_digest(model.state_dict()))}
@@ -87,6 +102,8 @@ def main():
                        target_std=batch.target_std.numpy(), u_gt=draws.u_gt.numpy())
         if sun:
             out.update(u_sun=draws.u_sun.numpy())
+        if args.beta:
+            out.update(ts=tkw["ts"].numpy(), t_weight=tkw["embedding"].weight.detach().numpy())
         for k in KEEP:
             if f"{k}_coarse" in res:
                 out["ref_" + k] = res[f"{k}_coarse"].detach().numpy()

@@ -118,14 +118,18 @@ def draw_queue(draws, valid_depth=None, mode="test", dtype=torch.float32):
     return [t.to(dtype) for t in q]
 
 
-def render(model, args, rays, draws, dtype=torch.float32, **kw):
-    """Call the live reference render_rays with injected draws; stdout is swallowed."""
+def render(model, args, rays, draws, dtype=torch.float32, ts=None, embedding=None, **kw):
+    """Call the live reference render_rays with injected draws; stdout is swallowed.  `ts` (N,) int64 + `embedding`
+    (nn.Embedding, models['t']) for models built with beta=True (rendering.py:228-229)."""
     ref_rendering, _, _ = load()
     mode = kw.get("mode", "test")
     q = draw_queue(draws, kw.get("valid_depth"), mode, dtype)
     buf = io.StringIO()
+    models = {"coarse": model}
+    if embedding is not None:
+        models["t"] = embedding
     with inject_draws(q) as rest, contextlib.redirect_stdout(buf):
-        res, btype = ref_rendering.render_rays({"coarse": model}, args, rays.to(dtype), None, **kw)
+        res, btype = ref_rendering.render_rays(models, args, rays.to(dtype), ts, **kw)
     if rest:
         raise RuntimeError(f"{len(rest)} queued draws were not consumed")
     return res, btype

@@ -96,6 +96,7 @@ class OracleModel:
         self.RPV = bool(args.funcM or args.funcF or args.funcH)
         self.MultiBRDF = bool(args.MultiBRDF)
         self.sun_v = args.sun_v
+        self.beta = bool(getattr(args, "beta", False))
 
     def parameters(self):
         return list(self.p.values())
@@ -116,7 +117,7 @@ class OracleModel:
         return torch.sigmoid(self.lin(name + ".2", torch.sin(self.lin(name + ".0", feats))))
 
     def forward(self, x, d=None, sigma_only=False, apply_brdf=False, apply_theta=False,
-                nr_an=False, nr_lr=False):
+                nr_an=False, nr_lr=False, t=None):
         """Per-point outputs as a dict (the reference packs them into channels, :694-757)."""
         if nr_an:
             x = x if x.requires_grad else x.detach().requires_grad_(True)
@@ -129,6 +130,9 @@ class OracleModel:
         feats = self.lin("feats_from_xyz", h)
         rgb_in = torch.cat([feats, fourier(d, self.nf_dir)], -1) if self.viewdir else feats
         out["albedo"] = torch.sigmoid(self.lin("rgb_from_xyzdir.2", torch.sin(self.lin("rgb_from_xyzdir.0", rgb_in))))
+        if self.beta:                                   # spsbrdfnerf.py:708-711: softplus(beta_from_xyz([features | t]))
+            hid = torch.sin(self.lin("beta_from_xyz.0", torch.cat([feats, t.to(feats.dtype)], -1)))
+            out["beta"] = Fnn.softplus(self.lin("beta_from_xyz.2", hid))
         if nr_an:
             with torch.enable_grad():
                 keep = torch.is_grad_enabled()
@@ -180,15 +184,17 @@ def _points(rays_o, rays_d, z):
     return rays_o.unsqueeze(1) + rays_d.unsqueeze(1) * z.unsqueeze(2)
 
 
-def _run_model(model, xyz, rays_d, chunk, **kw):
+def _run_model(model, xyz, rays_d, chunk, rays_t=None, **kw):
     """The reference evaluates the MLP in chunks of `args.chunk` points (spsbrdfnerf.py:119-125);
     results are independent of the chunking, the oracle keeps it only to bound memory."""
     n, s = xyz.shape[:2]
     pts = xyz.reshape(-1, 3)
     dirs = None if rays_d is None else torch.repeat_interleave(rays_d, s, dim=0)
+    ts_ = None if rays_t is None else torch.repeat_interleave(rays_t, s, dim=0)          # spsbrdfnerf.py:98
     outs = []
     for i in range(0, pts.shape[0], chunk):
-        outs.append(model.forward(pts[i:i + chunk], None if dirs is None else dirs[i:i + chunk], **kw))
+        outs.append(model.forward(pts[i:i + chunk], None if dirs is None else dirs[i:i + chunk],
+                                  t=None if ts_ is None else ts_[i:i + chunk], **kw))
     return {k: torch.cat([o[k] for o in outs], 0).reshape(n, s, -1) for k in outs[0]}
 
 
@@ -212,6 +218,8 @@ def shade(model, args, per_pt, z, rays_d, sun_d, noise, apply_brdf, apply_theta,
         res["sort_idx"] = sort_idx
     if z_unsort is not None:
         res["z_vals_unsort"] = z_unsort
+    if "beta" in per_pt:
+        res["beta"] = per_pt["beta"]                             # :225-226
     normal = None
     if "normal_an" in per_pt:
         res["normal_an"] = normal = per_pt["normal_an"]
@@ -324,7 +332,7 @@ def shade(model, args, per_pt, z, rays_d, sun_d, noise, apply_brdf, apply_theta,
 
 def render_rays(model: OracleModel, args, rays, draws: Draws, mode="test", valid_depth=None,
                 target_depths=None, target_std=None, apply_brdf=False, bTestNormal=False,
-                bTestSun_v=False, gsam_only=False, apply_theta=False, cos_irra_on=False):
+                bTestSun_v=False, gsam_only=False, apply_theta=False, cos_irra_on=False, rays_t=None):
     """rendering.py:168-291 for variant 'spsbrdf-nerf', guided_samples > 0, n_importance == 0.
     Returns (dict with '_coarse' keys, brdf_type, extras) — extras carries pass-1 tensors for tests."""
     dt = model.dtype
@@ -372,7 +380,7 @@ def render_rays(model: OracleModel, args, rays, draws: Draws, mode="test", valid
     extras["z2"] = torch.from_numpy(np.sort(z2, -1))
     nr_an = model.normal in ("analystic", "analystic_learned") or bTestNormal
     nr_lr = model.normal in ("learned", "analystic_learned")
-    pp2 = _run_model(model, _points(o, d, z), d, args.chunk, apply_brdf=apply_brdf, apply_theta=apply_theta,
+    pp2 = _run_model(model, _points(o, d, z), d, args.chunk, rays_t=rays_t, apply_brdf=apply_brdf, apply_theta=apply_theta,
                      nr_an=nr_an, nr_lr=nr_lr)
     res, brdf_type = shade(model, args, pp2, z, d, sun_d, draws.noise2.to(dt), apply_brdf, apply_theta,
                            cos_irra_on, sun_res=sun_res, sort_idx=idx, z_unsort=z_unsort)

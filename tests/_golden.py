@@ -30,6 +30,8 @@ CASES = {
     "lambertian_nomapping_test": ("lambertian", dict(mapping=False), dict(mode="test"), False),
     "rpv111_nomapping_brdf": ("rpv111", dict(mapping=False), dict(mode="test", apply_brdf=True, cos_irra_on=True), False),
     "rpv111_an_lr_normals": ("rpv111", dict(normal="analystic_learned"), dict(mode="test", apply_brdf=True, cos_irra_on=True), False),
+    "lambertian_beta_test": ("lambertian", dict(beta=True), dict(mode="test"), False),
+    "rpv111_beta_brdf": ("rpv111", dict(beta=True), dict(mode="test", apply_brdf=True, cos_irra_on=True), False),
 }
 
 
@@ -60,3 +62,14 @@ def supervision(g):
 def bits_equal(a: np.ndarray, b: np.ndarray) -> int:
     a, b = np.ascontiguousarray(a, np.float32), np.ascontiguousarray(b, np.float32)
     return int((a.view(np.uint32) != b.view(np.uint32)).sum())
+
+
+def time_embedding(g):
+    """(ts, nn.Embedding) of a beta case, rebuilt from the fixture (None, None otherwise)."""
+    if "ts" not in g:
+        return None, None
+    w = torch.from_numpy(g["t_weight"])
+    emb = torch.nn.Embedding(w.shape[0], w.shape[1])
+    with torch.no_grad():
+        emb.weight.copy_(w)
+    return torch.from_numpy(g["ts"]), emb

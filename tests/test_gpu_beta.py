@@ -1,0 +1,100 @@
+"""R19: the transient-uncertainty channel `beta` (reference spsbrdfnerf.py:571-575, 708-711; `rays_t = models['t'](ts)`,
+rendering.py:228-229): head on [features | time embedding], softplus output in packed channel 4 (before the normals),
+result key `beta_coarse`, early return of `inference` skipped.  fp32 mode <= 1e-3 against the oracle (pinned on the live
+reference in tests/test_oracle_vs_reference.py::test_beta_channel_vs_reference and on two goldens); bf16 mode looser."""
+import pytest
+import torch
+
+from brdf_nerf_b200.config import named_config
+from brdf_nerf_b200.models import load_model
+from brdf_nerf_b200.rendering import Draws, render_rays
+from brdf_nerf_b200.synth import make_rays
+from oracle import render_torch as RT
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(cfg, cuda, precision="fp32", **over):
+    args = named_config(cfg, beta=True, **over)
+    torch.manual_seed(0)
+    m = load_model(args, precision=precision)
+    state = {k: v.clone() for k, v in m.state_dict().items()}
+    torch.manual_seed(1)
+    emb = torch.nn.Embedding(args.t_embbeding_vocab, args.t_embbeding_tau)
+    return args, m.to(cuda), state, emb
+
+
+def _cols(ref, names):
+    return torch.cat([ref[k] for k in names if k in ref], -1)
+
+
+@pytest.mark.parametrize("cfg,kw,names", [
+    ("lambertian", {}, ("albedo", "sigma", "beta")),
+    ("rpv111", dict(apply_brdf=True, nr_an=True), ("albedo", "sigma", "beta", "normal_an", "rpv_k", "rpv_theta", "rpv_rhoc")),
+    ("hapke_bct", dict(apply_brdf=True, apply_theta=True), ("albedo", "sigma", "beta", "hpk_b", "hpk_c", "hpk_theta")),
+])
+def test_module_forward_and_backward_fp32(cuda, cfg, kw, names):
+    over = {} if kw.get("nr_an") else dict(normal="none")
+    args, m, state, emb = _setup(cfg, cuda, **over)
+    n = 600
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(n, 3, generator=g) * 1.6 - 0.8
+    t = emb(torch.randint(0, 30, (n,), generator=g)).detach()
+    om = RT.OracleModel(state, args, requires_grad=True)
+    okw = dict(kw)
+    ref = om.forward(x, t=t, **okw)
+    want = _cols(ref, names)
+    mkw = {("nr_an_on" if k == "nr_an" else k): v for k, v in kw.items()}
+    out = m(x.to(cuda), input_t=t.to(cuda), **mkw)
+    assert out.shape == want.shape, (out.shape, want.shape)
+    cols = [c for c in range(want.shape[1]) if not (kw.get("nr_an") and 5 <= c < 8)]      # raw normals: ill-conditioned
+    assert (out.detach().cpu() - want.detach())[:, cols].abs().max().item() < 1e-4
+    with pytest.raises(ValueError):
+        m(x.to(cuda))                                    # a beta model needs input_t
+    assert m(x.to(cuda), sigma_only=True).shape == (n, 1)
+    if kw.get("nr_an"):
+        return
+    G = torch.randn(want.shape, generator=g)
+    G[:, 4] *= 3.0                                        # make the beta channel count
+    (want * G).sum().backward()
+    m.flat_grads.zero_()
+    (out * G.to(cuda)).sum().backward()
+    for name, p in m.named_parameters():
+        r = om.p[name].grad
+        if r is None:
+            continue
+        d, s = (p.grad.cpu() - r).abs().max().item(), r.abs().max().item()
+        assert d <= 2e-3 * s + 1e-6, f"{cfg} grad {name}: {d} (scale {s})"
+    assert m.beta_from_xyz[0].weight.grad.abs().sum().item() > 0
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 3e-2)])
+@pytest.mark.parametrize("cfg,kw", [("lambertian", dict(mode="test")), ("lambertian_viewdir", dict(mode="test")),
+                                    ("rpv111", dict(mode="test", apply_brdf=True, cos_irra_on=True))])
+def test_render_rays_with_ts(cuda, cfg, kw, precision, tol):
+    """render_rays(models={'coarse', 't'}, ts): every result key of the oracle present, beta / rgb / depth within tolerance;
+    a beta model without ts raises like the reference does (torch.cat with None)."""
+    args, m, state, emb = _setup(cfg, cuda, precision=precision)
+    n = 96
+    batch = make_rays(n)
+    od = RT.Draws.make(n, 64, 64, 128, seed=8)
+    ts = torch.arange(n) % 3
+    with torch.no_grad():
+        ora, bt, _ = RT.render_rays(RT.OracleModel(state, args), args, batch.rays, od, rays_t=emb(ts), **kw)
+        res, bt2 = render_rays({"coarse": m, "t": emb.to(cuda)}, args, batch.rays.to(cuda), ts.to(cuda),
+                               _draws=Draws(u_strat=od.u_strat, u_pred=od.u_pred), **kw)
+    assert bt == bt2 and set(res) == set(ora), sorted(set(res) ^ set(ora))
+    assert res["beta_coarse"].shape == (n, 128, 1)
+    keys = ("beta_coarse", "depth_coarse", "albedo_accu_coarse") + (("rgb_coarse",) if precision == "fp32" or cfg != "rpv111" else ())
+    for k in keys:
+        d = (res[k].cpu() - ora[k]).abs().max().item()
+        assert d <= tol, f"{cfg}/{precision}: {k} differs by {d}"
+    with pytest.raises(ValueError):
+        render_rays({"coarse": m}, args, batch.rays.to(cuda), None, **kw)
+
+
+def test_trainer_refuses_beta_models(cuda):
+    from brdf_nerf_b200.train import Trainer
+    args, m, _, _ = _setup("lambertian", cuda)
+    with pytest.raises(NotImplementedError, match="beta"):
+        Trainer(m, args)

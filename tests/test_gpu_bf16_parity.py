@@ -129,6 +129,44 @@ def test_train_chain_stored_activations(cuda, n):
 
 
 # ----------------------------------------------------------------------------------------------------------------
+def test_fused_kernels_are_deterministic(cuda):
+    """The fused trunk forward (train_chain_kernel), the density chain (sigma_chain_kernel) and the fused data-gradient chain
+    (dgrad_chain_kernel) contain no atomics: 20 runs on the same inputs must give bit-identical activations / densities /
+    dZ buffers.  (compute-sanitizer is closed on this GPU pool, profiles/r02_sanitizer_note.txt: a hazard in the in-place
+    K-block hand-over, the TMA staging boxes or the mbarrier protocol would show up here as run-to-run differences.)"""
+    from brdf_nerf_b200 import ops
+    args = named_config("lambertian_ds")
+    torch.manual_seed(0)
+    model = load_model(args, precision="bf16").to(cuda)
+    n = 40000                                   # 157 blocks of 256 points: more than one round over the 74 CTA pairs
+    x = _pts(n, 3).to(cuda)
+    z = torch.zeros((n, 1), dtype=torch.float32, device=cuda)
+    flags = model.mlp_flags(train=True)
+    ws = model.workspace(n, flags, tag=None)
+    Cn = model.out_channels(flags)
+    out = torch.empty((n, Cn), dtype=torch.float32, device=cuda)
+    g_out = torch.randn(n, Cn, generator=torch.Generator().manual_seed(4)).to(cuda)
+    model.sync_weights()
+    sig = torch.empty((n, 1), dtype=torch.float32, device=cuda)
+    ws_s = model.workspace(n, L.MLP_SIGMA_ONLY, tag=None)
+    ref = None
+    for it in range(20):
+        ops.mlp_forward(model, x, 3, x, 3, z, flags, out, Cn, ws)
+        g = torch.zeros_like(model.flat_params)
+        ops.mlp_backward(model, out, g_out, Cn, n, 1, flags, g, ws)
+        ops.mlp_forward(model, x, 3, x, 3, z, L.MLP_SIGMA_ONLY, sig, 1, ws_s)
+        torch.cuda.synchronize()
+        h7 = _ws_tensor(model, ws, n, flags, 1, 7, 512).clone()
+        c3 = _ws_tensor(model, ws, n, flags, 2, 3, 512).clone()
+        cur = (out.clone(), h7, c3, sig.clone(), ws.clone())          # the workspace holds every dZ_l of the dgrad chain
+        if ref is None:
+            ref = cur
+        else:
+            for a, b, name in zip(ref, cur, ("packed output", "h_7", "c_3", "density", "workspace (activations + dZ_l)")):
+                assert torch.equal(a, b), f"run {it}: {name} differs from run 0"
+
+
+# ----------------------------------------------------------------------------------------------------------------
 # first-order backward of the bf16 path, per parameter tensor
 def _grad_report(m32, m16, floor=1e-5):
     """{tensor: (relative L2 error, cosine)} of the bf16 gradient against the fp32-mode gradient.  Tensors whose fp32

@@ -45,8 +45,11 @@ def test_against_reference_golden(cuda, name):
                   u_gt=torch.from_numpy(g["u_gt"]) if ds else None,
                   u_sun=torch.from_numpy(g["u_sun"]) if "u_sun" in g else None)
     sup = {k: v.to(cuda) for k, v in G.supervision(g).items()} if ds else {}
+    ts, emb = G.time_embedding(g)                      # beta cases: models['t'] and ts as the reference's callers pass them
+    models = {"coarse": model} if emb is None else {"coarse": model, "t": emb.to(cuda)}
     with torch.no_grad():
-        res, btype, ex = render_rays({"coarse": model}, args, rays, None, _draws=draws, _return_extras=True, **kw, **sup)
+        res, btype, ex = render_rays(models, args, rays, None if ts is None else ts.to(cuda), _draws=draws, _return_extras=True,
+                                     **kw, **sup)
     assert btype == str(g["brdf_type"])
     S1 = args.n_samples
     # stratified half of the unsorted samples is a pure function of rays + draws: bit-exact
@@ -54,7 +57,7 @@ def test_against_reference_golden(cuda, name):
         assert G.bits_equal(res["z_vals_unsort_coarse"][:, :S1].cpu().numpy(), g["ref_z_vals_unsort"][:, :S1]) == 0
     dz = np.abs(res["z_vals_coarse"].cpu().numpy() - g["ref_z_vals"]).max()
     assert dz <= 1e-4, f"z_vals moved by {dz}"
-    for k in ("depth", "rgb", "weights", "albedo_accu", "nr_vw", "nr_sun", "brdf", "sun", "weights_sc"):
+    for k in ("depth", "rgb", "weights", "albedo_accu", "nr_vw", "nr_sun", "brdf", "sun", "weights_sc", "beta"):
         if "ref_" + k in g:
             assert k + "_coarse" in res, f"missing result key {k}_coarse"
             got = res[k + "_coarse"].cpu().numpy()

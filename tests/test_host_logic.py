@@ -66,7 +66,9 @@ def test_unsupported_model_options_fail_loudly():
     with pytest.raises(ValueError):
         load_model(make_args(model="sps-nerf"))
     with pytest.raises(NotImplementedError):
-        load_model(named_config("lambertian", beta=True))
+        load_model(named_config("lambertian", indirect_light=True))
+    m = load_model(named_config("lambertian", beta=True))                  # beta head reads [features | t-embedding]
+    assert tuple(m.beta_from_xyz[0].weight.shape) == (256, 512 + 4) and m.number_of_outputs == 5
     m = load_model(named_config("lambertian", input_viewdir=1))            # colour head reads [features | Mapping(d)]
     assert tuple(m.rgb_from_xyzdir[0].weight.shape) == (256, 512 + 24)
     m = load_model(named_config("lambertian", input_viewdir=1, mapping=False))
@@ -250,14 +252,13 @@ def test_algorithmic_flops_match_the_survey():
 
 
 def test_refused_options_cite_their_reason():
-    """R19 is knowingly partial: the three optional channels that are not built are refused at construction
-    with the reference lines that justify it (not silently ignored)."""
+    """R19: `beta` is built (tests/test_gpu_beta.py); the two optional channels that are not are refused at
+    construction with the reference lines that justify it (not silently ignored)."""
     import pytest
     import torch
     from brdf_nerf_b200.config import named_config
     from brdf_nerf_b200.models import load_model
-    for over, needle in ((dict(beta=True), "spsbrdfnerf.py:571-575"), (dict(indirect_light=True), "out[..., 5:8]"),
-                         (dict(sun_v="learned"), "NameError")):
+    for over, needle in ((dict(indirect_light=True), "out[..., 5:8]"), (dict(sun_v="learned"), "NameError")):
         args = named_config("lambertian", **over)
         torch.manual_seed(0)
         with pytest.raises(NotImplementedError) as e:

@@ -28,7 +28,9 @@ def test_oracle_matches_reference_golden(name):
                      noise_sun=zeros(*g["u_sun"].shape) if "u_sun" in g else None)
     om = RT.OracleModel(state, args)
     with torch.no_grad():
-        res, btype, _ = RT.render_rays(om, args, rays, draws, **kw, **(G.supervision(g) if ds else {}))
+        ts, emb = G.time_embedding(g)
+        tkw = {} if ts is None else dict(rays_t=emb(ts))
+        res, btype, _ = RT.render_rays(om, args, rays, draws, **tkw, **kw, **(G.supervision(g) if ds else {}))
     assert btype == str(g["brdf_type"])
     assert G.bits_equal(res["z_vals_coarse"].numpy(), g["ref_z_vals"]) == 0
     assert G.bits_equal(res["z_vals_unsort_coarse"].numpy(), g["ref_z_vals_unsort"]) == 0
@@ -40,7 +42,7 @@ def test_oracle_matches_reference_golden(name):
         assert G.bits_equal(np.take_along_axis(un, idx, 1), np.take_along_axis(un, ridx, 1)) == 0
         ties = (np.diff(g["ref_z_vals"], axis=-1) == 0).any()
         assert ties or np.array_equal(idx, ridx)
-    for k in ("depth", "rgb", "weights", "albedo_accu", "sigmas", "nr_vw", "nr_sun", "brdf", "sun", "weights_sc"):
+    for k in ("depth", "rgb", "weights", "albedo_accu", "sigmas", "nr_vw", "nr_sun", "brdf", "sun", "weights_sc", "beta"):
         if "ref_" + k in g:
             d = np.abs(res[k + "_coarse"].numpy() - g["ref_" + k]).max()
             assert d <= 2e-6, f"{name}: {k} differs from the reference by {d}"

@@ -243,3 +243,41 @@ def test_option_variants_vs_reference(cfg, over, kw):
             assert torch.equal(ref[k], ora[k]), k
         else:
             assert (ref[k] - ora[k]).abs().max().item() <= 2e-6, k
+
+
+@pytest.mark.parametrize("cfg,kw", [("lambertian", dict(mode="test")), ("rpv111", dict(mode="test", apply_brdf=True, cos_irra_on=True)),
+                                    ("lambertian_viewdir", dict(mode="test"))])
+def test_beta_channel_vs_reference(cfg, kw):
+    """beta=True (transient-uncertainty head on [features | t-embedding], spsbrdfnerf.py:571-575, 708-711; rays_t =
+    models['t'](ts), rendering.py:228-229): identical state_dict keys and seeded weights, identical result keys (the early
+    return of `inference` is skipped: irradiance / rays_d / sun_d appear), every key equal to the live reference."""
+    import torch
+    from brdf_nerf_b200.config import named_config
+    from brdf_nerf_b200.models import load_model
+    from brdf_nerf_b200.synth import make_rays
+    from oracle import ref_harness as RH
+    from oracle import render_torch as RT
+    if not RH.available():
+        pytest.skip("reference tree not available")
+    args = named_config(cfg, beta=True)
+    n = 12
+    batch = make_rays(n)
+    draws = RT.Draws.make(n, 64, 64, 128, seed=5)
+    ref_model = RH.build_model(args, seed=0)
+    torch.manual_seed(1)
+    emb = torch.nn.Embedding(args.t_embbeding_vocab, args.t_embbeding_tau)
+    ts = torch.arange(n) % 3
+    with torch.no_grad():
+        ref, bt = RH.render(ref_model, args, batch.rays, draws, ts=ts, embedding=emb, **kw)
+    torch.manual_seed(0)
+    sd = load_model(args).state_dict()
+    rsd = ref_model.state_dict()
+    assert list(sd) == list(rsd)
+    assert all(torch.equal(sd[k], rsd[k]) for k in sd)
+    with torch.no_grad():
+        ora, bt2, _ = RT.render_rays(RT.OracleModel(sd, args), args, batch.rays, draws, rays_t=emb(ts), **kw)
+    assert bt == bt2 and set(ora) == set(ref)
+    assert "beta_coarse" in ref and ref["beta_coarse"].shape == (n, 128, 1) and "irradiance_coarse" in ref
+    for k in ref:
+        if ref[k].dtype.is_floating_point:
+            assert (ora[k].float() - ref[k].float()).abs().max().item() <= 2e-6, k
