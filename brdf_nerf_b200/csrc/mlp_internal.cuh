@@ -397,7 +397,8 @@ static int layer_wgrad(const bn_mlp* h, const T* G, long long ldg, const T* In, 
     }
   }
   EpiWgrad e{dW, ldw, Mo, No, pad_lo, pad_hi};
-  if (int rc = gemm_nt<T>(h, G, ldg, In, ldin, Mo, No, P, e, s, flops)) return rc;
+  // the CUDA-core GEMM wants widths in multiples of 8: round up (the operand's pitch covers it, the epilogue drops cols >= No)
+  if (int rc = gemm_nt<T>(h, G, ldg, In, ldin, Mo, (No + 7) / 8 * 8, P, e, s, flops)) return rc;
   if (bias_grad) return colsum<T>(G, ldg, Mo, P, bias_grad, s);
   return BN_OK;
 }

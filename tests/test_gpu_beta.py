@@ -98,3 +98,26 @@ def test_trainer_refuses_beta_models(cuda):
     args, m, _, _ = _setup("lambertian", cuda)
     with pytest.raises(NotImplementedError, match="beta"):
         Trainer(m, args)
+
+
+def test_beta_backward_bf16_vs_fp32(cuda):
+    """tcgen05 mode: the beta block's first-layer weight gradient goes through the TMA reduce-add maps with a gap
+    ([features | pad | t | pad] -> Linear(516)); per-tensor relative L2 error <= 3e-2, cosine >= 0.999 against the fp32 mode."""
+    n = 4096
+    g = torch.Generator().manual_seed(5)
+    x = (torch.rand(n, 3, generator=g) * 1.6 - 0.8).to(cuda)
+    grads = {}
+    for precision in ("fp32", "bf16"):
+        args, m, _, emb = _setup("lambertian", cuda, precision=precision)
+        t = emb(torch.randint(0, 30, (n,), generator=torch.Generator().manual_seed(6))).detach().to(cuda)
+        G = torch.randn(n, 5, generator=torch.Generator().manual_seed(7)).to(cuda)
+        m.flat_grads.zero_()
+        (m(x, input_t=t) * G).sum().backward()
+        grads[precision] = {k: p.grad.detach().flatten().double().clone() for k, p in m.named_parameters()}
+    for k, a in grads["fp32"].items():
+        b = grads["bf16"][k]
+        if a.norm().item() == 0.0:
+            continue
+        rel = ((a - b).norm() / a.norm()).item()
+        cos = torch.nn.functional.cosine_similarity(a, b, dim=0).item()
+        assert rel <= 3e-2 and cos >= 0.999, (k, rel, cos)
