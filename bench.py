@@ -355,8 +355,49 @@ def run_ours(opts):
     # kernel nodes every CUDA-graph replay executes (counted once, at capture time)
     launches = (lib.bn_launch_count() - lc0) + opts.steps * getattr(trainer, "graph_launches", 0)
     mark_main = clocks.mark() if clocks else 0
-    # ---- roofline leg: per-launch CUDA-event timing of the GEMM family on the launching stream, taken right after the
-    # timed steps (same thermal state: before the e2e and the seconds-long sustained leg push the GPU into its power cap) ----
+    total_rays = RAYS_PER_GPU * world
+    # ---- end to end through the public API, right after the resident leg (same steps, same thermal state): every step's
+    # batch starts in pinned host memory and is copied into the device (H2D), every step's loss is read back into host memory
+    # (D2H), both inside the timed region.  --feed inline (default):
+    # both copies are issued on the compute stream between two graph replays; --feed prefetch: Trainer.prefetch() copies batch
+    # k+1 on the trainer's copy stream while step k computes and read_loss_async() moves the loss on that same stream
+    # (measured on B200, profiles/r01f_exp_e2e.log: no gain, the two copies cost ~5 us each; the e2e leg differs from the
+    # resident leg mainly by running later, on a GPU that has reached its power cap).
+    # The host awaits the loss of step k after step k+1 has been enqueued, the way a training loop logs without stalling.
+    pin = torch.empty(4, dtype=torch.float32).pin_memory()
+    evs = [None] * 4
+    barrier()
+    e0.record()
+    prev = None
+    loss_host = float("nan")
+    if opts.feed == "prefetch":
+        staged = trainer.prefetch(host_batch)
+        for i in range(opts.steps):
+            loss = trainer.step(staged)
+            if i + 1 < opts.steps:
+                staged = trainer.prefetch(host_batch)
+            evs[i % 4] = trainer.read_loss_async(loss, pin[i % 4:i % 4 + 1])
+            if prev is not None:
+                evs[prev].synchronize()
+                loss_host = float(pin[prev])
+            prev = i % 4
+    else:
+        for i in range(opts.steps):
+            loss = trainer.step(host_batch if opts.graph else host_batch.to(dev, non_blocking=True))
+            pin[i % 4:i % 4 + 1].copy_(loss.reshape(1), non_blocking=True)
+            evs[i % 4] = torch.cuda.Event()
+            evs[i % 4].record()
+            if prev is not None:
+                evs[prev].synchronize()
+                loss_host = float(pin[prev])
+            prev = i % 4
+    evs[prev].synchronize()
+    loss_host = float(pin[prev])
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1) / opts.steps
+    # ---- roofline leg: per-launch CUDA-event timing of the GEMM family on the launching stream, taken right after the two
+    # timed legs (before the seconds-long sustained leg pushes the GPU into its power cap) ----
     roof = None
     if rank == 0:
         peaks = _peaks()
@@ -402,46 +443,6 @@ def run_ours(opts):
                                 "executed_gflop_per_step": gemm_flops / 1e9, "algorithmic_gflop_per_step_shared_trunk": alg_shared / 1e9,
                                 "reference_gflop_per_step": alg / 1e9,
                                 "by_kind": {"chain_fwd": kind(2), "chain_dgrad": kind(3), "tn_fwd_dgrad": kind(0), "nt_wgrad": kind(1)}}}
-    total_rays = RAYS_PER_GPU * world
-    # ---- end to end through the public API: every step's batch starts in pinned host memory and is copied into the device
-    # (H2D), every step's loss is read back into host memory (D2H), both inside the timed region.  --feed inline (default):
-    # both copies are issued on the compute stream between two graph replays; --feed prefetch: Trainer.prefetch() copies batch
-    # k+1 on the trainer's copy stream while step k computes and read_loss_async() moves the loss on that same stream
-    # (measured on B200, profiles/r01f_exp_e2e.log: no gain, the two copies cost ~5 us each; the e2e leg differs from the
-    # resident leg mainly by running later, on a GPU that has reached its power cap).
-    # The host awaits the loss of step k after step k+1 has been enqueued, the way a training loop logs without stalling.
-    pin = torch.empty(4, dtype=torch.float32).pin_memory()
-    evs = [None] * 4
-    barrier()
-    e0.record()
-    prev = None
-    loss_host = float("nan")
-    if opts.feed == "prefetch":
-        staged = trainer.prefetch(host_batch)
-        for i in range(opts.steps):
-            loss = trainer.step(staged)
-            if i + 1 < opts.steps:
-                staged = trainer.prefetch(host_batch)
-            evs[i % 4] = trainer.read_loss_async(loss, pin[i % 4:i % 4 + 1])
-            if prev is not None:
-                evs[prev].synchronize()
-                loss_host = float(pin[prev])
-            prev = i % 4
-    else:
-        for i in range(opts.steps):
-            loss = trainer.step(host_batch if opts.graph else host_batch.to(dev, non_blocking=True))
-            pin[i % 4:i % 4 + 1].copy_(loss.reshape(1), non_blocking=True)
-            evs[i % 4] = torch.cuda.Event()
-            evs[i % 4].record()
-            if prev is not None:
-                evs[prev].synchronize()
-                loss_host = float(pin[prev])
-            prev = i % 4
-    evs[prev].synchronize()
-    loss_host = float(pin[prev])
-    e1.record()
-    barrier()
-    ms_e2e = e0.elapsed_time(e1) / opts.steps
     mark1 = clocks.mark() if clocks else 0
     # ---- sustained leg: the same resident step for >= opts.sustain seconds back to back.  The K timed steps above last a few
     # tens of milliseconds (a burst: the GPU has not reached its 1 kW power cap); a training run lives here instead.

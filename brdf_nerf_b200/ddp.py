@@ -28,7 +28,11 @@ class _RawCuda:
 
 
 class PeerExchange:
-    """In-place sum of `bucket` (n fp32) over the ranks of `group` through NVLink peer memory."""
+    """In-place sum of `bucket` (n fp32) over the ranks of `group` through NVLink peer memory.
+
+    Construction is collective and cannot deadlock on a local failure: every rank always takes part in the same two
+    collectives (the all_gather of handle + status byte, the all_reduce of the final status); if any rank failed to allocate,
+    export or map, `ok` is False on EVERY rank and the caller falls back to torch.distributed."""
 
     N_BLOCKS = 128
 
@@ -43,29 +47,45 @@ class PeerExchange:
         flag_words = int(lib.bn_allreduce_p2p_flag_words())
         self.flag_off = (self.n * 4 + 255) // 256 * 256
         nbytes = self.flag_off + flag_words * 4
+        self._base, self._peer_base, self.error = None, [], None
+        payload = torch.zeros(65, dtype=torch.uint8, device=device)          # 64-byte IPC handle + status (1 = ok)
         with torch.cuda.device(device):
-            base = C.c_void_p()
-            L.check(lib.bn_peer_alloc(nbytes, C.byref(base)))
-            self._base = base
-            handle = (C.c_ubyte * 64)()
-            L.check(lib.bn_peer_export(base, handle))
-            mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device=device)
-            all_h = [torch.empty_like(mine) for _ in range(self.world)]
-            dist.all_gather(all_h, mine, group=group)
-            self._peer_base = []
-            for p in range(self.world):
-                if p == self.rank:
-                    self._peer_base.append(base.value)
-                    continue
-                hb = (C.c_ubyte * 64)(*all_h[p].cpu().tolist())
-                ptr = C.c_void_p()
-                L.check(lib.bn_peer_open(hb, C.byref(ptr)))
-                self._peer_base.append(ptr.value)
+            try:
+                base = C.c_void_p()
+                L.check(lib.bn_peer_alloc(nbytes, C.byref(base)))
+                self._base = base
+                handle = (C.c_ubyte * 64)()
+                L.check(lib.bn_peer_export(base, handle))
+                payload = torch.tensor(list(bytes(handle)) + [1], dtype=torch.uint8, device=device)
+            except Exception as e:                                           # noqa: BLE001
+                self.error = f"{type(e).__name__}: {e}"
+            all_h = [torch.empty_like(payload) for _ in range(self.world)]
+            dist.all_gather(all_h, payload, group=group)
+            all_h = [h.cpu().tolist() for h in all_h]
+            ok = all(h[64] == 1 for h in all_h)
+            if ok:
+                try:
+                    for p in range(self.world):
+                        if p == self.rank:
+                            self._peer_base.append(self._base.value)
+                            continue
+                        hb = (C.c_ubyte * 64)(*all_h[p][:64])
+                        ptr = C.c_void_p()
+                        L.check(lib.bn_peer_open(hb, C.byref(ptr)))
+                        self._peer_base.append(ptr.value)
+                except Exception as e:                                       # noqa: BLE001
+                    self.error = f"{type(e).__name__}: {e}"
+                    ok = False
+            flag = torch.tensor([1.0 if ok else 0.0], device=device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)         # also: every rank has opened every handle
+            self.ok = bool(flag.item() >= 1.0)
+        if not self.ok:
+            self.close()
+            return
         self._bufs = (C.c_void_p * self.world)(*[C.c_void_p(b) for b in self._peer_base])
         self._flags = (C.c_void_p * self.world)(*[C.c_void_p(b + self.flag_off) for b in self._peer_base])
-        self.bucket = torch.as_tensor(_RawCuda(base.value, self.n), device=device)      # this rank's bucket as a tensor
+        self.bucket = torch.as_tensor(_RawCuda(self._base.value, self.n), device=device)      # this rank's bucket as a tensor
         self._epoch = torch.zeros(128, dtype=torch.int32, device=device)
-        dist.barrier(group=group)                  # every rank has opened every handle before the first exchange
 
     def all_reduce_(self):
         """Enqueue the exchange on the current stream (graph-capturable)."""
@@ -80,6 +100,7 @@ class PeerExchange:
         if self._base is not None:
             self.lib.bn_peer_free(self._base)
             self._base = None
+        self.ok = False
 
 
 def make_exchange(model, group=None) -> Optional[PeerExchange]:
@@ -95,17 +116,12 @@ def make_exchange(model, group=None) -> Optional[PeerExchange]:
     flat = model.flat_params
     if not flat.is_cuda:
         return None
-    ok = torch.ones(1, device=flat.device)
-    ex = None
-    try:
-        ex = PeerExchange(flat.numel(), flat.device, group)
-    except Exception as e:                                  # noqa: BLE001  (peer mapping refused: fall back on every rank)
-        print(f"[brdf_nerf_b200.ddp] peer mapping unavailable ({type(e).__name__}: {e}); using torch.distributed.all_reduce")
-        ok.zero_()
-    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
-    if ok.item() < 1:
-        if ex is not None:
-            ex.close()
+    ex = PeerExchange(flat.numel(), flat.device, group)
+    if not ex.ok:
+        if ex.error:
+            import sys
+            print(f"[brdf_nerf_b200.ddp] peer mapping unavailable on rank {ex.rank} ({ex.error}); using torch.distributed.all_reduce",
+                  file=sys.stderr)
         return None
     model.rebind_grads(ex.bucket)
     return ex

@@ -47,6 +47,7 @@ def main():
     # ---- 1. the exchange kernel alone
     n = 2_297_000 // 8 * 8
     ex = ddp.PeerExchange(n, dev)
+    assert ex.ok, f"peer mapping failed: {ex.error}"
     g = torch.Generator(device=dev).manual_seed(100 + rank)
     worst = 0.0
     for it in range(5):
