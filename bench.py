@@ -31,11 +31,15 @@ import torch  # noqa: E402
 RAYS_PER_GPU = 1024
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel of the step, chain::train_chain_kernel at
 # P = 65536 points (two launches per step: stratified points, guided points), from the ncu --set full capture under profiles/
-NCU_CHAIN_DRAM_BYTES_PER_LAUNCH = 15.6e6 + 1026.8e6
-NCU_TRAFFIC_NOTE = ("ncu --set full (profiles/r01f_ncu_full_train_chain.csv and r01e_ncu_full_train_chain.csv, P = 65536): 15.7 MB read + 1026.7 MB written per launch "
-                    "= the algorithmic 1.07 GB (h_l, c_l of 8 layers + encoding, bf16; nothing is read back). "
-                    "trunk dgrad GEMM (profiles/r01e_ncu_full_gemm.csv): 269 MB read + 105 MB written per launch vs 384 MiB algorithmic "
-                    "(the tail of the writes is still in L2 at kernel end); trunk wgrad GEMM: 269.5 MB read vs 256 MiB algorithmic")
+NCU_CHAIN_DRAM_BYTES_PER_LAUNCH = 4.7e6 + 1024.3e6
+NCU_TRAFFIC_NOTE = ("ncu --set full (profiles/r02_ncu_full_chain_kernels.csv, P = 65536): 4.7 MB read + 1024.3 MB written per launch "
+                    "= the algorithmic 1.07 GB (h_l, c_l of 8 layers + encoding, bf16; nothing is read back; the weights stay in L2). "
+                    "fused data-gradient chain (dgrad_chain_kernel, P = 131072, same capture): 1079 MB read + 889 MB written vs "
+                    "1073 + 939 MB algorithmic (c_l of 7 layers + dZ_7 in, dZ_l of 7 layers out; the tail of the writes is still in L2); "
+                    "trunk wgrad GEMM (profiles/r01e_ncu_full_gemm.csv): 269.5 MB read vs 256 MiB algorithmic")
+# K-C kernels at 65 536 rays x 128 samples, dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/r02_ncu_full_kc_kernels.csv)
+NCU_KC_DRAM_BYTES = {"composite_fwd C=4": 167.8e6 + 69.6e6, "composite_bwd C=4": 270.0e6 + 105.9e6,
+                     "composite_fwd C=16": 570.4e6 + 94.8e6, "composite_bwd C=16": 676.0e6 + 490.3e6}
 METRIC = "train rays/s (SpS-BRDF-NeRF, 1/2/4/8 B200); MLP tensor-pipe %; composite GB/s"
 
 

@@ -264,3 +264,33 @@ def test_refused_options_cite_their_reason():
         with pytest.raises(NotImplementedError) as e:
             load_model(args)
         assert needle in str(e.value), str(e.value)
+
+
+def test_bench_and_package_have_no_undefined_names():
+    """bench.py cannot run on the CPU box (no fallback), so a NameError in one of its legs would only surface on the GPU:
+    a stdlib-only undefined-name check over bench.py and the package's Python modules."""
+    import ast
+    import builtins
+    import glob
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = [os.path.join(root, "bench.py"), os.path.join(root, "__graft_entry__.py")] + \
+        glob.glob(os.path.join(root, "brdf_nerf_b200", "**", "*.py"), recursive=True)
+    for path in files:
+        tree = ast.parse(open(path).read())
+        defined = set(dir(builtins)) | {"__file__"}
+        for n in ast.walk(tree):
+            if isinstance(n, (ast.FunctionDef, ast.ClassDef)):
+                defined.add(n.name)
+            elif isinstance(n, ast.Import):
+                defined.update(a.asname or a.name.split(".")[0] for a in n.names)
+            elif isinstance(n, ast.ImportFrom):
+                defined.update(a.asname or a.name for a in n.names)
+            elif isinstance(n, ast.Name) and isinstance(n.ctx, (ast.Store, ast.Del)):
+                defined.add(n.id)
+            elif isinstance(n, ast.arg):
+                defined.add(n.arg)
+            elif isinstance(n, ast.ExceptHandler) and n.name:
+                defined.add(n.name)
+        missing = sorted({n.id for n in ast.walk(tree) if isinstance(n, ast.Name) and isinstance(n.ctx, ast.Load)
+                          and n.id not in defined})
+        assert not missing, f"{os.path.relpath(path, root)}: undefined names {missing}"
