@@ -110,7 +110,9 @@ def test_beta_backward_bf16_vs_fp32(cuda):
     for precision in ("fp32", "bf16"):
         args, m, _, emb = _setup("lambertian", cuda, precision=precision)
         t = emb(torch.randint(0, 30, (n,), generator=torch.Generator().manual_seed(6))).detach().to(cuda)
-        G = torch.randn(n, 5, generator=torch.Generator().manual_seed(7)).to(cuda)
+        G = torch.randn(n, 5, generator=torch.Generator().manual_seed(7))
+        G[:, 4] = G[:, 4].abs()          # no cancellation in the (scalar / per-column) bias sums of the beta head: with random signs
+        G = G.to(cuda)                   # the sum is ~0.1 % of its terms and any 1e-3 forward difference reads as a 100 % error
         m.flat_grads.zero_()
         (m(x, input_t=t) * G).sum().backward()
         grads[precision] = {k: p.grad.detach().flatten().double().clone() for k, p in m.named_parameters()}
