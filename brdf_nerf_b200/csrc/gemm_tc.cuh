@@ -238,13 +238,38 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n, bool mn_major) {
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+// L2 prefetch of one box (no shared memory, no barrier): the DRAM access happens `distance` K blocks before the load
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1) : "memory");
+}
+// NT only: how many K blocks ahead of its loads the producer prefetches the operand boxes into L2.  The operand ring
+// (5 stages of 32 KB) holds about 2 000 cycles of work, less than the latency of a loaded HBM; the prefetch moves the
+// DRAM latency out of the ring, which then only has to cover an L2 hit.  MEASURED on B200 (profiles/r02m_ab_wgrad.txt): the
+// opposite — 752 us of weight gradients per step without, 774 / 793 / 849 / 951 us at distance 4 / 8 / 16 / 32.  The kernel is
+// not bound by its loads at all: with every load after the first ring pass, the bias MMAs and the epilogue stores removed it
+// takes the same time (profiles/r02o_ab_wgrad.txt), and the trace (scripts/trace_wgrad.py, profiles/r02p_trace_wgrad.txt) shows
+// the issuer thread inside the MMA issue for 897 cycles per K block = 224 cycles per 256x256x16 pair MMA (128 nominal, ~180 at
+// the cuBLAS rate this pool measures) while it waits ~100 cycles per K block for operands.  Off; BN_NT_PREFETCH=<k> enables.
+inline int nt_prefetch_distance() {
+  const char* e = getenv("BN_NT_PREFETCH");       // read per launch: A/B runs inside one process
+  return e ? atoi(e) : 0;
+}
+
 struct Work {
   int m_tiles, n_tiles, splits;   // 128-row tiles, BN-column tiles; splits only for kNT
   int kb_total, kb_per_split;     // k-blocks (of kBK) in the reduction dimension
   int n_cols;                     // real number of output columns (a multiple of the epilogue unit)
   int reverse;                    // TN only: walk the row tiles from the last to the first (see tile_reverse())
   uint64_t pol_a, pol_b;          // TN only: L2 eviction policies of the A (activation) and B (weight) tiles
+  int pf;                         // NT only: L2 prefetch distance in K blocks (0 = off)
+  long long* trace;               // NT pair only: [0] kernel entry, [1] setup done, [2] first MMA issued, [3] last MMA issued, [4] cycles the
+                                  // issuer waited for operands, [5] K blocks, [6] accumulator complete (epilogue), [7] epilogue done,
+                                  // [8] cycles the producer waited for free slots
 };
+// diagnostics (bn_debug_chain_trace with BN_NT_TRACE set): clock64() stamps of CTA pair 0 of the 512 x 512 weight-gradient launches
+inline long long*& nt_trace() { static long long* p = nullptr; return p; }
+
 
 // Tile order of the NEXT tn launches on this thread (experiment knob).  Idea: in a chain of GEMMs in which each one consumes
 // the [P, F] tensor its predecessor has just written, let the consumer start with the rows the producer wrote last, which
@@ -328,6 +353,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   pdl_launch_dependents();
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  [[maybe_unused]] const bool tr = kNT && kPair && wk.trace != nullptr && blockIdx.x == 0;
+  if (tr && threadIdx.x == 0) wk.trace[0] = clock64();
   const int m_groups = (wk.m_tiles + CL - 1) / CL;                 // row tiles are handed out CL at a time
   const int n_items = m_groups * wk.n_tiles * wk.splits;
   const int t_count = m_groups * wk.n_tiles;
@@ -363,6 +390,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();                              // the previous kernel's results are visible from here on
+  if (tr && threadIdx.x == 0) wk.trace[1] = clock64();
 
   if (warp == 0) {
     // ===================== TMA producer (every CTA stages its own A rows and its share of B) =====================
@@ -375,8 +403,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int ncol0 = n_blk * BN + crank * BNL;              // first B row / output column staged by this CTA
         const int kb0 = split * wk.kb_per_split;
         const int kb1 = min(wk.kb_total, kb0 + wk.kb_per_split);
+        [[maybe_unused]] auto prefetch_kb = [&](int kp) {
+#pragma unroll
+          for (int c = 0; c < kBM / 64; ++c) tma_prefetch_2d(&tmA, m_blk * kBM + c * 64, kp * kBK);
+#pragma unroll
+          for (int c = 0; c < BNL / 64; ++c) tma_prefetch_2d(&tmB, ncol0 + c * 64, kp * kBK);
+        };
+        if constexpr (kNT) {
+          if (wk.pf > 0)
+            for (int kp = kb0 + STAGES; kp < min(kb1, kb0 + wk.pf); ++kp) prefetch_kb(kp);
+        }
+        long long t_slot = 0;
         for (int kb = kb0; kb < kb1; ++kb) {
+          if constexpr (kNT) { if (wk.pf > 0 && kb + wk.pf < kb1) prefetch_kb(kb + wk.pf); }
+          const long long ts0 = tr ? clock64() : 0;
           mbar_wait(&empty[stage], phase ^ 1);          // the MMAs that read this slot have retired
+          if (tr) t_slot += clock64() - ts0;
           uint8_t* a = sA + stage * A_BYTES;
           uint8_t* b = sB + stage * B_BYTES;
           if constexpr (kPair) {
@@ -407,6 +449,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        if (tr) wk.trace[8] = t_slot;
       }
     }
   } else if (warp == 1) {
@@ -430,10 +473,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         fence_after_sync();
         const uint32_t d_tmem = tmem_base + acc * BN;
         [[maybe_unused]] int rot = kb0 % wk.n_tiles;               // kb % n_tiles without a division per K block
+        long long t_wait = 0;
+        if (tr) wk.trace[2] = clock64();
         for (int kb = kb0; kb < kb1; ++kb) {
           [[maybe_unused]] const bool bias_now = bias_on && rot == n_blk;
           if (++rot == wk.n_tiles) rot = 0;
+          const long long tw0 = tr ? clock64() : 0;
           mbar_wait(&full[stage], phase);
+          if (tr) t_wait += clock64() - tw0;
           fence_after_sync();
           const uint32_t a_addr = smem_u32(sA + stage * A_BYTES);
           const uint32_t b_addr = smem_u32(sB + stage * B_BYTES);
@@ -462,6 +509,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         if constexpr (kPair) umma_commit_pair(&tfull[acc]); else umma_commit(&tfull[acc]);
+        if (tr) { wk.trace[3] = clock64(); wk.trace[4] = t_wait; wk.trace[5] = kb1 - kb0; }
         if (++acc == ACC) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -584,6 +632,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int n_units = left >= BN ? BN / 32 : (left + 31) / 32;
         mbar_wait(&tfull[acc], acc_phase);
         fence_after_sync();
+        if (tr && warp == 4 && lane == 0) wk.trace[6] = clock64();
         const int row0 = m_blk * kBM + q * 32;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
         if constexpr (kBias) {
@@ -620,6 +669,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (++acc == ACC) { acc = 0; acc_phase ^= 1; }
       }
       if (lane == 0) bulk_wait0();
+      if (tr && warp == 4 && lane == 0) wk.trace[7] = clock64();
     }
   }
   fence_before_sync();
@@ -681,7 +731,7 @@ int launch_tn(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* B, lon
   if (K % kBK) { set_error("tc::launch_tn: K=%d not a multiple of 64", K); return BN_ERR_ARG; }
   if (Epi::kMode != EPI_DIRECT && N % 64) { set_error("tc::launch_tn: N=%d not a multiple of 64", N); return BN_ERR_ARG; }
   CUtensorMap ma, mb;
-  Work wk{(int)ceil_div_ll(M, kBM), ceil_div(N, BN), 1, K / kBK, K / kBK, N, tile_reverse() ? 1 : 0, pol_stream(), pol_weights()};
+  Work wk{(int)ceil_div_ll(M, kBM), ceil_div(N, BN), 1, K / kBK, K / kBK, N, tile_reverse() ? 1 : 0, pol_stream(), pol_weights(), 0, nullptr};
   if (int rc = make_map_bf16(&ma, A, M, K, lda, kBK, kBM)) return rc;
   if constexpr (BN >= 128) {
     if (wk.m_tiles >= 4) {               // CTA pairs: every CTA stages BN/2 rows of the B tile
@@ -709,6 +759,8 @@ int launch_nt(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* B, lon
   if (int rc = make_map_bf16(&mb, B, P, No, ldb, 64, kBK)) return rc;
   Work wk;
   wk.reverse = 0; wk.pol_a = wk.pol_b = kEvictNormal;
+  wk.pf = nt_prefetch_distance();
+  wk.trace = (Mo == 512 && No == 512) ? nt_trace() : nullptr;
   wk.m_tiles = ceil_div(Mo, kBM); wk.n_tiles = ceil_div(No, BN);
   wk.kb_total = (int)ceil_div_ll(P, kBK);
   wk.n_cols = No;

@@ -394,28 +394,51 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   p[i] = pi - (lr / bc1) * (mi / denom);
 }
 
-// Graph-replayable Adam: the step counter and the learning rate live in device memory (state = {lr, step, bc1, sqrt(bc2)}),
-// so a captured training step advances them itself.
-__global__ void adam_tick_kernel(float* __restrict__ state, float b1, float b2) {
-  const double t = (double)state[1] + 1.0;
-  state[1] = (float)t;
-  state[2] = 1.0f - (float)pow((double)b1, t);
-  state[3] = sqrtf(1.0f - (float)pow((double)b2, t));
-}
-__global__ void adam_state_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                                  float* __restrict__ v, long long n, const float* __restrict__ state, float b1, float b2,
-                                  float eps, float wd, float gscale) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float lr = state[0], bc1 = state[2], bc2_sqrt = state[3];
-  float gi = g[i] * gscale;
-  float pi = p[i];
-  if (wd != 0.f) gi += wd * pi;
-  const float mi = b1 * m[i] + (1.0f - b1) * gi;
-  const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
-  m[i] = mi; v[i] = vi;
-  const float denom = sqrtf(vi) / bc2_sqrt + eps;
-  p[i] = pi - (lr / bc1) * (mi / denom);
+// Graph-replayable Adam: the step counter and the learning rate live in device memory (state = {lr, step, block counter, -}),
+// so a captured training step advances them itself.  ONE launch: every block derives the bias corrections of update
+// t = step + 1, applies it to its 4096 elements, and the block that finishes last stores the new step — after every block
+// has read the old one.  The corrections 1 - b^t are -expm1f(t ln b) with ln b split into two floats: no cancellation (the
+// host path's 1.0f - (float)pow(b, t) carries up to 3e-5 of relative rounding at t = 1, this form 1e-7) and no fp64 on the
+// device (two double-precision pow per block cost 11 us per step on B200: measured, profiles/r02r_launches_step_summary.txt).
+constexpr int kAdamThreads = 1024, kAdamPerThread = 4;
+__global__ void __launch_bounds__(kAdamThreads) adam_state_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                                  float* __restrict__ v, long long n, float* __restrict__ state, float b1,
+                                                                  float b2, float eps, float wd, float gscale, float ln_b1_hi,
+                                                                  float ln_b1_lo, float ln_b2_hi, float ln_b2_lo) {
+  __shared__ float s_bc[3];
+  if (threadIdx.x == 0) {
+    const float t = state[1] + 1.0f;                 // exact up to 2^24 updates
+    s_bc[0] = t;
+    s_bc[1] = -expm1f(fmaf(t, ln_b1_hi, t * ln_b1_lo));
+    s_bc[2] = sqrtf(-expm1f(fmaf(t, ln_b2_hi, t * ln_b2_lo)));
+  }
+  __syncthreads();
+  const float lr = state[0], bc1 = s_bc[1], bc2_sqrt = s_bc[2];
+  const long long i0 = ((long long)blockIdx.x * kAdamThreads + threadIdx.x) * kAdamPerThread;
+  auto update = [&](float& pi, float gi, float& mi, float& vi) {
+    gi *= gscale;
+    if (wd != 0.f) gi += wd * pi;
+    mi = b1 * mi + (1.0f - b1) * gi;
+    vi = b2 * vi + (1.0f - b2) * gi * gi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    pi = pi - (lr / bc1) * (mi / denom);
+  };
+  if (i0 + kAdamPerThread <= n) {
+    float4 P4 = *reinterpret_cast<const float4*>(p + i0), M4 = *reinterpret_cast<const float4*>(m + i0);
+    float4 V4 = *reinterpret_cast<const float4*>(v + i0);
+    const float4 G4 = *reinterpret_cast<const float4*>(g + i0);
+    update(P4.x, G4.x, M4.x, V4.x); update(P4.y, G4.y, M4.y, V4.y); update(P4.z, G4.z, M4.z, V4.z); update(P4.w, G4.w, M4.w, V4.w);
+    *reinterpret_cast<float4*>(p + i0) = P4; *reinterpret_cast<float4*>(m + i0) = M4; *reinterpret_cast<float4*>(v + i0) = V4;
+  } else {
+    for (long long i = i0; i < n; ++i) update(p[i], g[i], m[i], v[i]);
+  }
+  // the last block to finish publishes the new step count (and leaves the counter at zero for the next launch)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned* counter = reinterpret_cast<unsigned*>(state + 2);
+    __threadfence();
+    if (atomicAdd(counter, 1u) == gridDim.x - 1) { *counter = 0u; state[1] = s_bc[0]; }
+  }
 }
 
 // tcgen05 mode, no learned normal: one thread per point turns the gradient of the packed output row into
@@ -496,10 +519,17 @@ __global__ void pack_w2_kernel(HeadPlan hp, const float* __restrict__ params, __
 // forward operands of the heads' second layers as tcgen05 B matrices (N = 64 padded outputs, K-major):
 //   W2pT [64, ldk] : row o = W2_o laid over the columns of its hidden block, zeros elsewhere
 //   Wsig [64, F]   : row 0 = w_sigma, rows 1..3 = grad_from_xyz (learned normal) when evaluated
+//   W2p  [hk, 64]  : the backward's copy (pack_w2_kernel), written here as well when the forward is a training forward
 __global__ void pack_heads_fwd_kernel(HeadPlan hp, const float* __restrict__ params, __nv_bfloat16* __restrict__ W2pT,
-                                      int ldk, __nv_bfloat16* __restrict__ Wsig, int F) {
+                                      int ldk, __nv_bfloat16* __restrict__ Wsig, int F, __nv_bfloat16* __restrict__ W2p) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int hk = hp.n_blocks * hp.HH;
+  if (W2p != nullptr && idx < hk * 64) {
+    const int r = idx / 64, o = idx % 64;
+    float v = 0.f;
+    if (o < hp.n_out && hp.o[o].block == r / hp.HH) v = params[hp.o[o].w_off + (r % hp.HH)];
+    W2p[idx] = __float2bfloat16_rn(v);
+  }
   if (idx < 64 * hk) {
     const int o = idx / hk, cix = idx % hk;
     float v = 0.f;
@@ -520,9 +550,11 @@ __global__ void pack_heads_fwd_kernel(HeadPlan hp, const float* __restrict__ par
 struct EpiHeadsOut {
   static constexpr int kMode = 0, kIn = 0, kOut = 0;
   HeadPlan hp; const float* params; float* out; int pitch; int M;
+  const float* sig;               // density of every row, already computed by the fused trunk kernel (nullptr: not available)
   template <int n> __device__ __forceinline__ void apply(int row, int col0, const float (&acc)[n]) const {
     if (col0 != 0 || row >= M) return;
     float* orow = out + (long long)row * pitch;
+    if (sig) orow[hp.ch_sigma] = __ldg(sig + row);
 #pragma unroll
     for (int o = 0; o < kMaxOut; ++o) {
       if (o < hp.n_out) {
@@ -547,8 +579,10 @@ struct EpiSigmaOut {
   template <int n> __device__ __forceinline__ void apply(int row, int col0, const float (&acc)[n]) const {
     if (col0 != 0 || row >= M) return;
     float* orow = out + (long long)row * pitch;
-    const float sv = acc[0] + __ldg(bsig);
-    orow[ch_sigma] = sv > 20.f ? sv : log1pf(expf(sv));
+    if (ch_sigma >= 0) {
+      const float sv = acc[0] + __ldg(bsig);
+      orow[ch_sigma] = sv > 20.f ? sv : log1pf(expf(sv));
+    }
     if (ch_nlr >= 0) {
       const float g0 = acc[1] + __ldg(bg), g1 = acc[2] + __ldg(bg + 1), g2 = acc[3] + __ldg(bg + 2);
       const float inv = 1.0f / sqrtf(fmaxf(g0 * g0 + g1 * g1 + g2 * g2, 1.1920929e-07f));
@@ -616,6 +650,27 @@ struct PackJob { long long w_off; int N, Kreal, E, Kpad; void* Wp; long long ldp
 constexpr int kMaxPackJobs = 40;
 struct PackJobs { int n; PackJob j[kMaxPackJobs]; };
 
+// bias blocks of the fused trunk kernels (see mlp_chain.cuh): (layer row, column) elements of Wb [L * F, 64], grid-stride over
+// the blocks of one pack job
+__device__ __forceinline__ void pack_bias_blocks(const float* __restrict__ params, __nv_bfloat16* __restrict__ Wb, int L, int F, int E,
+                                                 int skip, const long long* __restrict__ offs) {
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < L * F * 64; idx += gridDim.x * blockDim.x) {
+    const int col = idx & 63, row = (idx >> 6) % F, l = idx / (64 * F);
+    const long long w_off = offs[2 * l], b_off = offs[2 * l + 1];
+    float v = 0.f;
+    if (col < E && (l == 0 || l == skip)) {
+      const int kreal = l == 0 ? E : E + F;                    // the encoding is the FIRST E input columns of both layers
+      v = params[w_off + (long long)row * kreal + col];
+    } else if (col == chain::kOneCol) {
+      v = params[b_off + row];
+    } else if (col == chain::kOneCol + 1) {
+      const float b = params[b_off + row];
+      v = b - __bfloat162float(__float2bfloat16(b));
+    }
+    Wb[idx] = __float2bfloat16(v);
+  }
+}
+
 // One 64 x 64 tile (n x padded k) per block iteration: the fp32 rows are read coalesced along k, the row-major copy Wp is
 // written coalesced along k, and the transposed copy WTp leaves through shared memory coalesced along n (a thread-per-
 // element version wrote WTp with a 2-byte stride-ldt pattern and took 29 us per step for 2.7 M weights).
@@ -624,6 +679,11 @@ template <typename T>
 __global__ void __launch_bounds__(256) pack_all_kernel(const __grid_constant__ PackJobs jobs, const float* __restrict__ params) {
   __shared__ float tile[kPackTile][kPackTile + 1];
   const PackJob& q = jobs.j[blockIdx.y];
+  if (q.Kreal == -2) {                            // bias blocks of the fused trunk kernels (N = L, ldp = F, Kpad = skip, WTp = offsets)
+    if constexpr (std::is_same<T, __nv_bfloat16>::value)
+      pack_bias_blocks(params, reinterpret_cast<__nv_bfloat16*>(q.Wp), q.N, (int)q.ldp, q.E, q.Kpad, reinterpret_cast<const long long*>(q.WTp));
+    return;
+  }
   if (q.Kreal < 0) {                              // bias copy job: Wp is a float* destination, N values
     for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < q.N; n += gridDim.x * blockDim.x)
       reinterpret_cast<float*>(q.Wp)[q.row0 + n] = params[q.w_off + n];
@@ -660,26 +720,6 @@ __global__ void __launch_bounds__(256) pack_all_kernel(const __grid_constant__ P
   }
 }
 
-// bias blocks of the fused trunk kernels (see mlp_chain.cuh): one thread per (layer row, column) of Wb [L * F, 64]
-__global__ void __launch_bounds__(256) pack_bias_blocks_kernel(const float* __restrict__ params, __nv_bfloat16* __restrict__ Wb,
-                                                               int L, int F, int E, int skip, const long long* __restrict__ offs) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= L * F * 64) return;
-  const int col = idx & 63, row = (idx >> 6) % F, l = idx / (64 * F);
-  const long long w_off = offs[2 * l], b_off = offs[2 * l + 1];
-  float v = 0.f;
-  if (col < E && (l == 0 || l == skip)) {
-    const int kreal = l == 0 ? E : E + F;                    // the encoding is the FIRST E input columns of both layers
-    v = params[w_off + (long long)row * kreal + col];
-  } else if (col == chain::kOneCol) {
-    v = params[b_off + row];
-  } else if (col == chain::kOneCol + 1) {
-    const float b = params[b_off + row];
-    v = b - __bfloat162float(__float2bfloat16(b));
-  }
-  Wb[idx] = __float2bfloat16(v);
-}
-
 template <typename T>
 static int sync_weights_t(bn_mlp* h, const float* params, cudaStream_t s) {
   const bn_mlp_cfg& c = h->cfg;
@@ -703,14 +743,13 @@ static int sync_weights_t(bn_mlp* h, const float* params, cudaStream_t s) {
     jobs.j[jobs.n++] = PackJob{c.b_off[h->blk_lin0[b]], h->HH, -1, -1, 1, h->b1cat, 0, nullptr, 0, b * h->HH, kEncPad};
   }
   if (h->bf16) pack(BN_LIN_SIGMA, 1, h->F, -1, h->F, h->WsigA, h->F, nullptr, 0, 0);   // row 0 of the [64, F] density operand
+  if (h->bf16 && h->Wb)
+    jobs.j[jobs.n++] = PackJob{0, h->L, -2, h->E, h->skip, h->Wb, h->F, (void*)h->Wb_offs, 0, 0, kEncPad};
   if (jobs.n > kMaxPackJobs) { set_error("too many pack jobs"); return BN_ERR_STATE; }
   pack_all_kernel<T><<<dim3(64, jobs.n), 256, 0, s>>>(jobs, params);
   if (int rc = after_launch("pack_all_kernel")) return rc;
-  if (h->bf16 && h->Wb) {
-    pack_bias_blocks_kernel<<<ceil_div(h->L * h->F * 64, 256), 256, 0, s>>>(params, (__nv_bfloat16*)h->Wb, h->L, h->F, h->E, h->skip, h->Wb_offs);
-    if (int rc = after_launch("pack_bias_blocks_kernel")) return rc;
-  }
   h->synced = true;
+  h->w2p_flags = -1;                      // the heads' second-layer operands are re-packed by the next heads forward
   return BN_OK;
 }
 
@@ -758,7 +797,8 @@ static int sigma_chain(bn_mlp* h, const float* params, const float* origins, int
 // trunk of a training (or analytic-normal) forward as ONE fused kernel: X3, H_l, C_l of every layer are
 // written for the backward pass, the layer inputs themselves never leave the SM
 static int train_chain(bn_mlp* h, const float* params, const float* origins, int o_stride, const float* dirs, int d_stride,
-                       const float* z, int N, int S, const Ws<__nv_bfloat16>& w, bool keep_c, bool train, cudaStream_t s) {
+                       const float* z, int N, int S, const Ws<__nv_bfloat16>& w, bool keep_c, bool train, float* sigma_out,
+                       cudaStream_t s) {
   const bn_mlp_cfg& c = h->cfg;
   const long long P = (long long)N * S;
   chain::TrainChainParams prm;
@@ -775,8 +815,8 @@ static int train_chain(bn_mlp* h, const float* params, const float* origins, int
   prm.L = h->L; prm.skip = h->skip; prm.n_freq = c.n_freq_xyz;
   prm.store_c = keep_c ? 1 : 0; prm.h_from = train ? 0 : h->L - 1;
   prm.trace = h->chain_trace;
-  prm.c_stg = getenv("BN_CHAIN_CSTG") != nullptr;             // experiment knob, read per launch
-  for (int l = 0; l < h->L; ++l) prm.cptr[l] = keep_c ? w.C[l] : nullptr;
+  prm.wsig = params + c.w_off[BN_LIN_SIGMA]; prm.bsig = params + c.b_off[BN_LIN_SIGMA]; prm.sig_out = chain_sigma_ok(h) ? w.SIGC : nullptr;
+  prm.sig_out2 = prm.sig_out ? sigma_out : nullptr;
   prm.pol_w = tc::pol_weights(); prm.pol_s = tc::pol_stream();
   const int n_blocks = (int)ceil_div_ll(P, 256);
   constexpr int smem = chain::chain_smem<true>();
@@ -812,12 +852,14 @@ static void offset_rows(const bn_mlp* h, Ws<T>* w, long long row0) {
     w->H[l] += row0 * w->Hld[l];
     if (w->C[l]) w->C[l] += row0 * h->F;
   }
+  if (w->SIGC) w->SIGC += row0;
 }
 
 // PE + trunk of N*S points whose activations land in `w` (already offset to the first row of this call)
 template <typename T>
 static int trunk_t(bn_mlp* h, const float* params, const float* origins, int o_stride, const float* dirs, int d_stride,
-                   const float* z, int N, int S, bool keep_c, bool train, const Ws<T>& w, cudaStream_t s) {
+                   const float* z, int N, int S, bool keep_c, bool train, const Ws<T>& w, cudaStream_t s,
+                   float* sigma_out = nullptr) {
   const long long P = (long long)N * S;
   const bn_mlp_cfg& c = h->cfg;
   const int F = h->F, L = h->L;
@@ -827,8 +869,8 @@ static int trunk_t(bn_mlp* h, const float* params, const float* origins, int o_s
     BN_LAUNCH_CHECK();
   }
   if constexpr (std::is_same<T, __nv_bfloat16>::value) {
-    if (h->F == chain::kF && h->skip >= 1 && !h->no_chain)
-      return train_chain(h, params, origins, o_stride, dirs, d_stride, z, N, S, w, keep_c, train, s);
+    if (train_chain_ok(h))
+      return train_chain(h, params, origins, o_stride, dirs, d_stride, z, N, S, w, keep_c, train, sigma_out, s);
   }
   encode_kernel<T><<<(unsigned)ceil_div_ll(P, 128), 128, 0, s>>>(origins, o_stride, dirs, d_stride, z, S, P,
                                                                c.n_freq_xyz, w.X3, w.ldx3);
@@ -883,11 +925,17 @@ static int heads_t(bn_mlp* h, const float* params, long long P, int flags, float
     const int HKa = hp.n_blocks * h->HH;
     const int ldk = h->n_blocks * h->HH;
     pack_heads_fwd_kernel<<<ceil_div(64 * max(HKa, F), 256), 256, 0, s>>>(hp, params, (__nv_bfloat16*)h->W2pT, ldk,
-                                                                          (__nv_bfloat16*)h->Wsig, F);
+                                                                          (__nv_bfloat16*)h->Wsig, F,
+                                                                          train ? (__nv_bfloat16*)h->W2p : nullptr);
     BN_LAUNCH_CHECK();
-    EpiHeadsOut eh{hp, params, out, pitch, (int)P};
+    h->w2p_flags = train ? flags : -1;       // host-side note for the backward of the same flags: W2p is current
+    // the fused trunk kernel already left the density of every row in w.SIGC (fp32 dot product of the last layer's sines):
+    // it goes out with the heads' rows, and the sigma GEMM only remains for the learned normal
+    const float* sig = chain_sigma_ok(h) ? w.SIGC : nullptr;
+    EpiHeadsOut eh{hp, params, out, pitch, (int)P, sig};
     if (int rc = gemm_tn<T>(h, w.HD, w.ldhd, (const T*)h->W2pT, ldk, P, 64, HKa, eh, s, hp.n_out * h->HH / 64)) return rc;
-    EpiSigmaOut es{params + hp.bsig, params + hp.bg, out, pitch, hp.ch_sigma, hp.ch_nlr, (int)P};
+    if (sig && hp.ch_nlr < 0) return BN_OK;
+    EpiSigmaOut es{params + hp.bsig, params + hp.bg, out, pitch, sig ? -1 : hp.ch_sigma, hp.ch_nlr, (int)P};
     return gemm_tn<T>(h, Hl, ldl, (const T*)h->Wsig, F, P, 64, F, es, s, (hp.ch_nlr >= 0 ? 4 : 1) * F / 64);
   } else {
     heads_fwd_kernel<T><<<heads_grid(h, P), 256, 0, s>>>(hp, params, Hl, ldl, F, w.HD, w.ldhd, out, pitch, P, false, false);
@@ -929,8 +977,12 @@ static int trunk_rows_t(bn_mlp* h, const float* params, const float* origins, in
                         void* wsp, cudaStream_t s) {
   Ws<T> w; carve<T>(h, total, flags, wsp, &w);
   offset_rows<T>(h, &w, row0);
-  if (int rc = trunk_t<T>(h, params, origins, o_stride, dirs, d_stride, z, N, S, keep_cos(flags), (flags & BN_MLP_TRAIN) != 0, w, s)) return rc;
-  if (sigma_out) return sigma_rows_t<T>(h, params, w.H[h->L - 1], w.Hld[h->L - 1], (long long)N * S, sigma_out, 1, s);
+  if (int rc = trunk_t<T>(h, params, origins, o_stride, dirs, d_stride, z, N, S, keep_cos(flags), (flags & BN_MLP_TRAIN) != 0, w, s,
+                          sigma_out)) return rc;
+  if (sigma_out) {
+    if (chain_sigma_ok(h) && w.SIGC) return BN_OK;       // the fused trunk kernel wrote it on the way
+    return sigma_rows_t<T>(h, params, w.H[h->L - 1], w.Hld[h->L - 1], (long long)N * S, sigma_out, 1, s);
+  }
   return BN_OK;
 }
 
@@ -1010,8 +1062,11 @@ static int backward_t(bn_mlp* h, const float* params, const float* out, const fl
   }
   if constexpr (kTC) {
     // GHD = (DPRE W2p^T) ⊙ CD, first-layer bias gradients = its column sums
-    pack_w2_kernel<<<ceil_div(HKa * 64, 256), 256, 0, s>>>(hp, params, (__nv_bfloat16*)h->W2p);
-    BN_LAUNCH_CHECK();
+    if (h->w2p_flags != flags) {           // not left behind by the forward of this step (other flags, or weights re-packed since)
+      pack_w2_kernel<<<ceil_div(HKa * 64, 256), 256, 0, s>>>(hp, params, (__nv_bfloat16*)h->W2p);
+      BN_LAUNCH_CHECK();
+      h->w2p_flags = flags;
+    }
     for (int b = 0; b < hp.n_blocks; ++b) {
       DgradArgs<T> a; a.mulc = w.CD + (long long)b * h->HH; a.ldm = w.ldhd;
       if (int rc = layer_dgrad<T>(h, w.DPRE, 64, (const T*)h->W2p + (long long)b * h->HH * 64, 64, P, h->HH, 64, a,
@@ -1363,10 +1418,13 @@ extern "C" __attribute__((visibility("default")))
 int bn_adam_step_graph(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float* state,
                        float beta1, float beta2, float eps, float weight_decay, float grad_scale, cudaStream_t stream) {
   BN_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && state && n > 0, "bad arguments");
-  adam_tick_kernel<<<1, 1, 0, stream>>>(state, beta1, beta2);
-  BN_LAUNCH_CHECK();
-  adam_state_kernel<<<(unsigned)ceil_div_ll(n, 256), 256, 0, stream>>>(params, grads, exp_avg, exp_avg_sq, n, state, beta1, beta2,
-                                                                      eps, weight_decay, grad_scale);
+  BN_CHECK_ARG(((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grads) | reinterpret_cast<uintptr_t>(exp_avg) |
+                 reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15) == 0, "buffers must be 16-byte aligned");
+  const double l1 = log((double)beta1), l2 = log((double)beta2);
+  const float l1h = (float)l1, l2h = (float)l2;
+  adam_state_kernel<<<(unsigned)ceil_div_ll(n, kAdamThreads * kAdamPerThread), kAdamThreads, 0, stream>>>(
+      params, grads, exp_avg, exp_avg_sq, n, state, beta1, beta2, eps, weight_decay, grad_scale, l1h, (float)(l1 - (double)l1h), l2h,
+      (float)(l2 - (double)l2h));
   BN_LAUNCH_CHECK();
   return BN_OK;
 }
@@ -1422,6 +1480,8 @@ int bn_debug_gemm_epi(int kind, const void* A, long long lda, const void* B, lon
 extern "C" __attribute__((visibility("default"))) int bn_debug_chain_trace(bn_mlp* h, long long* device_buf) {
   BN_CHECK_ARG(h != nullptr, "null handle");
   h->chain_trace = device_buf;
+  // BN_NT_TRACE: the weight-gradient GEMM's stamps follow the chain's 512 words (scripts/trace_wgrad.py sizes the buffer)
+  tc::nt_trace() = (device_buf && getenv("BN_NT_TRACE")) ? device_buf + 512 : nullptr;
   return BN_OK;
 }
 

@@ -73,13 +73,14 @@ struct TrainChainParams {
   int h_from;                           // h_l leaves the SM only for l >= h_from (0 when training, L-1 for inference)
   long long* trace;                     // diagnostics (bn_debug_chain_trace): clock64() stamps of pair 0's leader CTA, first block
   uint64_t pol_w, pol_s;                // L2 eviction policies: weight tiles (resident), activation stores (streaming)
-  __nv_bfloat16* cptr[kMaxLayers];      // C_l base pointers (c_stg experiment: direct global stores)
-  int c_stg;                            // 1: cosines leave through st.global instead of staging box + TMA (BN_CHAIN_CSTG)
+  // density of every point from the fp32 sines of the last layer, exactly as the density pass computes it (nullptr: off)
+  const float* wsig; const float* bsig; float* sig_out;
+  float* sig_out2;                      // optional second copy (the caller's own density buffer)
 };
 
 template <bool kTrain> __host__ __device__ constexpr int chain_smem() {
   // activations + weight ring + (cosine boxes | sigma exchange) + barriers + alignment slack
-  return kNKB * kKBBytes + w_stages<kTrain>() * kKBBytes + (kTrain ? 4 * 4096 : 1024) + 512 + 1024;
+  return kNKB * kKBBytes + w_stages<kTrain>() * kKBBytes + (kTrain ? 4 * 4096 + 512 : 1024) + 512 + 1024;
 }
 constexpr int sigma_chain_smem() { return chain_smem<false>(); }
 
@@ -347,7 +348,8 @@ __global__ void __launch_bounds__(kThreads, 1) train_chain_kernel(const __grid_c
   uint8_t* sAct = smem;
   uint8_t* sW = sAct + kNKB * kKBBytes;
   uint8_t* sC = sW + kWStages * kKBBytes;                      // [8 warps][32 rows][64 B] cosine staging boxes
-  uint64_t* wfull = reinterpret_cast<uint64_t*>(sC + kCBytes);
+  float* sSig = reinterpret_cast<float*>(sC + kCBytes);        // [128] partial sigma of the hsel = 1 warps
+  uint64_t* wfull = reinterpret_cast<uint64_t*>(sSig + 128);
   uint64_t* wempty = wfull + kWStages;
   uint64_t* tfull = wempty + kWStages;
   uint64_t* tempty = tfull + 2;
@@ -415,8 +417,10 @@ __global__ void __launch_bounds__(kThreads, 1) train_chain_kernel(const __grid_c
         if (lane == 0) { tma_store_2d_hint(&prm.x3map, sAct + q * 4096, 0, grow0, prm.pol_s); bulk_commit(); }
       }
       arrive_leader(&act_ready[0]);
+      float sig = 0.f;
       for (int l = 0; l < L; ++l) {
         const bool last = l == L - 1;
+        const bool sig_on = last && prm.sig_out != nullptr;
         for (int n = 0; n < 2; ++n) {
           const bool tr = prm.trace != nullptr && blk == pair0 && pair0 == 0 && crank == 0 && warp == 4 && lane == 0;
           if (tr) prm.trace[(l * 2 + n) * 16 + 11] = clock64();   // [11] epilogue starts waiting for the half
@@ -427,7 +431,6 @@ __global__ void __launch_bounds__(kThreads, 1) train_chain_kernel(const __grid_c
           const uint32_t tbase = tmem_base + t_lane + n * 256 + hsel * 32;
           const bool store_h = l >= prm.h_from;
           const bool l0 = l == 0;
-          __nv_bfloat16* const crow = prm.cptr[l] + (long long)(grow0 + lane) * kF + n * 256 + hsel * 32;   // c_stg only
           const bool row_ok = (long long)grow0 + lane < prm.P;
           tmem_ld32_issue(tbase, va);
 #pragma unroll
@@ -454,8 +457,20 @@ __global__ void __launch_bounds__(kThreads, 1) train_chain_kernel(const __grid_c
                 if (prm.store_c) pc[j] = bf_pack(__cosf(a0), __cosf(a1));
               }
             }
+            if (sig_on) {
+              // last layer: density = w_sigma . h from the sines as they are stored (bf16), fp32 weights and accumulation;
+              // unpacking the 16 words costs two ALU operations each, re-evaluating 32 sines would sit on the MUFU pipe
+              // that bounds this epilogue
+              const float2* wp = reinterpret_cast<const float2*>(prm.wsig + n * 256 + u * 64 + hsel * 32);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float2 ws = __ldg(wp + j);
+                sig = fmaf(__uint_as_float(pk[j] << 16), ws.x, sig);
+                sig = fmaf(__uint_as_float(pk[j] & 0xFFFF0000u), ws.y, sig);
+              }
+            }
             uint8_t* box = cbox + (kCBox2 ? (cu & 1) * 2048 : 0);
-            if (prm.store_c && !prm.c_stg) {
+            if (prm.store_c) {
               // cosines: registers -> this warp's staging box -> TMA.  The box was read out by the TMA (with two boxes: the
               // store before the previous one); the leader's wait also covers the h_l boxes of the previous half
               if (lane == 0) { if (kCBox2 && !leader) bulk_wait_read1(); else bulk_wait_read0(); }
@@ -475,18 +490,8 @@ __global__ void __launch_bounds__(kThreads, 1) train_chain_kernel(const __grid_c
               sts128(kbp + row_off + (((hsel * 4 + j) << 4) ^ swz), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
             fence_async_smem();                                  // ONE proxy fence covers both the K block and the cosine box
             if (!last) arrive_leader(&act_ready[1 + 4 * n + u]); else __syncwarp();
-            if (prm.store_c) {
-              if (prm.c_stg) {
-                // experiment (BN_CHAIN_CSTG=1): cosines straight from registers, 64 contiguous bytes per row — no staging box,
-                // no wait for the previous store's read-out, at the price of 128 LSU wavefronts per unit
-                if (row_ok) {
-#pragma unroll
-                  for (int j = 0; j < 4; ++j)
-                    *reinterpret_cast<uint4*>(crow + u * 64 + j * 8) = make_uint4(pc[4 * j], pc[4 * j + 1], pc[4 * j + 2], pc[4 * j + 3]);
-                }
-              } else if (lane == 0) {
-                tma_store_2d_hint(&prm.cmap[l], box, n * 256 + u * 64 + hsel * 32, grow0, prm.pol_s); bulk_commit();
-              }
+            if (prm.store_c && lane == 0) {
+              tma_store_2d_hint(&prm.cmap[l], box, n * 256 + u * 64 + hsel * 32, grow0, prm.pol_s); bulk_commit();
             }
           }
           if (n == 0) kf_ph ^= 1;
@@ -494,12 +499,22 @@ __global__ void __launch_bounds__(kThreads, 1) train_chain_kernel(const __grid_c
           if (store_h) {
             // h_l of this half: both warps of the quadrant have written their columns -> four 64-column boxes straight out
             // of the K blocks (read-only for everyone until the next layer's epilogue of the same half)
+            // (last layer, second half: the same barrier hands the hsel = 1 warp's half of the sigma dot product over;
+            // the next write of sSig[row] is a whole block of these barriers away)
+            const bool sig_now = sig_on && n == 1;
+            if (sig_now && hsel == 1) sSig[row] = sig;
             named_bar_sync(1 + q, 64);
             if (leader) {
 #pragma unroll
               for (int u = 0; u < 4; ++u)
                 tma_store_2d_hint(&prm.hmap[l], sAct + (1 + n * 4 + u) * kKBBytes + q * 4096, n * 256 + u * 64, grow0, prm.pol_s);
               bulk_commit();
+            }
+            if (sig_now && hsel == 0 && row_ok) {
+              const float sv = sig + sSig[row] + __ldg(prm.bsig);
+              const float sp = sv > 20.f ? sv : log1pf(expf(sv));
+              prm.sig_out[p] = sp;
+              if (prm.sig_out2) prm.sig_out2[p] = sp;
             }
           }
         }

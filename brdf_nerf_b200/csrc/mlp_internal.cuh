@@ -73,6 +73,7 @@ struct bn_mlp {
   int blk_lin0[bn::kMaxBlocks], blk_lin2[bn::kMaxBlocks], blk_head[bn::kMaxBlocks];
   bool synced;
   bool no_chain;
+  int w2p_flags;                // flags of the training forward that last packed W2p for the backward (-1: stale)
   bool no_dchain;               // BN_NO_DGRAD_CHAIN=1: per-layer data-gradient GEMMs instead of the fused chain (A/B timing aid)
   // backward: weight gradients run on a side stream next to the data-gradient chain (forked from / joined into the caller's stream)
   cudaStream_t s2; cudaEvent_t ev_dz[16]; cudaEvent_t ev_w[16]; cudaEvent_t ev_h[8]; bool overlap;
@@ -169,11 +170,17 @@ template <typename T> struct Ws {
   T* UBX;          // [P,64+F]: cols 0..63 = adjoint of EE, cols 64.. = ubar_{skip-1}
   T* UBA; T* UBB;  // ubar ping-pong
   T* SG;           // [P,64]: col 0 = sigmoid(s_p), other columns zero (A operand of the w_sigma second-order wgrad)
+  float* SIGC;     // [P] density of every row, written by the fused trunk kernel (tcgen05 mode, full forward)
 };
 
 static inline size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
 
 // the fused data-gradient chain (mlp_dgrad_chain.cuh) is specialised like the forward chain: bf16, 512-wide trunk
+// the fused forward trunk kernel (mlp_chain.cuh): bf16, 512-wide trunk with a skip connection
+static inline bool train_chain_ok(const bn_mlp* h) { return h->bf16 && h->F == 512 && h->skip >= 1 && h->L <= 16 && !h->no_chain; }
+// ... which also leaves the density of every row behind (BN_CHAIN_NO_SIG=1, read per call: the separate sigma GEMMs instead —
+// A/B knob; a forward and the calls that consume its workspace must run under the same setting)
+static inline bool chain_sigma_ok(const bn_mlp* h) { return train_chain_ok(h) && getenv("BN_CHAIN_NO_SIG") == nullptr; }
 static inline bool dgrad_chain_ok(const bn_mlp* h) { return h->bf16 && h->F == 512 && h->L >= 3 && !h->no_chain && !h->no_dchain; }
 
 template <typename T>
@@ -209,6 +216,7 @@ static inline size_t carve(const bn_mlp* h, long long P, int flags, void* base, 
     t.ldfe = h->ldfe;
     t.FE = take(P * t.ldfe);
     t.HD = take(P * t.ldhd);
+    t.SIGC = reinterpret_cast<float*>(take(P * (long long)(sizeof(float) / sizeof(T))));
     if (train) {
       t.CD = take(P * t.ldhd); t.GHD = take(P * t.ldhd);
       t.G7D = take(P * F); t.GFE = take(P * F); t.GA = take(P * F); t.GB = take(P * F);

@@ -128,6 +128,15 @@ def _forward(model, args, rays: torch.Tensor, draws: Optional[Draws], mode: str,
                 u[valid] = torch.rand((int(valid.sum().item()), G), device=dev, dtype=torch.float32)
                 return u
         else:
+            # one generator launch for all the uniforms of the call (the order inside the block is the reference's draw order)
+            widths = [S1] + ([S_sun] if want_sun else []) + [G] + ([G] if use_gt else [])
+            block = torch.rand((N * sum(widths),), device=dev, dtype=torch.float32)
+            chunks, off = [], 0
+            for wd in widths:
+                chunks.append(block[off:off + N * wd].view(N, wd))
+                off += N * wd
+            chunks = iter(chunks)
+            rnd = lambda *sh: next(chunks)
             rndn = lambda *sh: torch.randn(sh, device=dev, dtype=torch.float32) if noise_std != 0.0 else None
             rnd_gt = lambda: rnd(N, G)
         # keyword arguments are evaluated left to right: the order below is the reference's draw order (App. B)

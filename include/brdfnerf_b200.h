@@ -319,7 +319,8 @@ int bn_adam_step(float* params, const float* grads, float* exp_avg, float* exp_a
 
 /* The same update for a CUDA-graph-captured training step: the learning rate and the step counter live in DEVICE memory,
  * state = {lr, step (number of updates done so far, as a float), scratch, scratch}; the call increments step, derives the
- * bias corrections on the device and applies the update, so replaying the captured graph advances the optimizer. */
+ * bias corrections on the device and applies the update, so replaying the captured graph advances the optimizer.  One
+ * launch; the scratch words must be zero when the state is created (a block counter lives there); buffers 16-byte aligned. */
 int bn_adam_step_graph(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                        float* state, float beta1, float beta2, float eps, float weight_decay, float grad_scale,
                        cudaStream_t stream);

@@ -47,17 +47,15 @@ def main():
         sig = torch.empty((n, S), dtype=torch.float32, device=dev)
         fn = lambda: ops.mlp_trunk_forward(m, rays[:, 0:3], 11, rays[:, 3:6], 11, z, flags, n * S, 0, None, ws)
         for rep in range(3):
-            for tag, envs in (("default", {}), ("c via st.global", {"BN_CHAIN_CSTG": "1"}), ("two c boxes", {"BN_CHAIN_CBOX2": "1"}),
-                              ("no L2 hints", {"BN_NO_L2_HINTS": "1"})):
-                for k in ("BN_CHAIN_CSTG", "BN_NO_L2_HINTS"):
+            for tag, envs in (("default", {}), ("two c boxes", {"BN_CHAIN_CBOX2": "1"}), ("no L2 hints", {"BN_NO_L2_HINTS": "1"})):
+                for k in ("BN_NO_L2_HINTS",):
                     os.environ.pop(k, None)
                 if "BN_CHAIN_CBOX2" in envs:
                     continue          # read once per process (static): timed by its own run of this script
                 os.environ.update(envs)
                 us = timeit(fn)
                 print(f"train chain {tag:16s} P={n * S:7d} rep {rep}: {us:8.1f} us  {flops / us / 1e6:7.1f} TFLOP/s", flush=True)
-        for k in ("BN_CHAIN_CSTG", "BN_NO_L2_HINTS"):
-            os.environ.pop(k, None)
+        os.environ.pop("BN_NO_L2_HINTS", None)
         ws1 = m.workspace(n * S, L.MLP_SIGMA_ONLY, tag="ws_sigma")
         fs = lambda: ops.mlp_forward(m, rays[:, 0:3], 11, rays[:, 3:6], 11, z, L.MLP_SIGMA_ONLY, sig, 1, ws1)
         us = timeit(fs)
