@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(384, 1) mma_rate_kernel(int n_kblocks, int N, 
   if (kPair) cluster_sync_all();
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  if (warp == 1 && lane == 0 && crank == 0) {
+  if (warp == 1 && lane == 0 && crank == 0 && !(variant & 4)) {
     const uint32_t idesc = make_idesc(kPair ? 256 : 128, N, mn_major != 0);
     int stage = 0; uint32_t phase = 0;
     const long long t0 = clock64();
@@ -57,8 +57,10 @@ __global__ void __launch_bounds__(384, 1) mma_rate_kernel(int n_kblocks, int N, 
       for (int k = 0; k < 4; ++k) {
         const uint64_t da = mn_major ? make_desc(a_addr + k * 2048, 8192, 1024) : make_desc(a_addr + k * 32, 16, 1024);
         const uint64_t db = mn_major ? make_desc(b_addr + k * 2048, 8192, 1024) : make_desc(b_addr + k * 32, 16, 1024);
-        if constexpr (kPair) umma_bf16_pair(tmem_base, da, db, idesc, (kb | k) ? 1u : 0u);
-        else umma_bf16(tmem_base, da, db, idesc, (kb | k) ? 1u : 0u);
+        const uint32_t d = tmem_base + ((variant & 8) ? (k & 1) * 256 : 0);      // bit 3: ONE thread, two accumulators in turn
+        const uint32_t acc = (variant & 8) ? ((kb | (k >> 1)) ? 1u : 0u) : ((kb | k) ? 1u : 0u);
+        if constexpr (kPair) umma_bf16_pair(d, da, db, idesc, acc);
+        else umma_bf16(d, da, db, idesc, acc);
       }
       if constexpr (kPair) umma_commit_pair(&bars[stage]); else umma_commit(&bars[stage]);
       if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -68,6 +70,31 @@ __global__ void __launch_bounds__(384, 1) mma_rate_kernel(int n_kblocks, int N, 
     mbar_wait(&bars[kStages], 0);                         // ... and retired
     const long long t2 = clock64();
     if (blockIdx.x == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+  } else if ((variant & 4) && (warp == 0 || warp == 3) && lane == 0 && crank == 0) {
+    // variant bit 2: TWO issuing threads, each with half of the K blocks, its own two ring slots and its own accumulator
+    // (columns 0..255 / 256..511): does the floor belong to the issuing thread or to the tensor pipe?
+    const int w = warp == 0 ? 0 : 1;
+    const uint32_t idesc = make_idesc(kPair ? 256 : 128, N, mn_major != 0);
+    const long long t0 = clock64();
+    for (int j = 0; j < n_kblocks / 2; ++j) {
+      const int stage = w * 2 + (j & 1);
+      if (j >= 2) mbar_wait(&bars[stage], ((j >> 1) & 1) ^ 1);
+      const uint32_t a_addr = smem_u32(smem + stage * kStageBytes), b_addr = a_addr + 16384;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint64_t da = mn_major ? make_desc(a_addr + k * 2048, 8192, 1024) : make_desc(a_addr + k * 32, 16, 1024);
+        const uint64_t db = mn_major ? make_desc(b_addr + k * 2048, 8192, 1024) : make_desc(b_addr + k * 32, 16, 1024);
+        const uint32_t d = tmem_base + ((variant & 16) ? 0 : w * 256);           // bit 4: both threads into the SAME accumulator
+        if constexpr (kPair) umma_bf16_pair(d, da, db, idesc, (j | k) ? 1u : 0u);
+        else umma_bf16(d, da, db, idesc, (j | k) ? 1u : 0u);
+      }
+      if constexpr (kPair) umma_commit_pair(&bars[stage]); else umma_commit(&bars[stage]);
+    }
+    const long long t1 = clock64();
+    if constexpr (kPair) umma_commit_pair(&fullb[w]); else umma_commit(&fullb[w]);
+    mbar_wait(&fullb[w], 0);
+    const long long t2 = clock64();
+    if (blockIdx.x == 0 && w == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
   } else if (warp == 0 && lane == 0 && (variant & 2)) {
     // the real kernels' producer: waits for the slot to be free, then (leader only) completes the slot's "full" phase
     int stage = 0; uint32_t phase = 0;
@@ -99,7 +126,7 @@ static void run(const char* name, int n_sm, int N, int mn_major, int wait_slots,
   auto kern = mma_rate_kernel<kPair>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(kPair ? n_sm / 2 * 2 : n_sm); cfg.blockDim = dim3(waiters ? 384 : 128); cfg.dynamicSmemBytes = smem;
+  cfg.gridDim = dim3(kPair ? n_sm / 2 * 2 : n_sm); cfg.blockDim = dim3(waiters ? 384 : 128); cfg.dynamicSmemBytes = smem;   // warps 0..3 always exist
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kPair ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -138,6 +165,13 @@ int main() {
   run<true>("pair, RANDOM operands, ONE pair alone", 2, 256, 1, 1, 0, 1);
   run<false>("single CTA, RANDOM operands", n_sm, 256, 1, 1, 0, 1);
   run<true>("pair, RANDOM operands, N = 128", n_sm, 128, 1, 1, 0, 1);
+  run<true>("pair, random, TWO issuer threads / accumulators", n_sm, 256, 1, 1, 0, 1, 4);
+  run<true>("pair, random, TWO issuers, N = 128", n_sm, 128, 1, 1, 0, 1, 4);
+  run<true>("pair, random, ONE issuer, two accumulators in turn", n_sm, 256, 1, 1, 0, 1, 8);
+  run<true>("pair, random, ONE issuer, two accumulators, K-major", n_sm, 256, 0, 1, 0, 1, 8);
+  run<true>("pair, random, ONE issuer, two accumulators, N = 128", n_sm, 128, 1, 1, 0, 1, 8);
+  run<true>("pair, random, TWO issuers, SAME accumulator", n_sm, 256, 1, 1, 0, 1, 20);
+  run<false>("single CTA, random, TWO issuers", n_sm, 256, 1, 1, 0, 1, 4);
   run<true>("pair, random, fence::after_thread_sync per K block", n_sm, 256, 1, 1, 0, 1, 1);
   run<true>("pair, random, producer relay (empty -> full)", n_sm, 256, 1, 1, 0, 1, 2);
   run<true>("pair, random, relay + fence", n_sm, 256, 1, 1, 0, 1, 3);
