@@ -49,11 +49,13 @@ _SIGS = {
     "bn_sample_stratified": (C.c_int, [_P, _P, _I, _P, _P, _P, _I, _I, _P]),
     "bn_sample_guided": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _F, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _P]),
     "bn_merge_samples": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "bn_coarse_to_fine": (C.c_int, [_P, _P, _P, _F, _P, _P, _P, _P, _P, _F, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                                    _I, _I, _I, _P]),
     "bn_sort_rows": (C.c_int, [_P, _P, _I, _I, _P]),
     "bn_permute_samples": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "bn_composite_sigma": (C.c_int, [_P, _P, _P, _F, _P, _P, _P, _P, _P, _I, _I, _P]),
-    "bn_composite_forward": (C.c_int, [_P, _P, _I, _I, _P, _F, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
-    "bn_composite_backward": (C.c_int, [_P, _P, _I, _I, _P, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
+    "bn_composite_forward": (C.c_int, [_P, _P, _I, _I, _P, _F, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _I, _P]),
+    "bn_composite_backward": (C.c_int, [_P, _P, _I, _I, _P, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _I, _P]),
     "bn_shade_rays_forward": (C.c_int, [C.POINTER(ShadeCfg), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
     "bn_shade_rays_backward": (C.c_int, [C.POINTER(ShadeCfg), _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
     "bn_brdf_points_forward": (C.c_int, [C.POINTER(ShadeCfg), _P, _P, _P, _I, _I, _P]),

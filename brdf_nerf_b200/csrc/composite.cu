@@ -15,49 +15,12 @@
 // HBM traffic (algorithmic, fp32): fwd reads z + packed (+noise when noise_std != 0), writes
 // alpha, T, w; bwd re-reads z, packed, alpha, T, w and writes d_packed.
 #include "common.cuh"
+#include "composite_ray.cuh"
 
 namespace bn {
 
 constexpr int kRaysPerBlock = 4;
 constexpr int kMaxSamples = 512;
-
-struct CompositeFwd {
-  const float* z;        // (N,S)
-  const float* packed;   // (N,S,C)  channel `sigma_ch` is the density
-  const float* noise;    // (N,S) or null
-  const float* irr;      // (N,S) or null : per-sample irradiance scalar (sun visibility)
-  float noise_std;
-  float *alpha, *trans, *weights;          // (N,S) each, alpha/trans nullable
-  float *depth, *wsum, *std;               // (N) each, wsum/std nullable
-  float *acc;                              // (N,C)  Σ w·x  (entry sigma_ch holds Σ w·sigma, unused)
-  float *acc_irr;                          // (N,4)  Σ w·irr·[x0,x1,x2,1]  (only when irr != null)
-  int N, S, sigma_ch;
-};
-
-template <int C>
-__device__ __forceinline__ void load_row(const float* __restrict__ p, float (&x)[C]) {
-  if constexpr (C % 4 == 0) {
-#pragma unroll
-    for (int v = 0; v < C / 4; ++v) {
-      float4 q = __ldg(reinterpret_cast<const float4*>(p) + v);
-      x[4 * v] = q.x; x[4 * v + 1] = q.y; x[4 * v + 2] = q.z; x[4 * v + 3] = q.w;
-    }
-  } else {
-#pragma unroll
-    for (int c = 0; c < C; ++c) x[c] = __ldg(p + c);
-  }
-}
-template <int C>
-__device__ __forceinline__ void store_row(float* __restrict__ p, const float (&x)[C]) {
-  if constexpr (C % 4 == 0) {
-#pragma unroll
-    for (int v = 0; v < C / 4; ++v)
-      reinterpret_cast<float4*>(p)[v] = make_float4(x[4 * v], x[4 * v + 1], x[4 * v + 2], x[4 * v + 3]);
-  } else {
-#pragma unroll
-    for (int c = 0; c < C; ++c) p[c] = x[c];
-  }
-}
 
 // Narrow rows (Lambertian: C = 4, density pass: C = 1) at the path's standard ray length S = 128: the whole ray is loaded
 // up front — four 32-sample rows x (z + C channels) per lane, 2.6 KB in flight per warp — and then composited out of
@@ -77,7 +40,7 @@ __global__ void __launch_bounds__(kRaysPerBlock * kWarp) composite_fwd128_kernel
   for (int k = 0; k < R; ++k) {
     const int i = k * kWarp + lane;
     z[k] = __ldg(a.z + base + i);
-    load_row<C>(a.packed + (base + i) * C, x[k]);
+    load_row<C>(a.packed + packed_row(a.sort_idx, a.N, S, a.S1, r, i) * C, x[k]);
     nz[k] = a.noise ? __ldg(a.noise + base + i) : 0.f;
     ir[k] = 0.f;
     if constexpr (C > 1) { if (a.irr) ir[k] = __ldg(a.irr + base + i); }
@@ -141,101 +104,13 @@ __global__ void __launch_bounds__(kRaysPerBlock * kWarp) composite_fwd128_kernel
   }
 }
 
-// C == 1 is the sigma-only pass (packed == sigma, nothing but depth accumulated).
+// generic ray length: composite_ray (composite_ray.cuh), one warp per ray
 template <int C>
 __global__ void __launch_bounds__(kRaysPerBlock * kWarp) composite_fwd_kernel(CompositeFwd a) {
   const int lane = threadIdx.x % kWarp;
   const int r = blockIdx.x * kRaysPerBlock + threadIdx.x / kWarp;
   if (r >= a.N) return;
-  const int S = a.S;
-  const long long base = (long long)r * S;
-  float acc[C];
-#pragma unroll
-  for (int c = 0; c < C; ++c) acc[c] = 0.f;
-  float acc_i[4] = {0.f, 0.f, 0.f, 0.f};
-  constexpr int kSig = (C == 1) ? 0 : 3;      // density channel of the packed row (spsbrdfnerf.py:694)
-  float depth = 0.f, wsum = 0.f;
-  float carry = 1.0f;                         // transmittance in front of the current 32-sample row
-  // software pipeline: the loads of 32-sample row k+1 are in flight while row k goes through exp / scan / accumulate
-  // (one row per iteration left a warp with ~640 B outstanding: 61 % of the HBM roofline at 65 536 rays)
-  float zn = 0.f, nzn = 0.f, irn = 0.f;
-  float xn[C];
-#pragma unroll
-  for (int c = 0; c < C; ++c) xn[c] = 0.f;
-  auto fetch = [&](int i) {
-    if (i < S) {
-      zn = __ldg(a.z + base + i);
-      load_row<C>(a.packed + (base + i) * C, xn);
-      if (a.noise) nzn = __ldg(a.noise + base + i);
-      if constexpr (C > 1) { if (a.irr) irn = __ldg(a.irr + base + i); }
-    } else {
-      zn = 0.f; nzn = 0.f; irn = 0.f;
-#pragma unroll
-      for (int c = 0; c < C; ++c) xn[c] = 0.f;
-    }
-  };
-  fetch(lane);
-  for (int i0 = 0; i0 < S; i0 += kWarp) {
-    const int i = i0 + lane;
-    const bool ok = i < S;
-    const float zi = zn, nz = nzn, ir = irn;
-    float x[C];
-#pragma unroll
-    for (int c = 0; c < C; ++c) x[c] = xn[c];
-    fetch(i + kWarp);                                          // next row (zeros past the end)
-    float znext = __shfl_down_sync(kFull, zi, 1);
-    const float zfirst_next = __shfl_sync(kFull, zn, 0);       // z of the next row's first sample, for lane 31
-    if (lane == kWarp - 1) znext = zfirst_next;
-    float sg = x[kSig];
-    if (a.noise) sg += nz * a.noise_std;
-    const float delta = (i + 1 < S) ? (znext - zi) : 1e10f;
-    // accurate expf: alpha feeds the guided sampler through the weights
-    const float al = ok ? 1.0f - expf(-delta * fmaxf(sg, 0.f)) : 0.f;
-    const float f = 1.0f - al + 1e-10f;
-    float incl = warp_scan_mul(ok ? f : 1.0f, lane);
-    float excl = __shfl_up_sync(kFull, incl, 1);
-    if (lane == 0) excl = 1.0f;
-    const float T = carry * excl;
-    const float w = al * T;
-    carry *= __shfl_sync(kFull, incl, kWarp - 1);
-    if (ok) {
-      if (a.alpha) a.alpha[base + i] = al;
-      if (a.trans) a.trans[base + i] = T;
-      a.weights[base + i] = w;
-      depth += w * zi; wsum += w;
-      if constexpr (C > 1) {
-#pragma unroll
-        for (int c = 0; c < C; ++c) acc[c] += w * x[c];
-        if (a.irr) {
-          float wi = w * ir;
-          acc_i[0] += wi * x[0]; acc_i[1] += wi * x[1]; acc_i[2] += wi * x[2]; acc_i[3] += wi;
-        }
-      }
-    }
-  }
-  depth = warp_sum(depth); wsum = warp_sum(wsum);
-  if (a.std) {
-    // Σ w (z-d)² evaluated in the numerically safe two-pass form
-    __syncwarp();
-    float s2 = 0.f;
-    for (int i = lane; i < S; i += kWarp) { float dz = a.z[base + i] - depth; s2 += dz * dz * a.weights[base + i]; }
-    s2 = warp_sum(s2);
-    if (lane == 0) a.std[r] = sqrtf(s2);
-  }
-  if constexpr (C > 1) {
-#pragma unroll
-    for (int c = 0; c < C; ++c) acc[c] = warp_sum(acc[c]);
-    if (a.irr) { for (int c = 0; c < 4; ++c) acc_i[c] = warp_sum(acc_i[c]); }
-  }
-  if (lane == 0) {
-    a.depth[r] = depth;
-    if (a.wsum) a.wsum[r] = wsum;
-    if constexpr (C > 1) {
-#pragma unroll
-      for (int c = 0; c < C; ++c) a.acc[(long long)r * C + c] = acc[c];
-      if (a.irr && a.acc_irr) { for (int c = 0; c < 4; ++c) a.acc_irr[r * 4 + c] = acc_i[c]; }
-    }
-  }
+  composite_ray<C>(a, r, lane);
 }
 
 struct CompositeBwd {
@@ -249,6 +124,7 @@ struct CompositeBwd {
   const float *g_packed_direct;            // (N,S,C) nullable: explicit grad wrt per-sample channels
   float* g_packed;                         // (N,S,C) out
   int N, S, sigma_ch;
+  const long long* sort_idx; int S1;       // optional, as in CompositeFwd: packed AND g_packed are in the MLP's row order
 };
 
 template <int C>
@@ -276,8 +152,9 @@ __global__ void __launch_bounds__(kRaysPerBlock * kWarp) composite_bwd_kernel(Co
 #pragma unroll
     for (int c = 0; c < C; ++c) x[c] = 0.f;
     float zi = 0.f, al = 0.f, T = 0.f, w = 0.f, znext = 0.f, irr = 0.f;
+    const long long prow = ok ? packed_row(a.sort_idx, a.N, S, a.S1, r, i) : 0;
     if (ok) {
-      load_row<C>(a.packed + (base + i) * C, x);
+      load_row<C>(a.packed + prow * C, x);
       zi = a.z[base + i]; al = a.alpha[base + i]; T = a.trans[base + i]; w = a.weights[base + i];
       znext = (i + 1 < S) ? a.z[base + i + 1] : 0.f;
       if (a.irr) irr = a.irr[base + i];
@@ -313,7 +190,7 @@ __global__ void __launch_bounds__(kRaysPerBlock * kWarp) composite_bwd_kernel(Co
 #pragma unroll
         for (int c = 0; c < C; ++c) out[c] += e[c];
       }
-      store_row<C>(a.g_packed + (base + i) * C, out);
+      store_row<C>(a.g_packed + prow * C, out);
     }
   }
 }
@@ -369,8 +246,9 @@ extern "C" __attribute__((visibility("default"))) int bn_composite_forward(const
                                     const float* noise, float noise_std, const float* irr,
                                     float* alpha, float* trans, float* weights,
                                     float* depth, float* wsum, float* acc, float* acc_irr,
-                                    int n_rays, int n_samples, cudaStream_t stream) {
+                                    int n_rays, int n_samples, const int64_t* sort_idx, int n_stratified, cudaStream_t stream) {
   BN_CHECK_ARG(z && packed && alpha && trans && weights && depth && acc, "null pointer");
+  BN_CHECK_ARG(!sort_idx || (n_stratified >= 0 && n_stratified <= n_samples), "n_stratified out of range");
   BN_CHECK_ARG(n_samples >= 1 && n_samples <= kMaxSamples, "n_samples out of range");
   BN_CHECK_ARG(sigma_channel == 3, "the packed row keeps the density in channel 3 (reference layout)");
   BN_CHECK_ARG(!irr || acc_irr, "irr given without acc_irr");
@@ -379,6 +257,7 @@ extern "C" __attribute__((visibility("default"))) int bn_composite_forward(const
   a.z = z; a.packed = packed; a.noise = (noise && noise_std != 0.f) ? noise : nullptr; a.noise_std = noise_std;
   a.irr = irr; a.alpha = alpha; a.trans = trans; a.weights = weights; a.depth = depth; a.wsum = wsum;
   a.acc = acc; a.acc_irr = acc_irr; a.N = n_rays; a.S = n_samples; a.sigma_ch = sigma_channel;
+  a.sort_idx = (const long long*)sort_idx; a.S1 = n_stratified;
   return dispatch_fwd(n_channels, a, stream);
 }
 
@@ -387,8 +266,10 @@ extern "C" __attribute__((visibility("default"))) int bn_composite_backward(cons
                                      const float* alpha, const float* trans, const float* weights,
                                      const float* g_acc, const float* g_acc_irr, const float* g_depth,
                                      const float* g_wsum, const float* g_weights, const float* g_packed_direct,
-                                     float* g_packed, int n_rays, int n_samples, cudaStream_t stream) {
+                                     float* g_packed, int n_rays, int n_samples, const int64_t* sort_idx, int n_stratified,
+                                     cudaStream_t stream) {
   BN_CHECK_ARG(z && packed && alpha && trans && weights && g_acc && g_packed, "null pointer");
+  BN_CHECK_ARG(!sort_idx || (n_stratified >= 0 && n_stratified <= n_samples), "n_stratified out of range");
   BN_CHECK_ARG(n_samples >= 1 && n_samples <= kMaxSamples, "n_samples out of range");
   BN_CHECK_ARG(sigma_channel == 3, "the packed row keeps the density in channel 3 (reference layout)");
   if (n_rays <= 0) return n_rays == 0 ? BN_OK : BN_ERR_ARG;
@@ -398,5 +279,6 @@ extern "C" __attribute__((visibility("default"))) int bn_composite_backward(cons
   a.g_acc = g_acc; a.g_acc_irr = g_acc_irr; a.g_depth = g_depth; a.g_wsum = g_wsum;
   a.g_weights = g_weights; a.g_packed_direct = g_packed_direct; a.g_packed = g_packed;
   a.N = n_rays; a.S = n_samples; a.sigma_ch = sigma_channel;
+  a.sort_idx = (const long long*)sort_idx; a.S1 = n_stratified;
   return dispatch_bwd(n_channels, a, stream);
 }

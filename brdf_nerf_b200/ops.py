@@ -79,6 +79,28 @@ def sort_rows(x):
     return out
 
 
+def coarse_to_fine(z1, sigma1, noise1, noise_std, t_g, gauss_g, u_pred, near0, far0, d_range, valid_depth=None, gt_depth=None,
+                   gt_depth_stride=1, gt_std=None, u_gt=None, want_std=False):
+    """composite_sigma + sample_guided + merge_samples in one launch (bn_coarse_to_fine); same results, bit for bit."""
+    n, s1 = z1.shape
+    g = u_pred.shape[1]
+    dev = z1.device
+    w1 = torch.empty_like(z1)
+    depth1 = torch.empty(n, dtype=torch.float32, device=dev)
+    std1 = torch.empty(n, dtype=torch.float32, device=dev) if want_std else None
+    z2 = torch.empty((n, g), dtype=torch.float32, device=dev)
+    z = torch.empty((n, s1 + g), dtype=torch.float32, device=dev)
+    idx = torch.empty((n, s1 + g), dtype=torch.int64, device=dev)
+    unsort = torch.empty((n, s1 + g), dtype=torch.float32, device=dev)
+    L.check(L.load().bn_coarse_to_fine(
+        L.ptr(z1), L.ptr(sigma1), L.ptr(noise1), float(noise_std), L.ptr(t_g), L.ptr(gauss_g), L.ptr(u_pred),
+        C.c_void_p(near0.data_ptr()), C.c_void_p(far0.data_ptr()), float(d_range), L.ptr(valid_depth, torch.int64),
+        None if gt_depth is None else C.c_void_p(gt_depth.data_ptr()), int(gt_depth_stride), L.ptr(gt_std), L.ptr(u_gt),
+        L.ptr(w1), L.ptr(depth1), L.ptr(std1), L.ptr(z2), L.ptr(z), L.ptr(idx, torch.int64), L.ptr(unsort), n, s1, g,
+        L.stream_ptr()))
+    return w1, depth1, std1, z2, z, idx, unsort
+
+
 def composite_sigma(z, sigma, noise, noise_std, want_all=False, want_std=False):
     n, s = z.shape
     dev = z.device
@@ -92,8 +114,10 @@ def composite_sigma(z, sigma, noise, noise_std, want_all=False, want_std=False):
     return alpha, trans, w, depth, std
 
 
-def composite_forward(z, packed, noise, noise_std, irr=None):
-    n, s, c = packed.shape
+def composite_forward(z, packed, noise, noise_std, irr=None, sort_idx=None, n_stratified=0):
+    """`sort_idx` (N,S) int64: `packed` is the MLP's [N*S, C] rows in generation order and is gathered through the index."""
+    n, s = z.shape
+    c = packed.shape[-1]
     dev = z.device
     alpha, trans, w = torch.empty_like(z), torch.empty_like(z), torch.empty_like(z)
     depth = torch.empty(n, dtype=torch.float32, device=dev)
@@ -102,18 +126,21 @@ def composite_forward(z, packed, noise, noise_std, irr=None):
     acc_irr = torch.empty((n, 4), dtype=torch.float32, device=dev) if irr is not None else None
     L.check(L.load().bn_composite_forward(L.ptr(z), L.ptr(packed), c, 3, L.ptr(noise), float(noise_std), L.ptr(irr),
                                           L.ptr(alpha), L.ptr(trans), L.ptr(w), L.ptr(depth), L.ptr(wsum), L.ptr(acc),
-                                          L.ptr(acc_irr), n, s, L.stream_ptr()))
+                                          L.ptr(acc_irr), n, s, L.ptr(sort_idx, torch.int64), int(n_stratified),
+                                          L.stream_ptr()))
     return alpha, trans, w, depth, wsum, acc, acc_irr
 
 
 def composite_backward(z, packed, noise, noise_std, irr, alpha, trans, w, g_acc, g_acc_irr, g_depth, g_wsum,
-                       g_weights, g_packed_direct):
-    n, s, c = packed.shape
+                       g_weights, g_packed_direct, sort_idx=None, n_stratified=0):
+    """With `sort_idx`, `packed` and the returned gradient are [N*S, C] rows in the MLP's generation order."""
+    n, s = z.shape
+    c = packed.shape[-1]
     g_packed = torch.empty_like(packed)
     L.check(L.load().bn_composite_backward(
         L.ptr(z), L.ptr(packed), c, 3, L.ptr(noise), float(noise_std), L.ptr(irr), L.ptr(alpha), L.ptr(trans), L.ptr(w),
         L.ptr(g_acc), L.ptr(g_acc_irr), L.ptr(g_depth), L.ptr(g_wsum), L.ptr(g_weights), L.ptr(g_packed_direct),
-        L.ptr(g_packed), n, s, L.stream_ptr()))
+        L.ptr(g_packed), n, s, L.ptr(sort_idx, torch.int64), int(n_stratified), L.stream_ptr()))
     return g_packed
 
 

@@ -59,6 +59,7 @@ class _State:
     packed_rows: Optional[torch.Tensor] = None      # MLP row order when the trunk is shared between the passes
     idx: Optional[torch.Tensor] = None
     s1: int = 0
+    lazy: bool = False                              # packed was never materialised: compositing works on packed_rows through idx
     noise: Optional[torch.Tensor] = None
     noise_std: float = 0.0
     irr: Optional[torch.Tensor] = None
@@ -88,8 +89,11 @@ def _call_brdf_type(model, args, apply_brdf: bool) -> int:
 def _forward(model, args, rays: torch.Tensor, draws: Optional[Draws], mode: str, valid_depth, target_depths,
              target_std, apply_brdf: bool, bTestNormal: bool, bTestSun_v: bool, gsam_only: bool, apply_theta: bool,
              cos_irra_on: bool, train: bool, debug_nan: bool = False, own_ws: bool = False, sync: bool = True,
-             reference_rng: bool = False, rays_t: Optional[torch.Tensor] = None):
-    """`own_ws`: the MLP workspace is allocated for this call and owned by the returned state (autograd bridge: several
+             reference_rng: bool = False, rays_t: Optional[torch.Tensor] = None, lazy_packed: bool = False):
+    """`lazy_packed` (Trainer, plain Lambertian stage): nobody reads the depth-ordered per-sample rows, so they are never
+    materialised — compositing gathers the MLP's rows through sort_idx and its backward scatters the gradients the same way
+    (no bn_permute_samples launch in either direction); `outs["packed"]` is None then.
+    `own_ws`: the MLP workspace is allocated for this call and owned by the returned state (autograd bridge: several
     forwards may be alive before their backwards run); otherwise the model's cached per-tag buffer is reused.
     `sync=False`: the caller (Trainer) has refreshed the packed weight copies itself.
     `reference_rng`: draw from torch's generator exactly like the reference does: the sigma-noise
@@ -171,7 +175,31 @@ def _forward(model, args, rays: torch.Tensor, draws: Optional[Draws], mode: str,
         ws1 = model.workspace(N * max(S1, S_sun), L.MLP_SIGMA_ONLY, tag="ws_sigma")
     if not share_trunk:
         ops.mlp_forward(model, origins, 11, dirs, 11, z1, L.MLP_SIGMA_ONLY, sigma1, 1, ws1)
-    _, _, w1, depth1, _ = ops.composite_sigma(z1, sigma1, draws.noise1, noise_std)
+    # ---- ground-truth depth override of the guided samples (GenerateGuidedSamples, rendering.py:132-147)
+    gt_depth = gt_std = vd = None
+    gt_stride = 1
+    if use_gt:
+        vd = valid_depth.to(device=dev, dtype=torch.int64).contiguous()
+        td = target_depths.to(device=dev, dtype=torch.float32).contiguous()
+        gt_depth, gt_stride = td, td.shape[1] if td.dim() == 2 else 1
+        gt_std = target_std.to(device=dev, dtype=torch.float32).contiguous()
+    guided_kw = dict(valid_depth=vd, gt_depth=gt_depth, gt_depth_stride=gt_stride, gt_std=gt_std,
+                     u_gt=draws.u_gt if use_gt else None, want_std=debug_nan)
+    # compositing of the stratified densities, guided samples around the predicted (or ground-truth) depth, merge: one launch
+    # (bn_coarse_to_fine) unless only the guided samples are kept (gsam_only: a plain sort instead of the merge)
+    std1 = None
+    if not gsam_only:
+        w1, depth1, std1, z2, z, idx, z_unsort = ops.coarse_to_fine(z1, sigma1, draws.noise1, noise_std, t_g, gauss_g, draws.u_pred,
+                                                                    rays[0:1, 6], rays[0:1, 7], d_range, **guided_kw)
+    else:
+        _, _, w1, depth1, _ = ops.composite_sigma(z1, sigma1, draws.noise1, noise_std)
+        z2 = ops.sample_guided(z1, depth1, w1, t_g, gauss_g, draws.u_pred, rays[0:1, 6], rays[0:1, 7], d_range, **guided_kw)
+        if debug_nan:
+            z2, std1 = z2
+        z, idx, z_unsort = z2, None, z2
+    nan_counts = None
+    if debug_nan:       # check_nan(pred_depth / pred_weight / sampling_std) of rendering.py:121-123, counted on the device
+        nan_counts = (ops.count_nan([depth1, w1, std1]), (depth1.numel(), w1.numel(), std1.numel()))
 
     # ---- optional sun-visibility march from the predicted surface (rendering.py:244-259)
     sun_res = {}
@@ -187,26 +215,6 @@ def _forward(model, args, rays: torch.Tensor, draws: Optional[Draws], mode: str,
         ops.mlp_forward(model, surf, 3, sun_c, 3, z_sun, L.MLP_SIGMA_ONLY, sig_sun, 1, ws1)
         _, T_sun, w_sun, _, _ = ops.composite_sigma(z_sun, sig_sun, draws.noise_sun, noise_std, want_all=True)
         sun_res = {"sun": T_sun.unsqueeze(-1), "weights_sc": w_sun}
-
-    # ---- guided samples around the predicted (or ground-truth) depth, then merge
-    gt_depth = gt_std = vd = None
-    gt_stride = 1
-    if use_gt:
-        vd = valid_depth.to(device=dev, dtype=torch.int64).contiguous()
-        td = target_depths.to(device=dev, dtype=torch.float32).contiguous()
-        gt_depth, gt_stride = td, td.shape[1] if td.dim() == 2 else 1
-        gt_std = target_std.to(device=dev, dtype=torch.float32).contiguous()
-    z2 = ops.sample_guided(z1, depth1, w1, t_g, gauss_g, draws.u_pred, rays[0:1, 6], rays[0:1, 7], d_range,
-                           valid_depth=vd, gt_depth=gt_depth, gt_depth_stride=gt_stride, gt_std=gt_std,
-                           u_gt=draws.u_gt if use_gt else None, want_std=debug_nan)
-    nan_counts = None
-    if debug_nan:       # check_nan(pred_depth / pred_weight / sampling_std) of rendering.py:121-123, counted on the device
-        z2, std1 = z2
-        nan_counts = (ops.count_nan([depth1, w1, std1]), (depth1.numel(), w1.numel(), std1.numel()))
-    if gsam_only:
-        z, idx, z_unsort = z2, None, z2
-    else:
-        z, idx, z_unsort = ops.merge_samples(z1, z2)
 
     # ---- pass 2: full model
     C = model.out_channels(flags)
@@ -235,8 +243,10 @@ def _forward(model, args, rays: torch.Tensor, draws: Optional[Draws], mode: str,
         ops.mlp_heads_forward(model, N * S, flags, packed_rows, pitch, ws)
         if nr_an:
             ops.mlp_normals_forward(model, packed_rows, pitch, N, S, flags, ws)
-        packed = ops.permute_samples(packed_rows, idx, N, S1, G, pitch, scatter=False)
+        lazy = lazy_packed and not has_normal and not multi and not has_beta and brdf_type == L.BN_BRDF_NONE
+        packed = None if lazy else ops.permute_samples(packed_rows, idx, N, S1, G, pitch, scatter=False)
     else:
+        lazy = False
         packed = torch.empty((N, S, pitch), dtype=torch.float32, device=dev)
         ws = model.workspace(N * S, flags, tag=None if own_ws else ("ws_train" if train else "ws_full"))
         if has_beta:
@@ -281,12 +291,16 @@ def _forward(model, args, rays: torch.Tensor, draws: Optional[Draws], mode: str,
     aux_pts = None
     if multi:
         aux_pts = ops.brdf_points_forward(cfg, rays, packed, want_aux=not train)
-    alpha, trans, w, depth, wsum, acc, acc_irr = ops.composite_forward(z, packed, draws.noise2, noise_std, irr)
+    if lazy:
+        alpha, trans, w, depth, wsum, acc, acc_irr = ops.composite_forward(z, packed_rows, draws.noise2, noise_std, irr,
+                                                                           sort_idx=idx, n_stratified=S1)
+    else:
+        alpha, trans, w, depth, wsum, acc, acc_irr = ops.composite_forward(z, packed, draws.noise2, noise_std, irr)
     sh = ops.shade_rays_forward(cfg, rays, acc, wsum, acc_irr, irr_last, want_normal=has_normal,
                                 want_brdf=brdf_type != L.BN_BRDF_NONE and not multi)
 
     st = _State(n=N, s=S, pitch=pitch, flags=flags, cfg=cfg, rays=rays, z=z, packed=packed, packed_rows=packed_rows,
-                idx=idx, s1=S1,
+                idx=idx, s1=S1, lazy=lazy,
                 noise=draws.noise2 if noise_std != 0.0 else None, noise_std=noise_std, irr=irr, irr_last=irr_last,
                 alpha=alpha, trans=trans, weights=w, wsum=wsum, acc=acc, acc_irr=acc_irr, ws=ws, multi=multi,
                 normal_an=nr_an)
@@ -304,6 +318,15 @@ def _backward(model, st: _State, g_rgb, g_depth, g_weights, g_packed, g_params: 
         g_rgb = torch.zeros((st.n, 3), dtype=torch.float32, device=dev)
     g_acc, g_wsum, g_acc_irr = ops.shade_rays_backward(st.cfg, st.rays, st.acc, st.wsum, st.acc_irr, st.irr_last,
                                                        g_rgb.contiguous())
+    if st.lazy:           # gradient rows come out in the MLP's row order directly
+        if g_packed is not None:
+            raise RuntimeError("lazy_packed render: there are no depth-ordered per-sample rows to take a gradient of")
+        gp = ops.composite_backward(st.z, st.packed_rows, st.noise, st.noise_std, st.irr, st.alpha, st.trans, st.weights,
+                                    g_acc, g_acc_irr, None if g_depth is None else g_depth.contiguous(), g_wsum,
+                                    None if g_weights is None else g_weights.contiguous(), None,
+                                    sort_idx=st.idx, n_stratified=st.s1)
+        ops.mlp_backward(model, st.packed_rows, gp, st.pitch, st.n, st.s, st.flags, g_params, st.ws)
+        return
     gp = ops.composite_backward(st.z, st.packed, st.noise, st.noise_std, st.irr, st.alpha, st.trans, st.weights,
                                 g_acc, g_acc_irr, None if g_depth is None else g_depth.contiguous(), g_wsum,
                                 None if g_weights is None else g_weights.contiguous(),

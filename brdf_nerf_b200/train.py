@@ -95,9 +95,11 @@ class Trainer:
     # one optimisation step; `batch` tensors must already live on the model's device
     def _step_impl(self, batch: RayBatch, draws, kw):
         model, args = self.model, self.args
+        # nothing below reads the depth-ordered per-sample rows unless a regulariser is on (normals: decided inside _forward)
+        hs_on = self.use_hard_surface and float(getattr(args, "hs_lambda", 0.0)) != 0.0
         outs, st = R._forward(model, args, batch.rays, draws, train=True, mode="train",
                               valid_depth=batch.valid_depth, target_depths=batch.target_depths,
-                              target_std=batch.target_std, **kw)
+                              target_std=batch.target_std, lazy_packed=not hs_on, **kw)
         use_depth = float(args.ds_lambda) > 0 and self.use_depth_loss
         loss, g_rgb, g_depth = loss_and_grads(args, outs, st, batch, use_depth)
         g_weights = g_packed = None

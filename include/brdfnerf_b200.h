@@ -83,6 +83,18 @@ int bn_sample_guided(const float* z1, const float* depth, const float* weights,
 int bn_merge_samples(const float* z1, const float* z2, float* z_out, int64_t* idx_out,
                      float* unsort_out, int n_rays, int n_samples, int n_guided, cudaStream_t stream);
 
+/* Everything between the two network passes of render_rays in ONE launch (rendering.py:262-273): compositing of the
+ * stratified densities (cal_weight, models/spsbrdfnerf.py:50-69 -> weights1 (N,S1), depth1 (N)), the depth-guided samples
+ * (bn_sample_guided -> z2 (N,G), std1 (N) optional) and the merge (bn_merge_samples -> z_out, idx_out, unsort_out (N,S1+G);
+ * the last two optional).  Arguments as in bn_composite_sigma / bn_sample_guided / bn_merge_samples; results bit-identical
+ * to calling the three. */
+int bn_coarse_to_fine(const float* z1, const float* sigma1, const float* noise1, float noise_std,
+                      const float* t_vals, const float* gauss_w, const float* u_pred, const float* near0, const float* far0,
+                      float d_range, const int64_t* valid_depth, const float* gt_depth, int gt_depth_stride,
+                      const float* gt_std, const float* u_gt, float* weights1, float* depth1, float* std1, float* z2,
+                      float* z_out, int64_t* idx_out, float* unsort_out, int n_rays, int n_samples, int n_guided,
+                      cudaStream_t stream);
+
 /* Applies sort_idx (rendering.py:271-273) to per-point rows of `pitch` floats.  The MLP may evaluate the
  * points of a call in generation order - all stratified samples ([N][S1] rows), then all guided samples
  * ([N][G] rows) - so that the stratified points' trunk is evaluated once for the density pass and the full
@@ -106,22 +118,27 @@ int bn_composite_sigma(const float* z, const float* sigma, const float* noise, f
  * 292,314-317,326-338).  packed (N,S,C) is the MLP's packed per-sample output in the reference's
  * channel order [albedo(3), sigma, normal_an(3)?, normal_lr(3)?, brdf params...]; acc (N,C) receives
  * sum_s w*packed (channel 3 is meaningless), wsum (N) = sum_s w.  irr (N,S) optional per-sample
- * irradiance scalar (sun visibility) -> acc_irr (N,3) = sum_s w*irr*albedo. */
+ * irradiance scalar (sun visibility) -> acc_irr (N,3) = sum_s w*irr*albedo.
+ * sort_idx (N,S) int64, optional: `packed` is then in the MLP's generation order (all stratified samples [N][n_stratified]
+ * rows, then all guided samples [N][S - n_stratified] rows, see bn_permute_samples) and sample s of ray r is read from the
+ * row sort_idx[r][s] points at (rendering.py:271-273 applied on load instead of by a separate pass). */
 int bn_composite_forward(const float* z, const float* packed, int n_channels, int sigma_channel,
                          const float* noise, float noise_std, const float* irr,
                          float* alpha, float* trans, float* weights,
                          float* depth, float* wsum, float* acc, float* acc_irr,
-                         int n_rays, int n_samples, cudaStream_t stream);
+                         int n_rays, int n_samples, const int64_t* sort_idx, int n_stratified, cudaStream_t stream);
 
 /* backward of bn_composite_forward: given grads w.r.t. acc / acc_irr / depth / wsum (per ray),
  * weights (per sample, optional) and optionally direct grads w.r.t. packed, writes g_packed
- * (N,S,C) (channel 3 = d loss / d sigma). */
+ * (N,S,C) (channel 3 = d loss / d sigma).  With sort_idx (as in bn_composite_forward) packed is read from, and g_packed
+ * written to, the MLP's row order; g_packed_direct stays in depth order. */
 int bn_composite_backward(const float* z, const float* packed, int n_channels, int sigma_channel,
                           const float* noise, float noise_std, const float* irr,
                           const float* alpha, const float* trans, const float* weights,
                           const float* g_acc, const float* g_acc_irr, const float* g_depth,
                           const float* g_wsum, const float* g_weights, const float* g_packed_direct,
-                          float* g_packed, int n_rays, int n_samples, cudaStream_t stream);
+                          float* g_packed, int n_rays, int n_samples, const int64_t* sort_idx, int n_stratified,
+                          cudaStream_t stream);
 
 /* ------------------------------------------------------------------ K-C  shading / BRDF */
 

@@ -69,6 +69,32 @@ def test_composite_forward_backward(cuda, n, s, c, noise_std, with_irr):
     assert err <= 2e-5 * max(1.0, scale), f"composite backward max err {err} (scale {scale})"
 
 
+@pytest.mark.parametrize("n,s1,g,c", [(64, 64, 64, 4), (33, 64, 64, 7), (17, 48, 80, 4), (5, 64, 64, 16)])
+def test_composite_through_sort_index(cuda, n, s1, g, c):
+    """sort_idx folded into the compositing kernels (the Trainer's lazy_packed path): reading the MLP's generation-order rows
+    through the index == compositing the rows bn_permute_samples has put into depth order, bit for bit, forward and backward
+    (whose gradient rows come out in generation order)."""
+    s = s1 + g
+    gen = torch.Generator().manual_seed(31 + n)
+    z, packed, noise = _inputs(n, s, c, 5)
+    rows = packed.reshape(n * s, c).to(cuda)                     # any content: row order = [N][S1] block, then [N][G] block
+    idx = torch.stack([torch.randperm(s, generator=gen) for _ in range(n)]).to(cuda)
+    z, noise = z.to(cuda), noise.to(cuda)
+    sorted_rows = ops.permute_samples(rows, idx, n, s1, g, c, scatter=False)
+    ref = ops.composite_forward(z, sorted_rows, noise, 0.1)
+    got = ops.composite_forward(z, rows, noise, 0.1, sort_idx=idx, n_stratified=s1)
+    for a, b in zip(ref, got):
+        assert (a is None and b is None) or torch.equal(a, b)
+    alpha, trans, w = ref[0], ref[1], ref[2]
+    g_acc = torch.randn(n, c, generator=gen).to(cuda)
+    g_depth, g_wsum = torch.randn(n, generator=gen).to(cuda), torch.randn(n, generator=gen).to(cuda)
+    g_w = torch.randn(n, s, generator=gen).to(cuda)
+    gs = ops.composite_backward(z, sorted_rows, noise, 0.1, None, alpha, trans, w, g_acc, None, g_depth, g_wsum, g_w, None)
+    gr = ops.composite_backward(z, rows, noise, 0.1, None, alpha, trans, w, g_acc, None, g_depth, g_wsum, g_w, None,
+                                sort_idx=idx, n_stratified=s1)
+    assert torch.equal(gr, ops.permute_samples(gs, idx, n, s1, g, c, scatter=True))
+
+
 @pytest.mark.parametrize("n", [1, 3, 4, 1023, 4096 * 33 + 5])
 def test_device_nan_counter(cuda, n):
     """bn_count_nan == torch.isnan(x).sum() (train_utils.check_nan, train_utils.py:61-78), accumulated without a host sync;

@@ -75,6 +75,30 @@ def test_guided_and_merge_bit_exact(cuda, n, s, with_gt, zero_std):
         assert np.abs(z2n[v] - gt[:, None]).max() <= 1e-6
 
 
+@pytest.mark.parametrize("n,s,with_gt,noise_std", [(1024, 64, True, 0.0), (257, 64, False, 0.0), (300, 64, True, 1.0),
+                                                   (19, 48, True, 0.0), (5, 128, False, 0.0)])
+def test_coarse_to_fine_equals_the_three_launches(cuda, n, s, with_gt, noise_std):
+    """bn_coarse_to_fine (compositing of the stratified densities + guided samples + merge in one launch, the path render_rays
+    takes) == bn_composite_sigma -> bn_sample_guided -> bn_merge_samples, bit for bit, on every output."""
+    b, u, z1, _, _ = _pass1_like(n, s, seed=200 + n)
+    g = torch.Generator().manual_seed(11)
+    sigma = (torch.rand(n, s, generator=g) * 8.0 * (torch.rand(n, s, generator=g) > 0.5)).to(cuda)
+    noise = torch.randn(n, s, generator=g).to(cuda)
+    u_pred, u_gt = torch.rand(n, s, generator=g).to(cuda), torch.rand(n, s, generator=g).to(cuda)
+    rays = b.rays.to(cuda)
+    tv, gv = ops.sampler_tables(s, 3.0, cuda)
+    z1c = torch.from_numpy(z1).to(cuda)
+    kw = dict(valid_depth=b.valid_depth.to(cuda) if with_gt else None, gt_depth=b.target_depths.to(cuda) if with_gt else None,
+              gt_depth_stride=2, gt_std=b.target_std.to(cuda) if with_gt else None, u_gt=u_gt if with_gt else None, want_std=True)
+    _, _, w1, d1, _ = ops.composite_sigma(z1c, sigma, noise, noise_std)
+    z2, std = ops.sample_guided(z1c, d1, w1, tv, gv, u_pred, rays[0:1, 6], rays[0:1, 7], 3.0, **kw)
+    z, idx, unsort = ops.merge_samples(z1c, z2)
+    f = ops.coarse_to_fine(z1c, sigma, noise, noise_std, tv, gv, u_pred, rays[0:1, 6], rays[0:1, 7], 3.0, **kw)
+    for name, a, c in zip(("weights", "depth", "std", "z2", "z", "idx", "unsort"), f, (w1, d1, std, z2, z, idx, unsort)):
+        assert torch.equal(a, c), name
+    assert bool(torch.isfinite(f[4]).all()) and bool((f[4][:, 1:] >= f[4][:, :-1]).all())
+
+
 def test_sort_rows(cuda):
     x = torch.rand(77, 64, generator=torch.Generator().manual_seed(1))
     out = ops.sort_rows(x.to(cuda)).cpu()

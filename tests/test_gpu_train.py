@@ -358,3 +358,33 @@ def test_train_loop_checkpoint_restores_schedule_and_feed(cuda):
     got = [loop2.feed.next_batch().rays.clone() for _ in range(10)]
     assert all(torch.equal(a, b) for a, b in zip(want, got))
     assert ckpt["epoch"] == 1 and abs(loop2.schedule.next().lr - args.lr * 0.9) < 1e-12
+
+
+def test_lazy_packed_step_equals_materialised_rows(cuda):
+    """The Trainer's Lambertian step never materialises the depth-ordered per-sample rows (lazy_packed: compositing gathers the
+    MLP's rows through sort_idx, its backward scatters the gradient rows): same loss bit for bit, same gradients up to the
+    order of the weight-gradient atomics, as the step with bn_permute_samples in both directions."""
+    from brdf_nerf_b200 import rendering as R
+    args = named_config("lambertian_ds")
+    batch = make_rays(256, depth_supervision=True).to(cuda)
+    out = {}
+    for lazy in (True, False):
+        torch.manual_seed(0)
+        model = load_model(args, precision="bf16").to(cuda)
+        model.sync_weights()
+        od = RT.Draws.make(256, 64, 64, 128, seed=3, with_gt=True)
+        from brdf_nerf_b200.rendering import Draws
+        d = Draws(u_strat=od.u_strat, u_pred=od.u_pred, u_gt=od.u_gt).to(cuda)
+        outs, st = R._forward(model, args, batch.rays, d, train=True, mode="train", valid_depth=batch.valid_depth,
+                              target_depths=batch.target_depths, target_std=batch.target_std, apply_brdf=False,
+                              bTestNormal=False, bTestSun_v=False, gsam_only=False, apply_theta=False, cos_irra_on=False,
+                              lazy_packed=lazy)
+        assert (outs["packed"] is None) == lazy
+        g_rgb = (outs["rgb"] - batch.rgbs) * (2.0 / outs["rgb"].numel())
+        grads = torch.zeros_like(model.flat_params)
+        R._backward(model, st, g_rgb, None, None, None, grads)
+        out[lazy] = (outs["rgb"].clone(), outs["depth"].clone(), grads)
+    assert torch.equal(out[True][0], out[False][0]) and torch.equal(out[True][1], out[False][1])
+    ga, gb = out[True][2], out[False][2]
+    assert (ga - gb).abs().max().item() <= 1e-5 * gb.abs().max().item() + 1e-9
+
