@@ -49,6 +49,7 @@ _SIGS = {
     "bn_sample_stratified": (C.c_int, [_P, _P, _I, _P, _P, _P, _I, _I, _P]),
     "bn_sample_guided": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _F, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _P]),
     "bn_merge_samples": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "bn_lambertian_render_loss": (C.c_int, [_P, _P, _P, _I, _P, _P, _P, _P, _I, _P, _F, _F, _I, _P, _P, _P, _P, _I, _I, _P]),
     "bn_coarse_to_fine": (C.c_int, [_P, _P, _P, _F, _P, _P, _P, _P, _P, _F, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                     _I, _I, _I, _P]),
     "bn_sort_rows": (C.c_int, [_P, _P, _I, _I, _P]),

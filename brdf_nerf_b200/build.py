@@ -20,7 +20,7 @@ COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler",
           "-diag-suppress", "177"]
 # per-file extra flags: the sample generator must round after every operation (bit-exact contract)
 EXTRA = {"sampler.cu": ["-fmad=false"], "dsm.cu": ["-fmad=false"], "georays.cu": ["-fmad=false"]}
-SOURCES = ["api.cu", "sampler.cu", "composite.cu", "coarse_to_fine.cu", "shade.cu", "loss.cu", "mlp.cu", "normals.cu", "tc_host.cu", "dsm.cu", "georays.cu", "ddp.cu"]
+SOURCES = ["api.cu", "sampler.cu", "composite.cu", "coarse_to_fine.cu", "render_loss.cu", "shade.cu", "loss.cu", "mlp.cu", "normals.cu", "tc_host.cu", "dsm.cu", "georays.cu", "ddp.cu"]
 
 
 def _digest() -> str:

@@ -282,6 +282,33 @@ def loss_color_depth(rgb, target_rgb, lambda_rgb, depth=None, z=None, weights=No
     return loss, g_rgb, g_depth
 
 
+def lambertian_render_loss(z, rows, sort_idx, n_stratified, target_rgb, lambda_rgb, valid_depth=None, target_depths=None,
+                           target_std=None, lambda_ds=0.0, use_all_depth=False, no_weights=False, want_outputs=False):
+    """Compositing + Lambertian colour + colour / depth loss + their backward in one launch (bn_lambertian_render_loss).
+    Returns (loss (1,), g_rows [N*S, 4], rgb (N,3) or None, depth (N) or None)."""
+    n, s = z.shape
+    dev = z.device
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    g_rows = torch.empty_like(rows)
+    rgb = torch.empty((n, 3), dtype=torch.float32, device=dev) if want_outputs else None
+    depth = torch.empty(n, dtype=torch.float32, device=dev) if want_outputs else None
+    use_ds = valid_depth is not None and float(lambda_ds) > 0
+    td = tw = None
+    stride = 1
+    if use_ds:
+        tdm = target_depths.contiguous().float()
+        stride = tdm.shape[1] if tdm.dim() == 2 else 1
+        td = tdm
+        tw = None if (no_weights or tdm.dim() != 2) else tdm[:, 1]
+        valid_depth = valid_depth.to(torch.int64).contiguous()
+    L.check(L.load().bn_lambertian_render_loss(
+        L.ptr(z), L.ptr(rows), L.ptr(sort_idx, torch.int64), int(n_stratified), L.ptr(target_rgb.contiguous()),
+        L.ptr(valid_depth, torch.int64) if use_ds else None, L.ptr(td), (C.c_void_p(tw.data_ptr()) if tw is not None else None),
+        stride, L.ptr(target_std.contiguous().float()) if use_ds else None, float(lambda_rgb), float(lambda_ds) if use_ds else 0.0,
+        int(bool(use_all_depth)), L.ptr(loss), L.ptr(g_rows), L.ptr(rgb), L.ptr(depth), n, s, L.stream_ptr()))
+    return loss, g_rows, rgb, depth
+
+
 def loss_regularizers(loss, weights, z, depth, packed, rays, normal_an_ch=-1, lambda_nr_an=0.0, normal_lr_ch=-1,
                       lambda_nr_lr=0.0, lambda_hs=0.0, g_depth=None, want_bad_count=False):
     """NormalRegLoss / HardSurfaceLoss (metrics.py:179-216, 263-290) fused with their gradients.  ADDS to `loss` (1,) and

@@ -89,10 +89,13 @@ def _call_brdf_type(model, args, apply_brdf: bool) -> int:
 def _forward(model, args, rays: torch.Tensor, draws: Optional[Draws], mode: str, valid_depth, target_depths,
              target_std, apply_brdf: bool, bTestNormal: bool, bTestSun_v: bool, gsam_only: bool, apply_theta: bool,
              cos_irra_on: bool, train: bool, debug_nan: bool = False, own_ws: bool = False, sync: bool = True,
-             reference_rng: bool = False, rays_t: Optional[torch.Tensor] = None, lazy_packed: bool = False):
+             reference_rng: bool = False, rays_t: Optional[torch.Tensor] = None, lazy_packed: bool = False,
+             defer_kc: bool = False):
     """`lazy_packed` (Trainer, plain Lambertian stage): nobody reads the depth-ordered per-sample rows, so they are never
     materialised — compositing gathers the MLP's rows through sort_idx and its backward scatters the gradients the same way
     (no bn_permute_samples launch in either direction); `outs["packed"]` is None then.
+    `defer_kc` (with lazy_packed, 128-sample rays, noise_std 0): compositing / shading are NOT run here; the caller finishes the
+    step with `_lambertian_loss_backward` (one launch for compositing + colour + loss + their backward); `outs["deferred"]`.
     `own_ws`: the MLP workspace is allocated for this call and owned by the returned state (autograd bridge: several
     forwards may be alive before their backwards run); otherwise the model's cached per-tag buffer is reused.
     `sync=False`: the caller (Trainer) has refreshed the packed weight copies itself.
@@ -288,6 +291,13 @@ def _forward(model, args, rays: torch.Tensor, draws: Optional[Draws], mode: str,
     else:
         cfg.irr_mode = L.BN_IRR_ONES
 
+    if lazy and defer_kc and S == 128 and pitch == 4 and noise_std == 0.0 and cfg.irr_mode == L.BN_IRR_ONES:
+        st = _State(n=N, s=S, pitch=pitch, flags=flags, cfg=cfg, rays=rays, z=z, packed=None, packed_rows=packed_rows, idx=idx,
+                    s1=S1, lazy=True, noise=None, noise_std=0.0, ws=ws, multi=False, normal_an=False)
+        outs = dict(deferred=True, packed=None, z=z, z_unsort=z_unsort, idx=idx, sun_res=sun_res, C=C, nr_an=False, nr_lr=False,
+                    has_beta=False, brdf_type=brdf_type,
+                    extras=dict(z1=z1, z2=z2, sigma1=sigma1, weights1=w1, depth1=depth1, nan_counts=nan_counts))
+        return outs, st
     aux_pts = None
     if multi:
         aux_pts = ops.brdf_points_forward(cfg, rays, packed, want_aux=not train)
@@ -309,6 +319,20 @@ def _forward(model, args, rays: torch.Tensor, draws: Optional[Draws], mode: str,
                 has_beta=has_beta,
                 brdf_type=brdf_type, extras=dict(z1=z1, z2=z2, sigma1=sigma1, weights1=w1, depth1=depth1, nan_counts=nan_counts))
     return outs, st
+
+
+def _lambertian_loss_backward(model, st: _State, args, target_rgb, valid_depth, target_depths, target_std, use_depth: bool,
+                              g_params: torch.Tensor, want_outputs: bool = False):
+    """Second half of a `defer_kc` forward: compositing + Lambertian colour + colour / depth loss + their backward in one launch
+    (bn_lambertian_render_loss), then the MLP backward.  Returns the loss (1,) [, rgb (N,3), depth (N)]."""
+    use_ds = use_depth and valid_depth is not None
+    loss, g_rows, rgb, depth = ops.lambertian_render_loss(
+        st.z, st.packed_rows, st.idx, st.s1, target_rgb, float(args.lambda_rgb), valid_depth=valid_depth if use_ds else None,
+        target_depths=target_depths, target_std=target_std, lambda_ds=float(args.ds_lambda) if use_ds else 0.0,
+        use_all_depth=bool(getattr(args, "usealldepth", False)), no_weights=bool(getattr(args, "ds_noweights", False)),
+        want_outputs=want_outputs)
+    ops.mlp_backward(model, st.packed_rows, g_rows, st.pitch, st.n, st.s, st.flags, g_params, st.ws)
+    return (loss, rgb, depth) if want_outputs else loss
 
 
 def _backward(model, st: _State, g_rgb, g_depth, g_weights, g_packed, g_params: torch.Tensor):

@@ -99,7 +99,14 @@ class Trainer:
         hs_on = self.use_hard_surface and float(getattr(args, "hs_lambda", 0.0)) != 0.0
         outs, st = R._forward(model, args, batch.rays, draws, train=True, mode="train",
                               valid_depth=batch.valid_depth, target_depths=batch.target_depths,
-                              target_std=batch.target_std, lazy_packed=not hs_on, **kw)
+                              target_std=batch.target_std, lazy_packed=not hs_on, defer_kc=not hs_on, **kw)
+        if outs.get("deferred"):          # plain Lambertian stage: compositing, colour, loss and their backward in one launch
+            grads = model.flat_grads
+            grads.zero_()
+            loss = R._lambertian_loss_backward(model, st, args, batch.rgbs, batch.valid_depth, batch.target_depths,
+                                               batch.target_std, float(args.ds_lambda) > 0 and self.use_depth_loss, grads)
+            self._mask_frozen(grads)
+            return loss
         use_depth = float(args.ds_lambda) > 0 and self.use_depth_loss
         loss, g_rgb, g_depth = loss_and_grads(args, outs, st, batch, use_depth)
         g_weights = g_packed = None

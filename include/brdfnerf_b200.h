@@ -140,6 +140,19 @@ int bn_composite_backward(const float* z, const float* packed, int n_channels, i
                           float* g_packed, int n_rays, int n_samples, const int64_t* sort_idx, int n_stratified,
                           cudaStream_t stream);
 
+/* K-C of the Lambertian training step in one launch, both directions (csrc/render_loss.cu): compositing of the 128-sample ray
+ * (cal_weight + weighted sums, models/spsbrdfnerf.py:50-69,196-199), Lambertian colour with rgb_padding (:281-283,459),
+ * SNerfLoss + DepthLoss(subset) (metrics.py:39-61,82-161) and the backward of all three down to g_rows, the gradient of every
+ * packed MLP row.  rows / g_rows: [N*128, 4] (albedo rgb, sigma) in the MLP's generation order when sort_idx is given (see
+ * bn_composite_forward), else in depth order.  Same arithmetic as bn_composite_forward -> bn_shade_rays_forward ->
+ * bn_loss_color_depth -> bn_shade_rays_backward -> bn_composite_backward; loss (1) is zeroed by the call; rgb (N,3) and depth (N)
+ * are optional per-ray outputs.  No normals, no BRDF, irradiance 1, noise_std 0, n_samples == 128. */
+int bn_lambertian_render_loss(const float* z, const float* rows, const int64_t* sort_idx, int n_stratified,
+                              const float* target_rgb, const int64_t* valid_depth, const float* target_depth,
+                              const float* target_weight, int td_stride, const float* target_std, float lambda_rgb,
+                              float lambda_ds, int use_all_depth, float* loss, float* g_rows, float* rgb, float* depth,
+                              int n_rays, int n_samples, cudaStream_t stream);
+
 /* ------------------------------------------------------------------ K-C  shading / BRDF */
 
 enum { BN_BRDF_NONE = 0, BN_BRDF_MICROFACET = 1, BN_BRDF_RPV = 2, BN_BRDF_HAPKE = 3 };

@@ -95,6 +95,45 @@ def test_composite_through_sort_index(cuda, n, s1, g, c):
     assert torch.equal(gr, ops.permute_samples(gs, idx, n, s1, g, c, scatter=True))
 
 
+@pytest.mark.parametrize("n,with_depth,use_all", [(256, True, False), (33, True, True), (64, False, False)])
+def test_lambertian_render_loss_equals_the_five_launches(cuda, n, with_depth, use_all):
+    """bn_lambertian_render_loss (the Trainer's Lambertian K-C: compositing + colour + loss + their backward in one launch, rows
+    gathered / scattered through sort_idx) against bn_permute_samples -> bn_composite_forward -> bn_shade_rays_forward ->
+    bn_loss_color_depth -> bn_shade_rays_backward -> bn_composite_backward -> bn_permute_samples."""
+    from brdf_nerf_b200 import _lib as L
+    s1 = g = 64
+    s, c = s1 + g, 4
+    gen = torch.Generator().manual_seed(77 + n)
+    z, packed, _ = _inputs(n, s, c, 9)
+    packed[..., 3] = packed[..., 3] * (torch.rand(n, s, generator=gen) > 0.3)           # some empty space
+    rows = packed.reshape(n * s, c).to(cuda)
+    idx = torch.stack([torch.randperm(s, generator=gen) for _ in range(n)]).to(cuda)
+    z = z.to(cuda)
+    target = torch.rand(n, 3, generator=gen).to(cuda)
+    valid = (torch.rand(n, generator=gen) < 0.7).to(torch.int64).to(cuda)
+    tdep = torch.stack([torch.rand(n, generator=gen) * 0.6, torch.rand(n, generator=gen)], -1).to(cuda)
+    tstd = (torch.rand(n, generator=gen) * 0.05).to(cuda)
+    rays = torch.zeros(n, 11, device=cuda)
+    kw = dict(valid_depth=valid if with_depth else None, target_depths=tdep, target_std=tstd,
+              lambda_ds=10.0 if with_depth else 0.0, use_all_depth=use_all)
+    # five launches (+ two permutations)
+    srt = ops.permute_samples(rows, idx, n, s1, g, c, scatter=False)
+    alpha, trans, w, depth, wsum, acc, _ = ops.composite_forward(z, srt, None, 0.0)
+    cfg = L.ShadeCfg()
+    cfg.n_channels, cfg.normal_ch, cfg.param_ch, cfg.brdf_ch = c, -1, -1, -1
+    cfg.brdf_type, cfg.irr_mode = L.BN_BRDF_NONE, L.BN_IRR_ONES
+    sh = ops.shade_rays_forward(cfg, rays, acc, wsum, None, None, want_normal=False, want_brdf=False)
+    loss, g_rgb, g_depth = ops.loss_color_depth(sh["rgb"], target, 1.0, depth=depth, z=z, weights=w, **kw)
+    g_acc, g_wsum, _ = ops.shade_rays_backward(cfg, rays, acc, wsum, None, None, g_rgb)
+    gs = ops.composite_backward(z, srt, None, 0.0, None, alpha, trans, w, g_acc, None, g_depth, g_wsum, None, None)
+    ref_rows = ops.permute_samples(gs, idx, n, s1, g, c, scatter=True)
+    # one launch
+    loss1, g_rows, rgb1, depth1 = ops.lambertian_render_loss(z, rows, idx, s1, target, 1.0, want_outputs=True, **kw)
+    assert torch.equal(rgb1, sh["rgb"]) and torch.equal(depth1, depth)
+    assert abs(loss1.item() - loss.item()) <= 1e-6 * abs(loss.item()) + 1e-9          # same terms, atomics in another order
+    assert torch.equal(g_rows, ref_rows)
+
+
 @pytest.mark.parametrize("n", [1, 3, 4, 1023, 4096 * 33 + 5])
 def test_device_nan_counter(cuda, n):
     """bn_count_nan == torch.isnan(x).sum() (train_utils.check_nan, train_utils.py:61-78), accumulated without a host sync;
