@@ -164,6 +164,13 @@ __device__ __forceinline__ void tma_load_2d_pair_hint(void* smem_dst, const CUte
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1), "l"(pol)
       : "memory");
 }
+// one lane of a converged warp (the warp stays converged around the elected block: descriptors and addresses are warp-uniform
+// values, which lets the compiler keep them in uniform registers instead of voting them over on every tcgen05 instruction)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(p));
+  return p != 0;
+}
 __device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
@@ -454,12 +461,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA of a pair only) =====================
-    if (lane == 0 && crank == 0) {
+    // LEAN issue loop (scripts/mma_rate.cu, profiles/r02q_mma_rate.txt): the loop runs on the WHOLE warp with uniform control flow
+    // and one elected lane issues; shared-memory descriptors are a base plus constant increments.  The first version ran on one
+    // lane and rebuilt both descriptors from the address for every instruction: ~40 scalar instructions (shifts, masks, R2UR, a
+    // vote loop around every tcgen05 instruction) between two MMAs = 186-224 cycles per 256x256x16 MMA against the pipe's 128.
+    if (crank == 0) {
       constexpr uint32_t idesc = make_idesc(kPair ? 256 : 128, BN, kNT);
+      constexpr uint32_t k_inc = (kNT ? 2048u : 32u) >> 4;             // descriptor address units (16 bytes) per K slice of 16
+      const uint64_t a_desc0 = kNT ? make_desc(smem_u32(sA), 8192, 1024) : make_desc(smem_u32(sA), 16, 1024);
+      const uint64_t b_desc0 = kNT ? make_desc(smem_u32(sB), 8192, 1024) : make_desc(smem_u32(sB), 16, 1024);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       [[maybe_unused]] constexpr uint32_t idesc_bias = make_idesc(kPair ? 256 : 128, 16, kNT);
-      [[maybe_unused]] const uint32_t ones_addr = smem_u32(sOnes);
+      [[maybe_unused]] const uint64_t ones_desc0 = make_desc(smem_u32(sOnes), 8192, 1024);
+      const bool tr1 = tr && lane == 0;
       for (int it = item0; it < n_items; it += item_step) {
         const int split = it / (m_groups * wk.n_tiles);
         const int kb0 = split * wk.kb_per_split;
@@ -474,42 +489,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t d_tmem = tmem_base + acc * BN;
         [[maybe_unused]] int rot = kb0 % wk.n_tiles;               // kb % n_tiles without a division per K block
         long long t_wait = 0;
-        if (tr) wk.trace[2] = clock64();
+        if (tr1) wk.trace[2] = clock64();
         for (int kb = kb0; kb < kb1; ++kb) {
           [[maybe_unused]] const bool bias_now = bias_on && rot == n_blk;
           if (++rot == wk.n_tiles) rot = 0;
-          const long long tw0 = tr ? clock64() : 0;
+          const long long tw0 = tr1 ? clock64() : 0;
           mbar_wait(&full[stage], phase);
-          if (tr) t_wait += clock64() - tw0;
+          if (tr1) t_wait += clock64() - tw0;
           fence_after_sync();
-          const uint32_t a_addr = smem_u32(sA + stage * A_BYTES);
-          const uint32_t b_addr = smem_u32(sB + stage * B_BYTES);
+          const uint64_t da0 = a_desc0 + (uint64_t)(stage * (int)(A_BYTES >> 4));
+          const uint64_t db0 = b_desc0 + (uint64_t)(stage * (int)(B_BYTES >> 4));
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            uint64_t da, db;
-            if (!kNT) {
-              da = make_desc(a_addr + k * 32, 16, 1024);
-              db = make_desc(b_addr + k * 32, 16, 1024);
-            } else {
-              da = make_desc(a_addr + k * 2048, 8192, 1024);
-              db = make_desc(b_addr + k * 2048, 8192, 1024);
-            }
-            if constexpr (kPair) umma_bf16_pair(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            else umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            if constexpr (kBias) {
-              if (bias_now) {     // D'[m][0..15] += sum_k A[k][m] * 1
-                const uint64_t dones = make_desc(ones_addr + k * 2048, 8192, 1024);
-                if constexpr (kPair) umma_bf16_pair(tmem_base + ACC * BN, da, dones, idesc_bias, bias_started ? 1u : 0u);
-                else umma_bf16(tmem_base + ACC * BN, da, dones, idesc_bias, bias_started ? 1u : 0u);
-                bias_started = true;
+            for (int k = 0; k < kBK / 16; ++k) {
+              const uint64_t da = da0 + k * k_inc, db = db0 + k * k_inc;
+              if constexpr (kPair) umma_bf16_pair(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              else umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              if constexpr (kBias) {
+                if (bias_now) {     // D'[m][0..15] += sum_k A[k][m] * 1
+                  const uint64_t dones = ones_desc0 + k * k_inc;
+                  if constexpr (kPair) umma_bf16_pair(tmem_base + ACC * BN, da, dones, idesc_bias, (bias_started || k > 0) ? 1u : 0u);
+                  else umma_bf16(tmem_base + ACC * BN, da, dones, idesc_bias, (bias_started || k > 0) ? 1u : 0u);
+                }
               }
             }
+            if constexpr (kPair) umma_commit_pair(&empty[stage]); else umma_commit(&empty[stage]);
           }
-          if constexpr (kPair) umma_commit_pair(&empty[stage]); else umma_commit(&empty[stage]);
+          __syncwarp();
+          if constexpr (kBias) { if (bias_now) bias_started = true; }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if constexpr (kPair) umma_commit_pair(&tfull[acc]); else umma_commit(&tfull[acc]);
-        if (tr) { wk.trace[3] = clock64(); wk.trace[4] = t_wait; wk.trace[5] = kb1 - kb0; }
+        if (elect_one()) { if constexpr (kPair) umma_commit_pair(&tfull[acc]); else umma_commit(&tfull[acc]); }
+        __syncwarp();
+        if (tr1) { wk.trace[3] = clock64(); wk.trace[4] = t_wait; wk.trace[5] = kb1 - kb0; }
         if (++acc == ACC) { acc = 0; acc_phase ^= 1; }
       }
     }

@@ -114,11 +114,17 @@ __device__ __forceinline__ void chain_producer(const CUtensorMap* wmap, const CU
 }
 
 // ---- MMA issuer (leader CTA): layer = two column halves x the layer's K blocks ----
+// Runs on the WHOLE warp (uniform control flow; one elected lane issues) with descriptors = base + constant increments: the lean
+// issue loop of gemm_tc.cuh — the one-lane version spent 195 cycles per 256 x 256 x 16 MMA on its own scalar instructions
+// against the pipe's 128 (scripts/mma_rate.cu).
 template <int STAGES>
 __device__ __forceinline__ void chain_mma(uint8_t* sAct, uint8_t* sW, uint64_t* wfull, uint64_t* wempty, uint64_t* tfull,
                                           uint64_t* tempty, uint64_t* act_ready, uint64_t* kfree, uint32_t tmem_base,
                                           int pair0, int npairs, int n_blocks, int L, int skip, long long* trace = nullptr) {
   constexpr uint32_t idesc = make_idesc(256, 256, false);
+  const uint64_t a_desc0 = make_desc(smem_u32(sAct), 16, 1024), b_desc0 = make_desc(smem_u32(sW), 16, 1024);
+  constexpr int kb_inc = kKBBytes >> 4;                 // descriptor address units per K block / weight stage
+  if ((threadIdx.x & 31) != 0) trace = nullptr;
   int stage = 0; uint32_t phase = 0;
   uint32_t te_ph[2] = {0, 0};
   uint32_t ar_ph = 0;                                   // bit kb: parity the next wait on act_ready[kb] expects
@@ -129,7 +135,6 @@ __device__ __forceinline__ void chain_mma(uint8_t* sAct, uint8_t* sW, uint64_t* 
         fence_after_sync();
         const bool tr = trace != nullptr && blk == pair0 && pair0 == 0;
         if (tr) trace[(l * 2 + n) * 16 + 0] = clock64();      // [0] TMEM half free
-        bool first = true;
         const int k_first0 = layer_reads_enc(l, skip) ? 0 : 3;   // K block 0: all of it, or only the slice with the constant 1
         long long t_act = 0, t_w = 0;                            // trace: cycles spent waiting for activations / weights
         for (int kb = 0; kb <= layer_kb_last(l); ++kb) {
@@ -146,26 +151,29 @@ __device__ __forceinline__ void chain_mma(uint8_t* sAct, uint8_t* sW, uint64_t* 
             if (tr) t_w += clock64() - t0;
           }
           fence_after_sync();
-          const uint32_t a_addr = smem_u32(sAct + kb * kKBBytes);
-          const uint32_t b_addr = smem_u32(sW + stage * kKBBytes);
+          const uint64_t da0 = a_desc0 + (uint64_t)(kb * kb_inc), db0 = b_desc0 + (uint64_t)(stage * kb_inc);
+          if (elect_one()) {
+            if (kb == 0 && k_first0 == 3) {
+              umma_bf16_pair(tmem_base + n * 256, da0 + 6, db0 + 6, idesc, 0u);       // slice 3 only: overwrites the accumulator
+            } else {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (kb == 0 && k < k_first0) continue;
-            umma_bf16_pair(tmem_base + n * 256, make_desc(a_addr + k * 32, 16, 1024), make_desc(b_addr + k * 32, 16, 1024),
-                           idesc, first ? 0u : 1u);
-            first = false;
+              for (int k = 0; k < 4; ++k)
+                umma_bf16_pair(tmem_base + n * 256, da0 + 2 * k, db0 + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit_pair(&wempty[stage]);
+            // K block kb (1..4) has now been read by both halves of this layer: the first half's epilogue may overwrite it
+            // (one barrier per K block, so that its units publish their results one by one while K blocks 5..8 are still
+            // being multiplied); a layer that reads no activation K block at all (layer 0) releases the four at once
+            if (n == 1) {
+              if (kb >= 1 && kb <= 4) umma_commit_pair(&kfree[kb - 1]);
+              else if (kb == 0 && layer_kb_last(l) == 0) { for (int j = 0; j < 4; ++j) umma_commit_pair(&kfree[j]); }
+            }
           }
-          umma_commit_pair(&wempty[stage]);
-          // K block kb (1..4) has now been read by both halves of this layer: the first half's epilogue may overwrite it
-          // (one barrier per K block, so that its units publish their results one by one while K blocks 5..8 are still
-          // being multiplied); a layer that reads no activation K block at all (layer 0) releases the four at once
-          if (n == 1) {
-            if (kb >= 1 && kb <= 4) umma_commit_pair(&kfree[kb - 1]);
-            else if (kb == 0 && layer_kb_last(l) == 0) { for (int j = 0; j < 4; ++j) umma_commit_pair(&kfree[j]); }
-          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit_pair(&tfull[n]);
+        if (elect_one()) umma_commit_pair(&tfull[n]);
+        __syncwarp();
         if (tr) {
           trace[(l * 2 + n) * 16 + 10] = clock64();           // [10] all MMAs of the half issued
           trace[(l * 2 + n) * 16 + 14] = t_act;               // [14] cycles the issuer waited for activation K blocks
@@ -247,7 +255,7 @@ __global__ void __launch_bounds__(kThreads, 1) sigma_chain_kernel(const __grid_c
   if (warp == 0) {
     if (lane == 0) chain_producer<kWStages>(prm.wmap, &prm.bmap, sW, wfull, wempty, crank, pair0, npairs, n_blocks, L, skip, prm.pol_w, prm.noload != 0);
   } else if (warp == 1) {
-    if (lane == 0 && crank == 0)
+    if (crank == 0)
       chain_mma<kWStages>(sAct, sW, wfull, wempty, tfull, tempty, act_ready, kfree, tmem_base, pair0, npairs, n_blocks, L, skip, prm.trace);
   } else if (warp >= 4) {
     // ===================== positional encoding + epilogues =====================
@@ -385,7 +393,7 @@ __global__ void __launch_bounds__(kThreads, 1) train_chain_kernel(const __grid_c
   if (warp == 0) {
     if (lane == 0) chain_producer<kWStages>(prm.wmap, &prm.bmap, sW, wfull, wempty, crank, pair0, npairs, n_blocks, L, skip, prm.pol_w);
   } else if (warp == 1) {
-    if (lane == 0 && crank == 0)
+    if (crank == 0)
       chain_mma<kWStages>(sAct, sW, wfull, wempty, tfull, tempty, act_ready, kfree, tmem_base, pair0, npairs, n_blocks, L, skip, prm.trace);
   } else if (warp >= 4) {
     const int q = warp & 3, hsel = (warp - 4) >> 2;

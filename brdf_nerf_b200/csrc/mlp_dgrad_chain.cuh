@@ -105,8 +105,11 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad_chain_kernel(const __grid_c
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA) =====================
-    if (lane == 0 && crank == 0) {
+    // lean issue loop (see chain_mma in mlp_chain.cuh): whole warp, one elected lane issues, descriptors = base + increments
+    if (crank == 0) {
       constexpr uint32_t idesc = make_idesc(256, 256, false);
+      const uint64_t a_desc0 = make_desc(smem_u32(sAct), 16, 1024), b_desc0 = make_desc(smem_u32(sW), 16, 1024);
+      constexpr int kb_inc = kKBBytes >> 4;
       int stage = 0; uint32_t phase = 0;
       uint32_t te_ph[2] = {0, 0};
       uint32_t ar_ph = 0, gi_ph = 0;
@@ -123,17 +126,19 @@ __global__ void __launch_bounds__(kThreads, 1) dgrad_chain_kernel(const __grid_c
               }
               mbar_wait(&wfull[stage], phase);
               fence_after_sync();
-              const uint32_t a_addr = smem_u32(sAct + kb * kKBBytes);
-              const uint32_t b_addr = smem_u32(sW + stage * kKBBytes);
+              const uint64_t da0 = a_desc0 + (uint64_t)(kb * kb_inc), db0 = b_desc0 + (uint64_t)(stage * kb_inc);
+              if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16_pair(tmem_base + n * 256, make_desc(a_addr + k * 32, 16, 1024), make_desc(b_addr + k * 32, 16, 1024),
-                               idesc, (kb > 0 || k > 0) ? 1u : 0u);
-              umma_commit_pair(&wempty[stage]);
-              if (n == 1 && kb < 4) umma_commit_pair(&kfree[kb]);     // K block kb may be overwritten by the first half's epilogue
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16_pair(tmem_base + n * 256, da0 + 2 * k, db0 + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                umma_commit_pair(&wempty[stage]);
+                if (n == 1 && kb < 4) umma_commit_pair(&kfree[kb]);     // K block kb may be overwritten by the first half's epilogue
+              }
+              __syncwarp();
               if (++stage == kDWStages) { stage = 0; phase ^= 1; }
             }
-            umma_commit_pair(&tfull[n]);
+            if (elect_one()) umma_commit_pair(&tfull[n]);
+            __syncwarp();
           }
         gi_ph ^= 1;
       }

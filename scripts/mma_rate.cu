@@ -17,6 +17,12 @@ constexpr int kStages = 4;
 constexpr int kStageBytes = 49152;      // A 16 KB + B up to 32 KB (single CTA, N = 256)
 
 // mode bit 0: MN-major operands (weight-gradient layout) instead of K-major; pair: cta_group::2 (M = 256) or ::1 (M = 128)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(p));
+  return p != 0;
+}
+
 template <bool kPair>
 __global__ void __launch_bounds__(384, 1) mma_rate_kernel(int n_kblocks, int N, int mn_major, int wait_slots, long long* out, int waiters, int fill, int variant) {
   extern __shared__ uint8_t smem_raw[];
@@ -44,7 +50,37 @@ __global__ void __launch_bounds__(384, 1) mma_rate_kernel(int n_kblocks, int N, 
   if (kPair) cluster_sync_all();
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  if (warp == 1 && lane == 0 && crank == 0 && !(variant & 4)) {
+  if ((variant & 32) && warp == 1 && crank == 0) {
+    // variant bit 5: LEAN issue loop.  The whole warp runs the loop (uniform control flow, descriptors are warp-uniform values
+    // the compiler can keep in uniform registers), one elected lane issues; descriptors are a base + constant increments
+    // instead of being rebuilt from the address for every instruction.
+    const uint32_t idesc = make_idesc(kPair ? 256 : 128, N, mn_major != 0);
+    const uint64_t a_base = mn_major ? make_desc(smem_u32(smem), 8192, 1024) : make_desc(smem_u32(smem), 16, 1024);
+    const uint64_t b_base = mn_major ? make_desc(smem_u32(smem) + 16384, 8192, 1024) : make_desc(smem_u32(smem) + 16384, 16, 1024);
+    const uint32_t k_inc = (mn_major ? 2048 : 32) >> 4, s_inc = kStageBytes >> 4;
+    int stage = 0; uint32_t phase = 0;
+    const long long t0 = clock64();
+    for (int kb = 0; kb < n_kblocks; ++kb) {
+      if (wait_slots && kb >= kStages) mbar_wait(&bars[stage], phase ^ 1);
+      const uint64_t da0 = a_base + (uint64_t)(stage * s_inc), db0 = b_base + (uint64_t)(stage * s_inc);
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if constexpr (kPair) umma_bf16_pair(tmem_base, da0 + k * k_inc, db0 + k * k_inc, idesc, (kb | k) ? 1u : 0u);
+          else umma_bf16(tmem_base, da0 + k * k_inc, db0 + k * k_inc, idesc, (kb | k) ? 1u : 0u);
+        }
+        if constexpr (kPair) umma_commit_pair(&bars[stage]); else umma_commit(&bars[stage]);
+      }
+      __syncwarp();
+      if (++stage == kStages) { stage = 0; phase ^= 1; }
+    }
+    const long long t1 = clock64();
+    if (elect_one()) { if constexpr (kPair) umma_commit_pair(&bars[kStages]); else umma_commit(&bars[kStages]); }
+    __syncwarp();
+    mbar_wait(&bars[kStages], 0);
+    const long long t2 = clock64();
+    if (blockIdx.x == 0 && lane == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+  } else if (warp == 1 && lane == 0 && crank == 0 && !(variant & 4)) {
     const uint32_t idesc = make_idesc(kPair ? 256 : 128, N, mn_major != 0);
     int stage = 0; uint32_t phase = 0;
     const long long t0 = clock64();
@@ -167,6 +203,10 @@ int main() {
   run<true>("pair, RANDOM operands, N = 128", n_sm, 128, 1, 1, 0, 1);
   run<true>("pair, random, TWO issuer threads / accumulators", n_sm, 256, 1, 1, 0, 1, 4);
   run<true>("pair, random, TWO issuers, N = 128", n_sm, 128, 1, 1, 0, 1, 4);
+  run<true>("pair, random, LEAN loop (elect, uniform descriptors)", n_sm, 256, 1, 1, 0, 1, 32);
+  run<true>("pair, random, LEAN loop, K-major", n_sm, 256, 0, 1, 0, 1, 32);
+  run<true>("pair, random, LEAN loop, N = 128", n_sm, 128, 1, 1, 0, 1, 32);
+  run<false>("single CTA, random, LEAN loop", n_sm, 256, 1, 1, 0, 1, 32);
   run<true>("pair, random, ONE issuer, two accumulators in turn", n_sm, 256, 1, 1, 0, 1, 8);
   run<true>("pair, random, ONE issuer, two accumulators, K-major", n_sm, 256, 0, 1, 0, 1, 8);
   run<true>("pair, random, ONE issuer, two accumulators, N = 128", n_sm, 128, 1, 1, 0, 1, 8);
