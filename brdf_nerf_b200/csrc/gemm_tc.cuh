@@ -158,6 +158,16 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1)
       : "memory");
 }
+// multicast pair load (clusters of two CTA pairs): the box lands at the same CTA-relative offset of every CTA in `mask`, and
+// each destination's bytes are counted on the barrier at `bar_leader`'s offset in the destination's PAIR LEADER (`bar_leader` =
+// shared::cluster address of the issuing CTA's own pair leader's barrier, i.e. its own address with the peer bit cleared, which is
+// what CUTLASS's SM100_TMA_2SM_LOAD_MULTICAST passes)
+__device__ __forceinline__ void tma_load_2d_pair_mc(void* smem_dst, const CUtensorMap* map, uint32_t bar_leader, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_leader), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_2d_pair_hint(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, uint64_t pol) {
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
@@ -181,6 +191,11 @@ __device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, 
 __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+// ... on the barrier at the same offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_pair_mask(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -329,11 +344,16 @@ template <int BN, bool kPair, class Epi> __host__ __device__ constexpr int smem_
   return pick_stages<BN, kPair, Epi>() * stage_bytes<BN, kPair>() + epi_smem<Epi>() + 512 + 1024;
 }
 
-template <int BN, int STAGES, bool kNT, bool kPair, class Epi>
+// kMC (NT pair kernels only): clusters of FOUR CTAs = two pairs that work on the same column tile and K range of two adjacent
+// 256-row groups.  They need the same B tile: each CTA loads ONE of the two 64-column boxes of its half and multicasts it to its
+// counterpart in the other pair, so the B operand crosses the L2 -> SM fabric once per cluster instead of once per pair (the
+// weight-gradient GEMM moves 537 MB per launch through L2 and is bound by exactly that once the issue loop is lean).
+template <int BN, int STAGES, bool kNT, bool kPair, class Epi, bool kMC = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Work wk,
                const __grid_constant__ Epi epi) {
-  constexpr int CL = kPair ? 2 : 1;
+  static_assert(!kMC || (kNT && kPair && BN == 256), "multicast variant: weight-gradient pair kernel with 256-column tiles");
+  constexpr int CL = kMC ? 4 : (kPair ? 2 : 1);
   constexpr int BNL = kPair ? BN / 2 : BN;                     // B rows (output columns) staged by this CTA
   constexpr uint32_t A_BYTES = kBM * kBK * 2;
   constexpr uint32_t B_BYTES = BNL * kBK * 2;
@@ -371,7 +391,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (!kNT && wk.reverse) return (m_groups - 1 - t / wk.n_tiles) * wk.n_tiles + t % wk.n_tiles;
     return t;
   };
-  const int crank = kPair ? (int)cluster_ctarank() : 0;
+  const int crank = kPair ? (int)cluster_ctarank() : 0;          // rank in the cluster (0..CL-1) = 128-row tile of the row group
+  [[maybe_unused]] const int prank = crank & 1;                   // rank in the CTA pair
+  [[maybe_unused]] const int lead = crank & ~1;                   // cluster rank of this pair's leader
+  [[maybe_unused]] const uint16_t pair_mask = (uint16_t)(3u << lead);
   const int item0 = kPair ? (int)cluster_id_x() : (int)blockIdx.x;
   const int item_step = kPair ? (int)cluster_nctaid_x() : (int)gridDim.x;
 
@@ -380,9 +403,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    // empty: one commit per pair that reads what lands in this CTA's slot (kMC: both pairs write into each other's slots)
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kMC ? 2 : 1); }
     // tempty: one arrival per epilogue warp; in a pair the leader's barrier collects both CTAs' warps
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8 * CL); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], kPair ? 16 : 8); }
     for (int s = 0; s < 8; ++s) mbar_init(&ibar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -407,7 +431,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int split = it / (m_groups * wk.n_tiles);
         const int t = item_tile(it);
         const int m_blk = (t / wk.n_tiles) * CL + crank, n_blk = t % wk.n_tiles;
-        const int ncol0 = n_blk * BN + crank * BNL;              // first B row / output column staged by this CTA
+        const int ncol0 = n_blk * BN + prank * BNL;              // first B row / output column staged by this CTA
         const int kb0 = split * wk.kb_per_split;
         const int kb1 = min(wk.kb_total, kb0 + wk.kb_per_split);
         [[maybe_unused]] auto prefetch_kb = [&](int kp) {
@@ -430,9 +454,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint8_t* b = sB + stage * B_BYTES;
           if constexpr (kPair) {
             // the leader's barrier expects the bytes of both CTAs; the peer only issues its loads
-            if (crank == 0) mbar_expect_tx(&full[stage], 2 * (A_BYTES + B_BYTES));
-            const uint32_t bar = mapa_u32(smem_u32(&full[stage]), 0);
-            if (!kNT) {                      // A: activations streaming through once; B: weights, re-read by every row tile
+            if (prank == 0) mbar_expect_tx(&full[stage], 2 * (A_BYTES + B_BYTES));
+            const uint32_t bar = mapa_u32(smem_u32(&full[stage]), lead);
+            if constexpr (kMC) {
+#pragma unroll
+              for (int c = 0; c < kBM / 64; ++c) tma_load_2d_pair(a + c * 8192, &tmA, bar, m_blk * kBM + c * 64, kb * kBK);
+              // this CTA's half of B is two 64-column boxes: pair 0 loads the first, pair 1 the second, each for both pairs
+              const int c = crank >> 1;
+              tma_load_2d_pair_mc(b + c * 8192, &tmB, bar, ncol0 + c * 64, kb * kBK, (uint16_t)(5u << prank));
+            } else if (!kNT) {               // A: activations streaming through once; B: weights, re-read by every row tile
               tma_load_2d_pair_hint(a, &tmA, bar, kb * kBK, m_blk * kBM, wk.pol_a);
               tma_load_2d_pair_hint(b, &tmB, bar, kb * kBK, ncol0, wk.pol_b);
             } else {
@@ -465,7 +495,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // and one elected lane issues; shared-memory descriptors are a base plus constant increments.  The first version ran on one
     // lane and rebuilt both descriptors from the address for every instruction: ~40 scalar instructions (shifts, masks, R2UR, a
     // vote loop around every tcgen05 instruction) between two MMAs = 186-224 cycles per 256x256x16 MMA against the pipe's 128.
-    if (crank == 0) {
+    if (prank == 0) {
       constexpr uint32_t idesc = make_idesc(kPair ? 256 : 128, BN, kNT);
       constexpr uint32_t k_inc = (kNT ? 2048u : 32u) >> 4;             // descriptor address units (16 bytes) per K slice of 16
       const uint64_t a_desc0 = kNT ? make_desc(smem_u32(sA), 8192, 1024) : make_desc(smem_u32(sA), 16, 1024);
@@ -513,13 +543,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
               }
             }
-            if constexpr (kPair) umma_commit_pair(&empty[stage]); else umma_commit(&empty[stage]);
+            if constexpr (kMC) umma_commit_pair_mask(&empty[stage], (uint16_t)0xF);       // both pairs' producers write this slot
+            else if constexpr (kPair) umma_commit_pair(&empty[stage]);
+            else umma_commit(&empty[stage]);
           }
           __syncwarp();
           if constexpr (kBias) { if (bias_now) bias_started = true; }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if (elect_one()) { if constexpr (kPair) umma_commit_pair(&tfull[acc]); else umma_commit(&tfull[acc]); }
+        if (elect_one()) { if constexpr (kPair) umma_commit_pair_mask(&tfull[acc], pair_mask); else umma_commit(&tfull[acc]); }
         __syncwarp();
         if (tr1) { wk.trace[3] = clock64(); wk.trace[4] = t_wait; wk.trace[5] = kb1 - kb0; }
         if (++acc == ACC) { acc = 0; acc_phase ^= 1; }
@@ -537,7 +569,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       fence_before_sync();
       __syncwarp();
       if (lane == 0) {
-        if constexpr (kPair) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[a]), 0));
+        if constexpr (kPair) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[a]), lead));
         else mbar_arrive(&tempty[a]);
       }
     };
@@ -784,6 +816,33 @@ int launch_nt(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* B, lon
   int splits = max(1, min(slots_avail, ceil_div(wk.kb_total, 8)));
   wk.kb_per_split = ceil_div(wk.kb_total, splits);
   wk.splits = ceil_div(wk.kb_total, wk.kb_per_split);
+  if constexpr (BN == 256) {
+    // clusters of two pairs with the B tile multicast between them (kMC): BN_NT_MC=1, read per call (A/B knob)
+    if (pair && wk.m_tiles % 4 == 0 && getenv("BN_NT_MC") != nullptr) {
+      auto kern = gemm_tc_kernel<BN, pick_stages<BN, true, Epi>(), true, true, Epi, true>;
+      constexpr int smem = smem_bytes<BN, true, Epi>();
+      static int max_clusters = -1;                  // resident 4-CTA clusters of this kernel (GPC granularity: fewer than SMs / 4)
+      if (max_clusters < 0) {
+        BN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(num_sms / 4 * 4); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 4; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        int nc = 0;
+        BN_CUDA(cudaOccupancyMaxActiveClusters(&nc, kern, &cfg));
+        max_clusters = nc;
+      }
+      const int cluster_tiles = (wk.m_tiles / 4) * wk.n_tiles;
+      if (max_clusters >= cluster_tiles) {
+        splits = max(1, min(max_clusters / cluster_tiles, ceil_div(wk.kb_total, 8)));
+        wk.kb_per_split = ceil_div(wk.kb_total, splits);
+        wk.splits = ceil_div(wk.kb_total, wk.kb_per_split);
+        return launch_kernel<4>(kern, smem, 4 * max_clusters, cluster_tiles * wk.splits, ma, mb, wk, epi, s, "gemm_tc_kernel<nt,pair,mc>");
+      }
+    }
+  }
   if constexpr (BN >= 128) {
     if (pair)
       return launch_kernel<2>(gemm_tc_kernel<BN, pick_stages<BN, true, Epi>(), true, true, Epi>, smem_bytes<BN, true, Epi>(), num_sms,

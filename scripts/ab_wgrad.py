@@ -34,9 +34,10 @@ def main():
         tr.step(batch)
     torch.cuda.synchronize()
     for rep in range(3):
-        for d, env in (("base", {}), ("no chain sigma", {"BN_CHAIN_NO_SIG": "1"}), ("prefetch 8", {"BN_NT_PREFETCH": "8"}),
-                       ("prefetch 16", {"BN_NT_PREFETCH": "16"})):
-            for k in ("BN_NT_PREFETCH", "BN_NT_EXP", "BN_CHAIN_NO_SIG"):
+        for d, env in (("base", {}), ("prefetch 4", {"BN_NT_PREFETCH": "4"}), ("prefetch 8", {"BN_NT_PREFETCH": "8"}),
+                       ("prefetch 16", {"BN_NT_PREFETCH": "16"}), ("B multicast (4-CTA)", {"BN_NT_MC": "1"}),
+                       ("multicast + prefetch 8", {"BN_NT_MC": "1", "BN_NT_PREFETCH": "8"})):
+            for k in ("BN_NT_PREFETCH", "BN_NT_EXP", "BN_CHAIN_NO_SIG", "BN_NT_MC"):
                 os.environ.pop(k, None)
             os.environ.update(env)
             tr.step(batch)
@@ -51,7 +52,7 @@ def main():
             print(f"{d:>18s} rep {rep}: wgrad (nt) {1e3 * tms[1] / 3:7.1f} us/step in {cnt[1] / 3:.0f} launches  "
                   f"{work[1] / max(tms[1], 1e-9) / 1e9:7.1f} TFLOP/s | tn {1e3 * tms[0] / 3:6.1f} us/step in {cnt[0] / 3:.0f} | "
                   f"chain {1e3 * tms[2] / max(cnt[2], 1):6.1f} us | dgrad chain {1e3 * tms[3] / max(cnt[3], 1):6.1f} us", flush=True)
-    for k in ("BN_NT_PREFETCH", "BN_NT_EXP", "BN_CHAIN_NO_SIG"):
+    for k in ("BN_NT_PREFETCH", "BN_NT_EXP", "BN_CHAIN_NO_SIG", "BN_NT_MC"):
         os.environ.pop(k, None)
 
 

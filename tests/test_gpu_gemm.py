@@ -54,6 +54,20 @@ def test_nt_tcgen05_bf16(cuda, Mo, No, P):
     assert err < 2e-3 * max(1.0, ref.abs().max().item()), f"tcgen05 NT gemm max err {err}"
 
 
+@pytest.mark.parametrize("Mo,No,P", [(512, 512, 4096), (512, 576, 131072), (512, 512, 1000)])
+def test_nt_multicast_variant(cuda, monkeypatch, Mo, No, P):
+    """BN_NT_MC=1 (read per call): clusters of two CTA pairs, the B tile multicast between them (gemm_tc.cuh, kMC).  Off by default
+    (measured: no gain, the weight gradient is HBM-bound); kept correct."""
+    monkeypatch.setenv("BN_NT_MC", "1")
+    g = torch.Generator().manual_seed(Mo + No + P)
+    A = (torch.randn(P, Mo, generator=g) * 0.1).to(cuda).to(torch.bfloat16)
+    B = (torch.randn(P, No, generator=g) * 0.5).to(cuda).to(torch.bfloat16)
+    ref = A.float().t() @ B.float()
+    out = _gemm(1, L.BN_PREC_BF16, A, B, Mo, No, P)
+    err = (out - ref).abs().max().item()
+    assert err < 2e-3 * max(1.0, ref.abs().max().item()), f"tcgen05 NT gemm (multicast) max err {err}"
+
+
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (1000, 512, 576), (77, 256, 512)])
 def test_tn_simt_fp32(cuda, M, N, K):
     g = torch.Generator().manual_seed(3)
