@@ -31,8 +31,8 @@ import torch  # noqa: E402
 RAYS_PER_GPU = 1024
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel of the step, chain::train_chain_kernel at
 # P = 65536 points (two launches per step: stratified points, guided points), from the ncu --set full capture under profiles/
-NCU_CHAIN_DRAM_BYTES_PER_LAUNCH = 4.7e6 + 1024.3e6
-NCU_TRAFFIC_NOTE = ("ncu --set full (profiles/r02_ncu_full_chain_kernels.csv, P = 65536): 4.7 MB read + 1024.3 MB written per launch "
+NCU_CHAIN_DRAM_BYTES_PER_LAUNCH = 4.7e6 + 1026.3e6
+NCU_TRAFFIC_NOTE = ("ncu --set full (profiles/r03_ncu_full_tensor_kernels.csv, P = 65536): 4.7 MB read + 1026.3 MB written per launch "
                     "= the algorithmic 1.07 GB (h_l, c_l of 8 layers + encoding, bf16; nothing is read back; the weights stay in L2). "
                     "fused data-gradient chain (dgrad_chain_kernel, P = 131072, same capture): 1079 MB read + 889 MB written vs "
                     "1073 + 939 MB algorithmic (c_l of 7 layers + dZ_7 in, dZ_l of 7 layers out; the tail of the writes is still in L2); "
