@@ -76,6 +76,17 @@ def test_transverse_mercator_against_independent_checks():
     assert south[0] < 0                                                     # "+zone=17R" has no +south: no false northing
 
 
+def test_utm_published_worked_example():
+    """Known-answer anchor for the restated (unpinned) projection: the worked example of the UTM article most readers know —
+    the CN Tower, 43 deg 38' 33.24" N, 79 deg 23' 13.7" W, lies in zone 17 at 630 084 m east, 4 833 438 m north (WGS84 / GRS80
+    differ by 0.1 mm in the semi-minor axis: invisible at the metre the example is quoted to)."""
+    lat = 43 + 38 / 60 + 33.24 / 3600
+    lon = -(79 + 23 / 60 + 13.7 / 3600)
+    assert G.utm_zone_number(lat, lon) == 17
+    e, n = G.utm_forward(np.array([lat]), np.array([lon]), 17)
+    assert abs(e[0] - 630084.0) < 1.0 and abs(n[0] - 4833438.0) < 1.0
+
+
 def test_product_host_logic_matches_oracle():
     rpc_o = G.synthetic_rpc(1)
     d = {k: getattr(rpc_o, k) for k in PG._KEYS + PG._POLYS}
