@@ -772,7 +772,6 @@ static int sigma_chain(bn_mlp* h, const float* params, const float* origins, int
   prm.L = h->L; prm.skip = h->skip; prm.n_freq = c.n_freq_xyz;
   prm.trace = h->chain_trace;
   prm.pol_w = tc::pol_weights(); prm.pol_s = tc::pol_stream();
-  prm.noload = getenv("BN_CHAIN_NOLOAD") != nullptr;
   const int n_blocks = (int)ceil_div_ll(prm.P, 256);
   constexpr int smem = chain::sigma_chain_smem();
   BN_CUDA(cudaFuncSetAttribute(chain::sigma_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -53,7 +53,6 @@ struct SigmaChainParams {
   long long P;
   int o_stride, d_stride, S, L, skip, n_freq;
   uint64_t pol_w, pol_s;                // L2 eviction policies: weight tiles (resident), activation stores (streaming)
-  int noload;                           // timing experiment (BN_CHAIN_NOLOAD): the weight TMA loads are skipped, results are garbage
   long long* trace;                     // diagnostics (bn_debug_chain_trace): clock64() stamps of pair 0's leader CTA, first block
 };
 
@@ -94,21 +93,17 @@ __device__ __forceinline__ int layer_wcol(int l, int skip, int kb) { return (l =
 template <int STAGES>
 __device__ __forceinline__ void chain_producer(const CUtensorMap* wmap, const CUtensorMap* bmap, uint8_t* sW, uint64_t* wfull,
                                                uint64_t* wempty, int crank, int pair0, int npairs, int n_blocks, int L, int skip,
-                                               uint64_t pol_w, bool noload = false) {
+                                               uint64_t pol_w) {
   int stage = 0; uint32_t phase = 0;
   for (int blk = pair0; blk < n_blocks; blk += npairs)
     for (int l = 0; l < L; ++l)
       for (int n = 0; n < 2; ++n)
         for (int kb = 0; kb <= layer_kb_last(l); ++kb) {
           mbar_wait(&wempty[stage], phase ^ 1);
-          if (noload) {                                  // timing experiment: MMAs run on whatever the slot holds
-            if (crank == 0) mbar_expect_tx(&wfull[stage], 0);
-          } else {
-            if (crank == 0) mbar_expect_tx(&wfull[stage], 2 * kKBBytes);
-            const uint32_t bar = mapa_u32(smem_u32(&wfull[stage]), 0);
-            if (kb == 0) tma_load_2d_pair_hint(sW + stage * kKBBytes, bmap, bar, 0, l * kF + n * 256 + crank * 128, pol_w);
-            else tma_load_2d_pair_hint(sW + stage * kKBBytes, &wmap[l], bar, layer_wcol(l, skip, kb), n * 256 + crank * 128, pol_w);
-          }
+          if (crank == 0) mbar_expect_tx(&wfull[stage], 2 * kKBBytes);
+          const uint32_t bar = mapa_u32(smem_u32(&wfull[stage]), 0);
+          if (kb == 0) tma_load_2d_pair_hint(sW + stage * kKBBytes, bmap, bar, 0, l * kF + n * 256 + crank * 128, pol_w);
+          else tma_load_2d_pair_hint(sW + stage * kKBBytes, &wmap[l], bar, layer_wcol(l, skip, kb), n * 256 + crank * 128, pol_w);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
 }
@@ -253,7 +248,7 @@ __global__ void __launch_bounds__(kThreads, 1) sigma_chain_kernel(const __grid_c
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) chain_producer<kWStages>(prm.wmap, &prm.bmap, sW, wfull, wempty, crank, pair0, npairs, n_blocks, L, skip, prm.pol_w, prm.noload != 0);
+    if (lane == 0) chain_producer<kWStages>(prm.wmap, &prm.bmap, sW, wfull, wempty, crank, pair0, npairs, n_blocks, L, skip, prm.pol_w);
   } else if (warp == 1) {
     if (crank == 0)
       chain_mma<kWStages>(sAct, sW, wfull, wempty, tfull, tempty, act_ready, kfree, tmem_base, pair0, npairs, n_blocks, L, skip, prm.trace);
